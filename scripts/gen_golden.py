@@ -1,0 +1,203 @@
+#!/usr/bin/env python
+"""Generate tests/golden/* by running the UNMODIFIED reference Python (/root/reference) in the build
+container, with the ``rvo2`` stand-in from oracle/refshim (the real rvo2 is not installable here).
+
+Everything first-party on the hot path (CrowdSim.reset/step/onestep_lookahead, SARL.predict, rotate,
+compute_reward, build_action_space, ValueNetwork.forward) is executed by the reference's own code; the
+fixtures therefore pin the oracle's restatement of that code.  ORCA velocities inside the fixtures come
+from the oracle's rvo2 restatement (parity unpinned for that third-party piece, see crowdnav_oracle.h).
+
+Usage:  python scripts/gen_golden.py [--episodes]   (the --episodes pass runs 500 full episodes, minutes)
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import oracle  # noqa: E402
+import oracle.refshim as refshim  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+INFO_CODE = {"Nothing": 0, "Danger": 1, "ReachGoal": 2, "Collision": 3, "Timeout": 4}
+
+
+def agents_of(env):
+    rows = []
+    for a in [env.robot] + env.humans:
+        rows.append([a.px, a.py, a.vx, a.vy, a.gx, a.gy, a.radius, a.v_pref])
+    return np.array(rows, dtype=np.float64)
+
+
+def run_trajectory(env, robot, policy, phase, case, max_steps=None):
+    """Teacher-forced record of one episode driven exactly like explorer.py:53-69."""
+    ob = env.reset(phase, case)
+    rec = dict(agents=[], time=[], human_v=[], values=[], best=[], reward=[], done=[], info=[], dmin=[],
+               action=[])
+    done = False
+    steps = 0
+    table = None
+    while not done and (max_steps is None or steps < max_steps):
+        rec["agents"].append(agents_of(env))
+        rec["time"].append(env.global_time)
+        action = robot.act(ob)
+        if table is None:
+            table = np.array([[a.vx, a.vy] for a in policy.action_space])
+        vals = np.array(policy.action_values, dtype=np.float64)
+        rec["values"].append(vals)
+        best = int(np.argmin(np.abs(table[:, 0] - action.vx) + np.abs(table[:, 1] - action.vy)))
+        rec["best"].append(best)
+        rec["action"].append([action.vx, action.vy])
+        before = agents_of(env)
+        ob, reward, done, info = env.step(action)
+        after = agents_of(env)
+        rec["human_v"].append(after[1:, 2:4].copy())  # ORCA velocities applied this step
+        rec["reward"].append(reward)
+        rec["done"].append(done)
+        rec["info"].append(INFO_CODE[type(info).__name__])
+        rec["dmin"].append(getattr(info, "min_dist", np.inf))
+        assert np.array_equal(before[:, 4:], after[:, 4:])
+        steps += 1
+    out = {k: np.array(v) for k, v in rec.items()}
+    out["table"] = table
+    return out
+
+
+def gen_units():
+    refshim.install()
+    import torch
+    from crowd_sim.envs.utils.utils import point_to_segment_dist
+    from crowd_sim.envs.utils.state import FullState, ObservableState
+    env, robot, policy = refshim.make_env_and_sarl(seed=0)
+    policy.time_step = 0.25                               # set by CrowdSim.reset (crowd_sim.py:307-309)
+    rs = np.random.RandomState(1234)
+    out = {}
+    # action space (cadrl.py:82-102)
+    policy.build_action_space(1.0)
+    out["action_space"] = np.array([[a.vx, a.vy] for a in policy.action_space])
+    out["gamma_bar"] = np.array(pow(policy.gamma, 0.25 * 1.0))
+    # weights of the reference ValueNetwork under torch.manual_seed(0)
+    sd = policy.get_model().state_dict()
+    out["weight_keys"] = np.array(list(sd.keys()))
+    flat = np.concatenate([v.numpy().ravel() for v in sd.values()]).astype(np.float32)
+    np.save(os.path.join(GOLD, "sarl_weights_seed0.npy"), flat)
+    assert np.array_equal(flat, oracle.default_sarl_weights(0)), "oracle weight init differs from reference"
+    # point_to_segment_dist (utils.py:4-26)
+    seg = rs.uniform(-3, 3, size=(256, 6))
+    seg[:8, 2:4] = seg[:8, 0:2]           # degenerate segments
+    seg[:, 4:] = 0
+    out["seg_in"] = seg
+    out["seg_out"] = np.array([point_to_segment_dist(*row) for row in seg])
+    # rotate (cadrl.py:217-252), torch float32
+    rows = rs.uniform(-5, 5, size=(512, 14)).astype(np.float32)
+    rows[:, 4] = 0.3; rows[:, 13] = 0.3; rows[:, 7] = 1.0
+    out["rotate_in"] = rows
+    out["rotate_out"] = policy.rotate(torch.from_numpy(rows)).numpy()
+    # compute_reward (multi_human_rl.py:65-88)
+    cr_in, cr_out = [], []
+    for i in range(256):
+        nav = FullState(*rs.uniform(-2, 2, 2), 0, 0, 0.3, *rs.uniform(-2, 2, 2), 1.0, 0)
+        if i % 16 == 0:
+            nav = FullState(nav.gx + 0.1, nav.gy, 0, 0, 0.3, nav.gx, nav.gy, 1.0, 0)
+        hs = [ObservableState(*(np.array([nav.px, nav.py]) + rs.uniform(-1.5, 1.5, 2)), 0, 0, 0.3) for _ in range(5)]
+        cr_in.append([nav.px, nav.py, nav.radius, nav.gx, nav.gy] + sum([[h.px, h.py, h.radius] for h in hs], []))
+        cr_out.append(policy.compute_reward(nav, hs))
+    out["reward_in"] = np.array(cr_in)
+    out["reward_out"] = np.array(cr_out, dtype=np.float64)
+    # ValueNetwork.forward (sarl.py:28-65) on rotated random joint states, H = 5 and 10
+    for H in (5, 10):
+        x = policy.rotate(torch.from_numpy(rs.uniform(-4, 4, size=(64 * H, 14)).astype(np.float32)))
+        x = x.reshape(64, H, 13)
+        with torch.no_grad():
+            v = policy.get_model()(x).numpy().ravel()
+        out["vnet_in_h%d" % H] = x.numpy()
+        out["vnet_out_h%d" % H] = v
+    np.savez_compressed(os.path.join(GOLD, "units.npz"), **out)
+    print("units.npz written;", len(out), "arrays")
+
+
+TRAJ_SPECS = [
+    # name, H, sim, query_env, robot_visible, [(phase, case, max_steps)]
+    ("circle5_qfalse", 5, "circle_crossing", False, False, [("test", 0, 40), ("test", 1, 40), ("test", 7, 40), ("train", 3, 40)]),
+    ("circle5_qtrue", 5, "circle_crossing", True, False, [("test", 2, 30), ("test", 499, 30)]),
+    ("circle5_visible", 5, "circle_crossing", False, True, [("test", 5, 30)]),
+    ("square10_qfalse", 10, "square_crossing", False, False, [("test", 0, 30), ("val", 11, 30)]),
+    ("square10_qtrue", 10, "square_crossing", True, False, [("test", 3, 20)]),
+]
+
+
+def gen_trajectories():
+    for name, H, sim, qenv, vis, cases in TRAJ_SPECS:
+        env, robot, policy = refshim.make_env_and_sarl(human_num=H, sim=sim, query_env=qenv, seed=0,
+                                                        robot_visible=vis)
+        out = {"H": np.array(H), "query_env": np.array(int(qenv)), "robot_visible": np.array(int(vis)),
+               "sim": np.array(sim)}
+        t0 = time.time()
+        for (phase, case, max_steps) in cases:
+            rec = run_trajectory(env, robot, policy, phase, case, max_steps)
+            key = "%s_%d" % (phase, case)
+            for k, v in rec.items():
+                out[key + "/" + k] = v
+            # scene pin: oracle generator == reference reset
+            scene = oracle.generate_scene(phase, case, human_num=H, rule=sim)
+            assert np.array_equal(scene, rec["agents"][0]), (name, key)
+        out["cases"] = np.array(["%s_%d" % (p, c) for p, c, _ in cases])
+        np.savez_compressed(os.path.join(GOLD, "traj_%s.npz" % name), **out)
+        print("traj_%s.npz written in %.1fs" % (name, time.time() - t0))
+
+
+def run_episode_chunk(args):
+    lo, hi, H, sim, qenv = args
+    import torch
+    torch.set_num_threads(1)
+    env, robot, policy = refshim.make_env_and_sarl(human_num=H, sim=sim, query_env=qenv, seed=0)
+    res = []
+    for case in range(lo, hi):
+        ob = env.reset("test", case)
+        done, steps, too_close, ret = False, 0, 0, 0.0
+        while not done:
+            action = robot.act(ob)
+            ob, reward, done, info = env.step(action)
+            ret += pow(0.9, steps * 0.25 * 1.0) * reward
+            steps += 1
+            too_close += type(info).__name__ == "Danger"
+        res.append((case, INFO_CODE[type(info).__name__], steps, too_close, env.global_time, ret))
+    return res
+
+
+def gen_episodes(n_proc):
+    """crowd_nav/test.py equivalent: 500 test cases, SARL (seed-0 random weights), circle_crossing, H=5."""
+    import multiprocessing as mp
+    chunks = [(lo, min(lo + 10, 500), 5, "circle_crossing", False) for lo in range(0, 500, 10)]
+    t0 = time.time()
+    with mp.get_context("fork").Pool(n_proc) as pool:
+        res = sum(pool.map(run_episode_chunk, chunks), [])
+    res = np.array(sorted(res), dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLD, "episodes_circle5_seed0.npz"), case=res[:, 0].astype(np.int32),
+                        info=res[:, 1].astype(np.int8), steps=res[:, 2].astype(np.int32),
+                        too_close=res[:, 3].astype(np.int32), end_time=res[:, 4], ret=res[:, 5])
+    k = len(res)
+    print("episodes: success %.3f collision %.3f timeout %.3f  steps %d  (%.0fs, %d procs)" % (
+        np.mean(res[:, 1] == 2), np.mean(res[:, 1] == 3), np.mean(res[:, 1] == 4), res[:, 2].sum(),
+        time.time() - t0, n_proc))
+    return k
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--episodes", action="store_true")
+    ap.add_argument("--procs", type=int, default=6)
+    ap.add_argument("--skip-units", action="store_true")
+    a = ap.parse_args()
+    assert refshim.available(), "/root/reference is required"
+    os.makedirs(GOLD, exist_ok=True)
+    oracle.build()
+    if a.episodes:
+        gen_episodes(a.procs)
+    else:
+        if not a.skip_units:
+            gen_units()
+        gen_trajectories()

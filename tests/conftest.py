@@ -1,0 +1,45 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle_mod():
+    import oracle
+    oracle.build()
+    return oracle
+
+
+@pytest.fixture(scope="session")
+def units():
+    return dict(np.load(os.path.join(GOLDEN, "units.npz"), allow_pickle=False))
+
+
+@pytest.fixture(scope="session")
+def weights0():
+    return np.load(os.path.join(GOLDEN, "sarl_weights_seed0.npy"))
+
+
+def load_traj(name):
+    z = np.load(os.path.join(GOLDEN, "traj_%s.npz" % name), allow_pickle=False)
+    out = {"H": int(z["H"]), "query_env": int(z["query_env"]), "robot_visible": int(z["robot_visible"]),
+           "sim": str(z["sim"]), "cases": {}}
+    for case in z["cases"]:
+        case = str(case)
+        out["cases"][case] = {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith(case + "/")}
+    return out
+
+
+TRAJ_NAMES = ["circle5_qfalse", "circle5_qtrue", "circle5_visible", "square10_qfalse", "square10_qtrue"]

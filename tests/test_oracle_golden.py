@@ -1,0 +1,97 @@
+"""Pin the C oracle against fixtures produced by the reference's own Python (scripts/gen_golden.py)."""
+import numpy as np
+import pytest
+
+from conftest import TRAJ_NAMES, load_traj
+
+
+def test_action_space_matches_reference(oracle_mod, units):
+    tab = oracle_mod.action_space(1.0, 5, 16)
+    assert tab.shape == (81, 2)
+    assert np.array_equal(tab, units["action_space"])          # bit-exact (f64)
+    # speeds and gamma_bar known answers
+    assert np.allclose(np.hypot(*tab[1:6].T), [0.12885, 0.28623, 0.47845, 0.71324, 1.0], atol=1e-5)
+    assert float(units["gamma_bar"]) == 0.9740037464252967
+
+
+def test_weight_init_matches_reference(oracle_mod, weights0):
+    assert weights0.size == 96502 == oracle_mod.sarl_param_count(oracle_mod.SarlCfg.default())
+    assert np.array_equal(oracle_mod.default_sarl_weights(0), weights0)
+
+
+def test_point_to_segment(oracle_mod, units):
+    got = np.array([oracle_mod.lib().orc_point_to_segment_dist(*map(float, r)) for r in units["seg_in"]])
+    assert np.array_equal(got, units["seg_out"])               # bit-exact (f64)
+
+
+def test_rotate(oracle_mod, units):
+    got = oracle_mod.rotate(units["rotate_in"])
+    # torch f32 atan2/cos/sin vs glibc: a few ulp on values up to ~15
+    assert np.max(np.abs(got - units["rotate_out"])) < 5e-6
+
+
+def test_compute_reward(oracle_mod, units):
+    rin = units["reward_in"]
+    got = np.array([oracle_mod.compute_reward(r[:5], r[5:].reshape(5, 3)) for r in rin])
+    assert np.array_equal(got, units["reward_out"])            # bit-exact (f64)
+    assert {-0.25, 1.0, 0.0} <= set(np.unique(got))            # every ladder rung exercised
+
+
+@pytest.mark.parametrize("H", [5, 10])
+def test_value_network(oracle_mod, units, weights0, H):
+    scfg = oracle_mod.SarlCfg.default()
+    x = units["vnet_in_h%d" % H]
+    got = np.array([oracle_mod.sarl_forward(scfg, weights0, xi) for xi in x])
+    ref = units["vnet_out_h%d" % H]
+    assert np.max(np.abs(got - ref)) <= 1e-5 * max(1.0, np.max(np.abs(ref)))
+
+
+@pytest.mark.parametrize("name", TRAJ_NAMES)
+def test_trajectories(oracle_mod, weights0, name):
+    """Teacher-forced, step by step: ORCA velocities, outcome ladder, state update, 81 values, argmax."""
+    o = oracle_mod
+    tr = load_traj(name)
+    H = tr["H"]
+    ecfg = o.EnvCfg.default(robot_visible=tr["robot_visible"])
+    scfg = o.SarlCfg.default()
+    n_steps = 0
+    for case, rec in tr["cases"].items():
+        table = rec["table"]
+        for t in range(len(rec["time"])):
+            agents = np.ascontiguousarray(rec["agents"][t])
+            gt = float(rec["time"][t])
+            hv = o.human_actions(ecfg, agents)
+            assert np.array_equal(hv, rec["human_v"][t]), (case, t)
+            best, values, reached = o.lookahead(ecfg, scfg, weights0, agents, gt, table, tr["query_env"], hv)
+            assert not reached
+            ref_v = rec["values"][t]
+            assert np.max(np.abs(values - ref_v)) <= 1e-5 * max(1.0, np.max(np.abs(ref_v))), (case, t)
+            top2 = np.sort(ref_v)[-2:]
+            if top2[1] - top2[0] > 1e-5:
+                assert best == int(rec["best"][t]), (case, t)
+            a = table[int(rec["best"][t])]
+            r, done, info, dmin = o.step_outcome(ecfg, agents, gt, a)
+            assert r == rec["reward"][t] and done == bool(rec["done"][t]) and info == int(rec["info"][t])
+            if info == o.DANGER:
+                assert dmin == rec["dmin"][t]
+            if t + 1 < len(rec["time"]):
+                nt = o.apply_step(ecfg, agents, gt, a, hv)
+                assert nt == rec["time"][t + 1]
+                assert np.array_equal(agents, rec["agents"][t + 1]), (case, t)
+            n_steps += 1
+    assert n_steps >= 20
+
+
+def test_scene_known_answers(oracle_mod):
+    """SURVEY §8(c) golden scenes captured from the reference's own reset()."""
+    s = oracle_mod.generate_scene("test", 0)
+    exp = [(-2.6625559084662678, -2.8379852903266491), (-3.6025107218593906, 0.15897818498977118),
+           (3.7670532713727254, 0.74515630301793467), (1.8871992410374889, -3.1111986546762234),
+           (-3.4340226851763447, 2.7512881890275414)]
+    assert np.array_equal(s[1:, :2], np.array(exp))
+    assert np.array_equal(s[1:, 4:6], -np.array(exp))
+    assert tuple(oracle_mod.generate_scene("test", 1)[1, :2]) == (-1.6189844599022485, 3.4489804011123173)
+    assert tuple(oracle_mod.generate_scene("test", 499)[1, :2]) == (1.1864128465707466, -3.4844207477053897)
+    sq = oracle_mod.generate_scene("test", 0, human_num=10, rule="square_crossing")
+    assert tuple(sq[1, :2]) == (-0.57503471562202868, 4.5028286434902451)
+    assert tuple(sq[1, 4:6]) == (2.4109570071399911, 3.7247453518203533)
