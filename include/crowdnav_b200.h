@@ -1,0 +1,208 @@
+/*
+ * crowdnav_b200.h -- C ABI of libcrowdnav_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the data-parallel hot path of minh86/ModelCrowdNav: the CrowdSim
+ * environment step (ORCA humans, kinematics, collision/discomfort, reward/done) and the
+ * SARL / MultiHumanRL one-step lookahead, batched over E independent environments that live
+ * in HBM as a struct-of-arrays.  Plain pointers and sizes only; no torch types.
+ *
+ * Every entry point names the reference interface it replaces (file:line relative to the
+ * reference repository root).  All functions return 0 (CN_OK) or a negative CN_E* code;
+ * cn_last_error() gives the thread-local message.  One handle per GPU per process, not
+ * thread-safe.  `stream` arguments are cudaStream_t passed as void* (0 = default stream; pass
+ * torch.cuda.current_stream().cuda_stream); nothing synchronises except the functions
+ * documented as blocking (host getters).  There is NO CPU fallback: every compute entry point
+ * fails with CN_ECUDA when no sm_100 device is usable.
+ */
+#ifndef CROWDNAV_B200_H
+#define CROWDNAV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CN_OK 0
+#define CN_EINVAL (-1)
+#define CN_ECUDA (-2)
+#define CN_ENOMEM (-3)
+#define CN_EUNSUPPORTED (-4)
+#define CN_EVALUE (-5) /* "Value network is not well trained." (multi_human_rl.py:57-58) */
+
+#define CN_AGENT_STRIDE 8     /* px py vx vy gx gy radius v_pref */
+#define CN_MAX_NEIGHBORS 16   /* ORCA max_neighbors supported by the kernel (reference: 10) */
+#define CN_MAX_HUMANS 64
+#define CN_MAX_ACTIONS 128
+
+/* info codes = crowd_sim/envs/utils/info.py:1-38 */
+enum { CN_NOTHING = 0, CN_DANGER = 1, CN_REACHGOAL = 2, CN_COLLISION = 3, CN_TIMEOUT = 4 };
+/* scene rules = crowd_sim.py:105-112 */
+enum { CN_CIRCLE_CROSSING = 0, CN_SQUARE_CROSSING = 1 };
+/* value-network arithmetic */
+enum { CN_PREC_F32 = 0 /* FP32 CUDA cores */, CN_PREC_F16_TC = 1 /* fp16 operands, fp32 accumulate, tcgen05 */ };
+
+typedef struct cn_env cn_env;
+typedef struct cn_policy cn_policy;
+
+/* CrowdSim.configure (crowd_sim.py:58-89) + ORCA.__init__ (orca.py:55-67) + agent attributes
+ * (agent.py:16-18), flattened.  Use cn_env_cfg_default() then override. */
+typedef struct {
+    int32_t num_envs;            /* E: environments resident on this GPU */
+    int32_t human_num;           /* H ([sim] human_num) */
+    double time_limit;           /* [env] time_limit = 25 */
+    double time_step;            /* [env] time_step = 0.25 */
+    double success_reward;       /* [reward] */
+    double collision_penalty;
+    double discomfort_dist;
+    double discomfort_penalty_factor;
+    double neighbor_dist;        /* orca.py:61 */
+    int32_t max_neighbors;       /* orca.py:62 */
+    double time_horizon;         /* orca.py:63 */
+    double human_safety_space;   /* orca.py:60 */
+    int32_t robot_visible;       /* [robot] visible */
+    /* device-side reset (throughput runs; parity runs upload host scenes with cn_env_set_state) */
+    int32_t sim_rule;            /* CN_CIRCLE_CROSSING / CN_SQUARE_CROSSING */
+    double circle_radius;        /* [sim] circle_radius = 4 */
+    double square_width;         /* [sim] square_width = 10 */
+    double human_radius, human_v_pref, robot_radius, robot_v_pref;
+    uint64_t seed;               /* Philox key */
+    int64_t env_id_offset;       /* global id of env 0 (rank * E): results do not depend on the GPU count */
+    int32_t auto_reset;          /* 1: an env that finished an episode is re-generated at the end of the step */
+    double gamma;                /* [rl] gamma, for the per-episode discounted return (explorer.py:124-125) */
+} cn_env_cfg;
+
+/* SARL.configure (sarl.py:73-86) + CADRL.set_common_parameters (cadrl.py:64-73) */
+typedef struct {
+    int32_t input_dim;           /* 13 (cadrl.py:53-55) */
+    int32_t self_state_dim;      /* 6 */
+    int32_t mlp1_dims[2];        /* 150,100 */
+    int32_t mlp2_dims[2];        /* 100,50 */
+    int32_t attn_dims[3];        /* 100,100,1 */
+    int32_t mlp3_dims[4];        /* 150,100,100,1 */
+    int32_t speed_samples;       /* 5 */
+    int32_t rotation_samples;    /* 16 */
+    double gamma;                /* 0.9 */
+    double v_pref;               /* robot v_pref used to build the action table (cadrl.py:147) */
+    int32_t precision;           /* CN_PREC_* */
+} cn_sarl_cfg;
+
+/* Episode statistics accumulated on the device by cn_env_step(update=1); the counters
+ * Explorer.run_k_episodes keeps (explorer.py:41-51,92-108,124-141). */
+typedef struct {
+    int64_t episodes, success, collision, timeout;
+    int64_t steps;               /* env steps taken (update=1) */
+    int64_t too_close;           /* Danger steps */
+    double sum_min_dist;         /* sum of Danger.min_dist */
+    double sum_success_time, sum_collision_time, sum_timeout_time;
+    double sum_return;           /* sum over finished episodes of sum_t gamma^(t*dt*v_pref) r_t */
+} cn_stats;
+
+const char *cn_last_error(void);
+int cn_version(void);
+int cn_device_count(void);
+
+void cn_env_cfg_default(cn_env_cfg *cfg);   /* values of crowd_nav/configs/env.config */
+void cn_sarl_cfg_default(cn_sarl_cfg *cfg); /* values of crowd_nav/configs/policy.config */
+
+/* ---- environment: replaces gym.make('CrowdSim-v0') + configure (crowd_sim.py:19-89) ---- */
+int cn_env_create(const cn_env_cfg *cfg, int device, cn_env **out);
+int cn_env_destroy(cn_env *env);
+
+/* CrowdSim.reset with host-generated scenes (crowd_sim.py:261-323).  agents: E x (H+1) x 8 doubles
+ * (agent 0 = robot), times: E doubles or NULL (= 0).  Clears per-episode accumulators. */
+int cn_env_set_state(cn_env *env, const double *agents_host, const double *times_host, void *stream);
+/* Blocking read-back in the same layout. */
+int cn_env_get_state(cn_env *env, double *agents_host, double *times_host, void *stream);
+/* CrowdSim.reset on the device (crowd_sim.py:165-217 distributions and rejection rule, Philox stream
+ * keyed by (seed, global env id, episode counter)).  env_mask_dev: E bytes on the device, NULL = all. */
+int cn_env_reset(cn_env *env, void *stream);
+
+/* Human ORCA actions for the current state: replaces the rvo2.PyRVOSimulator traffic of
+ * ORCA.predict (orca.py:82-132) for every human of every env (crowd_sim.py:337-342).  The result is
+ * cached on the device and reused by cn_env_step and cn_policy_lookahead (query_env). */
+int cn_env_orca(cn_env *env, void *stream);
+/* Robot action from an ORCA policy (imitation learning, train.py:157-166): writes the env's
+ * pending action. */
+int cn_env_robot_orca(cn_env *env, double safety_space, void *stream);
+
+/* CrowdSim.step(action, update) / onestep_lookahead (crowd_sim.py:325-434).  action_xy_dev: device
+ * pointer E x 2 doubles, or NULL to use the pending action chosen by cn_policy_lookahead /
+ * cn_env_robot_orca.  Requires cn_env_orca for the current state. update=0 leaves the state untouched
+ * and fills next_obs. */
+int cn_env_step(cn_env *env, const double *action_xy_dev, int update, void *stream);
+
+/* Device views of the last step's outputs (valid until the next call that writes them). */
+typedef struct {
+    const double *reward;      /* E */
+    const uint8_t *done;       /* E */
+    const uint8_t *info;       /* E, CN_* info code */
+    const double *dmin;        /* E, Danger.min_dist (inf when no human was closer) */
+    const double *human_v;     /* 2 x H x E (component-major): cached ORCA velocities */
+    const double *next_obs;    /* 5 x H x E (px py vx vy radius), update=0 only */
+    const double *state;       /* 8 x (H+1) x E field-major SoA */
+    const double *time;        /* E */
+    const int32_t *action_idx; /* E, pending action index (-1 when set from raw xy) */
+    const double *action_xy;   /* 2 x E pending action */
+} cn_env_views;
+int cn_env_get_views(cn_env *env, cn_env_views *out);
+
+/* Blocking host read of (reward, done, info, dmin); any pointer may be NULL. */
+int cn_env_read_outputs(cn_env *env, double *reward, uint8_t *done, uint8_t *info, double *dmin, void *stream);
+/* Blocking host read of the ORCA velocities as E x H x 2 doubles. */
+int cn_env_read_human_actions(cn_env *env, double *human_vxy_host, void *stream);
+/* Blocking host read of update=0 observations as E x H x 5 doubles. */
+int cn_env_read_next_obs(cn_env *env, double *obs_host, void *stream);
+/* Set the pending action from the host: E x 2 doubles. */
+int cn_env_set_actions(cn_env *env, const double *action_xy_host, void *stream);
+/* Blocking: reduce the device accumulators (explorer.py counters).  reset != 0 clears them. */
+int cn_env_read_stats(cn_env *env, cn_stats *out, int reset, void *stream);
+
+/* ---- policy: replaces policy_factory['sarl']() + configure (sarl.py:68-89) ---- */
+int cn_policy_create(const cn_sarl_cfg *cfg, int device, cn_policy **out);
+int cn_policy_destroy(cn_policy *p);
+int64_t cn_policy_param_count(const cn_sarl_cfg *cfg);
+/* model.load_state_dict (test.py:59): flat fp32 parameters in state-dict order
+ * mlp1.{0,2} mlp2.{0,2} attention.{0,2,4} mlp3.{0,2,4,6}, each .weight ([out][in] row-major) then .bias. */
+int cn_policy_load_weights(cn_policy *p, const float *flat_host, int64_t n, void *stream);
+/* CADRL.build_action_space (cadrl.py:82-102), holonomic; out: A x 2 doubles; returns A via *n_actions. */
+int cn_policy_action_table(cn_policy *p, double *out_xy_host, int32_t *n_actions);
+
+/* MultiHumanRL.predict for every env (multi_human_rl.py:11-63): rotate, propagate the A actions,
+ * reward + gamma_bar * V through mlp1 -> attention -> mlp3, first-strict-max argmax.
+ * query_env != 0 uses the cached ORCA velocities and the env reward ladder (crowd_sim.py:325-329),
+ * else constant-velocity humans and compute_reward (multi_human_rl.py:65-88).
+ * epsilon > 0 applies the train-phase epsilon-greedy draw (multi_human_rl.py:28-30) from a per-env
+ * Philox stream.  Writes the env's pending action. */
+int cn_policy_lookahead(cn_policy *p, cn_env *env, int query_env, double epsilon, void *stream);
+/* Blocking host read of the last lookahead: best_idx E int32, values E x A doubles (NULL to skip).
+ * Returns CN_EVALUE when some env had no finite value (reference raises ValueError). */
+int cn_policy_read(cn_policy *p, cn_env *env, int32_t *best_idx, double *values, void *stream);
+/* MultiHumanRL.transform (multi_human_rl.py:90-104) for every env: E x H x 13 fp32 into a DEVICE buffer. */
+int cn_policy_transform(cn_policy *p, cn_env *env, float *out_dev, void *stream);
+/* ValueNetwork.forward (sarl.py:28-65) on a DEVICE batch x: B x H x 13 fp32 -> B fp32 (FP32 path;
+ * used for TD targets, explorer.py:168-174). */
+int cn_policy_forward(cn_policy *p, const float *x_dev, int32_t batch, int32_t human_num, float *out_dev,
+                      void *stream);
+
+/* ---- the fused hot path: one env step preceded by one full lookahead ---- */
+/* orca -> lookahead -> step(update=1) [-> auto reset], all on `stream`, no host round trip.
+ * This is what Explorer.run_k_episodes' inner loop (explorer.py:62-69) does per env. */
+int cn_rollout_step(cn_policy *p, cn_env *env, int query_env, double epsilon, void *stream);
+/* Same through HOST buffers (blocking): uploads agents/times (E x (H+1) x 8, E), runs the step and
+ * downloads the new state, reward, done, info and the chosen action index.  Pinned memory recommended. */
+int cn_rollout_step_host(cn_policy *p, cn_env *env, int query_env, double epsilon, const double *agents_in,
+                         const double *times_in, double *agents_out, double *times_out, double *reward,
+                         uint8_t *done, uint8_t *info, int32_t *action_idx, void *stream);
+
+/* Number of kernels this library launched so far in this process. */
+int64_t cn_launch_count(void);
+
+/* Self-test of the tcgen05/TMEM building block: D[128 x N] = A[128 x K] * B[N x K]^T with fp16 operands,
+ * fp32 accumulate.  a_host: 128 x K, b_host: N x K (row-major fp32, rounded to fp16 inside), d_host: 128 x N. */
+int cn_selftest_umma(int32_t N, int32_t K, const float *a_host, const float *b_host, float *d_host, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,146 @@
+"""ctypes binding of ``csrc/libcrowdnav_b200.so`` (declared in ``include/crowdnav_b200.h``).
+
+The product path has no CPU fallback: if the CUDA library is missing, ``load()`` raises, and every compute
+entry point fails with ``CrowdNavError`` when no sm_100 device is usable.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libcrowdnav_b200.so")
+
+CN_OK, CN_EINVAL, CN_ECUDA, CN_ENOMEM, CN_EUNSUPPORTED, CN_EVALUE = 0, -1, -2, -3, -4, -5
+NOTHING, DANGER, REACHGOAL, COLLISION, TIMEOUT = 0, 1, 2, 3, 4
+CIRCLE_CROSSING, SQUARE_CROSSING = 0, 1
+PREC_F32, PREC_F16_TC = 0, 1
+AGENT_STRIDE = 8
+
+EXPORTS = [
+    "cn_last_error", "cn_version", "cn_device_count", "cn_env_cfg_default", "cn_sarl_cfg_default",
+    "cn_env_create", "cn_env_destroy", "cn_env_set_state", "cn_env_get_state", "cn_env_reset", "cn_env_orca",
+    "cn_env_robot_orca", "cn_env_step", "cn_env_get_views", "cn_env_read_outputs", "cn_env_read_human_actions",
+    "cn_env_read_next_obs", "cn_env_set_actions", "cn_env_read_stats", "cn_policy_create", "cn_policy_destroy",
+    "cn_policy_param_count", "cn_policy_load_weights", "cn_policy_action_table", "cn_policy_lookahead",
+    "cn_policy_read", "cn_policy_transform", "cn_policy_forward", "cn_rollout_step", "cn_rollout_step_host",
+    "cn_launch_count", "cn_selftest_umma",
+]
+
+
+class CrowdNavError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libcrowdnav_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class EnvCfg(C.Structure):
+    _fields_ = [("num_envs", C.c_int32), ("human_num", C.c_int32), ("time_limit", C.c_double),
+                ("time_step", C.c_double), ("success_reward", C.c_double), ("collision_penalty", C.c_double),
+                ("discomfort_dist", C.c_double), ("discomfort_penalty_factor", C.c_double),
+                ("neighbor_dist", C.c_double), ("max_neighbors", C.c_int32), ("time_horizon", C.c_double),
+                ("human_safety_space", C.c_double), ("robot_visible", C.c_int32), ("sim_rule", C.c_int32),
+                ("circle_radius", C.c_double), ("square_width", C.c_double), ("human_radius", C.c_double),
+                ("human_v_pref", C.c_double), ("robot_radius", C.c_double), ("robot_v_pref", C.c_double),
+                ("seed", C.c_uint64), ("env_id_offset", C.c_int64), ("auto_reset", C.c_int32),
+                ("gamma", C.c_double)]
+
+
+class SarlCfg(C.Structure):
+    _fields_ = [("input_dim", C.c_int32), ("self_state_dim", C.c_int32), ("mlp1_dims", C.c_int32 * 2),
+                ("mlp2_dims", C.c_int32 * 2), ("attn_dims", C.c_int32 * 3), ("mlp3_dims", C.c_int32 * 4),
+                ("speed_samples", C.c_int32), ("rotation_samples", C.c_int32), ("gamma", C.c_double),
+                ("v_pref", C.c_double), ("precision", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("episodes", C.c_int64), ("success", C.c_int64), ("collision", C.c_int64),
+                ("timeout", C.c_int64), ("steps", C.c_int64), ("too_close", C.c_int64),
+                ("sum_min_dist", C.c_double), ("sum_success_time", C.c_double),
+                ("sum_collision_time", C.c_double), ("sum_timeout_time", C.c_double),
+                ("sum_return", C.c_double)]
+
+
+class EnvViews(C.Structure):
+    _fields_ = [("reward", C.c_void_p), ("done", C.c_void_p), ("info", C.c_void_p), ("dmin", C.c_void_p),
+                ("human_v", C.c_void_p), ("next_obs", C.c_void_p), ("state", C.c_void_p), ("time", C.c_void_p),
+                ("action_idx", C.c_void_p), ("action_xy", C.c_void_p)]
+
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    L.cn_last_error.restype = C.c_char_p
+    L.cn_launch_count.restype = i64
+    L.cn_policy_param_count.restype = i64
+    L.cn_policy_param_count.argtypes = [C.POINTER(SarlCfg)]
+    L.cn_env_cfg_default.argtypes = [C.POINTER(EnvCfg)]
+    L.cn_env_cfg_default.restype = None
+    L.cn_sarl_cfg_default.argtypes = [C.POINTER(SarlCfg)]
+    L.cn_sarl_cfg_default.restype = None
+    L.cn_env_create.argtypes = [C.POINTER(EnvCfg), C.c_int, C.POINTER(vp)]
+    L.cn_env_destroy.argtypes = [vp]
+    L.cn_env_set_state.argtypes = [vp, vp, vp, vp]
+    L.cn_env_get_state.argtypes = [vp, vp, vp, vp]
+    L.cn_env_reset.argtypes = [vp, vp]
+    L.cn_env_orca.argtypes = [vp, vp]
+    L.cn_env_robot_orca.argtypes = [vp, dbl, vp]
+    L.cn_env_step.argtypes = [vp, vp, C.c_int, vp]
+    L.cn_env_get_views.argtypes = [vp, C.POINTER(EnvViews)]
+    L.cn_env_read_outputs.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.cn_env_read_human_actions.argtypes = [vp, vp, vp]
+    L.cn_env_read_next_obs.argtypes = [vp, vp, vp]
+    L.cn_env_set_actions.argtypes = [vp, vp, vp]
+    L.cn_env_read_stats.argtypes = [vp, C.POINTER(Stats), C.c_int, vp]
+    L.cn_policy_create.argtypes = [C.POINTER(SarlCfg), C.c_int, C.POINTER(vp)]
+    L.cn_policy_destroy.argtypes = [vp]
+    L.cn_policy_load_weights.argtypes = [vp, vp, i64, vp]
+    L.cn_policy_action_table.argtypes = [vp, vp, C.POINTER(i32)]
+    L.cn_policy_lookahead.argtypes = [vp, vp, C.c_int, dbl, vp]
+    L.cn_policy_read.argtypes = [vp, vp, vp, vp, vp]
+    L.cn_policy_transform.argtypes = [vp, vp, vp, vp]
+    L.cn_policy_forward.argtypes = [vp, vp, i32, i32, vp, vp]
+    L.cn_rollout_step.argtypes = [vp, vp, C.c_int, dbl, vp]
+    L.cn_rollout_step_host.argtypes = [vp, vp, C.c_int, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.cn_selftest_umma.argtypes = [i32, i32, vp, vp, vp, C.c_int]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != CN_OK:
+        raise CrowdNavError(rc, load().cn_last_error().decode())
+    return rc
+
+
+def default_env_cfg(**kw):
+    cfg = EnvCfg()
+    load().cn_env_cfg_default(C.byref(cfg))
+    for k, v in kw.items():
+        if not hasattr(cfg, k):
+            raise AttributeError("cn_env_cfg has no field %r" % k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+def default_sarl_cfg(**kw):
+    cfg = SarlCfg()
+    load().cn_sarl_cfg_default(C.byref(cfg))
+    for k, v in kw.items():
+        if not hasattr(cfg, k):
+            raise AttributeError("cn_sarl_cfg has no field %r" % k)
+        if isinstance(v, (list, tuple)):
+            arr = getattr(cfg, k)
+            for i, x in enumerate(v):
+                arr[i] = x
+        else:
+            setattr(cfg, k, v)
+    return cfg

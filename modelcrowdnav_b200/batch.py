@@ -1,0 +1,213 @@
+"""Batched host API over the C ABI: E environments per GPU, one SARL policy.
+
+This is the layer the drop-in façades (``crowd_sim.CrowdSim``, ``policy.SARL``, ``explorer.Explorer``)
+and ``bench.py`` are built on.  Host arrays are numpy; device tensors (torch) are only used for hand-off
+(`transform`, `forward`).  Layout of the exchange format: ``agents[E, H+1, 8]`` float64 with columns
+``px py vx vy gx gy radius v_pref`` and agent 0 = robot (crowd_sim/envs/utils/state.py FullState order
+minus theta, which is unused for holonomic kinematics).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import check
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _stream(stream):
+    return C.c_void_p(int(stream)) if stream else None
+
+
+class BatchedCrowdSim(object):
+    """E CrowdSim environments in HBM (replaces CrowdSim, crowd_sim/envs/crowd_sim.py:15-434)."""
+
+    def __init__(self, num_envs, human_num=5, device=0, **cfg):
+        self.lib = _capi.load()
+        self.cfg = _capi.default_env_cfg(num_envs=num_envs, human_num=human_num, **cfg)
+        self.E, self.H, self.device = num_envs, human_num, device
+        self.handle = C.c_void_p()
+        check(self.lib.cn_env_create(C.byref(self.cfg), device, C.byref(self.handle)))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.cn_env_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- state ------------------------------------------------------------------------------------
+    def set_state(self, agents, times=None, stream=None):
+        agents = np.ascontiguousarray(agents, dtype=np.float64)
+        assert agents.shape == (self.E, self.H + 1, _capi.AGENT_STRIDE), agents.shape
+        if times is not None:
+            times = np.ascontiguousarray(times, dtype=np.float64)
+            assert times.shape == (self.E,)
+        check(self.lib.cn_env_set_state(self.handle, _ptr(agents), _ptr(times), _stream(stream)))
+
+    def get_state(self, stream=None):
+        agents = np.empty((self.E, self.H + 1, _capi.AGENT_STRIDE), np.float64)
+        times = np.empty(self.E, np.float64)
+        check(self.lib.cn_env_get_state(self.handle, _ptr(agents), _ptr(times), _stream(stream)))
+        return agents, times
+
+    def reset_device(self, stream=None):
+        """CrowdSim.reset on the GPU (Philox scenes; crowd_sim.py:165-217 distributions)."""
+        check(self.lib.cn_env_reset(self.handle, _stream(stream)))
+
+    # -- ORCA / step ------------------------------------------------------------------------------
+    def orca(self, stream=None):
+        check(self.lib.cn_env_orca(self.handle, _stream(stream)))
+
+    def human_actions(self, stream=None):
+        out = np.empty((self.E, self.H, 2), np.float64)
+        check(self.lib.cn_env_read_human_actions(self.handle, _ptr(out), _stream(stream)))
+        return out
+
+    def robot_orca(self, safety_space=0.0, stream=None):
+        check(self.lib.cn_env_robot_orca(self.handle, float(safety_space), _stream(stream)))
+
+    def set_actions(self, actions, stream=None):
+        actions = np.ascontiguousarray(actions, dtype=np.float64)
+        assert actions.shape == (self.E, 2)
+        check(self.lib.cn_env_set_actions(self.handle, _ptr(actions), _stream(stream)))
+
+    def step(self, actions=None, update=True, read=True, stream=None):
+        """CrowdSim.step for every env. actions: (E,2) host array or None (= pending action)."""
+        if actions is not None:
+            self.set_actions(actions, stream)
+        check(self.lib.cn_env_step(self.handle, None, int(bool(update)), _stream(stream)))
+        return self.read_outputs(stream) if read else None
+
+    def read_outputs(self, stream=None):
+        reward = np.empty(self.E, np.float64)
+        done = np.empty(self.E, np.uint8)
+        info = np.empty(self.E, np.uint8)
+        dmin = np.empty(self.E, np.float64)
+        check(self.lib.cn_env_read_outputs(self.handle, _ptr(reward), _ptr(done), _ptr(info), _ptr(dmin),
+                                           _stream(stream)))
+        return reward, done, info, dmin
+
+    def next_obs(self, stream=None):
+        out = np.empty((self.E, self.H, 5), np.float64)
+        check(self.lib.cn_env_read_next_obs(self.handle, _ptr(out), _stream(stream)))
+        return out
+
+    def views(self):
+        v = _capi.EnvViews()
+        check(self.lib.cn_env_get_views(self.handle, C.byref(v)))
+        return v
+
+    def stats(self, reset=False, stream=None):
+        s = _capi.Stats()
+        check(self.lib.cn_env_read_stats(self.handle, C.byref(s), int(reset), _stream(stream)))
+        return {k: getattr(s, k) for k, _ in _capi.Stats._fields_}
+
+
+class BatchedSARL(object):
+    """SARL lookahead policy on the GPU (replaces SARL/MultiHumanRL.predict, sarl.py:68-89,
+    multi_human_rl.py:11-63)."""
+
+    def __init__(self, device=0, precision="f32", **cfg):
+        self.lib = _capi.load()
+        prec = {"f32": _capi.PREC_F32, "f16_tc": _capi.PREC_F16_TC}[precision]
+        self.cfg = _capi.default_sarl_cfg(precision=prec, **cfg)
+        self.device = device
+        self.handle = C.c_void_p()
+        check(self.lib.cn_policy_create(C.byref(self.cfg), device, C.byref(self.handle)))
+        self.n_params = int(self.lib.cn_policy_param_count(C.byref(self.cfg)))
+        n = C.c_int32()
+        check(self.lib.cn_policy_action_table(self.handle, None, C.byref(n)))
+        self.action_table = np.empty((n.value, 2), np.float64)
+        check(self.lib.cn_policy_action_table(self.handle, _ptr(self.action_table), C.byref(n)))
+        self.A = n.value
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.cn_policy_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_weights(self, weights, stream=None):
+        """weights: flat fp32 array in state-dict order, or a ValueNetwork state_dict (test.py:59)."""
+        if isinstance(weights, dict):
+            weights = np.concatenate([np.asarray(v.detach().cpu().numpy() if hasattr(v, "detach") else v,
+                                                 dtype=np.float32).ravel() for v in weights.values()])
+        weights = np.ascontiguousarray(weights, dtype=np.float32)
+        check(self.lib.cn_policy_load_weights(self.handle, _ptr(weights), weights.size, _stream(stream)))
+
+    def lookahead(self, env, query_env=False, epsilon=0.0, stream=None):
+        check(self.lib.cn_policy_lookahead(self.handle, env.handle, int(bool(query_env)), float(epsilon),
+                                           _stream(stream)))
+
+    def read(self, env, values=True, stream=None):
+        best = np.empty(env.E, np.int32)
+        vals = np.empty((env.E, self.A), np.float64) if values else None
+        check(self.lib.cn_policy_read(self.handle, env.handle, _ptr(best), _ptr(vals), _stream(stream)))
+        return best, vals
+
+    def transform(self, env, stream=None):
+        """MultiHumanRL.transform for every env -> torch CUDA tensor (E, H, 13) fp32."""
+        import torch
+        out = torch.empty((env.E, env.H, 13), dtype=torch.float32, device="cuda:%d" % self.device)
+        check(self.lib.cn_policy_transform(self.handle, env.handle, C.c_void_p(out.data_ptr()), _stream(stream)))
+        return out
+
+    def forward(self, x, stream=None):
+        """ValueNetwork.forward on a CUDA tensor (B, H, 13) fp32 -> (B,) fp32 (FP32 kernel)."""
+        import torch
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.shape[2] == 13
+        x = x.contiguous()
+        out = torch.empty((x.shape[0],), dtype=torch.float32, device=x.device)
+        check(self.lib.cn_policy_forward(self.handle, C.c_void_p(x.data_ptr()), x.shape[0], x.shape[1],
+                                         C.c_void_p(out.data_ptr()), _stream(stream)))
+        return out
+
+
+def rollout_step(policy, env, query_env=False, epsilon=0.0, stream=None):
+    """orca -> lookahead -> step(update=True) [-> auto reset] without a host round trip."""
+    check(policy.lib.cn_rollout_step(policy.handle, env.handle, int(bool(query_env)), float(epsilon),
+                                     _stream(stream)))
+
+
+class HostStepBuffers(object):
+    """Pinned host buffers for ``rollout_step_host`` (the end-to-end path with HOST state)."""
+
+    def __init__(self, env, pinned=True):
+        E, A1 = env.E, env.H + 1
+        shapes = dict(agents_in=((E, A1, 8), np.float64), times_in=((E,), np.float64),
+                      agents_out=((E, A1, 8), np.float64), times_out=((E,), np.float64),
+                      reward=((E,), np.float64), done=((E,), np.uint8), info=((E,), np.uint8),
+                      action_idx=((E,), np.int32))
+        self._keep = []
+        for k, (shape, dt) in shapes.items():
+            if pinned:
+                import torch
+                t = torch.empty(shape, dtype=getattr(torch, np.dtype(dt).name), pin_memory=True)
+                self._keep.append(t)
+                setattr(self, k, t.numpy())
+            else:
+                setattr(self, k, np.empty(shape, dt))
+        self.h2d_bytes = self.agents_in.nbytes + self.times_in.nbytes
+        self.d2h_bytes = (self.agents_out.nbytes + self.times_out.nbytes + self.reward.nbytes + self.done.nbytes
+                          + self.info.nbytes + self.action_idx.nbytes)
+
+
+def rollout_step_host(policy, env, buf, query_env=False, epsilon=0.0, stream=None):
+    """One lookahead + env step through host buffers: H2D state, kernels, D2H results (blocking)."""
+    check(policy.lib.cn_rollout_step_host(policy.handle, env.handle, int(bool(query_env)), float(epsilon),
+                                          _ptr(buf.agents_in), _ptr(buf.times_in), _ptr(buf.agents_out),
+                                          _ptr(buf.times_out), _ptr(buf.reward), _ptr(buf.done), _ptr(buf.info),
+                                          _ptr(buf.action_idx), _stream(stream)))

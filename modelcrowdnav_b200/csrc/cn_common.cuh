@@ -1,0 +1,197 @@
+// cn_common.cuh -- internal definitions shared by the kernels and the C ABI (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/crowdnav_b200.h"
+
+// ---- field-major SoA state in HBM: state[(field * A1 + agent) * E + env] (f64) -----------------
+enum { F_PX = 0, F_PY, F_VX, F_VY, F_GX, F_GY, F_R, F_VPREF, F_COUNT };
+
+struct EnvDims {
+    int E;   // envs on this GPU
+    int H;   // humans
+    int A1;  // H + 1 agents, agent 0 = robot
+};
+
+__host__ __device__ __forceinline__ size_t st_idx(const EnvDims &d, int field, int agent, int env)
+{
+    return ((size_t)field * d.A1 + agent) * d.E + env;
+}
+
+struct EnvParams {
+    EnvDims d;
+    double time_limit, time_step;
+    double success_reward, collision_penalty, discomfort_dist, discomfort_penalty_factor;
+    float neighbor_dist, time_horizon, time_step_f;
+    int max_neighbors;
+    double human_safety_space;
+    int robot_visible;
+    int sim_rule;
+    double circle_radius, square_width, human_radius, human_v_pref, robot_radius, robot_v_pref;
+    uint64_t seed;
+    int64_t env_id_offset;
+    int auto_reset;
+    double gamma;
+};
+
+// per-env episode accumulators (explorer.py:41-51,92-108,124-141)
+struct EnvAccum {
+    int32_t *ep_steps;       // steps in the running episode
+    double *ep_return;       // running discounted return
+    int64_t *episodes, *success, *collision, *timeout, *steps, *too_close;
+    double *sum_min_dist, *sum_success_time, *sum_collision_time, *sum_timeout_time, *sum_return;
+    uint32_t *episode_ctr;   // Philox subsequence of the next device reset
+};
+
+struct cn_env {
+    int device;
+    EnvParams p;
+    double *state;        // 8 x A1 x E
+    double *time;         // E
+    double *human_v;      // 2 x H x E
+    double *action_xy;    // 2 x E (pending robot action)
+    int32_t *action_idx;  // E
+    double *reward;       // E
+    uint8_t *done;        // E
+    uint8_t *info;        // E
+    double *dmin;         // E
+    double *next_obs;     // 5 x H x E
+    uint8_t *frozen;      // E: episode finished and auto_reset off -> env no longer advances
+    EnvAccum acc;
+    void *accum_block;    // single allocation backing acc.*
+    double *stage;        // device staging, E x A1 x 8 (AoS exchange layout)
+    uint32_t *step_ctr;   // E: lookahead draws (epsilon-greedy Philox subsequence)
+    int orca_valid;
+};
+
+struct SarlDims {
+    int in, self_dim;
+    int m1[2], m2[2], at[3], m3[4];
+    int A;  // actions
+};
+
+// fp32 weights on the device, transposed to [in][out_padded] (out padded to a multiple of 4)
+struct LinearDev {
+    const float *wt;
+    const float *b;
+    int in, out, ld;
+};
+
+struct SarlWeightsDev {
+    LinearDev m1[2], m2[2], at[3], m3[4];
+};
+
+struct cn_policy {
+    int device;
+    cn_sarl_cfg cfg;
+    SarlDims d;
+    double gamma_bar;          // pow(gamma, time_step * v_pref), set per lookahead from the env
+    double action_host[CN_MAX_ACTIONS * 2];
+    double *action_dev;        // A x 2
+    float *w_raw;              // flat state-dict order copy (device)
+    float *w_t;                // transposed/padded fp32 block
+    SarlWeightsDev w;
+    int64_t n_params;
+    int weights_loaded;
+    // lookahead outputs
+    double *values;            // E x A
+    int32_t *bad_flag;         // 1 int: some env had no finite value
+    int values_E;
+    // tcgen05 path (lookahead_tc.cu)
+    void *tc;                  // opaque, owned by the TC module
+};
+
+// ---- error plumbing --------------------------------------------------------------------------
+void cn_set_error(const char *fmt, ...);
+extern int64_t g_cn_launches;
+
+#define CN_CUDA_CHECK(call)                                                                     \
+    do {                                                                                        \
+        cudaError_t _e = (call);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            cn_set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return CN_ECUDA;                                                                    \
+        }                                                                                       \
+    } while (0)
+
+#define CN_LAUNCH_CHECK()                                                                       \
+    do {                                                                                        \
+        ++g_cn_launches;                                                                        \
+        cudaError_t _e = cudaGetLastError();                                                    \
+        if (_e != cudaSuccess) {                                                                \
+            cn_set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return CN_ECUDA;                                                                    \
+        }                                                                                       \
+    } while (0)
+
+// ---- Philox4x32-10 (counter-based RNG; Salmon et al. 2011) ------------------------------------
+struct Philox {
+    uint32_t key[2];
+    uint32_t ctr[4];
+    __host__ __device__ static inline void mulhilo(uint32_t a, uint32_t b, uint32_t &hi, uint32_t &lo)
+    {
+        const uint64_t p = (uint64_t)a * b;
+        hi = (uint32_t)(p >> 32);
+        lo = (uint32_t)p;
+    }
+    __host__ __device__ inline void block(uint32_t out[4]) const
+    {
+        uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+        uint32_t k0 = key[0], k1 = key[1];
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            uint32_t hi0, lo0, hi1, lo1;
+            mulhilo(0xD2511F53u, c0, hi0, lo0);
+            mulhilo(0xCD9E8D57u, c2, hi1, lo1);
+            const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        }
+        out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    }
+};
+
+// Uniform double in [0,1) with 53 random bits (same construction as MT19937 genrand_res53).
+struct PhiloxStream {
+    Philox ph;
+    uint32_t buf[4];
+    int have;
+    uint32_t draw;
+    __host__ __device__ inline void init(uint64_t seed, uint64_t env_gid, uint32_t subseq, uint32_t domain)
+    {
+        ph.key[0] = (uint32_t)seed; ph.key[1] = (uint32_t)(seed >> 32);
+        ph.ctr[1] = subseq; ph.ctr[2] = (uint32_t)env_gid;
+        ph.ctr[3] = (uint32_t)(env_gid >> 32) ^ (domain << 24);
+        have = 0; draw = 0;
+    }
+    __host__ __device__ inline double next()
+    {
+        if (have < 2) { ph.ctr[0] = draw++; ph.block(buf); have = 4; }
+        const uint32_t a = buf[4 - have] >> 5, b = buf[5 - have] >> 6;
+        have -= 2;
+        return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+    }
+};
+
+// np.linalg.norm of a 2-vector as numpy evaluates it: sqrt(fma(b, b, a*a))
+__host__ __device__ __forceinline__ double norm2d(double a, double b) { return sqrt(fma(b, b, a * a)); }
+
+// ---- module entry points (each .cu) -----------------------------------------------------------
+int cn_launch_orca(cn_env *env, cudaStream_t s);
+int cn_launch_robot_orca(cn_env *env, double safety_space, cudaStream_t s);
+int cn_launch_step(cn_env *env, const double *action_xy_dev, int update, cudaStream_t s);
+int cn_launch_reset(cn_env *env, int only_done, cudaStream_t s);
+int cn_launch_pack(cn_env *env, int to_soa, cudaStream_t s);  // stage (AoS) <-> state (SoA)
+int cn_launch_stats_reduce(cn_env *env, cn_stats *out_dev_as_host, int reset, cudaStream_t s);
+
+int cn_lookahead_f32(cn_policy *p, cn_env *env, int query_env, double epsilon, cudaStream_t s);
+int cn_transform_f32(cn_policy *p, cn_env *env, float *out_dev, cudaStream_t s);
+int cn_forward_f32(cn_policy *p, const float *x_dev, int batch, int H, float *out_dev, cudaStream_t s);
+
+int cn_tc_init(cn_policy *p);
+void cn_tc_destroy(cn_policy *p);
+int cn_tc_load_weights(cn_policy *p, const float *flat_host, cudaStream_t s);
+int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cudaStream_t s);

@@ -1,0 +1,528 @@
+// orca_step.cu -- ORCA human motion (K1), CrowdSim.step (K2), device reset, AoS<->SoA packing.
+//
+// Compiled with -fmad=false: the reference arithmetic (x86 rvo2 in float32, CPython in float64)
+// never contracts mul+add, and collision/done codes must be bit-exact.  The only fused operation
+// on the reference path is numpy's 2-element dot inside np.linalg.norm (norm2d, explicit fma()).
+//
+// Reference (file:line relative to the reference root):
+//   ORCA.predict                     crowd_sim/envs/policy/orca.py:82-132
+//   rvo2 Agent::computeNeighbors / computeNewVelocity / linearProgram1-3 (third-party RVO2 2.0.x)
+//   CrowdSim.step                    crowd_sim/envs/crowd_sim.py:331-434
+//   point_to_segment_dist            crowd_sim/envs/utils/utils.py:4-26
+//   CrowdSim.reset + generators      crowd_sim/envs/crowd_sim.py:165-217,261-323
+//   Explorer counters                crowd_nav/utils/explorer.py:41-51,92-141
+#include "env_math.cuh"
+
+#include <math.h>
+
+#define RVO_EPSILON 0.00001f
+
+namespace {
+
+struct v2 { float x, y; };
+struct Line { v2 point, direction; };
+
+__device__ __forceinline__ v2 V(float x, float y) { v2 r; r.x = x; r.y = y; return r; }
+__device__ __forceinline__ v2 vadd(v2 a, v2 b) { return V(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ v2 vsub(v2 a, v2 b) { return V(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ v2 vneg(v2 a) { return V(-a.x, -a.y); }
+__device__ __forceinline__ v2 vscale(float s, v2 a) { return V(s * a.x, s * a.y); }
+__device__ __forceinline__ float vdot(v2 a, v2 b) { return a.x * b.x + a.y * b.y; }
+__device__ __forceinline__ float vdet(v2 a, v2 b) { return a.x * b.y - a.y * b.x; }
+__device__ __forceinline__ float vabssq(v2 a) { return vdot(a, a); }
+__device__ __forceinline__ float vabs(v2 a) { return sqrtf(vdot(a, a)); }
+// RVO2 Vector2::operator/(float) multiplies by the reciprocal
+__device__ __forceinline__ v2 vdiv(v2 a, float s) { const float inv = 1.0f / s; return V(a.x * inv, a.y * inv); }
+__device__ __forceinline__ v2 vnormalize(v2 a) { return vdiv(a, vabs(a)); }
+__device__ __forceinline__ float sqrf(float a) { return a * a; }
+
+// linearProgram1: optimise along line `lineNo` subject to lines [0, lineNo) and the speed disc.
+__device__ bool lp1(const Line *lines, int lineNo, float radius, v2 opt, bool directionOpt, v2 &result)
+{
+    const Line L = lines[lineNo];
+    const float dotProduct = vdot(L.point, L.direction);
+    const float discriminant = sqrf(dotProduct) + sqrf(radius) - vabssq(L.point);
+    if (discriminant < 0.0f) return false;
+
+    const float sqrtDiscriminant = sqrtf(discriminant);
+    float tLeft = -dotProduct - sqrtDiscriminant;
+    float tRight = -dotProduct + sqrtDiscriminant;
+
+    for (int i = 0; i < lineNo; ++i) {
+        const Line Li = lines[i];
+        const float denominator = vdet(L.direction, Li.direction);
+        const float numerator = vdet(Li.direction, vsub(L.point, Li.point));
+        if (fabsf(denominator) <= RVO_EPSILON) {
+            if (numerator < 0.0f) return false;
+            continue;
+        }
+        const float t = numerator / denominator;
+        if (denominator >= 0.0f) tRight = fminf(tRight, t);
+        else tLeft = fmaxf(tLeft, t);
+        if (tLeft > tRight) return false;
+    }
+
+    if (directionOpt) {
+        if (vdot(opt, L.direction) > 0.0f) result = vadd(L.point, vscale(tRight, L.direction));
+        else result = vadd(L.point, vscale(tLeft, L.direction));
+    } else {
+        const float t = vdot(L.direction, vsub(opt, L.point));
+        if (t < tLeft) result = vadd(L.point, vscale(tLeft, L.direction));
+        else if (t > tRight) result = vadd(L.point, vscale(tRight, L.direction));
+        else result = vadd(L.point, vscale(t, L.direction));
+    }
+    return true;
+}
+
+__device__ int lp2(const Line *lines, int n, float radius, v2 opt, bool directionOpt, v2 &result)
+{
+    if (directionOpt) result = vscale(radius, opt);
+    else if (vabssq(opt) > sqrf(radius)) result = vscale(radius, vnormalize(opt));
+    else result = opt;
+
+    for (int i = 0; i < n; ++i) {
+        if (vdet(lines[i].direction, vsub(lines[i].point, result)) > 0.0f) {
+            const v2 tmp = result;
+            if (!lp1(lines, i, radius, opt, directionOpt, result)) {
+                result = tmp;
+                return i;
+            }
+        }
+    }
+    return n;
+}
+
+__device__ void lp3(const Line *lines, int n, int beginLine, float radius, v2 &result)
+{
+    float distance = 0.0f;
+    Line proj[CN_MAX_NEIGHBORS];
+    for (int i = beginLine; i < n; ++i) {
+        if (vdet(lines[i].direction, vsub(lines[i].point, result)) > distance) {
+            int np = 0;
+            const Line Li = lines[i];
+            for (int j = 0; j < i; ++j) {
+                const Line Lj = lines[j];
+                Line line;
+                const float determinant = vdet(Li.direction, Lj.direction);
+                if (fabsf(determinant) <= RVO_EPSILON) {
+                    if (vdot(Li.direction, Lj.direction) > 0.0f) continue;
+                    line.point = vscale(0.5f, vadd(Li.point, Lj.point));
+                } else {
+                    const float t = vdet(Lj.direction, vsub(Li.point, Lj.point)) / determinant;
+                    line.point = vadd(Li.point, vscale(t, Li.direction));
+                }
+                line.direction = vnormalize(vsub(Lj.direction, Li.direction));
+                proj[np++] = line;
+            }
+            const v2 tmp = result;
+            if (lp2(proj, np, radius, V(-Li.direction.y, Li.direction.x), true, result) < np) result = tmp;
+            distance = vdet(Li.direction, vsub(Li.point, result));
+        }
+    }
+}
+
+// One ORCA solve: `self` against the candidate list cand[0..n_cand) of agent indices, visited in
+// list order (rvo2 kd-tree single-leaf order = addAgent order, orca.py:100-104).
+__device__ void orca_solve(const EnvParams &p, const double *__restrict__ st, int e, int self,
+                           const int *cand_first, int n_first, int extra_agent /* -1 or robot */,
+                           double safety_space, float &out_vx, float &out_vy)
+{
+    const EnvDims d = p.d;
+    auto ldf = [&](int field, int agent) { return (float)st[st_idx(d, field, agent, e)]; };
+    const v2 pos = V(ldf(F_PX, self), ldf(F_PY, self));
+    const v2 vel = V(ldf(F_VX, self), ldf(F_VY, self));
+    const float radius_self = (float)(st[st_idx(d, F_R, self, e)] + 0.01 + safety_space);
+    const float max_speed = (float)st[st_idx(d, F_VPREF, self, e)];
+    const v2 pref = V((float)(st[st_idx(d, F_GX, self, e)] - st[st_idx(d, F_PX, self, e)]),
+                      (float)(st[st_idx(d, F_GY, self, e)] - st[st_idx(d, F_PY, self, e)]));
+
+    // Agent::computeNeighbors / insertAgentNeighbor
+    float nb_d2[CN_MAX_NEIGHBORS];
+    int nb_id[CN_MAX_NEIGHBORS];
+    int nn = 0;
+    const int maxN = p.max_neighbors;
+    float rangeSq = sqrf(p.neighbor_dist);
+    const int n_cand = n_first + (extra_agent >= 0 ? 1 : 0);
+    if (maxN > 0) {
+        for (int c = 0; c < n_cand; ++c) {
+            int o;
+            if (c < n_first) { o = cand_first[0] + c; if (o >= self && cand_first[1]) ++o; }
+            else o = extra_agent;
+            const float distSq = vabssq(vsub(pos, V(ldf(F_PX, o), ldf(F_PY, o))));
+            if (distSq < rangeSq) {
+                if (nn < maxN) { nb_d2[nn] = distSq; nb_id[nn] = o; ++nn; }
+                int i = nn - 1;
+                while (i != 0 && distSq < nb_d2[i - 1]) {
+                    nb_d2[i] = nb_d2[i - 1]; nb_id[i] = nb_id[i - 1];
+                    --i;
+                }
+                nb_d2[i] = distSq; nb_id[i] = o;
+                if (nn == maxN) rangeSq = nb_d2[nn - 1];
+            }
+        }
+    }
+
+    // Agent::computeNewVelocity
+    Line lines[CN_MAX_NEIGHBORS];
+    const float invTimeHorizon = 1.0f / p.time_horizon;
+    for (int k = 0; k < nn; ++k) {
+        const int o = nb_id[k];
+        const v2 relativePosition = vsub(V(ldf(F_PX, o), ldf(F_PY, o)), pos);
+        const v2 relativeVelocity = vsub(vel, V(ldf(F_VX, o), ldf(F_VY, o)));
+        const float distSq = vabssq(relativePosition);
+        const float radius_o = (float)(st[st_idx(d, F_R, o, e)] + 0.01 + safety_space);
+        const float combinedRadius = radius_self + radius_o;
+        const float combinedRadiusSq = sqrf(combinedRadius);
+        Line line;
+        v2 u;
+        if (distSq > combinedRadiusSq) {
+            const v2 w = vsub(relativeVelocity, vscale(invTimeHorizon, relativePosition));
+            const float wLengthSq = vabssq(w);
+            const float dotProduct1 = vdot(w, relativePosition);
+            if (dotProduct1 < 0.0f && sqrf(dotProduct1) > combinedRadiusSq * wLengthSq) {
+                const float wLength = sqrtf(wLengthSq);
+                const v2 unitW = vdiv(w, wLength);
+                line.direction = V(unitW.y, -unitW.x);
+                u = vscale(combinedRadius * invTimeHorizon - wLength, unitW);
+            } else {
+                const float leg = sqrtf(distSq - combinedRadiusSq);
+                if (vdet(relativePosition, w) > 0.0f) {
+                    line.direction = vdiv(V(relativePosition.x * leg - relativePosition.y * combinedRadius,
+                                            relativePosition.x * combinedRadius + relativePosition.y * leg), distSq);
+                } else {
+                    line.direction = vneg(vdiv(V(relativePosition.x * leg + relativePosition.y * combinedRadius,
+                                                 -relativePosition.x * combinedRadius + relativePosition.y * leg), distSq));
+                }
+                const float dotProduct2 = vdot(relativeVelocity, line.direction);
+                u = vsub(vscale(dotProduct2, line.direction), relativeVelocity);
+            }
+        } else {
+            const float invTimeStep = 1.0f / p.time_step_f;
+            const v2 w = vsub(relativeVelocity, vscale(invTimeStep, relativePosition));
+            const float wLength = vabs(w);
+            const v2 unitW = vdiv(w, wLength);
+            line.direction = V(unitW.y, -unitW.x);
+            u = vscale(combinedRadius * invTimeStep - wLength, unitW);
+        }
+        line.point = vadd(vel, vscale(0.5f, u));
+        lines[k] = line;
+    }
+
+    v2 newV;
+    const int lineFail = lp2(lines, nn, max_speed, pref, false, newV);
+    if (lineFail < nn) lp3(lines, nn, lineFail, max_speed, newV);
+    out_vx = newV.x;
+    out_vy = newV.y;
+}
+
+// K1: one thread per (human, env); consecutive threads = consecutive envs (coalesced SoA reads).
+__global__ void __launch_bounds__(128) orca_humans_kernel(EnvParams p, const double *__restrict__ st,
+                                                          const uint8_t *__restrict__ frozen,
+                                                          double *__restrict__ human_v)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int E = p.d.E, H = p.d.H;
+    if (tid >= E * H) return;
+    const int h = tid / E, e = tid - h * E;
+    if (frozen[e]) return;
+    // others = humans 1..H except self, in list order (crowd_sim.py:339), robot last if visible (:340-341)
+    const int cand[2] = {1, 1};
+    float vx, vy;
+    orca_solve(p, st, e, h + 1, cand, H - 1, p.robot_visible ? 0 : -1, p.human_safety_space, vx, vy);
+    human_v[(size_t)(0 * H + h) * E + e] = (double)vx;
+    human_v[(size_t)(1 * H + h) * E + e] = (double)vy;
+}
+
+// Robot with an ORCA policy (imitation learning, train.py:157-166): self = robot, others = all humans.
+__global__ void __launch_bounds__(128) orca_robot_kernel(EnvParams p, const double *__restrict__ st,
+                                                         const uint8_t *__restrict__ frozen, double safety_space,
+                                                         double *__restrict__ action_xy,
+                                                         int32_t *__restrict__ action_idx)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.d.E || frozen[e]) return;
+    const int cand[2] = {1, 0};
+    float vx, vy;
+    orca_solve(p, st, e, 0, cand, p.d.H, -1, safety_space, vx, vy);
+    action_xy[e] = (double)vx;
+    action_xy[p.d.E + e] = (double)vy;
+    action_idx[e] = -1;
+}
+
+// K2: CrowdSim.step for one env per thread (crowd_sim.py:344-434).
+__global__ void __launch_bounds__(128) step_kernel(EnvParams p, double *__restrict__ st, double *__restrict__ time,
+                                                   const double *__restrict__ human_v,
+                                                   const double *__restrict__ act, int act_aos, int update,
+                                                   double *__restrict__ reward_o, uint8_t *__restrict__ done_o,
+                                                   uint8_t *__restrict__ info_o, double *__restrict__ dmin_o,
+                                                   double *__restrict__ next_obs, uint8_t *__restrict__ frozen,
+                                                   EnvAccum acc)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const EnvDims d = p.d;
+    if (e >= d.E) return;
+    if (frozen[e]) { reward_o[e] = 0.0; done_o[e] = 1; return; }
+    const int E = d.E, H = d.H;
+    const double ax = act_aos ? act[2 * (size_t)e] : act[e];
+    const double ay = act_aos ? act[2 * (size_t)e + 1] : act[E + e];
+    const double dt = p.time_step;
+    const double t = time[e];
+    auto ag = [&](int f, int a) { return st[st_idx(d, f, a, e)]; };
+    const StepOutcome oc = cn_step_outcome(p, ag, H, t, ax, ay);
+    const double reward = oc.reward, dmin = oc.dmin;
+    const int done = oc.done, info = oc.info;
+    const double endx = ag(F_PX, 0) + ax * dt, endy = ag(F_PY, 0) + ay * dt;
+    reward_o[e] = reward; done_o[e] = (uint8_t)done; info_o[e] = (uint8_t)info; dmin_o[e] = dmin;
+
+    if (update) {
+        // crowd_sim.py:414-417, agent.py:122-135 (holonomic)
+        st[st_idx(d, F_PX, 0, e)] = endx;
+        st[st_idx(d, F_PY, 0, e)] = endy;
+        st[st_idx(d, F_VX, 0, e)] = ax;
+        st[st_idx(d, F_VY, 0, e)] = ay;
+        for (int h = 1; h <= H; ++h) {
+            const double hvx = human_v[(size_t)(0 * H + h - 1) * E + e];
+            const double hvy = human_v[(size_t)(1 * H + h - 1) * E + e];
+            st[st_idx(d, F_PX, h, e)] = st[st_idx(d, F_PX, h, e)] + hvx * dt;
+            st[st_idx(d, F_PY, h, e)] = st[st_idx(d, F_PY, h, e)] + hvy * dt;
+            st[st_idx(d, F_VX, h, e)] = hvx;
+            st[st_idx(d, F_VY, h, e)] = hvy;
+        }
+        const double tn = t + dt;
+        time[e] = tn;
+        // explorer.py counters
+        const int k = acc.ep_steps[e];
+        const double disc = pow(p.gamma, (double)k * dt * st[st_idx(d, F_VPREF, 0, e)]);
+        const double ret = acc.ep_return[e] + disc * reward;
+        acc.steps[e] += 1;
+        if (info == CN_DANGER) { acc.too_close[e] += 1; acc.sum_min_dist[e] += dmin; }
+        if (done) {
+            acc.episodes[e] += 1;
+            if (info == CN_REACHGOAL) { acc.success[e] += 1; acc.sum_success_time[e] += tn; }
+            else if (info == CN_COLLISION) { acc.collision[e] += 1; acc.sum_collision_time[e] += tn; }
+            else { acc.timeout[e] += 1; acc.sum_timeout_time[e] += p.time_limit; }
+            acc.sum_return[e] += ret;
+            acc.ep_return[e] = 0.0; acc.ep_steps[e] = 0;
+            if (!p.auto_reset) frozen[e] = 1;
+        } else {
+            acc.ep_return[e] = ret; acc.ep_steps[e] = k + 1;
+        }
+    } else {
+        // onestep_lookahead observation (crowd_sim.py:428-430, agent.py:63-74)
+        for (int h = 1; h <= H; ++h) {
+            const double hvx = human_v[(size_t)(0 * H + h - 1) * E + e];
+            const double hvy = human_v[(size_t)(1 * H + h - 1) * E + e];
+            next_obs[(size_t)(0 * H + h - 1) * E + e] = st[st_idx(d, F_PX, h, e)] + hvx * dt;
+            next_obs[(size_t)(1 * H + h - 1) * E + e] = st[st_idx(d, F_PY, h, e)] + hvy * dt;
+            next_obs[(size_t)(2 * H + h - 1) * E + e] = hvx;
+            next_obs[(size_t)(3 * H + h - 1) * E + e] = hvy;
+            next_obs[(size_t)(4 * H + h - 1) * E + e] = st[st_idx(d, F_R, h, e)];
+        }
+    }
+}
+
+// CrowdSim.reset on the device: crowd_sim.py:165-217 distributions and rejection rule; Philox stream
+// keyed by (seed, global env id, episode counter).  One thread per env.
+__global__ void __launch_bounds__(128) reset_kernel(EnvParams p, double *__restrict__ st, double *__restrict__ time,
+                                                    const uint8_t *__restrict__ done, int only_done,
+                                                    uint8_t *__restrict__ frozen, EnvAccum acc)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const EnvDims d = p.d;
+    if (e >= d.E) return;
+    if (only_done && !done[e]) return;
+    PhiloxStream rng;
+    rng.init(p.seed, (uint64_t)(p.env_id_offset + e), acc.episode_ctr[e], 0u);
+    acc.episode_ctr[e] += 1;
+    const double PI = 3.141592653589793;
+    // robot (crowd_sim.py:284)
+    st[st_idx(d, F_PX, 0, e)] = 0.0; st[st_idx(d, F_PY, 0, e)] = -p.circle_radius;
+    st[st_idx(d, F_VX, 0, e)] = 0.0; st[st_idx(d, F_VY, 0, e)] = 0.0;
+    st[st_idx(d, F_GX, 0, e)] = 0.0; st[st_idx(d, F_GY, 0, e)] = p.circle_radius;
+    st[st_idx(d, F_R, 0, e)] = p.robot_radius; st[st_idx(d, F_VPREF, 0, e)] = p.robot_v_pref;
+    const int MAX_TRIES = 4096;
+    for (int i = 1; i <= d.H; ++i) {
+        double px = 0, py = 0, gx = 0, gy = 0;
+        if (p.sim_rule == CN_CIRCLE_CROSSING) {
+            for (int tries = 0; tries < MAX_TRIES; ++tries) {
+                const double angle = rng.next() * PI * 2;
+                const double px_noise = (rng.next() - 0.5) * p.human_v_pref;
+                const double py_noise = (rng.next() - 0.5) * p.human_v_pref;
+                px = p.circle_radius * cos(angle) + px_noise;
+                py = p.circle_radius * sin(angle) + py_noise;
+                bool collide = false;
+                for (int a = 0; a < i; ++a) {
+                    const double min_dist = p.human_radius + st[st_idx(d, F_R, a, e)] + p.discomfort_dist;
+                    if (norm2d(px - st[st_idx(d, F_PX, a, e)], py - st[st_idx(d, F_PY, a, e)]) < min_dist ||
+                        norm2d(px - st[st_idx(d, F_GX, a, e)], py - st[st_idx(d, F_GY, a, e)]) < min_dist) {
+                        collide = true;
+                        break;
+                    }
+                }
+                if (!collide) break;
+            }
+            gx = -px; gy = -py;
+        } else {
+            const double sign = (rng.next() > 0.5) ? -1.0 : 1.0;
+            for (int tries = 0; tries < MAX_TRIES; ++tries) {
+                px = rng.next() * p.square_width * 0.5 * sign;
+                py = (rng.next() - 0.5) * p.square_width;
+                bool collide = false;
+                for (int a = 0; a < i; ++a) {
+                    if (norm2d(px - st[st_idx(d, F_PX, a, e)], py - st[st_idx(d, F_PY, a, e)]) <
+                        p.human_radius + st[st_idx(d, F_R, a, e)] + p.discomfort_dist) { collide = true; break; }
+                }
+                if (!collide) break;
+            }
+            for (int tries = 0; tries < MAX_TRIES; ++tries) {
+                gx = rng.next() * p.square_width * 0.5 * -sign;
+                gy = (rng.next() - 0.5) * p.square_width;
+                bool collide = false;
+                for (int a = 0; a < i; ++a) {
+                    if (norm2d(gx - st[st_idx(d, F_GX, a, e)], gy - st[st_idx(d, F_GY, a, e)]) <
+                        p.human_radius + st[st_idx(d, F_R, a, e)] + p.discomfort_dist) { collide = true; break; }
+                }
+                if (!collide) break;
+            }
+        }
+        st[st_idx(d, F_PX, i, e)] = px; st[st_idx(d, F_PY, i, e)] = py;
+        st[st_idx(d, F_VX, i, e)] = 0.0; st[st_idx(d, F_VY, i, e)] = 0.0;
+        st[st_idx(d, F_GX, i, e)] = gx; st[st_idx(d, F_GY, i, e)] = gy;
+        st[st_idx(d, F_R, i, e)] = p.human_radius; st[st_idx(d, F_VPREF, i, e)] = p.human_v_pref;
+    }
+    time[e] = 0.0;
+    frozen[e] = 0;
+    acc.ep_steps[e] = 0; acc.ep_return[e] = 0.0;
+}
+
+// stage (AoS, E x A1 x 8) <-> state (SoA, 8 x A1 x E)
+__global__ void pack_kernel(EnvDims d, double *__restrict__ st, double *__restrict__ stage, int to_soa)
+{
+    const size_t n = (size_t)d.E * d.A1 * F_COUNT;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        // i indexes the SoA side so that its accesses are coalesced
+        const int e = (int)(i % d.E);
+        const size_t r = i / d.E;
+        const int a = (int)(r % d.A1), f = (int)(r / d.A1);
+        const size_t j = ((size_t)e * d.A1 + a) * F_COUNT + f;
+        if (to_soa) st[i] = stage[j];
+        else stage[j] = st[i];
+    }
+}
+
+__global__ void clear_episode_kernel(int E, uint8_t *frozen, EnvAccum acc, uint8_t *done)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    frozen[e] = 0; done[e] = 0;
+    acc.ep_steps[e] = 0; acc.ep_return[e] = 0.0;
+}
+
+// human_v (2 x H x E) -> E x H x 2 ; next_obs (5 x H x E) -> E x H x 5
+__global__ void transpose_out_kernel(int E, int H, int C, const double *__restrict__ src, double *__restrict__ dst)
+{
+    const size_t n = (size_t)E * H * C;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int e = (int)(i % E);
+        const size_t r = i / E;
+        const int h = (int)(r % H), c = (int)(r / H);
+        dst[((size_t)e * H + h) * C + c] = src[i];
+    }
+}
+
+__global__ void set_actions_kernel(int E, const double *__restrict__ aos, double *__restrict__ action_xy,
+                                   int32_t *__restrict__ action_idx)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    action_xy[e] = aos[2 * (size_t)e];
+    action_xy[E + e] = aos[2 * (size_t)e + 1];
+    action_idx[e] = -1;
+}
+
+}  // namespace
+
+static inline int grid_for(int n, int block) { return (n + block - 1) / block; }
+
+int cn_launch_orca(cn_env *env, cudaStream_t s)
+{
+    const int n = env->p.d.E * env->p.d.H;
+    orca_humans_kernel<<<grid_for(n, 128), 128, 0, s>>>(env->p, env->state, env->frozen, env->human_v);
+    CN_LAUNCH_CHECK();
+    env->orca_valid = 1;
+    return CN_OK;
+}
+
+int cn_launch_robot_orca(cn_env *env, double safety_space, cudaStream_t s)
+{
+    orca_robot_kernel<<<grid_for(env->p.d.E, 128), 128, 0, s>>>(env->p, env->state, env->frozen, safety_space,
+                                                                  env->action_xy, env->action_idx);
+    CN_LAUNCH_CHECK();
+    return CN_OK;
+}
+
+int cn_launch_step(cn_env *env, const double *action_xy_dev, int update, cudaStream_t s)
+{
+    const double *act = action_xy_dev ? action_xy_dev : env->action_xy;
+    step_kernel<<<grid_for(env->p.d.E, 128), 128, 0, s>>>(env->p, env->state, env->time, env->human_v, act,
+                                                            action_xy_dev ? 1 : 0, update, env->reward, env->done,
+                                                            env->info, env->dmin, env->next_obs, env->frozen,
+                                                            env->acc);
+    CN_LAUNCH_CHECK();
+    if (update) env->orca_valid = 0;
+    return CN_OK;
+}
+
+int cn_launch_reset(cn_env *env, int only_done, cudaStream_t s)
+{
+    reset_kernel<<<grid_for(env->p.d.E, 128), 128, 0, s>>>(env->p, env->state, env->time, env->done, only_done,
+                                                             env->frozen, env->acc);
+    CN_LAUNCH_CHECK();
+    env->orca_valid = 0;
+    return CN_OK;
+}
+
+int cn_launch_pack(cn_env *env, int to_soa, cudaStream_t s)
+{
+    const size_t n = (size_t)env->p.d.E * env->p.d.A1 * F_COUNT;
+    int grid = (int)((n + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    pack_kernel<<<grid, 256, 0, s>>>(env->p.d, env->state, env->stage, to_soa);
+    CN_LAUNCH_CHECK();
+    if (to_soa) {
+        clear_episode_kernel<<<grid_for(env->p.d.E, 128), 128, 0, s>>>(env->p.d.E, env->frozen, env->acc, env->done);
+        CN_LAUNCH_CHECK();
+        env->orca_valid = 0;
+    }
+    return CN_OK;
+}
+
+// host-stepped mode: refresh the SoA from the staging buffer but keep episode accumulators / frozen flags
+int cn_launch_pack_keep(cn_env *env, cudaStream_t s)
+{
+    const size_t n = (size_t)env->p.d.E * env->p.d.A1 * F_COUNT;
+    int grid = (int)((n + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    pack_kernel<<<grid, 256, 0, s>>>(env->p.d, env->state, env->stage, 1);
+    CN_LAUNCH_CHECK();
+    env->orca_valid = 0;
+    return CN_OK;
+}
+
+int cn_launch_transpose_out(int E, int H, int C, const double *src, double *dst, cudaStream_t s)
+{
+    const size_t n = (size_t)E * H * C;
+    int grid = (int)((n + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    transpose_out_kernel<<<grid, 256, 0, s>>>(E, H, C, src, dst);
+    CN_LAUNCH_CHECK();
+    return CN_OK;
+}
+
+int cn_launch_set_actions(cn_env *env, const double *aos_dev, cudaStream_t s)
+{
+    set_actions_kernel<<<grid_for(env->p.d.E, 128), 128, 0, s>>>(env->p.d.E, aos_dev, env->action_xy,
+                                                                   env->action_idx);
+    CN_LAUNCH_CHECK();
+    return CN_OK;
+}

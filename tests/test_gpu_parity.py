@@ -1,0 +1,337 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the reference goldens."""
+import numpy as np
+import pytest
+
+from conftest import TRAJ_NAMES, load_traj
+
+pytestmark = pytest.mark.gpu
+
+VALUE_TOL = {"f32": 1e-5, "f16_tc": 1e-3}   # relative to max(1, |v|) (north star: 1e-3 relative)
+
+
+@pytest.fixture(scope="module")
+def mcn():
+    import modelcrowdnav_b200 as m
+    assert m._capi.load().cn_device_count() > 0, "GPU tests need a CUDA device"
+    return m
+
+
+def _scenes(oracle_mod, n, H, rule="circle_crossing", phase="test", start=0):
+    return np.stack([oracle_mod.generate_scene(phase, start + c, human_num=H, rule=rule) for c in range(n)])
+
+
+@pytest.mark.parametrize("H,rule,visible", [(5, "circle_crossing", 0), (10, "square_crossing", 0),
+                                            (5, "circle_crossing", 1), (20, "square_crossing", 0)])
+def test_orca_and_step_bit_exact(mcn, oracle_mod, H, rule, visible):
+    """ORCA velocities, reward/done/info codes and the updated state are bit-exact over 30 steps."""
+    o = oracle_mod
+    E = 96
+    ecfg = o.EnvCfg.default(robot_visible=visible)
+    env = mcn.BatchedCrowdSim(E, H, robot_visible=visible)
+    agents = _scenes(o, E, H, rule)
+    env.set_state(agents)
+    rs = np.random.RandomState(0)
+    table = o.action_space()
+    times = np.zeros(E)
+    infos = set()
+    for step in range(30):
+        env.orca()
+        hv = env.human_actions()
+        acts = table[rs.randint(0, 81, E)]
+        reward, done, info, dmin = env.step(acts, update=True)
+        got, gtimes = env.get_state()
+        for e in range(E):
+            if step > 0 and frozen[e]:
+                continue
+            ohv = o.human_actions(ecfg, agents[e])
+            assert np.array_equal(ohv, hv[e]), (step, e)
+            r, d, i, dm = o.step_outcome(ecfg, agents[e], times[e], acts[e])
+            assert (r, d, i) == (reward[e], bool(done[e]), int(info[e])), (step, e)
+            if i == o.DANGER:
+                assert dm == dmin[e]
+            times[e] = o.apply_step(ecfg, agents[e], times[e], acts[e], ohv)
+            infos.add(i)
+        frozen = done.astype(bool) if step == 0 else (frozen | done.astype(bool))
+        live = ~frozen | done.astype(bool)
+        assert np.array_equal(got[live], agents[live]) and np.array_equal(gtimes[live], times[live])
+    assert {o.NOTHING, o.DANGER} <= infos
+    env.close()
+
+
+def test_step_ladder_edge_cases(mcn, oracle_mod):
+    """Timeout > Collision > ReachGoal > Danger > Nothing priority, degenerate segment, update=False."""
+    o = oracle_mod
+    ecfg = o.EnvCfg.default()
+    base = o.generate_scene("test", 0)
+    cases, times, acts = [], [], []
+    a = base.copy(); cases.append(a); times.append(24.0); acts.append([0.0, 1.0])                 # timeout
+    a = base.copy(); a[1, :2] = a[0, :2] + [0.5, 0.0]; cases.append(a); times.append(0.0); acts.append([1.0, 0.0])  # collision
+    a = base.copy(); a[0, :2] = [0.0, 3.9]; cases.append(a); times.append(3.0); acts.append([0.0, 0.4])  # reach goal
+    a = base.copy(); a[1, :2] = a[0, :2] + [0.75, 0.0]; cases.append(a); times.append(0.0); acts.append([0.0, 0.0])  # danger, static
+    a = base.copy(); a[0, :2] = [0.0, 3.9]; a[1, :2] = a[0, :2] + [0.3, 0]; cases.append(a); times.append(24.0); acts.append([0.0, 0.4])  # all at once
+    a = base.copy(); cases.append(a); times.append(0.0); acts.append([0.0, 0.0])                  # nothing
+    E = len(cases)
+    env = mcn.BatchedCrowdSim(E, 5)
+    agents = np.stack(cases); times = np.array(times); acts = np.array(acts)
+    env.set_state(agents, times)
+    env.orca()
+    reward, done, info, dmin = env.step(acts, update=False)
+    obs = env.next_obs()
+    got, gt = env.get_state()
+    assert np.array_equal(got, agents) and np.array_equal(gt, times)       # update=False does not mutate
+    hv = env.human_actions()
+    for e in range(E):
+        r, d, i, dm = o.step_outcome(ecfg, agents[e], times[e], acts[e])
+        assert (r, d, i) == (reward[e], bool(done[e]), int(info[e])), e
+        # crowd_sim.py:428-430 / agent.py:63-74
+        assert np.array_equal(obs[e, :, 0:2], agents[e, 1:, 0:2] + hv[e] * 0.25)
+        assert np.array_equal(obs[e, :, 2:4], hv[e]) and np.array_equal(obs[e, :, 4], agents[e, 1:, 6])
+    assert list(info) == [o.TIMEOUT, o.COLLISION, o.REACHGOAL, o.DANGER, o.TIMEOUT, o.NOTHING]
+    env.close()
+
+
+@pytest.mark.parametrize("precision", ["f32", "f16_tc"])
+@pytest.mark.parametrize("name", TRAJ_NAMES)
+def test_golden_trajectories(mcn, oracle_mod, weights0, name, precision):
+    """Teacher-forced replay of the reference's own episodes (tests/golden, scripts/gen_golden.py)."""
+    tr = load_traj(name)
+    H = tr["H"]
+    states, times, recs = [], [], []
+    for case, rec in tr["cases"].items():
+        for t in range(len(rec["time"])):
+            states.append(rec["agents"][t]); times.append(rec["time"][t]); recs.append((rec, t))
+    E = len(states)
+    env = mcn.BatchedCrowdSim(E, H, robot_visible=tr["robot_visible"])
+    pol = mcn.BatchedSARL(precision=precision)
+    pol.load_weights(weights0)
+    assert np.array_equal(pol.action_table, recs[0][0]["table"])            # bit-exact action table
+    env.set_state(np.stack(states), np.array(times))
+    env.orca()
+    hv = env.human_actions()
+    pol.lookahead(env, query_env=tr["query_env"])
+    best, values = pol.read(env)
+    # step with the REFERENCE's action so the state transition is compared like for like
+    acts = np.stack([rec["action"][t] for rec, t in recs])
+    reward, done, info, dmin = env.step(acts, update=True)
+    got, gt = env.get_state()
+    tol = VALUE_TOL[precision]
+    agree = total = 0
+    for e, (rec, t) in enumerate(recs):
+        assert np.array_equal(hv[e], rec["human_v"][t]), (name, e)
+        ref_v = rec["values"][t]
+        assert np.max(np.abs(values[e] - ref_v)) <= tol * max(1.0, np.max(np.abs(ref_v))), (name, e)
+        top2 = np.sort(ref_v)[-2:]
+        if top2[1] - top2[0] > 2 * tol:                                     # ties excluded
+            total += 1
+            agree += int(best[e] == rec["best"][t])
+        assert (reward[e], bool(done[e]), int(info[e])) == (rec["reward"][t], bool(rec["done"][t]), int(rec["info"][t]))
+        if t + 1 < len(rec["time"]):
+            assert np.array_equal(got[e], rec["agents"][t + 1]) and gt[e] == rec["time"][t + 1]
+    assert total == 0 or agree / total >= 0.999, (agree, total)
+    env.close(); pol.close()
+
+
+@pytest.mark.parametrize("precision", ["f32", "f16_tc"])
+@pytest.mark.parametrize("H,rule,query_env", [(5, "circle_crossing", 0), (5, "circle_crossing", 1),
+                                              (10, "square_crossing", 0), (3, "circle_crossing", 0)])
+def test_lookahead_vs_oracle(mcn, oracle_mod, weights0, H, rule, query_env, precision):
+    """81 action values and the argmax against the oracle on evolving states (not only reset states)."""
+    o = oracle_mod
+    E = 48
+    ecfg, scfg = o.EnvCfg.default(), o.SarlCfg.default()
+    env = mcn.BatchedCrowdSim(E, H)
+    pol = mcn.BatchedSARL(precision=precision)
+    pol.load_weights(weights0)
+    agents = _scenes(o, E, H, rule, phase="val")
+    env.set_state(agents)
+    tol = VALUE_TOL[precision]
+    agree = total = 0
+    for step in range(6):
+        env.orca()
+        pol.lookahead(env, query_env=query_env)
+        best, values = pol.read(env)
+        hv = env.human_actions()
+        state, times = env.get_state()
+        for e in range(E):
+            obest, ovals, reached = o.lookahead(ecfg, scfg, weights0, state[e], times[e], pol.action_table,
+                                                query_env, hv[e])
+            assert np.max(np.abs(values[e] - ovals)) <= tol * max(1.0, np.max(np.abs(ovals))), (step, e)
+            top2 = np.sort(ovals)[-2:]
+            if top2[1] - top2[0] > 2 * tol:
+                total += 1
+                agree += int(best[e] == obest)
+        env.step(update=True, read=False)      # advance with the GPU's own chosen actions
+    assert total > 0 and agree / total >= 0.999, (agree, total)
+    env.close(); pol.close()
+
+
+def test_reach_destination_and_untrained(mcn, oracle_mod, weights0):
+    """policy.py:43-49 early exit (action 0) and the all-NaN ValueError (multi_human_rl.py:57-58)."""
+    o = oracle_mod
+    agents = _scenes(o, 4, 5)
+    agents[1, 0, :2] = [0.05, 3.9]            # robot already within its radius of the goal
+    env = mcn.BatchedCrowdSim(4, 5)
+    pol = mcn.BatchedSARL()
+    pol.load_weights(weights0)
+    env.set_state(agents)
+    pol.lookahead(env)
+    best, _ = pol.read(env)
+    assert best[1] == 0
+    w = weights0.copy(); w[-1] = np.nan       # mlp3.6.bias = NaN -> every value NaN
+    pol.load_weights(w)
+    pol.lookahead(env)
+    with pytest.raises(mcn.CrowdNavError) as ei:
+        pol.read(env)
+    assert ei.value.code == mcn._capi.CN_EVALUE and "not well trained" in str(ei.value)
+    env.close(); pol.close()
+
+
+def test_transform_and_forward(mcn, oracle_mod, weights0, units):
+    """MultiHumanRL.transform and ValueNetwork.forward on device tensors vs reference fixtures."""
+    import torch
+    o = oracle_mod
+    pol = mcn.BatchedSARL()
+    pol.load_weights(weights0)
+    for H in (5, 10):
+        x = torch.from_numpy(units["vnet_in_h%d" % H]).cuda()
+        v = pol.forward(x).cpu().numpy()
+        ref = units["vnet_out_h%d" % H]
+        assert np.max(np.abs(v - ref)) <= 1e-5 * max(1.0, np.max(np.abs(ref)))
+    E, H = 32, 5
+    env = mcn.BatchedCrowdSim(E, H)
+    agents = _scenes(o, E, H)
+    agents[:, :, 2:4] = np.random.RandomState(1).uniform(-1, 1, (E, H + 1, 2))
+    env.set_state(agents)
+    t = pol.transform(env).cpu().numpy()
+    for e in range(E):
+        assert np.max(np.abs(t[e] - o.transform(agents[e]))) < 5e-6
+    env.close(); pol.close()
+
+
+def test_robot_orca_il(mcn, oracle_mod):
+    """Robot driven by ORCA with safety_space 0.15 (imitation learning, train.py:157-166)."""
+    o = oracle_mod
+    E, H = 64, 5
+    ecfg = o.EnvCfg.default()
+    env = mcn.BatchedCrowdSim(E, H)
+    agents = _scenes(o, E, H, phase="train")
+    env.set_state(agents)
+    for step in range(10):
+        env.orca(); env.robot_orca(0.15)
+        env.step(update=True, read=False)
+        for e in range(E):
+            hv = o.human_actions(ecfg, agents[e])
+            ra = o.robot_orca_action(ecfg, agents[e], 0.15)
+            o.apply_step(ecfg, agents[e], 0.0, ra, hv)
+        got, _ = env.get_state()
+        assert np.array_equal(got, agents), step
+    env.close()
+
+
+def test_episode_stats_and_freeze(mcn, oracle_mod, weights0):
+    """Explorer counters accumulated on the device (explorer.py:41-51,92-141); finished envs freeze."""
+    o = oracle_mod
+    E, H = 64, 5
+    ecfg, scfg = o.EnvCfg.default(), o.SarlCfg.default()
+    env = mcn.BatchedCrowdSim(E, H)
+    pol = mcn.BatchedSARL()
+    pol.load_weights(weights0)
+    agents = _scenes(o, E, H)
+    agents[:8, 0, :2] = [0.0, 3.0]             # some robots close to the goal -> ReachGoal quickly
+    env.set_state(agents)
+    ref = dict(episodes=0, success=0, collision=0, timeout=0, steps=0, too_close=0, sum_min_dist=0.0,
+               sum_success_time=0.0, sum_collision_time=0.0, sum_timeout_time=0.0, sum_return=0.0)
+    times = np.zeros(E); done_flags = np.zeros(E, bool); ep_ret = np.zeros(E); ep_steps = np.zeros(E, int)
+    for step in range(12):
+        mcn.rollout_step(pol, env, query_env=False)
+        best, _ = pol.read(env, values=False)
+        for e in range(E):
+            if done_flags[e]:
+                continue
+            hv = o.human_actions(ecfg, agents[e])
+            act = pol.action_table[best[e]]
+            r, d, i, dm = o.step_outcome(ecfg, agents[e], times[e], act)
+            times[e] = o.apply_step(ecfg, agents[e], times[e], act, hv)
+            ep_ret[e] += pow(0.9, ep_steps[e] * 0.25 * 1.0) * r; ep_steps[e] += 1
+            ref["steps"] += 1
+            if i == o.DANGER:
+                ref["too_close"] += 1; ref["sum_min_dist"] += dm
+            if d:
+                done_flags[e] = True; ref["episodes"] += 1; ref["sum_return"] += ep_ret[e]
+                key = {o.REACHGOAL: "success", o.COLLISION: "collision", o.TIMEOUT: "timeout"}[i]
+                ref[key] += 1
+                ref["sum_%s_time" % key] += 25.0 if i == o.TIMEOUT else times[e]
+    st = env.stats()
+    got, _ = env.get_state()
+    assert np.array_equal(got, agents)
+    for k, v in ref.items():
+        assert st[k] == pytest.approx(v, rel=1e-12, abs=1e-12), k
+    assert st["success"] >= 1
+    env.close(); pol.close()
+
+
+def test_device_reset_properties(mcn):
+    """Device-side reset: scene invariants of crowd_sim.py:165-217 and shard invariance (global env id)."""
+    E, H = 512, 5
+    for rule, name in ((0, "circle"), (1, "square")):
+        env = mcn.BatchedCrowdSim(E, H, sim_rule=rule, seed=7)
+        env.reset_device()
+        a, t = env.get_state()
+        assert np.all(t == 0) and np.all(a[:, :, 2:4] == 0)
+        assert np.all(a[:, 0, :2] == [0, -4]) and np.all(a[:, 0, 4:6] == [0, 4])
+        if rule == 0:
+            assert np.array_equal(a[:, 1:, 4:6], -a[:, 1:, 0:2])
+            r = np.hypot(a[:, 1:, 0], a[:, 1:, 1])
+            assert np.all(r > 4 - 0.75) and np.all(r < 4 + 0.75)
+        else:
+            assert np.all(np.abs(a[:, 1:, 0]) <= 5) and np.all(np.abs(a[:, 1:, 1]) <= 5)
+            assert np.all(a[:, 1:, 0] * a[:, 1:, 4] <= 0)          # goal on the other side
+        for i in range(1, H + 1):                                   # min separation 0.8 vs earlier agents
+            for j in range(i):
+                d = np.hypot(a[:, i, 0] - a[:, j, 0], a[:, i, 1] - a[:, j, 1])
+                assert np.all(d >= 0.8)
+        # shard invariance: envs [256, 512) generated alone equal the second half
+        env2 = mcn.BatchedCrowdSim(E // 2, H, sim_rule=rule, seed=7, env_id_offset=E // 2)
+        env2.reset_device()
+        b, _ = env2.get_state()
+        assert np.array_equal(b, a[E // 2:])
+        env.close(); env2.close()
+
+
+def test_auto_reset_rollout_runs(mcn, weights0):
+    """Throughput mode: auto_reset keeps every env alive; counters add up."""
+    E, H = 256, 5
+    env = mcn.BatchedCrowdSim(E, H, auto_reset=1, seed=3)
+    pol = mcn.BatchedSARL()
+    pol.load_weights(weights0)
+    env.reset_device()
+    n = 110
+    for _ in range(n):
+        mcn.rollout_step(pol, env)
+    st = env.stats()
+    assert st["steps"] == E * n
+    assert st["episodes"] == st["success"] + st["collision"] + st["timeout"] >= E   # >= 1 timeout each (97 steps)
+    a, t = env.get_state()
+    assert np.all(np.isfinite(a)) and np.all(t <= 25.0)
+    env.close(); pol.close()
+
+
+def test_host_step_matches_device_step(mcn, oracle_mod, weights0):
+    """cn_rollout_step_host (HOST buffers, e2e path) == device-resident rollout."""
+    o = oracle_mod
+    E, H = 128, 5
+    agents = _scenes(o, E, H)
+    env_a = mcn.BatchedCrowdSim(E, H); env_b = mcn.BatchedCrowdSim(E, H)
+    pol = mcn.BatchedSARL(); pol.load_weights(weights0)
+    env_a.set_state(agents); env_b.set_state(agents)
+    buf = mcn.HostStepBuffers(env_b)
+    buf.agents_in[...] = agents; buf.times_in[...] = 0
+    for step in range(5):
+        mcn.rollout_step(pol, env_a)
+        ra, da, ia, _ = env_a.read_outputs()
+        mcn.rollout_step_host(pol, env_b, buf)
+        sa, ta = env_a.get_state()
+        assert np.array_equal(sa, buf.agents_out) and np.array_equal(ta, buf.times_out)
+        assert np.array_equal(ra, buf.reward) and np.array_equal(da, buf.done) and np.array_equal(ia, buf.info)
+        buf.agents_in[...] = buf.agents_out; buf.times_in[...] = buf.times_out
+    env_a.close(); env_b.close(); pol.close()
