@@ -1,11 +1,677 @@
-// lookahead_tc.cu -- SARL lookahead on tcgen05 tensor cores (CN_PREC_F16_TC). Placeholder until the
-// UMMA kernel lands: creating a policy with this precision fails loudly, nothing falls back.
-#include "cn_common.cuh"
+// lookahead_tc.cu -- SARL one-step lookahead on tcgen05 tensor cores (CN_PREC_F16_TC).
+//
+// fp16 operands, fp32 accumulation in TMEM, M = 128 rows per UMMA.  Two persistent kernels (1 CTA / SM):
+//
+//  tc_rows_kernel   rows = (env, action, human).  Per 128-row tile, all on chip:
+//       propagate + reward + rotate  -> X (13 features, split hi+lo fp16 so layer 1 sees ~22-bit inputs)
+//       mlp1.0 -> mlp1.2 -> {mlp2.0 -> mlp2.2 ; attention.0 on [mlp1_out | group mean] -> attention.2}
+//       attention.4 (fp32 dot) -> masked softmax over the humans of a group -> weighted feature
+//       -> joint state J (fp16, 160 B per (env, action)) to HBM, already in UMMA operand order
+//     All six GEMM stages chain smem -> tcgen05.mma -> TMEM -> tcgen05.ld -> smem; the full fp16 weight set
+//     of the row network (157 KB) stays resident in shared memory for the life of the CTA.
+//  tc_mlp3_kernel   rows = (env, action).  mlp3.0 -> .2 -> .4 on tensor cores, .6 as an fp32 dot,
+//       value = reward + gamma_bar * V  -> values[E][A]; the shared argmax kernel follows.
+//
+// Biases ride inside the GEMMs: every activation tile carries two constant-one columns and the weight
+// images hold bias_hi / bias_lo (fp16 split) in the matching K rows, so epilogues are pure
+// tcgen05.ld -> cvt.rn.relu.f16x2 -> st.shared.
+//
+// Reference (file:line relative to the reference root): see lookahead_f32.cu; the network is
+// crowd_nav/policy/sarl.py:28-65 with the default [sarl] dims of crowd_nav/configs/policy.config:41-49.
+#include "env_math.cuh"
+#include "umma.cuh"
 
-int cn_tc_init(cn_policy *p) { (void)p; cn_set_error("CN_PREC_F16_TC is not built yet"); return CN_EUNSUPPORTED; }
-void cn_tc_destroy(cn_policy *p) { (void)p; }
-int cn_tc_load_weights(cn_policy *p, const float *flat_host, cudaStream_t s) { (void)p; (void)flat_host; (void)s; return CN_EUNSUPPORTED; }
+#include <cuda_fp16.h>
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+int cn_lookahead_prepare(cn_policy *p, cn_env *env, cudaStream_t s);
+int cn_lookahead_argmax(cn_policy *p, cn_env *env, double epsilon, cudaStream_t s);
+
+namespace {
+
+using namespace umma;
+
+// ---- padded GEMM shapes (default SARL dims) ---------------------------------------------------------
+constexpr int K_X = 32;     // 13 hi | 1 1 0 | 13 lo | 0 0 0
+constexpr int N_H1 = 160;   // 150 + ones(150,151)
+constexpr int N_M1 = 112;   // 100 + ones(100,101)
+constexpr int N_F = 64;     // 50
+constexpr int K_A1 = 224;   // [mlp1_out 112 | group mean 112]
+constexpr int K_J = 80;     // 50 weighted | 6 pad | 6 self_hi 1 1 | 6 self_lo 0 0 | 8 pad
+constexpr int ROWS = 128;
+
+__host__ __device__ constexpr uint32_t bytes_of(int rows, int K) { return (uint32_t)rows * K * 2; }
+// weight image of tc_rows_kernel
+constexpr uint32_t OFF_W1 = 0;
+constexpr uint32_t OFF_W2 = OFF_W1 + bytes_of(N_H1, K_X);
+constexpr uint32_t OFF_W3 = OFF_W2 + bytes_of(N_M1, N_H1);
+constexpr uint32_t OFF_W4 = OFF_W3 + bytes_of(N_M1, N_M1);
+constexpr uint32_t OFF_WA1 = OFF_W4 + bytes_of(N_F, N_M1);
+constexpr uint32_t OFF_WA2 = OFF_WA1 + bytes_of(N_M1, K_A1);
+constexpr uint32_t OFF_TAILA = OFF_WA2 + bytes_of(N_M1, N_M1);   // fp32: attention.4 weight[100], bias
+constexpr uint32_t TAIL_BYTES = 416;
+constexpr uint32_t IMG_A_BYTES = OFF_TAILA + TAIL_BYTES;
+// weight image of tc_mlp3_kernel
+constexpr uint32_t OFF_M1 = 0;
+constexpr uint32_t OFF_M2 = OFF_M1 + bytes_of(N_H1, K_J);
+constexpr uint32_t OFF_M3 = OFF_M2 + bytes_of(N_M1, N_H1);
+constexpr uint32_t OFF_TAILB = OFF_M3 + bytes_of(N_M1, N_M1);    // fp32: mlp3.6 weight[100], bias
+constexpr uint32_t IMG_B_BYTES = OFF_TAILB + TAIL_BYTES;
+
+// shared memory maps
+constexpr uint32_t A_BUFA = (IMG_A_BYTES + 127) & ~127u;                 // 128 x 160 fp16
+constexpr uint32_t A_BUFB = A_BUFA + bytes_of(ROWS, N_H1);               // 128 x 112 fp16
+constexpr uint32_t A_MISC = A_BUFB + bytes_of(ROWS, N_M1);               // S[128] f32, mbar, tmem ptr
+constexpr uint32_t A_SMEM = A_MISC + 512 + 16;
+constexpr uint32_t B_BUFJ = (IMG_B_BYTES + 127) & ~127u;                 // 128 x 80 fp16
+constexpr uint32_t B_BUFU0 = B_BUFJ + bytes_of(ROWS, K_J);
+constexpr uint32_t B_BUFU1 = B_BUFU0 + bytes_of(ROWS, N_H1);
+constexpr uint32_t B_MISC = B_BUFU1 + bytes_of(ROWS, N_M1);
+constexpr uint32_t B_SMEM = B_MISC + 16;
+static_assert(A_SMEM <= 232448, "tc_rows_kernel exceeds 227 KB of shared memory");
+constexpr uint32_t J_TILE_BYTES = bytes_of(ROWS, K_J);
+
+constexpr int kTmemCols = 256;
+
+struct TcState {
+    uint8_t *img_a, *img_b;   // device weight images
+    uint8_t *J;               // joint-state tiles
+    double *rew;              // NG rewards
+    size_t cap_groups;
+    int num_sms;
+};
+
+__device__ __forceinline__ void copy_image_to_smem(uint8_t *dst, const uint8_t *__restrict__ src, uint32_t bytes)
+{
+    for (uint32_t i = threadIdx.x * 16; i < bytes; i += blockDim.x * 16)
+        *reinterpret_cast<uint4 *>(dst + i) = __ldg(reinterpret_cast<const uint4 *>(src + i));
+}
+
+__device__ __forceinline__ uint32_t h2(float lo, float hi) { return pack_f16x2(lo, hi); }
+
+// split x into fp16 hi + fp16 lo (x ~ hi + lo to ~22 bits)
+__device__ __forceinline__ void split_hl(float x, float &hi, float &lo)
+{
+    hi = __half2float(__float2half_rn(x));
+    lo = x - hi;
+}
+
+// =====================================================================================================
+// kernel A: the per-(env, action, human) row network
+// =====================================================================================================
+__global__ void __launch_bounds__(128, 1)
+tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restrict__ time,
+               const double *__restrict__ human_v, const double *__restrict__ actions, int A, int query_env,
+               const uint8_t *__restrict__ wimg, uint8_t *__restrict__ J, double *__restrict__ rew, int NG, int G,
+               int ntiles)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const EnvDims ed = p.d;
+    const int H = ed.H, A1 = ed.A1;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint8_t *bufA = smem + A_BUFA, *bufB = smem + A_BUFB;
+    float *S = reinterpret_cast<float *>(smem + A_MISC);
+    const uint32_t mbar = smem_u32(smem + A_MISC + 512);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + A_MISC + 512 + 8);
+    const float *tail = reinterpret_cast<const float *>(smem + OFF_TAILA);
+
+    copy_image_to_smem(smem, wimg, IMG_A_BYTES);
+    if (tid == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t sW1 = smem_u32(smem + OFF_W1), sW2 = smem_u32(smem + OFF_W2), sW3 = smem_u32(smem + OFF_W3);
+    const uint32_t sW4 = smem_u32(smem + OFF_W4), sWA1 = smem_u32(smem + OFF_WA1), sWA2 = smem_u32(smem + OFF_WA2);
+    const uint32_t sA = smem_u32(bufA), sB = smem_u32(bufB);
+    uint32_t phase = 0;
+    const int rows = G * H;
+    const int slot_doubles = F_COUNT * A1 + 2 * H + 1;
+    const double dt = p.time_step;
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int g0 = tile * G;
+        const int e_first = g0 / A;
+        int g_last = g0 + G - 1;
+        if (g_last >= NG) g_last = NG - 1;
+        const int nslots = g_last / A - e_first + 1;
+        // ---- P0a: stage the (<= 3) environments this tile touches (bufA is free here) ----
+        double *slots = reinterpret_cast<double *>(bufA);
+        for (int i = tid; i < nslots * slot_doubles; i += blockDim.x) {
+            const int sl = i / slot_doubles, j = i - sl * slot_doubles;
+            const int e = e_first + sl;
+            double v;
+            if (j < F_COUNT * A1) { const int a = j / F_COUNT, f = j - a * F_COUNT; v = st[st_idx(ed, f, a, e)]; }
+            else if (j < F_COUNT * A1 + 2 * H) {
+                const int q = j - F_COUNT * A1, h = q >> 1, c = q & 1;
+                v = query_env ? human_v[(size_t)(c * H + h) * ed.E + e] : 0.0;
+            } else v = time[e];
+            slots[i] = v;
+        }
+        __syncthreads();
+        // ---- P0b: rewards (one thread per group), features (one thread per row) ----
+        if (tid < G && g0 + tid < NG) {
+            const int g = g0 + tid, e = g / A, a = g - e * A;
+            const double *sv = slots + (size_t)(e - e_first) * slot_doubles;
+            auto ag = [&](int f, int agent) { return sv[agent * F_COUNT + f]; };
+            const double ax = actions[2 * a], ay = actions[2 * a + 1];
+            double reward;
+            if (query_env) {
+                reward = cn_step_outcome(p, ag, H, sv[slot_doubles - 1], ax, ay).reward;   // crowd_sim.py:325-329
+            } else {
+                // multi_human_rl.py:65-88
+                const double npx = ag(F_PX, 0) + ax * dt, npy = ag(F_PY, 0) + ay * dt, rr = ag(F_R, 0);
+                double dmin = INFINITY;
+                bool collision = false;
+                for (int h = 1; h <= H; ++h) {
+                    const double nhx = ag(F_PX, h) + ag(F_VX, h) * dt, nhy = ag(F_PY, h) + ag(F_VY, h) * dt;
+                    const double dist = norm2d(npx - nhx, npy - nhy) - rr - ag(F_R, h);
+                    if (dist < 0) { collision = true; break; }
+                    if (dist < dmin) dmin = dist;
+                }
+                const bool reaching_goal = norm2d(npx - ag(F_GX, 0), npy - ag(F_GY, 0)) < rr;
+                if (collision) reward = -0.25;
+                else if (reaching_goal) reward = 1;
+                else if (dmin < 0.2) reward = (dmin - 0.2) * 0.5 * dt;
+                else reward = 0;
+            }
+            rew[g] = reward;
+        }
+        {
+            const int r = tid;
+            uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0, c2 = c0, c3 = c0;
+            const int gl = r / H, h = r - gl * H, g = g0 + gl;
+            if (r < rows && g < NG) {
+                const int e = g / A, a = g - e * A;
+                const double *sv = slots + (size_t)(e - e_first) * slot_doubles;
+                auto ag = [&](int f, int agent) { return sv[agent * F_COUNT + f]; };
+                const double ax = actions[2 * a], ay = actions[2 * a + 1];
+                double hvx, hvy;
+                if (query_env) { hvx = sv[F_COUNT * A1 + 2 * h]; hvy = sv[F_COUNT * A1 + 2 * h + 1]; }   // agent.py:63-74
+                else { hvx = ag(F_VX, h + 1); hvy = ag(F_VY, h + 1); }                                  // cadrl.py:107-109
+                float s[14], o[13];
+                s[0] = (float)(ag(F_PX, 0) + ax * dt); s[1] = (float)(ag(F_PY, 0) + ay * dt);
+                s[2] = (float)ax; s[3] = (float)ay; s[4] = (float)ag(F_R, 0);
+                s[5] = (float)ag(F_GX, 0); s[6] = (float)ag(F_GY, 0); s[7] = (float)ag(F_VPREF, 0); s[8] = 0.0f;
+                s[9] = (float)(ag(F_PX, h + 1) + hvx * dt); s[10] = (float)(ag(F_PY, h + 1) + hvy * dt);
+                s[11] = (float)hvx; s[12] = (float)hvy; s[13] = (float)ag(F_R, h + 1);
+                cn_rotate(s, o);
+                float hi[13], lo[13];
+#pragma unroll
+                for (int k = 0; k < 13; ++k) split_hl(o[k], hi[k], lo[k]);
+                c0 = make_uint4(h2(hi[0], hi[1]), h2(hi[2], hi[3]), h2(hi[4], hi[5]), h2(hi[6], hi[7]));
+                c1 = make_uint4(h2(hi[8], hi[9]), h2(hi[10], hi[11]), h2(hi[12], 1.0f), h2(1.0f, 0.0f));
+                c2 = make_uint4(h2(lo[0], lo[1]), h2(lo[2], lo[3]), h2(lo[4], lo[5]), h2(lo[6], lo[7]));
+                c3 = make_uint4(h2(lo[8], lo[9]), h2(lo[10], lo[11]), h2(lo[12], 0.0f), 0u);
+                if (h == 0) {
+                    // self-state part of the joint state (sarl.py:36,63): J chunks 7 (hi, 1, 1), 8 (lo), 9 (pad)
+                    uint8_t *jt = J + (size_t)(g >> 7) * J_TILE_BYTES;
+                    const int rb = g & 127;
+                    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 7)) =
+                        make_uint4(h2(hi[0], hi[1]), h2(hi[2], hi[3]), h2(hi[4], hi[5]), h2(1.0f, 1.0f));
+                    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 8)) =
+                        make_uint4(h2(lo[0], lo[1]), h2(lo[2], lo[3]), h2(lo[4], lo[5]), 0u);
+                    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 9)) = make_uint4(0, 0, 0, 0);
+                }
+            }
+            *reinterpret_cast<uint4 *>(bufB + chunk_off(ROWS, r, 0)) = c0;
+            *reinterpret_cast<uint4 *>(bufB + chunk_off(ROWS, r, 1)) = c1;
+            *reinterpret_cast<uint4 *>(bufB + chunk_off(ROWS, r, 2)) = c2;
+            *reinterpret_cast<uint4 *>(bufB + chunk_off(ROWS, r, 3)) = c3;
+        }
+        fence_async_smem();
+        __syncthreads();
+        // ---- mlp1.0: X (K=32) -> TMEM[0,160) ----
+        if (tid == 0) {
+            fence_after_sync();
+            mma_layer(tmem + 0, sB, ROWS, sW1, N_H1, K_X, N_H1, false);
+            commit(mbar);
+        }
+        mbar_wait(mbar, phase); phase ^= 1;
+        fence_after_sync();
+        epilogue_to_smem<true>(tlane, 0, N_H1, bufA, tid, 0);              // H1 (overwrites the env slots)
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+        // ---- mlp1.2: H1 (K=160) -> TMEM[0,112) ----
+        if (tid == 0) {
+            fence_after_sync();
+            mma_layer(tmem + 0, sA, ROWS, sW2, N_M1, N_H1, N_M1, false);
+            commit(mbar);
+        }
+        mbar_wait(mbar, phase); phase ^= 1;
+        fence_after_sync();
+        epilogue_to_smem<true>(tlane, 0, N_M1, bufB, tid, 0);              // mlp1 output (X is dead)
+        fence_before_sync();
+        __syncthreads();
+        // ---- group mean of the mlp1 output (sarl.py:42), replicated to every row of the group -> bufA ----
+        for (int it = tid; it < G * (N_M1 / 8); it += blockDim.x) {
+            const int gl = it / (N_M1 / 8), c = it - gl * (N_M1 / 8);
+            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int h = 0; h < H; ++h) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(bufB + chunk_off(ROWS, gl * H + h, c));
+                const __half2 *hv = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 f = __half22float2(hv[q]);
+                    acc[2 * q] += f.x; acc[2 * q + 1] += f.y;
+                }
+            }
+            const float inv = 1.0f / (float)H;
+            uint4 o;
+            o.x = h2(acc[0] * inv, acc[1] * inv); o.y = h2(acc[2] * inv, acc[3] * inv);
+            o.z = h2(acc[4] * inv, acc[5] * inv); o.w = h2(acc[6] * inv, acc[7] * inv);
+            for (int h = 0; h < H; ++h) *reinterpret_cast<uint4 *>(bufA + chunk_off(ROWS, gl * H + h, c)) = o;
+        }
+        for (int it = tid; it < (ROWS - rows) * (N_M1 / 8); it += blockDim.x) {   // padding rows of the mean tile
+            const int r = rows + it / (N_M1 / 8), c = it % (N_M1 / 8);
+            *reinterpret_cast<uint4 *>(bufA + chunk_off(ROWS, r, c)) = make_uint4(0, 0, 0, 0);
+        }
+        fence_async_smem();
+        __syncthreads();
+        // ---- mlp2.0 -> TMEM[0,112) ; attention.0 on [mlp1_out | mean] (K=224) -> TMEM[112,224) ----
+        if (tid == 0) {
+            fence_after_sync();
+            mma_layer(tmem + 0, sB, ROWS, sW3, N_M1, N_M1, N_M1, false);
+            mma_layer(tmem + N_M1, sB, ROWS, sWA1, N_M1, N_M1, N_M1, false);
+            mma_layer(tmem + N_M1, sA, ROWS, sWA1 + (N_M1 / 8) * (N_M1 * 16), N_M1, N_M1, N_M1, true);
+            commit(mbar);
+        }
+        mbar_wait(mbar, phase); phase ^= 1;
+        fence_after_sync();
+        epilogue_to_smem<true>(tlane, 0, N_M1, bufA, tid, 0);              // mlp2.0 out
+        epilogue_to_smem<true>(tlane, N_M1, N_M1, bufB, tid, 0);           // attention.0 out
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+        // ---- mlp2.2 -> TMEM[0,64) ; attention.2 -> TMEM[64,176) ----
+        if (tid == 0) {
+            fence_after_sync();
+            mma_layer(tmem + 0, sA, ROWS, sW4, N_F, N_M1, N_F, false);
+            mma_layer(tmem + N_F, sB, ROWS, sWA2, N_M1, N_M1, N_M1, false);
+            commit(mbar);
+        }
+        mbar_wait(mbar, phase); phase ^= 1;
+        fence_after_sync();
+        // ---- attention.4 (fp32 dot over ReLU(attention.2)) -> exp(score) * (score != 0)  (sarl.py:48-52) ----
+        {
+            float score = tail[100];
+#pragma unroll 1
+            for (int c0 = 0; c0 < 96; c0 += 32) {
+                uint32_t v[32];
+                ld32(tlane + N_F + c0, v);
+                wait_ld();
+#pragma unroll
+                for (int k = 0; k < 32; ++k) score = fmaf(fmaxf(__uint_as_float(v[k]), 0.0f), tail[c0 + k], score);
+            }
+            {
+                uint32_t v[16];
+                ld16(tlane + N_F + 96, v);
+                wait_ld();
+#pragma unroll
+                for (int k = 0; k < 4; ++k) score = fmaf(fmaxf(__uint_as_float(v[k]), 0.0f), tail[96 + k], score);
+            }
+            S[tid] = expf(score) * (score != 0.0f ? 1.0f : 0.0f);
+        }
+        __syncthreads();
+        // ---- softmax weight of this row, weighted feature rows (fp32) -> bufA (mlp2.0 tile is dead) ----
+        float *WF = reinterpret_cast<float *>(bufA);   // [128][52]
+        {
+            const int r = tid;
+            float w = 0.0f;
+            if (r < rows) {
+                const int gl = r / H;
+                float ssum = 0.0f;
+                for (int h = 0; h < H; ++h) ssum += S[gl * H + h];
+                w = S[r] / ssum;
+            }
+            uint32_t v[32];
+            ld32(tlane + 0, v);
+            wait_ld();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) WF[r * 52 + k] = w * __uint_as_float(v[k]);
+            uint32_t u[16];
+            ld16(tlane + 32, u);
+            wait_ld();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) WF[r * 52 + 32 + k] = w * __uint_as_float(u[k]);
+            uint32_t t2[16];
+            ld16(tlane + 48, t2);
+            wait_ld();
+            WF[r * 52 + 48] = w * __uint_as_float(t2[0]);
+            WF[r * 52 + 49] = w * __uint_as_float(t2[1]);
+        }
+        fence_before_sync();
+        __syncthreads();
+        // ---- weighted feature = sum over the group's rows (sarl.py:57-60) -> J chunks 0..6 ----
+        for (int it = tid; it < G * 7; it += blockDim.x) {
+            const int gl = it / 7, c = it - gl * 7, g = g0 + gl;
+            if (g >= NG) continue;
+            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            const int ncol = (c < 6) ? 8 : 2;
+            for (int h = 0; h < H; ++h) {
+                const float *row = WF + (gl * H + h) * 52 + c * 8;
+                for (int k = 0; k < ncol; ++k) acc[k] += row[k];
+            }
+            uint8_t *jt = J + (size_t)(g >> 7) * J_TILE_BYTES;
+            *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, g & 127, c)) =
+                make_uint4(h2(acc[0], acc[1]), h2(acc[2], acc[3]), h2(acc[4], acc[5]), h2(acc[6], acc[7]));
+        }
+        __syncthreads();   // WF (bufA) is reused as the env staging area of the next tile
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+}
+
+// =====================================================================================================
+// kernel B: mlp3 on the joint states + scoring
+// =====================================================================================================
+__global__ void __launch_bounds__(128, 1)
+tc_mlp3_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *__restrict__ wimg,
+               const uint8_t *__restrict__ J, const double *__restrict__ rew, int A, int NG, double gamma,
+               double gamma_bar_host, double v_pref_host, double *__restrict__ values, int ntiles)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint8_t *bufJ = smem + B_BUFJ, *bufU0 = smem + B_BUFU0, *bufU1 = smem + B_BUFU1;
+    const uint32_t mbar = smem_u32(smem + B_MISC);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + B_MISC + 8);
+    const float *tail = reinterpret_cast<const float *>(smem + OFF_TAILB);
+
+    copy_image_to_smem(smem, wimg, IMG_B_BYTES);
+    if (tid == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t sM1 = smem_u32(smem + OFF_M1), sM2 = smem_u32(smem + OFF_M2), sM3 = smem_u32(smem + OFF_M3);
+    const uint32_t sJ = smem_u32(bufJ), sU0 = smem_u32(bufU0), sU1 = smem_u32(bufU1);
+    uint32_t phase = 0;
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint8_t *src = J + (size_t)tile * J_TILE_BYTES;
+        for (uint32_t i = tid * 16; i < J_TILE_BYTES; i += blockDim.x * 16)
+            *reinterpret_cast<uint4 *>(bufJ + i) = *reinterpret_cast<const uint4 *>(src + i);
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {   // mlp3.0
+            fence_after_sync();
+            mma_layer(tmem + 0, sJ, ROWS, sM1, N_H1, K_J, N_H1, false);
+            commit(mbar);
+        }
+        mbar_wait(mbar, phase); phase ^= 1;
+        fence_after_sync();
+        epilogue_to_smem<true>(tlane, 0, N_H1, bufU0, tid, 0);
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {   // mlp3.2
+            fence_after_sync();
+            mma_layer(tmem + 0, sU0, ROWS, sM2, N_M1, N_H1, N_M1, false);
+            commit(mbar);
+        }
+        mbar_wait(mbar, phase); phase ^= 1;
+        fence_after_sync();
+        epilogue_to_smem<true>(tlane, 0, N_M1, bufU1, tid, 0);
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {   // mlp3.4
+            fence_after_sync();
+            mma_layer(tmem + 0, sU1, ROWS, sM3, N_M1, N_M1, N_M1, false);
+            commit(mbar);
+        }
+        mbar_wait(mbar, phase); phase ^= 1;
+        fence_after_sync();
+        // mlp3.6 as an fp32 dot over ReLU(mlp3.4), then value = reward + gamma_bar * V (multi_human_rl.py:52)
+        float v = tail[100];
+#pragma unroll 1
+        for (int c0 = 0; c0 < 96; c0 += 32) {
+            uint32_t x[32];
+            ld32(tlane + c0, x);
+            wait_ld();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v = fmaf(fmaxf(__uint_as_float(x[k]), 0.0f), tail[c0 + k], v);
+        }
+        {
+            uint32_t x[16];
+            ld16(tlane + 96, x);
+            wait_ld();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v = fmaf(fmaxf(__uint_as_float(x[k]), 0.0f), tail[96 + k], v);
+        }
+        const int g = tile * ROWS + tid;
+        if (g < NG) {
+            const int e = g / A;
+            const double vp = st[st_idx(p.d, F_VPREF, 0, e)];
+            const double gamma_bar = (vp == v_pref_host) ? gamma_bar_host : pow(gamma, p.time_step * vp);
+            values[g] = rew[g] + gamma_bar * (double)v;
+        }
+        fence_before_sync();
+        __syncthreads();
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+}
+
+// =====================================================================================================
+// self-test kernel: D[128 x N] = A[128 x K] * B[N x K]^T
+// =====================================================================================================
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_kernel(const uint8_t *__restrict__ a_img, const uint8_t *__restrict__ b_img, float *__restrict__ d,
+                     int N, int K)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t a_bytes = bytes_of(ROWS, K), b_bytes = bytes_of(N, K);
+    uint8_t *sa = smem, *sb = smem + a_bytes;
+    uint8_t *misc = smem + ((a_bytes + b_bytes + 15) & ~15u);
+    const uint32_t mbar = smem_u32(misc);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(misc + 8);
+    copy_image_to_smem(sa, a_img, a_bytes);
+    copy_image_to_smem(sb, b_img, b_bytes);
+    if (tid == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    if (tid == 0) {
+        mma_layer(tmem, smem_u32(sa), ROWS, smem_u32(sb), N, K, N, false);
+        commit(mbar);
+    }
+    mbar_wait(mbar, 0);
+    fence_after_sync();
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        uint32_t v[16];
+        ld16(tlane + c0, v);
+        wait_ld();
+        for (int k = 0; k < 16; ++k) d[(size_t)tid * N + c0 + k] = __uint_as_float(v[k]);
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+}
+
+// ---- host-side weight images ------------------------------------------------------------------------
+struct HostLinear { const float *w, *b; int in, out; };
+
+inline void put(std::vector<uint8_t> &img, uint32_t base, int R, int r, int k, float v)
+{
+    const __half h = __float2half_rn(v);
+    memcpy(&img[base + chunk_off(R, r, k >> 3) + (k & 7) * 2], &h, 2);
+}
+inline float f16r(float v) { return __half2float(__float2half_rn(v)); }
+
+// generic layer: rows n < out get W[n][k] at K index kmap(k), bias hi/lo at kb/kb+1; ones columns at
+// output rows (ones_n, ones_n+1) fed from K index kb (which holds 1.0 in the activation tile)
+void fill_layer(std::vector<uint8_t> &img, uint32_t base, int R, const HostLinear &L, int k_in0, int n_in, int k_dst0,
+                int kb, int ones_n)
+{
+    for (int n = 0; n < L.out; ++n) {
+        for (int k = 0; k < n_in; ++k) put(img, base, R, n, k_dst0 + k, L.w[(size_t)n * L.in + k_in0 + k]);
+        if (kb >= 0) {
+            const float bh = f16r(L.b[n]);
+            put(img, base, R, n, kb, bh);
+            put(img, base, R, n, kb + 1, L.b[n] - bh);
+        }
+    }
+    if (ones_n >= 0 && kb >= 0) { put(img, base, R, ones_n, kb, 1.0f); put(img, base, R, ones_n + 1, kb, 1.0f); }
+}
+
+}  // namespace
+
+int cn_tc_init(cn_policy *p)
+{
+    const SarlDims &d = p->d;
+    const bool ok = d.in == 13 && d.self_dim == 6 && d.m1[0] == 150 && d.m1[1] == 100 && d.m2[0] == 100 && d.m2[1] == 50 &&
+                    d.at[0] == 100 && d.at[1] == 100 && d.at[2] == 1 && d.m3[0] == 150 && d.m3[1] == 100 &&
+                    d.m3[2] == 100 && d.m3[3] == 1;
+    if (!ok) {
+        cn_set_error("CN_PREC_F16_TC is specialised for the default [sarl] dims (150,100 / 100,50 / 100,100,1 / "
+                     "150,100,100,1); use CN_PREC_F32 for other shapes");
+        return CN_EUNSUPPORTED;
+    }
+    TcState *t = new TcState();
+    memset(t, 0, sizeof(*t));
+    cudaDeviceProp prop;
+    CN_CUDA_CHECK(cudaGetDeviceProperties(&prop, p->device));
+    t->num_sms = prop.multiProcessorCount;
+    if (cudaMalloc((void **)&t->img_a, IMG_A_BYTES) != cudaSuccess || cudaMalloc((void **)&t->img_b, IMG_B_BYTES) != cudaSuccess) {
+        cn_set_error("cudaMalloc failed for the tensor-core weight images");
+        delete t;
+        return CN_ENOMEM;
+    }
+    CN_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A_SMEM));
+    CN_CUDA_CHECK(cudaFuncSetAttribute(tc_mlp3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B_SMEM));
+    p->tc = t;
+    return CN_OK;
+}
+
+void cn_tc_destroy(cn_policy *p)
+{
+    TcState *t = (TcState *)p->tc;
+    if (!t) return;
+    if (t->img_a) cudaFree(t->img_a);
+    if (t->img_b) cudaFree(t->img_b);
+    if (t->J) cudaFree(t->J);
+    if (t->rew) cudaFree(t->rew);
+    delete t;
+    p->tc = nullptr;
+}
+
+int cn_tc_load_weights(cn_policy *p, const float *flat, cudaStream_t s)
+{
+    TcState *t = (TcState *)p->tc;
+    const SarlDims &d = p->d;
+    HostLinear L[11];
+    const int ins[11] = {d.in, d.m1[0], d.m1[1], d.m2[0], 2 * d.m1[1], d.at[0], d.at[1], d.m2[1] + d.self_dim, d.m3[0], d.m3[1], d.m3[2]};
+    const int outs[11] = {d.m1[0], d.m1[1], d.m2[0], d.m2[1], d.at[0], d.at[1], d.at[2], d.m3[0], d.m3[1], d.m3[2], d.m3[3]};
+    const float *src = flat;
+    for (int i = 0; i < 11; ++i) {
+        L[i].w = src; src += (size_t)ins[i] * outs[i];
+        L[i].b = src; src += outs[i];
+        L[i].in = ins[i]; L[i].out = outs[i];
+    }
+    std::vector<uint8_t> a(IMG_A_BYTES, 0), b(IMG_B_BYTES, 0);
+    // mlp1.0: K = [x_hi(13) 1 1 0 | x_lo(13) 0 0 0]; bias at k = 13,14; ones -> n = 150,151
+    fill_layer(a, OFF_W1, N_H1, L[0], 0, 13, 0, 13, 150);
+    fill_layer(a, OFF_W1, N_H1, L[0], 0, 13, 16, -1, -1);
+    fill_layer(a, OFF_W2, N_M1, L[1], 0, 150, 0, 150, 100);          // mlp1.2
+    fill_layer(a, OFF_W3, N_M1, L[2], 0, 100, 0, 100, 100);          // mlp2.0
+    fill_layer(a, OFF_W4, N_F, L[3], 0, 100, 0, 100, -1);            // mlp2.2 (no ones needed downstream)
+    fill_layer(a, OFF_WA1, N_M1, L[4], 0, 100, 0, 100, 100);         // attention.0, mlp1_out half
+    fill_layer(a, OFF_WA1, N_M1, L[4], 100, 100, N_M1, -1, -1);      //              group-mean half
+    fill_layer(a, OFF_WA2, N_M1, L[5], 0, 100, 0, 100, -1);          // attention.2
+    float tail[TAIL_BYTES / 4] = {0};
+    for (int k = 0; k < 100; ++k) tail[k] = L[6].w[k];
+    tail[100] = L[6].b[0];
+    memcpy(&a[OFF_TAILA], tail, TAIL_BYTES);
+    // mlp3.0 on J = [weighted(50) pad6 | self_hi(6) 1 1 | self_lo(6) 0 0 | pad8]; joint = [self(6), weighted(50)]
+    fill_layer(b, OFF_M1, N_H1, L[7], 6, 50, 0, -1, -1);
+    fill_layer(b, OFF_M1, N_H1, L[7], 0, 6, 56, 62, 150);
+    fill_layer(b, OFF_M1, N_H1, L[7], 0, 6, 64, -1, -1);
+    fill_layer(b, OFF_M2, N_M1, L[8], 0, 150, 0, 150, 100);          // mlp3.2
+    fill_layer(b, OFF_M3, N_M1, L[9], 0, 100, 0, 100, -1);           // mlp3.4
+    for (int k = 0; k < 100; ++k) tail[k] = L[10].w[k];
+    tail[100] = L[10].b[0];
+    memcpy(&b[OFF_TAILB], tail, TAIL_BYTES);
+    CN_CUDA_CHECK(cudaMemcpyAsync(t->img_a, a.data(), IMG_A_BYTES, cudaMemcpyHostToDevice, s));
+    CN_CUDA_CHECK(cudaMemcpyAsync(t->img_b, b.data(), IMG_B_BYTES, cudaMemcpyHostToDevice, s));
+    CN_CUDA_CHECK(cudaStreamSynchronize(s));
+    return CN_OK;
+}
+
 int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cudaStream_t s)
-{ (void)p; (void)env; (void)query_env; (void)epsilon; (void)s; return CN_EUNSUPPORTED; }
-extern "C" int cn_selftest_umma(int32_t N, int32_t K, const float *a, const float *b, float *d, int device)
-{ (void)N; (void)K; (void)a; (void)b; (void)d; (void)device; cn_set_error("not built yet"); return CN_EUNSUPPORTED; }
+{
+    TcState *t = (TcState *)p->tc;
+    const EnvDims ed = env->p.d;
+    if (ed.H > CN_MAX_HUMANS) { cn_set_error("human_num too large"); return CN_EUNSUPPORTED; }
+    int rc = cn_lookahead_prepare(p, env, s);
+    if (rc) return rc;
+    const int A = p->d.A;
+    const size_t NG = (size_t)ed.E * A;
+    if (NG > t->cap_groups) {
+        if (t->J) cudaFree(t->J);
+        if (t->rew) cudaFree(t->rew);
+        t->J = nullptr; t->rew = nullptr; t->cap_groups = 0;
+        const size_t jtiles = (NG + ROWS - 1) / ROWS;
+        CN_CUDA_CHECK(cudaMalloc((void **)&t->J, jtiles * J_TILE_BYTES));
+        CN_CUDA_CHECK(cudaMalloc((void **)&t->rew, sizeof(double) * NG));
+        CN_CUDA_CHECK(cudaMemsetAsync(t->J, 0, jtiles * J_TILE_BYTES, s));
+        t->cap_groups = NG;
+    }
+    int G = ROWS / ed.H;
+    if (G > 64) G = 64;                      // keeps the staged environments of a tile within bufA
+    const int ntiles_a = (int)((NG + G - 1) / G);
+    const int ntiles_b = (int)((NG + ROWS - 1) / ROWS);
+    const double gamma_bar = pow(p->cfg.gamma, env->p.time_step * p->cfg.v_pref);
+    const int grid_a = ntiles_a < t->num_sms ? ntiles_a : t->num_sms;
+    const int grid_b = ntiles_b < t->num_sms ? ntiles_b : t->num_sms;
+    tc_rows_kernel<<<grid_a, 128, A_SMEM, s>>>(env->p, env->state, env->time, env->human_v, p->action_dev, A, query_env,
+                                               t->img_a, t->J, t->rew, (int)NG, G, ntiles_a);
+    CN_LAUNCH_CHECK();
+    tc_mlp3_kernel<<<grid_b, 128, B_SMEM, s>>>(env->p, env->state, t->img_b, t->J, t->rew, A, (int)NG, p->cfg.gamma,
+                                               gamma_bar, p->cfg.v_pref, p->values, ntiles_b);
+    CN_LAUNCH_CHECK();
+    return cn_lookahead_argmax(p, env, epsilon, s);
+}
+
+extern "C" int cn_selftest_umma(int32_t N, int32_t K, const float *a_host, const float *b_host, float *d_host, int device)
+{
+    if (N < 16 || N > 256 || N % 16 || K < 16 || K % 16 || K > 256) { cn_set_error("N in [16,256] step 16, K in [16,256] step 16"); return CN_EINVAL; }
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); cn_set_error("no CUDA device available; no CPU fallback"); return CN_ECUDA; }
+    CN_CUDA_CHECK(cudaSetDevice(device));
+    std::vector<uint8_t> ai(bytes_of(ROWS, K), 0), bi(bytes_of(N, K), 0);
+    for (int r = 0; r < ROWS; ++r) for (int k = 0; k < K; ++k) put(ai, 0, ROWS, r, k, a_host[(size_t)r * K + k]);
+    for (int r = 0; r < N; ++r) for (int k = 0; k < K; ++k) put(bi, 0, N, r, k, b_host[(size_t)r * K + k]);
+    uint8_t *da = nullptr, *db = nullptr;
+    float *dd = nullptr;
+    CN_CUDA_CHECK(cudaMalloc((void **)&da, ai.size()));
+    CN_CUDA_CHECK(cudaMalloc((void **)&db, bi.size()));
+    CN_CUDA_CHECK(cudaMalloc((void **)&dd, sizeof(float) * ROWS * N));
+    CN_CUDA_CHECK(cudaMemcpy(da, ai.data(), ai.size(), cudaMemcpyHostToDevice));
+    CN_CUDA_CHECK(cudaMemcpy(db, bi.data(), bi.size(), cudaMemcpyHostToDevice));
+    const size_t smem = ai.size() + bi.size() + 64;
+    CN_CUDA_CHECK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_selftest_kernel<<<1, 128, smem>>>(da, db, dd, N, K);
+    CN_LAUNCH_CHECK();
+    CN_CUDA_CHECK(cudaDeviceSynchronize());
+    CN_CUDA_CHECK(cudaMemcpy(d_host, dd, sizeof(float) * ROWS * N, cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dd);
+    return CN_OK;
+}

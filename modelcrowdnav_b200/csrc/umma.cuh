@@ -1,0 +1,183 @@
+// umma.cuh -- thin inline-PTX layer over the Blackwell tensor-core path used by lookahead_tc.cu:
+// tcgen05.mma (kind::f16, cta_group::1, M=128) with operands in shared memory (SWIZZLE_NONE, K-major
+// canonical layout), accumulators in TMEM, tcgen05.ld for the epilogue, mbarrier completion.
+//
+// Operand layout used everywhere in this library ("chunked K-major"):
+//   element (row r, k) of an R-row operand lives at byte   (k/8) * (R*16) + r*16 + (k%8)*2
+// i.e. 8-element (16-byte) K-chunks; within a chunk the rows are contiguous.  In UMMA terms: core matrix =
+// 8 rows x 16 B contiguous (128 B), SBO (8-row group stride) = 128 B, LBO (K-chunk stride) = R*16 B.
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// SM100 shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), SWIZZLE_NONE, version 1.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): F16 x F16 -> F32, both operands K-major, M = 128.
+__host__ __device__ __forceinline__ uint32_t make_idesc_f16(int N)
+{
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// D[128 x N] (+)= A[128 x K] * B[N x K]^T, K a multiple of 16; one elected thread calls this.
+// a_base/b_base: shared addresses of chunked K-major operands with a_rows / b_rows rows.
+__device__ __forceinline__ void mma_layer(uint32_t tmem_d, uint32_t a_base, uint32_t a_rows, uint32_t b_base,
+                                          uint32_t b_rows, int K, int N, bool accumulate_first)
+{
+    const uint32_t idesc = make_idesc_f16(N);
+    const uint32_t a_lbo = a_rows * 16, b_lbo = b_rows * 16;
+    for (int s = 0; s < K / 16; ++s) {
+        const uint64_t ad = make_desc(a_base + (uint32_t)s * 2 * a_lbo, a_lbo, 128);
+        const uint64_t bd = make_desc(b_base + (uint32_t)s * 2 * b_lbo, b_lbo, 128);
+        mma_f16(tmem_d, ad, bd, idesc, (s > 0 || accumulate_first) ? 1u : 0u);
+    }
+}
+
+__device__ __forceinline__ void commit(uint32_t mbar_saddr)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar_saddr) : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar_saddr, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar_saddr), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t mbar_saddr, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}\n"
+        :: "r"(mbar_saddr), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// one warp allocates `ncols` TMEM columns (power of two >= 32) and publishes the base address in smem
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_saddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(dst_saddr), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+
+// 32 lanes x 32 columns of fp32: thread i of the warp receives columns [col, col+32) of TMEM lane (base lane + i)
+__device__ __forceinline__ void ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void ld16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+
+// pack two fp32 into f16x2 (lo = a, hi = b), optional ReLU fused in the conversion
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi)
+{
+    uint32_t d;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_f16x2_relu(float lo, float hi)
+{
+    uint32_t d;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
+// byte offset of the 16-byte chunk holding (row r, k in [8c, 8c+8)) in an R-row chunked K-major operand
+__host__ __device__ __forceinline__ uint32_t chunk_off(uint32_t R, uint32_t r, uint32_t c) { return c * (R * 16) + r * 16; }
+
+// Epilogue: TMEM columns [col, col + ncols) of this thread's lane -> fp16 row `row` of a 128-row operand in
+// shared memory starting at K-chunk kc0 (ncols a multiple of 16).  RELU selects cvt.rn.relu.
+template <bool RELU>
+__device__ __forceinline__ void epilogue_to_smem(uint32_t taddr_lane, int col, int ncols, uint8_t *dst, int row, int kc0)
+{
+    int done = 0;
+    while (done < ncols) {
+        if (ncols - done >= 32) {
+            uint32_t v[32];
+            ld32(taddr_lane + col + done, v);
+            wait_ld();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint4 o;
+                const float *f = reinterpret_cast<const float *>(v) + q * 8;
+                if (RELU) {
+                    o.x = pack_f16x2_relu(f[0], f[1]); o.y = pack_f16x2_relu(f[2], f[3]);
+                    o.z = pack_f16x2_relu(f[4], f[5]); o.w = pack_f16x2_relu(f[6], f[7]);
+                } else {
+                    o.x = pack_f16x2(f[0], f[1]); o.y = pack_f16x2(f[2], f[3]);
+                    o.z = pack_f16x2(f[4], f[5]); o.w = pack_f16x2(f[6], f[7]);
+                }
+                *reinterpret_cast<uint4 *>(dst + chunk_off(128, row, kc0 + done / 8 + q)) = o;
+            }
+            done += 32;
+        } else {
+            uint32_t v[16];
+            ld16(taddr_lane + col + done, v);
+            wait_ld();
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                uint4 o;
+                const float *f = reinterpret_cast<const float *>(v) + q * 8;
+                if (RELU) {
+                    o.x = pack_f16x2_relu(f[0], f[1]); o.y = pack_f16x2_relu(f[2], f[3]);
+                    o.z = pack_f16x2_relu(f[4], f[5]); o.w = pack_f16x2_relu(f[6], f[7]);
+                } else {
+                    o.x = pack_f16x2(f[0], f[1]); o.y = pack_f16x2(f[2], f[3]);
+                    o.z = pack_f16x2(f[4], f[5]); o.w = pack_f16x2(f[6], f[7]);
+                }
+                *reinterpret_cast<uint4 *>(dst + chunk_off(128, row, kc0 + done / 8 + q)) = o;
+            }
+            done += 16;
+        }
+    }
+}
+
+}  // namespace umma
