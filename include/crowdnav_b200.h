@@ -201,6 +201,9 @@ int64_t cn_launch_count(void);
 /* Self-test of the tcgen05/TMEM building block: D[128 x N] = A[128 x K] * B[N x K]^T with fp16 operands,
  * fp32 accumulate.  a_host: 128 x K, b_host: N x K (row-major fp32, rounded to fp16 inside), d_host: 128 x N. */
 int cn_selftest_umma(int32_t N, int32_t K, const float *a_host, const float *b_host, float *d_host, int device);
+/* Same product with the B operand read MN-major from an activation-style image (rows = K index, K <= 128):
+ * the form the kernel uses to sum the attention-weighted features over the humans of a group. */
+int cn_selftest_umma_bmn(int32_t N, int32_t K, const float *a_host, const float *b_host, float *d_host, int device);
 
 #ifdef __cplusplus
 }

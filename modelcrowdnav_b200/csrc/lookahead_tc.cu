@@ -65,12 +65,12 @@ constexpr uint32_t IMG_B_BYTES = OFF_TAILB + TAIL_BYTES;
 constexpr uint32_t A_BUFA = (IMG_A_BYTES + 127) & ~127u;                 // 128 x 160 fp16
 constexpr uint32_t A_BUFB = A_BUFA + bytes_of(ROWS, N_H1);               // 128 x 112 fp16
 constexpr uint32_t A_MISC = A_BUFB + bytes_of(ROWS, N_M1);               // S[128] f32, mbar, tmem ptr
-constexpr uint32_t A_SMEM = A_MISC + 512 + 16;
+constexpr uint32_t A_SMEM = A_MISC + 1024 + 16;
 constexpr uint32_t B_BUFJ = (IMG_B_BYTES + 127) & ~127u;                 // 128 x 80 fp16
 constexpr uint32_t B_BUFU0 = B_BUFJ + bytes_of(ROWS, K_J);
 constexpr uint32_t B_BUFU1 = B_BUFU0 + bytes_of(ROWS, N_H1);
 constexpr uint32_t B_MISC = B_BUFU1 + bytes_of(ROWS, N_M1);
-constexpr uint32_t B_SMEM = B_MISC + 16;
+constexpr uint32_t B_SMEM = B_MISC + 512 + 16;
 static_assert(A_SMEM <= 232448, "tc_rows_kernel exceeds 227 KB of shared memory");
 constexpr uint32_t J_TILE_BYTES = bytes_of(ROWS, K_J);
 
@@ -100,9 +100,13 @@ __device__ __forceinline__ void split_hl(float x, float &hi, float &lo)
 }
 
 // =====================================================================================================
-// kernel A: the per-(env, action, human) row network
+// kernel A: the per-(env, action, human) row network.  256 threads: warps w and w+4 own TMEM lanes
+// 32*(w%4)..+31 (the hardware ties a warp to the lane quarter warpid%4) and split the columns of every
+// epilogue between them.
 // =====================================================================================================
-__global__ void __launch_bounds__(128, 1)
+constexpr int kThreadsTC = 256;
+
+__global__ void __launch_bounds__(kThreadsTC, 1)
 tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restrict__ time,
                const double *__restrict__ human_v, const double *__restrict__ actions, int A, int query_env,
                const uint8_t *__restrict__ wimg, uint8_t *__restrict__ J, double *__restrict__ rew, int NG, int G,
@@ -111,11 +115,14 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
     extern __shared__ __align__(128) uint8_t smem[];
     const EnvDims ed = p.d;
     const int H = ed.H, A1 = ed.A1;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, hf = warp >> 2;
+    const int row = q * 32 + lane;            // TMEM lane == tile row owned by this thread
     uint8_t *bufA = smem + A_BUFA, *bufB = smem + A_BUFB;
-    float *S = reinterpret_cast<float *>(smem + A_MISC);
-    const uint32_t mbar = smem_u32(smem + A_MISC + 512);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + A_MISC + 512 + 8);
+    float *S0 = reinterpret_cast<float *>(smem + A_MISC);          // [128] partial scores, columns [0,64)
+    float *S1 = S0 + 128;                                          // [128] partial scores, columns [64,100)
+    const uint32_t mbar = smem_u32(smem + A_MISC + 1024);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + A_MISC + 1024 + 8);
     const float *tail = reinterpret_cast<const float *>(smem + OFF_TAILA);
 
     copy_image_to_smem(smem, wimg, IMG_A_BYTES);
@@ -126,7 +133,7 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
     const uint32_t sW1 = smem_u32(smem + OFF_W1), sW2 = smem_u32(smem + OFF_W2), sW3 = smem_u32(smem + OFF_W3);
     const uint32_t sW4 = smem_u32(smem + OFF_W4), sWA1 = smem_u32(smem + OFF_WA1), sWA2 = smem_u32(smem + OFF_WA2);
     const uint32_t sA = smem_u32(bufA), sB = smem_u32(bufB);
@@ -134,6 +141,7 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
     const int rows = G * H;
     const int slot_doubles = F_COUNT * A1 + 2 * H + 1;
     const double dt = p.time_step;
+    constexpr int T_F = 0, T_A2 = N_F, T_D2 = N_F + N_M1;   // TMEM columns of the last two stages
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int g0 = tile * G;
@@ -149,41 +157,43 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
             double v;
             if (j < F_COUNT * A1) { const int a = j / F_COUNT, f = j - a * F_COUNT; v = st[st_idx(ed, f, a, e)]; }
             else if (j < F_COUNT * A1 + 2 * H) {
-                const int q = j - F_COUNT * A1, h = q >> 1, c = q & 1;
+                const int qq = j - F_COUNT * A1, h = qq >> 1, c = qq & 1;
                 v = query_env ? human_v[(size_t)(c * H + h) * ed.E + e] : 0.0;
             } else v = time[e];
             slots[i] = v;
         }
         __syncthreads();
-        // ---- P0b: rewards (one thread per group), features (one thread per row) ----
-        if (tid < G && g0 + tid < NG) {
-            const int g = g0 + tid, e = g / A, a = g - e * A;
-            const double *sv = slots + (size_t)(e - e_first) * slot_doubles;
-            auto ag = [&](int f, int agent) { return sv[agent * F_COUNT + f]; };
-            const double ax = actions[2 * a], ay = actions[2 * a + 1];
-            double reward;
-            if (query_env) {
-                reward = cn_step_outcome(p, ag, H, sv[slot_doubles - 1], ax, ay).reward;   // crowd_sim.py:325-329
-            } else {
-                // multi_human_rl.py:65-88
-                const double npx = ag(F_PX, 0) + ax * dt, npy = ag(F_PY, 0) + ay * dt, rr = ag(F_R, 0);
-                double dmin = INFINITY;
-                bool collision = false;
-                for (int h = 1; h <= H; ++h) {
-                    const double nhx = ag(F_PX, h) + ag(F_VX, h) * dt, nhy = ag(F_PY, h) + ag(F_VY, h) * dt;
-                    const double dist = norm2d(npx - nhx, npy - nhy) - rr - ag(F_R, h);
-                    if (dist < 0) { collision = true; break; }
-                    if (dist < dmin) dmin = dist;
+        // ---- P0b: features (threads 0..127, one per row) | rewards (threads 128.., one per group) ----
+        if (tid >= 128) {
+            const int gl = tid - 128;
+            if (gl < G && g0 + gl < NG) {
+                const int g = g0 + gl, e = g / A, a = g - e * A;
+                const double *sv = slots + (size_t)(e - e_first) * slot_doubles;
+                auto ag = [&](int f, int agent) { return sv[agent * F_COUNT + f]; };
+                const double ax = actions[2 * a], ay = actions[2 * a + 1];
+                double reward;
+                if (query_env) {
+                    reward = cn_step_outcome(p, ag, H, sv[slot_doubles - 1], ax, ay).reward;   // crowd_sim.py:325-329
+                } else {
+                    // multi_human_rl.py:65-88
+                    const double npx = ag(F_PX, 0) + ax * dt, npy = ag(F_PY, 0) + ay * dt, rr = ag(F_R, 0);
+                    double dmin = INFINITY;
+                    bool collision = false;
+                    for (int h = 1; h <= H; ++h) {
+                        const double nhx = ag(F_PX, h) + ag(F_VX, h) * dt, nhy = ag(F_PY, h) + ag(F_VY, h) * dt;
+                        const double dist = norm2d(npx - nhx, npy - nhy) - rr - ag(F_R, h);
+                        if (dist < 0) { collision = true; break; }
+                        if (dist < dmin) dmin = dist;
+                    }
+                    const bool reaching_goal = norm2d(npx - ag(F_GX, 0), npy - ag(F_GY, 0)) < rr;
+                    if (collision) reward = -0.25;
+                    else if (reaching_goal) reward = 1;
+                    else if (dmin < 0.2) reward = (dmin - 0.2) * 0.5 * dt;
+                    else reward = 0;
                 }
-                const bool reaching_goal = norm2d(npx - ag(F_GX, 0), npy - ag(F_GY, 0)) < rr;
-                if (collision) reward = -0.25;
-                else if (reaching_goal) reward = 1;
-                else if (dmin < 0.2) reward = (dmin - 0.2) * 0.5 * dt;
-                else reward = 0;
+                rew[g] = reward;
             }
-            rew[g] = reward;
-        }
-        {
+        } else {
             const int r = tid;
             uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0, c2 = c0, c3 = c0;
             const int gl = r / H, h = r - gl * H, g = g0 + gl;
@@ -235,7 +245,8 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
         }
         mbar_wait(mbar, phase); phase ^= 1;
         fence_after_sync();
-        epilogue_to_smem<true>(tlane, 0, N_H1, bufA, tid, 0);              // H1 (overwrites the env slots)
+        if (hf == 0) epilogue_to_smem<true>(tlane, 0, 96, bufA, row, 0);       // H1 (overwrites the env slots)
+        else epilogue_to_smem<true>(tlane, 96, 64, bufA, row, 12);
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
@@ -247,20 +258,22 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
         }
         mbar_wait(mbar, phase); phase ^= 1;
         fence_after_sync();
-        epilogue_to_smem<true>(tlane, 0, N_M1, bufB, tid, 0);              // mlp1 output (X is dead)
+        if (hf == 0) epilogue_to_smem<true>(tlane, 0, 64, bufB, row, 0);       // mlp1 output (X is dead)
+        else epilogue_to_smem<true>(tlane, 64, 48, bufB, row, 8);
         fence_before_sync();
         __syncthreads();
         // ---- group mean of the mlp1 output (sarl.py:42), replicated to every row of the group -> bufA ----
+        // item = (K-chunk c, group gl); consecutive threads take consecutive groups (conflict-free 16 B accesses)
         for (int it = tid; it < G * (N_M1 / 8); it += blockDim.x) {
-            const int gl = it / (N_M1 / 8), c = it - gl * (N_M1 / 8);
+            const int c = it / G, gl = it - c * G;
             float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             for (int h = 0; h < H; ++h) {
                 const uint4 v = *reinterpret_cast<const uint4 *>(bufB + chunk_off(ROWS, gl * H + h, c));
                 const __half2 *hv = reinterpret_cast<const __half2 *>(&v);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float2 f = __half22float2(hv[q]);
-                    acc[2 * q] += f.x; acc[2 * q + 1] += f.y;
+                for (int k = 0; k < 4; ++k) {
+                    const float2 f = __half22float2(hv[k]);
+                    acc[2 * k] += f.x; acc[2 * k + 1] += f.y;
                 }
             }
             const float inv = 1.0f / (float)H;
@@ -270,7 +283,7 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
             for (int h = 0; h < H; ++h) *reinterpret_cast<uint4 *>(bufA + chunk_off(ROWS, gl * H + h, c)) = o;
         }
         for (int it = tid; it < (ROWS - rows) * (N_M1 / 8); it += blockDim.x) {   // padding rows of the mean tile
-            const int r = rows + it / (N_M1 / 8), c = it % (N_M1 / 8);
+            const int c = it / (ROWS - rows), r = rows + it % (ROWS - rows);
             *reinterpret_cast<uint4 *>(bufA + chunk_off(ROWS, r, c)) = make_uint4(0, 0, 0, 0);
         }
         fence_async_smem();
@@ -285,85 +298,126 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
         }
         mbar_wait(mbar, phase); phase ^= 1;
         fence_after_sync();
-        epilogue_to_smem<true>(tlane, 0, N_M1, bufA, tid, 0);              // mlp2.0 out
-        epilogue_to_smem<true>(tlane, N_M1, N_M1, bufB, tid, 0);           // attention.0 out
+        if (hf == 0) epilogue_to_smem<true>(tlane, 0, N_M1, bufA, row, 0);     // mlp2.0 out
+        else epilogue_to_smem<true>(tlane, N_M1, N_M1, bufB, row, 0);          // attention.0 out
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
         // ---- mlp2.2 -> TMEM[0,64) ; attention.2 -> TMEM[64,176) ----
         if (tid == 0) {
             fence_after_sync();
-            mma_layer(tmem + 0, sA, ROWS, sW4, N_F, N_M1, N_F, false);
-            mma_layer(tmem + N_F, sB, ROWS, sWA2, N_M1, N_M1, N_M1, false);
+            mma_layer(tmem + T_F, sA, ROWS, sW4, N_F, N_M1, N_F, false);
+            mma_layer(tmem + T_A2, sB, ROWS, sWA2, N_M1, N_M1, N_M1, false);
             commit(mbar);
         }
         mbar_wait(mbar, phase); phase ^= 1;
         fence_after_sync();
-        // ---- attention.4 (fp32 dot over ReLU(attention.2)) -> exp(score) * (score != 0)  (sarl.py:48-52) ----
+        // ---- group-selection matrix P'[g][r] = (r / H == g) -> bufA (mlp2.0 tile is dead): the weighted sum over
+        //      the humans of a group (sarl.py:57-60) becomes one more UMMA, D2 = P' * (w .* F) ----
+        for (int it = tid; it < ROWS * (ROWS / 8); it += blockDim.x) {
+            const int c = it >> 7, g = it & 127;
+            const int lo = g * H, hi = lo + H, k0 = c * 8;
+            uint32_t wds[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ka = k0 + 2 * j, kb = ka + 1;
+                const uint32_t a = (ka >= lo && ka < hi && ka < rows) ? 0x3C00u : 0u;   // fp16 1.0
+                const uint32_t b = (kb >= lo && kb < hi && kb < rows) ? 0x3C00u : 0u;
+                wds[j] = a | (b << 16);
+            }
+            *reinterpret_cast<uint4 *>(bufA + chunk_off(ROWS, g, c)) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+        }
+        // ---- attention.4 (fp32 dot over ReLU(attention.2)), split between the two warps of a lane quarter ----
         {
-            float score = tail[100];
+            float part = 0.0f;
+            if (hf == 0) {
 #pragma unroll 1
-            for (int c0 = 0; c0 < 96; c0 += 32) {
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t v[32];
+                    ld32(tlane + T_A2 + c0, v);
+                    wait_ld();
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) part = fmaf(fmaxf(__uint_as_float(v[k]), 0.0f), tail[c0 + k], part);
+                }
+                S0[row] = part;
+            } else {
                 uint32_t v[32];
-                ld32(tlane + N_F + c0, v);
+                ld32(tlane + T_A2 + 64, v);
                 wait_ld();
 #pragma unroll
-                for (int k = 0; k < 32; ++k) score = fmaf(fmaxf(__uint_as_float(v[k]), 0.0f), tail[c0 + k], score);
-            }
-            {
-                uint32_t v[16];
-                ld16(tlane + N_F + 96, v);
+                for (int k = 0; k < 32; ++k) part = fmaf(fmaxf(__uint_as_float(v[k]), 0.0f), tail[64 + k], part);
+                uint32_t u[16];
+                ld16(tlane + T_A2 + 96, u);
                 wait_ld();
 #pragma unroll
-                for (int k = 0; k < 4; ++k) score = fmaf(fmaxf(__uint_as_float(v[k]), 0.0f), tail[96 + k], score);
+                for (int k = 0; k < 4; ++k) part = fmaf(fmaxf(__uint_as_float(u[k]), 0.0f), tail[96 + k], part);
+                S1[row] = part;
             }
-            S[tid] = expf(score) * (score != 0.0f ? 1.0f : 0.0f);
         }
         __syncthreads();
-        // ---- softmax weight of this row, weighted feature rows (fp32) -> bufA (mlp2.0 tile is dead) ----
-        float *WF = reinterpret_cast<float *>(bufA);   // [128][52]
+        // ---- masked un-stabilised softmax over the group (sarl.py:52-53); F' = w .* F as fp16 -> bufB ----
         {
-            const int r = tid;
             float w = 0.0f;
-            if (r < rows) {
-                const int gl = r / H;
-                float ssum = 0.0f;
-                for (int h = 0; h < H; ++h) ssum += S[gl * H + h];
-                w = S[r] / ssum;
+            if (row < rows) {
+                const int gl = row / H;
+                float ssum = 0.0f, mine = 0.0f;
+                for (int h = 0; h < H; ++h) {
+                    const int r2 = gl * H + h;
+                    const float sc = S0[r2] + S1[r2] + tail[100];
+                    const float se = expf(sc) * (sc != 0.0f ? 1.0f : 0.0f);
+                    ssum += se;
+                    if (r2 == row) mine = se;
+                }
+                w = mine / ssum;
             }
             uint32_t v[32];
-            ld32(tlane + 0, v);
+            ld32(tlane + T_F + hf * 32, v);
             wait_ld();
 #pragma unroll
-            for (int k = 0; k < 32; ++k) WF[r * 52 + k] = w * __uint_as_float(v[k]);
-            uint32_t u[16];
-            ld16(tlane + 32, u);
-            wait_ld();
-#pragma unroll
-            for (int k = 0; k < 16; ++k) WF[r * 52 + 32 + k] = w * __uint_as_float(u[k]);
-            uint32_t t2[16];
-            ld16(tlane + 48, t2);
-            wait_ld();
-            WF[r * 52 + 48] = w * __uint_as_float(t2[0]);
-            WF[r * 52 + 49] = w * __uint_as_float(t2[1]);
+            for (int c = 0; c < 4; ++c) {
+                const float *f = reinterpret_cast<const float *>(v) + c * 8;
+                uint4 o;
+                o.x = h2(w * f[0], w * f[1]); o.y = h2(w * f[2], w * f[3]);
+                o.z = h2(w * f[4], w * f[5]); o.w = h2(w * f[6], w * f[7]);
+                *reinterpret_cast<uint4 *>(bufB + chunk_off(ROWS, row, hf * 4 + c)) = o;
+            }
         }
+        fence_async_smem();
         fence_before_sync();
         __syncthreads();
-        // ---- weighted feature = sum over the group's rows (sarl.py:57-60) -> J chunks 0..6 ----
-        for (int it = tid; it < G * 7; it += blockDim.x) {
-            const int gl = it / 7, c = it - gl * 7, g = g0 + gl;
-            if (g >= NG) continue;
-            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            const int ncol = (c < 6) ? 8 : 2;
-            for (int h = 0; h < H; ++h) {
-                const float *row = WF + (gl * H + h) * 52 + c * 8;
-                for (int k = 0; k < ncol; ++k) acc[k] += row[k];
-            }
-            uint8_t *jt = J + (size_t)(g >> 7) * J_TILE_BYTES;
-            *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, g & 127, c)) =
-                make_uint4(h2(acc[0], acc[1]), h2(acc[2], acc[3]), h2(acc[4], acc[5]), h2(acc[6], acc[7]));
+        if (tid == 0) {
+            fence_after_sync();
+            mma_layer_bmn(tmem + T_D2, sA, ROWS, sB, ROWS, N_F, false);
+            commit(mbar);
         }
-        __syncthreads();   // WF (bufA) is reused as the env staging area of the next tile
+        mbar_wait(mbar, phase); phase ^= 1;
+        fence_after_sync();
+        // ---- weighted feature of group g (TMEM lane g) -> J chunks 0..6 (fp16) ----
+        if (tid < 128 && (tid >> 5) * 32 < G) {       // warp-uniform: tcgen05.ld is .sync.aligned
+            uint32_t v[32], u[32];
+            ld32(tlane + T_D2, v);
+            ld32(tlane + T_D2 + 32, u);
+            wait_ld();
+            const int g = g0 + tid;
+            if (tid < G && g < NG) {
+                uint8_t *jt = J + (size_t)(g >> 7) * J_TILE_BYTES;
+                const int rb = g & 127;
+                const float *f = reinterpret_cast<const float *>(v);
+                const float *f2 = reinterpret_cast<const float *>(u);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, c)) =
+                        make_uint4(h2(f[8 * c], f[8 * c + 1]), h2(f[8 * c + 2], f[8 * c + 3]),
+                                   h2(f[8 * c + 4], f[8 * c + 5]), h2(f[8 * c + 6], f[8 * c + 7]));
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 4 + c)) =
+                        make_uint4(h2(f2[8 * c], f2[8 * c + 1]), h2(f2[8 * c + 2], f2[8 * c + 3]),
+                                   h2(f2[8 * c + 4], f2[8 * c + 5]), h2(f2[8 * c + 6], f2[8 * c + 7]));
+            }
+        }
+        fence_before_sync();
+        __syncthreads();   // bufA / bufB / TMEM are reused by the next tile
     }
     fence_before_sync();
     __syncthreads();
@@ -371,18 +425,21 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
 }
 
 // =====================================================================================================
-// kernel B: mlp3 on the joint states + scoring
+// kernel B: mlp3 on the joint states + scoring (256 threads, same lane-quarter / column-half split)
 // =====================================================================================================
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(kThreadsTC, 1)
 tc_mlp3_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *__restrict__ wimg,
                const uint8_t *__restrict__ J, const double *__restrict__ rew, int A, int NG, double gamma,
                double gamma_bar_host, double v_pref_host, double *__restrict__ values, int ntiles)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, hf = warp >> 2;
+    const int row = q * 32 + lane;
     uint8_t *bufJ = smem + B_BUFJ, *bufU0 = smem + B_BUFU0, *bufU1 = smem + B_BUFU1;
-    const uint32_t mbar = smem_u32(smem + B_MISC);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + B_MISC + 8);
+    float *S1 = reinterpret_cast<float *>(smem + B_MISC);          // [128] partial of the upper column half
+    const uint32_t mbar = smem_u32(smem + B_MISC + 512);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + B_MISC + 512 + 8);
     const float *tail = reinterpret_cast<const float *>(smem + OFF_TAILB);
 
     copy_image_to_smem(smem, wimg, IMG_B_BYTES);
@@ -393,15 +450,22 @@ tc_mlp3_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *__rest
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
     const uint32_t sM1 = smem_u32(smem + OFF_M1), sM2 = smem_u32(smem + OFF_M2), sM3 = smem_u32(smem + OFF_M3);
     const uint32_t sJ = smem_u32(bufJ), sU0 = smem_u32(bufU0), sU1 = smem_u32(bufU1);
     uint32_t phase = 0;
+    constexpr int kJVec = J_TILE_BYTES / 16 / kThreadsTC;   // 5 x 16 B per thread
+    static_assert(J_TILE_BYTES == kJVec * 16 * kThreadsTC, "J tile must split evenly");
 
+    uint4 pre[kJVec];
+    if ((int)blockIdx.x < ntiles) {
+        const uint8_t *src = J + (size_t)blockIdx.x * J_TILE_BYTES;
+#pragma unroll
+        for (int i = 0; i < kJVec; ++i) pre[i] = *reinterpret_cast<const uint4 *>(src + (size_t)(i * kThreadsTC + tid) * 16);
+    }
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint8_t *src = J + (size_t)tile * J_TILE_BYTES;
-        for (uint32_t i = tid * 16; i < J_TILE_BYTES; i += blockDim.x * 16)
-            *reinterpret_cast<uint4 *>(bufJ + i) = *reinterpret_cast<const uint4 *>(src + i);
+#pragma unroll
+        for (int i = 0; i < kJVec; ++i) *reinterpret_cast<uint4 *>(bufJ + (size_t)(i * kThreadsTC + tid) * 16) = pre[i];
         fence_async_smem();
         __syncthreads();
         if (tid == 0) {   // mlp3.0
@@ -409,9 +473,15 @@ tc_mlp3_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *__rest
             mma_layer(tmem + 0, sJ, ROWS, sM1, N_H1, K_J, N_H1, false);
             commit(mbar);
         }
+        if (tile + (int)gridDim.x < ntiles) {   // prefetch the next joint-state tile while the tensor cores work
+            const uint8_t *src = J + (size_t)(tile + gridDim.x) * J_TILE_BYTES;
+#pragma unroll
+            for (int i = 0; i < kJVec; ++i) pre[i] = *reinterpret_cast<const uint4 *>(src + (size_t)(i * kThreadsTC + tid) * 16);
+        }
         mbar_wait(mbar, phase); phase ^= 1;
         fence_after_sync();
-        epilogue_to_smem<true>(tlane, 0, N_H1, bufU0, tid, 0);
+        if (hf == 0) epilogue_to_smem<true>(tlane, 0, 96, bufU0, row, 0);
+        else epilogue_to_smem<true>(tlane, 96, 64, bufU0, row, 12);
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
@@ -422,7 +492,8 @@ tc_mlp3_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *__rest
         }
         mbar_wait(mbar, phase); phase ^= 1;
         fence_after_sync();
-        epilogue_to_smem<true>(tlane, 0, N_M1, bufU1, tid, 0);
+        if (hf == 0) epilogue_to_smem<true>(tlane, 0, 64, bufU1, row, 0);
+        else epilogue_to_smem<true>(tlane, 64, 48, bufU1, row, 8);
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
@@ -434,31 +505,42 @@ tc_mlp3_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *__rest
         mbar_wait(mbar, phase); phase ^= 1;
         fence_after_sync();
         // mlp3.6 as an fp32 dot over ReLU(mlp3.4), then value = reward + gamma_bar * V (multi_human_rl.py:52)
-        float v = tail[100];
+        float part = 0.0f;
+        if (hf == 0) {
 #pragma unroll 1
-        for (int c0 = 0; c0 < 96; c0 += 32) {
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t x[32];
+                ld32(tlane + c0, x);
+                wait_ld();
+#pragma unroll
+                for (int k = 0; k < 32; ++k) part = fmaf(fmaxf(__uint_as_float(x[k]), 0.0f), tail[c0 + k], part);
+            }
+        } else {
             uint32_t x[32];
-            ld32(tlane + c0, x);
+            ld32(tlane + 64, x);
             wait_ld();
 #pragma unroll
-            for (int k = 0; k < 32; ++k) v = fmaf(fmaxf(__uint_as_float(x[k]), 0.0f), tail[c0 + k], v);
-        }
-        {
-            uint32_t x[16];
-            ld16(tlane + 96, x);
+            for (int k = 0; k < 32; ++k) part = fmaf(fmaxf(__uint_as_float(x[k]), 0.0f), tail[64 + k], part);
+            uint32_t u[16];
+            ld16(tlane + 96, u);
             wait_ld();
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v = fmaf(fmaxf(__uint_as_float(x[k]), 0.0f), tail[96 + k], v);
-        }
-        const int g = tile * ROWS + tid;
-        if (g < NG) {
-            const int e = g / A;
-            const double vp = st[st_idx(p.d, F_VPREF, 0, e)];
-            const double gamma_bar = (vp == v_pref_host) ? gamma_bar_host : pow(gamma, p.time_step * vp);
-            values[g] = rew[g] + gamma_bar * (double)v;
+            for (int k = 0; k < 4; ++k) part = fmaf(fmaxf(__uint_as_float(u[k]), 0.0f), tail[96 + k], part);
+            S1[row] = part;
         }
         fence_before_sync();
         __syncthreads();
+        if (hf == 0) {
+            const float v = part + S1[row] + tail[100];
+            const int g = tile * ROWS + row;
+            if (g < NG) {
+                const int e = g / A;
+                const double vp = st[st_idx(p.d, F_VPREF, 0, e)];
+                const double gamma_bar = (vp == v_pref_host) ? gamma_bar_host : pow(gamma, p.time_step * vp);
+                values[g] = rew[g] + gamma_bar * (double)v;
+            }
+        }
+        // S1 is rewritten only after the next tile's three barriers; bufJ after the next loop-top barrier
     }
     fence_before_sync();
     __syncthreads();
@@ -470,11 +552,11 @@ tc_mlp3_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *__rest
 // =====================================================================================================
 __global__ void __launch_bounds__(128, 1)
 umma_selftest_kernel(const uint8_t *__restrict__ a_img, const uint8_t *__restrict__ b_img, float *__restrict__ d,
-                     int N, int K)
+                     int N, int K, int b_mn_major)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
-    const uint32_t a_bytes = bytes_of(ROWS, K), b_bytes = bytes_of(N, K);
+    const uint32_t a_bytes = bytes_of(ROWS, K), b_bytes = b_mn_major ? bytes_of(ROWS, N) : bytes_of(N, K);
     uint8_t *sa = smem, *sb = smem + a_bytes;
     uint8_t *misc = smem + ((a_bytes + b_bytes + 15) & ~15u);
     const uint32_t mbar = smem_u32(misc);
@@ -490,7 +572,8 @@ umma_selftest_kernel(const uint8_t *__restrict__ a_img, const uint8_t *__restric
     const uint32_t tmem = *tmem_slot;
     const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
     if (tid == 0) {
-        mma_layer(tmem, smem_u32(sa), ROWS, smem_u32(sb), N, K, N, false);
+        if (b_mn_major) mma_layer_bmn(tmem, smem_u32(sa), ROWS, smem_u32(sb), K, N, false);
+        else mma_layer(tmem, smem_u32(sa), ROWS, smem_u32(sb), N, K, N, false);
         commit(mbar);
     }
     mbar_wait(mbar, 0);
@@ -641,24 +724,31 @@ int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cu
     const double gamma_bar = pow(p->cfg.gamma, env->p.time_step * p->cfg.v_pref);
     const int grid_a = ntiles_a < t->num_sms ? ntiles_a : t->num_sms;
     const int grid_b = ntiles_b < t->num_sms ? ntiles_b : t->num_sms;
-    tc_rows_kernel<<<grid_a, 128, A_SMEM, s>>>(env->p, env->state, env->time, env->human_v, p->action_dev, A, query_env,
+    tc_rows_kernel<<<grid_a, kThreadsTC, A_SMEM, s>>>(env->p, env->state, env->time, env->human_v, p->action_dev, A, query_env,
                                                t->img_a, t->J, t->rew, (int)NG, G, ntiles_a);
     CN_LAUNCH_CHECK();
-    tc_mlp3_kernel<<<grid_b, 128, B_SMEM, s>>>(env->p, env->state, t->img_b, t->J, t->rew, A, (int)NG, p->cfg.gamma,
+    tc_mlp3_kernel<<<grid_b, kThreadsTC, B_SMEM, s>>>(env->p, env->state, t->img_b, t->J, t->rew, A, (int)NG, p->cfg.gamma,
                                                gamma_bar, p->cfg.v_pref, p->values, ntiles_b);
     CN_LAUNCH_CHECK();
     return cn_lookahead_argmax(p, env, epsilon, s);
 }
 
-extern "C" int cn_selftest_umma(int32_t N, int32_t K, const float *a_host, const float *b_host, float *d_host, int device)
+static int selftest_impl(int32_t N, int32_t K, const float *a_host, const float *b_host, float *d_host, int device, int bmn)
 {
-    if (N < 16 || N > 256 || N % 16 || K < 16 || K % 16 || K > 256) { cn_set_error("N in [16,256] step 16, K in [16,256] step 16"); return CN_EINVAL; }
+    if (N < 16 || N > 256 || N % 16 || K < 16 || K % 16 || K > 256 || (bmn && K > ROWS)) {
+        cn_set_error("N in [16,256] step 16, K in [16,256] step 16 (K <= 128 for the MN-major variant)");
+        return CN_EINVAL;
+    }
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); cn_set_error("no CUDA device available; no CPU fallback"); return CN_ECUDA; }
     CN_CUDA_CHECK(cudaSetDevice(device));
-    std::vector<uint8_t> ai(bytes_of(ROWS, K), 0), bi(bytes_of(N, K), 0);
+    std::vector<uint8_t> ai(bytes_of(ROWS, K), 0), bi(bmn ? bytes_of(ROWS, N) : bytes_of(N, K), 0);
     for (int r = 0; r < ROWS; ++r) for (int k = 0; k < K; ++k) put(ai, 0, ROWS, r, k, a_host[(size_t)r * K + k]);
-    for (int r = 0; r < N; ++r) for (int k = 0; k < K; ++k) put(bi, 0, N, r, k, b_host[(size_t)r * K + k]);
+    for (int r = 0; r < N; ++r)
+        for (int k = 0; k < K; ++k) {
+            if (bmn) put(bi, 0, ROWS, k, r, b_host[(size_t)r * K + k]);   // activation-style image: rows = k, columns = n
+            else put(bi, 0, N, r, k, b_host[(size_t)r * K + k]);
+        }
     uint8_t *da = nullptr, *db = nullptr;
     float *dd = nullptr;
     CN_CUDA_CHECK(cudaMalloc((void **)&da, ai.size()));
@@ -668,10 +758,20 @@ extern "C" int cn_selftest_umma(int32_t N, int32_t K, const float *a_host, const
     CN_CUDA_CHECK(cudaMemcpy(db, bi.data(), bi.size(), cudaMemcpyHostToDevice));
     const size_t smem = ai.size() + bi.size() + 64;
     CN_CUDA_CHECK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    umma_selftest_kernel<<<1, 128, smem>>>(da, db, dd, N, K);
+    umma_selftest_kernel<<<1, 128, smem>>>(da, db, dd, N, K, bmn);
     CN_LAUNCH_CHECK();
     CN_CUDA_CHECK(cudaDeviceSynchronize());
     CN_CUDA_CHECK(cudaMemcpy(d_host, dd, sizeof(float) * ROWS * N, cudaMemcpyDeviceToHost));
     cudaFree(da); cudaFree(db); cudaFree(dd);
     return CN_OK;
+}
+
+extern "C" int cn_selftest_umma(int32_t N, int32_t K, const float *a_host, const float *b_host, float *d_host, int device)
+{
+    return selftest_impl(N, K, a_host, b_host, d_host, device, 0);
+}
+
+extern "C" int cn_selftest_umma_bmn(int32_t N, int32_t K, const float *a_host, const float *b_host, float *d_host, int device)
+{
+    return selftest_impl(N, K, a_host, b_host, d_host, device, 1);
 }

@@ -39,6 +39,22 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_
         :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// Same with the B operand MN-major (idesc bit 16): B is read from a 128-row activation-style image whose
+// ROWS are the K index and whose columns are N, i.e. element (k, n) at (n/8)*2048 + k*16 + (n%8)*2 -- exactly
+// what epilogue_to_smem writes.  In descriptor terms: SBO (8-wide N-group stride) = 2048, LBO (8-row K-group
+// stride) = 128; each K=16 step advances the start address by 256 B.
+__device__ __forceinline__ void mma_layer_bmn(uint32_t tmem_d, uint32_t a_base, uint32_t a_rows, uint32_t b_base,
+                                              int K, int N, bool accumulate_first)
+{
+    const uint32_t idesc = make_idesc_f16(N) | (1u << 16);
+    const uint32_t a_lbo = a_rows * 16;
+    for (int s = 0; s < K / 16; ++s) {
+        const uint64_t ad = make_desc(a_base + (uint32_t)s * 2 * a_lbo, a_lbo, 128);
+        const uint64_t bd = make_desc(b_base + (uint32_t)s * 256, 128, 2048);
+        mma_f16(tmem_d, ad, bd, idesc, (s > 0 || accumulate_first) ? 1u : 0u);
+    }
+}
+
 // D[128 x N] (+)= A[128 x K] * B[N x K]^T, K a multiple of 16; one elected thread calls this.
 // a_base/b_base: shared addresses of chunked K-major operands with a_rows / b_rows rows.
 __device__ __forceinline__ void mma_layer(uint32_t tmem_d, uint32_t a_base, uint32_t a_rows, uint32_t b_base,

@@ -338,8 +338,9 @@ def test_host_step_matches_device_step(mcn, oracle_mod, weights0):
     env_a.close(); env_b.close(); pol.close()
 
 
-@pytest.mark.parametrize("N,K", [(16, 16), (64, 112), (112, 112), (160, 32), (112, 224), (160, 80), (256, 64)])
-def test_umma_selftest(mcn, N, K):
+@pytest.mark.parametrize("N,K,bmn", [(16, 16, 0), (64, 112, 0), (112, 112, 0), (160, 32, 0), (112, 224, 0), (160, 80, 0),
+                                     (256, 64, 0), (64, 128, 1), (112, 128, 1), (16, 16, 1), (64, 48, 1)])
+def test_umma_selftest(mcn, N, K, bmn):
     """tcgen05.mma building block (descriptor / chunked K-major layout / TMEM read-back) vs fp32 matmul."""
     import ctypes as C
     rs = np.random.RandomState(N * 1000 + K)
@@ -347,7 +348,8 @@ def test_umma_selftest(mcn, N, K):
     b = rs.uniform(-1, 1, (N, K)).astype(np.float16).astype(np.float32)
     d = np.zeros((128, N), np.float32)
     lib = mcn._capi.load()
-    mcn._capi.check(lib.cn_selftest_umma(N, K, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
+    fn = lib.cn_selftest_umma_bmn if bmn else lib.cn_selftest_umma
+    mcn._capi.check(fn(N, K, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
                                          d.ctypes.data_as(C.c_void_p), 0))
     ref = a.astype(np.float64) @ b.astype(np.float64).T
     assert np.max(np.abs(d - ref)) < 1e-4 * K
