@@ -106,6 +106,117 @@ __device__ __forceinline__ void split_hl(float x, float &hi, float &lo)
 // =====================================================================================================
 constexpr int kThreadsTC = 256;
 
+// Inputs of one (env, action, human) row, fetched straight from the SoA (L2-resident) one tile ahead.
+struct RowIn {
+    double rpx, rpy, rgx, rgy, rr, rvp, hpx, hpy, hvx, hvy, hr, ax, ay;
+    int valid;
+};
+
+__device__ __forceinline__ void load_row_inputs(RowIn &in, const EnvDims &ed, const double *__restrict__ st,
+                                                const double *__restrict__ human_v, const double *__restrict__ actions,
+                                                int A, int query_env, int NG, int G, int tile, int r)
+{
+    const int H = ed.H;
+    const int gl = r / H, h = r - gl * H, g = tile * G + gl;
+    in.valid = (gl < G && g < NG) ? 1 : 0;
+    if (!in.valid) return;
+    const int e = g / A, a = g - e * A;
+    in.rpx = st[st_idx(ed, F_PX, 0, e)]; in.rpy = st[st_idx(ed, F_PY, 0, e)];
+    in.rgx = st[st_idx(ed, F_GX, 0, e)]; in.rgy = st[st_idx(ed, F_GY, 0, e)];
+    in.rr = st[st_idx(ed, F_R, 0, e)];   in.rvp = st[st_idx(ed, F_VPREF, 0, e)];
+    in.hpx = st[st_idx(ed, F_PX, h + 1, e)]; in.hpy = st[st_idx(ed, F_PY, h + 1, e)];
+    in.hr = st[st_idx(ed, F_R, h + 1, e)];
+    if (query_env) {                                                                    // agent.py:63-74
+        in.hvx = human_v[(size_t)(0 * H + h) * ed.E + e]; in.hvy = human_v[(size_t)(1 * H + h) * ed.E + e];
+    } else {                                                                            // cadrl.py:107-109
+        in.hvx = st[st_idx(ed, F_VX, h + 1, e)]; in.hvy = st[st_idx(ed, F_VY, h + 1, e)];
+    }
+    in.ax = actions[2 * a]; in.ay = actions[2 * a + 1];
+}
+
+// propagate + rotate (cadrl.py:104-129,217-252) -> the four 16-byte K-chunks of the X operand row:
+// [x_hi(13) 1 1 0 | x_lo(13) 0 0 0]
+__device__ __forceinline__ void row_features(const RowIn &in, double dt, uint4 &c0, uint4 &c1, uint4 &c2, uint4 &c3)
+{
+    c0 = make_uint4(0, 0, 0, 0); c1 = c0; c2 = c0; c3 = c0;
+    if (!in.valid) return;
+    float s[14], o[13];
+    s[0] = (float)(in.rpx + in.ax * dt); s[1] = (float)(in.rpy + in.ay * dt);
+    s[2] = (float)in.ax; s[3] = (float)in.ay; s[4] = (float)in.rr;
+    s[5] = (float)in.rgx; s[6] = (float)in.rgy; s[7] = (float)in.rvp; s[8] = 0.0f;
+    s[9] = (float)(in.hpx + in.hvx * dt); s[10] = (float)(in.hpy + in.hvy * dt);
+    s[11] = (float)in.hvx; s[12] = (float)in.hvy; s[13] = (float)in.hr;
+    cn_rotate(s, o);
+    float hi[13], lo[13];
+#pragma unroll
+    for (int k = 0; k < 13; ++k) split_hl(o[k], hi[k], lo[k]);
+    c0 = make_uint4(h2(hi[0], hi[1]), h2(hi[2], hi[3]), h2(hi[4], hi[5]), h2(hi[6], hi[7]));
+    c1 = make_uint4(h2(hi[8], hi[9]), h2(hi[10], hi[11]), h2(hi[12], 1.0f), h2(1.0f, 0.0f));
+    c2 = make_uint4(h2(lo[0], lo[1]), h2(lo[2], lo[3]), h2(lo[4], lo[5]), h2(lo[6], lo[7]));
+    c3 = make_uint4(h2(lo[8], lo[9]), h2(lo[10], lo[11]), h2(lo[12], 0.0f), 0u);
+}
+
+// Per (env, action) group: lookahead reward -> rew[g]; self-state part of the joint state -> J chunks 7..9.
+__device__ __forceinline__ void group_work(const EnvParams &p, const double *__restrict__ st,
+                                           const double *__restrict__ time, const double *__restrict__ human_v,
+                                           const double *__restrict__ actions, int A, int query_env, int NG, int G,
+                                           int tile, int gl, uint8_t *__restrict__ J, double *__restrict__ rew)
+{
+    const EnvDims ed = p.d;
+    const int H = ed.H;
+    const int g = tile * G + gl;
+    if (gl >= G || g >= NG) return;
+    const int e = g / A, a = g - e * A;
+    const double dt = p.time_step;
+    auto ag = [&](int f, int agent) { return st[st_idx(ed, f, agent, e)]; };
+    const double ax = actions[2 * a], ay = actions[2 * a + 1];
+    const double rpx = ag(F_PX, 0), rpy = ag(F_PY, 0), rr = ag(F_R, 0), rgx = ag(F_GX, 0), rgy = ag(F_GY, 0);
+    double reward;
+    if (query_env) {
+        reward = cn_step_outcome(p, ag, H, time[e], ax, ay).reward;                     // crowd_sim.py:325-329
+    } else {
+        // multi_human_rl.py:65-88
+        const double npx = rpx + ax * dt, npy = rpy + ay * dt;
+        double dmin = INFINITY;
+        bool collision = false;
+        for (int h = 1; h <= H; ++h) {
+            const double nhx = ag(F_PX, h) + ag(F_VX, h) * dt, nhy = ag(F_PY, h) + ag(F_VY, h) * dt;
+            const double dist = norm2d(npx - nhx, npy - nhy) - rr - ag(F_R, h);
+            if (dist < 0) { collision = true; break; }
+            if (dist < dmin) dmin = dist;
+        }
+        const bool reaching_goal = norm2d(npx - rgx, npy - rgy) < rr;
+        if (collision) reward = -0.25;
+        else if (reaching_goal) reward = 1;
+        else if (dmin < 0.2) reward = (dmin - 0.2) * 0.5 * dt;
+        else reward = 0;
+    }
+    rew[g] = reward;
+    // self state = rotated row columns 0..5 (sarl.py:36): dg, v_pref, theta(0), radius, vx', vy'
+    float s[14], o[13];
+    s[0] = (float)(rpx + ax * dt); s[1] = (float)(rpy + ay * dt); s[2] = (float)ax; s[3] = (float)ay;
+    s[4] = (float)rr; s[5] = (float)rgx; s[6] = (float)rgy; s[7] = (float)ag(F_VPREF, 0); s[8] = 0.0f;
+    s[9] = s[10] = s[11] = s[12] = s[13] = 0.0f;
+    cn_rotate(s, o);
+    float hi[6], lo[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) split_hl(o[k], hi[k], lo[k]);
+    uint8_t *jt = J + (size_t)(g >> 7) * J_TILE_BYTES;
+    const int rb = g & 127;
+    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 7)) =
+        make_uint4(h2(hi[0], hi[1]), h2(hi[2], hi[3]), h2(hi[4], hi[5]), h2(1.0f, 1.0f));
+    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 8)) =
+        make_uint4(h2(lo[0], lo[1]), h2(lo[2], lo[3]), h2(lo[4], lo[5]), 0u);
+    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 9)) = make_uint4(0, 0, 0, 0);
+}
+
+__device__ __forceinline__ void pin(const uint4 &a, const uint4 &b, const uint4 &c, const uint4 &d)
+{
+    // keeps the prefetched feature words computed where they are written in the source (under the MMA wait)
+    asm volatile("" :: "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w),
+                       "r"(c.x), "r"(c.y), "r"(c.z), "r"(c.w), "r"(d.x), "r"(d.y), "r"(d.z), "r"(d.w));
+}
+
 __global__ void __launch_bounds__(kThreadsTC, 1)
 tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restrict__ time,
                const double *__restrict__ human_v, const double *__restrict__ actions, int A, int query_env,
@@ -114,7 +225,7 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const EnvDims ed = p.d;
-    const int H = ed.H, A1 = ed.A1;
+    const int H = ed.H;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, hf = warp >> 2;
     const int row = q * 32 + lane;            // TMEM lane == tile row owned by this thread
@@ -124,7 +235,19 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
     const uint32_t mbar = smem_u32(smem + A_MISC + 1024);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + A_MISC + 1024 + 8);
     const float *tail = reinterpret_cast<const float *>(smem + OFF_TAILA);
+    const double dt = p.time_step;
 
+    // features / rewards of this CTA's first tile overlap the weight-image copy
+    uint4 c0, c1, c2, c3;
+    RowIn in;
+    if ((int)blockIdx.x < ntiles) {
+        if (tid < 128) {
+            load_row_inputs(in, ed, st, human_v, actions, A, query_env, NG, G, blockIdx.x, tid);
+            row_features(in, dt, c0, c1, c2, c3);
+        } else {
+            group_work(p, st, time, human_v, actions, A, query_env, NG, G, blockIdx.x, tid - 128, J, rew);
+        }
+    }
     copy_image_to_smem(smem, wimg, IMG_A_BYTES);
     if (tid == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
@@ -139,101 +262,17 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
     const uint32_t sA = smem_u32(bufA), sB = smem_u32(bufB);
     uint32_t phase = 0;
     const int rows = G * H;
-    const int slot_doubles = F_COUNT * A1 + 2 * H + 1;
-    const double dt = p.time_step;
     constexpr int T_F = 0, T_A2 = N_F, T_D2 = N_F + N_M1;   // TMEM columns of the last two stages
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int g0 = tile * G;
-        const int e_first = g0 / A;
-        int g_last = g0 + G - 1;
-        if (g_last >= NG) g_last = NG - 1;
-        const int nslots = g_last / A - e_first + 1;
-        // ---- P0a: stage the (<= 3) environments this tile touches (bufA is free here) ----
-        double *slots = reinterpret_cast<double *>(bufA);
-        for (int i = tid; i < nslots * slot_doubles; i += blockDim.x) {
-            const int sl = i / slot_doubles, j = i - sl * slot_doubles;
-            const int e = e_first + sl;
-            double v;
-            if (j < F_COUNT * A1) { const int a = j / F_COUNT, f = j - a * F_COUNT; v = st[st_idx(ed, f, a, e)]; }
-            else if (j < F_COUNT * A1 + 2 * H) {
-                const int qq = j - F_COUNT * A1, h = qq >> 1, c = qq & 1;
-                v = query_env ? human_v[(size_t)(c * H + h) * ed.E + e] : 0.0;
-            } else v = time[e];
-            slots[i] = v;
-        }
-        __syncthreads();
-        // ---- P0b: features (threads 0..127, one per row) | rewards (threads 128.., one per group) ----
-        if (tid >= 128) {
-            const int gl = tid - 128;
-            if (gl < G && g0 + gl < NG) {
-                const int g = g0 + gl, e = g / A, a = g - e * A;
-                const double *sv = slots + (size_t)(e - e_first) * slot_doubles;
-                auto ag = [&](int f, int agent) { return sv[agent * F_COUNT + f]; };
-                const double ax = actions[2 * a], ay = actions[2 * a + 1];
-                double reward;
-                if (query_env) {
-                    reward = cn_step_outcome(p, ag, H, sv[slot_doubles - 1], ax, ay).reward;   // crowd_sim.py:325-329
-                } else {
-                    // multi_human_rl.py:65-88
-                    const double npx = ag(F_PX, 0) + ax * dt, npy = ag(F_PY, 0) + ay * dt, rr = ag(F_R, 0);
-                    double dmin = INFINITY;
-                    bool collision = false;
-                    for (int h = 1; h <= H; ++h) {
-                        const double nhx = ag(F_PX, h) + ag(F_VX, h) * dt, nhy = ag(F_PY, h) + ag(F_VY, h) * dt;
-                        const double dist = norm2d(npx - nhx, npy - nhy) - rr - ag(F_R, h);
-                        if (dist < 0) { collision = true; break; }
-                        if (dist < dmin) dmin = dist;
-                    }
-                    const bool reaching_goal = norm2d(npx - ag(F_GX, 0), npy - ag(F_GY, 0)) < rr;
-                    if (collision) reward = -0.25;
-                    else if (reaching_goal) reward = 1;
-                    else if (dmin < 0.2) reward = (dmin - 0.2) * 0.5 * dt;
-                    else reward = 0;
-                }
-                rew[g] = reward;
-            }
-        } else {
-            const int r = tid;
-            uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0, c2 = c0, c3 = c0;
-            const int gl = r / H, h = r - gl * H, g = g0 + gl;
-            if (r < rows && g < NG) {
-                const int e = g / A, a = g - e * A;
-                const double *sv = slots + (size_t)(e - e_first) * slot_doubles;
-                auto ag = [&](int f, int agent) { return sv[agent * F_COUNT + f]; };
-                const double ax = actions[2 * a], ay = actions[2 * a + 1];
-                double hvx, hvy;
-                if (query_env) { hvx = sv[F_COUNT * A1 + 2 * h]; hvy = sv[F_COUNT * A1 + 2 * h + 1]; }   // agent.py:63-74
-                else { hvx = ag(F_VX, h + 1); hvy = ag(F_VY, h + 1); }                                  // cadrl.py:107-109
-                float s[14], o[13];
-                s[0] = (float)(ag(F_PX, 0) + ax * dt); s[1] = (float)(ag(F_PY, 0) + ay * dt);
-                s[2] = (float)ax; s[3] = (float)ay; s[4] = (float)ag(F_R, 0);
-                s[5] = (float)ag(F_GX, 0); s[6] = (float)ag(F_GY, 0); s[7] = (float)ag(F_VPREF, 0); s[8] = 0.0f;
-                s[9] = (float)(ag(F_PX, h + 1) + hvx * dt); s[10] = (float)(ag(F_PY, h + 1) + hvy * dt);
-                s[11] = (float)hvx; s[12] = (float)hvy; s[13] = (float)ag(F_R, h + 1);
-                cn_rotate(s, o);
-                float hi[13], lo[13];
-#pragma unroll
-                for (int k = 0; k < 13; ++k) split_hl(o[k], hi[k], lo[k]);
-                c0 = make_uint4(h2(hi[0], hi[1]), h2(hi[2], hi[3]), h2(hi[4], hi[5]), h2(hi[6], hi[7]));
-                c1 = make_uint4(h2(hi[8], hi[9]), h2(hi[10], hi[11]), h2(hi[12], 1.0f), h2(1.0f, 0.0f));
-                c2 = make_uint4(h2(lo[0], lo[1]), h2(lo[2], lo[3]), h2(lo[4], lo[5]), h2(lo[6], lo[7]));
-                c3 = make_uint4(h2(lo[8], lo[9]), h2(lo[10], lo[11]), h2(lo[12], 0.0f), 0u);
-                if (h == 0) {
-                    // self-state part of the joint state (sarl.py:36,63): J chunks 7 (hi, 1, 1), 8 (lo), 9 (pad)
-                    uint8_t *jt = J + (size_t)(g >> 7) * J_TILE_BYTES;
-                    const int rb = g & 127;
-                    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 7)) =
-                        make_uint4(h2(hi[0], hi[1]), h2(hi[2], hi[3]), h2(hi[4], hi[5]), h2(1.0f, 1.0f));
-                    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 8)) =
-                        make_uint4(h2(lo[0], lo[1]), h2(lo[2], lo[3]), h2(lo[4], lo[5]), 0u);
-                    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 9)) = make_uint4(0, 0, 0, 0);
-                }
-            }
-            *reinterpret_cast<uint4 *>(bufB + chunk_off(ROWS, r, 0)) = c0;
-            *reinterpret_cast<uint4 *>(bufB + chunk_off(ROWS, r, 1)) = c1;
-            *reinterpret_cast<uint4 *>(bufB + chunk_off(ROWS, r, 2)) = c2;
-            *reinterpret_cast<uint4 *>(bufB + chunk_off(ROWS, r, 3)) = c3;
+        const int next = tile + gridDim.x;
+        // ---- X operand of this tile (computed one tile ahead, lives in registers until here) ----
+        if (tid < 128) {
+            *reinterpret_cast<uint4 *>(bufB + chunk_off(ROWS, tid, 0)) = c0;
+            *reinterpret_cast<uint4 *>(bufB + chunk_off(ROWS, tid, 1)) = c1;
+            *reinterpret_cast<uint4 *>(bufB + chunk_off(ROWS, tid, 2)) = c2;
+            *reinterpret_cast<uint4 *>(bufB + chunk_off(ROWS, tid, 3)) = c3;
         }
         fence_async_smem();
         __syncthreads();
@@ -245,7 +284,7 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
         }
         mbar_wait(mbar, phase); phase ^= 1;
         fence_after_sync();
-        if (hf == 0) epilogue_to_smem<true>(tlane, 0, 96, bufA, row, 0);       // H1 (overwrites the env slots)
+        if (hf == 0) epilogue_to_smem<true>(tlane, 0, 96, bufA, row, 0);       // H1
         else epilogue_to_smem<true>(tlane, 96, 64, bufA, row, 12);
         fence_async_smem();
         fence_before_sync();
@@ -256,6 +295,8 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
             mma_layer(tmem + 0, sA, ROWS, sW2, N_M1, N_H1, N_M1, false);
             commit(mbar);
         }
+        // next tile's row inputs: loads fly while the tensor cores work
+        if (tid < 128 && next < ntiles) load_row_inputs(in, ed, st, human_v, actions, A, query_env, NG, G, next, tid);
         mbar_wait(mbar, phase); phase ^= 1;
         fence_after_sync();
         if (hf == 0) epilogue_to_smem<true>(tlane, 0, 64, bufB, row, 0);       // mlp1 output (X is dead)
@@ -296,6 +337,11 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
             mma_layer(tmem + N_M1, sA, ROWS, sWA1 + (N_M1 / 8) * (N_M1 * 16), N_M1, N_M1, N_M1, true);
             commit(mbar);
         }
+        // next tile: rotate + pack (rows) | rewards + self-state chunks (groups), hidden under the longest MMA
+        if (next < ntiles) {
+            if (tid < 128) { row_features(in, dt, c0, c1, c2, c3); pin(c0, c1, c2, c3); }
+            else group_work(p, st, time, human_v, actions, A, query_env, NG, G, next, tid - 128, J, rew);
+        }
         mbar_wait(mbar, phase); phase ^= 1;
         fence_after_sync();
         if (hf == 0) epilogue_to_smem<true>(tlane, 0, N_M1, bufA, row, 0);     // mlp2.0 out
@@ -314,41 +360,45 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
         fence_after_sync();
         // ---- group-selection matrix P'[g][r] = (r / H == g) -> bufA (mlp2.0 tile is dead): the weighted sum over
         //      the humans of a group (sarl.py:57-60) becomes one more UMMA, D2 = P' * (w .* F) ----
-        for (int it = tid; it < ROWS * (ROWS / 8); it += blockDim.x) {
-            const int c = it >> 7, g = it & 127;
-            const int lo = g * H, hi = lo + H, k0 = c * 8;
-            uint32_t wds[4];
+        {
+            const int g = tid & 127, cbase = (tid >> 7) * 8;
+            const int lo = g * H, hi = min(lo + H, rows);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int ka = k0 + 2 * j, kb = ka + 1;
-                const uint32_t a = (ka >= lo && ka < hi && ka < rows) ? 0x3C00u : 0u;   // fp16 1.0
-                const uint32_t b = (kb >= lo && kb < hi && kb < rows) ? 0x3C00u : 0u;
-                wds[j] = a | (b << 16);
+            for (int cc = 0; cc < 8; ++cc) {
+                const int c = cbase + cc, k0 = c * 8;
+                uint4 o = make_uint4(0, 0, 0, 0);
+                if (k0 < hi && k0 + 8 > lo) {
+                    uint32_t wds[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int ka = k0 + 2 * j, kb = ka + 1;
+                        wds[j] = ((ka >= lo && ka < hi) ? 0x3C00u : 0u) | ((kb >= lo && kb < hi) ? 0x3C000000u : 0u);
+                    }
+                    o = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+                }
+                *reinterpret_cast<uint4 *>(bufA + chunk_off(ROWS, g, c)) = o;
             }
-            *reinterpret_cast<uint4 *>(bufA + chunk_off(ROWS, g, c)) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
         }
         // ---- attention.4 (fp32 dot over ReLU(attention.2)), split between the two warps of a lane quarter ----
         {
             float part = 0.0f;
             if (hf == 0) {
-#pragma unroll 1
-                for (int c0 = 0; c0 < 64; c0 += 32) {
-                    uint32_t v[32];
-                    ld32(tlane + T_A2 + c0, v);
-                    wait_ld();
+                uint32_t v[32], u[32];
+                ld32(tlane + T_A2, v);
+                ld32(tlane + T_A2 + 32, u);
+                wait_ld();
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) part = fmaf(fmaxf(__uint_as_float(v[k]), 0.0f), tail[c0 + k], part);
-                }
+                for (int k = 0; k < 32; ++k) part = fmaf(fmaxf(__uint_as_float(v[k]), 0.0f), tail[k], part);
+#pragma unroll
+                for (int k = 0; k < 32; ++k) part = fmaf(fmaxf(__uint_as_float(u[k]), 0.0f), tail[32 + k], part);
                 S0[row] = part;
             } else {
-                uint32_t v[32];
+                uint32_t v[32], u[16];
                 ld32(tlane + T_A2 + 64, v);
+                ld16(tlane + T_A2 + 96, u);
                 wait_ld();
 #pragma unroll
                 for (int k = 0; k < 32; ++k) part = fmaf(fmaxf(__uint_as_float(v[k]), 0.0f), tail[64 + k], part);
-                uint32_t u[16];
-                ld16(tlane + T_A2 + 96, u);
-                wait_ld();
 #pragma unroll
                 for (int k = 0; k < 4; ++k) part = fmaf(fmaxf(__uint_as_float(u[k]), 0.0f), tail[96 + k], part);
                 S1[row] = part;
@@ -402,18 +452,10 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
             if (tid < G && g < NG) {
                 uint8_t *jt = J + (size_t)(g >> 7) * J_TILE_BYTES;
                 const int rb = g & 127;
-                const float *f = reinterpret_cast<const float *>(v);
-                const float *f2 = reinterpret_cast<const float *>(u);
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, c)) =
-                        make_uint4(h2(f[8 * c], f[8 * c + 1]), h2(f[8 * c + 2], f[8 * c + 3]),
-                                   h2(f[8 * c + 4], f[8 * c + 5]), h2(f[8 * c + 6], f[8 * c + 7]));
+                for (int c = 0; c < 4; ++c) cvt_store8<false>(v + 8 * c, jt + chunk_off(ROWS, rb, c));
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 4 + c)) =
-                        make_uint4(h2(f2[8 * c], f2[8 * c + 1]), h2(f2[8 * c + 2], f2[8 * c + 3]),
-                                   h2(f2[8 * c + 4], f2[8 * c + 5]), h2(f2[8 * c + 6], f2[8 * c + 7]));
+                for (int c = 0; c < 3; ++c) cvt_store8<false>(u + 8 * c, jt + chunk_off(ROWS, rb, 4 + c));
             }
         }
         fence_before_sync();

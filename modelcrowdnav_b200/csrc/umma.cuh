@@ -152,47 +152,61 @@ __host__ __device__ __forceinline__ uint32_t chunk_off(uint32_t R, uint32_t r, u
 // Epilogue: TMEM columns [col, col + ncols) of this thread's lane -> fp16 row `row` of a 128-row operand in
 // shared memory starting at K-chunk kc0 (ncols a multiple of 16).  RELU selects cvt.rn.relu.
 template <bool RELU>
+__device__ __forceinline__ void cvt_store8(const uint32_t *v, uint8_t *dst)
+{
+    const float *f = reinterpret_cast<const float *>(v);
+    uint4 o;
+    if (RELU) {
+        o.x = pack_f16x2_relu(f[0], f[1]); o.y = pack_f16x2_relu(f[2], f[3]);
+        o.z = pack_f16x2_relu(f[4], f[5]); o.w = pack_f16x2_relu(f[6], f[7]);
+    } else {
+        o.x = pack_f16x2(f[0], f[1]); o.y = pack_f16x2(f[2], f[3]);
+        o.z = pack_f16x2(f[4], f[5]); o.w = pack_f16x2(f[6], f[7]);
+    }
+    *reinterpret_cast<uint4 *>(dst) = o;
+}
+
+template <bool RELU>
 __device__ __forceinline__ void epilogue_to_smem(uint32_t taddr_lane, int col, int ncols, uint8_t *dst, int row, int kc0)
 {
     int done = 0;
-    while (done < ncols) {
-        if (ncols - done >= 32) {
-            uint32_t v[32];
-            ld32(taddr_lane + col + done, v);
-            wait_ld();
+    while (ncols - done >= 64) {          // two TMEM loads in flight per wait
+        uint32_t v[32], u[32];
+        ld32(taddr_lane + col + done, v);
+        ld32(taddr_lane + col + done + 32, u);
+        wait_ld();
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint4 o;
-                const float *f = reinterpret_cast<const float *>(v) + q * 8;
-                if (RELU) {
-                    o.x = pack_f16x2_relu(f[0], f[1]); o.y = pack_f16x2_relu(f[2], f[3]);
-                    o.z = pack_f16x2_relu(f[4], f[5]); o.w = pack_f16x2_relu(f[6], f[7]);
-                } else {
-                    o.x = pack_f16x2(f[0], f[1]); o.y = pack_f16x2(f[2], f[3]);
-                    o.z = pack_f16x2(f[4], f[5]); o.w = pack_f16x2(f[6], f[7]);
-                }
-                *reinterpret_cast<uint4 *>(dst + chunk_off(128, row, kc0 + done / 8 + q)) = o;
-            }
-            done += 32;
-        } else {
-            uint32_t v[16];
-            ld16(taddr_lane + col + done, v);
-            wait_ld();
+        for (int q = 0; q < 4; ++q) cvt_store8<RELU>(v + q * 8, dst + chunk_off(128, row, kc0 + done / 8 + q));
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                uint4 o;
-                const float *f = reinterpret_cast<const float *>(v) + q * 8;
-                if (RELU) {
-                    o.x = pack_f16x2_relu(f[0], f[1]); o.y = pack_f16x2_relu(f[2], f[3]);
-                    o.z = pack_f16x2_relu(f[4], f[5]); o.w = pack_f16x2_relu(f[6], f[7]);
-                } else {
-                    o.x = pack_f16x2(f[0], f[1]); o.y = pack_f16x2(f[2], f[3]);
-                    o.z = pack_f16x2(f[4], f[5]); o.w = pack_f16x2(f[6], f[7]);
-                }
-                *reinterpret_cast<uint4 *>(dst + chunk_off(128, row, kc0 + done / 8 + q)) = o;
-            }
-            done += 16;
-        }
+        for (int q = 0; q < 4; ++q) cvt_store8<RELU>(u + q * 8, dst + chunk_off(128, row, kc0 + done / 8 + 4 + q));
+        done += 64;
+    }
+    if (ncols - done >= 48) {
+        uint32_t v[32], u[16];
+        ld32(taddr_lane + col + done, v);
+        ld16(taddr_lane + col + done + 32, u);
+        wait_ld();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cvt_store8<RELU>(v + q * 8, dst + chunk_off(128, row, kc0 + done / 8 + q));
+#pragma unroll
+        for (int q = 0; q < 2; ++q) cvt_store8<RELU>(u + q * 8, dst + chunk_off(128, row, kc0 + done / 8 + 4 + q));
+        done += 48;
+    }
+    if (ncols - done >= 32) {
+        uint32_t v[32];
+        ld32(taddr_lane + col + done, v);
+        wait_ld();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cvt_store8<RELU>(v + q * 8, dst + chunk_off(128, row, kc0 + done / 8 + q));
+        done += 32;
+    }
+    if (ncols - done >= 16) {
+        uint32_t v[16];
+        ld16(taddr_lane + col + done, v);
+        wait_ld();
+#pragma unroll
+        for (int q = 0; q < 2; ++q) cvt_store8<RELU>(v + q * 8, dst + chunk_off(128, row, kc0 + done / 8 + q));
+        done += 16;
     }
 }
 
