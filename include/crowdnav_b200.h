@@ -153,6 +153,9 @@ int cn_env_read_outputs(cn_env *env, double *reward, uint8_t *done, uint8_t *inf
 int cn_env_read_human_actions(cn_env *env, double *human_vxy_host, void *stream);
 /* Blocking host read of update=0 observations as E x H x 5 doubles. */
 int cn_env_read_next_obs(cn_env *env, double *obs_host, void *stream);
+/* Blocking host read of the pending action: xy as E x 2 doubles and/or the action index (E int32, -1 when the
+ * action did not come from the lookahead table); either pointer may be NULL. */
+int cn_env_read_actions(cn_env *env, double *action_xy_host, int32_t *action_idx_host, void *stream);
 /* Set the pending action from the host: E x 2 doubles. */
 int cn_env_set_actions(cn_env *env, const double *action_xy_host, void *stream);
 /* Blocking: reduce the device accumulators (explorer.py counters).  reset != 0 clears them. */

@@ -8,5 +8,13 @@ from . import _capi  # noqa: F401
 from ._capi import CrowdNavError  # noqa: F401
 from .batch import BatchedCrowdSim, BatchedSARL, HostStepBuffers, rollout_step, rollout_step_host  # noqa: F401
 
-__all__ = ["BatchedCrowdSim", "BatchedSARL", "HostStepBuffers", "rollout_step", "rollout_step_host",
+from .envs import (ActionRot, ActionXY, Collision, CrowdSim, Danger, FullState, Human, JointState, Nothing,  # noqa: F401
+                   ObservableState, ReachGoal, Robot, Timeout)
+from .policy import ORCA, SARL, policy_factory  # noqa: F401
+from .explorer import Explorer, ReplayMemory  # noqa: F401
+
+__all__ = ["CrowdSim", "Robot", "Human", "SARL", "ORCA", "policy_factory", "Explorer", "ReplayMemory",
+           "ActionXY", "ActionRot", "FullState", "ObservableState", "JointState",
+           "Timeout", "ReachGoal", "Danger", "Collision", "Nothing",
+           "BatchedCrowdSim", "BatchedSARL", "HostStepBuffers", "rollout_step", "rollout_step_host",
            "CrowdNavError"]

@@ -74,6 +74,13 @@ class BatchedCrowdSim(object):
     def robot_orca(self, safety_space=0.0, stream=None):
         check(self.lib.cn_env_robot_orca(self.handle, float(safety_space), _stream(stream)))
 
+    def pending_actions(self, stream=None):
+        """(E,2) action xy and (E,) table index of the action chosen by the lookahead / robot ORCA."""
+        xy = np.empty((self.E, 2), np.float64)
+        idx = np.empty(self.E, np.int32)
+        check(self.lib.cn_env_read_actions(self.handle, _ptr(xy), _ptr(idx), _stream(stream)))
+        return xy, idx
+
     def set_actions(self, actions, stream=None):
         actions = np.ascontiguousarray(actions, dtype=np.float64)
         assert actions.shape == (self.E, 2)

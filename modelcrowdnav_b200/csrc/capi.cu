@@ -285,6 +285,22 @@ int cn_env_read_next_obs(cn_env *env, double *obs_host, void *stream)
     return CN_OK;
 }
 
+int cn_env_read_actions(cn_env *env, double *action_xy_host, int32_t *action_idx_host, void *stream)
+{
+    CN_ENV_ENTER(env);
+    const size_t E = env->p.d.E;
+    if (action_xy_host) {
+        // pending action is 2 x E on the device; transpose through the staging buffer
+        int rc = cn_launch_transpose_out((int)E, 1, 2, env->action_xy, env->stage, s);
+        if (rc) return rc;
+        CN_CUDA_CHECK(cudaMemcpyAsync(action_xy_host, env->stage, sizeof(double) * 2 * E, cudaMemcpyDeviceToHost, s));
+    }
+    if (action_idx_host)
+        CN_CUDA_CHECK(cudaMemcpyAsync(action_idx_host, env->action_idx, sizeof(int32_t) * E, cudaMemcpyDeviceToHost, s));
+    CN_CUDA_CHECK(cudaStreamSynchronize(s));
+    return CN_OK;
+}
+
 int cn_env_set_actions(cn_env *env, const double *action_xy_host, void *stream)
 {
     CN_ENV_ENTER(env);

@@ -1,0 +1,286 @@
+"""Batched episode driver: mirror of crowd_nav/utils/explorer.py:13-193 and crowd_nav/utils/memory.py:4-34.
+
+`Explorer.run_k_episodes(k, phase, ...)` keeps the reference's signature, log lines and return values, but the
+k episodes run side by side as k environments of one GPU batch (cases c, c+1, ... exactly as k successive
+`env.reset(phase)` calls would pick them).  The inner loop of the reference (explorer.py:62-69: act, step) is one
+`cn_rollout_step`-style sequence per step for all envs; only rewards / done / info codes come back to the host.
+
+Replay filling (`update_memory`, explorer.py:153-186) is batched as well: states are kept as (T, k, H, 13) device
+tensors, IL targets are discounted returns-to-go, RL targets r + gamma_bar * V_target(s') with V_target evaluated
+by the FP32 CUDA value network (cn_policy_forward).
+"""
+import copy
+import logging
+
+import numpy as np
+
+from . import _capi, scenes
+from .batch import BatchedCrowdSim
+from .envs import batch_env_kwargs
+from .policy import ORCA, SARL
+
+
+class ReplayMemory(object):
+    """Ring buffer of (state (H,13) fp32, value (1,) fp32) pairs (memory.py:4-34), stored as two device tensors."""
+
+    def __init__(self, capacity, device=None):
+        self.capacity = capacity
+        self.device = device
+        self.states = None       # (capacity, H, 13)
+        self.values = None       # (capacity, 1)
+        self.size = 0
+        self.position = 0
+
+    def _ensure(self, state):
+        import torch
+        if self.states is None:
+            dev = self.device if self.device is not None else state.device
+            self.states = torch.zeros((self.capacity,) + tuple(state.shape), dtype=torch.float32, device=dev)
+            self.values = torch.zeros((self.capacity, 1), dtype=torch.float32, device=dev)
+
+    def push(self, item):
+        state, value = item
+        self._ensure(state)
+        self.states[self.position] = state
+        self.values[self.position] = value.reshape(1)
+        self.size = max(self.size, self.position + 1) if self.size < self.capacity else self.capacity
+        self.position = (self.position + 1) % self.capacity
+
+    def push_batch(self, states, values):
+        """states (n, H, 13), values (n,) -- same ring semantics as n successive push() calls."""
+        import torch
+        n = states.shape[0]
+        if n == 0:
+            return
+        self._ensure(states[0])
+        idx = (self.position + torch.arange(n, device=self.states.device)) % self.capacity
+        if n > self.capacity:           # only the last `capacity` items survive
+            states, values, idx = states[-self.capacity:], values[-self.capacity:], idx[-self.capacity:]
+        self.states[idx] = states.to(self.states.device)
+        self.values[idx] = values.to(self.states.device).reshape(-1, 1).float()
+        self.size = min(self.capacity, max(self.size, self.position + n))
+        self.position = (self.position + n) % self.capacity
+
+    def is_full(self):
+        return self.size == self.capacity
+
+    def __getitem__(self, item):
+        return self.states[item], self.values[item]
+
+    def __len__(self):
+        return self.size
+
+    def clear(self):
+        self.size = 0
+        self.position = 0
+
+
+def average(input_list):
+    return sum(input_list) / len(input_list) if len(input_list) else 0
+
+
+class Explorer(object):
+    def __init__(self, env, robot, device, memory=None, gamma=None, target_policy=None, dist_group=None):
+        self.env = env
+        self.robot = robot
+        self.device = device
+        self.memory = memory
+        self.gamma = gamma
+        self.target_policy = target_policy
+        self.target_model = None
+        self.dist_group = dist_group     # optional torch.distributed group: statistics are all-reduced over ranks
+        self._batches = {}
+        self._target_handle = None
+
+    def update_target_model(self, target_model):
+        """explorer.py:24-25: keep a frozen copy for TD targets; its weights also go to the FP32 CUDA network."""
+        self.target_model = copy.deepcopy(target_model)
+        self._target_handle = None
+
+    # -- GPU plumbing ------------------------------------------------------------------------------
+    def _batch(self, k):
+        key = (k, self.env.human_num)
+        if key not in self._batches:
+            dev = getattr(self.device, "index", None) or 0     # torch.device('cuda') has index None -> GPU 0
+            self._batches[key] = BatchedCrowdSim(k, self.env.human_num, device=dev, gamma=self.gamma or 0.9,
+                                                 **batch_env_kwargs(self.env))
+        return self._batches[key]
+
+    def _target_forward(self, states):
+        """V_target(s) for a (n, H, 13) device tensor via cn_policy_forward (FP32 CUDA kernel)."""
+        policy = self.target_policy if isinstance(self.target_policy, SARL) else self.robot.policy
+        if self._target_handle is None:
+            h = policy.handle(self.robot.v_pref, precision="f32")
+            # a separate handle so that the behaviour policy's weights are untouched
+            from .batch import BatchedSARL
+            d = policy._dims
+            self._target_handle = BatchedSARL(device=h.device, precision="f32", mlp1_dims=d["mlp1_dims"],
+                                              mlp2_dims=d["mlp2_dims"], attn_dims=d["attn_dims"],
+                                              mlp3_dims=d["mlp3_dims"], gamma=policy.gamma, v_pref=self.robot.v_pref)
+            self._target_handle.load_weights(self.target_model.state_dict())
+        return self._target_handle.forward(states.contiguous())
+
+    # -- the reference entry point (explorer.py:36-151) ----------------------------------------------
+    def run_k_episodes(self, k, phase, update_memory=False, imitation_learning=False, episode=None,
+                       print_failure=False, update_raw_ob=False, stay=False, returnRate=True, test_case=None,
+                       returnNav=False, cacheFile=None):
+        import torch
+        env, robot, policy = self.env, self.robot, self.robot.policy
+        policy.set_phase(phase)
+        if update_raw_ob or cacheFile is not None:
+            raise NotImplementedError("raw-observation / SGAN caches belong to the model-based branch (out of scope)")
+        if robot.kinematics != "holonomic":
+            raise NotImplementedError("unicycle kinematics is outside the B200 hot path")
+        cases = env.next_cases(phase, k, test_case)
+        agents = scenes.generate_batch(phase, cases, **env.scene_kwargs(phase))
+        b = self._batch(k)
+        b.set_state(agents, np.zeros(k))
+        dt, v_pref = env.time_step, robot.v_pref
+        robot.time_step = dt                      # CrowdSim.reset does this for every agent (crowd_sim.py:307-309)
+        policy.time_step = dt
+        is_sarl = isinstance(policy, SARL)
+        if is_sarl:
+            if policy.action_space is None:
+                policy.build_action_space(v_pref)
+            if policy.device is None:
+                raise AttributeError("Phase, device attributes have to be set!")
+            if phase == "train" and policy.epsilon is None:
+                raise AttributeError("Epsilon attribute has to be set in training phase")
+            handle = policy.handle(v_pref)
+            eps = float(policy.epsilon) if phase == "train" else 0.0
+        elif not isinstance(policy, ORCA) and not stay:
+            raise NotImplementedError("robot policy %r is not on the B200 hot path" % type(policy).__name__)
+        tr_policy = self.target_policy if (imitation_learning and self.target_policy is not None) else policy
+
+        active = np.ones(k, bool)
+        rewards_t, states_t, active_t = [], [], []
+        final_info = np.zeros(k, np.int64)
+        end_time = np.zeros(k)
+        too_close, min_dist = 0, []
+        max_steps = int(round(env.time_limit / dt)) + 2
+        for _ in range(max_steps):
+            if not active.any():
+                break
+            if update_memory:
+                # policy.last_state = transform(state) (multi_human_rl.py:60-61) / target_policy.transform (explorer.py:163)
+                if not isinstance(tr_policy, SARL):
+                    raise ValueError("update_memory needs a SARL policy (or target_policy) to transform states")
+                states_t.append(tr_policy.handle(v_pref).transform(b))
+            b.orca()
+            if stay:
+                b.set_actions(np.zeros((k, 2)))
+            elif is_sarl:
+                handle.lookahead(b, query_env=policy.query_env, epsilon=eps)
+                try:
+                    handle.read(b, values=False)
+                except _capi.CrowdNavError as e:
+                    if e.code == _capi.CN_EVALUE:
+                        raise ValueError("Value network is not well trained. ")
+                    raise
+            else:
+                b.robot_orca(policy.safety_space)
+            reward, done, info, dmin = b.step(update=True)
+            rewards_t.append(np.where(active, reward, 0.0))
+            active_t.append(active.copy())
+            danger = active & (info == _capi.DANGER)
+            too_close += int(danger.sum())
+            min_dist.extend(dmin[danger].tolist())
+            finished = active & (done != 0)
+            if finished.any():
+                final_info[finished] = info[finished]
+                _, times = b.get_state()
+                end_time[finished] = times[finished]
+            active &= ~finished
+        if active.any():
+            raise ValueError("Invalid end signal from environment")
+
+        R = np.stack(rewards_t)                      # (T, k)
+        M = np.stack(active_t)
+        success = final_info == _capi.REACHGOAL
+        collision = final_info == _capi.COLLISION
+        timeout = final_info == _capi.TIMEOUT
+        success_times = end_time[success].tolist()
+        collision_times = end_time[collision].tolist()
+        timeout_times = [env.time_limit] * int(timeout.sum())
+        collision_cases = np.nonzero(collision)[0].tolist()
+        timeout_cases = np.nonzero(timeout)[0].tolist()
+        disc = np.array([pow(self.gamma, t * robot.time_step * robot.v_pref) for t in range(R.shape[0])]) \
+            if self.gamma is not None else np.ones(R.shape[0])
+        cumulative_rewards = (R * disc[:, None]).sum(0).tolist()
+
+        if update_memory:
+            if self.memory is None or self.gamma is None:
+                raise ValueError("Memory or gamma value is not set!")
+            keep = np.nonzero(success | collision)[0]              # explorer.py:110-113
+            if len(keep):
+                S = torch.stack(states_t)                          # (T, k, H, 13) on the device
+                self._update_memory_batched(S, R, M, keep, imitation_learning)
+
+        counts = np.array([success.sum(), collision.sum(), timeout.sum(), too_close, k], dtype=np.float64)
+        sums = np.array([sum(success_times), sum(collision_times), sum(timeout_times), sum(min_dist),
+                         sum(cumulative_rewards)], dtype=np.float64)
+        if self.dist_group is not None:
+            counts, sums = self._all_reduce(counts, sums)
+        n_success, n_collision, n_timeout, too_close, k_all = (int(x) for x in counts)
+        success_rate, collision_rate = n_success / k_all, n_collision / k_all
+        timeout_rate = (k_all - n_success - n_collision) / k_all
+        assert n_success + n_collision + n_timeout == k_all
+        avg_nav_time = sums[0] / n_success if n_success else env.time_limit
+        avg_return = sums[4] / k_all
+
+        extra_info = "" if episode is None else "in episode {} ".format(episode)
+        if not stay:
+            logging.info("{:<5} {}has success rate: {:.2f}, collision rate: {:.2f}, nav time: {:.2f}, total reward: {:.4f}".
+                         format(phase.upper(), extra_info, success_rate, collision_rate, avg_nav_time, avg_return))
+        if phase in ["val", "test"]:
+            num_step = (sums[0] + sums[1] + sums[2]) / robot.time_step
+            logging.info("Frequency of being in danger: %.2f and average min separate distance in danger: %.2f",
+                         too_close / num_step, sums[3] / too_close if too_close else 0)
+        if print_failure:
+            logging.info("Collision cases: " + " ".join([str(x) for x in collision_cases]))
+            logging.info("Timeout cases: " + " ".join([str(x) for x in timeout_cases]))
+        self.last_run = dict(cases=cases, info=final_info, end_time=end_time, steps=M.sum(0), too_close=too_close,
+                             returns=np.array(cumulative_rewards))
+        if returnRate and returnNav:
+            return avg_return, success_rate, collision_rate, timeout_rate, avg_nav_time
+        if returnRate:
+            return avg_return, success_rate, collision_rate, timeout_rate
+        return avg_return, n_success, n_collision, (k_all - n_success - n_collision)
+
+    def _all_reduce(self, counts, sums):
+        """Episode statistics summed over ranks: one small all-reduce per run_k_episodes."""
+        import torch
+        import torch.distributed as dist
+        dev = self.device if dist.get_backend(self.dist_group) == "nccl" else "cpu"
+        t = torch.tensor(np.concatenate([counts, sums]), dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.dist_group)
+        t = t.cpu().numpy()
+        return t[:len(counts)], t[len(counts):]
+
+    def _update_memory_batched(self, S, R, M, keep, imitation_learning):
+        """explorer.py:153-186 for every kept episode at once; pushes in episode-then-time order."""
+        import torch
+        T = R.shape[0]
+        dev = S.device
+        gamma_bar = pow(self.gamma, self.robot.time_step * self.robot.v_pref)
+        Rk = torch.as_tensor(R[:, keep], dtype=torch.float64, device=dev)          # (T, n)
+        Mk = torch.as_tensor(M[:, keep], device=dev)
+        if imitation_learning:
+            # value_i = sum_{t >= i} gamma^((t - i) * dt * v_pref) * r_t  (explorer.py:161-166): reverse scan
+            V = torch.zeros_like(Rk)
+            acc = torch.zeros(Rk.shape[1], dtype=torch.float64, device=dev)
+            for t in range(T - 1, -1, -1):
+                acc = Rk[t] + gamma_bar * acc
+                V[t] = acc
+        else:
+            # value_i = r_i + gamma_bar * V_target(s_{i+1}); terminal: r (explorer.py:168-174)
+            Sk = S[:, keep]                                                        # (T, n, H, 13)
+            nxt = torch.zeros((T,) + tuple(Rk.shape[1:]), dtype=torch.float64, device=dev)
+            if T > 1:
+                flat = Sk[1:].reshape((-1,) + tuple(Sk.shape[2:]))
+                nxt[:-1] = self._target_forward(flat).reshape(T - 1, -1).double()
+            last = Mk & ~torch.cat([Mk[1:], torch.zeros_like(Mk[:1])])
+            V = torch.where(last, Rk, Rk + gamma_bar * nxt)
+        for j, e in enumerate(keep):                                               # episode order, then time order
+            n = int(M[:, e].sum())
+            self.memory.push_batch(S[:n, e], V[:n, j].float())

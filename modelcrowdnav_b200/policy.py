@@ -1,0 +1,332 @@
+"""Host-side mirror of the reference policy interface:
+
+    Policy                    crowd_sim/envs/policy/policy.py:5-49
+    ORCA                      crowd_sim/envs/policy/orca.py:7-132      (robot in imitation learning; humans)
+    CADRL.set_common_parameters / build_action_space / set_device / set_epsilon   crowd_nav/policy/cadrl.py:57-102
+    MultiHumanRL.predict / transform                                             crowd_nav/policy/multi_human_rl.py:11-104
+    ValueNetwork, SARL        crowd_nav/policy/sarl.py:9-89
+    policy_factory            crowd_nav/policy/policy_factory.py:6-8, crowd_sim/envs/policy/policy_factory.py:9-12
+
+`SARL.get_model()` returns a torch ValueNetwork with the reference's state-dict keys (mlp1.0.weight ...), so
+`load_state_dict(torch.load('rl_model.pth'))`, optimisers and checkpoints work unchanged; the lookahead itself
+(`predict`) runs on the GPU through the C ABI.  torch is used for tensor hand-off and training only.
+"""
+import logging
+
+import numpy as np
+
+from . import _capi
+from .batch import BatchedCrowdSim, BatchedSARL
+
+
+class Policy(object):
+    def __init__(self):
+        self.trainable = False
+        self.phase = None
+        self.model = None
+        self.device = None
+        self.last_state = None
+        self.time_step = None
+        self.env = None
+
+    def configure(self, config):
+        return
+
+    def set_phase(self, phase):
+        self.phase = phase
+
+    def set_device(self, device):
+        self.device = device
+
+    def set_env(self, env):
+        self.env = env
+
+    def get_model(self):
+        return self.model
+
+    @staticmethod
+    def reach_destination(state):
+        s = state.self_state
+        return bool(np.linalg.norm((s.py - s.gy, s.px - s.gx)) < s.radius)
+
+
+def _cuda_index(device):
+    if device is None:
+        return 0
+    idx = getattr(device, "index", None)
+    return 0 if idx is None else int(idx)
+
+
+def joint_state_to_agents(state):
+    """JointState -> (H+1, 8) exchange rows [px py vx vy gx gy radius v_pref]; unknown human goals = position."""
+    s = state.self_state
+    rows = [[s.px, s.py, s.vx, s.vy, s.gx, s.gy, s.radius, s.v_pref]]
+    for h in state.human_states:
+        rows.append([h.px, h.py, h.vx, h.vy, h.px, h.py, h.radius, 1.0])
+    return np.asarray(rows, dtype=np.float64)
+
+
+class ORCA(Policy):
+    """ORCA policy object (orca.py:7-132).  predict() solves one agent's ORCA problem on the GPU."""
+
+    def __init__(self):
+        super().__init__()
+        self.name = "ORCA"
+        self.trainable = False
+        self.multiagent_training = None
+        self.kinematics = "holonomic"
+        self.safety_space = 0
+        self.neighbor_dist = 10
+        self.max_neighbors = 10
+        self.time_horizon = 5
+        self.time_horizon_obst = 5
+        self.radius = 0.3
+        self.max_speed = 1
+        self._batch = None
+
+    def predict(self, state):
+        from .envs import ActionXY
+        agents = joint_state_to_agents(state)
+        H = agents.shape[0] - 1
+        if self._batch is None or self._batch.H != H:
+            self._batch = BatchedCrowdSim(1, H, device=_cuda_index(self.device), time_step=self.time_step or 0.25,
+                                          neighbor_dist=self.neighbor_dist, max_neighbors=self.max_neighbors,
+                                          time_horizon=self.time_horizon)
+        b = self._batch
+        b.set_state(agents[None])
+        b.robot_orca(self.safety_space)      # self = agent 0, others in list order (orca.py:99-110)
+        xy, _ = b.pending_actions()
+        self.last_state = state
+        return ActionXY(float(xy[0, 0]), float(xy[0, 1]))
+
+
+def mlp(input_dim, mlp_dims, last_relu=False):
+    """cadrl.py:11-19"""
+    import torch.nn as nn
+    layers = []
+    mlp_dims = [input_dim] + list(mlp_dims)
+    for i in range(len(mlp_dims) - 1):
+        layers.append(nn.Linear(mlp_dims[i], mlp_dims[i + 1]))
+        if i != len(mlp_dims) - 2 or last_relu:
+            layers.append(nn.ReLU())
+    return nn.Sequential(*layers)
+
+
+def make_value_network(input_dim, self_state_dim, mlp1_dims, mlp2_dims, mlp3_dims, attention_dims,
+                       with_global_state=True):
+    """torch ValueNetwork with the reference's parameter names and forward (sarl.py:9-65); used for
+    checkpoints, training (autograd) and as the source of the weights uploaded to the CUDA lookahead."""
+    import torch
+    import torch.nn as nn
+
+    class ValueNetwork(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.self_state_dim = self_state_dim
+            self.global_state_dim = mlp1_dims[-1]
+            self.mlp1 = mlp(input_dim, mlp1_dims, last_relu=True)
+            self.mlp2 = mlp(mlp1_dims[-1], mlp2_dims)
+            self.with_global_state = with_global_state
+            self.attention = mlp(mlp1_dims[-1] * 2 if with_global_state else mlp1_dims[-1], attention_dims)
+            self.mlp3 = mlp(mlp2_dims[-1] + self_state_dim, mlp3_dims)
+            self.attention_weights = None
+
+        def forward(self, state):
+            size = state.shape
+            self_state = state[:, 0, :self.self_state_dim]
+            mlp1_output = self.mlp1(state.reshape((-1, size[2])))
+            mlp2_output = self.mlp2(mlp1_output)
+            if self.with_global_state:
+                global_state = torch.mean(mlp1_output.view(size[0], size[1], -1), 1, keepdim=True)
+                global_state = global_state.expand((size[0], size[1], self.global_state_dim)).contiguous().view(
+                    -1, self.global_state_dim)
+                attention_input = torch.cat([mlp1_output, global_state], dim=1)
+            else:
+                attention_input = mlp1_output
+            scores = self.attention(attention_input).view(size[0], size[1], 1).squeeze(dim=2)
+            scores_exp = torch.exp(scores) * (scores != 0).float()
+            weights = (scores_exp / torch.sum(scores_exp, dim=1, keepdim=True)).unsqueeze(2)
+            self.attention_weights = weights[0, :, 0].data.cpu().numpy()
+            features = mlp2_output.view(size[0], size[1], -1)
+            weighted_feature = torch.sum(torch.mul(weights, features), dim=1)
+            joint_state = torch.cat([self_state, weighted_feature], dim=1)
+            return self.mlp3(joint_state)
+
+    return ValueNetwork()
+
+
+class SARL(Policy):
+    """SARL with the MultiHumanRL lookahead on the GPU (sarl.py:68-89, multi_human_rl.py:11-104)."""
+
+    def __init__(self):
+        super().__init__()
+        self.name = "SARL"
+        self.trainable = True
+        self.multiagent_training = None
+        self.kinematics = None
+        self.epsilon = None
+        self.gamma = None
+        self.sampling = None
+        self.speed_samples = None
+        self.rotation_samples = None
+        self.query_env = None
+        self.action_space = None
+        self.speeds = None
+        self.rotations = None
+        self.action_values = None
+        self.with_om = None
+        self.cell_num = self.cell_size = self.om_channel_size = None
+        self.self_state_dim = 6
+        self.human_state_dim = 7
+        self.joint_state_dim = self.self_state_dim + self.human_state_dim
+        self.precision = "f16_tc"      # lookahead arithmetic on the GPU: "f16_tc" (tcgen05) or "f32"
+        self._dims = None
+        self._handles = {}             # (precision, v_pref) -> BatchedSARL
+        self._weights_version = None
+        self._single = None            # one-env batch used by predict()
+
+    # -- configuration (cadrl.py:64-73, sarl.py:73-86) ---------------------------------------------
+    def set_common_parameters(self, config):
+        self.gamma = config.getfloat("rl", "gamma")
+        # policy.config:14 -- the reference fork comments this read out (cadrl.py:66); the north star
+        # specifies the holonomic 81-action space, so it is honoured here.
+        self.kinematics = config.get("action_space", "kinematics")
+        self.sampling = config.get("action_space", "sampling")
+        self.speed_samples = config.getint("action_space", "speed_samples")
+        self.rotation_samples = config.getint("action_space", "rotation_samples")
+        self.query_env = config.getboolean("action_space", "query_env")
+        self.cell_num = config.getint("om", "cell_num")
+        self.cell_size = config.getfloat("om", "cell_size")
+        self.om_channel_size = config.getint("om", "om_channel_size")
+
+    def configure(self, config):
+        self.set_common_parameters(config)
+        if self.kinematics != "holonomic":
+            raise NotImplementedError("only holonomic kinematics is on the B200 hot path (SURVEY §8(f) rank 2)")
+        mlp1_dims = [int(x) for x in config.get("sarl", "mlp1_dims").split(", ")]
+        mlp2_dims = [int(x) for x in config.get("sarl", "mlp2_dims").split(", ")]
+        mlp3_dims = [int(x) for x in config.get("sarl", "mlp3_dims").split(", ")]
+        attention_dims = [int(x) for x in config.get("sarl", "attention_dims").split(", ")]
+        self.with_om = config.getboolean("sarl", "with_om")
+        if self.with_om:
+            raise NotImplementedError("OM-SARL occupancy maps are outside the B200 hot path (SURVEY §8(f) rank 3)")
+        with_global_state = config.getboolean("sarl", "with_global_state")
+        if not with_global_state:
+            raise NotImplementedError("with_global_state = false is not supported by the CUDA lookahead")
+        self._dims = dict(mlp1_dims=mlp1_dims, mlp2_dims=mlp2_dims, attn_dims=attention_dims, mlp3_dims=mlp3_dims)
+        self.model = make_value_network(self.joint_state_dim, self.self_state_dim, mlp1_dims, mlp2_dims, mlp3_dims,
+                                        attention_dims, with_global_state)
+        self.multiagent_training = config.getboolean("sarl", "multiagent_training")
+        logging.info("Policy: {} {} global state".format(self.name, "w/" if with_global_state else "w/o"))
+
+    def set_device(self, device):
+        self.device = device
+        self.model.to(device)
+
+    def set_epsilon(self, epsilon):
+        self.epsilon = epsilon
+
+    def get_attention_weights(self):
+        return self.model.attention_weights
+
+    def build_action_space(self, v_pref):
+        """cadrl.py:82-102 (holonomic); the table itself comes from the C ABI (cn_policy_action_table)."""
+        from .envs import ActionXY
+        h = self.handle(v_pref)
+        self.speeds = [(np.exp((i + 1) / self.speed_samples) - 1) / (np.e - 1) * v_pref
+                       for i in range(self.speed_samples)]
+        self.rotations = np.linspace(0, 2 * np.pi, self.rotation_samples, endpoint=False)
+        self.action_space = [ActionXY(float(x), float(y)) for x, y in h.action_table]
+
+    # -- GPU handles -------------------------------------------------------------------------------
+    def handle(self, v_pref=1.0, precision=None):
+        """BatchedSARL for (precision, v_pref) with the torch model's current weights."""
+        precision = precision or self.precision
+        key = (precision, float(v_pref))
+        if key not in self._handles:
+            d = self._dims
+            self._handles[key] = [BatchedSARL(device=_cuda_index(self.device), precision=precision,
+                                              mlp1_dims=d["mlp1_dims"], mlp2_dims=d["mlp2_dims"],
+                                              attn_dims=d["attn_dims"], mlp3_dims=d["mlp3_dims"],
+                                              speed_samples=self.speed_samples, rotation_samples=self.rotation_samples,
+                                              gamma=self.gamma, v_pref=float(v_pref)), None]
+        entry = self._handles[key]
+        version = self._model_version()
+        if entry[1] != version:
+            entry[0].load_weights(self.flat_weights())
+            entry[1] = version
+        return entry[0]
+
+    def _model_version(self):
+        return tuple(p._version for p in self.model.parameters()) + tuple(p.data_ptr() for p in self.model.parameters())
+
+    def flat_weights(self):
+        return np.concatenate([v.detach().cpu().numpy().ravel() for v in self.model.state_dict().values()]).astype(
+            np.float32)
+
+    def sync_weights(self):
+        """Force re-upload of the torch model's weights to every GPU handle (after training steps)."""
+        for entry in self._handles.values():
+            entry[1] = None
+
+    # -- the reference call (multi_human_rl.py:11-63) ---------------------------------------------
+    def predict(self, state):
+        from .envs import ActionXY
+        if self.phase is None or self.device is None:
+            raise AttributeError("Phase, device attributes have to be set!")
+        if self.phase == "train" and self.epsilon is None:
+            raise AttributeError("Epsilon attribute has to be set in training phase")
+        if self.reach_destination(state):
+            return ActionXY(0, 0)
+        v_pref = state.self_state.v_pref
+        if self.action_space is None:
+            self.build_action_space(v_pref)
+        h = self.handle(v_pref)
+        if self.query_env:
+            # the env façade owns the one-env batch; its ORCA result is shared with the following step()
+            b = self.env._ensure_batch()
+            if self.env._human_v is None:
+                b.orca()
+                self.env._human_v = True
+        else:
+            agents = joint_state_to_agents(state)
+            H = agents.shape[0] - 1
+            if self._single is None or self._single.H != H:
+                self._single = BatchedCrowdSim(1, H, device=_cuda_index(self.device),
+                                               time_step=self.time_step or 0.25)
+            b = self._single
+            b.set_state(agents[None])
+        eps = float(self.epsilon) if self.phase == "train" else 0.0
+        h.lookahead(b, query_env=self.query_env, epsilon=eps)
+        try:
+            best, values = h.read(b)
+        except _capi.CrowdNavError as e:
+            if e.code == _capi.CN_EVALUE:      # multi_human_rl.py:57-58
+                raise ValueError("Value network is not well trained. ")
+            raise
+        self.action_values = list(values[0])
+        if self.phase == "train":
+            self.last_state = self.transform(state)
+        return self.action_space[int(best[0])]
+
+    def transform(self, state):
+        """multi_human_rl.py:90-104 -> tensor (H, 13) on self.device."""
+        import torch
+        agents = joint_state_to_agents(state)
+        H = agents.shape[0] - 1
+        if self._single is None or self._single.H != H:
+            self._single = BatchedCrowdSim(1, H, device=_cuda_index(self.device), time_step=self.time_step or 0.25)
+        self._single.set_state(agents[None])
+        t = self.handle(state.self_state.v_pref).transform(self._single)[0]
+        return t.to(self.device) if self.device is not None else t
+
+    def input_dim(self):
+        return self.joint_state_dim
+
+
+def _none():
+    return None
+
+
+# crowd_nav/policy/policy_factory.py + crowd_sim/envs/policy/policy_factory.py (hot-path policies only)
+policy_factory = {"orca": ORCA, "none": _none, "sarl": SARL}

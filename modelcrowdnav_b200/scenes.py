@@ -1,0 +1,58 @@
+"""Host-side scene generation with numpy's legacy MT19937 stream, exactly as CrowdSim.reset seeds and draws
+it (crowd_sim/envs/crowd_sim.py:165-217,261-323).  Used for parity runs and for the single-env façade;
+throughput runs generate scenes on the GPU (cn_env_reset, Philox).
+"""
+import numpy as np
+
+# crowd_sim.py:68,282-283: counter_offset = {'train': val+test capacity, 'val': 0, 'test': val capacity}
+COUNTER_OFFSET = {"train": 2000, "val": 0, "test": 1000}
+
+
+def _norm(a, b):
+    return float(np.linalg.norm((a, b)))
+
+
+def generate_scene(phase, case, human_num=5, rule="circle_crossing", circle_radius=4.0, square_width=10.0,
+                   human_radius=0.3, human_v_pref=1.0, discomfort_dist=0.2, robot_radius=0.3, robot_v_pref=1.0):
+    """Agents (H+1, 8) float64 [px py vx vy gx gy radius v_pref]; agent 0 = robot (crowd_sim.py:284)."""
+    rs = np.random.RandomState(COUNTER_OFFSET[phase] + case)
+    agents = np.zeros((human_num + 1, 8))
+    agents[0] = [0, -circle_radius, 0, 0, 0, circle_radius, robot_radius, robot_v_pref]
+    for i in range(1, human_num + 1):
+        prev = agents[:i]
+        if rule == "circle_crossing":
+            while True:
+                angle = rs.random_sample() * np.pi * 2
+                px_noise = (rs.random_sample() - 0.5) * human_v_pref
+                py_noise = (rs.random_sample() - 0.5) * human_v_pref
+                px = circle_radius * np.cos(angle) + px_noise
+                py = circle_radius * np.sin(angle) + py_noise
+                collide = False
+                for a in prev:
+                    min_dist = human_radius + a[6] + discomfort_dist
+                    if _norm(px - a[0], py - a[1]) < min_dist or _norm(px - a[4], py - a[5]) < min_dist:
+                        collide = True
+                        break
+                if not collide:
+                    break
+            agents[i] = [px, py, 0, 0, -px, -py, human_radius, human_v_pref]
+        elif rule == "square_crossing":
+            sign = -1 if rs.random_sample() > 0.5 else 1
+            while True:
+                px = rs.random_sample() * square_width * 0.5 * sign
+                py = (rs.random_sample() - 0.5) * square_width
+                if not any(_norm(px - a[0], py - a[1]) < human_radius + a[6] + discomfort_dist for a in prev):
+                    break
+            while True:
+                gx = rs.random_sample() * square_width * 0.5 * -sign
+                gy = (rs.random_sample() - 0.5) * square_width
+                if not any(_norm(gx - a[4], gy - a[5]) < human_radius + a[6] + discomfort_dist for a in prev):
+                    break
+            agents[i] = [px, py, 0, 0, gx, gy, human_radius, human_v_pref]
+        else:
+            raise ValueError("Rule doesn't exist")
+    return agents
+
+
+def generate_batch(phase, cases, **kw):
+    return np.stack([generate_scene(phase, int(c), **kw) for c in cases])
