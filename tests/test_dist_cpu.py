@@ -1,0 +1,125 @@
+"""world_size-2 gloo tests of the N>1 host logic: environments shard with no data-path collective;
+the only collectives are the gradient all-reduce of the trainer and the statistics all-reduce of the explorer."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, fn, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        res = fn(rank, world)
+        np.save(os.path.join(out_dir, "r%d.npy" % rank), np.asarray(res, dtype=np.float64))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(fn, tmp_path, world=2):
+    mp.spawn(_worker, args=(world, _free_port(), fn, str(tmp_path)), nprocs=world, join=True)
+    return [np.load(os.path.join(str(tmp_path), "r%d.npy" % r)) for r in range(world)]
+
+
+def _make_model():
+    from modelcrowdnav_b200.policy import make_value_network
+    torch.manual_seed(0)
+    return make_value_network(13, 6, [150, 100], [100, 50], [150, 100, 100, 1], [100, 100, 1])
+
+
+class _Mem(object):
+    def __init__(self, states, values):
+        self.states, self.values = states, values
+
+    def __len__(self):
+        return self.states.shape[0]
+
+
+def _data(n=200):
+    g = torch.Generator().manual_seed(1)
+    return torch.rand((n, 5, 13), generator=g), torch.rand((n, 1), generator=g)
+
+
+def _trainer_rank(rank, world):
+    from modelcrowdnav_b200.trainer import Trainer
+    torch.set_num_threads(1)
+    model = _make_model()
+    states, values = _data()
+    half = states.shape[0] // world
+    mem = _Mem(states[rank * half:(rank + 1) * half], values[rank * half:(rank + 1) * half])
+    tr = Trainer(model, mem, torch.device("cpu"), 100, dist_group=dist.group.WORLD)
+    tr.broadcast_weights()
+    tr.set_learning_rate(0.01)
+    for _ in range(3):
+        tr._step(torch.arange(half))          # each rank: its own shard, gradients averaged over ranks
+    return torch.cat([p.detach().reshape(-1) for p in model.parameters()]).numpy()
+
+
+def test_gradient_allreduce_equals_single_process(tmp_path):
+    """2 ranks x 100 samples with averaged gradients == 1 process x 200 samples (MSE mean reduction)."""
+    from modelcrowdnav_b200.trainer import Trainer
+    res = _run(_trainer_rank, tmp_path)
+    assert np.array_equal(res[0], res[1])                 # replicas stay in lock-step
+    torch.set_num_threads(1)
+    model = _make_model()
+    states, values = _data()
+    tr = Trainer(model, _Mem(states, values), torch.device("cpu"), 200)
+    tr.set_learning_rate(0.01)
+    for _ in range(3):
+        tr._step(torch.arange(200))
+    ref = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).numpy()
+    assert np.max(np.abs(res[0] - ref)) < 1e-6
+    assert ref.size == 96502
+
+
+def _stats_rank(rank, world):
+    from modelcrowdnav_b200.explorer import Explorer
+    ex = Explorer(None, None, torch.device("cpu"), dist_group=dist.group.WORLD)
+    counts = np.array([3 + rank, 1, 2 * rank, 7, 10], dtype=np.float64)
+    sums = np.array([10.5 * (rank + 1), 2.0, 25.0 * rank, 0.3, -1.5 + rank], dtype=np.float64)
+    c, s = ex._all_reduce(counts, sums)
+    return np.concatenate([c, s])
+
+
+def test_explorer_statistics_allreduce(tmp_path):
+    res = _run(_stats_rank, tmp_path)
+    exp = np.array([7, 2, 2, 14, 20, 31.5, 4.0, 25.0, 0.6, -2.0])
+    assert np.allclose(res[0], exp) and np.array_equal(res[0], res[1])
+
+
+def test_shards_are_disjoint_and_cover_all_cases():
+    """Contiguous global-id sharding used by bench.py / the batched explorer: rank r owns [r*E, (r+1)*E)."""
+    from modelcrowdnav_b200 import scenes
+    world, E = 4, 6
+    full = scenes.generate_batch("test", range(world * E))
+    for r in range(world):
+        shard = scenes.generate_batch("test", range(r * E, (r + 1) * E))
+        assert np.array_equal(shard, full[r * E:(r + 1) * E])
+
+
+def test_product_scene_generator_matches_reference_fixture(oracle_mod):
+    """modelcrowdnav_b200.scenes (product) == the reference's reset() scenes (pinned through the oracle goldens)."""
+    from conftest import load_traj
+    from modelcrowdnav_b200 import scenes
+    tr = load_traj("square10_qfalse")
+    for case, rec in tr["cases"].items():
+        phase, c = case.split("_")
+        s = scenes.generate_scene(phase, int(c), human_num=10, rule="square_crossing")
+        assert np.array_equal(s, rec["agents"][0])
+    tr = load_traj("circle5_qfalse")
+    for case, rec in tr["cases"].items():
+        phase, c = case.split("_")
+        assert np.array_equal(scenes.generate_scene(phase, int(c)), rec["agents"][0])
