@@ -29,6 +29,10 @@ METRIC = "env-steps/s (ORCA step + SARL lookahead)"
 UNIT = "env-steps/s"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture
+NCU_DRAM_BYTES = {("f16_tc", 8192, 5): 2536192 + 54225920}
+
+
 def flops_per_env_step(H):
     """literal ValueNetwork formulation, 2 FLOP/MAC, 81 actions."""
     return 81 * (124100 * H + 67000)
@@ -155,7 +159,7 @@ def workload_name(a):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("CN_BENCH_PRECISION", "f16_tc"), choices=["f32", "f16_tc"])
@@ -279,7 +283,10 @@ def main():
                     "d2h_bytes_per_step": buf.d2h_bytes, "steps": ne},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                         "traffic": None, "kernel": "lookahead (value network)", "kernel_ms": la_ms,
+                         "traffic": NCU_DRAM_BYTES.get((a.precision, E, H)),
+                         "traffic_source": "ncu --set full, tc_rows_kernel, dram__bytes_read+write per launch "
+                                           "(profiles/r01c_tc_rows_kernel_ncu_summary.txt)",
+                         "kernel": "lookahead (value network)", "kernel_ms": la_ms,
                          "flops_per_env_step": F, "peak_source": peaks["source"] + ", sustained bf16"},
         }
         if not a.no_cpu_baseline:

@@ -57,7 +57,21 @@ def policy_config(query_env=False):
     return cp
 
 
-def make_env_and_sarl(human_num=5, sim="circle_crossing", query_env=False, seed=0, robot_visible=False):
+def load_flat_weights(model, flat):
+    """Load a flat fp32 vector (state-dict order) into a reference ValueNetwork."""
+    import torch
+    sd = model.state_dict()
+    off = 0
+    new = {}
+    for k, v in sd.items():
+        n = v.numel()
+        new[k] = torch.from_numpy(flat[off:off + n].reshape(tuple(v.shape)).copy())
+        off += n
+    assert off == flat.size
+    model.load_state_dict(new)
+
+
+def make_env_and_sarl(human_num=5, sim="circle_crossing", query_env=False, seed=0, robot_visible=False, weights=None):
     """Reference CrowdSim + Robot + SARL wired as crowd_nav/test.py:52-87 does (holonomic honoured)."""
     install()
     import torch
@@ -69,6 +83,8 @@ def make_env_and_sarl(human_num=5, sim="circle_crossing", query_env=False, seed=
     torch.manual_seed(seed)
     policy.configure(policy_config(query_env))
     policy.kinematics = "holonomic"                        # policy.config:14 honoured (cadrl.py:66 quirk)
+    if weights is not None:
+        load_flat_weights(policy.get_model(), weights)
     env = gym.make("CrowdSim-v0")
     env.configure(ecfg)
     robot = Robot(ecfg, "robot")

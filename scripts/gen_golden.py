@@ -129,10 +129,16 @@ TRAJ_SPECS = [
 ]
 
 
-def gen_trajectories():
-    for name, H, sim, qenv, vis, cases in TRAJ_SPECS:
+TRAJ_SPECS_TRAINED = [
+    ("circle5_qfalse_trained", 5, "circle_crossing", False, False, [("test", 10, 60), ("test", 11, 60), ("test", 12, 60)]),
+    ("circle5_qtrue_trained", 5, "circle_crossing", True, False, [("test", 13, 60)]),
+]
+
+
+def gen_trajectories(specs=None, weights=None):
+    for name, H, sim, qenv, vis, cases in (specs or TRAJ_SPECS):
         env, robot, policy = refshim.make_env_and_sarl(human_num=H, sim=sim, query_env=qenv, seed=0,
-                                                        robot_visible=vis)
+                                                        robot_visible=vis, weights=weights)
         out = {"H": np.array(H), "query_env": np.array(int(qenv)), "robot_visible": np.array(int(vis)),
                "sim": np.array(sim)}
         t0 = time.time()
@@ -150,10 +156,11 @@ def gen_trajectories():
 
 
 def run_episode_chunk(args):
-    lo, hi, H, sim, qenv = args
+    lo, hi, H, sim, qenv, wpath = args
     import torch
     torch.set_num_threads(1)
-    env, robot, policy = refshim.make_env_and_sarl(human_num=H, sim=sim, query_env=qenv, seed=0)
+    env, robot, policy = refshim.make_env_and_sarl(human_num=H, sim=sim, query_env=qenv, seed=0,
+                                                    weights=np.load(wpath) if wpath else None)
     res = []
     for case in range(lo, hi):
         ob = env.reset("test", case)
@@ -168,15 +175,15 @@ def run_episode_chunk(args):
     return res
 
 
-def gen_episodes(n_proc):
-    """crowd_nav/test.py equivalent: 500 test cases, SARL (seed-0 random weights), circle_crossing, H=5."""
+def gen_episodes(n_proc, wpath=None, tag="seed0"):
+    """crowd_nav/test.py equivalent: 500 test cases, SARL, circle_crossing, H=5."""
     import multiprocessing as mp
-    chunks = [(lo, min(lo + 10, 500), 5, "circle_crossing", False) for lo in range(0, 500, 10)]
+    chunks = [(lo, min(lo + 10, 500), 5, "circle_crossing", False, wpath) for lo in range(0, 500, 10)]
     t0 = time.time()
     with mp.get_context("fork").Pool(n_proc) as pool:
         res = sum(pool.map(run_episode_chunk, chunks), [])
     res = np.array(sorted(res), dtype=np.float64)
-    np.savez_compressed(os.path.join(GOLD, "episodes_circle5_seed0.npz"), case=res[:, 0].astype(np.int32),
+    np.savez_compressed(os.path.join(GOLD, "episodes_circle5_%s.npz" % tag), case=res[:, 0].astype(np.int32),
                         info=res[:, 1].astype(np.int8), steps=res[:, 2].astype(np.int32),
                         too_close=res[:, 3].astype(np.int32), end_time=res[:, 4], ret=res[:, 5])
     k = len(res)
@@ -191,12 +198,16 @@ if __name__ == "__main__":
     ap.add_argument("--episodes", action="store_true")
     ap.add_argument("--procs", type=int, default=6)
     ap.add_argument("--skip-units", action="store_true")
+    ap.add_argument("--trained", action="store_true", help="use tests/golden/sarl_weights_trained.npy (GPU-trained SARL)")
     a = ap.parse_args()
+    wtrained = os.path.join(GOLD, "sarl_weights_trained.npy")
     assert refshim.available(), "/root/reference is required"
     os.makedirs(GOLD, exist_ok=True)
     oracle.build()
     if a.episodes:
-        gen_episodes(a.procs)
+        gen_episodes(a.procs, wtrained if a.trained else None, "trained" if a.trained else "seed0")
+    elif a.trained:
+        gen_trajectories(TRAJ_SPECS_TRAINED, np.load(wtrained))
     else:
         if not a.skip_units:
             gen_units()

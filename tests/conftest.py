@@ -42,4 +42,11 @@ def load_traj(name):
     return out
 
 
-TRAJ_NAMES = ["circle5_qfalse", "circle5_qtrue", "circle5_visible", "square10_qfalse", "square10_qtrue"]
+TRAJ_NAMES = ["circle5_qfalse", "circle5_qtrue", "circle5_visible", "square10_qfalse", "square10_qtrue",
+              "circle5_qfalse_trained", "circle5_qtrue_trained"]
+
+
+def weights_for(name):
+    """seed-0 random init for the plain fixtures, the GPU-trained SARL (scripts/train_sarl.py) for *_trained."""
+    f = "sarl_weights_trained.npy" if name.endswith("trained") else "sarl_weights_seed0.npy"
+    return np.load(os.path.join(GOLDEN, f))

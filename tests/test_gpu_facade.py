@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, load_traj
+from conftest import GOLDEN, load_traj, weights_for
 
 pytestmark = pytest.mark.gpu
 
@@ -110,12 +110,13 @@ def test_state_dict_keys_match_reference(weights0, units):
     assert np.array_equal(policy.flat_weights(), weights0)
 
 
-@pytest.mark.parametrize("name", ["circle5_qfalse", "circle5_qtrue"])
-def test_facade_replays_reference_episode(weights0, name):
+@pytest.mark.parametrize("name", ["circle5_qfalse", "circle5_qtrue", "circle5_qfalse_trained", "circle5_qtrue_trained"])
+def test_facade_replays_reference_episode(name):
     """gym-style loop (explorer.py:53-69) through the single-env façade: ob/reward/done/info, action values and
     chosen actions equal the reference's, step by step, while the façade follows its own actions."""
     import modelcrowdnav_b200 as mcn
     tr = load_traj(name)
+    weights0 = weights_for(name)
     env, robot, policy, _ = _setup(weights0, "f32", query_env=bool(tr["query_env"]))
     case = [c for c in tr["cases"] if c.startswith("test_")][0]
     rec = tr["cases"][case]

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import TRAJ_NAMES, load_traj
+from conftest import TRAJ_NAMES, load_traj, weights_for
 
 pytestmark = pytest.mark.gpu
 
@@ -96,6 +96,7 @@ def test_step_ladder_edge_cases(mcn, oracle_mod):
 def test_golden_trajectories(mcn, oracle_mod, weights0, name, precision):
     """Teacher-forced replay of the reference's own episodes (tests/golden, scripts/gen_golden.py)."""
     tr = load_traj(name)
+    weights0 = weights_for(name)
     H = tr["H"]
     states, times, recs = [], [], []
     for case, rec in tr["cases"].items():

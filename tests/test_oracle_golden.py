@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import TRAJ_NAMES, load_traj
+from conftest import TRAJ_NAMES, load_traj, weights_for
 
 
 def test_action_space_matches_reference(oracle_mod, units):
@@ -51,6 +51,7 @@ def test_trajectories(oracle_mod, weights0, name):
     """Teacher-forced, step by step: ORCA velocities, outcome ladder, state update, 81 values, argmax."""
     o = oracle_mod
     tr = load_traj(name)
+    weights0 = weights_for(name)
     H = tr["H"]
     ecfg = o.EnvCfg.default(robot_visible=tr["robot_visible"])
     scfg = o.SarlCfg.default()
