@@ -208,6 +208,14 @@ int cn_selftest_umma(int32_t N, int32_t K, const float *a_host, const float *b_h
  * the form the kernel uses to sum the attention-weighted features over the humans of a group. */
 int cn_selftest_umma_bmn(int32_t N, int32_t K, const float *a_host, const float *b_host, float *d_host, int device);
 
+/* Developer diagnostic: clock64() at the phase boundaries of one tile of the tensor-core row kernel (CTA 0).
+ * The first call arms the probes; call again after a lookahead to read 16 timestamps. */
+int cn_debug_tc_timing(cn_policy *p, long long *out16);
+/* Developer diagnostic: the self-test product with a selectable operand mode (0 = A and B in shared memory,
+ * 1 = B MN-major, 2 = A in TMEM), repeated `reps` times; *cycles = clock64() ticks of issue + commit + wait. */
+int cn_debug_umma_bench(int32_t N, int32_t K, int32_t mode, int32_t reps, const float *a_host, const float *b_host,
+                        float *d_host, long long *cycles, int device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,7 @@ constexpr int kTmemCols = 256;
 
 struct TcState {
     uint8_t *img_a, *img_b;   // device weight images
+    long long *dbg;           // optional phase timestamps of CTA 0 (cn_debug_tc_timing)
     uint8_t *J;               // joint-state tiles
     double *rew;              // NG rewards
     size_t cap_groups;
@@ -104,7 +105,11 @@ __device__ __forceinline__ void split_hl(float x, float &hi, float &lo)
 // 32*(w%4)..+31 (the hardware ties a warp to the lane quarter warpid%4) and split the columns of every
 // epilogue between them.
 // =====================================================================================================
-constexpr int kThreadsTC = 256;
+constexpr int kThreadsTC = 256;      // worker threads (8 warps)
+// A dedicated issuer warp was measured (tcgen05.mma issue blocks for about the MMA duration, ~62 cycles per
+// M=128,K=16 instruction) but with one tile in flight it does not pay: 1.424 ms vs 1.372 ms per lookahead.
+constexpr bool kIssuerWarp = false;
+constexpr int kThreadsRows = kIssuerWarp ? 288 : 256;
 
 // Inputs of one (env, action, human) row, fetched straight from the SoA (L2-resident) one tile ahead.
 struct RowIn {
@@ -114,10 +119,10 @@ struct RowIn {
 
 __device__ __forceinline__ void load_row_inputs(RowIn &in, const EnvDims &ed, const double *__restrict__ st,
                                                 const double *__restrict__ human_v, const double *__restrict__ actions,
-                                                int A, int query_env, int NG, int G, int tile, int r)
+                                                int A, int query_env, int NG, int G, int tile, int gl, int h)
 {
     const int H = ed.H;
-    const int gl = r / H, h = r - gl * H, g = tile * G + gl;
+    const int g = tile * G + gl;
     in.valid = (gl < G && g < NG) ? 1 : 0;
     if (!in.valid) return;
     const int e = g / A, a = g - e * A;
@@ -157,57 +162,90 @@ __device__ __forceinline__ void row_features(const RowIn &in, double dt, uint4 &
 }
 
 // Per (env, action) group: lookahead reward -> rew[g]; self-state part of the joint state -> J chunks 7..9.
+// Runs on the upper 128 threads (warps 4..7): thread (gl, h) evaluates human h's clearance, a named barrier
+// joins the 128 threads, then thread gl < G folds the H clearances through the reward ladder.  "Break on the first
+// collision" (crowd_sim.py:360-363, multi_human_rl.py:71-73) only matters for dmin, which is unused once any
+// clearance is negative, so min/any over all humans is the same result.
 __device__ __forceinline__ void group_work(const EnvParams &p, const double *__restrict__ st,
                                            const double *__restrict__ time, const double *__restrict__ human_v,
                                            const double *__restrict__ actions, int A, int query_env, int NG, int G,
-                                           int tile, int gl, uint8_t *__restrict__ J, double *__restrict__ rew)
+                                           int tile, int t2, int gl, int h, double *__restrict__ D,
+                                           uint8_t *__restrict__ J, double *__restrict__ rew)
 {
     const EnvDims ed = p.d;
     const int H = ed.H;
-    const int g = tile * G + gl;
-    if (gl >= G || g >= NG) return;
-    const int e = g / A, a = g - e * A;
     const double dt = p.time_step;
-    auto ag = [&](int f, int agent) { return st[st_idx(ed, f, agent, e)]; };
-    const double ax = actions[2 * a], ay = actions[2 * a + 1];
-    const double rpx = ag(F_PX, 0), rpy = ag(F_PY, 0), rr = ag(F_R, 0), rgx = ag(F_GX, 0), rgy = ag(F_GY, 0);
-    double reward;
-    if (query_env) {
-        reward = cn_step_outcome(p, ag, H, time[e], ax, ay).reward;                     // crowd_sim.py:325-329
-    } else {
-        // multi_human_rl.py:65-88
-        const double npx = rpx + ax * dt, npy = rpy + ay * dt;
+    {
+        const int g = tile * G + gl;
+        double clear = INFINITY;
+        if (gl < G && g < NG) {
+            const int e = g / A, a = g - e * A;
+            auto ag = [&](int f, int agent) { return st[st_idx(ed, f, agent, e)]; };
+            const double ax = actions[2 * a], ay = actions[2 * a + 1];
+            const double rpx = ag(F_PX, 0), rpy = ag(F_PY, 0), rr = ag(F_R, 0);
+            if (query_env) {
+                // crowd_sim.py:347-359: relative segment over the step, human's CURRENT velocity
+                const double px = ag(F_PX, h + 1) - rpx, py = ag(F_PY, h + 1) - rpy;
+                const double vx = ag(F_VX, h + 1) - ax, vy = ag(F_VY, h + 1) - ay;
+                const double ex = px + vx * dt, ey = py + vy * dt;
+                clear = cn_point_to_segment_dist0(px, py, ex, ey) - ag(F_R, h + 1) - rr;
+            } else {
+                // multi_human_rl.py:69-70: end-point distance with constant-velocity humans
+                const double npx = rpx + ax * dt, npy = rpy + ay * dt;
+                const double nhx = ag(F_PX, h + 1) + ag(F_VX, h + 1) * dt, nhy = ag(F_PY, h + 1) + ag(F_VY, h + 1) * dt;
+                clear = norm2d(npx - nhx, npy - nhy) - rr - ag(F_R, h + 1);
+            }
+        }
+        D[t2] = clear;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int g = tile * G + t2;
+    if (t2 < G && g < NG) {
+        const int e = g / A, a = g - e * A;
+        auto ag = [&](int f, int agent) { return st[st_idx(ed, f, agent, e)]; };
+        const double ax = actions[2 * a], ay = actions[2 * a + 1];
+        const double rpx = ag(F_PX, 0), rpy = ag(F_PY, 0), rr = ag(F_R, 0), rgx = ag(F_GX, 0), rgy = ag(F_GY, 0);
         double dmin = INFINITY;
         bool collision = false;
-        for (int h = 1; h <= H; ++h) {
-            const double nhx = ag(F_PX, h) + ag(F_VX, h) * dt, nhy = ag(F_PY, h) + ag(F_VY, h) * dt;
-            const double dist = norm2d(npx - nhx, npy - nhy) - rr - ag(F_R, h);
-            if (dist < 0) { collision = true; break; }
-            if (dist < dmin) dmin = dist;
+        for (int k = 0; k < H; ++k) {
+            const double c = D[t2 * H + k];
+            if (c < 0) collision = true;
+            else if (c < dmin) dmin = c;
         }
+        const double npx = rpx + ax * dt, npy = rpy + ay * dt;
         const bool reaching_goal = norm2d(npx - rgx, npy - rgy) < rr;
-        if (collision) reward = -0.25;
-        else if (reaching_goal) reward = 1;
-        else if (dmin < 0.2) reward = (dmin - 0.2) * 0.5 * dt;
-        else reward = 0;
-    }
-    rew[g] = reward;
-    // self state = rotated row columns 0..5 (sarl.py:36): dg, v_pref, theta(0), radius, vx', vy'
-    float s[14], o[13];
-    s[0] = (float)(rpx + ax * dt); s[1] = (float)(rpy + ay * dt); s[2] = (float)ax; s[3] = (float)ay;
-    s[4] = (float)rr; s[5] = (float)rgx; s[6] = (float)rgy; s[7] = (float)ag(F_VPREF, 0); s[8] = 0.0f;
-    s[9] = s[10] = s[11] = s[12] = s[13] = 0.0f;
-    cn_rotate(s, o);
-    float hi[6], lo[6];
+        double reward;
+        if (query_env) {                                                                 // crowd_sim.py:382-403
+            if (time[e] >= p.time_limit - 1) reward = 0;
+            else if (collision) reward = p.collision_penalty;
+            else if (reaching_goal) reward = p.success_reward;
+            else if (dmin < p.discomfort_dist) reward = (dmin - p.discomfort_dist) * p.discomfort_penalty_factor * dt;
+            else reward = 0;
+        } else {                                                                         // multi_human_rl.py:77-86
+            if (collision) reward = -0.25;
+            else if (reaching_goal) reward = 1;
+            else if (dmin < 0.2) reward = (dmin - 0.2) * 0.5 * dt;
+            else reward = 0;
+        }
+        rew[g] = reward;
+        // self state = rotated row columns 0..5 (sarl.py:36): dg, v_pref, theta(0), radius, vx', vy'
+        float s[14], o[13];
+        s[0] = (float)npx; s[1] = (float)npy; s[2] = (float)ax; s[3] = (float)ay;
+        s[4] = (float)rr; s[5] = (float)rgx; s[6] = (float)rgy; s[7] = (float)ag(F_VPREF, 0); s[8] = 0.0f;
+        s[9] = s[10] = s[11] = s[12] = s[13] = 0.0f;
+        cn_rotate(s, o);
+        float hi[6], lo[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) split_hl(o[k], hi[k], lo[k]);
-    uint8_t *jt = J + (size_t)(g >> 7) * J_TILE_BYTES;
-    const int rb = g & 127;
-    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 7)) =
-        make_uint4(h2(hi[0], hi[1]), h2(hi[2], hi[3]), h2(hi[4], hi[5]), h2(1.0f, 1.0f));
-    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 8)) =
-        make_uint4(h2(lo[0], lo[1]), h2(lo[2], lo[3]), h2(lo[4], lo[5]), 0u);
-    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 9)) = make_uint4(0, 0, 0, 0);
+        for (int k = 0; k < 6; ++k) split_hl(o[k], hi[k], lo[k]);
+        uint8_t *jt = J + (size_t)(g >> 7) * J_TILE_BYTES;
+        const int rb = g & 127;
+        *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 7)) =
+            make_uint4(h2(hi[0], hi[1]), h2(hi[2], hi[3]), h2(hi[4], hi[5]), h2(1.0f, 1.0f));
+        *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 8)) =
+            make_uint4(h2(lo[0], lo[1]), h2(lo[2], lo[3]), h2(lo[4], lo[5]), 0u);
+        *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 9)) = make_uint4(0, 0, 0, 0);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // D is reused (it aliases the score scratch)
 }
 
 __device__ __forceinline__ void pin(const uint4 &a, const uint4 &b, const uint4 &c, const uint4 &d)
@@ -217,17 +255,19 @@ __device__ __forceinline__ void pin(const uint4 &a, const uint4 &b, const uint4 
                        "r"(c.x), "r"(c.y), "r"(c.z), "r"(c.w), "r"(d.x), "r"(d.y), "r"(d.z), "r"(d.w));
 }
 
-__global__ void __launch_bounds__(kThreadsTC, 1)
+__global__ void __launch_bounds__(kThreadsRows, 1)
 tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restrict__ time,
                const double *__restrict__ human_v, const double *__restrict__ actions, int A, int query_env,
                const uint8_t *__restrict__ wimg, uint8_t *__restrict__ J, double *__restrict__ rew, int NG, int G,
-               int ntiles)
+               int ntiles, long long *__restrict__ dbg)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const EnvDims ed = p.d;
     const int H = ed.H;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q = warp & 3, hf = warp >> 2;
+    const int q = warp & 3, hf = warp >> 2;   // hf: 0/1 = column half of the 8 worker warps, 2 = MMA issuer warp
+    const bool worker = warp < 8;
+    const bool issuer = kIssuerWarp ? ((warp == 8) && (lane == 0)) : (tid == 0);
     const int row = q * 32 + lane;            // TMEM lane == tile row owned by this thread
     uint8_t *bufA = smem + A_BUFA, *bufB = smem + A_BUFB;
     float *S0 = reinterpret_cast<float *>(smem + A_MISC);          // [128] partial scores, columns [0,64)
@@ -240,12 +280,15 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
     // features / rewards of this CTA's first tile overlap the weight-image copy
     uint4 c0, c1, c2, c3;
     RowIn in;
+    const int t2 = tid & 127;                 // row index (lower half) / (group, human) slot (upper half)
+    const int my_gl = t2 / H, my_h = t2 - my_gl * H;
+    double *Dscr = reinterpret_cast<double *>(smem + A_MISC);      // 128 clearances; aliases S0/S1
     if ((int)blockIdx.x < ntiles) {
         if (tid < 128) {
-            load_row_inputs(in, ed, st, human_v, actions, A, query_env, NG, G, blockIdx.x, tid);
+            load_row_inputs(in, ed, st, human_v, actions, A, query_env, NG, G, blockIdx.x, my_gl, my_h);
             row_features(in, dt, c0, c1, c2, c3);
-        } else {
-            group_work(p, st, time, human_v, actions, A, query_env, NG, G, blockIdx.x, tid - 128, J, rew);
+        } else if (worker) {
+            group_work(p, st, time, human_v, actions, A, query_env, NG, G, blockIdx.x, t2, my_gl, my_h, Dscr, J, rew);
         }
     }
     copy_image_to_smem(smem, wimg, IMG_A_BYTES);
@@ -264,9 +307,11 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
     const int rows = G * H;
     constexpr int T_F = 0, T_A2 = N_F, T_D2 = N_F + N_M1;   // TMEM columns of the last two stages
 
+#define TPROBE(i) do { if (dbg && blockIdx.x == 0 && tile == (int)(3 * gridDim.x)) { if (tid == 0) dbg[i] = clock64(); else if (tid == 255) dbg[32 + (i)] = clock64(); else if (tid == 64) dbg[64 + (i)] = clock64(); } } while (0)
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int g0 = tile * G;
         const int next = tile + gridDim.x;
+        TPROBE(0);
         // ---- X operand of this tile (computed one tile ahead, lives in registers until here) ----
         if (tid < 128) {
             *reinterpret_cast<uint4 *>(bufB + chunk_off(ROWS, tid, 0)) = c0;
@@ -276,91 +321,131 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
         }
         fence_async_smem();
         __syncthreads();
+        TPROBE(1);
         // ---- mlp1.0: X (K=32) -> TMEM[0,160) ----
-        if (tid == 0) {
+        if (issuer) {
             fence_after_sync();
             mma_layer(tmem + 0, sB, ROWS, sW1, N_H1, K_X, N_H1, false);
             commit(mbar);
         }
-        mbar_wait(mbar, phase); phase ^= 1;
+        if (worker) mbar_wait(mbar, phase);
+        phase ^= 1;
+        TPROBE(2);
         fence_after_sync();
         if (hf == 0) epilogue_to_smem<true>(tlane, 0, 96, bufA, row, 0);       // H1
-        else epilogue_to_smem<true>(tlane, 96, 64, bufA, row, 12);
+        else if (hf == 1) epilogue_to_smem<true>(tlane, 96, 64, bufA, row, 12);
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
+        TPROBE(3);
         // ---- mlp1.2: H1 (K=160) -> TMEM[0,112) ----
-        if (tid == 0) {
+        if (issuer) {
             fence_after_sync();
             mma_layer(tmem + 0, sA, ROWS, sW2, N_M1, N_H1, N_M1, false);
             commit(mbar);
         }
         // next tile's row inputs: loads fly while the tensor cores work
-        if (tid < 128 && next < ntiles) load_row_inputs(in, ed, st, human_v, actions, A, query_env, NG, G, next, tid);
-        mbar_wait(mbar, phase); phase ^= 1;
+        if (tid < 128 && next < ntiles) load_row_inputs(in, ed, st, human_v, actions, A, query_env, NG, G, next, my_gl, my_h);
+        if (worker) mbar_wait(mbar, phase);
+        phase ^= 1;
+        TPROBE(4);
         fence_after_sync();
         if (hf == 0) epilogue_to_smem<true>(tlane, 0, 64, bufB, row, 0);       // mlp1 output (X is dead)
-        else epilogue_to_smem<true>(tlane, 64, 48, bufB, row, 8);
+        else if (hf == 1) epilogue_to_smem<true>(tlane, 64, 48, bufB, row, 8);
+        fence_async_smem();
         fence_before_sync();
         __syncthreads();
-        // ---- group mean of the mlp1 output (sarl.py:42), replicated to every row of the group -> bufA ----
-        // item = (K-chunk c, group gl); consecutive threads take consecutive groups (conflict-free 16 B accesses)
-        for (int it = tid; it < G * (N_M1 / 8); it += blockDim.x) {
-            const int c = it / G, gl = it - c * G;
-            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            for (int h = 0; h < H; ++h) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(bufB + chunk_off(ROWS, gl * H + h, c));
-                const __half2 *hv = reinterpret_cast<const __half2 *>(&v);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float2 f = __half22float2(hv[k]);
-                    acc[2 * k] += f.x; acc[2 * k + 1] += f.y;
-                }
-            }
-            const float inv = 1.0f / (float)H;
-            uint4 o;
-            o.x = h2(acc[0] * inv, acc[1] * inv); o.y = h2(acc[2] * inv, acc[3] * inv);
-            o.z = h2(acc[4] * inv, acc[5] * inv); o.w = h2(acc[6] * inv, acc[7] * inv);
-            for (int h = 0; h < H; ++h) *reinterpret_cast<uint4 *>(bufA + chunk_off(ROWS, gl * H + h, c)) = o;
-        }
-        for (int it = tid; it < (ROWS - rows) * (N_M1 / 8); it += blockDim.x) {   // padding rows of the mean tile
-            const int c = it / (ROWS - rows), r = rows + it % (ROWS - rows);
-            *reinterpret_cast<uint4 *>(bufA + chunk_off(ROWS, r, c)) = make_uint4(0, 0, 0, 0);
-        }
-        fence_async_smem();
-        __syncthreads();
-        // ---- mlp2.0 -> TMEM[0,112) ; attention.0 on [mlp1_out | mean] (K=224) -> TMEM[112,224) ----
-        if (tid == 0) {
+        TPROBE(5);
+        // ---- mlp2.0 -> TMEM[0,112) and the mlp1_out half of attention.0 -> TMEM[112,224) start now; the group mean
+        //      below runs on the CUDA cores while the tensor pipe works (no commit yet) ----
+        if (issuer) {
             fence_after_sync();
             mma_layer(tmem + 0, sB, ROWS, sW3, N_M1, N_M1, N_M1, false);
             mma_layer(tmem + N_M1, sB, ROWS, sWA1, N_M1, N_M1, N_M1, false);
+        }
+        TPROBE(14);
+        // ---- group mean of the mlp1 output (sarl.py:42), replicated to every row of the group -> bufA ----
+        // item = (K-chunk c, group gl); consecutive threads take consecutive groups (conflict-free 16 B accesses);
+        // two independent items per thread are interleaved for ILP
+        {
+            const int nitems = G * (N_M1 / 8);
+            const float inv = 1.0f / (float)H;
+            for (int it0 = worker ? tid : nitems; it0 < nitems; it0 += 2 * kThreadsTC) {
+                const int it1 = it0 + kThreadsTC;
+                const bool two = it1 < nitems;
+                const int ca = it0 / G, ga = it0 - ca * G;
+                const int cb = two ? it1 / G : ca, gb = two ? it1 - cb * G : ga;
+                float acca[8] = {0, 0, 0, 0, 0, 0, 0, 0}, accb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                for (int h = 0; h < H; ++h) {
+                    const uint4 va = *reinterpret_cast<const uint4 *>(bufB + chunk_off(ROWS, ga * H + h, ca));
+                    const uint4 vb = *reinterpret_cast<const uint4 *>(bufB + chunk_off(ROWS, gb * H + h, cb));
+                    const __half2 *ha = reinterpret_cast<const __half2 *>(&va);
+                    const __half2 *hb = reinterpret_cast<const __half2 *>(&vb);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 fa = __half22float2(ha[k]), fb = __half22float2(hb[k]);
+                        acca[2 * k] += fa.x; acca[2 * k + 1] += fa.y;
+                        accb[2 * k] += fb.x; accb[2 * k + 1] += fb.y;
+                    }
+                }
+                uint4 oa, ob;
+                oa.x = h2(acca[0] * inv, acca[1] * inv); oa.y = h2(acca[2] * inv, acca[3] * inv);
+                oa.z = h2(acca[4] * inv, acca[5] * inv); oa.w = h2(acca[6] * inv, acca[7] * inv);
+                ob.x = h2(accb[0] * inv, accb[1] * inv); ob.y = h2(accb[2] * inv, accb[3] * inv);
+                ob.z = h2(accb[4] * inv, accb[5] * inv); ob.w = h2(accb[6] * inv, accb[7] * inv);
+                for (int h = 0; h < H; ++h) {
+                    *reinterpret_cast<uint4 *>(bufA + chunk_off(ROWS, ga * H + h, ca)) = oa;
+                    if (two) *reinterpret_cast<uint4 *>(bufA + chunk_off(ROWS, gb * H + h, cb)) = ob;
+                }
+            }
+        }
+        TPROBE(15);
+        for (int it = worker ? tid : (1 << 30); it < (ROWS - rows) * (N_M1 / 8); it += kThreadsTC) {   // padding rows of the mean tile
+            const int c = it / (ROWS - rows), r = rows + it % (ROWS - rows);
+            *reinterpret_cast<uint4 *>(bufA + chunk_off(ROWS, r, c)) = make_uint4(0, 0, 0, 0);
+        }
+        TPROBE(16);
+        fence_async_smem();
+        TPROBE(17);
+        __syncthreads();
+        TPROBE(6);
+        // ---- group-mean half of attention.0 (K=112 more) accumulates into TMEM[112,224) ----
+        if (issuer) {
+            fence_after_sync();
             mma_layer(tmem + N_M1, sA, ROWS, sWA1 + (N_M1 / 8) * (N_M1 * 16), N_M1, N_M1, N_M1, true);
             commit(mbar);
         }
         // next tile: rotate + pack (rows) | rewards + self-state chunks (groups), hidden under the longest MMA
         if (next < ntiles) {
             if (tid < 128) { row_features(in, dt, c0, c1, c2, c3); pin(c0, c1, c2, c3); }
-            else group_work(p, st, time, human_v, actions, A, query_env, NG, G, next, tid - 128, J, rew);
+            else if (worker) group_work(p, st, time, human_v, actions, A, query_env, NG, G, next, t2, my_gl, my_h, Dscr, J, rew);
         }
-        mbar_wait(mbar, phase); phase ^= 1;
+        TPROBE(18);
+        if (worker) mbar_wait(mbar, phase);
+        phase ^= 1;
+        TPROBE(7);
         fence_after_sync();
         if (hf == 0) epilogue_to_smem<true>(tlane, 0, N_M1, bufA, row, 0);     // mlp2.0 out
-        else epilogue_to_smem<true>(tlane, N_M1, N_M1, bufB, row, 0);          // attention.0 out
+        else if (hf == 1) epilogue_to_smem<true>(tlane, N_M1, N_M1, bufB, row, 0);   // attention.0 out
+        TPROBE(19);
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
+        TPROBE(8);
         // ---- mlp2.2 -> TMEM[0,64) ; attention.2 -> TMEM[64,176) ----
-        if (tid == 0) {
+        if (issuer) {
             fence_after_sync();
             mma_layer(tmem + T_F, sA, ROWS, sW4, N_F, N_M1, N_F, false);
             mma_layer(tmem + T_A2, sB, ROWS, sWA2, N_M1, N_M1, N_M1, false);
             commit(mbar);
         }
-        mbar_wait(mbar, phase); phase ^= 1;
+        if (worker) mbar_wait(mbar, phase);
+        phase ^= 1;
+        TPROBE(9);
         fence_after_sync();
         // ---- group-selection matrix P'[g][r] = (r / H == g) -> bufA (mlp2.0 tile is dead): the weighted sum over
         //      the humans of a group (sarl.py:57-60) becomes one more UMMA, D2 = P' * (w .* F) ----
-        {
+        if (worker) {
             const int g = tid & 127, cbase = (tid >> 7) * 8;
             const int lo = g * H, hi = min(lo + H, rows);
 #pragma unroll
@@ -380,7 +465,7 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
             }
         }
         // ---- attention.4 (fp32 dot over ReLU(attention.2)), split between the two warps of a lane quarter ----
-        {
+        if (worker) {
             float part = 0.0f;
             if (hf == 0) {
                 uint32_t v[32], u[32];
@@ -405,8 +490,9 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
             }
         }
         __syncthreads();
+        TPROBE(10);
         // ---- masked un-stabilised softmax over the group (sarl.py:52-53); F' = w .* F as fp16 -> bufB ----
-        {
+        if (worker) {
             float w = 0.0f;
             if (row < rows) {
                 const int gl = row / H;
@@ -435,12 +521,15 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
+        TPROBE(11);
+        if (issuer) {
             fence_after_sync();
             mma_layer_bmn(tmem + T_D2, sA, ROWS, sB, ROWS, N_F, false);
             commit(mbar);
         }
-        mbar_wait(mbar, phase); phase ^= 1;
+        if (worker) mbar_wait(mbar, phase);
+        phase ^= 1;
+        TPROBE(12);
         fence_after_sync();
         // ---- weighted feature of group g (TMEM lane g) -> J chunks 0..6 (fp16) ----
         if (tid < 128 && (tid >> 5) * 32 < G) {       // warp-uniform: tcgen05.ld is .sync.aligned
@@ -460,6 +549,7 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
         }
         fence_before_sync();
         __syncthreads();   // bufA / bufB / TMEM are reused by the next tile
+        TPROBE(13);
     }
     fence_before_sync();
     __syncthreads();
@@ -594,11 +684,12 @@ tc_mlp3_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *__rest
 // =====================================================================================================
 __global__ void __launch_bounds__(128, 1)
 umma_selftest_kernel(const uint8_t *__restrict__ a_img, const uint8_t *__restrict__ b_img, float *__restrict__ d,
-                     int N, int K, int b_mn_major)
+                     int N, int K, int mode /*0 SS, 1 SS with MN-major B, 2 TS (A in TMEM)*/, int reps,
+                     long long *__restrict__ cycles)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
-    const uint32_t a_bytes = bytes_of(ROWS, K), b_bytes = b_mn_major ? bytes_of(ROWS, N) : bytes_of(N, K);
+    const uint32_t a_bytes = bytes_of(ROWS, K), b_bytes = mode == 1 ? bytes_of(ROWS, N) : bytes_of(N, K);
     uint8_t *sa = smem, *sb = smem + a_bytes;
     uint8_t *misc = smem + ((a_bytes + b_bytes + 15) & ~15u);
     const uint32_t mbar = smem_u32(misc);
@@ -606,19 +697,43 @@ umma_selftest_kernel(const uint8_t *__restrict__ a_img, const uint8_t *__restric
     copy_image_to_smem(sa, a_img, a_bytes);
     copy_image_to_smem(sb, b_img, b_bytes);
     if (tid == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
-    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem = *tmem_slot;
     const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
-    if (tid == 0) {
-        if (b_mn_major) mma_layer_bmn(tmem, smem_u32(sa), ROWS, smem_u32(sb), K, N, false);
-        else mma_layer(tmem, smem_u32(sa), ROWS, smem_u32(sb), N, K, N, false);
-        commit(mbar);
+    const uint32_t T_A = 256;   // TMEM columns of the A operand in TS mode
+    if (mode == 2) {
+        // row `tid` of A: K/2 packed words, 8 per tcgen05.st
+        for (int c8 = 0; c8 < K / 16; ++c8) {
+            uint32_t w[8];
+            for (int j = 0; j < 8; ++j) {
+                const int k = c8 * 16 + 2 * j;   // element k lives in chunk k/8 at position k%8
+                const __half2 h = *reinterpret_cast<const __half2 *>(sa + chunk_off(ROWS, tid, k >> 3) + (k & 7) * 2);
+                w[j] = *reinterpret_cast<const uint32_t *>(&h);
+            }
+            st8(tlane + T_A + c8 * 8, w);
+        }
+        wait_st();
+        fence_before_sync();
+        __syncthreads();
+        fence_after_sync();
     }
-    mbar_wait(mbar, 0);
+    uint32_t ph = 0;
+    long long t0 = 0, t1 = 0;
+    if (tid == 0) t0 = clock64();
+    for (int rep = 0; rep < reps; ++rep) {
+        if (tid == 0) {
+            if (mode == 1) mma_layer_bmn(tmem, smem_u32(sa), ROWS, smem_u32(sb), K, N, false);
+            else if (mode == 2) mma_layer_ts(tmem, tmem + T_A, smem_u32(sb), N, K, N, false);
+            else mma_layer(tmem, smem_u32(sa), ROWS, smem_u32(sb), N, K, N, false);
+            commit(mbar);
+        }
+        mbar_wait(mbar, ph); ph ^= 1;
+    }
+    if (tid == 0) { t1 = clock64(); if (cycles) *cycles = t1 - t0; }
     fence_after_sync();
     for (int c0 = 0; c0 < N; c0 += 16) {
         uint32_t v[16];
@@ -628,7 +743,7 @@ umma_selftest_kernel(const uint8_t *__restrict__ a_img, const uint8_t *__restric
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+    if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 // ---- host-side weight images ------------------------------------------------------------------------
@@ -694,6 +809,7 @@ void cn_tc_destroy(cn_policy *p)
     if (t->img_b) cudaFree(t->img_b);
     if (t->J) cudaFree(t->J);
     if (t->rew) cudaFree(t->rew);
+    if (t->dbg) cudaFree(t->dbg);
     delete t;
     p->tc = nullptr;
 }
@@ -766,8 +882,8 @@ int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cu
     const double gamma_bar = pow(p->cfg.gamma, env->p.time_step * p->cfg.v_pref);
     const int grid_a = ntiles_a < t->num_sms ? ntiles_a : t->num_sms;
     const int grid_b = ntiles_b < t->num_sms ? ntiles_b : t->num_sms;
-    tc_rows_kernel<<<grid_a, kThreadsTC, A_SMEM, s>>>(env->p, env->state, env->time, env->human_v, p->action_dev, A, query_env,
-                                               t->img_a, t->J, t->rew, (int)NG, G, ntiles_a);
+    tc_rows_kernel<<<grid_a, kThreadsRows, A_SMEM, s>>>(env->p, env->state, env->time, env->human_v, p->action_dev, A, query_env,
+                                               t->img_a, t->J, t->rew, (int)NG, G, ntiles_a, t->dbg);
     CN_LAUNCH_CHECK();
     tc_mlp3_kernel<<<grid_b, kThreadsTC, B_SMEM, s>>>(env->p, env->state, t->img_b, t->J, t->rew, A, (int)NG, p->cfg.gamma,
                                                gamma_bar, p->cfg.v_pref, p->values, ntiles_b);
@@ -775,8 +891,10 @@ int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cu
     return cn_lookahead_argmax(p, env, epsilon, s);
 }
 
-static int selftest_impl(int32_t N, int32_t K, const float *a_host, const float *b_host, float *d_host, int device, int bmn)
+static int selftest_impl(int32_t N, int32_t K, const float *a_host, const float *b_host, float *d_host, int device, int mode,
+                         int reps, long long *cycles_host)
 {
+    const int bmn = mode == 1;
     if (N < 16 || N > 256 || N % 16 || K < 16 || K % 16 || K > 256 || (bmn && K > ROWS)) {
         cn_set_error("N in [16,256] step 16, K in [16,256] step 16 (K <= 128 for the MN-major variant)");
         return CN_EINVAL;
@@ -793,27 +911,54 @@ static int selftest_impl(int32_t N, int32_t K, const float *a_host, const float 
         }
     uint8_t *da = nullptr, *db = nullptr;
     float *dd = nullptr;
+    long long *dc = nullptr;
     CN_CUDA_CHECK(cudaMalloc((void **)&da, ai.size()));
     CN_CUDA_CHECK(cudaMalloc((void **)&db, bi.size()));
     CN_CUDA_CHECK(cudaMalloc((void **)&dd, sizeof(float) * ROWS * N));
+    CN_CUDA_CHECK(cudaMalloc((void **)&dc, sizeof(long long)));
     CN_CUDA_CHECK(cudaMemcpy(da, ai.data(), ai.size(), cudaMemcpyHostToDevice));
     CN_CUDA_CHECK(cudaMemcpy(db, bi.data(), bi.size(), cudaMemcpyHostToDevice));
     const size_t smem = ai.size() + bi.size() + 64;
     CN_CUDA_CHECK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    umma_selftest_kernel<<<1, 128, smem>>>(da, db, dd, N, K, bmn);
+    umma_selftest_kernel<<<1, 128, smem>>>(da, db, dd, N, K, mode, reps, dc);
     CN_LAUNCH_CHECK();
     CN_CUDA_CHECK(cudaDeviceSynchronize());
     CN_CUDA_CHECK(cudaMemcpy(d_host, dd, sizeof(float) * ROWS * N, cudaMemcpyDeviceToHost));
-    cudaFree(da); cudaFree(db); cudaFree(dd);
+    if (cycles_host) CN_CUDA_CHECK(cudaMemcpy(cycles_host, dc, sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dd); cudaFree(dc);
     return CN_OK;
 }
 
 extern "C" int cn_selftest_umma(int32_t N, int32_t K, const float *a_host, const float *b_host, float *d_host, int device)
 {
-    return selftest_impl(N, K, a_host, b_host, d_host, device, 0);
+    return selftest_impl(N, K, a_host, b_host, d_host, device, 0, 1, nullptr);
 }
 
 extern "C" int cn_selftest_umma_bmn(int32_t N, int32_t K, const float *a_host, const float *b_host, float *d_host, int device)
 {
-    return selftest_impl(N, K, a_host, b_host, d_host, device, 1);
+    return selftest_impl(N, K, a_host, b_host, d_host, device, 1, 1, nullptr);
+}
+
+// Developer diagnostic (not part of the reference surface): clock64() at the phase boundaries of one tile of
+// tc_rows_kernel's CTA 0.  First call arms the probes; later calls return the last recorded timestamps.
+extern "C" int cn_debug_tc_timing(cn_policy *p, long long *out16)
+{
+    if (!p || !p->tc) { cn_set_error("policy has no tensor-core state"); return CN_EINVAL; }
+    TcState *t = (TcState *)p->tc;
+    CN_CUDA_CHECK(cudaSetDevice(p->device));
+    if (!t->dbg) {
+        CN_CUDA_CHECK(cudaMalloc((void **)&t->dbg, 96 * sizeof(long long)));
+        CN_CUDA_CHECK(cudaMemset(t->dbg, 0, 96 * sizeof(long long)));
+    }
+    CN_CUDA_CHECK(cudaDeviceSynchronize());
+    CN_CUDA_CHECK(cudaMemcpy(out16, t->dbg, 96 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return CN_OK;
+}
+
+// Developer diagnostic: same product, selectable operand mode (0 = A and B in smem, 1 = B MN-major, 2 = A in TMEM),
+// repeated `reps` times; *cycles = clock64() ticks of the issue+commit+wait loop.
+extern "C" int cn_debug_umma_bench(int32_t N, int32_t K, int32_t mode, int32_t reps, const float *a_host,
+                                   const float *b_host, float *d_host, long long *cycles, int device)
+{
+    return selftest_impl(N, K, a_host, b_host, d_host, device, mode, reps, cycles);
 }

@@ -55,6 +55,34 @@ __device__ __forceinline__ void mma_layer_bmn(uint32_t tmem_d, uint32_t a_base, 
     }
 }
 
+// A operand from TMEM (lane = row, 32-bit column c holds k = 2c (low half) and 2c+1 (high half)), B from smem.
+__device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// D[128 x N] (+)= A[128 x K](TMEM) * B[N x K]^T(smem, chunked K-major, b_rows rows)
+__device__ __forceinline__ void mma_layer_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_base, uint32_t b_rows, int K, int N,
+                                             bool accumulate_first)
+{
+    const uint32_t idesc = make_idesc_f16(N);
+    const uint32_t b_lbo = b_rows * 16;
+    for (int s = 0; s < K / 16; ++s) {
+        const uint64_t bd = make_desc(b_base + (uint32_t)s * 2 * b_lbo, b_lbo, 128);
+        mma_f16_ts(tmem_d, tmem_a + (uint32_t)s * 8, bd, idesc, (s > 0 || accumulate_first) ? 1u : 0u);
+    }
+}
+
+__device__ __forceinline__ void st8(uint32_t taddr, const uint32_t (&r)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // D[128 x N] (+)= A[128 x K] * B[N x K]^T, K a multiple of 16; one elected thread calls this.
 // a_base/b_base: shared addresses of chunked K-major operands with a_rows / b_rows rows.
 __device__ __forceinline__ void mma_layer(uint32_t tmem_d, uint32_t a_base, uint32_t a_rows, uint32_t b_base,
