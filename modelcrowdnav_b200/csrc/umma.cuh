@@ -76,12 +76,47 @@ __device__ __forceinline__ void mma_layer_ts(uint32_t tmem_d, uint32_t tmem_a, u
     }
 }
 
+// A from TMEM, B MN-major from an activation-style smem image (rows = K index): the two group reductions
+// (mean of mlp1 outputs, attention-weighted feature sum) are products with a constant 0/1 matrix kept in TMEM.
+__device__ __forceinline__ void mma_layer_ts_bmn(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_base, int K, int N, bool accumulate_first)
+{
+    const uint32_t idesc = make_idesc_f16(N) | (1u << 16);
+    for (int s = 0; s < K / 16; ++s) {
+        const uint64_t bd = make_desc(b_base + (uint32_t)s * 256, 128, 2048);
+        mma_f16_ts(tmem_d, tmem_a + (uint32_t)s * 8, bd, idesc, (s > 0 || accumulate_first) ? 1u : 0u);
+    }
+}
+
 __device__ __forceinline__ void st8(uint32_t taddr, const uint32_t (&r)[8])
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n"
                  :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
+__device__ __forceinline__ void st16(uint32_t taddr, const uint32_t (&r)[16])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                    "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
 __device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar_saddr)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" :: "r"(mbar_saddr) : "memory");
+}
+
+// mbarrier wait that traps instead of hanging the GPU if the producer never arrives (protocol bug guard)
+__device__ __forceinline__ void mbar_wait_guarded(uint32_t mbar_saddr, uint32_t parity)
+{
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, P1;\n\t}\n" : "=r"(ok) : "r"(mbar_saddr), "r"(parity) : "memory");
+        if (ok) break;
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
 
 // D[128 x N] (+)= A[128 x K] * B[N x K]^T, K a multiple of 16; one elected thread calls this.
 // a_base/b_base: shared addresses of chunked K-major operands with a_rows / b_rows rows.
@@ -237,5 +272,44 @@ __device__ __forceinline__ void epilogue_to_smem(uint32_t taddr_lane, int col, i
         done += 16;
     }
 }
+
+// TMEM[col_src, +ncols) fp32 of this thread's lane -> fp16 pairs packed into TMEM[col_dst, +ncols/2), ascending,
+// safe in place (col_dst == col_src): every store lands behind the columns still to be read.
+// SCALE: multiply by `scale` (no ReLU); otherwise ReLU fused in the conversion.
+template <bool RELU>
+__device__ __forceinline__ void compact_to_tmem(uint32_t tlane, int col_src, int ncols, int col_dst, float scale, bool ftz = false, int synth = 0)
+{
+    int done = 0;
+    while (ncols - done >= 32) {
+        uint32_t v[32], w[16];
+        ld32(tlane + col_src + done, v);
+        wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
+            if (ftz) { a = fabsf(a) < 6.1035156e-5f ? 0.0f : a; b = fabsf(b) < 6.1035156e-5f ? 0.0f : b; }
+            w[j] = RELU ? pack_f16x2_relu(a, b) : pack_f16x2(a * scale, b * scale);
+            if (synth == 1) w[j] = 0x3C003C00u;                                   // diagnostic: all ones
+            if (synth == 2) w[j] = pack_f16x2((float)((done + j) & 7) * 0.125f, 0.5f);   // diagnostic: smooth dense pattern
+        }
+        st16(tlane + col_dst + done / 2, w);
+        done += 32;
+    }
+    if (ncols - done >= 16) {
+        uint32_t v[16], w[8];
+        ld16(tlane + col_src + done, v);
+        wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
+            if (ftz) { a = fabsf(a) < 6.1035156e-5f ? 0.0f : a; b = fabsf(b) < 6.1035156e-5f ? 0.0f : b; }
+            w[j] = RELU ? pack_f16x2_relu(a, b) : pack_f16x2(a * scale, b * scale);
+        }
+        st8(tlane + col_dst + done / 2, w);
+        done += 16;
+    }
+    wait_st();
+}
+
 
 }  // namespace umma
