@@ -250,6 +250,105 @@ __device__ __forceinline__ void group_work(const EnvParams &p, const double *__r
     asm volatile("bar.sync 1, 128;" ::: "memory");   // D is reused (it aliases the score scratch)
 }
 
+// Split form of group_work used by tc_rows_kernel: the SoA loads are issued one MMA wait earlier than the
+// arithmetic, and the self-state chunks are written by the h == 0 ROW thread (it already holds them).
+struct GrpIn {
+    double rpx, rpy, rr, hpx, hpy, cvx, cvy, hr, ax, ay;   // role (gl, h): clearance of human h
+    double gax, gay, gpx, gpy, grr, ggx, ggy, gt;          // role group t2 < G: reward ladder
+    int valid, gvalid;
+};
+
+__device__ __forceinline__ void group_load(GrpIn &in, const EnvDims &ed, const double *__restrict__ st,
+                                           const double *__restrict__ time, const double *__restrict__ actions, int A,
+                                           int query_env, int NG, int G, int tile, int t2, int gl, int h)
+{
+    {
+        const int g = tile * G + gl;
+        in.valid = (gl < G && g < NG) ? 1 : 0;
+        if (in.valid) {
+            const int e = g / A, a = g - e * A;
+            in.rpx = st[st_idx(ed, F_PX, 0, e)]; in.rpy = st[st_idx(ed, F_PY, 0, e)]; in.rr = st[st_idx(ed, F_R, 0, e)];
+            in.hpx = st[st_idx(ed, F_PX, h + 1, e)]; in.hpy = st[st_idx(ed, F_PY, h + 1, e)];
+            in.cvx = st[st_idx(ed, F_VX, h + 1, e)]; in.cvy = st[st_idx(ed, F_VY, h + 1, e)];
+            in.hr = st[st_idx(ed, F_R, h + 1, e)];
+            in.ax = actions[2 * a]; in.ay = actions[2 * a + 1];
+        }
+    }
+    {
+        const int g = tile * G + t2;
+        in.gvalid = (t2 < G && g < NG) ? 1 : 0;
+        if (in.gvalid) {
+            const int e = g / A, a = g - e * A;
+            in.gax = actions[2 * a]; in.gay = actions[2 * a + 1];
+            in.gpx = st[st_idx(ed, F_PX, 0, e)]; in.gpy = st[st_idx(ed, F_PY, 0, e)]; in.grr = st[st_idx(ed, F_R, 0, e)];
+            in.ggx = st[st_idx(ed, F_GX, 0, e)]; in.ggy = st[st_idx(ed, F_GY, 0, e)];
+            in.gt = query_env ? time[e] : 0.0;
+        }
+    }
+}
+
+__device__ __forceinline__ void group_compute(const EnvParams &p, const GrpIn &in, int H, int query_env, int G, int tile,
+                                              int t2, double *__restrict__ D, double *__restrict__ rew)
+{
+    const double dt = p.time_step;
+    double clear = INFINITY;
+    if (in.valid) {
+        if (query_env) {   // crowd_sim.py:347-359
+            const double px = in.hpx - in.rpx, py = in.hpy - in.rpy;
+            const double vx = in.cvx - in.ax, vy = in.cvy - in.ay;
+            const double ex = px + vx * dt, ey = py + vy * dt;
+            clear = cn_point_to_segment_dist0(px, py, ex, ey) - in.hr - in.rr;
+        } else {           // multi_human_rl.py:69-70
+            const double npx = in.rpx + in.ax * dt, npy = in.rpy + in.ay * dt;
+            const double nhx = in.hpx + in.cvx * dt, nhy = in.hpy + in.cvy * dt;
+            clear = norm2d(npx - nhx, npy - nhy) - in.rr - in.hr;
+        }
+    }
+    D[t2] = clear;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (in.gvalid) {
+        double dmin = INFINITY;
+        bool collision = false;
+        for (int k = 0; k < H; ++k) {
+            const double c = D[t2 * H + k];
+            if (c < 0) collision = true;
+            else if (c < dmin) dmin = c;
+        }
+        const double npx = in.gpx + in.gax * dt, npy = in.gpy + in.gay * dt;
+        const bool reaching_goal = norm2d(npx - in.ggx, npy - in.ggy) < in.grr;
+        double reward;
+        if (query_env) {                                                                 // crowd_sim.py:382-403
+            if (in.gt >= p.time_limit - 1) reward = 0;
+            else if (collision) reward = p.collision_penalty;
+            else if (reaching_goal) reward = p.success_reward;
+            else if (dmin < p.discomfort_dist) reward = (dmin - p.discomfort_dist) * p.discomfort_penalty_factor * dt;
+            else reward = 0;
+        } else {                                                                         // multi_human_rl.py:77-86
+            if (collision) reward = -0.25;
+            else if (reaching_goal) reward = 1;
+            else if (dmin < 0.2) reward = (dmin - 0.2) * 0.5 * dt;
+            else reward = 0;
+        }
+        rew[tile * G + t2] = reward;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // D aliases the score scratch
+}
+
+// row_features plus, on the h == 0 row of a group, the self-state chunks 7..9 of the joint state (sarl.py:36)
+__device__ __forceinline__ void row_features_j(const RowIn &in, double dt, int h, int g, uint8_t *__restrict__ J,
+                                               uint4 &c0, uint4 &c1, uint4 &c2, uint4 &c3)
+{
+    row_features(in, dt, c0, c1, c2, c3);
+    if (in.valid && h == 0) {
+        // c0 = hi[0..7], c2 = lo[0..7]: the self state is columns 0..5 of the rotated row
+        uint8_t *jt = J + (size_t)(g >> 7) * J_TILE_BYTES;
+        const int rb = g & 127;
+        *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 7)) = make_uint4(c0.x, c0.y, c0.z, h2(1.0f, 1.0f));
+        *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 8)) = make_uint4(c2.x, c2.y, c2.z, 0u);
+        *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 9)) = make_uint4(0, 0, 0, 0);
+    }
+}
+
 __device__ __forceinline__ void pin(const uint4 &a, const uint4 &b, const uint4 &c, const uint4 &d)
 {
     // keeps the prefetched feature words computed where they are written in the source (under the MMA wait)
@@ -282,26 +381,47 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
     // features / rewards of this CTA's first tile overlap the weight-image copy
     uint4 c0, c1, c2, c3;
     RowIn in;
+    GrpIn gin;
     const int t2 = tid & 127;                 // row index (lower half) / (group, human) slot (upper half)
     const int my_gl = t2 / H, my_h = t2 - my_gl * H;
     double *Dscr = reinterpret_cast<double *>(smem + A_MISC);      // 128 clearances; aliases S0/S1
     if ((int)blockIdx.x < ntiles) {
         if (tid < 128) {
             load_row_inputs(in, ed, st, human_v, actions, A, query_env, NG, G, blockIdx.x, my_gl, my_h);
-            row_features(in, dt, c0, c1, c2, c3);
+            row_features_j(in, dt, my_h, blockIdx.x * G + my_gl, J, c0, c1, c2, c3);
         } else if (worker) {
-            group_work(p, st, time, human_v, actions, A, query_env, NG, G, blockIdx.x, t2, my_gl, my_h, Dscr, J, rew);
+            group_load(gin, ed, st, time, actions, A, query_env, NG, G, blockIdx.x, t2, my_gl, my_h);
+            group_compute(p, gin, H, query_env, G, blockIdx.x, t2, Dscr, rew);
         }
     }
     copy_image_to_smem(smem, wimg, IMG_A_BYTES);
     if (tid == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
-    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem = *tmem_slot;
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    constexpr uint32_t T_P = 448;
+    // constant same-group matrix P[r][k] = (k / H == r / H), r, k < G*H, kept in TMEM for the whole kernel as the
+    // A operand of the two group reductions (TS mode: column c of lane r holds k = 2c and 2c + 1)
+    if (tid < 128) {
+        const int lo = (tid / H) * H, hi = (tid < G * H) ? lo + H : lo;
+        for (int c8 = 0; c8 < 8; ++c8) {
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int ka = (c8 * 8 + j) * 2, kb = ka + 1;
+                w[j] = ((ka >= lo && ka < hi) ? 0x3C00u : 0u) | ((kb >= lo && kb < hi) ? 0x3C000000u : 0u);
+            }
+            st8(tlane + T_P + c8 * 8, w);
+        }
+        wait_st();
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
     const uint32_t sW1 = smem_u32(smem + OFF_W1), sW2 = smem_u32(smem + OFF_W2), sW3 = smem_u32(smem + OFF_W3);
     const uint32_t sW4 = smem_u32(smem + OFF_W4), sWA1 = smem_u32(smem + OFF_WA1), sWA2 = smem_u32(smem + OFF_WA2);
     const uint32_t sA = smem_u32(bufA), sB = smem_u32(bufB);
@@ -347,7 +467,10 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
             commit(mbar);
         }
         // next tile's row inputs: loads fly while the tensor cores work
-        if (tid < 128 && next < ntiles) load_row_inputs(in, ed, st, human_v, actions, A, query_env, NG, G, next, my_gl, my_h);
+        if (next < ntiles) {
+            if (tid < 128) load_row_inputs(in, ed, st, human_v, actions, A, query_env, NG, G, next, my_gl, my_h);
+            else if (worker) group_load(gin, ed, st, time, actions, A, query_env, NG, G, next, t2, my_gl, my_h);
+        }
         if (worker) mbar_wait(mbar, phase);
         phase ^= 1;
         TPROBE(4);
@@ -358,69 +481,42 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
         fence_before_sync();
         __syncthreads();
         TPROBE(5);
-        // ---- mlp2.0 -> TMEM[0,112) and the mlp1_out half of attention.0 -> TMEM[112,224) start now; the group mean
-        //      below runs on the CUDA cores while the tensor pipe works (no commit yet) ----
+        // ---- group sum of the mlp1 output over the humans of a group (sarl.py:42) as a UMMA: P (TMEM) x mlp1_out
+        //      (read MN-major from bufB) -> TMEM[112,224); mlp2.0 -> TMEM[0,112) is queued right behind it and runs
+        //      while the mean is converted ----
         if (issuer) {
             fence_after_sync();
+            mma_layer_ts_bmn(tmem + N_M1, tmem + T_P, sB, ROWS, N_M1, false);
+            commit(mbar);
             mma_layer(tmem + 0, sB, ROWS, sW3, N_M1, N_M1, N_M1, false);
-            mma_layer(tmem + N_M1, sB, ROWS, sWA1, N_M1, N_M1, N_M1, false);
         }
         TPROBE(14);
-        // ---- group mean of the mlp1 output (sarl.py:42), replicated to every row of the group -> bufA ----
-        // item = (K-chunk c, group gl); consecutive threads take consecutive groups (conflict-free 16 B accesses);
-        // two independent items per thread are interleaved for ILP
-        {
-            const int nitems = G * (N_M1 / 8);
-            const float inv = 1.0f / (float)H;
-            for (int it0 = worker ? tid : nitems; it0 < nitems; it0 += 2 * kThreadsTC) {
-                const int it1 = it0 + kThreadsTC;
-                const bool two = it1 < nitems;
-                const int ca = it0 / G, ga = it0 - ca * G;
-                const int cb = two ? it1 / G : ca, gb = two ? it1 - cb * G : ga;
-                float acca[8] = {0, 0, 0, 0, 0, 0, 0, 0}, accb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                for (int h = 0; h < H; ++h) {
-                    const uint4 va = *reinterpret_cast<const uint4 *>(bufB + chunk_off(ROWS, ga * H + h, ca));
-                    const uint4 vb = *reinterpret_cast<const uint4 *>(bufB + chunk_off(ROWS, gb * H + h, cb));
-                    const __half2 *ha = reinterpret_cast<const __half2 *>(&va);
-                    const __half2 *hb = reinterpret_cast<const __half2 *>(&vb);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float2 fa = __half22float2(ha[k]), fb = __half22float2(hb[k]);
-                        acca[2 * k] += fa.x; acca[2 * k + 1] += fa.y;
-                        accb[2 * k] += fb.x; accb[2 * k + 1] += fb.y;
-                    }
-                }
-                uint4 oa, ob;
-                oa.x = h2(acca[0] * inv, acca[1] * inv); oa.y = h2(acca[2] * inv, acca[3] * inv);
-                oa.z = h2(acca[4] * inv, acca[5] * inv); oa.w = h2(acca[6] * inv, acca[7] * inv);
-                ob.x = h2(accb[0] * inv, accb[1] * inv); ob.y = h2(accb[2] * inv, accb[3] * inv);
-                ob.z = h2(accb[4] * inv, accb[5] * inv); ob.w = h2(accb[6] * inv, accb[7] * inv);
-                for (int h = 0; h < H; ++h) {
-                    *reinterpret_cast<uint4 *>(bufA + chunk_off(ROWS, ga * H + h, ca)) = oa;
-                    if (two) *reinterpret_cast<uint4 *>(bufA + chunk_off(ROWS, gb * H + h, cb)) = ob;
-                }
-            }
-        }
+        if (worker) mbar_wait(mbar, phase);
+        phase ^= 1;
+        fence_after_sync();
         TPROBE(15);
-        for (int it = worker ? tid : (1 << 30); it < (ROWS - rows) * (N_M1 / 8); it += kThreadsTC) {   // padding rows of the mean tile
-            const int c = it / (ROWS - rows), r = rows + it % (ROWS - rows);
-            *reinterpret_cast<uint4 *>(bufA + chunk_off(ROWS, r, c)) = make_uint4(0, 0, 0, 0);
+        {
+            const float inv = 1.0f / (float)H;                                  // mean = sum / H -> fp16 -> bufA
+            if (hf == 0) epilogue_scaled_to_smem(tlane, N_M1, 64, inv, bufA, row, 0);
+            else if (hf == 1) epilogue_scaled_to_smem(tlane, N_M1 + 64, 48, inv, bufA, row, 8);
         }
         TPROBE(16);
         fence_async_smem();
+        fence_before_sync();
         TPROBE(17);
         __syncthreads();
         TPROBE(6);
-        // ---- group-mean half of attention.0 (K=112 more) accumulates into TMEM[112,224) ----
+        // ---- attention.0 on [mlp1_out | mean] (K = 224) -> TMEM[112,224) ----
         if (issuer) {
             fence_after_sync();
+            mma_layer(tmem + N_M1, sB, ROWS, sWA1, N_M1, N_M1, N_M1, false);
             mma_layer(tmem + N_M1, sA, ROWS, sWA1 + (N_M1 / 8) * (N_M1 * 16), N_M1, N_M1, N_M1, true);
             commit(mbar);
         }
         // next tile: rotate + pack (rows) | rewards + self-state chunks (groups), hidden under the longest MMA
         if (next < ntiles) {
-            if (tid < 128) { row_features(in, dt, c0, c1, c2, c3); pin(c0, c1, c2, c3); }
-            else if (worker) group_work(p, st, time, human_v, actions, A, query_env, NG, G, next, t2, my_gl, my_h, Dscr, J, rew);
+            if (tid < 128) { row_features_j(in, dt, my_h, next * G + my_gl, J, c0, c1, c2, c3); pin(c0, c1, c2, c3); }
+            else if (worker) group_compute(p, gin, H, query_env, G, next, t2, Dscr, rew);
         }
         TPROBE(18);
         if (worker) mbar_wait(mbar, phase);
@@ -445,27 +541,6 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
         phase ^= 1;
         TPROBE(9);
         fence_after_sync();
-        // ---- group-selection matrix P'[g][r] = (r / H == g) -> bufA (mlp2.0 tile is dead): the weighted sum over
-        //      the humans of a group (sarl.py:57-60) becomes one more UMMA, D2 = P' * (w .* F) ----
-        if (worker) {
-            const int g = tid & 127, cbase = (tid >> 7) * 8;
-            const int lo = g * H, hi = min(lo + H, rows);
-#pragma unroll
-            for (int cc = 0; cc < 8; ++cc) {
-                const int c = cbase + cc, k0 = c * 8;
-                uint4 o = make_uint4(0, 0, 0, 0);
-                if (k0 < hi && k0 + 8 > lo) {
-                    uint32_t wds[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int ka = k0 + 2 * j, kb = ka + 1;
-                        wds[j] = ((ka >= lo && ka < hi) ? 0x3C00u : 0u) | ((kb >= lo && kb < hi) ? 0x3C000000u : 0u);
-                    }
-                    o = make_uint4(wds[0], wds[1], wds[2], wds[3]);
-                }
-                *reinterpret_cast<uint4 *>(bufA + chunk_off(ROWS, g, c)) = o;
-            }
-        }
         // ---- attention.4 (fp32 dot over ReLU(attention.2)), split between the two warps of a lane quarter ----
         if (worker) {
             float part = 0.0f;
@@ -526,21 +601,21 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
         TPROBE(11);
         if (issuer) {
             fence_after_sync();
-            mma_layer_bmn(tmem + T_D2, sA, ROWS, sB, ROWS, N_F, false);
+            mma_layer_ts_bmn(tmem + T_D2, tmem + T_P, sB, ROWS, N_F, false);   // every row of a group gets the group sum
             commit(mbar);
         }
         if (worker) mbar_wait(mbar, phase);
         phase ^= 1;
         TPROBE(12);
         fence_after_sync();
-        // ---- weighted feature of group g (TMEM lane g) -> J chunks 0..6 (fp16) ----
-        if (tid < 128 && (tid >> 5) * 32 < G) {       // warp-uniform: tcgen05.ld is .sync.aligned
+        // ---- weighted feature of the group (replicated on its rows; the h == 0 row stores it) -> J chunks 0..6 ----
+        if (tid < 128) {
             uint32_t v[32], u[32];
             ld32(tlane + T_D2, v);
             ld32(tlane + T_D2 + 32, u);
             wait_ld();
-            const int g = g0 + tid;
-            if (tid < G && g < NG) {
+            const int g = g0 + my_gl;
+            if (my_h == 0 && my_gl < G && g < NG) {
                 uint8_t *jt = J + (size_t)(g >> 7) * J_TILE_BYTES;
                 const int rb = g & 127;
 #pragma unroll
@@ -555,7 +630,7 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+    if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 // =====================================================================================================

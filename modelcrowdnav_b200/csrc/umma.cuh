@@ -229,6 +229,39 @@ __device__ __forceinline__ void cvt_store8(const uint32_t *v, uint8_t *dst)
     *reinterpret_cast<uint4 *>(dst) = o;
 }
 
+// scaled, no ReLU: used for the group mean (sum / H)
+__device__ __forceinline__ void scale_store8(const uint32_t *v, float scale, uint8_t *dst)
+{
+    const float *f = reinterpret_cast<const float *>(v);
+    uint4 o;
+    o.x = pack_f16x2(f[0] * scale, f[1] * scale); o.y = pack_f16x2(f[2] * scale, f[3] * scale);
+    o.z = pack_f16x2(f[4] * scale, f[5] * scale); o.w = pack_f16x2(f[6] * scale, f[7] * scale);
+    *reinterpret_cast<uint4 *>(dst) = o;
+}
+
+// TMEM columns [col, col + ncols) * scale -> fp16 row of a 128-row smem operand (ncols a multiple of 16)
+__device__ __forceinline__ void epilogue_scaled_to_smem(uint32_t taddr_lane, int col, int ncols, float scale, uint8_t *dst,
+                                                        int row, int kc0)
+{
+    int done = 0;
+    while (ncols - done >= 32) {
+        uint32_t v[32];
+        ld32(taddr_lane + col + done, v);
+        wait_ld();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) scale_store8(v + q * 8, scale, dst + chunk_off(128, row, kc0 + done / 8 + q));
+        done += 32;
+    }
+    if (ncols - done >= 16) {
+        uint32_t v[16];
+        ld16(taddr_lane + col + done, v);
+        wait_ld();
+#pragma unroll
+        for (int q = 0; q < 2; ++q) scale_store8(v + q * 8, scale, dst + chunk_off(128, row, kc0 + done / 8 + q));
+        done += 16;
+    }
+}
+
 template <bool RELU>
 __device__ __forceinline__ void epilogue_to_smem(uint32_t taddr_lane, int col, int ncols, uint8_t *dst, int row, int kc0)
 {
