@@ -208,6 +208,11 @@ int cn_selftest_umma(int32_t N, int32_t K, const float *a_host, const float *b_h
  * the form the kernel uses to sum the attention-weighted features over the humans of a group. */
 int cn_selftest_umma_bmn(int32_t N, int32_t K, const float *a_host, const float *b_host, float *d_host, int device);
 
+/* CTA-pair building block (tcgen05 cta_group::2, M = 256 over the two SMs of a cluster, B split in N halves):
+ * D[256 x N] = A[256 x K] * B[N x K]^T, repeated `reps` times; *cycles (optional) = clock64() ticks of the loop. */
+int cn_selftest_umma_pair(int32_t N, int32_t K, const float *a_host, const float *b_host, float *d_host, int32_t reps,
+                          long long *cycles, int device);
+
 /* Developer diagnostic: clock64() at the phase boundaries of one tile of the tensor-core row kernel (CTA 0).
  * The first call arms the probes; call again after a lookahead to read 16 timestamps. */
 int cn_debug_tc_timing(cn_policy *p, long long *out16);

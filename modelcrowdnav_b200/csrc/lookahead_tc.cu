@@ -79,12 +79,13 @@ constexpr int kTmemCols = 256;
 
 struct TcState {
     uint8_t *img_a, *img_b;   // device weight images
+    uint8_t *img_pair;        // two half images of the row network for tc_rows_pair_kernel (rank 0 | rank 1)
     long long *dbg;           // optional phase timestamps of CTA 0 (cn_debug_tc_timing)
     uint8_t *J;               // joint-state tiles
     double *rew;              // NG rewards
     size_t cap_groups;
     int num_sms;
-    int variant;              // 0 = one tile in flight (tc_rows_kernel), 1 = ping-pong (tc_rows_pp_kernel)
+    int variant;              // 0 = one tile in flight per SM (tc_rows_kernel), 2 = CTA pairs, two tiles in flight per SM
 };
 
 __device__ __forceinline__ void copy_image_to_smem(uint8_t *dst, const uint8_t *__restrict__ src, uint32_t bytes)
@@ -633,410 +634,7 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-// =====================================================================================================
-// kernel A, ping-pong variant ("pp"): TWO 128-row tiles in flight per SM so that the epilogue of one tile
-// overlaps the tensor-core work of the other.  Warps 0-3 / 4-7 are two epilogue groups (one thread per row),
-// warp 8 only issues tcgen05.mma + commit.  Groups and issuer hand stages over through mbarriers; there is no
-// CTA-wide barrier in the tile loop.  To fit two tiles, activations that are A operands live in TMEM
-// (tcgen05.st, compacted in place over the accumulator they came from) and only mlp1_out / attention.0 /
-// F' pass through one 28 KB shared-memory buffer per group; both group reductions (mean over humans, weighted
-// feature sum) are UMMAs with a constant same-group 0/1 matrix that stays in TMEM.
-//   per tile, 224 TMEM columns:   stage  A operand            D columns      epilogue
-//     0 mlp1.0      SS X (smem)          [0,160)      H1 -> fp16 in place [0,80)
-//     1 mlp1.2      TS H1                [80,192)     mlp1_out -> smem
-//     2 group sum   TS P, B = smem MN    [0,112)      mean -> fp16 in place [0,56)
-//     3 mlp2.0      SS mlp1_out          [56,168)     H3 -> fp16 in place [56,112)
-//     4 attention.0 SS mlp1_out + TS mean [112,224)   Ha1 -> smem
-//     5 attention.2 SS Ha1               [112,224)    score dot, exp, softmax weight
-//     6 mlp2.2      TS H3                [112,176)    F' = w * F -> smem
-//     7 weighted sum TS P, B = smem MN   [0,64)       joint state -> HBM
-// =====================================================================================================
-constexpr int kThreadsPP = 288;
-constexpr int PP_CTX = 224;                // TMEM columns per tile context
-constexpr int PP_TP = 448;                 // same-group matrix P: 64 columns
-constexpr uint32_t P_BUF0 = (IMG_A_BYTES + 127) & ~127u;
-constexpr uint32_t P_BUF1 = P_BUF0 + bytes_of(ROWS, N_M1);
-constexpr uint32_t P_MISC = P_BUF1 + bytes_of(ROWS, N_M1);   // S[2][128] f32 | D[2][128] f64 | 4 mbarriers | tmem slot
-constexpr uint32_t P_SMEM = P_MISC + 1024 + 2048 + 32 + 16;
-static_assert(P_SMEM <= 232448, "tc_rows_pp_kernel exceeds 227 KB of shared memory");
-
-struct RowInPP {
-    double rpx, rpy, rgx, rgy, rr, rvp, hpx, hpy, hvx, hvy, cvx, cvy, hr, ax, ay, t;
-    int valid;
-};
-
-__device__ __forceinline__ void pp_load_inputs(RowInPP &in, const EnvDims &ed, const double *__restrict__ st,
-                                               const double *__restrict__ time, const double *__restrict__ human_v,
-                                               const double *__restrict__ actions, int A, int query_env, int NG, int G,
-                                               int tile, int gl, int h)
-{
-    const int H = ed.H;
-    const int g = tile * G + gl;
-    in.valid = (gl < G && g < NG) ? 1 : 0;
-    if (!in.valid) return;
-    const int e = g / A, a = g - e * A;
-    in.rpx = st[st_idx(ed, F_PX, 0, e)]; in.rpy = st[st_idx(ed, F_PY, 0, e)];
-    in.rgx = st[st_idx(ed, F_GX, 0, e)]; in.rgy = st[st_idx(ed, F_GY, 0, e)];
-    in.rr = st[st_idx(ed, F_R, 0, e)];   in.rvp = st[st_idx(ed, F_VPREF, 0, e)];
-    in.hpx = st[st_idx(ed, F_PX, h + 1, e)]; in.hpy = st[st_idx(ed, F_PY, h + 1, e)];
-    in.hr = st[st_idx(ed, F_R, h + 1, e)];
-    in.cvx = st[st_idx(ed, F_VX, h + 1, e)]; in.cvy = st[st_idx(ed, F_VY, h + 1, e)];
-    if (query_env) {                                                                    // agent.py:63-74
-        in.hvx = human_v[(size_t)(0 * H + h) * ed.E + e]; in.hvy = human_v[(size_t)(1 * H + h) * ed.E + e];
-        in.t = time[e];
-    } else {                                                                            // cadrl.py:107-109
-        in.hvx = in.cvx; in.hvy = in.cvy; in.t = 0.0;
-    }
-    in.ax = actions[2 * a]; in.ay = actions[2 * a + 1];
-}
-
-// clearance of this row's human for the lookahead reward (see group_work for the equivalence with the
-// reference's break-on-first-collision loops)
-__device__ __forceinline__ double pp_clearance(const RowInPP &in, double dt, int query_env)
-{
-    if (!in.valid) return INFINITY;
-    if (query_env) {   // crowd_sim.py:347-359
-        const double px = in.hpx - in.rpx, py = in.hpy - in.rpy;
-        const double vx = in.cvx - in.ax, vy = in.cvy - in.ay;
-        const double ex = px + vx * dt, ey = py + vy * dt;
-        return cn_point_to_segment_dist0(px, py, ex, ey) - in.hr - in.rr;
-    }
-    // multi_human_rl.py:69-70
-    const double npx = in.rpx + in.ax * dt, npy = in.rpy + in.ay * dt;
-    const double nhx = in.hpx + in.cvx * dt, nhy = in.hpy + in.cvy * dt;
-    return norm2d(npx - nhx, npy - nhy) - in.rr - in.hr;
-}
-
-__device__ __forceinline__ void pp_features(const RowInPP &in, double dt, uint4 &c0, uint4 &c1, uint4 &c2, uint4 &c3,
-                                            float (&self_hi)[6], float (&self_lo)[6])
-{
-    c0 = make_uint4(0, 0, 0, 0); c1 = c0; c2 = c0; c3 = c0;
-    if (!in.valid) return;
-    float s[14], o[13];
-    s[0] = (float)(in.rpx + in.ax * dt); s[1] = (float)(in.rpy + in.ay * dt);
-    s[2] = (float)in.ax; s[3] = (float)in.ay; s[4] = (float)in.rr;
-    s[5] = (float)in.rgx; s[6] = (float)in.rgy; s[7] = (float)in.rvp; s[8] = 0.0f;
-    s[9] = (float)(in.hpx + in.hvx * dt); s[10] = (float)(in.hpy + in.hvy * dt);
-    s[11] = (float)in.hvx; s[12] = (float)in.hvy; s[13] = (float)in.hr;
-    cn_rotate(s, o);
-    float hi[13], lo[13];
-#pragma unroll
-    for (int k = 0; k < 13; ++k) split_hl(o[k], hi[k], lo[k]);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) { self_hi[k] = hi[k]; self_lo[k] = lo[k]; }
-    c0 = make_uint4(h2(hi[0], hi[1]), h2(hi[2], hi[3]), h2(hi[4], hi[5]), h2(hi[6], hi[7]));
-    c1 = make_uint4(h2(hi[8], hi[9]), h2(hi[10], hi[11]), h2(hi[12], 1.0f), h2(1.0f, 0.0f));
-    c2 = make_uint4(h2(lo[0], lo[1]), h2(lo[2], lo[3]), h2(lo[4], lo[5]), h2(lo[6], lo[7]));
-    c3 = make_uint4(h2(lo[8], lo[9]), h2(lo[10], lo[11]), h2(lo[12], 0.0f), 0u);
-}
-
-// thread with h == 0: fold the group's clearances through the reward ladder, store reward and self-state chunks
-__device__ __forceinline__ void pp_group_finish(const EnvParams &p, const RowInPP &in, const double *__restrict__ D, int H,
-                                                int query_env, int g, const float (&self_hi)[6], const float (&self_lo)[6],
-                                                uint8_t *__restrict__ J, double *__restrict__ rew)
-{
-    const double dt = p.time_step;
-    double dmin = INFINITY;
-    bool collision = false;
-    for (int k = 0; k < H; ++k) {
-        const double c = D[k];
-        if (c < 0) collision = true;
-        else if (c < dmin) dmin = c;
-    }
-    const double npx = in.rpx + in.ax * dt, npy = in.rpy + in.ay * dt;
-    const bool reaching_goal = norm2d(npx - in.rgx, npy - in.rgy) < in.rr;
-    double reward;
-    if (query_env) {                                                                 // crowd_sim.py:382-403
-        if (in.t >= p.time_limit - 1) reward = 0;
-        else if (collision) reward = p.collision_penalty;
-        else if (reaching_goal) reward = p.success_reward;
-        else if (dmin < p.discomfort_dist) reward = (dmin - p.discomfort_dist) * p.discomfort_penalty_factor * dt;
-        else reward = 0;
-    } else {                                                                         // multi_human_rl.py:77-86
-        if (collision) reward = -0.25;
-        else if (reaching_goal) reward = 1;
-        else if (dmin < 0.2) reward = (dmin - 0.2) * 0.5 * dt;
-        else reward = 0;
-    }
-    rew[g] = reward;
-    uint8_t *jt = J + (size_t)(g >> 7) * J_TILE_BYTES;
-    const int rb = g & 127;
-    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 7)) =
-        make_uint4(h2(self_hi[0], self_hi[1]), h2(self_hi[2], self_hi[3]), h2(self_hi[4], self_hi[5]), h2(1.0f, 1.0f));
-    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 8)) =
-        make_uint4(h2(self_lo[0], self_lo[1]), h2(self_lo[2], self_lo[3]), h2(self_lo[4], self_lo[5]), 0u);
-    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 9)) = make_uint4(0, 0, 0, 0);
-}
-
-__device__ __forceinline__ void eg_barrier(int eg)
-{
-    if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-    else asm volatile("bar.sync 2, 128;" ::: "memory");
-}
-
-__global__ void __launch_bounds__(kThreadsPP, 1)   // 9 warps: one SMSP hosts 3 of them -> at most 168 registers per thread
-tc_rows_pp_kernel(EnvParams p, const double *__restrict__ st, const double *__restrict__ time,
-                  const double *__restrict__ human_v, const double *__restrict__ actions, int A, int query_env,
-                  const uint8_t *__restrict__ wimg, uint8_t *__restrict__ J, double *__restrict__ rew, int NG, int G,
-                  int ntiles, long long *__restrict__ dbg, int flags)
-{
-#define PP_WAIT(bar, par) do { if (flags & 1) mbar_wait(bar, par); else mbar_wait_guarded(bar, par); } while (0)
-#define PPROBE(slot, i) do { if (dbg && blockIdx.x == 0 && probe_round) dbg[(slot) * 32 + (i)] = clock64(); } while (0)
-    extern __shared__ __align__(128) uint8_t smem[];
-    const EnvDims ed = p.d;
-    const int H = ed.H;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int eg = warp >> 2;                       // 0 / 1 = epilogue group, 2 = issuer warp
-    const int row = tid & 127;                      // tile row == TMEM lane of this thread (epilogue groups)
-    const int my_gl = row / H, my_h = row - my_gl * H;
-    const int rows = G * H;
-    const double dt = p.time_step;
-    uint8_t *buf = smem + (eg == 1 ? P_BUF1 : P_BUF0);
-    float *S = reinterpret_cast<float *>(smem + P_MISC) + (eg & 1) * 128;
-    double *D = reinterpret_cast<double *>(smem + P_MISC + 1024) + (eg & 1) * 128;
-    const uint32_t bar0 = smem_u32(smem + P_MISC + 1024 + 2048);
-    const uint32_t req0 = bar0, req1 = bar0 + 8, done0 = bar0 + 16, done1 = bar0 + 24;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + P_MISC + 1024 + 2048 + 32);
-    const float *tail = reinterpret_cast<const float *>(smem + OFF_TAILA);
-    const int stride = 2 * gridDim.x;               // tiles: 2 * (blockIdx.x + k * gridDim.x) + eg
-
-    copy_image_to_smem(smem, wimg, IMG_A_BYTES);
-    if (tid == 0) {
-        mbar_init(req0, 128); mbar_init(req1, 128); mbar_init(done0, 1); mbar_init(done1, 1);
-        fence_mbar_init();
-    }
-    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
-    fence_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
-    const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(eg & 1) * PP_CTX;   // lane quarter + context
-    // constant same-group matrix P[r][k] = (k / H == r / H) for r, k < rows, as a TS A operand: column c of lane r
-    // holds k = 2c (low half), 2c + 1 (high half)
-    if (eg == 0) {
-        const int lo = my_gl * H, hi = (row < rows) ? lo + H : lo;
-        for (int c8 = 0; c8 < 8; ++c8) {
-            uint32_t w[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int ka = (c8 * 8 + j) * 2, kb = ka + 1;
-                w[j] = ((ka >= lo && ka < hi) ? 0x3C00u : 0u) | ((kb >= lo && kb < hi) ? 0x3C000000u : 0u);
-            }
-            st8(tmem + ((uint32_t)((warp & 3) * 32) << 16) + PP_TP + c8 * 8, w);
-        }
-        wait_st();
-    }
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-
-    if (eg == 2) {
-        // ================= issuer warp =================
-        if (lane == 0) {
-            const uint32_t sW1 = smem_u32(smem + OFF_W1), sW2 = smem_u32(smem + OFF_W2), sW3 = smem_u32(smem + OFF_W3);
-            const uint32_t sW4 = smem_u32(smem + OFF_W4), sWA1 = smem_u32(smem + OFF_WA1), sWA2 = smem_u32(smem + OFF_WA2);
-            const uint32_t tP = tmem + PP_TP;
-            uint32_t ph[2] = {0, 0};
-            for (int base = 2 * blockIdx.x; base < ntiles; base += stride) {
-                const int nctx = ((base + 1 < ntiles) && !(flags & 2)) ? 2 : 1;
-                const bool probe_round = base == 2 * (int)blockIdx.x + 3 * stride;
-#pragma unroll 1
-                for (int s = 0; s < 8; ++s) {
-                    for (int c = 0; c < nctx; ++c) {
-                        PP_WAIT(c ? req1 : req0, ph[c]); ph[c] ^= 1;
-                        if (c == 0) PPROBE(2, 2 * s);
-                        fence_after_sync();
-                        const uint32_t tm = tmem + (uint32_t)c * PP_CTX;
-                        const uint32_t sB = smem_u32(smem + (c ? P_BUF1 : P_BUF0));
-                        switch (s) {
-                        case 0: mma_layer(tm + 0, sB, ROWS, sW1, N_H1, K_X, N_H1, false); break;
-                        case 1:
-                            if (flags & 256) { const long long tw = clock64(); while (clock64() - tw < 1500) { } }
-                            if (c == 0 && dbg && blockIdx.x == 0 && probe_round && !(flags & 12)) {
-                                // per-instruction issue timestamps of this TS stage (diagnostic round only)
-                                const uint32_t idesc = make_idesc_f16(N_M1);
-                                for (int k2 = 0; k2 < N_H1 / 16; ++k2) {
-                                    const uint64_t bd = make_desc(sW2 + (uint32_t)k2 * 2 * (N_M1 * 16), N_M1 * 16, 128);
-                                    mma_f16_ts(tm + 80, tm + 0 + (uint32_t)k2 * 8, bd, idesc, k2 > 0 ? 1u : 0u);
-                                    dbg[64 + 16 + k2] = clock64();
-                                }
-                            } else if (flags & 4) {      // diagnostic: A = constant P (K = 128)
-                                mma_layer_ts(tm + 80, tP, sW2, N_M1, 128, N_M1, false);
-                            } else if (flags & 8) {      // diagnostic: SS from the smem buffer (K = 112)
-                                mma_layer(tm + 80, sB, ROWS, sW2, N_M1, N_M1, N_M1, false);
-                            } else {
-                                mma_layer_ts(tm + 80, tm + ((flags & 128) ? 224 : 0), sW2, N_M1, N_H1, N_M1, false);
-                            }
-                            break;
-                        case 2: mma_layer_ts_bmn(tm + 0, tP, sB, ROWS, N_M1, false); break;
-                        case 3: mma_layer(tm + 56, sB, ROWS, sW3, N_M1, N_M1, N_M1, false); break;
-                        case 4:
-                            mma_layer(tm + 112, sB, ROWS, sWA1, N_M1, N_M1, N_M1, false);
-                            mma_layer_ts(tm + 112, tm + 0, sWA1 + (N_M1 / 8) * (N_M1 * 16), N_M1, N_M1, N_M1, true);
-                            break;
-                        case 5: mma_layer(tm + 112, sB, ROWS, sWA2, N_M1, N_M1, N_M1, false); break;
-                        case 6: mma_layer_ts(tm + 112, tm + 56, sW4, N_F, N_M1, N_F, false); break;
-                        default: mma_layer_ts_bmn(tm + 0, tP, sB, ROWS, N_F, false); break;
-                        }
-                        commit(c ? done1 : done0);
-                        if (c == 0) PPROBE(2, 2 * s + 1);
-                    }
-                }
-            }
-        }
-    } else {
-        // ================= epilogue group `eg` =================
-        const uint32_t req = eg ? req1 : req0, done = eg ? done1 : done0;
-        uint32_t ph = 0;
-        const float invH = 1.0f / (float)H;
-        uint4 c0, c1, c2, c3;
-        float shi[6], slo[6];
-        RowInPP in;
-        int tile = 2 * blockIdx.x + eg;
-        if ((flags & 2) && eg == 1) tile = ntiles;     // diagnostic: single context
-        if (tile < ntiles) {
-            // inputs of the first tile: features -> registers, clearances -> D, rewards / self-state -> HBM
-            pp_load_inputs(in, ed, st, time, human_v, actions, A, query_env, NG, G, tile, my_gl, my_h);
-            D[row] = pp_clearance(in, dt, query_env);
-            pp_features(in, dt, c0, c1, c2, c3, shi, slo);
-            eg_barrier(eg);
-            if (in.valid && my_h == 0) pp_group_finish(p, in, D + row, H, query_env, tile * G + my_gl, shi, slo, J, rew);
-            eg_barrier(eg);
-        }
-        for (; tile < ntiles; tile += stride) {
-            const int next = tile + stride;
-            const bool has_next = next < ntiles;
-            const int g = tile * G + my_gl;
-            const bool row_valid = (row < rows) && (g < NG);
-            const bool probe_round = (row == 0) && tile == 2 * (int)blockIdx.x + eg + 3 * stride;
-            int pst = 0;
-            PPROBE(eg, 30);
-            // ---- X operand -> smem, request stage 0 ----
-            *reinterpret_cast<uint4 *>(buf + chunk_off(ROWS, row, 0)) = c0;
-            *reinterpret_cast<uint4 *>(buf + chunk_off(ROWS, row, 1)) = c1;
-            *reinterpret_cast<uint4 *>(buf + chunk_off(ROWS, row, 2)) = c2;
-            *reinterpret_cast<uint4 *>(buf + chunk_off(ROWS, row, 3)) = c3;
-            fence_async_smem();
-            mbar_arrive(req); PPROBE(eg, 31);
-            // next tile's inputs: global loads fly under stage 0
-            if (has_next) pp_load_inputs(in, ed, st, time, human_v, actions, A, query_env, NG, G, next, my_gl, my_h);
-            // ---- E0: H1 = relu(acc) -> fp16, compacted in place [0,80) ----
-            PP_WAIT(done, ph); ph ^= 1; PPROBE(eg, 2 * pst); fence_after_sync();
-            compact_to_tmem<true>(tl, 0, N_H1, (flags & 128) ? 224 : 0, 1.0f, (flags & 16) != 0, (flags >> 5) & 3);
-            fence_before_sync();
-            mbar_arrive(req); PPROBE(eg, 2 * pst + 1); ++pst;
-            // ---- E1: mlp1_out = relu(acc[80,192)) -> smem (A of stages 3/4, B of stage 2) ----
-            PP_WAIT(done, ph); ph ^= 1; PPROBE(eg, 2 * pst); fence_after_sync();
-            epilogue_to_smem<true>(tl, 80, N_M1, buf, row, 0);
-            fence_async_smem();
-            fence_before_sync();
-            mbar_arrive(req); PPROBE(eg, 2 * pst + 1); ++pst;
-            if (has_next) D[row] = pp_clearance(in, dt, query_env);     // under stage 2
-            // ---- E2: group mean = acc[0,112) / H -> fp16 in place [0,56) ----
-            PP_WAIT(done, ph); ph ^= 1; PPROBE(eg, 2 * pst); fence_after_sync();
-            compact_to_tmem<false>(tl, 0, N_M1, 0, invH, (flags & 16) != 0);
-            fence_before_sync();
-            mbar_arrive(req); PPROBE(eg, 2 * pst + 1); ++pst;
-            float nshi[6], nslo[6];
-            uint4 n0, n1, n2, n3;
-            if (has_next) { pp_features(in, dt, n0, n1, n2, n3, nshi, nslo); pin(n0, n1, n2, n3); }   // under stage 3
-            // ---- E3: H3 = relu(acc[56,168)) -> fp16 in place [56,112) ----
-            PP_WAIT(done, ph); ph ^= 1; PPROBE(eg, 2 * pst); fence_after_sync();
-            compact_to_tmem<true>(tl, 56, N_M1, 56, 1.0f, (flags & 16) != 0);
-            fence_before_sync();
-            mbar_arrive(req); PPROBE(eg, 2 * pst + 1); ++pst;
-            if (has_next) {                                             // under stage 4
-                eg_barrier(eg);
-                if (in.valid && my_h == 0) pp_group_finish(p, in, D + row, H, query_env, next * G + my_gl, nshi, nslo, J, rew);
-            }
-            // ---- E4: Ha1 = relu(acc[112,224)) -> smem (mlp1_out is dead) ----
-            PP_WAIT(done, ph); ph ^= 1; PPROBE(eg, 2 * pst); fence_after_sync();
-            epilogue_to_smem<true>(tl, 112, N_M1, buf, row, 0);
-            fence_async_smem();
-            fence_before_sync();
-            mbar_arrive(req); PPROBE(eg, 2 * pst + 1); ++pst;
-            // ---- E5: attention.4 dot, exp, softmax weight (sarl.py:48-53) ----
-            PP_WAIT(done, ph); ph ^= 1; PPROBE(eg, 2 * pst); fence_after_sync();
-            float score = tail[100];
-            {
-                uint32_t v[32], u[32];
-                ld32(tl + 112, v);
-                ld32(tl + 144, u);
-                wait_ld();
-#pragma unroll
-                for (int k = 0; k < 32; ++k) score = fmaf(fmaxf(__uint_as_float(v[k]), 0.0f), tail[k], score);
-#pragma unroll
-                for (int k = 0; k < 32; ++k) score = fmaf(fmaxf(__uint_as_float(u[k]), 0.0f), tail[32 + k], score);
-                uint32_t x[32], y[16];
-                ld32(tl + 176, x);
-                ld16(tl + 208, y);
-                wait_ld();
-#pragma unroll
-                for (int k = 0; k < 32; ++k) score = fmaf(fmaxf(__uint_as_float(x[k]), 0.0f), tail[64 + k], score);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) score = fmaf(fmaxf(__uint_as_float(y[k]), 0.0f), tail[96 + k], score);
-            }
-            const float se = expf(score) * (score != 0.0f ? 1.0f : 0.0f);
-            S[row] = se;
-            fence_before_sync();
-            mbar_arrive(req); PPROBE(eg, 2 * pst + 1); ++pst;                                           // stage 6 (mlp2.2) may overwrite acc[112,176)
-            eg_barrier(eg);
-            float w = 0.0f;
-            if (row_valid) {
-                float ssum = 0.0f;
-                for (int h = 0; h < H; ++h) ssum += S[my_gl * H + h];
-                w = se / ssum;
-            }
-            // ---- E6: F' = w * F (acc[112,176)) -> fp16 -> smem (Ha1 is dead) ----
-            PP_WAIT(done, ph); ph ^= 1; PPROBE(eg, 2 * pst); fence_after_sync();
-            {
-                uint32_t v[32], u[32];
-                ld32(tl + 112, v);
-                ld32(tl + 144, u);
-                wait_ld();
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const float *f = reinterpret_cast<const float *>(v) + c * 8;
-                    *reinterpret_cast<uint4 *>(buf + chunk_off(ROWS, row, c)) =
-                        make_uint4(h2(w * f[0], w * f[1]), h2(w * f[2], w * f[3]), h2(w * f[4], w * f[5]), h2(w * f[6], w * f[7]));
-                }
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const float *f = reinterpret_cast<const float *>(u) + c * 8;
-                    *reinterpret_cast<uint4 *>(buf + chunk_off(ROWS, row, 4 + c)) =
-                        make_uint4(h2(w * f[0], w * f[1]), h2(w * f[2], w * f[3]), h2(w * f[4], w * f[5]), h2(w * f[6], w * f[7]));
-                }
-            }
-            fence_async_smem();
-            fence_before_sync();
-            mbar_arrive(req); PPROBE(eg, 2 * pst + 1); ++pst;
-            // ---- E7: weighted feature (every lane of a group holds the group sum) -> J chunks 0..6 ----
-            PP_WAIT(done, ph); ph ^= 1; PPROBE(eg, 2 * pst); fence_after_sync();
-            {
-                uint32_t v[32], u[32];
-                ld32(tl + 0, v);
-                ld32(tl + 32, u);
-                wait_ld();
-                if (row_valid && my_h == 0) {
-                    uint8_t *jt = J + (size_t)(g >> 7) * J_TILE_BYTES;
-                    const int rb = g & 127;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) cvt_store8<false>(v + 8 * c, jt + chunk_off(ROWS, rb, c));
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) cvt_store8<false>(u + 8 * c, jt + chunk_off(ROWS, rb, 4 + c));
-                }
-            }
-            fence_before_sync();
-            if (has_next) {
-                c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-            }
-        }
-    }
-    fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 512);
-}
+#include "tc_rows_pair.cuh"
 
 // =====================================================================================================
 // kernel B: mlp3 on the joint states + scoring (256 threads, same lane-quarter / column-half split)
@@ -1290,6 +888,14 @@ void fill_layer(std::vector<uint8_t> &img, uint32_t base, int R, const HostLinea
     if (ones_n >= 0 && kb >= 0) { put(img, base, R, ones_n, kb, 1.0f); put(img, base, R, ones_n + 1, kb, 1.0f); }
 }
 
+// rows [rank N/2, (rank+1) N/2) of a chunked K-major [N x K] image -> chunked K-major [N/2 x K]
+void split_rows(uint8_t *dst, const uint8_t *src, int N, int K, int rank)
+{
+    const int hn = N / 2;
+    for (int c = 0; c < K / 8; ++c)
+        memcpy(dst + (size_t)c * hn * 16, src + (size_t)c * N * 16 + (size_t)rank * hn * 16, (size_t)hn * 16);
+}
+
 }  // namespace
 
 int cn_tc_init(cn_policy *p)
@@ -1315,9 +921,13 @@ int cn_tc_init(cn_policy *p)
     }
     CN_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A_SMEM));
     CN_CUDA_CHECK(cudaFuncSetAttribute(tc_mlp3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B_SMEM));
-    CN_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM));
-    const char *var = getenv("CN_TC_VARIANT");
-    t->variant = (var && strcmp(var, "v3") == 0) ? 0 : ((var && strcmp(var, "pp") == 0) ? 1 : 0);
+    CN_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
+    if (cudaMalloc((void **)&t->img_pair, 2 * IMG_H_BYTES) != cudaSuccess) {
+        cn_set_error("cudaMalloc failed for the tensor-core weight images");
+        return CN_ENOMEM;
+    }
+    const char *var = getenv("CN_TC_VARIANT");   // developer switch: "single" = one tile in flight per SM
+    t->variant = (var && strcmp(var, "single") == 0) ? 0 : 2;
     p->tc = t;
     return CN_OK;
 }
@@ -1328,6 +938,7 @@ void cn_tc_destroy(cn_policy *p)
     if (!t) return;
     if (t->img_a) cudaFree(t->img_a);
     if (t->img_b) cudaFree(t->img_b);
+    if (t->img_pair) cudaFree(t->img_pair);
     if (t->J) cudaFree(t->J);
     if (t->rew) cudaFree(t->rew);
     if (t->dbg) cudaFree(t->dbg);
@@ -1371,6 +982,20 @@ int cn_tc_load_weights(cn_policy *p, const float *flat, cudaStream_t s)
     for (int k = 0; k < 100; ++k) tail[k] = L[10].w[k];
     tail[100] = L[10].b[0];
     memcpy(&b[OFF_TAILB], tail, TAIL_BYTES);
+    // half images for the CTA-pair kernel: CTA `rank` holds output rows [rank N/2, (rank+1) N/2) of every layer
+    std::vector<uint8_t> hp(2 * IMG_H_BYTES, 0);
+    for (int rank = 0; rank < 2; ++rank) {
+        uint8_t *h = hp.data() + (size_t)rank * IMG_H_BYTES;
+        split_rows(h + H_W1, a.data() + OFF_W1, N_H1, K_X, rank);
+        split_rows(h + H_W2, a.data() + OFF_W2, N_M1, N_H1, rank);
+        // stage 2, N = 224: rank 0 = mlp2.0 (all 112 rows), rank 1 = attention.0 rows on the mlp1_out half of K
+        memcpy(h + H_W3A, rank == 0 ? a.data() + OFF_W3 : a.data() + OFF_WA1, bytes_of(N_M1, N_M1));
+        split_rows(h + H_WB, a.data() + OFF_WA1 + bytes_of(N_M1, N_M1), N_M1, N_M1, rank);   // group-mean half of K
+        split_rows(h + H_W4, a.data() + OFF_W4, N_F, N_M1, rank);
+        split_rows(h + H_WA2, a.data() + OFF_WA2, N_M1, N_M1, rank);
+        memcpy(h + H_TAIL, a.data() + OFF_TAILA, TAIL_BYTES);
+    }
+    CN_CUDA_CHECK(cudaMemcpyAsync(t->img_pair, hp.data(), 2 * IMG_H_BYTES, cudaMemcpyHostToDevice, s));
     CN_CUDA_CHECK(cudaMemcpyAsync(t->img_a, a.data(), IMG_A_BYTES, cudaMemcpyHostToDevice, s));
     CN_CUDA_CHECK(cudaMemcpyAsync(t->img_b, b.data(), IMG_B_BYTES, cudaMemcpyHostToDevice, s));
     CN_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -1403,12 +1028,15 @@ int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cu
     const double gamma_bar = pow(p->cfg.gamma, env->p.time_step * p->cfg.v_pref);
     const int grid_a = ntiles_a < t->num_sms ? ntiles_a : t->num_sms;
     const int grid_b = ntiles_b < t->num_sms ? ntiles_b : t->num_sms;
-    if (t->variant == 1) {
-        const int pairs = (ntiles_a + 1) / 2;
-        const int grid_p = pairs < t->num_sms ? pairs : t->num_sms;
-        tc_rows_pp_kernel<<<grid_p, kThreadsPP, P_SMEM, s>>>(env->p, env->state, env->time, env->human_v, p->action_dev, A,
-                                                             query_env, t->img_a, t->J, t->rew, (int)NG, G, ntiles_a, t->dbg,
-                                                             getenv("CN_PP_FLAGS") ? atoi(getenv("CN_PP_FLAGS")) : 0);
+    if (t->variant == 2) {
+        // CTA pairs: every (cluster, rank, context) slot runs the same number of rounds; tiles past the end are all padding
+        int nclusters = t->num_sms / 2;
+        const int slots_needed = (ntiles_a + 3) / 4;
+        if (nclusters > slots_needed) nclusters = slots_needed;
+        const int rounds = (ntiles_a + 4 * nclusters - 1) / (4 * nclusters);
+        tc_rows_pair_kernel<<<2 * nclusters, kThreadsPair, Q_SMEM, s>>>(env->p, env->state, env->time, env->human_v, p->action_dev,
+                                                                       A, query_env, t->img_pair, t->J, t->rew, (int)NG, G, rounds,
+                                                                       t->dbg);
     } else {
         tc_rows_kernel<<<grid_a, kThreadsRows, A_SMEM, s>>>(env->p, env->state, env->time, env->human_v, p->action_dev, A,
                                                             query_env, t->img_a, t->J, t->rew, (int)NG, G, ntiles_a, t->dbg);
@@ -1466,6 +1094,43 @@ extern "C" int cn_selftest_umma(int32_t N, int32_t K, const float *a_host, const
 extern "C" int cn_selftest_umma_bmn(int32_t N, int32_t K, const float *a_host, const float *b_host, float *d_host, int device)
 {
     return selftest_impl(N, K, a_host, b_host, d_host, device, 1, 1, nullptr);
+}
+
+// CTA-pair building block: D[256 x N] = A[256 x K] * B[N x K]^T with one cta_group::2 UMMA chain (N % 16 == 0)
+extern "C" int cn_selftest_umma_pair(int32_t N, int32_t K, const float *a_host, const float *b_host, float *d_host,
+                                     int32_t reps, long long *cycles_host, int device)
+{
+    if (N < 32 || N > 256 || N % 16 || K < 16 || K % 16 || K > 256 || reps < 1) {
+        cn_set_error("N in [32,256] step 16, K in [16,256] step 16, reps >= 1");
+        return CN_EINVAL;
+    }
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); cn_set_error("no CUDA device available; no CPU fallback"); return CN_ECUDA; }
+    CN_CUDA_CHECK(cudaSetDevice(device));
+    const size_t a_bytes = bytes_of(ROWS, K), b_bytes = bytes_of(N / 2, K);
+    std::vector<uint8_t> ai(2 * a_bytes, 0), bi(2 * b_bytes, 0);
+    for (int r = 0; r < 2 * ROWS; ++r)
+        for (int k = 0; k < K; ++k) put(ai, (uint32_t)((r / ROWS) * a_bytes), ROWS, r % ROWS, k, a_host[(size_t)r * K + k]);
+    for (int r = 0; r < N; ++r)
+        for (int k = 0; k < K; ++k) put(bi, (uint32_t)((r / (N / 2)) * b_bytes), N / 2, r % (N / 2), k, b_host[(size_t)r * K + k]);
+    uint8_t *da = nullptr, *db = nullptr;
+    float *dd = nullptr;
+    long long *dc = nullptr;
+    CN_CUDA_CHECK(cudaMalloc((void **)&da, ai.size()));
+    CN_CUDA_CHECK(cudaMalloc((void **)&db, bi.size()));
+    CN_CUDA_CHECK(cudaMalloc((void **)&dd, sizeof(float) * 2 * ROWS * N));
+    CN_CUDA_CHECK(cudaMalloc((void **)&dc, sizeof(long long)));
+    CN_CUDA_CHECK(cudaMemcpy(da, ai.data(), ai.size(), cudaMemcpyHostToDevice));
+    CN_CUDA_CHECK(cudaMemcpy(db, bi.data(), bi.size(), cudaMemcpyHostToDevice));
+    const size_t smem = a_bytes + b_bytes + 64;
+    CN_CUDA_CHECK(cudaFuncSetAttribute(umma_pair_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_pair_selftest_kernel<<<2, 160, smem>>>(da, db, dd, N, K, reps, dc);
+    CN_LAUNCH_CHECK();
+    CN_CUDA_CHECK(cudaDeviceSynchronize());
+    CN_CUDA_CHECK(cudaMemcpy(d_host, dd, sizeof(float) * 2 * ROWS * N, cudaMemcpyDeviceToHost));
+    if (cycles_host) CN_CUDA_CHECK(cudaMemcpy(cycles_host, dc, sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dd); cudaFree(dc);
+    return CN_OK;
 }
 
 // Developer diagnostic (not part of the reference surface): clock64() at the phase boundaries of one tile of

@@ -1,0 +1,491 @@
+// tc_rows_pair.cuh -- the row network of the SARL lookahead on CTA PAIRS (tcgen05 cta_group::2).
+// Included by lookahead_tc.cu inside its anonymous namespace (shares the padded shapes and the input helpers).
+//
+// Why pairs: with one CTA per SM the fp16 weights of the row network (157 KB) leave room for the activations
+// of only ONE 128-row tile, so the tensor pipe idles during every epilogue (tc_rows_kernel: 21 % tensor-active).
+// A cta_group::2 UMMA splits the B operand (the weights) in halves between the two SMs of a cluster, so each SM
+// keeps 78.5 KB of weights and has room for TWO tile contexts (2 x 68 KB of activations, 2 x 224 TMEM columns).
+// Per SM: epilogue group 0 (warps 0-3) owns context 0, group 1 (warps 4-7) owns context 1, warp 8 of the
+// rank-0 CTA issues every UMMA of the pair (M = 256 = tile of CTA 0 + tile of CTA 1 for the same context).
+// Hand-over is pure dataflow through mbarriers, no CTA-wide barrier in the tile loop:
+//   req[c]  (rank-0 CTA, 8 arrivals = 4 warps x 2 CTAs)  "operand of context c's next stage is in shared memory"
+//   reqm[c] (same, for stage 3 only: stages 2 and 3 are requested without a completion wait in between, and
+//            the two CTAs are not in lock step, so a shared barrier could see stage-3 arrivals in stage 2's phase)
+//   done[c] (both CTAs, multicast tcgen05.commit)          "accumulator of context c's stage is complete"
+//
+// Per context and tile (rows = (env, action, human); D = TMEM columns relative to the context base):
+//   stage  UMMA (M=256 over the pair)                         A operand        D          epilogue (CUDA cores)
+//   0      mlp1.0                K=32   N=160                 X    (R1 tail)   [0,160)    ReLU -> H1 (R1)
+//   1      mlp1.2                K=160  N=112                 H1   (R1)        [0,112)    ReLU -> mlp1_out (R2)
+//   2      [mlp2.0 | attn.0a]    K=112  N=224                 mlp1_out (R2)    [0,224)    group mean of mlp1_out in smem
+//   3      attn.0b (mean half)   K=112  N=112, accumulate     mean (R1)        [112,224)  ReLU -> H3 (R1), Ha1 (R2)
+//   4      mlp2.2 ; attn.2       K=112  N=64 ; N=112          H3 ; Ha1         [0,64) ; [64,176)
+//          attention.4 as an fp32 dot -> masked softmax over the group -> w * F (fp32, smem) -> sum over the
+//          humans of the group in shared memory -> joint state J (fp16) -> HBM
+// The next tile's propagate / rotate features, clearances and rewards are computed under stages 2-3.
+//
+// Reference: crowd_nav/policy/sarl.py:28-65 (value network), cadrl.py:104-129,217-252 (propagate, rotate),
+// multi_human_rl.py:65-88 / crowd_sim.py:344-403 (lookahead reward).
+
+constexpr int kThreadsPair = 288;
+constexpr int N_S2 = 2 * N_M1;             // stage 2: [mlp2.0 (rank-0 half) | attention.0 on mlp1_out (rank-1 half)]
+constexpr int PAIR_CTX_COLS = 224;         // TMEM columns per tile context
+
+// per-CTA HALF weight image: rows [rank * N/2, (rank+1) * N/2) of every layer, chunked K-major with R = N/2
+constexpr uint32_t H_W1 = 0;                                        //  80 x 32
+constexpr uint32_t H_W2 = H_W1 + bytes_of(N_H1 / 2, K_X);           //  56 x 160
+constexpr uint32_t H_W3A = H_W2 + bytes_of(N_M1 / 2, N_H1);         // 112 x 112  (rank 0: mlp2.0, rank 1: attention.0 first half)
+constexpr uint32_t H_WB = H_W3A + bytes_of(N_M1, N_M1);             //  56 x 112  attention.0, group-mean half
+constexpr uint32_t H_W4 = H_WB + bytes_of(N_M1 / 2, N_M1);          //  32 x 112
+constexpr uint32_t H_WA2 = H_W4 + bytes_of(N_F / 2, N_M1);          //  56 x 112
+constexpr uint32_t H_TAIL = H_WA2 + bytes_of(N_M1 / 2, N_M1);       // fp32: attention.4 weight[100], bias
+constexpr uint32_t IMG_H_BYTES = H_TAIL + TAIL_BYTES;
+
+// shared-memory map of tc_rows_pair_kernel
+constexpr uint32_t Q_R1_BYTES = bytes_of(ROWS, N_H1);               // 40 KB: H1 | mean, next X | H3 | w*F (fp32)
+constexpr uint32_t Q_R2_BYTES = bytes_of(ROWS, N_M1);               // 28 KB: mlp1_out | Ha1
+constexpr uint32_t Q_X_OFF = bytes_of(ROWS, N_M1);                  // next tile's X inside R1 (behind the 112-column tiles)
+constexpr uint32_t Q_CTX_BYTES = Q_R1_BYTES + Q_R2_BYTES;
+constexpr uint32_t Q_CTX0 = (IMG_H_BYTES + 127) & ~127u;
+constexpr uint32_t Q_MISC = Q_CTX0 + 2 * Q_CTX_BYTES;               // S[2][128] f32 | D[2][128] f64 | 6 mbarriers | tmem slot
+constexpr uint32_t Q_SMEM = Q_MISC + 1024 + 2048 + 48 + 16;
+static_assert(Q_X_OFF + bytes_of(ROWS, K_X) <= Q_R1_BYTES, "next-tile X must fit behind the 112-column tiles");
+static_assert(ROWS * 56 * 4 <= Q_X_OFF, "fp32 weighted features must not reach the next tile's X");
+static_assert(Q_SMEM <= 232448, "tc_rows_pair_kernel exceeds 227 KB of shared memory");
+
+struct RowInPP {
+    double rpx, rpy, rgx, rgy, rr, rvp, hpx, hpy, hvx, hvy, cvx, cvy, hr, ax, ay, t;
+    int valid;
+};
+
+__device__ __forceinline__ void pp_load_inputs(RowInPP &in, const EnvDims &ed, const double *__restrict__ st,
+                                               const double *__restrict__ time, const double *__restrict__ human_v,
+                                               const double *__restrict__ actions, int A, int query_env, int NG, int G,
+                                               int tile, int gl, int h)
+{
+    const int H = ed.H;
+    const long long g = (long long)tile * G + gl;
+    in.valid = (gl < G && g < NG) ? 1 : 0;
+    if (!in.valid) return;
+    const int e = (int)(g / A), a = (int)(g - (long long)e * A);
+    in.rpx = st[st_idx(ed, F_PX, 0, e)]; in.rpy = st[st_idx(ed, F_PY, 0, e)];
+    in.rgx = st[st_idx(ed, F_GX, 0, e)]; in.rgy = st[st_idx(ed, F_GY, 0, e)];
+    in.rr = st[st_idx(ed, F_R, 0, e)];   in.rvp = st[st_idx(ed, F_VPREF, 0, e)];
+    in.hpx = st[st_idx(ed, F_PX, h + 1, e)]; in.hpy = st[st_idx(ed, F_PY, h + 1, e)];
+    in.hr = st[st_idx(ed, F_R, h + 1, e)];
+    in.cvx = st[st_idx(ed, F_VX, h + 1, e)]; in.cvy = st[st_idx(ed, F_VY, h + 1, e)];
+    if (query_env) {                                                                    // agent.py:63-74
+        in.hvx = human_v[(size_t)(0 * H + h) * ed.E + e]; in.hvy = human_v[(size_t)(1 * H + h) * ed.E + e];
+        in.t = time[e];
+    } else {                                                                            // cadrl.py:107-109
+        in.hvx = in.cvx; in.hvy = in.cvy; in.t = 0.0;
+    }
+    in.ax = actions[2 * a]; in.ay = actions[2 * a + 1];
+}
+
+// clearance of this row's human for the lookahead reward (see group_work for the equivalence with the
+// reference's break-on-first-collision loops)
+__device__ __forceinline__ double pp_clearance(const RowInPP &in, double dt, int query_env)
+{
+    if (!in.valid) return INFINITY;
+    if (query_env) {   // crowd_sim.py:347-359
+        const double px = in.hpx - in.rpx, py = in.hpy - in.rpy;
+        const double vx = in.cvx - in.ax, vy = in.cvy - in.ay;
+        const double ex = px + vx * dt, ey = py + vy * dt;
+        return cn_point_to_segment_dist0(px, py, ex, ey) - in.hr - in.rr;
+    }
+    // multi_human_rl.py:69-70
+    const double npx = in.rpx + in.ax * dt, npy = in.rpy + in.ay * dt;
+    const double nhx = in.hpx + in.cvx * dt, nhy = in.hpy + in.cvy * dt;
+    return norm2d(npx - nhx, npy - nhy) - in.rr - in.hr;
+}
+
+__device__ __forceinline__ void pp_features(const RowInPP &in, double dt, uint4 &c0, uint4 &c1, uint4 &c2, uint4 &c3)
+{
+    c0 = make_uint4(0, 0, 0, 0); c1 = c0; c2 = c0; c3 = c0;
+    if (!in.valid) return;
+    float s[14], o[13];
+    s[0] = (float)(in.rpx + in.ax * dt); s[1] = (float)(in.rpy + in.ay * dt);
+    s[2] = (float)in.ax; s[3] = (float)in.ay; s[4] = (float)in.rr;
+    s[5] = (float)in.rgx; s[6] = (float)in.rgy; s[7] = (float)in.rvp; s[8] = 0.0f;
+    s[9] = (float)(in.hpx + in.hvx * dt); s[10] = (float)(in.hpy + in.hvy * dt);
+    s[11] = (float)in.hvx; s[12] = (float)in.hvy; s[13] = (float)in.hr;
+    cn_rotate(s, o);
+    float hi[13], lo[13];
+#pragma unroll
+    for (int k = 0; k < 13; ++k) split_hl(o[k], hi[k], lo[k]);
+    c0 = make_uint4(h2(hi[0], hi[1]), h2(hi[2], hi[3]), h2(hi[4], hi[5]), h2(hi[6], hi[7]));
+    c1 = make_uint4(h2(hi[8], hi[9]), h2(hi[10], hi[11]), h2(hi[12], 1.0f), h2(1.0f, 0.0f));
+    c2 = make_uint4(h2(lo[0], lo[1]), h2(lo[2], lo[3]), h2(lo[4], lo[5]), h2(lo[6], lo[7]));
+    c3 = make_uint4(h2(lo[8], lo[9]), h2(lo[10], lo[11]), h2(lo[12], 0.0f), 0u);
+}
+
+// thread with h == 0: fold the group's clearances through the reward ladder, store the reward and the self-state
+// chunks 7..9 of the joint state (c0 = hi[0..7], c2 = lo[0..7]: the self state is columns 0..5 of the rotated row)
+__device__ __forceinline__ void pp_group_finish(const EnvParams &p, const RowInPP &in, const double *__restrict__ D, int H,
+                                                int query_env, long long g, const uint4 &c0, const uint4 &c2,
+                                                uint8_t *__restrict__ J, double *__restrict__ rew)
+{
+    const double dt = p.time_step;
+    double dmin = INFINITY;
+    bool collision = false;
+    for (int k = 0; k < H; ++k) {
+        const double c = D[k];
+        if (c < 0) collision = true;
+        else if (c < dmin) dmin = c;
+    }
+    const double npx = in.rpx + in.ax * dt, npy = in.rpy + in.ay * dt;
+    const bool reaching_goal = norm2d(npx - in.rgx, npy - in.rgy) < in.rr;
+    double reward;
+    if (query_env) {                                                                 // crowd_sim.py:382-403
+        if (in.t >= p.time_limit - 1) reward = 0;
+        else if (collision) reward = p.collision_penalty;
+        else if (reaching_goal) reward = p.success_reward;
+        else if (dmin < p.discomfort_dist) reward = (dmin - p.discomfort_dist) * p.discomfort_penalty_factor * dt;
+        else reward = 0;
+    } else {                                                                         // multi_human_rl.py:77-86
+        if (collision) reward = -0.25;
+        else if (reaching_goal) reward = 1;
+        else if (dmin < 0.2) reward = (dmin - 0.2) * 0.5 * dt;
+        else reward = 0;
+    }
+    rew[g] = reward;
+    uint8_t *jt = J + (size_t)(g >> 7) * J_TILE_BYTES;
+    const int rb = (int)(g & 127);
+    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 7)) = make_uint4(c0.x, c0.y, c0.z, h2(1.0f, 1.0f));
+    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 8)) = make_uint4(c2.x, c2.y, c2.z, 0u);
+    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 9)) = make_uint4(0, 0, 0, 0);
+}
+
+__device__ __forceinline__ void ctx_barrier(int eg)
+{
+    if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+    else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
+
+// Everything the NEXT tile needs before its stage 0: X operand -> shared memory, clearances -> D, and (after a
+// context barrier) reward + self-state chunks -> HBM.  Called under the stage-2/3 UMMAs of the current tile.
+__device__ __forceinline__ void pair_prepare_tile(const EnvParams &p, const RowInPP &in, int H, int query_env, int G, int tile,
+                                                  int row, int my_gl, int my_h, int eg, uint8_t *__restrict__ xbuf,
+                                                  double *__restrict__ D, uint8_t *__restrict__ J, double *__restrict__ rew)
+{
+    const double dt = p.time_step;
+    uint4 c0, c1, c2, c3;
+    D[row] = pp_clearance(in, dt, query_env);
+    pp_features(in, dt, c0, c1, c2, c3);
+    *reinterpret_cast<uint4 *>(xbuf + chunk_off(ROWS, row, 0)) = c0;
+    *reinterpret_cast<uint4 *>(xbuf + chunk_off(ROWS, row, 1)) = c1;
+    *reinterpret_cast<uint4 *>(xbuf + chunk_off(ROWS, row, 2)) = c2;
+    *reinterpret_cast<uint4 *>(xbuf + chunk_off(ROWS, row, 3)) = c3;
+    ctx_barrier(eg);
+    if (in.valid && my_h == 0) pp_group_finish(p, in, D + row, H, query_env, (long long)tile * G + my_gl, c0, c2, J, rew);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsPair, 1)
+tc_rows_pair_kernel(EnvParams p, const double *__restrict__ st, const double *__restrict__ time,
+                    const double *__restrict__ human_v, const double *__restrict__ actions, int A, int query_env,
+                    const uint8_t *__restrict__ wimg, uint8_t *__restrict__ J, double *__restrict__ rew, int NG, int G,
+                    int rounds, long long *__restrict__ dbg)
+{
+#define QPROBE(slot, i) do { if (dbg && blockIdx.x == 0 && probe_round) dbg[(slot) * 32 + (i)] = clock64(); } while (0)
+    extern __shared__ __align__(128) uint8_t smem[];
+    const EnvDims ed = p.d;
+    const int H = ed.H;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int eg = warp >> 2;                       // 0 / 1 = epilogue group == tile context, 2 = issuer warp
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+    const int row = tid & 127;                      // tile row == TMEM lane of this thread (epilogue groups)
+    const int my_gl = row / H, my_h = row - my_gl * H;
+    const int rows = G * H;
+    uint8_t *R1 = smem + Q_CTX0 + (uint32_t)(eg & 1) * Q_CTX_BYTES, *R2 = R1 + Q_R1_BYTES;
+    float *S = reinterpret_cast<float *>(smem + Q_MISC) + (eg & 1) * 128;
+    double *D = reinterpret_cast<double *>(smem + Q_MISC + 1024) + (eg & 1) * 128;
+    const uint32_t bar0 = smem_u32(smem + Q_MISC + 1024 + 2048);
+    const uint32_t req0 = bar0, req1 = bar0 + 8, done0 = bar0 + 16, done1 = bar0 + 24, reqm0 = bar0 + 32, reqm1 = bar0 + 40;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Q_MISC + 1024 + 2048 + 48);
+    const float *tail = reinterpret_cast<const float *>(smem + H_TAIL);
+
+    copy_image_to_smem(smem, wimg + (size_t)rank * IMG_H_BYTES, IMG_H_BYTES);
+    for (uint32_t i = tid * 16; i < 2 * Q_CTX_BYTES; i += kThreadsPair * 16)       // padding rows stay finite
+        *reinterpret_cast<uint4 *>(smem + Q_CTX0 + i) = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        mbar_init(req0, 8); mbar_init(req1, 8); mbar_init(done0, 1); mbar_init(done1, 1);
+        mbar_init(reqm0, 8); mbar_init(reqm1, 8);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc_2(smem_u32(tmem_slot), 512);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    if (eg == 2) {
+        // ================= issuer warp (rank-0 CTA only) =================
+        if (rank == 0 && lane == 0) {
+            const uint32_t sW1 = smem_u32(smem + H_W1), sW2 = smem_u32(smem + H_W2), sW3A = smem_u32(smem + H_W3A);
+            const uint32_t sWB = smem_u32(smem + H_WB), sW4 = smem_u32(smem + H_W4), sWA2 = smem_u32(smem + H_WA2);
+            const int total = 5 * rounds;
+            int stage0 = 0, stage1 = 0;
+            uint32_t ph0 = 0, ph1 = 0, phm0 = 0, phm1 = 0;
+            long long t_last = clock64();
+            while (stage0 < total || stage1 < total) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    int &stage = c ? stage1 : stage0;
+                    if (stage >= total) continue;
+                    const int s = stage % 5;
+                    uint32_t &ph = (s == 3) ? (c ? phm1 : phm0) : (c ? ph1 : ph0);
+                    if (!mbar_test_wait_cluster((s == 3) ? (c ? reqm1 : reqm0) : (c ? req1 : req0), ph)) continue;
+                    ph ^= 1;
+                    fence_after_sync();
+                    const uint32_t tm = tmem + (uint32_t)c * PAIR_CTX_COLS;
+                    const uint32_t sR1 = smem_u32(smem + Q_CTX0 + (uint32_t)c * Q_CTX_BYTES), sR2 = sR1 + Q_R1_BYTES;
+                    const uint32_t done = c ? done1 : done0;
+                    if (s == 0) {
+                        mma_layer_2(tm, sR1 + Q_X_OFF, ROWS, sW1, K_X, N_H1, false);
+                        commit_2(done, 3);
+                    } else if (s == 1) {
+                        mma_layer_2(tm, sR1, ROWS, sW2, N_H1, N_M1, false);
+                        commit_2(done, 3);
+                    } else if (s == 2) {
+                        mma_layer_2(tm, sR2, ROWS, sW3A, N_M1, N_S2, false);          // completion rides on stage 3's commit
+                    } else if (s == 3) {
+                        mma_layer_2(tm + N_M1, sR1, ROWS, sWB, N_M1, N_M1, true);
+                        commit_2(done, 3);
+                    } else {
+                        mma_layer_2(tm, sR1, ROWS, sW4, N_M1, N_F, false);
+                        mma_layer_2(tm + N_F, sR2, ROWS, sWA2, N_M1, N_M1, false);
+                        commit_2(done, 3);
+                    }
+                    ++stage;
+                    t_last = clock64();
+                }
+                if (clock64() - t_last > 4000000000LL) __trap();    // protocol bug guard: never hang the GPU
+            }
+        }
+    } else {
+        // ================= epilogue group `eg` (both CTAs) =================
+        const uint32_t done = eg ? done1 : done0;
+        const uint32_t req_leader = mapa(eg ? req1 : req0, 0), reqm_leader = mapa(eg ? reqm1 : reqm0, 0);
+        const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)eg * PAIR_CTX_COLS;
+        uint8_t *xbuf = R1 + Q_X_OFF;
+        uint32_t ph = 0;
+        const float invH = 1.0f / (float)H;
+        const int tile_stride = 4 * nclusters;
+        int tile = (cluster_id * 2 + (int)rank) * 2 + eg;
+        // operand hand-over: generic-proxy writes -> async proxy, TMEM reads ordered, one arrival per warp
+#define PAIR_SIGNAL_TO(bar) do { fence_async_smem(); fence_before_sync(); __syncwarp(); if (lane == 0) mbar_arrive_cluster(bar); } while (0)
+#define PAIR_SIGNAL() PAIR_SIGNAL_TO(req_leader)
+#define PAIR_WAIT() do { mbar_wait_guarded(done, ph); ph ^= 1; fence_after_sync(); } while (0)
+        {
+            RowInPP in;
+            pp_load_inputs(in, ed, st, time, human_v, actions, A, query_env, NG, G, tile, my_gl, my_h);
+            pair_prepare_tile(p, in, H, query_env, G, tile, row, my_gl, my_h, eg, xbuf, D, J, rew);
+        }
+        for (int rnd = 0; rnd < rounds; ++rnd, tile += tile_stride) {
+            const bool has_next = rnd + 1 < rounds;
+            const bool probe_round = (row == 0) && rnd == 3;
+            const long long g = (long long)tile * G + my_gl;
+            const bool row_valid = (row < rows) && (g < NG);
+            QPROBE(eg, 0);
+            // ---- stage 0 request: X of this tile is in R1's tail (written one tile ago / by the prologue) ----
+            PAIR_SIGNAL();
+            // ---- E0: H1 = relu(acc[0,160)) -> R1 ----
+            PAIR_WAIT(); QPROBE(eg, 1);
+            epilogue_to_smem<true>(tl, 0, N_H1, R1, row, 0);
+            PAIR_SIGNAL(); QPROBE(eg, 2);
+            // ---- E1: mlp1_out = relu(acc[0,112)) -> R2 ----
+            PAIR_WAIT(); QPROBE(eg, 3);
+            epilogue_to_smem<true>(tl, 0, N_M1, R2, row, 0);
+            PAIR_SIGNAL(); QPROBE(eg, 4);                                          // stage 2 may start
+            RowInPP in;
+            if (has_next) pp_load_inputs(in, ed, st, time, human_v, actions, A, query_env, NG, G, tile + tile_stride, my_gl, my_h);
+            // ---- group mean of mlp1_out over the humans of a group (sarl.py:42), replicated on the group's rows -> R1 ----
+            ctx_barrier(eg);
+            {
+                const int nitems = G * (N_M1 / 8);
+                for (int it = row; it < nitems; it += 128) {                       // consecutive threads -> consecutive groups
+                    const int c = it / G, gl = it - c * G;
+                    const uint8_t *src = R2 + chunk_off(ROWS, gl * H, c);
+                    __half2 acc[4];
+                    {
+                        const uint4 v = *reinterpret_cast<const uint4 *>(src);
+                        const __half2 *hv = reinterpret_cast<const __half2 *>(&v);
+                        acc[0] = hv[0]; acc[1] = hv[1]; acc[2] = hv[2]; acc[3] = hv[3];
+                    }
+                    for (int h = 1; h < H; ++h) {
+                        const uint4 v = *reinterpret_cast<const uint4 *>(src + h * 16);
+                        const __half2 *hv = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) acc[k] = __hadd2(acc[k], hv[k]);
+                    }
+                    uint4 o;
+                    {
+                        const float2 f0 = __half22float2(acc[0]), f1 = __half22float2(acc[1]);
+                        const float2 f2 = __half22float2(acc[2]), f3 = __half22float2(acc[3]);
+                        o.x = h2(f0.x * invH, f0.y * invH); o.y = h2(f1.x * invH, f1.y * invH);
+                        o.z = h2(f2.x * invH, f2.y * invH); o.w = h2(f3.x * invH, f3.y * invH);
+                    }
+                    uint8_t *dst = R1 + chunk_off(ROWS, gl * H, c);
+                    for (int h = 0; h < H; ++h) *reinterpret_cast<uint4 *>(dst + h * 16) = o;
+                }
+            }
+            PAIR_SIGNAL_TO(reqm_leader); QPROBE(eg, 5);                            // stage 3 may start
+            // ---- next tile: clearances, rotate + pack -> X, rewards + self state (under stages 2-3) ----
+            if (has_next) pair_prepare_tile(p, in, H, query_env, G, tile + tile_stride, row, my_gl, my_h, eg, xbuf, D, J, rew);
+            QPROBE(eg, 6);
+            // ---- E3: H3 = relu(acc[0,112)) -> R1 ; Ha1 = relu(acc[112,224)) -> R2 ----
+            PAIR_WAIT(); QPROBE(eg, 7);
+            epilogue_to_smem<true>(tl, 0, N_M1, R1, row, 0);
+            epilogue_to_smem<true>(tl, N_M1, N_M1, R2, row, 0);
+            PAIR_SIGNAL(); QPROBE(eg, 8);
+            // ---- E4: attention.4 dot, exp, masked softmax (sarl.py:48-53), weighted feature sum (sarl.py:57-60) ----
+            PAIR_WAIT(); QPROBE(eg, 9);
+            float score = tail[100];
+            {
+                uint32_t v[32], u[32];
+                ld32(tl + N_F, v);
+                ld32(tl + N_F + 32, u);
+                wait_ld();
+#pragma unroll
+                for (int k = 0; k < 32; ++k) score = fmaf(fmaxf(__uint_as_float(v[k]), 0.0f), tail[k], score);
+#pragma unroll
+                for (int k = 0; k < 32; ++k) score = fmaf(fmaxf(__uint_as_float(u[k]), 0.0f), tail[32 + k], score);
+                uint32_t x[32], y[16];
+                ld32(tl + N_F + 64, x);
+                ld16(tl + N_F + 96, y);
+                wait_ld();
+#pragma unroll
+                for (int k = 0; k < 32; ++k) score = fmaf(fmaxf(__uint_as_float(x[k]), 0.0f), tail[64 + k], score);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) score = fmaf(fmaxf(__uint_as_float(y[k]), 0.0f), tail[96 + k], score);
+            }
+            const float se = expf(score) * (score != 0.0f ? 1.0f : 0.0f);
+            S[row] = se;
+            ctx_barrier(eg);
+            float w = 0.0f;
+            if (row_valid) {
+                float ssum = 0.0f;
+                for (int h = 0; h < H; ++h) ssum += S[my_gl * H + h];
+                w = se / ssum;
+            }
+            {
+                // w * F in fp32, chunked [c][row][8 floats] over the (dead) H3 tile
+                uint32_t v[32], u[32];
+                ld32(tl + 0, v);
+                ld32(tl + 32, u);
+                wait_ld();
+                float *fdst = reinterpret_cast<float *>(R1) + row * 8;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float *f = reinterpret_cast<const float *>(v) + c * 8;
+                    *reinterpret_cast<float4 *>(fdst + c * (ROWS * 8)) = make_float4(w * f[0], w * f[1], w * f[2], w * f[3]);
+                    *reinterpret_cast<float4 *>(fdst + c * (ROWS * 8) + 4) = make_float4(w * f[4], w * f[5], w * f[6], w * f[7]);
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float *f = reinterpret_cast<const float *>(u) + c * 8;
+                    *reinterpret_cast<float4 *>(fdst + (4 + c) * (ROWS * 8)) = make_float4(w * f[0], w * f[1], w * f[2], w * f[3]);
+                    *reinterpret_cast<float4 *>(fdst + (4 + c) * (ROWS * 8) + 4) = make_float4(w * f[4], w * f[5], w * f[6], w * f[7]);
+                }
+            }
+            fence_before_sync();
+            ctx_barrier(eg);
+            QPROBE(eg, 10);
+            {
+                const int nitems = G * 7;                                          // (chunk of 8 features, group)
+                for (int it = row; it < nitems; it += 128) {
+                    const int c = it / G, gl = it - c * G;
+                    const long long gg = (long long)tile * G + gl;
+                    if (gg >= NG) continue;
+                    const float *src = reinterpret_cast<const float *>(R1) + c * (ROWS * 8) + gl * H * 8;
+                    float4 a0 = *reinterpret_cast<const float4 *>(src), a1 = *reinterpret_cast<const float4 *>(src + 4);
+                    for (int h = 1; h < H; ++h) {
+                        const float4 b0 = *reinterpret_cast<const float4 *>(src + h * 8);
+                        const float4 b1 = *reinterpret_cast<const float4 *>(src + h * 8 + 4);
+                        a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w;
+                        a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
+                    }
+                    uint8_t *jt = J + (size_t)(gg >> 7) * J_TILE_BYTES;
+                    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, (uint32_t)(gg & 127), c)) =
+                        make_uint4(h2(a0.x, a0.y), h2(a0.z, a0.w), h2(a1.x, a1.y), h2(a1.z, a1.w));
+                }
+            }
+            QPROBE(eg, 11);
+        }
+#undef PAIR_SIGNAL
+#undef PAIR_SIGNAL_TO
+#undef PAIR_WAIT
+    }
+    fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 0) tmem_dealloc_2(tmem, 512);
+#undef QPROBE
+}
+
+// =====================================================================================================
+// self-test of the CTA-pair building block: D[256 x N] = A[256 x K] * B[N x K]^T, including the remote
+// "operand ready" arrival and the multicast completion used by tc_rows_pair_kernel
+// =====================================================================================================
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(160, 1)
+umma_pair_selftest_kernel(const uint8_t *__restrict__ a_img /*2 x [128 x K]*/, const uint8_t *__restrict__ b_img /*2 x [N/2 x K]*/,
+                          float *__restrict__ d, int N, int K, int reps, long long *__restrict__ cycles)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t a_bytes = bytes_of(ROWS, K), b_bytes = bytes_of(N / 2, K);
+    uint8_t *sa = smem, *sb = smem + a_bytes;
+    uint8_t *misc = smem + ((a_bytes + b_bytes + 15) & ~15u);
+    const uint32_t req = smem_u32(misc), done = smem_u32(misc + 8);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(misc + 16);
+    copy_image_to_smem(sa, a_img + (size_t)rank * a_bytes, a_bytes);
+    copy_image_to_smem(sb, b_img + (size_t)rank * b_bytes, b_bytes);
+    if (tid == 0) { mbar_init(req, 8); mbar_init(done, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc_2(smem_u32(tmem_slot), 512);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    long long t0 = clock64();
+    if (warp == 4) {
+        if (rank == 0 && lane == 0) {
+            uint32_t ph = 0;
+            for (int rep = 0; rep < reps; ++rep) {
+                mbar_wait_cluster(req, ph); ph ^= 1;
+                fence_after_sync();
+                mma_layer_2(tmem, smem_u32(sa), ROWS, smem_u32(sb), K, N, false);
+                commit_2(done, 3);
+            }
+        }
+    } else {
+        const uint32_t req_leader = mapa(req, 0);
+        const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+        uint32_t ph = 0;
+        for (int rep = 0; rep < reps; ++rep) {
+            fence_async_smem();
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(req_leader);
+            mbar_wait_guarded(done, ph); ph ^= 1;
+            fence_after_sync();
+        }
+        if (tid == 0 && rank == 0 && cycles) *cycles = clock64() - t0;
+        for (int c0 = 0; c0 < N; c0 += 16) {
+            uint32_t v[16];
+            ld16(tlane + c0, v);
+            wait_ld();
+            for (int k = 0; k < 16; ++k) d[((size_t)rank * ROWS + tid) * N + c0 + k] = __uint_as_float(v[k]);
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 0) tmem_dealloc_2(tmem, 512);
+}

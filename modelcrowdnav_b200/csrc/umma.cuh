@@ -172,6 +172,95 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
 }
 
+// ---- CTA pair (cta_group::2): one UMMA spans the two SMs of a 2-CTA cluster -----------------------------
+// M = 256: CTA r of the pair owns rows [128 r, 128 r + 128) -- its A tile in its own shared memory, its
+// accumulator in its own TMEM -- and supplies rows [r N/2, (r + 1) N/2) of the K-major B operand (N split in
+// halves), so each SM keeps only HALF of every weight matrix resident.  The shared-memory descriptors are CTA-local
+// offsets that both CTAs interpret in their own shared memory.  Only the rank-0 CTA issues; completion is
+// multicast to the same mbarrier offset in both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t mbar_saddr, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, P1;\n\t}\n" : "=r"(ok) : "r"(mbar_saddr), "r"(parity) : "memory");
+    return ok;
+}
+// non-blocking poll (try_wait may suspend the thread for a while; the issuer polls two contexts)
+__device__ __forceinline__ uint32_t mbar_test_wait_cluster(uint32_t mbar_saddr, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, P1;\n\t}\n" : "=r"(ok) : "r"(mbar_saddr), "r"(parity) : "memory");
+    return ok;
+}
+// guarded (traps instead of hanging) cluster-scope acquire wait
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t mbar_saddr, uint32_t parity)
+{
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(mbar_saddr, parity))
+        if (clock64() - t0 > 4000000000LL) __trap();
+}
+__host__ __device__ __forceinline__ uint32_t make_idesc_f16_m256(int N)
+{
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16_2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D[256 x N] (+)= A[256 x K] * B[N x K]^T over the CTA pair: a_base = this CTA's 128-row A tile (a_rows = 128),
+// b_base = this CTA's N/2-row half of B.  N a multiple of 16.
+__device__ __forceinline__ void mma_layer_2(uint32_t tmem_d, uint32_t a_base, uint32_t a_rows, uint32_t b_base, int K, int N,
+                                            bool accumulate_first)
+{
+    const uint32_t idesc = make_idesc_f16_m256(N);
+    const uint32_t a_lbo = a_rows * 16, b_lbo = (uint32_t)(N / 2) * 16;
+    for (int s = 0; s < K / 16; ++s) {
+        const uint64_t ad = make_desc(a_base + (uint32_t)s * 2 * a_lbo, a_lbo, 128);
+        const uint64_t bd = make_desc(b_base + (uint32_t)s * 2 * b_lbo, b_lbo, 128);
+        mma_f16_2(tmem_d, ad, bd, idesc, (s > 0 || accumulate_first) ? 1u : 0u);
+    }
+}
+__device__ __forceinline__ void commit_2(uint32_t mbar_saddr, uint16_t cta_mask)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(mbar_saddr), "h"(cta_mask) : "memory");
+}
+// executed by one warp of EACH CTA of the pair
+__device__ __forceinline__ void tmem_alloc_2(uint32_t dst_saddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(dst_saddr), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+
 // 32 lanes x 32 columns of fp32: thread i of the warp receives columns [col, col+32) of TMEM lane (base lane + i)
 __device__ __forceinline__ void ld32(uint32_t taddr, uint32_t (&r)[32])
 {

@@ -354,3 +354,19 @@ def test_umma_selftest(mcn, N, K, bmn):
                                          d.ctypes.data_as(C.c_void_p), 0))
     ref = a.astype(np.float64) @ b.astype(np.float64).T
     assert np.max(np.abs(d - ref)) < 1e-4 * K
+
+
+@pytest.mark.parametrize("N,K", [(32, 16), (64, 112), (112, 112), (160, 32), (112, 160), (224, 112), (256, 64)])
+def test_umma_pair_selftest(mcn, N, K):
+    """cta_group::2 building block: M = 256 over a 2-CTA cluster, B split in N halves, remote operand-ready
+    arrivals and multicast completion, vs fp32 matmul."""
+    import ctypes as C
+    rs = np.random.RandomState(N * 1000 + K + 7)
+    a = rs.uniform(-1, 1, (256, K)).astype(np.float16).astype(np.float32)
+    b = rs.uniform(-1, 1, (N, K)).astype(np.float16).astype(np.float32)
+    d = np.zeros((256, N), np.float32)
+    lib = mcn._capi.load()
+    mcn._capi.check(lib.cn_selftest_umma_pair(N, K, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
+                                              d.ctypes.data_as(C.c_void_p), 3, None, 0))
+    ref = a.astype(np.float64) @ b.astype(np.float64).T
+    assert np.max(np.abs(d - ref)) < 1e-4 * K
