@@ -77,6 +77,7 @@ constexpr uint32_t J_TILE_BYTES = bytes_of(ROWS, K_J);
 
 constexpr int kTmemCols = 256;
 
+struct TailW;
 struct TcState {
     uint8_t *img_a, *img_b;   // device weight images
     uint8_t *img_pair;        // two half images of the row network for tc_rows_pair_kernel (rank 0 | rank 1)
@@ -86,6 +87,7 @@ struct TcState {
     size_t cap_groups;
     int num_sms;
     int variant;              // 0 = one tile in flight per SM (tc_rows_kernel), 2 = CTA pairs, two tiles in flight per SM
+    float tail_a[104];        // attention.4 weight[100] + bias (kernel parameter of tc_rows_pair_kernel)
 };
 
 __device__ __forceinline__ void copy_image_to_smem(uint8_t *dst, const uint8_t *__restrict__ src, uint32_t bytes)
@@ -921,7 +923,9 @@ int cn_tc_init(cn_policy *p)
     }
     CN_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A_SMEM));
     CN_CUDA_CHECK(cudaFuncSetAttribute(tc_mlp3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B_SMEM));
-    CN_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
+    CN_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
+    CN_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_pair_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
+    CN_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_pair_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
     if (cudaMalloc((void **)&t->img_pair, 2 * IMG_H_BYTES) != cudaSuccess) {
         cn_set_error("cudaMalloc failed for the tensor-core weight images");
         return CN_ENOMEM;
@@ -973,6 +977,7 @@ int cn_tc_load_weights(cn_policy *p, const float *flat, cudaStream_t s)
     for (int k = 0; k < 100; ++k) tail[k] = L[6].w[k];
     tail[100] = L[6].b[0];
     memcpy(&a[OFF_TAILA], tail, TAIL_BYTES);
+    memcpy(t->tail_a, tail, sizeof(t->tail_a));
     // mlp3.0 on J = [weighted(50) pad6 | self_hi(6) 1 1 | self_lo(6) 0 0 | pad8]; joint = [self(6), weighted(50)]
     fill_layer(b, OFF_M1, N_H1, L[7], 6, 50, 0, -1, -1);
     fill_layer(b, OFF_M1, N_H1, L[7], 0, 6, 56, 62, 150);
@@ -1034,9 +1039,12 @@ int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cu
         const int slots_needed = (ntiles_a + 3) / 4;
         if (nclusters > slots_needed) nclusters = slots_needed;
         const int rounds = (ntiles_a + 4 * nclusters - 1) / (4 * nclusters);
-        tc_rows_pair_kernel<<<2 * nclusters, kThreadsPair, Q_SMEM, s>>>(env->p, env->state, env->time, env->human_v, p->action_dev,
-                                                                       A, query_env, t->img_pair, t->J, t->rew, (int)NG, G, rounds,
-                                                                       t->dbg);
+        TailW tw;
+        memcpy(tw.w, t->tail_a, sizeof(tw.w));
+        auto kern = (ed.H == 5 && G == ROWS / 5) ? tc_rows_pair_kernel<5>
+                    : ((ed.H == 10 && G == ROWS / 10) ? tc_rows_pair_kernel<10> : tc_rows_pair_kernel<0>);
+        kern<<<2 * nclusters, kThreadsPair, Q_SMEM, s>>>(env->p, env->state, env->time, env->human_v, p->action_dev, A, query_env,
+                                                        t->img_pair, t->J, t->rew, (int)NG, G, rounds, tw, t->dbg);
     } else {
         tc_rows_kernel<<<grid_a, kThreadsRows, A_SMEM, s>>>(env->p, env->state, env->time, env->human_v, p->action_dev, A,
                                                             query_env, t->img_a, t->J, t->rew, (int)NG, G, ntiles_a, t->dbg);
@@ -1141,11 +1149,11 @@ extern "C" int cn_debug_tc_timing(cn_policy *p, long long *out16)
     TcState *t = (TcState *)p->tc;
     CN_CUDA_CHECK(cudaSetDevice(p->device));
     if (!t->dbg) {
-        CN_CUDA_CHECK(cudaMalloc((void **)&t->dbg, 96 * sizeof(long long)));
-        CN_CUDA_CHECK(cudaMemset(t->dbg, 0, 96 * sizeof(long long)));
+        CN_CUDA_CHECK(cudaMalloc((void **)&t->dbg, 256 * sizeof(long long)));
+        CN_CUDA_CHECK(cudaMemset(t->dbg, 0, 256 * sizeof(long long)));
     }
     CN_CUDA_CHECK(cudaDeviceSynchronize());
-    CN_CUDA_CHECK(cudaMemcpy(out16, t->dbg, 96 * sizeof(long long), cudaMemcpyDeviceToHost));
+    CN_CUDA_CHECK(cudaMemcpy(out16, t->dbg, 256 * sizeof(long long), cudaMemcpyDeviceToHost));
     return CN_OK;
 }
 

@@ -5,10 +5,11 @@
 // of only ONE 128-row tile, so the tensor pipe idles during every epilogue (tc_rows_kernel: 21 % tensor-active).
 // A cta_group::2 UMMA splits the B operand (the weights) in halves between the two SMs of a cluster, so each SM
 // keeps 78.5 KB of weights and has room for TWO tile contexts (2 x 68 KB of activations, 2 x 224 TMEM columns).
-// Per SM: epilogue group 0 (warps 0-3) owns context 0, group 1 (warps 4-7) owns context 1, warp 8 of the
-// rank-0 CTA issues every UMMA of the pair (M = 256 = tile of CTA 0 + tile of CTA 1 for the same context).
+// Per SM: 16 epilogue warps = 2 contexts x 2 column halves x 4 TMEM lane quarters (the epilogues are latency
+// bound per warp, so every context gets 8 warps), and warp 16 of the rank-0 CTA issues every UMMA of the pair
+// (M = 256 = tile of CTA 0 + tile of CTA 1 for the same context).
 // Hand-over is pure dataflow through mbarriers, no CTA-wide barrier in the tile loop:
-//   req[c]  (rank-0 CTA, 8 arrivals = 4 warps x 2 CTAs)  "operand of context c's next stage is in shared memory"
+//   req[c]  (rank-0 CTA, 16 arrivals = 8 warps x 2 CTAs)  "operand of context c's next stage is in shared memory"
 //   reqm[c] (same, for stage 3 only: stages 2 and 3 are requested without a completion wait in between, and
 //            the two CTAs are not in lock step, so a shared barrier could see stage-3 arrivals in stage 2's phase)
 //   done[c] (both CTAs, multicast tcgen05.commit)          "accumulator of context c's stage is complete"
@@ -27,7 +28,7 @@
 // Reference: crowd_nav/policy/sarl.py:28-65 (value network), cadrl.py:104-129,217-252 (propagate, rotate),
 // multi_human_rl.py:65-88 / crowd_sim.py:344-403 (lookahead reward).
 
-constexpr int kThreadsPair = 288;
+constexpr int kThreadsPair = 544;        // 16 epilogue warps (2 contexts x 2 column halves x 4 lane quarters) + issuer warp
 constexpr int N_S2 = 2 * N_M1;             // stage 2: [mlp2.0 (rank-0 half) | attention.0 on mlp1_out (rank-1 half)]
 constexpr int PAIR_CTX_COLS = 224;         // TMEM columns per tile context
 
@@ -47,8 +48,8 @@ constexpr uint32_t Q_R2_BYTES = bytes_of(ROWS, N_M1);               // 28 KB: ml
 constexpr uint32_t Q_X_OFF = bytes_of(ROWS, N_M1);                  // next tile's X inside R1 (behind the 112-column tiles)
 constexpr uint32_t Q_CTX_BYTES = Q_R1_BYTES + Q_R2_BYTES;
 constexpr uint32_t Q_CTX0 = (IMG_H_BYTES + 127) & ~127u;
-constexpr uint32_t Q_MISC = Q_CTX0 + 2 * Q_CTX_BYTES;               // S[2][128] f32 | D[2][128] f64 | 6 mbarriers | tmem slot
-constexpr uint32_t Q_SMEM = Q_MISC + 1024 + 2048 + 48 + 16;
+constexpr uint32_t Q_MISC = Q_CTX0 + 2 * Q_CTX_BYTES;               // S[2][2][128] f32 | D[2][128] f64 | 6 mbarriers | tmem slot
+constexpr uint32_t Q_SMEM = Q_MISC + 2048 + 2048 + 48 + 16;
 static_assert(Q_X_OFF + bytes_of(ROWS, K_X) <= Q_R1_BYTES, "next-tile X must fit behind the 112-column tiles");
 static_assert(ROWS * 56 * 4 <= Q_X_OFF, "fp32 weighted features must not reach the next tile's X");
 static_assert(Q_SMEM <= 232448, "tc_rows_pair_kernel exceeds 227 KB of shared memory");
@@ -100,7 +101,32 @@ __device__ __forceinline__ double pp_clearance(const RowInPP &in, double dt, int
     return norm2d(npx - nhx, npy - nhy) - in.rr - in.hr;
 }
 
-__device__ __forceinline__ void pp_features(const RowInPP &in, double dt, uint4 &c0, uint4 &c1, uint4 &c2, uint4 &c3)
+// CADRL.rotate with the rotation taken from the normalised goal direction instead of atan2 -> sincos
+// (cos(atan2(dy, dx)) = dx / |d|): same quantity to ~1e-7, a fraction of the instructions.  The FP32 twin keeps
+// torch's atan2/cos/sin order (env_math.cuh); this path is fp16 downstream anyway.
+__device__ __forceinline__ void rotate_dir(const float *s, float *o)
+{
+    const float dx = s[5] - s[0], dy = s[6] - s[1];
+    const float d = sqrtf(dx * dx + dy * dy);
+    float c = 1.0f, sn = 0.0f;
+    if (d > 0.0f) { const float inv = 1.0f / d; c = dx * inv; sn = dy * inv; }
+    o[0] = d;
+    o[1] = s[7];
+    o[2] = 0.0f;
+    o[3] = s[4];
+    o[4] = s[2] * c + s[3] * sn;
+    o[5] = s[3] * c - s[2] * sn;
+    o[6] = (s[9] - s[0]) * c + (s[10] - s[1]) * sn;
+    o[7] = (s[10] - s[1]) * c - (s[9] - s[0]) * sn;
+    o[8] = s[11] * c + s[12] * sn;
+    o[9] = s[12] * c - s[11] * sn;
+    o[10] = s[13];
+    const float ax = s[0] - s[9], ay = s[1] - s[10];
+    o[11] = sqrtf(ax * ax + ay * ay);
+    o[12] = s[4] + s[13];
+}
+
+__device__ __forceinline__ void pair_features(const RowInPP &in, double dt, uint4 &c0, uint4 &c1, uint4 &c2, uint4 &c3)
 {
     c0 = make_uint4(0, 0, 0, 0); c1 = c0; c2 = c0; c3 = c0;
     if (!in.valid) return;
@@ -110,7 +136,7 @@ __device__ __forceinline__ void pp_features(const RowInPP &in, double dt, uint4 
     s[5] = (float)in.rgx; s[6] = (float)in.rgy; s[7] = (float)in.rvp; s[8] = 0.0f;
     s[9] = (float)(in.hpx + in.hvx * dt); s[10] = (float)(in.hpy + in.hvy * dt);
     s[11] = (float)in.hvx; s[12] = (float)in.hvy; s[13] = (float)in.hr;
-    cn_rotate(s, o);
+    rotate_dir(s, o);
     float hi[13], lo[13];
 #pragma unroll
     for (int k = 0; k < 13; ++k) split_hl(o[k], hi[k], lo[k]);
@@ -120,11 +146,10 @@ __device__ __forceinline__ void pp_features(const RowInPP &in, double dt, uint4 
     c3 = make_uint4(h2(lo[8], lo[9]), h2(lo[10], lo[11]), h2(lo[12], 0.0f), 0u);
 }
 
-// thread with h == 0: fold the group's clearances through the reward ladder, store the reward and the self-state
-// chunks 7..9 of the joint state (c0 = hi[0..7], c2 = lo[0..7]: the self state is columns 0..5 of the rotated row)
-__device__ __forceinline__ void pp_group_finish(const EnvParams &p, const RowInPP &in, const double *__restrict__ D, int H,
-                                                int query_env, long long g, const uint4 &c0, const uint4 &c2,
-                                                uint8_t *__restrict__ J, double *__restrict__ rew)
+// lookahead reward of one (env, action) group from the H clearances in D (see group_work for the equivalence
+// with the reference's break-on-first-collision loops)
+__device__ __forceinline__ double pair_reward(const EnvParams &p, const RowInPP &in, const double *__restrict__ D, int H,
+                                              int query_env)
 {
     const double dt = p.time_step;
     double dmin = INFINITY;
@@ -136,82 +161,95 @@ __device__ __forceinline__ void pp_group_finish(const EnvParams &p, const RowInP
     }
     const double npx = in.rpx + in.ax * dt, npy = in.rpy + in.ay * dt;
     const bool reaching_goal = norm2d(npx - in.rgx, npy - in.rgy) < in.rr;
-    double reward;
     if (query_env) {                                                                 // crowd_sim.py:382-403
-        if (in.t >= p.time_limit - 1) reward = 0;
-        else if (collision) reward = p.collision_penalty;
-        else if (reaching_goal) reward = p.success_reward;
-        else if (dmin < p.discomfort_dist) reward = (dmin - p.discomfort_dist) * p.discomfort_penalty_factor * dt;
-        else reward = 0;
-    } else {                                                                         // multi_human_rl.py:77-86
-        if (collision) reward = -0.25;
-        else if (reaching_goal) reward = 1;
-        else if (dmin < 0.2) reward = (dmin - 0.2) * 0.5 * dt;
-        else reward = 0;
+        if (in.t >= p.time_limit - 1) return 0;
+        if (collision) return p.collision_penalty;
+        if (reaching_goal) return p.success_reward;
+        if (dmin < p.discomfort_dist) return (dmin - p.discomfort_dist) * p.discomfort_penalty_factor * dt;
+        return 0;
     }
-    rew[g] = reward;
-    uint8_t *jt = J + (size_t)(g >> 7) * J_TILE_BYTES;
-    const int rb = (int)(g & 127);
-    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 7)) = make_uint4(c0.x, c0.y, c0.z, h2(1.0f, 1.0f));
-    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 8)) = make_uint4(c2.x, c2.y, c2.z, 0u);
-    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 9)) = make_uint4(0, 0, 0, 0);
+    if (collision) return -0.25;                                                     // multi_human_rl.py:77-86
+    if (reaching_goal) return 1;
+    if (dmin < 0.2) return (dmin - 0.2) * 0.5 * dt;
+    return 0;
 }
 
-__device__ __forceinline__ void ctx_barrier(int eg)
-{
-    if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-    else asm volatile("bar.sync 2, 128;" ::: "memory");
-}
+struct TailW { float w[104]; };   // attention.4: weight[100], bias at [100]; passed by value (constant bank operands)
 
-// Everything the NEXT tile needs before its stage 0: X operand -> shared memory, clearances -> D, and (after a
-// context barrier) reward + self-state chunks -> HBM.  Called under the stage-2/3 UMMAs of the current tile.
+// Everything the NEXT tile needs before its stage 0, split between the two warps that share a TMEM lane quarter:
+//   hf 0: propagate + rotate -> X operand in shared memory; h == 0 rows also store the self-state chunks of J
+//   hf 1: clearance of (row's human) -> D, then (h == 0 rows, after a barrier among the hf-1 warps) the reward
+template <int HT>
 __device__ __forceinline__ void pair_prepare_tile(const EnvParams &p, const RowInPP &in, int H, int query_env, int G, int tile,
-                                                  int row, int my_gl, int my_h, int eg, uint8_t *__restrict__ xbuf,
+                                                  int row, int my_gl, int my_h, int ctx, int hf, uint8_t *__restrict__ xbuf,
                                                   double *__restrict__ D, uint8_t *__restrict__ J, double *__restrict__ rew)
 {
     const double dt = p.time_step;
-    uint4 c0, c1, c2, c3;
-    D[row] = pp_clearance(in, dt, query_env);
-    pp_features(in, dt, c0, c1, c2, c3);
-    *reinterpret_cast<uint4 *>(xbuf + chunk_off(ROWS, row, 0)) = c0;
-    *reinterpret_cast<uint4 *>(xbuf + chunk_off(ROWS, row, 1)) = c1;
-    *reinterpret_cast<uint4 *>(xbuf + chunk_off(ROWS, row, 2)) = c2;
-    *reinterpret_cast<uint4 *>(xbuf + chunk_off(ROWS, row, 3)) = c3;
-    ctx_barrier(eg);
-    if (in.valid && my_h == 0) pp_group_finish(p, in, D + row, H, query_env, (long long)tile * G + my_gl, c0, c2, J, rew);
+    const long long g = (long long)tile * G + my_gl;
+    if (hf == 0) {
+        uint4 c0, c1, c2, c3;
+        pair_features(in, dt, c0, c1, c2, c3);
+        *reinterpret_cast<uint4 *>(xbuf + chunk_off(ROWS, row, 0)) = c0;
+        *reinterpret_cast<uint4 *>(xbuf + chunk_off(ROWS, row, 1)) = c1;
+        *reinterpret_cast<uint4 *>(xbuf + chunk_off(ROWS, row, 2)) = c2;
+        *reinterpret_cast<uint4 *>(xbuf + chunk_off(ROWS, row, 3)) = c3;
+        if (in.valid && my_h == 0) {
+            // c0 = hi[0..7], c2 = lo[0..7]: the self state is columns 0..5 of the rotated row (sarl.py:36)
+            uint8_t *jt = J + (size_t)(g >> 7) * J_TILE_BYTES;
+            const int rb = (int)(g & 127);
+            *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 7)) = make_uint4(c0.x, c0.y, c0.z, h2(1.0f, 1.0f));
+            *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 8)) = make_uint4(c2.x, c2.y, c2.z, 0u);
+            *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 9)) = make_uint4(0, 0, 0, 0);
+        }
+    } else {
+        D[row] = pp_clearance(in, dt, query_env);
+        if (ctx == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
+        else asm volatile("bar.sync 4, 128;" ::: "memory");
+        if (in.valid && my_h == 0) rew[g] = pair_reward(p, in, D + row, H, query_env);
+    }
 }
 
+__device__ __forceinline__ void ctx_barrier(int ctx)
+{
+    if (ctx == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+    else asm volatile("bar.sync 2, 256;" ::: "memory");
+}
+
+// HT = compile-time human count (5, 10: the benchmark configurations) or 0 = run-time H
+template <int HT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsPair, 1)
 tc_rows_pair_kernel(EnvParams p, const double *__restrict__ st, const double *__restrict__ time,
                     const double *__restrict__ human_v, const double *__restrict__ actions, int A, int query_env,
-                    const uint8_t *__restrict__ wimg, uint8_t *__restrict__ J, double *__restrict__ rew, int NG, int G,
-                    int rounds, long long *__restrict__ dbg)
+                    const uint8_t *__restrict__ wimg, uint8_t *__restrict__ J, double *__restrict__ rew, int NG, int G_rt,
+                    int rounds, const TailW tw, long long *__restrict__ dbg)
 {
-#define QPROBE(slot, i) do { if (dbg && blockIdx.x == 0 && probe_round) dbg[(slot) * 32 + (i)] = clock64(); } while (0)
+#define QPROBE(slot, i) do { if (dbg && blockIdx.x < 2 && probe_round) dbg[(blockIdx.x * 4 + (slot)) * 32 + (i)] = clock64(); } while (0)
     extern __shared__ __align__(128) uint8_t smem[];
     const EnvDims ed = p.d;
-    const int H = ed.H;
+    const int H = HT ? HT : ed.H;
+    const int G = HT ? ROWS / HT : G_rt;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int eg = warp >> 2;                       // 0 / 1 = epilogue group == tile context, 2 = issuer warp
+    const bool is_issuer_warp = warp == 16;
+    const int q = warp & 3, ctx = (warp >> 2) & 1, hf = (warp >> 3) & 1;     // lane quarter, tile context, column half
     const uint32_t rank = cluster_ctarank();
     const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
-    const int row = tid & 127;                      // tile row == TMEM lane of this thread (epilogue groups)
+    const int row = q * 32 + lane;                  // tile row == TMEM lane of this thread
+    const int t256 = hf * 128 + row;                // thread index within the context
     const int my_gl = row / H, my_h = row - my_gl * H;
     const int rows = G * H;
-    uint8_t *R1 = smem + Q_CTX0 + (uint32_t)(eg & 1) * Q_CTX_BYTES, *R2 = R1 + Q_R1_BYTES;
-    float *S = reinterpret_cast<float *>(smem + Q_MISC) + (eg & 1) * 128;
-    double *D = reinterpret_cast<double *>(smem + Q_MISC + 1024) + (eg & 1) * 128;
-    const uint32_t bar0 = smem_u32(smem + Q_MISC + 1024 + 2048);
+    uint8_t *R1 = smem + Q_CTX0 + (uint32_t)ctx * Q_CTX_BYTES, *R2 = R1 + Q_R1_BYTES;
+    float *S0 = reinterpret_cast<float *>(smem + Q_MISC) + ctx * 256, *S1 = S0 + 128;   // partial scores of the column halves
+    double *D = reinterpret_cast<double *>(smem + Q_MISC + 2048) + ctx * 128;
+    const uint32_t bar0 = smem_u32(smem + Q_MISC + 4096);
     const uint32_t req0 = bar0, req1 = bar0 + 8, done0 = bar0 + 16, done1 = bar0 + 24, reqm0 = bar0 + 32, reqm1 = bar0 + 40;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Q_MISC + 1024 + 2048 + 48);
-    const float *tail = reinterpret_cast<const float *>(smem + H_TAIL);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Q_MISC + 4096 + 48);
 
     copy_image_to_smem(smem, wimg + (size_t)rank * IMG_H_BYTES, IMG_H_BYTES);
     for (uint32_t i = tid * 16; i < 2 * Q_CTX_BYTES; i += kThreadsPair * 16)       // padding rows stay finite
         *reinterpret_cast<uint4 *>(smem + Q_CTX0 + i) = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
-        mbar_init(req0, 8); mbar_init(req1, 8); mbar_init(done0, 1); mbar_init(done1, 1);
-        mbar_init(reqm0, 8); mbar_init(reqm1, 8);
+        mbar_init(req0, 16); mbar_init(req1, 16); mbar_init(done0, 1); mbar_init(done1, 1);
+        mbar_init(reqm0, 16); mbar_init(reqm1, 16);
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc_2(smem_u32(tmem_slot), 512);
@@ -222,7 +260,7 @@ tc_rows_pair_kernel(EnvParams p, const double *__restrict__ st, const double *__
     fence_after_sync();
     const uint32_t tmem = *tmem_slot;
 
-    if (eg == 2) {
+    if (is_issuer_warp) {
         // ================= issuer warp (rank-0 CTA only) =================
         if (rank == 0 && lane == 0) {
             const uint32_t sW1 = smem_u32(smem + H_W1), sW2 = smem_u32(smem + H_W2), sW3A = smem_u32(smem + H_W3A);
@@ -240,6 +278,8 @@ tc_rows_pair_kernel(EnvParams p, const double *__restrict__ st, const double *__
                     uint32_t &ph = (s == 3) ? (c ? phm1 : phm0) : (c ? ph1 : ph0);
                     if (!mbar_test_wait_cluster((s == 3) ? (c ? reqm1 : reqm0) : (c ? req1 : req0), ph)) continue;
                     ph ^= 1;
+                    const bool probe_round = stage / 5 == 3;
+                    QPROBE(2 + c, 2 * s);
                     fence_after_sync();
                     const uint32_t tm = tmem + (uint32_t)c * PAIR_CTX_COLS;
                     const uint32_t sR1 = smem_u32(smem + Q_CTX0 + (uint32_t)c * Q_CTX_BYTES), sR2 = sR1 + Q_R1_BYTES;
@@ -260,6 +300,7 @@ tc_rows_pair_kernel(EnvParams p, const double *__restrict__ st, const double *__
                         mma_layer_2(tm + N_F, sR2, ROWS, sWA2, N_M1, N_M1, false);
                         commit_2(done, 3);
                     }
+                    QPROBE(2 + c, 2 * s + 1);
                     ++stage;
                     t_last = clock64();
                 }
@@ -267,15 +308,25 @@ tc_rows_pair_kernel(EnvParams p, const double *__restrict__ st, const double *__
             }
         }
     } else {
-        // ================= epilogue group `eg` (both CTAs) =================
-        const uint32_t done = eg ? done1 : done0;
-        const uint32_t req_leader = mapa(eg ? req1 : req0, 0), reqm_leader = mapa(eg ? reqm1 : reqm0, 0);
-        const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)eg * PAIR_CTX_COLS;
+        // ================= epilogue warps: context `ctx`, column half `hf` (both CTAs) =================
+        const uint32_t done = ctx ? done1 : done0;
+        const uint32_t req_leader = mapa(ctx ? req1 : req0, 0), reqm_leader = mapa(ctx ? reqm1 : reqm0, 0);
+        const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)ctx * PAIR_CTX_COLS;
         uint8_t *xbuf = R1 + Q_X_OFF;
         uint32_t ph = 0;
         const float invH = 1.0f / (float)H;
         const int tile_stride = 4 * nclusters;
-        int tile = (cluster_id * 2 + (int)rank) * 2 + eg;
+        int tile = (cluster_id * 2 + (int)rank) * 2 + ctx;
+        // loop-invariant work items of the two shared-memory group reductions (consecutive threads -> consecutive groups)
+        int mean_off[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int it = t256 + i * 256;
+            const int c = it / G, gl = it - c * G;
+            mean_off[i] = (it < G * (N_M1 / 8)) ? (int)chunk_off(ROWS, gl * H, c) : -1;
+        }
+        const int sum_c = t256 / G, sum_gl = t256 - sum_c * G;
+        const bool sum_item = t256 < G * 7;
         // operand hand-over: generic-proxy writes -> async proxy, TMEM reads ordered, one arrival per warp
 #define PAIR_SIGNAL_TO(bar) do { fence_async_smem(); fence_before_sync(); __syncwarp(); if (lane == 0) mbar_arrive_cluster(bar); } while (0)
 #define PAIR_SIGNAL() PAIR_SIGNAL_TO(req_leader)
@@ -283,138 +334,185 @@ tc_rows_pair_kernel(EnvParams p, const double *__restrict__ st, const double *__
         {
             RowInPP in;
             pp_load_inputs(in, ed, st, time, human_v, actions, A, query_env, NG, G, tile, my_gl, my_h);
-            pair_prepare_tile(p, in, H, query_env, G, tile, row, my_gl, my_h, eg, xbuf, D, J, rew);
+            pair_prepare_tile<HT>(p, in, H, query_env, G, tile, row, my_gl, my_h, ctx, hf, xbuf, D, J, rew);
         }
         for (int rnd = 0; rnd < rounds; ++rnd, tile += tile_stride) {
             const bool has_next = rnd + 1 < rounds;
-            const bool probe_round = (row == 0) && rnd == 3;
+            const bool probe_round = (t256 == 0) && rnd == 3;
             const long long g = (long long)tile * G + my_gl;
             const bool row_valid = (row < rows) && (g < NG);
-            QPROBE(eg, 0);
+            QPROBE(ctx, 0);
             // ---- stage 0 request: X of this tile is in R1's tail (written one tile ago / by the prologue) ----
             PAIR_SIGNAL();
             // ---- E0: H1 = relu(acc[0,160)) -> R1 ----
-            PAIR_WAIT(); QPROBE(eg, 1);
-            epilogue_to_smem<true>(tl, 0, N_H1, R1, row, 0);
-            PAIR_SIGNAL(); QPROBE(eg, 2);
+            PAIR_WAIT(); QPROBE(ctx, 1);
+            epilogue_to_smem<true>(tl, hf * 80, 80, R1, row, hf * 10);
+            PAIR_SIGNAL(); QPROBE(ctx, 2);
             // ---- E1: mlp1_out = relu(acc[0,112)) -> R2 ----
-            PAIR_WAIT(); QPROBE(eg, 3);
-            epilogue_to_smem<true>(tl, 0, N_M1, R2, row, 0);
-            PAIR_SIGNAL(); QPROBE(eg, 4);                                          // stage 2 may start
+            PAIR_WAIT(); QPROBE(ctx, 3);
+            if (hf == 0) epilogue_to_smem<true>(tl, 0, 64, R2, row, 0);
+            else epilogue_to_smem<true>(tl, 64, 48, R2, row, 8);
+            PAIR_SIGNAL(); QPROBE(ctx, 4);                                         // stage 2 may start
             RowInPP in;
             if (has_next) pp_load_inputs(in, ed, st, time, human_v, actions, A, query_env, NG, G, tile + tile_stride, my_gl, my_h);
+            QPROBE(ctx, 12);
             // ---- group mean of mlp1_out over the humans of a group (sarl.py:42), replicated on the group's rows -> R1 ----
-            ctx_barrier(eg);
-            {
-                const int nitems = G * (N_M1 / 8);
-                for (int it = row; it < nitems; it += 128) {                       // consecutive threads -> consecutive groups
-                    const int c = it / G, gl = it - c * G;
-                    const uint8_t *src = R2 + chunk_off(ROWS, gl * H, c);
-                    __half2 acc[4];
-                    {
-                        const uint4 v = *reinterpret_cast<const uint4 *>(src);
-                        const __half2 *hv = reinterpret_cast<const __half2 *>(&v);
-                        acc[0] = hv[0]; acc[1] = hv[1]; acc[2] = hv[2]; acc[3] = hv[3];
-                    }
-                    for (int h = 1; h < H; ++h) {
-                        const uint4 v = *reinterpret_cast<const uint4 *>(src + h * 16);
-                        const __half2 *hv = reinterpret_cast<const __half2 *>(&v);
+            ctx_barrier(ctx);
+            QPROBE(ctx, 13);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (mean_off[i] < 0) continue;
+                const uint8_t *src = R2 + mean_off[i];
+                uint4 v[HT ? HT : 1];
+                __half2 acc[4];
+                if (HT) {
+#pragma unroll
+                    for (int h = 0; h < HT; ++h) v[h] = *reinterpret_cast<const uint4 *>(src + h * 16);
+                    const __half2 *h0 = reinterpret_cast<const __half2 *>(&v[0]);
+                    acc[0] = h0[0]; acc[1] = h0[1]; acc[2] = h0[2]; acc[3] = h0[3];
+#pragma unroll
+                    for (int h = 1; h < HT; ++h) {
+                        const __half2 *hv = reinterpret_cast<const __half2 *>(&v[h]);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) acc[k] = __hadd2(acc[k], hv[k]);
                     }
-                    uint4 o;
-                    {
-                        const float2 f0 = __half22float2(acc[0]), f1 = __half22float2(acc[1]);
-                        const float2 f2 = __half22float2(acc[2]), f3 = __half22float2(acc[3]);
-                        o.x = h2(f0.x * invH, f0.y * invH); o.y = h2(f1.x * invH, f1.y * invH);
-                        o.z = h2(f2.x * invH, f2.y * invH); o.w = h2(f3.x * invH, f3.y * invH);
+                } else {
+                    v[0] = *reinterpret_cast<const uint4 *>(src);
+                    const __half2 *h0 = reinterpret_cast<const __half2 *>(&v[0]);
+                    acc[0] = h0[0]; acc[1] = h0[1]; acc[2] = h0[2]; acc[3] = h0[3];
+                    for (int h = 1; h < H; ++h) {
+                        const uint4 u = *reinterpret_cast<const uint4 *>(src + h * 16);
+                        const __half2 *hv = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) acc[k] = __hadd2(acc[k], hv[k]);
                     }
-                    uint8_t *dst = R1 + chunk_off(ROWS, gl * H, c);
+                }
+                uint4 o;
+                {
+                    const float2 f0 = __half22float2(acc[0]), f1 = __half22float2(acc[1]);
+                    const float2 f2 = __half22float2(acc[2]), f3 = __half22float2(acc[3]);
+                    o.x = h2(f0.x * invH, f0.y * invH); o.y = h2(f1.x * invH, f1.y * invH);
+                    o.z = h2(f2.x * invH, f2.y * invH); o.w = h2(f3.x * invH, f3.y * invH);
+                }
+                uint8_t *dst = R1 + mean_off[i];
+                if (HT) {
+#pragma unroll
+                    for (int h = 0; h < HT; ++h) *reinterpret_cast<uint4 *>(dst + h * 16) = o;
+                } else {
                     for (int h = 0; h < H; ++h) *reinterpret_cast<uint4 *>(dst + h * 16) = o;
                 }
             }
-            PAIR_SIGNAL_TO(reqm_leader); QPROBE(eg, 5);                            // stage 3 may start
-            // ---- next tile: clearances, rotate + pack -> X, rewards + self state (under stages 2-3) ----
-            if (has_next) pair_prepare_tile(p, in, H, query_env, G, tile + tile_stride, row, my_gl, my_h, eg, xbuf, D, J, rew);
-            QPROBE(eg, 6);
-            // ---- E3: H3 = relu(acc[0,112)) -> R1 ; Ha1 = relu(acc[112,224)) -> R2 ----
-            PAIR_WAIT(); QPROBE(eg, 7);
-            epilogue_to_smem<true>(tl, 0, N_M1, R1, row, 0);
-            epilogue_to_smem<true>(tl, N_M1, N_M1, R2, row, 0);
-            PAIR_SIGNAL(); QPROBE(eg, 8);
-            // ---- E4: attention.4 dot, exp, masked softmax (sarl.py:48-53), weighted feature sum (sarl.py:57-60) ----
-            PAIR_WAIT(); QPROBE(eg, 9);
-            float score = tail[100];
+            QPROBE(ctx, 14);
+            PAIR_SIGNAL_TO(reqm_leader); QPROBE(ctx, 5);                           // stage 3 may start
+            // ---- next tile: rotate + pack -> X, self state (hf 0) | clearances, rewards (hf 1), under stages 2-3 ----
+            if (has_next) pair_prepare_tile<HT>(p, in, H, query_env, G, tile + tile_stride, row, my_gl, my_h, ctx, hf, xbuf, D, J, rew);
+            QPROBE(ctx, 6);
+            // ---- E3: H3 = relu(acc[0,112)) -> R1 (hf 0) ; Ha1 = relu(acc[112,224)) -> R2 (hf 1) ----
+            PAIR_WAIT(); QPROBE(ctx, 7);
+            if (hf == 0) epilogue_to_smem<true>(tl, 0, N_M1, R1, row, 0);
+            else epilogue_to_smem<true>(tl, N_M1, N_M1, R2, row, 0);
+            PAIR_SIGNAL(); QPROBE(ctx, 8);
+            // ---- E4: attention.4 dot (split over the column halves), masked softmax (sarl.py:48-53), w * F ----
+            PAIR_WAIT(); QPROBE(ctx, 9);
             {
-                uint32_t v[32], u[32];
-                ld32(tl + N_F, v);
-                ld32(tl + N_F + 32, u);
-                wait_ld();
+                float part = 0.0f;
+                if (hf == 0) {
+                    uint32_t v[32], u[32];
+                    ld32(tl + N_F, v);
+                    ld32(tl + N_F + 32, u);
+                    wait_ld();
 #pragma unroll
-                for (int k = 0; k < 32; ++k) score = fmaf(fmaxf(__uint_as_float(v[k]), 0.0f), tail[k], score);
+                    for (int k = 0; k < 32; ++k) part = fmaf(fmaxf(__uint_as_float(v[k]), 0.0f), tw.w[k], part);
 #pragma unroll
-                for (int k = 0; k < 32; ++k) score = fmaf(fmaxf(__uint_as_float(u[k]), 0.0f), tail[32 + k], score);
-                uint32_t x[32], y[16];
-                ld32(tl + N_F + 64, x);
-                ld16(tl + N_F + 96, y);
-                wait_ld();
+                    for (int k = 0; k < 32; ++k) part = fmaf(fmaxf(__uint_as_float(u[k]), 0.0f), tw.w[32 + k], part);
+                    S0[row] = part;
+                } else {
+                    uint32_t x[32], y[16];
+                    ld32(tl + N_F + 64, x);
+                    ld16(tl + N_F + 96, y);
+                    wait_ld();
 #pragma unroll
-                for (int k = 0; k < 32; ++k) score = fmaf(fmaxf(__uint_as_float(x[k]), 0.0f), tail[64 + k], score);
+                    for (int k = 0; k < 32; ++k) part = fmaf(fmaxf(__uint_as_float(x[k]), 0.0f), tw.w[64 + k], part);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) score = fmaf(fmaxf(__uint_as_float(y[k]), 0.0f), tail[96 + k], score);
+                    for (int k = 0; k < 4; ++k) part = fmaf(fmaxf(__uint_as_float(y[k]), 0.0f), tw.w[96 + k], part);
+                    S1[row] = part;
+                }
             }
-            const float se = expf(score) * (score != 0.0f ? 1.0f : 0.0f);
-            S[row] = se;
-            ctx_barrier(eg);
+            QPROBE(ctx, 15);
+            ctx_barrier(ctx);
+            QPROBE(ctx, 16);
             float w = 0.0f;
             if (row_valid) {
-                float ssum = 0.0f;
-                for (int h = 0; h < H; ++h) ssum += S[my_gl * H + h];
-                w = se / ssum;
+                float ssum = 0.0f, mine = 0.0f;
+                const int r0 = my_gl * H;
+                if (HT) {
+#pragma unroll
+                    for (int h = 0; h < HT; ++h) {
+                        const float sc = S0[r0 + h] + S1[r0 + h] + tw.w[100];
+                        const float se = __expf(sc) * (sc != 0.0f ? 1.0f : 0.0f);
+                        ssum += se;
+                        if (h == my_h) mine = se;
+                    }
+                } else {
+                    for (int h = 0; h < H; ++h) {
+                        const float sc = S0[r0 + h] + S1[r0 + h] + tw.w[100];
+                        const float se = __expf(sc) * (sc != 0.0f ? 1.0f : 0.0f);
+                        ssum += se;
+                        if (h == my_h) mine = se;
+                    }
+                }
+                w = mine / ssum;
             }
             {
-                // w * F in fp32, chunked [c][row][8 floats] over the (dead) H3 tile
-                uint32_t v[32], u[32];
-                ld32(tl + 0, v);
-                ld32(tl + 32, u);
+                // w * F in fp32, chunked [c][row][8 floats] over the (dead) H3 tile: hf 0 -> features 0..31, hf 1 -> 32..55
+                uint32_t v[32];
+                ld32(tl + hf * 32, v);
                 wait_ld();
-                float *fdst = reinterpret_cast<float *>(R1) + row * 8;
+                float *fdst = reinterpret_cast<float *>(R1) + (hf * 4) * (ROWS * 8) + row * 8;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
+                    if (hf == 1 && c == 3) break;
                     const float *f = reinterpret_cast<const float *>(v) + c * 8;
                     *reinterpret_cast<float4 *>(fdst + c * (ROWS * 8)) = make_float4(w * f[0], w * f[1], w * f[2], w * f[3]);
                     *reinterpret_cast<float4 *>(fdst + c * (ROWS * 8) + 4) = make_float4(w * f[4], w * f[5], w * f[6], w * f[7]);
                 }
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float *f = reinterpret_cast<const float *>(u) + c * 8;
-                    *reinterpret_cast<float4 *>(fdst + (4 + c) * (ROWS * 8)) = make_float4(w * f[0], w * f[1], w * f[2], w * f[3]);
-                    *reinterpret_cast<float4 *>(fdst + (4 + c) * (ROWS * 8) + 4) = make_float4(w * f[4], w * f[5], w * f[6], w * f[7]);
-                }
             }
+            QPROBE(ctx, 17);
             fence_before_sync();
-            ctx_barrier(eg);
-            QPROBE(eg, 10);
-            {
-                const int nitems = G * 7;                                          // (chunk of 8 features, group)
-                for (int it = row; it < nitems; it += 128) {
-                    const int c = it / G, gl = it - c * G;
-                    const long long gg = (long long)tile * G + gl;
-                    if (gg >= NG) continue;
-                    const float *src = reinterpret_cast<const float *>(R1) + c * (ROWS * 8) + gl * H * 8;
+            ctx_barrier(ctx);
+            QPROBE(ctx, 10);
+            // ---- weighted feature of the group (sarl.py:57-60): sum over its humans -> J chunks 0..6 ----
+            if (sum_item) {
+                const long long gg = (long long)tile * G + sum_gl;
+                if (gg < NG) {
+                    const float *src = reinterpret_cast<const float *>(R1) + sum_c * (ROWS * 8) + sum_gl * H * 8;
                     float4 a0 = *reinterpret_cast<const float4 *>(src), a1 = *reinterpret_cast<const float4 *>(src + 4);
-                    for (int h = 1; h < H; ++h) {
-                        const float4 b0 = *reinterpret_cast<const float4 *>(src + h * 8);
-                        const float4 b1 = *reinterpret_cast<const float4 *>(src + h * 8 + 4);
-                        a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w;
-                        a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
+                    if (HT) {
+                        float4 b0[HT ? HT : 1], b1[HT ? HT : 1];
+#pragma unroll
+                        for (int h = 1; h < HT; ++h) {
+                            b0[h] = *reinterpret_cast<const float4 *>(src + h * 8);
+                            b1[h] = *reinterpret_cast<const float4 *>(src + h * 8 + 4);
+                        }
+#pragma unroll
+                        for (int h = 1; h < HT; ++h) {
+                            a0.x += b0[h].x; a0.y += b0[h].y; a0.z += b0[h].z; a0.w += b0[h].w;
+                            a1.x += b1[h].x; a1.y += b1[h].y; a1.z += b1[h].z; a1.w += b1[h].w;
+                        }
+                    } else {
+                        for (int h = 1; h < H; ++h) {
+                            const float4 b0 = *reinterpret_cast<const float4 *>(src + h * 8);
+                            const float4 b1 = *reinterpret_cast<const float4 *>(src + h * 8 + 4);
+                            a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w;
+                            a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
+                        }
                     }
                     uint8_t *jt = J + (size_t)(gg >> 7) * J_TILE_BYTES;
-                    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, (uint32_t)(gg & 127), c)) =
+                    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, (uint32_t)(gg & 127), sum_c)) =
                         make_uint4(h2(a0.x, a0.y), h2(a0.z, a0.w), h2(a1.x, a1.y), h2(a1.z, a1.w));
                 }
             }
-            QPROBE(eg, 11);
+            QPROBE(ctx, 11);
         }
 #undef PAIR_SIGNAL
 #undef PAIR_SIGNAL_TO

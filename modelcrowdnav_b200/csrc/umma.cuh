@@ -195,14 +195,18 @@ __device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank)
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
     return r;
 }
+// Remote arrival with the default .release.cta semantics.  A .release.cluster arrival compiles to
+// MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR (measured ~1500 cycles per hand-over with global loads in flight).  The
+// operands handed over here live in the ARRIVING CTA's own shared memory and are read by its own SM's tensor
+// core; fence.proxy.async before the arrival is what orders them, as in 2-SM GEMM epilogue -> mainloop signalling.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
 {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t mbar_saddr, uint32_t parity)
 {
     uint32_t ok;
-    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
                  "selp.u32 %0, 1, 0, P1;\n\t}\n" : "=r"(ok) : "r"(mbar_saddr), "r"(parity) : "memory");
     return ok;
 }
@@ -210,7 +214,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t mbar_saddr, u
 __device__ __forceinline__ uint32_t mbar_test_wait_cluster(uint32_t mbar_saddr, uint32_t parity)
 {
     uint32_t ok;
-    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
                  "selp.u32 %0, 1, 0, P1;\n\t}\n" : "=r"(ok) : "r"(mbar_saddr), "r"(parity) : "memory");
     return ok;
 }

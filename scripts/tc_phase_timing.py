@@ -20,7 +20,7 @@ def main(E=8192, H=5):
     env = mcn.BatchedCrowdSim(E, H, auto_reset=1)
     pol = mcn.BatchedSARL(precision="f16_tc"); pol.load_weights(w)
     env.reset_device()
-    out = (C.c_longlong * 96)()
+    out = (C.c_longlong * 256)()
     mcn._capi.check(pol.lib.cn_debug_tc_timing(pol.handle, out))      # arm
     for _ in range(3):
         pol.lookahead(env)
