@@ -82,6 +82,8 @@ struct TcState {
     uint8_t *img_a, *img_b;   // device weight images
     uint8_t *img_pair;        // two half images of the row network for tc_rows_pair_kernel (rank 0 | rank 1)
     long long *dbg;           // optional phase timestamps of CTA 0 (cn_debug_tc_timing)
+    uint8_t *X;               // layer-1 operand tiles of the CTA-pair path (tc_features_kernel -> tc_rows_pair_kernel)
+    size_t cap_xtiles;
     uint8_t *J;               // joint-state tiles
     double *rew;              // NG rewards
     size_t cap_groups;
@@ -944,6 +946,7 @@ void cn_tc_destroy(cn_policy *p)
     if (t->img_b) cudaFree(t->img_b);
     if (t->img_pair) cudaFree(t->img_pair);
     if (t->J) cudaFree(t->J);
+    if (t->X) cudaFree(t->X);
     if (t->rew) cudaFree(t->rew);
     if (t->dbg) cudaFree(t->dbg);
     delete t;
@@ -1039,12 +1042,22 @@ int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cu
         const int slots_needed = (ntiles_a + 3) / 4;
         if (nclusters > slots_needed) nclusters = slots_needed;
         const int rounds = (ntiles_a + 4 * nclusters - 1) / (4 * nclusters);
+        const size_t xtiles = (size_t)rounds * 4 * nclusters;
+        if (xtiles > t->cap_xtiles) {
+            if (t->X) cudaFree(t->X);
+            t->X = nullptr; t->cap_xtiles = 0;
+            CN_CUDA_CHECK(cudaMalloc((void **)&t->X, xtiles * X_TILE_BYTES));
+            t->cap_xtiles = xtiles;
+        }
         TailW tw;
         memcpy(tw.w, t->tail_a, sizeof(tw.w));
-        auto kern = (ed.H == 5 && G == ROWS / 5) ? tc_rows_pair_kernel<5>
-                    : ((ed.H == 10 && G == ROWS / 10) ? tc_rows_pair_kernel<10> : tc_rows_pair_kernel<0>);
-        kern<<<2 * nclusters, kThreadsPair, Q_SMEM, s>>>(env->p, env->state, env->time, env->human_v, p->action_dev, A, query_env,
-                                                        t->img_pair, t->J, t->rew, (int)NG, G, rounds, tw, t->dbg);
+        const int ht = (ed.H == 5 && G == ROWS / 5) ? 5 : ((ed.H == 10 && G == ROWS / 10) ? 10 : 0);
+        auto feat = ht == 5 ? tc_features_kernel<5> : (ht == 10 ? tc_features_kernel<10> : tc_features_kernel<0>);
+        auto kern = ht == 5 ? tc_rows_pair_kernel<5> : (ht == 10 ? tc_rows_pair_kernel<10> : tc_rows_pair_kernel<0>);
+        feat<<<(unsigned)xtiles, ROWS, 0, s>>>(env->p, env->state, env->time, env->human_v, p->action_dev, A, query_env, (int)NG, G,
+                                              t->X, t->J, t->rew);
+        CN_LAUNCH_CHECK();
+        kern<<<2 * nclusters, kThreadsPair, Q_SMEM, s>>>(env->p, t->img_pair, t->X, t->J, (int)NG, G, rounds, tw, t->dbg);
     } else {
         tc_rows_kernel<<<grid_a, kThreadsRows, A_SMEM, s>>>(env->p, env->state, env->time, env->human_v, p->action_dev, A,
                                                             query_env, t->img_a, t->J, t->rew, (int)NG, G, ntiles_a, t->dbg);

@@ -28,7 +28,7 @@
 // Reference: crowd_nav/policy/sarl.py:28-65 (value network), cadrl.py:104-129,217-252 (propagate, rotate),
 // multi_human_rl.py:65-88 / crowd_sim.py:344-403 (lookahead reward).
 
-constexpr int kThreadsPair = 544;        // 16 epilogue warps (2 contexts x 2 column halves x 4 lane quarters) + issuer warp
+constexpr int kThreadsPair = 608;        // 16 epilogue warps (2 contexts x 2 column halves x 4 lane quarters) + issuer warp + 2 loader warps
 constexpr int N_S2 = 2 * N_M1;             // stage 2: [mlp2.0 (rank-0 half) | attention.0 on mlp1_out (rank-1 half)]
 constexpr int PAIR_CTX_COLS = 224;         // TMEM columns per tile context
 
@@ -48,8 +48,8 @@ constexpr uint32_t Q_R2_BYTES = bytes_of(ROWS, N_M1);               // 28 KB: ml
 constexpr uint32_t Q_X_OFF = bytes_of(ROWS, N_M1);                  // next tile's X inside R1 (behind the 112-column tiles)
 constexpr uint32_t Q_CTX_BYTES = Q_R1_BYTES + Q_R2_BYTES;
 constexpr uint32_t Q_CTX0 = (IMG_H_BYTES + 127) & ~127u;
-constexpr uint32_t Q_MISC = Q_CTX0 + 2 * Q_CTX_BYTES;               // S[2][2][128] f32 | D[2][128] f64 | 6 mbarriers | tmem slot
-constexpr uint32_t Q_SMEM = Q_MISC + 2048 + 2048 + 48 + 16;
+constexpr uint32_t Q_MISC = Q_CTX0 + 2 * Q_CTX_BYTES;               // S[2][2][128] f32 | D[2][128] f64 | 10 mbarriers | tmem slot
+constexpr uint32_t Q_SMEM = Q_MISC + 2048 + 2048 + 96 + 16;
 static_assert(Q_X_OFF + bytes_of(ROWS, K_X) <= Q_R1_BYTES, "next-tile X must fit behind the 112-column tiles");
 static_assert(ROWS * 56 * 4 <= Q_X_OFF, "fp32 weighted features must not reach the next tile's X");
 static_assert(Q_SMEM <= 232448, "tc_rows_pair_kernel exceeds 227 KB of shared memory");
@@ -65,10 +65,10 @@ __device__ __forceinline__ void pp_load_inputs(RowInPP &in, const EnvDims &ed, c
                                                int tile, int gl, int h)
 {
     const int H = ed.H;
-    const long long g = (long long)tile * G + gl;
+    const int g = tile * G + gl;          // the host keeps (total tiles + 1) * G below 2^31
     in.valid = (gl < G && g < NG) ? 1 : 0;
     if (!in.valid) return;
-    const int e = (int)(g / A), a = (int)(g - (long long)e * A);
+    const int e = g / A, a = g - e * A;
     in.rpx = st[st_idx(ed, F_PX, 0, e)]; in.rpy = st[st_idx(ed, F_PY, 0, e)];
     in.rgx = st[st_idx(ed, F_GX, 0, e)]; in.rgy = st[st_idx(ed, F_GY, 0, e)];
     in.rr = st[st_idx(ed, F_R, 0, e)];   in.rvp = st[st_idx(ed, F_VPREF, 0, e)];
@@ -174,39 +174,51 @@ __device__ __forceinline__ double pair_reward(const EnvParams &p, const RowInPP 
     return 0;
 }
 
+
 struct TailW { float w[104]; };   // attention.4: weight[100], bias at [100]; passed by value (constant bank operands)
 
-// Everything the NEXT tile needs before its stage 0, split between the two warps that share a TMEM lane quarter:
-//   hf 0: propagate + rotate -> X operand in shared memory; h == 0 rows also store the self-state chunks of J
-//   hf 1: clearance of (row's human) -> D, then (h == 0 rows, after a barrier among the hf-1 warps) the reward
+constexpr uint32_t X_TILE_BYTES = bytes_of(ROWS, K_X);   // 8 KB: one tile of the layer-1 operand, already in UMMA order
+
+// Feature kernel: everything a row tile needs before its stage 0, for ALL tiles of the lookahead at once (one block
+// per tile, one thread per row): propagate + rotate -> X operand tile in HBM (consumed through TMA bulk copies by
+// tc_rows_pair_kernel), self-state chunks of J, lookahead rewards.  3.3 M rows of independent work: the massively
+// parallel form this needs -- inside the row kernel it sat on a few latency-bound warps (measured 4.6-7 k cycles
+// per tile against a 6-8 k cycle tile budget).  Costs one 64 B / row round trip through L2 / HBM.
 template <int HT>
-__device__ __forceinline__ void pair_prepare_tile(const EnvParams &p, const RowInPP &in, int H, int query_env, int G, int tile,
-                                                  int row, int my_gl, int my_h, int ctx, int hf, uint8_t *__restrict__ xbuf,
-                                                  double *__restrict__ D, uint8_t *__restrict__ J, double *__restrict__ rew)
+__global__ void __launch_bounds__(ROWS)
+tc_features_kernel(EnvParams p, const double *__restrict__ st, const double *__restrict__ time,
+                   const double *__restrict__ human_v, const double *__restrict__ actions, int A, int query_env, int NG,
+                   int G_rt, uint8_t *__restrict__ X, uint8_t *__restrict__ J, double *__restrict__ rew)
 {
+    __shared__ double D[ROWS];
+    const EnvDims ed = p.d;
+    const int H = HT ? HT : ed.H;
+    const int G = HT ? ROWS / HT : G_rt;
+    const int tile = blockIdx.x, r = threadIdx.x;
+    const int gl = r / H, h = r - gl * H;
     const double dt = p.time_step;
-    const long long g = (long long)tile * G + my_gl;
-    if (hf == 0) {
-        uint4 c0, c1, c2, c3;
-        pair_features(in, dt, c0, c1, c2, c3);
-        *reinterpret_cast<uint4 *>(xbuf + chunk_off(ROWS, row, 0)) = c0;
-        *reinterpret_cast<uint4 *>(xbuf + chunk_off(ROWS, row, 1)) = c1;
-        *reinterpret_cast<uint4 *>(xbuf + chunk_off(ROWS, row, 2)) = c2;
-        *reinterpret_cast<uint4 *>(xbuf + chunk_off(ROWS, row, 3)) = c3;
-        if (in.valid && my_h == 0) {
-            // c0 = hi[0..7], c2 = lo[0..7]: the self state is columns 0..5 of the rotated row (sarl.py:36)
-            uint8_t *jt = J + (size_t)(g >> 7) * J_TILE_BYTES;
-            const int rb = (int)(g & 127);
-            *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 7)) = make_uint4(c0.x, c0.y, c0.z, h2(1.0f, 1.0f));
-            *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 8)) = make_uint4(c2.x, c2.y, c2.z, 0u);
-            *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 9)) = make_uint4(0, 0, 0, 0);
-        }
-    } else {
-        D[row] = pp_clearance(in, dt, query_env);
-        if (ctx == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
-        else asm volatile("bar.sync 4, 128;" ::: "memory");
-        if (in.valid && my_h == 0) rew[g] = pair_reward(p, in, D + row, H, query_env);
+    RowInPP in;
+    pp_load_inputs(in, ed, st, time, human_v, actions, A, query_env, NG, G, tile, gl, h);
+    D[r] = pp_clearance(in, dt, query_env);
+    uint4 c0, c1, c2, c3;
+    pair_features(in, dt, c0, c1, c2, c3);
+    uint8_t *xt = X + (size_t)tile * X_TILE_BYTES;
+    *reinterpret_cast<uint4 *>(xt + chunk_off(ROWS, r, 0)) = c0;
+    *reinterpret_cast<uint4 *>(xt + chunk_off(ROWS, r, 1)) = c1;
+    *reinterpret_cast<uint4 *>(xt + chunk_off(ROWS, r, 2)) = c2;
+    *reinterpret_cast<uint4 *>(xt + chunk_off(ROWS, r, 3)) = c3;
+    const bool lead = in.valid && h == 0;
+    const int g = tile * G + gl;
+    if (lead) {
+        // c0 = hi[0..7], c2 = lo[0..7]: the self state is columns 0..5 of the rotated row (sarl.py:36)
+        uint8_t *jt = J + (size_t)(g >> 7) * J_TILE_BYTES;
+        const int rb = g & 127;
+        *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 7)) = make_uint4(c0.x, c0.y, c0.z, h2(1.0f, 1.0f));
+        *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 8)) = make_uint4(c2.x, c2.y, c2.z, 0u);
+        *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 9)) = make_uint4(0, 0, 0, 0);
     }
+    __syncthreads();
+    if (lead) rew[g] = pair_reward(p, in, D + r, H, query_env);
 }
 
 __device__ __forceinline__ void ctx_barrier(int ctx)
@@ -218,9 +230,8 @@ __device__ __forceinline__ void ctx_barrier(int ctx)
 // HT = compile-time human count (5, 10: the benchmark configurations) or 0 = run-time H
 template <int HT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsPair, 1)
-tc_rows_pair_kernel(EnvParams p, const double *__restrict__ st, const double *__restrict__ time,
-                    const double *__restrict__ human_v, const double *__restrict__ actions, int A, int query_env,
-                    const uint8_t *__restrict__ wimg, uint8_t *__restrict__ J, double *__restrict__ rew, int NG, int G_rt,
+tc_rows_pair_kernel(EnvParams p,
+                    const uint8_t *__restrict__ wimg, const uint8_t *__restrict__ X, uint8_t *__restrict__ J, int NG, int G_rt,
                     int rounds, const TailW tw, long long *__restrict__ dbg)
 {
 #define QPROBE(slot, i) do { if (dbg && blockIdx.x < 2 && probe_round) dbg[(blockIdx.x * 4 + (slot)) * 32 + (i)] = clock64(); } while (0)
@@ -229,7 +240,7 @@ tc_rows_pair_kernel(EnvParams p, const double *__restrict__ st, const double *__
     const int H = HT ? HT : ed.H;
     const int G = HT ? ROWS / HT : G_rt;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool is_issuer_warp = warp == 16;
+    const bool is_issuer_warp = warp == 16, is_producer_warp = warp > 16;
     const int q = warp & 3, ctx = (warp >> 2) & 1, hf = (warp >> 3) & 1;     // lane quarter, tile context, column half
     const uint32_t rank = cluster_ctarank();
     const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
@@ -239,10 +250,12 @@ tc_rows_pair_kernel(EnvParams p, const double *__restrict__ st, const double *__
     const int rows = G * H;
     uint8_t *R1 = smem + Q_CTX0 + (uint32_t)ctx * Q_CTX_BYTES, *R2 = R1 + Q_R1_BYTES;
     float *S0 = reinterpret_cast<float *>(smem + Q_MISC) + ctx * 256, *S1 = S0 + 128;   // partial scores of the column halves
-    double *D = reinterpret_cast<double *>(smem + Q_MISC + 2048) + ctx * 128;
     const uint32_t bar0 = smem_u32(smem + Q_MISC + 4096);
     const uint32_t req0 = bar0, req1 = bar0 + 8, done0 = bar0 + 16, done1 = bar0 + 24, reqm0 = bar0 + 32, reqm1 = bar0 + 40;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Q_MISC + 4096 + 48);
+    const uint32_t xfull0 = bar0 + 48, xfull1 = bar0 + 56;     // rank-0 CTA: X of the context's next tile has landed in both CTAs
+    const uint32_t xland0 = bar0 + 80, xland1 = bar0 + 88;     // per CTA: TMA transaction barrier of the X slot
+    const uint32_t xfree0 = bar0 + 64, xfree1 = bar0 + 72;     // per CTA: stage 1 of the context's tile is complete -> the X slot may be rewritten
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Q_MISC + 4096 + 96);
 
     copy_image_to_smem(smem, wimg + (size_t)rank * IMG_H_BYTES, IMG_H_BYTES);
     for (uint32_t i = tid * 16; i < 2 * Q_CTX_BYTES; i += kThreadsPair * 16)       // padding rows stay finite
@@ -250,6 +263,8 @@ tc_rows_pair_kernel(EnvParams p, const double *__restrict__ st, const double *__
     if (tid == 0) {
         mbar_init(req0, 16); mbar_init(req1, 16); mbar_init(done0, 1); mbar_init(done1, 1);
         mbar_init(reqm0, 16); mbar_init(reqm1, 16);
+        mbar_init(xfull0, 2); mbar_init(xfull1, 2); mbar_init(xfree0, 1); mbar_init(xfree1, 1);
+        mbar_init(xland0, 1); mbar_init(xland1, 1);
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc_2(smem_u32(tmem_slot), 512);
@@ -267,7 +282,7 @@ tc_rows_pair_kernel(EnvParams p, const double *__restrict__ st, const double *__
             const uint32_t sWB = smem_u32(smem + H_WB), sW4 = smem_u32(smem + H_W4), sWA2 = smem_u32(smem + H_WA2);
             const int total = 5 * rounds;
             int stage0 = 0, stage1 = 0;
-            uint32_t ph0 = 0, ph1 = 0, phm0 = 0, phm1 = 0;
+            uint32_t ph0 = 0, ph1 = 0, phm0 = 0, phm1 = 0, phx0 = 0, phx1 = 0;
             long long t_last = clock64();
             while (stage0 < total || stage1 < total) {
 #pragma unroll
@@ -277,6 +292,11 @@ tc_rows_pair_kernel(EnvParams p, const double *__restrict__ st, const double *__
                     const int s = stage % 5;
                     uint32_t &ph = (s == 3) ? (c ? phm1 : phm0) : (c ? ph1 : ph0);
                     if (!mbar_test_wait_cluster((s == 3) ? (c ? reqm1 : reqm0) : (c ? req1 : req0), ph)) continue;
+                    if (s == 0) {                                   // stage 0 also needs the producers' X
+                        uint32_t &phx = c ? phx1 : phx0;
+                        if (!mbar_test_wait_cluster(c ? xfull1 : xfull0, phx)) continue;
+                        phx ^= 1;
+                    }
                     ph ^= 1;
                     const bool probe_round = stage / 5 == 3;
                     QPROBE(2 + c, 2 * s);
@@ -307,12 +327,28 @@ tc_rows_pair_kernel(EnvParams p, const double *__restrict__ st, const double *__
                 if (clock64() - t_last > 4000000000LL) __trap();    // protocol bug guard: never hang the GPU
             }
         }
+    } else if (is_producer_warp) {
+        // ================= loader warps (both CTAs): warp 17 + c streams context c's X tiles from HBM by TMA bulk copy =================
+        if (lane == 0) {
+            const int c = warp - 17;
+            const uint32_t xl = c ? xland1 : xland0, xfree = c ? xfree1 : xfree0;
+            const uint32_t xfull_leader = mapa(c ? xfull1 : xfull0, 0);
+            const uint32_t dst = smem_u32(smem + Q_CTX0 + (uint32_t)c * Q_CTX_BYTES + Q_X_OFF);
+            const int tile_stride = 4 * nclusters;
+            int tile = (cluster_id * 2 + (int)rank) * 2 + c;
+            uint32_t phf = 0, phl = 0;
+            for (int rnd = 0; rnd < rounds; ++rnd, tile += tile_stride) {
+                if (rnd > 0) { mbar_wait_guarded(xfree, phf); phf ^= 1; }              // stage 1 of the previous tile is complete
+                bulk_load(dst, X + (size_t)tile * X_TILE_BYTES, X_TILE_BYTES, xl);
+                mbar_wait_guarded(xl, phl); phl ^= 1;                                   // the tile has landed in this CTA
+                mbar_arrive_cluster(xfull_leader);
+            }
+        }
     } else {
         // ================= epilogue warps: context `ctx`, column half `hf` (both CTAs) =================
         const uint32_t done = ctx ? done1 : done0;
         const uint32_t req_leader = mapa(ctx ? req1 : req0, 0), reqm_leader = mapa(ctx ? reqm1 : reqm0, 0);
         const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)ctx * PAIR_CTX_COLS;
-        uint8_t *xbuf = R1 + Q_X_OFF;
         uint32_t ph = 0;
         const float invH = 1.0f / (float)H;
         const int tile_stride = 4 * nclusters;
@@ -331,11 +367,6 @@ tc_rows_pair_kernel(EnvParams p, const double *__restrict__ st, const double *__
 #define PAIR_SIGNAL_TO(bar) do { fence_async_smem(); fence_before_sync(); __syncwarp(); if (lane == 0) mbar_arrive_cluster(bar); } while (0)
 #define PAIR_SIGNAL() PAIR_SIGNAL_TO(req_leader)
 #define PAIR_WAIT() do { mbar_wait_guarded(done, ph); ph ^= 1; fence_after_sync(); } while (0)
-        {
-            RowInPP in;
-            pp_load_inputs(in, ed, st, time, human_v, actions, A, query_env, NG, G, tile, my_gl, my_h);
-            pair_prepare_tile<HT>(p, in, H, query_env, G, tile, row, my_gl, my_h, ctx, hf, xbuf, D, J, rew);
-        }
         for (int rnd = 0; rnd < rounds; ++rnd, tile += tile_stride) {
             const bool has_next = rnd + 1 < rounds;
             const bool probe_round = (t256 == 0) && rnd == 3;
@@ -350,11 +381,10 @@ tc_rows_pair_kernel(EnvParams p, const double *__restrict__ st, const double *__
             PAIR_SIGNAL(); QPROBE(ctx, 2);
             // ---- E1: mlp1_out = relu(acc[0,112)) -> R2 ----
             PAIR_WAIT(); QPROBE(ctx, 3);
+            if (warp == 4 * ctx && lane == 0) mbar_arrive(ctx ? xfree1 : xfree0);      // H1 is dead: producers may write the next X
             if (hf == 0) epilogue_to_smem<true>(tl, 0, 64, R2, row, 0);
             else epilogue_to_smem<true>(tl, 64, 48, R2, row, 8);
             PAIR_SIGNAL(); QPROBE(ctx, 4);                                         // stage 2 may start
-            RowInPP in;
-            if (has_next) pp_load_inputs(in, ed, st, time, human_v, actions, A, query_env, NG, G, tile + tile_stride, my_gl, my_h);
             QPROBE(ctx, 12);
             // ---- group mean of mlp1_out over the humans of a group (sarl.py:42), replicated on the group's rows -> R1 ----
             ctx_barrier(ctx);
@@ -404,8 +434,6 @@ tc_rows_pair_kernel(EnvParams p, const double *__restrict__ st, const double *__
             }
             QPROBE(ctx, 14);
             PAIR_SIGNAL_TO(reqm_leader); QPROBE(ctx, 5);                           // stage 3 may start
-            // ---- next tile: rotate + pack -> X, self state (hf 0) | clearances, rewards (hf 1), under stages 2-3 ----
-            if (has_next) pair_prepare_tile<HT>(p, in, H, query_env, G, tile + tile_stride, row, my_gl, my_h, ctx, hf, xbuf, D, J, rew);
             QPROBE(ctx, 6);
             // ---- E3: H3 = relu(acc[0,112)) -> R1 (hf 0) ; Ha1 = relu(acc[112,224)) -> R2 (hf 1) ----
             PAIR_WAIT(); QPROBE(ctx, 7);

@@ -265,6 +265,15 @@ __device__ __forceinline__ void tmem_dealloc_2(uint32_t taddr, uint32_t ncols)
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
 }
 
+// TMA bulk copy global -> this CTA's shared memory (no tensor map: a contiguous, 16-byte aligned span); the bytes
+// are accounted on `mbar` (one arrival + expect_tx is posted here, so initialise the barrier with count 1)
+__device__ __forceinline__ void bulk_load(uint32_t dst_saddr, const void *src, uint32_t bytes, uint32_t mbar_saddr)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar_saddr), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst_saddr), "l"(src), "r"(bytes), "r"(mbar_saddr) : "memory");
+}
+
 // 32 lanes x 32 columns of fp32: thread i of the warp receives columns [col, col+32) of TMEM lane (base lane + i)
 __device__ __forceinline__ void ld32(uint32_t taddr, uint32_t (&r)[32])
 {
