@@ -51,7 +51,6 @@ constexpr uint32_t Q_CTX0 = (IMG_H_BYTES + 127) & ~127u;
 constexpr uint32_t Q_MISC = Q_CTX0 + 2 * Q_CTX_BYTES;               // S[2][2][128] f32 | D[2][128] f64 | 10 mbarriers | tmem slot
 constexpr uint32_t Q_SMEM = Q_MISC + 2048 + 2048 + 96 + 16;
 static_assert(Q_X_OFF + bytes_of(ROWS, K_X) <= Q_R1_BYTES, "next-tile X must fit behind the 112-column tiles");
-static_assert(ROWS * 56 * 4 <= Q_X_OFF, "fp32 weighted features must not reach the next tile's X");
 static_assert(Q_SMEM <= 232448, "tc_rows_pair_kernel exceeds 227 KB of shared memory");
 
 struct RowInPP {
@@ -354,15 +353,16 @@ tc_rows_pair_kernel(EnvParams p,
         const int tile_stride = 4 * nclusters;
         int tile = (cluster_id * 2 + (int)rank) * 2 + ctx;
         // loop-invariant work items of the two shared-memory group reductions (consecutive threads -> consecutive groups)
-        int mean_off[2];
+        // (HT: at most 2 mean items and 1 sum item per thread, decomposed once; run-time H: any count, decomposed in the loop)
+        constexpr int kMeanIters = HT ? 2 : 4;      // G <= 64 -> at most 896 mean items / 256 threads
+        int mean_off[kMeanIters];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kMeanIters; ++i) {
             const int it = t256 + i * 256;
             const int c = it / G, gl = it - c * G;
             mean_off[i] = (it < G * (N_M1 / 8)) ? (int)chunk_off(ROWS, gl * H, c) : -1;
         }
-        const int sum_c = t256 / G, sum_gl = t256 - sum_c * G;
-        const bool sum_item = t256 < G * 7;
+        constexpr int kSumIters = HT ? 1 : 2;       // at most 448 sum items / 256 threads
         // operand hand-over: generic-proxy writes -> async proxy, TMEM reads ordered, one arrival per warp
 #define PAIR_SIGNAL_TO(bar) do { fence_async_smem(); fence_before_sync(); __syncwarp(); if (lane == 0) mbar_arrive_cluster(bar); } while (0)
 #define PAIR_SIGNAL() PAIR_SIGNAL_TO(req_leader)
@@ -390,7 +390,7 @@ tc_rows_pair_kernel(EnvParams p,
             ctx_barrier(ctx);
             QPROBE(ctx, 13);
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < kMeanIters; ++i) {
                 if (mean_off[i] < 0) continue;
                 const uint8_t *src = R2 + mean_off[i];
                 uint4 v[HT ? HT : 1];
@@ -492,17 +492,17 @@ tc_rows_pair_kernel(EnvParams p,
                 w = mine / ssum;
             }
             {
-                // w * F in fp32, chunked [c][row][8 floats] over the (dead) H3 tile: hf 0 -> features 0..31, hf 1 -> 32..55
+                // w * F as fp16 (fp32 product rounded once), chunked like an operand over the (dead) H3 tile:
+                // hf 0 -> features 0..31, hf 1 -> 32..55
                 uint32_t v[32];
                 ld32(tl + hf * 32, v);
                 wait_ld();
-                float *fdst = reinterpret_cast<float *>(R1) + (hf * 4) * (ROWS * 8) + row * 8;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     if (hf == 1 && c == 3) break;
                     const float *f = reinterpret_cast<const float *>(v) + c * 8;
-                    *reinterpret_cast<float4 *>(fdst + c * (ROWS * 8)) = make_float4(w * f[0], w * f[1], w * f[2], w * f[3]);
-                    *reinterpret_cast<float4 *>(fdst + c * (ROWS * 8) + 4) = make_float4(w * f[4], w * f[5], w * f[6], w * f[7]);
+                    *reinterpret_cast<uint4 *>(R1 + chunk_off(ROWS, row, hf * 4 + c)) =
+                        make_uint4(h2(w * f[0], w * f[1]), h2(w * f[2], w * f[3]), h2(w * f[4], w * f[5]), h2(w * f[6], w * f[7]));
                 }
             }
             QPROBE(ctx, 17);
@@ -510,31 +510,33 @@ tc_rows_pair_kernel(EnvParams p,
             ctx_barrier(ctx);
             QPROBE(ctx, 10);
             // ---- weighted feature of the group (sarl.py:57-60): sum over its humans -> J chunks 0..6 ----
-            if (sum_item) {
+#pragma unroll
+            for (int si = 0; si < kSumIters; ++si) {
+                const int it = t256 + si * 256;
+                const int sum_c = it / G, sum_gl = it - sum_c * G;
                 const long long gg = (long long)tile * G + sum_gl;
-                if (gg < NG) {
-                    const float *src = reinterpret_cast<const float *>(R1) + sum_c * (ROWS * 8) + sum_gl * H * 8;
-                    float4 a0 = *reinterpret_cast<const float4 *>(src), a1 = *reinterpret_cast<const float4 *>(src + 4);
+                if (it < G * 7 && gg < NG) {
+                    const uint8_t *src = R1 + chunk_off(ROWS, sum_gl * H, sum_c);
+                    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                     if (HT) {
-                        float4 b0[HT ? HT : 1], b1[HT ? HT : 1];
+                        uint4 u[HT ? HT : 1];
 #pragma unroll
-                        for (int h = 1; h < HT; ++h) {
-                            b0[h] = *reinterpret_cast<const float4 *>(src + h * 8);
-                            b1[h] = *reinterpret_cast<const float4 *>(src + h * 8 + 4);
-                        }
+                        for (int h = 0; h < HT; ++h) u[h] = *reinterpret_cast<const uint4 *>(src + h * 16);
 #pragma unroll
-                        for (int h = 1; h < HT; ++h) {
-                            a0.x += b0[h].x; a0.y += b0[h].y; a0.z += b0[h].z; a0.w += b0[h].w;
-                            a1.x += b1[h].x; a1.y += b1[h].y; a1.z += b1[h].z; a1.w += b1[h].w;
+                        for (int h = 0; h < HT; ++h) {
+                            const __half2 *hv = reinterpret_cast<const __half2 *>(&u[h]);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(hv[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
                         }
                     } else {
-                        for (int h = 1; h < H; ++h) {
-                            const float4 b0 = *reinterpret_cast<const float4 *>(src + h * 8);
-                            const float4 b1 = *reinterpret_cast<const float4 *>(src + h * 8 + 4);
-                            a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w;
-                            a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
+                        for (int h = 0; h < H; ++h) {
+                            const uint4 u = *reinterpret_cast<const uint4 *>(src + h * 16);
+                            const __half2 *hv = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(hv[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
                         }
                     }
+                    const float4 a0 = make_float4(acc[0], acc[1], acc[2], acc[3]), a1 = make_float4(acc[4], acc[5], acc[6], acc[7]);
                     uint8_t *jt = J + (size_t)(gg >> 7) * J_TILE_BYTES;
                     *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, (uint32_t)(gg & 127), sum_c)) =
                         make_uint4(h2(a0.x, a0.y), h2(a0.z, a0.w), h2(a1.x, a1.y), h2(a1.z, a1.w));

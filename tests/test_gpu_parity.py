@@ -135,7 +135,9 @@ def test_golden_trajectories(mcn, oracle_mod, weights0, name, precision):
 
 @pytest.mark.parametrize("precision", ["f32", "f16_tc"])
 @pytest.mark.parametrize("H,rule,query_env", [(5, "circle_crossing", 0), (5, "circle_crossing", 1),
-                                              (10, "square_crossing", 0), (3, "circle_crossing", 0)])
+                                              (10, "square_crossing", 0), (3, "circle_crossing", 0),
+                                              (1, "circle_crossing", 0), (2, "circle_crossing", 1),
+                                              (7, "square_crossing", 1), (20, "square_crossing", 0)])
 def test_lookahead_vs_oracle(mcn, oracle_mod, weights0, H, rule, query_env, precision):
     """81 action values and the argmax against the oracle on evolving states (not only reset states)."""
     o = oracle_mod
