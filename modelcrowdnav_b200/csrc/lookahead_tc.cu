@@ -90,6 +90,8 @@ struct TcState {
     int num_sms;
     int variant;              // 0 = one tile in flight per SM (tc_rows_kernel), 2 = CTA pairs, two tiles in flight per SM
     float tail_a[104];        // attention.4 weight[100] + bias (kernel parameter of tc_rows_pair_kernel)
+    float tail_b[104];        // mlp3.6 weight[100] + bias (kernel parameter of tc_mlp3_pair_kernel)
+    uint8_t *img_pair_b;      // two half images of mlp3 for tc_mlp3_pair_kernel
 };
 
 __device__ __forceinline__ void copy_image_to_smem(uint8_t *dst, const uint8_t *__restrict__ src, uint32_t bytes)
@@ -639,6 +641,7 @@ tc_rows_kernel(EnvParams p, const double *__restrict__ st, const double *__restr
 }
 
 #include "tc_rows_pair.cuh"
+#include "tc_mlp3_pair.cuh"
 
 // =====================================================================================================
 // kernel B: mlp3 on the joint states + scoring (256 threads, same lane-quarter / column-half split)
@@ -928,7 +931,9 @@ int cn_tc_init(cn_policy *p)
     CN_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
     CN_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_pair_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
     CN_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_pair_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
-    if (cudaMalloc((void **)&t->img_pair, 2 * IMG_H_BYTES) != cudaSuccess) {
+    CN_CUDA_CHECK(cudaFuncSetAttribute(tc_mlp3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M_SMEM));
+    if (cudaMalloc((void **)&t->img_pair, 2 * IMG_H_BYTES) != cudaSuccess ||
+        cudaMalloc((void **)&t->img_pair_b, 2 * IMG_HM_BYTES) != cudaSuccess) {
         cn_set_error("cudaMalloc failed for the tensor-core weight images");
         return CN_ENOMEM;
     }
@@ -945,6 +950,7 @@ void cn_tc_destroy(cn_policy *p)
     if (t->img_a) cudaFree(t->img_a);
     if (t->img_b) cudaFree(t->img_b);
     if (t->img_pair) cudaFree(t->img_pair);
+    if (t->img_pair_b) cudaFree(t->img_pair_b);
     if (t->J) cudaFree(t->J);
     if (t->X) cudaFree(t->X);
     if (t->rew) cudaFree(t->rew);
@@ -990,6 +996,15 @@ int cn_tc_load_weights(cn_policy *p, const float *flat, cudaStream_t s)
     for (int k = 0; k < 100; ++k) tail[k] = L[10].w[k];
     tail[100] = L[10].b[0];
     memcpy(&b[OFF_TAILB], tail, TAIL_BYTES);
+    memcpy(t->tail_b, tail, sizeof(t->tail_b));
+    std::vector<uint8_t> hb(2 * IMG_HM_BYTES, 0);
+    for (int rank = 0; rank < 2; ++rank) {
+        uint8_t *h = hb.data() + (size_t)rank * IMG_HM_BYTES;
+        split_rows(h + HM_M1, b.data() + OFF_M1, N_H1, K_J, rank);
+        split_rows(h + HM_M2, b.data() + OFF_M2, N_M1, N_H1, rank);
+        split_rows(h + HM_M3, b.data() + OFF_M3, N_M1, N_M1, rank);
+    }
+    CN_CUDA_CHECK(cudaMemcpyAsync(t->img_pair_b, hb.data(), 2 * IMG_HM_BYTES, cudaMemcpyHostToDevice, s));
     // half images for the CTA-pair kernel: CTA `rank` holds output rows [rank N/2, (rank+1) N/2) of every layer
     std::vector<uint8_t> hp(2 * IMG_H_BYTES, 0);
     for (int rank = 0; rank < 2; ++rank) {
@@ -1023,7 +1038,8 @@ int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cu
         if (t->J) cudaFree(t->J);
         if (t->rew) cudaFree(t->rew);
         t->J = nullptr; t->rew = nullptr; t->cap_groups = 0;
-        const size_t jtiles = (NG + ROWS - 1) / ROWS;
+        // the CTA-pair mlp3 kernel reads whole rounds of tiles: pad with up to one round of (zero) tiles
+        const size_t jtiles = (NG + ROWS - 1) / ROWS + 4 * (size_t)(t->num_sms / 2);
         CN_CUDA_CHECK(cudaMalloc((void **)&t->J, jtiles * J_TILE_BYTES));
         CN_CUDA_CHECK(cudaMalloc((void **)&t->rew, sizeof(double) * NG));
         CN_CUDA_CHECK(cudaMemsetAsync(t->J, 0, jtiles * J_TILE_BYTES, s));
@@ -1063,8 +1079,19 @@ int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cu
                                                             query_env, t->img_a, t->J, t->rew, (int)NG, G, ntiles_a, t->dbg);
     }
     CN_LAUNCH_CHECK();
-    tc_mlp3_kernel<<<grid_b, kThreadsTC, B_SMEM, s>>>(env->p, env->state, t->img_b, t->J, t->rew, A, (int)NG, p->cfg.gamma,
-                                               gamma_bar, p->cfg.v_pref, p->values, ntiles_b);
+    if (t->variant == 2) {
+        int nclusters = t->num_sms / 2;
+        const int slots_needed = (ntiles_b + 3) / 4;
+        if (nclusters > slots_needed) nclusters = slots_needed;
+        const int rounds = (ntiles_b + 4 * nclusters - 1) / (4 * nclusters);
+        TailW tw;
+        memcpy(tw.w, t->tail_b, sizeof(tw.w));
+        tc_mlp3_pair_kernel<<<2 * nclusters, kThreadsM3, M_SMEM, s>>>(env->p, env->state, t->img_pair_b, t->J, t->rew, A, (int)NG,
+                                                                     p->cfg.gamma, gamma_bar, p->cfg.v_pref, p->values, rounds, tw);
+    } else {
+        tc_mlp3_kernel<<<grid_b, kThreadsTC, B_SMEM, s>>>(env->p, env->state, t->img_b, t->J, t->rew, A, (int)NG, p->cfg.gamma,
+                                                   gamma_bar, p->cfg.v_pref, p->values, ntiles_b);
+    }
     CN_LAUNCH_CHECK();
     return cn_lookahead_argmax(p, env, epsilon, s);
 }

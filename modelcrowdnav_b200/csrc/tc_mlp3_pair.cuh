@@ -1,0 +1,180 @@
+// tc_mlp3_pair.cuh -- mlp3 on the joint states + scoring on CTA pairs (tcgen05 cta_group::2), same dataflow skeleton
+// as tc_rows_pair.cuh: per SM two tile contexts, 16 epilogue warps (2 contexts x 2 column halves x 4 TMEM lane
+// quarters), warp 16 of the rank-0 CTA issues the UMMAs of the pair, warps 17 / 18 stream the joint-state tiles of
+// context 0 / 1 from HBM with TMA bulk copies.  Rows = (env, action); each CTA keeps HALF of the mlp3 weights (42 KB).
+//
+//   stage  UMMA (M=256 over the pair)     A operand          D           epilogue
+//   0      mlp3.0   K=80   N=160          J    (RA, by TMA)  [0,160)     ReLU -> U0 (RA, over the dead J tile)
+//   1      mlp3.2   K=160  N=112          U0   (RA)          [0,112)     ReLU -> U1 (RB)
+//   2      mlp3.4   K=112  N=112          U1   (RB)          [0,112)     mlp3.6 as an fp32 dot on ReLU(acc),
+//                                                                         value = reward + gamma_bar * V -> values[E][A]
+// Reference: crowd_nav/policy/sarl.py:62-64 (mlp3 on the joint state), multi_human_rl.py:52 (scoring).
+
+constexpr int kThreadsM3 = 608;
+constexpr int M3_CTX_COLS = 160;
+
+constexpr uint32_t HM_M1 = 0;                                        //  80 x 80
+constexpr uint32_t HM_M2 = HM_M1 + bytes_of(N_H1 / 2, K_J);          //  56 x 160
+constexpr uint32_t HM_M3 = HM_M2 + bytes_of(N_M1 / 2, N_H1);         //  56 x 112
+constexpr uint32_t IMG_HM_BYTES = HM_M3 + bytes_of(N_M1 / 2, N_M1);
+
+constexpr uint32_t M_RA_BYTES = bytes_of(ROWS, N_H1);                // 40 KB: J tile (20 KB) | U0
+constexpr uint32_t M_RB_BYTES = bytes_of(ROWS, N_M1);                // 28 KB: U1
+constexpr uint32_t M_CTX_BYTES = M_RA_BYTES + M_RB_BYTES;
+constexpr uint32_t M_CTX0 = (IMG_HM_BYTES + 127) & ~127u;
+constexpr uint32_t M_MISC = M_CTX0 + 2 * M_CTX_BYTES;                // S[2][128] f32 | 10 mbarriers | tmem slot
+constexpr uint32_t M_SMEM = M_MISC + 1024 + 96 + 16;
+static_assert(M_SMEM <= 232448, "tc_mlp3_pair_kernel exceeds 227 KB of shared memory");
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsM3, 1)
+tc_mlp3_pair_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *__restrict__ wimg,
+                    const uint8_t *__restrict__ J, const double *__restrict__ rew, int A, int NG, double gamma,
+                    double gamma_bar_host, double v_pref_host, double *__restrict__ values, int rounds, const TailW tw)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, ctx = (warp >> 2) & 1, hf = (warp >> 3) & 1;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+    const int row = q * 32 + lane;
+    uint8_t *RA = smem + M_CTX0 + (uint32_t)ctx * M_CTX_BYTES, *RB = RA + M_RA_BYTES;
+    float *S1 = reinterpret_cast<float *>(smem + M_MISC) + ctx * 128;       // partial dot of the upper column half
+    const uint32_t bar0 = smem_u32(smem + M_MISC + 1024);
+    const uint32_t req0 = bar0, req1 = bar0 + 8, done0 = bar0 + 16, done1 = bar0 + 24;
+    const uint32_t xfull0 = bar0 + 32, xfull1 = bar0 + 40, xfree0 = bar0 + 48, xfree1 = bar0 + 56, xland0 = bar0 + 64, xland1 = bar0 + 72;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + M_MISC + 1024 + 96);
+
+    copy_image_to_smem(smem, wimg + (size_t)rank * IMG_HM_BYTES, IMG_HM_BYTES);
+    for (uint32_t i = tid * 16; i < 2 * M_CTX_BYTES; i += kThreadsM3 * 16)
+        *reinterpret_cast<uint4 *>(smem + M_CTX0 + i) = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        mbar_init(req0, 16); mbar_init(req1, 16); mbar_init(done0, 1); mbar_init(done1, 1);
+        mbar_init(xfull0, 2); mbar_init(xfull1, 2); mbar_init(xfree0, 1); mbar_init(xfree1, 1);
+        mbar_init(xland0, 1); mbar_init(xland1, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc_2(smem_u32(tmem_slot), 512);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const int tile_stride = 4 * nclusters;
+
+    if (warp == 16) {
+        // ================= issuer (rank-0 CTA only) =================
+        if (rank == 0 && lane == 0) {
+            const uint32_t sM1 = smem_u32(smem + HM_M1), sM2 = smem_u32(smem + HM_M2), sM3 = smem_u32(smem + HM_M3);
+            const int total = 3 * rounds;
+            int stage0 = 0, stage1 = 0;
+            uint32_t ph0 = 0, ph1 = 0, phx0 = 0, phx1 = 0;
+            long long t_last = clock64();
+            while (stage0 < total || stage1 < total) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    int &stage = c ? stage1 : stage0;
+                    if (stage >= total) continue;
+                    const int s = stage % 3;
+                    uint32_t &ph = c ? ph1 : ph0;
+                    if (!mbar_test_wait_cluster(c ? req1 : req0, ph)) continue;
+                    if (s == 0) {                                   // stage 0 also needs the joint-state tile
+                        uint32_t &phx = c ? phx1 : phx0;
+                        if (!mbar_test_wait_cluster(c ? xfull1 : xfull0, phx)) continue;
+                        phx ^= 1;
+                    }
+                    ph ^= 1;
+                    fence_after_sync();
+                    const uint32_t tm = tmem + (uint32_t)c * M3_CTX_COLS;
+                    const uint32_t sRA = smem_u32(smem + M_CTX0 + (uint32_t)c * M_CTX_BYTES), sRB = sRA + M_RA_BYTES;
+                    if (s == 0) mma_layer_2(tm, sRA, ROWS, sM1, K_J, N_H1, false);
+                    else if (s == 1) mma_layer_2(tm, sRA, ROWS, sM2, N_H1, N_M1, false);
+                    else mma_layer_2(tm, sRB, ROWS, sM3, N_M1, N_M1, false);
+                    commit_2(c ? done1 : done0, 3);
+                    ++stage;
+                    t_last = clock64();
+                }
+                if (clock64() - t_last > 4000000000LL) __trap();
+            }
+        }
+    } else if (warp > 16) {
+        // ================= loader warps: warp 17 + c streams context c's joint-state tiles =================
+        if (lane == 0) {
+            const int c = warp - 17;
+            const uint32_t xl = c ? xland1 : xland0, xfree = c ? xfree1 : xfree0;
+            const uint32_t xfull_leader = mapa(c ? xfull1 : xfull0, 0);
+            const uint32_t dst = smem_u32(smem + M_CTX0 + (uint32_t)c * M_CTX_BYTES);
+            int tile = (cluster_id * 2 + (int)rank) * 2 + c;
+            uint32_t phf = 0, phl = 0;
+            for (int rnd = 0; rnd < rounds; ++rnd, tile += tile_stride) {
+                if (rnd > 0) { mbar_wait_guarded(xfree, phf); phf ^= 1; }              // stage 1 of the previous tile is complete: U0 is dead
+                bulk_load(dst, J + (size_t)tile * J_TILE_BYTES, J_TILE_BYTES, xl);
+                mbar_wait_guarded(xl, phl); phl ^= 1;
+                mbar_arrive_cluster(xfull_leader);
+            }
+        }
+    } else {
+        // ================= epilogue warps =================
+        const uint32_t done = ctx ? done1 : done0;
+        const uint32_t req_leader = mapa(ctx ? req1 : req0, 0);
+        const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)ctx * M3_CTX_COLS;
+        uint32_t ph = 0;
+        int tile = (cluster_id * 2 + (int)rank) * 2 + ctx;
+#define M3_SIGNAL() do { fence_async_smem(); fence_before_sync(); __syncwarp(); if (lane == 0) mbar_arrive_cluster(req_leader); } while (0)
+#define M3_WAIT() do { mbar_wait_guarded(done, ph); ph ^= 1; fence_after_sync(); } while (0)
+        for (int rnd = 0; rnd < rounds; ++rnd, tile += tile_stride) {
+            M3_SIGNAL();                                                           // stage 0: TMEM / RA are free
+            M3_WAIT();
+            epilogue_to_smem<true>(tl, hf * 80, 80, RA, row, hf * 10);             // U0 over the dead J tile
+            M3_SIGNAL();
+            M3_WAIT();
+            if (warp == 4 * ctx && lane == 0) mbar_arrive(ctx ? xfree1 : xfree0);  // U0 is dead: the next J tile may land
+            if (hf == 0) epilogue_to_smem<true>(tl, 0, 64, RB, row, 0);
+            else epilogue_to_smem<true>(tl, 64, 48, RB, row, 8);
+            M3_SIGNAL();
+            M3_WAIT();
+            // mlp3.6 as an fp32 dot over ReLU(mlp3.4), split over the column halves
+            float part = 0.0f;
+            if (hf == 0) {
+                uint32_t v[32], u[32];
+                ld32(tl, v);
+                ld32(tl + 32, u);
+                wait_ld();
+#pragma unroll
+                for (int k = 0; k < 32; ++k) part = fmaf(fmaxf(__uint_as_float(v[k]), 0.0f), tw.w[k], part);
+#pragma unroll
+                for (int k = 0; k < 32; ++k) part = fmaf(fmaxf(__uint_as_float(u[k]), 0.0f), tw.w[32 + k], part);
+            } else {
+                uint32_t x[32], y[16];
+                ld32(tl + 64, x);
+                ld16(tl + 96, y);
+                wait_ld();
+#pragma unroll
+                for (int k = 0; k < 32; ++k) part = fmaf(fmaxf(__uint_as_float(x[k]), 0.0f), tw.w[64 + k], part);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) part = fmaf(fmaxf(__uint_as_float(y[k]), 0.0f), tw.w[96 + k], part);
+                S1[row] = part;
+            }
+            fence_before_sync();
+            if (ctx == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+            else asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (hf == 0) {
+                const float v = part + S1[row] + tw.w[100];
+                const long long g = (long long)tile * ROWS + row;
+                if (g < NG) {
+                    const int e = (int)(g / A);
+                    const double vp = st[st_idx(p.d, F_VPREF, 0, e)];
+                    const double gamma_bar = (vp == v_pref_host) ? gamma_bar_host : pow(gamma, p.time_step * vp);
+                    values[g] = rew[g] + gamma_bar * (double)v;                   // multi_human_rl.py:52
+                }
+            }
+            // S1 is rewritten only after the next tile's three completion waits, which every hf-0 reader precedes
+        }
+#undef M3_SIGNAL
+#undef M3_WAIT
+    }
+    fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 0) tmem_dealloc_2(tmem, 512);
+}
