@@ -216,6 +216,9 @@ int cn_selftest_umma_pair(int32_t N, int32_t K, const float *a_host, const float
 /* Developer diagnostic: clock64() at the phase boundaries of one tile of the tensor-core row kernel (CTA 0).
  * The first call arms the probes; call again after a lookahead to read 16 timestamps. */
 int cn_debug_tc_timing(cn_policy *p, long long *out16);
+/* Developer diagnostic: tcgen05.ld throughput of one SM (mode 0 = x32 pairs, 1 = x64, 2 = x16, 3 = x32 pairs + the
+ * epilogue's convert / st.shared work); *cycles = clock64() ticks of the slowest of `nwarps` warps over `iters` loops. */
+int cn_debug_tmem_bench(int32_t mode, int32_t nwarps, int32_t iters, long long *cycles, int device);
 /* Developer diagnostic: the self-test product with a selectable operand mode (0 = A and B in shared memory,
  * 1 = B MN-major, 2 = A in TMEM), repeated `reps` times; *cycles = clock64() ticks of issue + commit + wait. */
 int cn_debug_umma_bench(int32_t N, int32_t K, int32_t mode, int32_t reps, const float *a_host, const float *b_host,

@@ -1197,6 +1197,101 @@ extern "C" int cn_debug_tc_timing(cn_policy *p, long long *out16)
     return CN_OK;
 }
 
+// Developer diagnostic: tcgen05.ld throughput.  `nwarps` warps (4 per TMEM lane quarter at most useful) each run
+// `iters` iterations of {loads of `cols` fp32 columns, wait::ld}; mode 0 = 32x32b.x32 loads, 1 = .x64, 2 = .x128,
+// 3 = x32 pairs followed by the epilogue's cvt + st.shared work.  *cycles = clock64() ticks of the slowest warp.
+namespace {
+__device__ __forceinline__ void ld64(uint32_t taddr, uint32_t (&r)[64])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
+          "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+          "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]),
+          "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]),
+          "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr) : "memory");
+}
+
+__global__ void __launch_bounds__(512, 1)
+tmem_ld_bench_kernel(int mode, int iters, long long *__restrict__ cycles, uint32_t *__restrict__ sink)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 512);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tl = tmem_slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) & 3) * 128;
+    uint32_t acc = 0;
+    const int row = (warp & 3) * 32 + lane;
+    uint8_t *dst = smem + (size_t)(warp >> 2) * 32768;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        if (mode == 0) {
+            uint32_t v[32], u[32];
+            ld32(tl, v); ld32(tl + 32, u);
+            wait_ld();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) acc ^= v[k] ^ u[k];
+        } else if (mode == 1) {
+            uint32_t v[64];
+            ld64(tl, v);
+            wait_ld();
+#pragma unroll
+            for (int k = 0; k < 64; ++k) acc ^= v[k];
+        } else if (mode == 3) {
+            uint32_t v[32], u[32];
+            ld32(tl, v); ld32(tl + 32, u);
+            wait_ld();
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) cvt_store8<true>(v + qd * 8, dst + chunk_off(128, row, qd));
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) cvt_store8<true>(u + qd * 8, dst + chunk_off(128, row, 4 + qd));
+        } else {
+            uint32_t v[16];
+            ld16(tl, v);
+            wait_ld();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc ^= v[k];
+        }
+    }
+    const long long t1 = clock64();
+    if (lane == 0) atomicMax((unsigned long long *)cycles, (unsigned long long)(t1 - t0));
+    if (acc == 0x12345678u) sink[tid] = acc;
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_slot, 512);
+}
+}  // namespace
+
+extern "C" int cn_debug_tmem_bench(int32_t mode, int32_t nwarps, int32_t iters, long long *cycles_host, int device)
+{
+    if (nwarps < 1 || nwarps > 16 || iters < 1) { cn_set_error("nwarps in [1,16], iters >= 1"); return CN_EINVAL; }
+    CN_CUDA_CHECK(cudaSetDevice(device));
+    long long *dc = nullptr;
+    uint32_t *sink = nullptr;
+    CN_CUDA_CHECK(cudaMalloc((void **)&dc, sizeof(long long)));
+    CN_CUDA_CHECK(cudaMalloc((void **)&sink, 512 * sizeof(uint32_t)));
+    CN_CUDA_CHECK(cudaMemset(dc, 0, sizeof(long long)));
+    CN_CUDA_CHECK(cudaFuncSetAttribute(tmem_ld_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 32768));
+    tmem_ld_bench_kernel<<<1, nwarps * 32, 4 * 32768>>>(mode, iters, dc, sink);
+    CN_LAUNCH_CHECK();
+    CN_CUDA_CHECK(cudaDeviceSynchronize());
+    CN_CUDA_CHECK(cudaMemcpy(cycles_host, dc, sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(dc); cudaFree(sink);
+    return CN_OK;
+}
+
 // Developer diagnostic: same product, selectable operand mode (0 = A and B in smem, 1 = B MN-major, 2 = A in TMEM),
 // repeated `reps` times; *cycles = clock64() ticks of the issue+commit+wait loop.
 extern "C" int cn_debug_umma_bench(int32_t N, int32_t K, int32_t mode, int32_t reps, const float *a_host,

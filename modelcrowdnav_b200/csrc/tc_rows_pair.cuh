@@ -367,14 +367,14 @@ tc_rows_pair_kernel(EnvParams p,
 #define PAIR_SIGNAL_TO(bar) do { fence_async_smem(); fence_before_sync(); __syncwarp(); if (lane == 0) mbar_arrive_cluster(bar); } while (0)
 #define PAIR_SIGNAL() PAIR_SIGNAL_TO(req_leader)
 #define PAIR_WAIT() do { mbar_wait_guarded(done, ph); ph ^= 1; fence_after_sync(); } while (0)
+        PAIR_SIGNAL();                                                             // stage 0 of the first tile
         for (int rnd = 0; rnd < rounds; ++rnd, tile += tile_stride) {
             const bool has_next = rnd + 1 < rounds;
             const bool probe_round = (t256 == 0) && rnd == 3;
             const long long g = (long long)tile * G + my_gl;
             const bool row_valid = (row < rows) && (g < NG);
             QPROBE(ctx, 0);
-            // ---- stage 0 request: X of this tile is in R1's tail (written one tile ago / by the prologue) ----
-            PAIR_SIGNAL();
+            // ---- stage 0 was requested at the end of the previous tile (before its group sums) / before the loop ----
             // ---- E0: H1 = relu(acc[0,160)) -> R1 ----
             PAIR_WAIT(); QPROBE(ctx, 1);
             epilogue_to_smem<true>(tl, hf * 80, 80, R1, row, hf * 10);
@@ -492,8 +492,8 @@ tc_rows_pair_kernel(EnvParams p,
                 w = mine / ssum;
             }
             {
-                // w * F as fp16 (fp32 product rounded once), chunked like an operand over the (dead) H3 tile:
-                // hf 0 -> features 0..31, hf 1 -> 32..55
+                // w * F as fp16 (fp32 product rounded once), chunked like an operand over the (dead) Ha1 tile in R2 -- not R1:
+                // the next tile's H1 epilogue may start while slower warps still sum: hf 0 -> features 0..31, hf 1 -> 32..55
                 uint32_t v[32];
                 ld32(tl + hf * 32, v);
                 wait_ld();
@@ -501,7 +501,7 @@ tc_rows_pair_kernel(EnvParams p,
                 for (int c = 0; c < 4; ++c) {
                     if (hf == 1 && c == 3) break;
                     const float *f = reinterpret_cast<const float *>(v) + c * 8;
-                    *reinterpret_cast<uint4 *>(R1 + chunk_off(ROWS, row, hf * 4 + c)) =
+                    *reinterpret_cast<uint4 *>(R2 + chunk_off(ROWS, row, hf * 4 + c)) =
                         make_uint4(h2(w * f[0], w * f[1]), h2(w * f[2], w * f[3]), h2(w * f[4], w * f[5]), h2(w * f[6], w * f[7]));
                 }
             }
@@ -509,6 +509,9 @@ tc_rows_pair_kernel(EnvParams p,
             fence_before_sync();
             ctx_barrier(ctx);
             QPROBE(ctx, 10);
+            // every TMEM read of this tile is done: request stage 0 of the next tile now, the group sums below overlap it.
+            // (R2 is next written by the next tile's E1, which needs every warp's stage-1 request, issued after its sums.)
+            if (has_next) PAIR_SIGNAL();
             // ---- weighted feature of the group (sarl.py:57-60): sum over its humans -> J chunks 0..6 ----
 #pragma unroll
             for (int si = 0; si < kSumIters; ++si) {
@@ -516,7 +519,7 @@ tc_rows_pair_kernel(EnvParams p,
                 const int sum_c = it / G, sum_gl = it - sum_c * G;
                 const long long gg = (long long)tile * G + sum_gl;
                 if (it < G * 7 && gg < NG) {
-                    const uint8_t *src = R1 + chunk_off(ROWS, sum_gl * H, sum_c);
+                    const uint8_t *src = R2 + chunk_off(ROWS, sum_gl * H, sum_c);
                     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                     if (HT) {
                         uint4 u[HT ? HT : 1];
