@@ -245,13 +245,13 @@ def main():
     buf.agents_in[...] = a0; buf.times_in[...] = t0
     for _ in range(2):
         mcn.rollout_step_host(pol, env, buf, a.query_env)
-        buf.agents_in[...] = buf.agents_out; buf.times_in[...] = buf.times_out
+        buf.swap()
     barrier()
     ne = max(5, min(a.steps, 30))
     te0 = time.perf_counter()
     for _ in range(ne):
         mcn.rollout_step_host(pol, env, buf, a.query_env)
-        buf.agents_in[...] = buf.agents_out; buf.times_in[...] = buf.times_out   # next step's input = host state
+        buf.swap()                                   # next step's input = the host state just downloaded (no host copy)
     barrier()
     e2e_s = time.perf_counter() - te0
 

@@ -212,6 +212,13 @@ class HostStepBuffers(object):
                           + self.info.nbytes + self.action_idx.nbytes)
 
 
+    def swap(self):
+        """Make the state just downloaded the next call's input without copying it (ping-pong of the two
+        pinned buffer pairs): what a host-resident simulation loop does between two steps."""
+        self.agents_in, self.agents_out = self.agents_out, self.agents_in
+        self.times_in, self.times_out = self.times_out, self.times_in
+
+
 def rollout_step_host(policy, env, buf, query_env=False, epsilon=0.0, stream=None):
     """One lookahead + env step through host buffers: H2D state, kernels, D2H results (blocking)."""
     check(policy.lib.cn_rollout_step_host(policy.handle, env.handle, int(bool(query_env)), float(epsilon),

@@ -122,8 +122,8 @@ tc_mlp3_pair_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *_
         int tile = (cluster_id * 2 + (int)rank) * 2 + ctx;
 #define M3_SIGNAL() do { fence_async_smem(); fence_before_sync(); __syncwarp(); if (lane == 0) mbar_arrive_cluster(req_leader); } while (0)
 #define M3_WAIT() do { mbar_wait_guarded(done, ph); ph ^= 1; fence_after_sync(); } while (0)
+        M3_SIGNAL();                                                               // stage 0 of the first tile
         for (int rnd = 0; rnd < rounds; ++rnd, tile += tile_stride) {
-            M3_SIGNAL();                                                           // stage 0: TMEM / RA are free
             M3_WAIT();
             epilogue_to_smem<true>(tl, hf * 80, 80, RA, row, hf * 10);             // U0 over the dead J tile
             M3_SIGNAL();
@@ -155,7 +155,8 @@ tc_mlp3_pair_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *_
                 for (int k = 0; k < 4; ++k) part = fmaf(fmaxf(__uint_as_float(y[k]), 0.0f), tw.w[96 + k], part);
                 S1[row] = part;
             }
-            fence_before_sync();
+            // every TMEM read of this tile is done: request stage 0 of the next tile before the scoring below
+            if (rnd + 1 < rounds) M3_SIGNAL();
             if (ctx == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
             else asm volatile("bar.sync 2, 256;" ::: "memory");
             if (hf == 0) {
