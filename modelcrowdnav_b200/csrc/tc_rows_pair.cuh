@@ -16,8 +16,8 @@
 //
 // Per context and tile (rows = (env, action, human); D = TMEM columns relative to the context base):
 //   stage  UMMA (M=256 over the pair)                         A operand        D          epilogue (CUDA cores)
-//   0      mlp1.0                K=32   N=160                 X    (R1 tail)   [0,160)    ReLU -> H1 (R1)
-//   1      mlp1.2                K=160  N=112                 H1   (R1)        [0,112)    ReLU -> mlp1_out (R2)
+//   0      mlp1.0                K=32   N=160                 X    (R1 tail)   [0,160)    ReLU -> H1, fp16 packed IN PLACE in TMEM
+//   1      mlp1.2                K=160  N=112                 H1   (TMEM, TS)  [120,232)  ReLU -> mlp1_out (R2)
 //   2      [mlp2.0 | attn.0a]    K=112  N=224                 mlp1_out (R2)    [0,224)    group mean of mlp1_out in smem
 //   3      attn.0b (mean half)   K=112  N=112, accumulate     mean (R1)        [112,224)  ReLU -> H3 (R1), Ha1 (R2)
 //   4      mlp2.2 ; attn.2       K=112  N=64 ; N=112          H3 ; Ha1         [0,64) ; [64,176)
@@ -30,7 +30,9 @@
 
 constexpr int kThreadsPair = 608;        // 16 epilogue warps (2 contexts x 2 column halves x 4 lane quarters) + issuer warp + 2 loader warps
 constexpr int N_S2 = 2 * N_M1;             // stage 2: [mlp2.0 (rank-0 half) | attention.0 on mlp1_out (rank-1 half)]
-constexpr int PAIR_CTX_COLS = 224;         // TMEM columns per tile context
+constexpr int PAIR_CTX_COLS = 256;         // TMEM columns per tile context
+constexpr int T_H1B = 80;                  // H1 as packed fp16 (TS-mode A operand): K 0..79 at [0,40), K 80..159 at [80,120)
+constexpr int T_D1 = 120;                  // mlp1.2 accumulator [120,232)
 
 // per-CTA HALF weight image: rows [rank * N/2, (rank+1) * N/2) of every layer, chunked K-major with R = N/2
 constexpr uint32_t H_W1 = 0;                                        //  80 x 32
@@ -276,6 +278,8 @@ tc_rows_pair_kernel(EnvParams p,
 
     if (is_issuer_warp) {
         // ================= issuer warp (rank-0 CTA only) =================
+        // ONE issuing thread polls both contexts.  (Two issuer warps, one blocking per context, were measured: the
+        // contexts then run in lock step, contend for the same resources at the same time, and the kernel is 3 % slower.)
         if (rank == 0 && lane == 0) {
             const uint32_t sW1 = smem_u32(smem + H_W1), sW2 = smem_u32(smem + H_W2), sW3A = smem_u32(smem + H_W3A);
             const uint32_t sWB = smem_u32(smem + H_WB), sW4 = smem_u32(smem + H_W4), sWA2 = smem_u32(smem + H_WA2);
@@ -291,7 +295,7 @@ tc_rows_pair_kernel(EnvParams p,
                     const int s = stage % 5;
                     uint32_t &ph = (s == 3) ? (c ? phm1 : phm0) : (c ? ph1 : ph0);
                     if (!mbar_test_wait_cluster((s == 3) ? (c ? reqm1 : reqm0) : (c ? req1 : req0), ph)) continue;
-                    if (s == 0) {                                   // stage 0 also needs the producers' X
+                    if (s == 0) {                                   // stage 0 also needs the TMA-landed X of both CTAs
                         uint32_t &phx = c ? phx1 : phx0;
                         if (!mbar_test_wait_cluster(c ? xfull1 : xfull0, phx)) continue;
                         phx ^= 1;
@@ -307,7 +311,9 @@ tc_rows_pair_kernel(EnvParams p,
                         mma_layer_2(tm, sR1 + Q_X_OFF, ROWS, sW1, K_X, N_H1, false);
                         commit_2(done, 3);
                     } else if (s == 1) {
-                        mma_layer_2(tm, sR1, ROWS, sW2, N_H1, N_M1, false);
+                        // A = H1 straight from TMEM (two packed halves, written in place by the two column-half warps)
+                        mma_steps_2_ts(tm + T_D1, tm, sW2, 0, N_H1 / 32, N_M1, false);
+                        mma_steps_2_ts(tm + T_D1, tm + T_H1B, sW2, N_H1 / 32, N_H1 / 16, N_M1, true);
                         commit_2(done, 3);
                     } else if (s == 2) {
                         mma_layer_2(tm, sR2, ROWS, sW3A, N_M1, N_S2, false);          // completion rides on stage 3's commit
@@ -377,13 +383,13 @@ tc_rows_pair_kernel(EnvParams p,
             // ---- stage 0 was requested at the end of the previous tile (before its group sums) / before the loop ----
             // ---- E0: H1 = relu(acc[0,160)) -> R1 ----
             PAIR_WAIT(); QPROBE(ctx, 1);
-            epilogue_to_smem<true>(tl, hf * 80, 80, R1, row, hf * 10);
+            compact_to_tmem<true>(tl, hf * 80, 80, hf * T_H1B, 1.0f);              // in place: no shared-memory traffic for H1
             PAIR_SIGNAL(); QPROBE(ctx, 2);
             // ---- E1: mlp1_out = relu(acc[0,112)) -> R2 ----
             PAIR_WAIT(); QPROBE(ctx, 3);
             if (warp == 4 * ctx && lane == 0) mbar_arrive(ctx ? xfree1 : xfree0);      // H1 is dead: producers may write the next X
-            if (hf == 0) epilogue_to_smem<true>(tl, 0, 64, R2, row, 0);
-            else epilogue_to_smem<true>(tl, 64, 48, R2, row, 8);
+            if (hf == 0) epilogue_to_smem<true>(tl, T_D1, 64, R2, row, 0);
+            else epilogue_to_smem<true>(tl, T_D1 + 64, 48, R2, row, 8);
             PAIR_SIGNAL(); QPROBE(ctx, 4);                                         // stage 2 may start
             QPROBE(ctx, 12);
             // ---- group mean of mlp1_out over the humans of a group (sarl.py:42), replicated on the group's rows -> R1 ----
@@ -433,7 +439,8 @@ tc_rows_pair_kernel(EnvParams p,
                 }
             }
             QPROBE(ctx, 14);
-            PAIR_SIGNAL_TO(reqm_leader); QPROBE(ctx, 5);                           // stage 3 may start
+            PAIR_SIGNAL_TO(reqm_leader); QPROBE(ctx, 5);
+            if (dbg && blockIdx.x < 2 && rnd == 3 && ctx == 0 && lane == 0) dbg[192 + blockIdx.x * 8 + hf * 4 + q] = clock64();                           // stage 3 may start
             QPROBE(ctx, 6);
             // ---- E3: H3 = relu(acc[0,112)) -> R1 (hf 0) ; Ha1 = relu(acc[112,224)) -> R2 (hf 1) ----
             PAIR_WAIT(); QPROBE(ctx, 7);

@@ -249,6 +249,25 @@ __device__ __forceinline__ void mma_layer_2(uint32_t tmem_d, uint32_t a_base, ui
         mma_f16_2(tmem_d, ad, bd, idesc, (s > 0 || accumulate_first) ? 1u : 0u);
     }
 }
+// A operand from TMEM (each CTA of the pair supplies its own 128 lanes; 32-bit column c holds k = 2c, 2c+1)
+__device__ __forceinline__ void mma_f16_2_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-steps [s0, s1) of D[256 x N] (+)= A(TMEM, packed fp16 from column tmem_a) * B[N x K]^T; b_base = this CTA's N/2-row half
+__device__ __forceinline__ void mma_steps_2_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_base, int s0, int s1, int N,
+                                               bool accumulate_first)
+{
+    const uint32_t idesc = make_idesc_f16_m256(N);
+    const uint32_t b_lbo = (uint32_t)(N / 2) * 16;
+    for (int s = s0; s < s1; ++s) {
+        const uint64_t bd = make_desc(b_base + (uint32_t)s * 2 * b_lbo, b_lbo, 128);
+        mma_f16_2_ts(tmem_d, tmem_a + (uint32_t)(s - s0) * 8, bd, idesc, (s > s0 || accumulate_first) ? 1u : 0u);
+    }
+}
 __device__ __forceinline__ void commit_2(uint32_t mbar_saddr, uint16_t cta_mask)
 {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -415,6 +434,25 @@ template <bool RELU>
 __device__ __forceinline__ void compact_to_tmem(uint32_t tlane, int col_src, int ncols, int col_dst, float scale, bool ftz = false, int synth = 0)
 {
     int done = 0;
+    while (ncols - done >= 64) {          // two TMEM loads in flight per wait (a load + wait round trip is ~290 cycles)
+        uint32_t v[32], u[32], w[16];
+        ld32(tlane + col_src + done, v);
+        ld32(tlane + col_src + done + 32, u);
+        wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
+            w[j] = RELU ? pack_f16x2_relu(a, b) : pack_f16x2(a * scale, b * scale);
+        }
+        st16(tlane + col_dst + done / 2, w);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float a = __uint_as_float(u[2 * j]), b = __uint_as_float(u[2 * j + 1]);
+            w[j] = RELU ? pack_f16x2_relu(a, b) : pack_f16x2(a * scale, b * scale);
+        }
+        st16(tlane + col_dst + done / 2 + 16, w);
+        done += 64;
+    }
     while (ncols - done >= 32) {
         uint32_t v[32], w[16];
         ld32(tlane + col_src + done, v);
