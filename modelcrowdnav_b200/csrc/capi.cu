@@ -174,6 +174,9 @@ int cn_env_destroy(cn_env *env)
     void *ptrs[] = {env->state, env->time, env->human_v, env->action_xy, env->action_idx, env->reward, env->done,
                     env->info, env->dmin, env->next_obs, env->frozen, env->stage, env->step_ctr, env->accum_block};
     for (void *q : ptrs) if (q) cudaFree(q);
+    if (env->side_stream) cudaStreamDestroy(env->side_stream);
+    if (env->ev_fork) cudaEventDestroy(env->ev_fork);
+    if (env->ev_join) cudaEventDestroy(env->ev_join);
     delete env;
     return CN_OK;
 }
@@ -555,10 +558,25 @@ int cn_rollout_step(cn_policy *p, cn_env *env, int query_env, double epsilon, vo
     if (rc) return rc;
     CN_CUDA_CHECK(cudaSetDevice(p->device));
     cudaStream_t s = (cudaStream_t)stream;
-    if ((rc = cn_launch_orca(env, s))) return rc;
+    // query_env = 0: the lookahead propagates humans with their current velocity (cadrl.py:107-109) and never reads
+    // the ORCA result, so ORCA (a latency-bound 16 us kernel) runs on a forked stream beside the lookahead and joins
+    // before the env step.  Event fork/join keeps the whole step capturable in a CUDA graph.
+    const bool fork = !query_env;
+    if (fork) {
+        if (!env->side_stream) {
+            CN_CUDA_CHECK(cudaStreamCreateWithFlags(&env->side_stream, cudaStreamNonBlocking));
+            CN_CUDA_CHECK(cudaEventCreateWithFlags(&env->ev_fork, cudaEventDisableTiming));
+            CN_CUDA_CHECK(cudaEventCreateWithFlags(&env->ev_join, cudaEventDisableTiming));
+        }
+        CN_CUDA_CHECK(cudaEventRecord(env->ev_fork, s));
+        CN_CUDA_CHECK(cudaStreamWaitEvent(env->side_stream, env->ev_fork, 0));
+        if ((rc = cn_launch_orca(env, env->side_stream))) return rc;
+        CN_CUDA_CHECK(cudaEventRecord(env->ev_join, env->side_stream));
+    } else if ((rc = cn_launch_orca(env, s))) return rc;
     if (p->cfg.precision == CN_PREC_F16_TC) rc = cn_lookahead_tc(p, env, query_env, epsilon, s);
     else rc = cn_lookahead_f32(p, env, query_env, epsilon, s);
     if (rc) return rc;
+    if (fork) CN_CUDA_CHECK(cudaStreamWaitEvent(s, env->ev_join, 0));
     if ((rc = cn_launch_step(env, nullptr, 1, s))) return rc;
     if (env->p.auto_reset) rc = cn_launch_reset(env, 1, s);
     return rc;

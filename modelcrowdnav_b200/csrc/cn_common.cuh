@@ -65,6 +65,9 @@ struct cn_env {
     double *stage;        // device staging, E x A1 x 8 (AoS exchange layout)
     uint32_t *step_ctr;   // E: lookahead draws (epsilon-greedy Philox subsequence)
     int orca_valid;
+    // fork/join resources of cn_rollout_step: ORCA runs beside the lookahead when the lookahead does not read it
+    cudaStream_t side_stream;
+    cudaEvent_t ev_fork, ev_join;
 };
 
 struct SarlDims {

@@ -252,15 +252,32 @@ lookahead_values_kernel(EnvParams p, SarlWeightsDev W, SarlDims d, F32Plan pl, c
 }
 
 // first-strict-max argmax + reach_destination + epsilon-greedy (multi_human_rl.py:22-30,53-58)
-__global__ void argmax_kernel(EnvParams p, int A, const double *__restrict__ st, const uint8_t *__restrict__ frozen,
-                              const double *__restrict__ values, const double *__restrict__ actions, double epsilon,
-                              uint32_t *__restrict__ step_ctr, double *__restrict__ action_xy,
-                              int32_t *__restrict__ action_idx, int32_t *__restrict__ bad_flag)
+// One WARP per env: the A values of an env are one contiguous, coalesced read; lane l scans a = l, l + 32, ...
+// (ascending, strict >: the lowest index wins inside a lane), then a shuffle reduction keeps the larger value and,
+// on equal values, the lower index -- the reference's "first strict maximum".  NaN never wins; all-NaN -> best = -1.
+__global__ void __launch_bounds__(128)
+argmax_kernel(EnvParams p, int A, const double *__restrict__ st, const uint8_t *__restrict__ frozen,
+              const double *__restrict__ values, const double *__restrict__ actions, double epsilon,
+              uint32_t *__restrict__ step_ctr, double *__restrict__ action_xy,
+              int32_t *__restrict__ action_idx, int32_t *__restrict__ bad_flag)
 {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const EnvDims d = p.d;
-    if (e >= d.E || frozen[e]) return;
+    if (e >= d.E || frozen[e]) return;       // warp-uniform
+    double max_value = -INFINITY;
     int best = -1;
+    for (int a = lane; a < A; a += 32) {
+        const double v = values[(size_t)e * A + a];
+        if (v > max_value) { max_value = v; best = a; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, max_value, off);
+        const int ob = __shfl_xor_sync(0xffffffffu, best, off);
+        // a lane that saw only NaN / nothing has best = -1 and never wins; ties go to the lower action index
+        if (ob >= 0 && (best < 0 || ov > max_value || (ov == max_value && ob < best))) { max_value = ov; best = ob; }
+    }
+    if (lane != 0) return;
     // policy.py:43-49: norm((py - gy, px - gx)) < radius
     const bool reached = norm2d(st[st_idx(d, F_PY, 0, e)] - st[st_idx(d, F_GY, 0, e)],
                                 st[st_idx(d, F_PX, 0, e)] - st[st_idx(d, F_GX, 0, e)]) < st[st_idx(d, F_R, 0, e)];
@@ -273,14 +290,7 @@ __global__ void argmax_kernel(EnvParams p, int A, const double *__restrict__ st,
             step_ctr[e] += 1;
             if (rng.next() < epsilon) { best = min(A - 1, (int)(rng.next() * A)); random_pick = true; }
         }
-        if (!random_pick) {
-            double max_value = -INFINITY;
-            for (int a = 0; a < A; ++a) {
-                const double v = values[(size_t)e * A + a];
-                if (v > max_value) { max_value = v; best = a; }
-            }
-            if (best < 0) { atomicExch(bad_flag, 1); best = 0; }
-        }
+        if (!random_pick && best < 0) { atomicExch(bad_flag, 1); best = 0; }
     }
     action_idx[e] = best;
     action_xy[e] = actions[2 * best];
@@ -368,7 +378,7 @@ static int ensure_values(cn_policy *p, int E)
 int cn_lookahead_argmax(cn_policy *p, cn_env *env, double epsilon, cudaStream_t s)
 {
     const int E = env->p.d.E;
-    argmax_kernel<<<(E + 127) / 128, 128, 0, s>>>(env->p, p->d.A, env->state, env->frozen, p->values, p->action_dev,
+    argmax_kernel<<<(E + 3) / 4, 128, 0, s>>>(env->p, p->d.A, env->state, env->frozen, p->values, p->action_dev,
                                                     epsilon, env->step_ctr, env->action_xy, env->action_idx,
                                                     p->bad_flag);
     CN_LAUNCH_CHECK();
