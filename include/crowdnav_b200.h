@@ -70,6 +70,8 @@ typedef struct {
     int64_t env_id_offset;       /* global id of env 0 (rank * E): results do not depend on the GPU count */
     int32_t auto_reset;          /* 1: an env that finished an episode is re-generated at the end of the step */
     double gamma;                /* [rl] gamma, for the per-episode discounted return (explorer.py:124-125) */
+    int32_t randomize_attributes; /* [env] randomize_attributes: device resets draw v_pref ~ U(0.5,1.5) and radius ~
+                                   * U(0.3,0.5) per human before placing it (crowd_sim.py:167-168, agent.py:39-45) */
 } cn_env_cfg;
 
 /* SARL.configure (sarl.py:73-86) + CADRL.set_common_parameters (cadrl.py:64-73) */

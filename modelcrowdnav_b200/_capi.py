@@ -41,7 +41,7 @@ class EnvCfg(C.Structure):
                 ("circle_radius", C.c_double), ("square_width", C.c_double), ("human_radius", C.c_double),
                 ("human_v_pref", C.c_double), ("robot_radius", C.c_double), ("robot_v_pref", C.c_double),
                 ("seed", C.c_uint64), ("env_id_offset", C.c_int64), ("auto_reset", C.c_int32),
-                ("gamma", C.c_double)]
+                ("gamma", C.c_double), ("randomize_attributes", C.c_int32)]
 
 
 class SarlCfg(C.Structure):

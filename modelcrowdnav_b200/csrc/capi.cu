@@ -47,6 +47,7 @@ void cn_env_cfg_default(cn_env_cfg *c)
     c->sim_rule = CN_CIRCLE_CROSSING; c->circle_radius = 4; c->square_width = 10;
     c->human_radius = 0.3; c->human_v_pref = 1; c->robot_radius = 0.3; c->robot_v_pref = 1;
     c->seed = 0; c->env_id_offset = 0; c->auto_reset = 0; c->gamma = 0.9;
+    c->randomize_attributes = 0;
 }
 
 void cn_sarl_cfg_default(cn_sarl_cfg *c)
@@ -118,6 +119,7 @@ int cn_env_create(const cn_env_cfg *cfg, int device, cn_env **out)
     p.robot_radius = cfg->robot_radius; p.robot_v_pref = cfg->robot_v_pref;
     p.seed = cfg->seed; p.env_id_offset = cfg->env_id_offset; p.auto_reset = cfg->auto_reset;
     p.gamma = cfg->gamma;
+    p.randomize_attributes = cfg->randomize_attributes;
 
     const size_t E = p.d.E, H = p.d.H, A1 = p.d.A1;
 #define CN_ALLOC(ptr, bytes)                                                     \

@@ -35,6 +35,7 @@ struct EnvParams {
     int64_t env_id_offset;
     int auto_reset;
     double gamma;
+    int randomize_attributes;
 };
 
 // per-env episode accumulators (explorer.py:41-51,92-108,124-141)

@@ -343,16 +343,21 @@ __global__ void __launch_bounds__(128) reset_kernel(EnvParams p, double *__restr
     const int MAX_TRIES = 4096;
     for (int i = 1; i <= d.H; ++i) {
         double px = 0, py = 0, gx = 0, gy = 0;
+        double h_radius = p.human_radius, h_v_pref = p.human_v_pref;
+        if (p.randomize_attributes) {                       // agent.py:39-45, drawn before the position (crowd_sim.py:167-168)
+            h_v_pref = 0.5 + (1.5 - 0.5) * rng.next();
+            h_radius = 0.3 + (0.5 - 0.3) * rng.next();
+        }
         if (p.sim_rule == CN_CIRCLE_CROSSING) {
             for (int tries = 0; tries < MAX_TRIES; ++tries) {
                 const double angle = rng.next() * PI * 2;
-                const double px_noise = (rng.next() - 0.5) * p.human_v_pref;
-                const double py_noise = (rng.next() - 0.5) * p.human_v_pref;
+                const double px_noise = (rng.next() - 0.5) * h_v_pref;
+                const double py_noise = (rng.next() - 0.5) * h_v_pref;
                 px = p.circle_radius * cos(angle) + px_noise;
                 py = p.circle_radius * sin(angle) + py_noise;
                 bool collide = false;
                 for (int a = 0; a < i; ++a) {
-                    const double min_dist = p.human_radius + st[st_idx(d, F_R, a, e)] + p.discomfort_dist;
+                    const double min_dist = h_radius + st[st_idx(d, F_R, a, e)] + p.discomfort_dist;
                     if (norm2d(px - st[st_idx(d, F_PX, a, e)], py - st[st_idx(d, F_PY, a, e)]) < min_dist ||
                         norm2d(px - st[st_idx(d, F_GX, a, e)], py - st[st_idx(d, F_GY, a, e)]) < min_dist) {
                         collide = true;
@@ -370,7 +375,7 @@ __global__ void __launch_bounds__(128) reset_kernel(EnvParams p, double *__restr
                 bool collide = false;
                 for (int a = 0; a < i; ++a) {
                     if (norm2d(px - st[st_idx(d, F_PX, a, e)], py - st[st_idx(d, F_PY, a, e)]) <
-                        p.human_radius + st[st_idx(d, F_R, a, e)] + p.discomfort_dist) { collide = true; break; }
+                        h_radius + st[st_idx(d, F_R, a, e)] + p.discomfort_dist) { collide = true; break; }
                 }
                 if (!collide) break;
             }
@@ -380,7 +385,7 @@ __global__ void __launch_bounds__(128) reset_kernel(EnvParams p, double *__restr
                 bool collide = false;
                 for (int a = 0; a < i; ++a) {
                     if (norm2d(gx - st[st_idx(d, F_GX, a, e)], gy - st[st_idx(d, F_GY, a, e)]) <
-                        p.human_radius + st[st_idx(d, F_R, a, e)] + p.discomfort_dist) { collide = true; break; }
+                        h_radius + st[st_idx(d, F_R, a, e)] + p.discomfort_dist) { collide = true; break; }
                 }
                 if (!collide) break;
             }
@@ -388,7 +393,7 @@ __global__ void __launch_bounds__(128) reset_kernel(EnvParams p, double *__restr
         st[st_idx(d, F_PX, i, e)] = px; st[st_idx(d, F_PY, i, e)] = py;
         st[st_idx(d, F_VX, i, e)] = 0.0; st[st_idx(d, F_VY, i, e)] = 0.0;
         st[st_idx(d, F_GX, i, e)] = gx; st[st_idx(d, F_GY, i, e)] = gy;
-        st[st_idx(d, F_R, i, e)] = p.human_radius; st[st_idx(d, F_VPREF, i, e)] = p.human_v_pref;
+        st[st_idx(d, F_R, i, e)] = h_radius; st[st_idx(d, F_VPREF, i, e)] = h_v_pref;
     }
     time[e] = 0.0;
     frozen[e] = 0;

@@ -198,7 +198,8 @@ def batch_env_kwargs(env):
                 robot_visible=int(env.robot.visible) if env.robot is not None else 0,
                 circle_radius=env.circle_radius, square_width=env.square_width,
                 human_radius=cfg.getfloat("humans", "radius"), human_v_pref=cfg.getfloat("humans", "v_pref"),
-                robot_radius=cfg.getfloat("robot", "radius"), robot_v_pref=cfg.getfloat("robot", "v_pref"))
+                robot_radius=cfg.getfloat("robot", "radius"), robot_v_pref=cfg.getfloat("robot", "v_pref"),
+                randomize_attributes=int(bool(env.randomize_attributes)))
 
 
 class CrowdSim(object):
@@ -235,11 +236,12 @@ class CrowdSim(object):
             self.human_num = config.getint("sim", "human_num")
         else:
             raise NotImplementedError
-        if self.randomize_attributes:
-            raise NotImplementedError("randomize_attributes is outside the B200 hot path (SURVEY §8(f) rank 2)")
         self.case_counter = {"train": 0, "test": 0, "val": 0}
         logging.info("human number: {}".format(self.human_num))
-        logging.info("Not randomize human's radius and preferred speed")
+        if self.randomize_attributes:
+            logging.info("Randomize human's radius and preferred speed")
+        else:
+            logging.info("Not randomize human's radius and preferred speed")
         logging.info("Training simulation: {}, test simulation: {}".format(self.train_val_sim, self.test_sim))
         logging.info("Square width: {}, circle width: {}".format(self.square_width, self.circle_radius))
 
@@ -252,7 +254,8 @@ class CrowdSim(object):
         return dict(human_num=self.human_num, rule=rule, circle_radius=self.circle_radius,
                     square_width=self.square_width, human_radius=self.config.getfloat("humans", "radius"),
                     human_v_pref=self.config.getfloat("humans", "v_pref"), discomfort_dist=self.discomfort_dist,
-                    robot_radius=self.robot.radius, robot_v_pref=self.robot.v_pref)
+                    robot_radius=self.robot.radius, robot_v_pref=self.robot.v_pref,
+                    randomize_attributes=bool(self.randomize_attributes))
 
     def next_cases(self, phase, k, test_case=None):
         """Case ids the next k reset() calls would use (crowd_sim.py:269-270,285-294); advances the counter."""
@@ -291,7 +294,7 @@ class CrowdSim(object):
         self.robot.set(*[float(agents[0, i]) for i in (0, 1, 4, 5, 2, 3)], np.pi / 2)
         self.humans = [Human(self.config, "humans") for _ in range(self.human_num)]
         for h, row in zip(self.humans, agents[1:]):
-            h.set(*[float(row[i]) for i in (0, 1, 4, 5, 2, 3)], 0)
+            h.set(*[float(row[i]) for i in (0, 1, 4, 5, 2, 3)], 0, radius=float(row[6]), v_pref=float(row[7]))
         for agent in [self.robot] + self.humans:
             agent.time_step = self.time_step
             agent.policy.time_step = self.time_step

@@ -13,13 +13,21 @@ def _norm(a, b):
 
 
 def generate_scene(phase, case, human_num=5, rule="circle_crossing", circle_radius=4.0, square_width=10.0,
-                   human_radius=0.3, human_v_pref=1.0, discomfort_dist=0.2, robot_radius=0.3, robot_v_pref=1.0):
-    """Agents (H+1, 8) float64 [px py vx vy gx gy radius v_pref]; agent 0 = robot (crowd_sim.py:284)."""
+                   human_radius=0.3, human_v_pref=1.0, discomfort_dist=0.2, robot_radius=0.3, robot_v_pref=1.0,
+                   randomize_attributes=False):
+    """Agents (H+1, 8) float64 [px py vx vy gx gy radius v_pref]; agent 0 = robot (crowd_sim.py:284).
+    randomize_attributes ([env] randomize_attributes): each human first draws v_pref ~ U(0.5, 1.5) and
+    radius ~ U(0.3, 0.5) from the same stream (crowd_sim.py:167-168,190-191; agent.py:39-45)."""
     rs = np.random.RandomState(COUNTER_OFFSET[phase] + case)
     agents = np.zeros((human_num + 1, 8))
     agents[0] = [0, -circle_radius, 0, 0, 0, circle_radius, robot_radius, robot_v_pref]
+    base_radius, base_v_pref = human_radius, human_v_pref
     for i in range(1, human_num + 1):
         prev = agents[:i]
+        human_radius, human_v_pref = base_radius, base_v_pref
+        if randomize_attributes:
+            human_v_pref = rs.uniform(0.5, 1.5)
+            human_radius = rs.uniform(0.3, 0.5)
         if rule == "circle_crossing":
             while True:
                 angle = rs.random_sample() * np.pi * 2

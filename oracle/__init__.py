@@ -260,12 +260,19 @@ def _norm2(a, b):
 
 
 def generate_scene(phase, case, human_num=5, rule="circle_crossing", circle_radius=4.0, square_width=10.0,
-                   radius=0.3, v_pref=1.0, discomfort_dist=0.2, robot_radius=0.3, robot_v_pref=1.0):
-    """Agents (H+1, 8) f64 for (phase, case); agent 0 = robot at (0,-R) -> (0,R)."""
+                   radius=0.3, v_pref=1.0, discomfort_dist=0.2, robot_radius=0.3, robot_v_pref=1.0, randomize=False):
+    """Agents (H+1, 8) f64 for (phase, case); agent 0 = robot at (0,-R) -> (0,R).
+    randomize = [env] randomize_attributes: every human first draws v_pref ~ U(0.5, 1.5) and radius ~ U(0.3, 0.5)
+    (crowd_sim.py:167-168,190-191; agent.py:39-45), one legacy-uniform draw each."""
     rs = np.random.RandomState(COUNTER_OFFSET[phase] + case)      # crowd_sim.py:286
     agents = np.zeros((human_num + 1, AGENT_STRIDE))
     agents[0] = [0, -circle_radius, 0, 0, 0, circle_radius, robot_radius, robot_v_pref]  # crowd_sim.py:284
+    base_radius, base_v_pref = radius, v_pref
     for i in range(1, human_num + 1):
+        radius, v_pref = base_radius, base_v_pref
+        if randomize:
+            v_pref = rs.uniform(0.5, 1.5)
+            radius = rs.uniform(0.3, 0.5)
         if rule == "circle_crossing":                              # crowd_sim.py:165-186
             while True:
                 angle = rs.random_sample() * np.pi * 2

@@ -71,14 +71,15 @@ def load_flat_weights(model, flat):
     model.load_state_dict(new)
 
 
-def make_env_and_sarl(human_num=5, sim="circle_crossing", query_env=False, seed=0, robot_visible=False, weights=None):
+def make_env_and_sarl(human_num=5, sim="circle_crossing", query_env=False, seed=0, robot_visible=False, weights=None,
+                      randomize=False):
     """Reference CrowdSim + Robot + SARL wired as crowd_nav/test.py:52-87 does (holonomic honoured)."""
     install()
     import torch
     import gym
     from crowd_sim.envs.utils.robot import Robot
     from crowd_nav.policy.policy_factory import policy_factory
-    ecfg = env_config(human_num, sim, robot_visible)
+    ecfg = env_config(human_num, sim, robot_visible, env__randomize_attributes="true" if randomize else "false")
     policy = policy_factory["sarl"]()
     torch.manual_seed(seed)
     policy.configure(policy_config(query_env))

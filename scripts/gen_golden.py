@@ -129,6 +129,13 @@ TRAJ_SPECS = [
 ]
 
 
+# [env] randomize_attributes = true: heterogeneous human radii / preferred speeds (agent.py:39-45)
+TRAJ_SPECS_RANDOM = [
+    ("circle5_random", 5, "circle_crossing", False, False, [("test", 20, 30), ("test", 21, 30), ("train", 8, 30)], True),
+    ("square10_random", 10, "square_crossing", True, False, [("test", 22, 20)], True),
+]
+
+
 TRAJ_SPECS_TRAINED = [
     ("circle5_qfalse_trained", 5, "circle_crossing", False, False, [("test", 10, 60), ("test", 11, 60), ("test", 12, 60)]),
     ("circle5_qtrue_trained", 5, "circle_crossing", True, False, [("test", 13, 60)]),
@@ -136,11 +143,13 @@ TRAJ_SPECS_TRAINED = [
 
 
 def gen_trajectories(specs=None, weights=None):
-    for name, H, sim, qenv, vis, cases in (specs or TRAJ_SPECS):
+    for spec in (specs or TRAJ_SPECS):
+        name, H, sim, qenv, vis, cases = spec[:6]
+        randomize = bool(spec[6]) if len(spec) > 6 else False
         env, robot, policy = refshim.make_env_and_sarl(human_num=H, sim=sim, query_env=qenv, seed=0,
-                                                        robot_visible=vis, weights=weights)
+                                                        robot_visible=vis, weights=weights, randomize=randomize)
         out = {"H": np.array(H), "query_env": np.array(int(qenv)), "robot_visible": np.array(int(vis)),
-               "sim": np.array(sim)}
+               "sim": np.array(sim), "randomize": np.array(int(randomize))}
         t0 = time.time()
         for (phase, case, max_steps) in cases:
             rec = run_trajectory(env, robot, policy, phase, case, max_steps)
@@ -148,7 +157,7 @@ def gen_trajectories(specs=None, weights=None):
             for k, v in rec.items():
                 out[key + "/" + k] = v
             # scene pin: oracle generator == reference reset
-            scene = oracle.generate_scene(phase, case, human_num=H, rule=sim)
+            scene = oracle.generate_scene(phase, case, human_num=H, rule=sim, randomize=randomize)
             assert np.array_equal(scene, rec["agents"][0]), (name, key)
         out["cases"] = np.array(["%s_%d" % (p, c) for p, c, _ in cases])
         np.savez_compressed(os.path.join(GOLD, "traj_%s.npz" % name), **out)
@@ -198,6 +207,7 @@ if __name__ == "__main__":
     ap.add_argument("--episodes", action="store_true")
     ap.add_argument("--procs", type=int, default=6)
     ap.add_argument("--skip-units", action="store_true")
+    ap.add_argument("--random", action="store_true", help="only the randomize_attributes trajectories")
     ap.add_argument("--trained", action="store_true", help="use tests/golden/sarl_weights_trained.npy (GPU-trained SARL)")
     a = ap.parse_args()
     wtrained = os.path.join(GOLD, "sarl_weights_trained.npy")
@@ -206,9 +216,12 @@ if __name__ == "__main__":
     oracle.build()
     if a.episodes:
         gen_episodes(a.procs, wtrained if a.trained else None, "trained" if a.trained else "seed0")
+    elif a.random:
+        gen_trajectories(TRAJ_SPECS_RANDOM)
     elif a.trained:
         gen_trajectories(TRAJ_SPECS_TRAINED, np.load(wtrained))
     else:
         if not a.skip_units:
             gen_units()
         gen_trajectories()
+        gen_trajectories(TRAJ_SPECS_RANDOM)

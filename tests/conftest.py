@@ -35,7 +35,7 @@ def weights0():
 def load_traj(name):
     z = np.load(os.path.join(GOLDEN, "traj_%s.npz" % name), allow_pickle=False)
     out = {"H": int(z["H"]), "query_env": int(z["query_env"]), "robot_visible": int(z["robot_visible"]),
-           "sim": str(z["sim"]), "cases": {}}
+           "sim": str(z["sim"]), "randomize": int(z["randomize"]) if "randomize" in z.files else 0, "cases": {}}
     for case in z["cases"]:
         case = str(case)
         out["cases"][case] = {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith(case + "/")}
@@ -43,7 +43,8 @@ def load_traj(name):
 
 
 TRAJ_NAMES = ["circle5_qfalse", "circle5_qtrue", "circle5_visible", "square10_qfalse", "square10_qtrue",
-              "circle5_qfalse_trained", "circle5_qtrue_trained"]
+              "circle5_qfalse_trained", "circle5_qtrue_trained",
+              "circle5_random", "square10_random"]      # [env] randomize_attributes = true (heterogeneous humans)
 
 
 def weights_for(name):

@@ -74,11 +74,12 @@ def _cfg(text, **over):
     return cp
 
 
-def _setup(weights0, precision="f32", query_env=False, human_num=5, sim="circle_crossing"):
+def _setup(weights0, precision="f32", query_env=False, human_num=5, sim="circle_crossing", randomize=False):
     """Wire env, robot, policy, explorer exactly as crowd_nav/test.py:52-87 does."""
     import torch
     import modelcrowdnav_b200 as mcn
-    ecfg = _cfg(ENV_INI, sim__human_num=human_num, sim__train_val_sim=sim, sim__test_sim=sim)
+    ecfg = _cfg(ENV_INI, sim__human_num=human_num, sim__train_val_sim=sim, sim__test_sim=sim,
+                env__randomize_attributes="true" if randomize else "false")
     pcfg = _cfg(POLICY_INI, action_space__query_env="true" if query_env else "false")
     policy = mcn.policy_factory["sarl"]()
     policy.configure(pcfg)
@@ -110,14 +111,16 @@ def test_state_dict_keys_match_reference(weights0, units):
     assert np.array_equal(policy.flat_weights(), weights0)
 
 
-@pytest.mark.parametrize("name", ["circle5_qfalse", "circle5_qtrue", "circle5_qfalse_trained", "circle5_qtrue_trained"])
+@pytest.mark.parametrize("name", ["circle5_qfalse", "circle5_qtrue", "circle5_qfalse_trained", "circle5_qtrue_trained",
+                                  "circle5_random", "square10_random"])
 def test_facade_replays_reference_episode(name):
     """gym-style loop (explorer.py:53-69) through the single-env façade: ob/reward/done/info, action values and
     chosen actions equal the reference's, step by step, while the façade follows its own actions."""
     import modelcrowdnav_b200 as mcn
     tr = load_traj(name)
     weights0 = weights_for(name)
-    env, robot, policy, _ = _setup(weights0, "f32", query_env=bool(tr["query_env"]))
+    env, robot, policy, _ = _setup(weights0, "f32", query_env=bool(tr["query_env"]), human_num=tr["H"], sim=tr["sim"],
+                                   randomize=bool(tr["randomize"]))
     case = [c for c in tr["cases"] if c.startswith("test_")][0]
     rec = tr["cases"][case]
     ob = env.reset("test", int(case.split("_")[1]))

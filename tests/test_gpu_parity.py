@@ -372,3 +372,24 @@ def test_umma_pair_selftest(mcn, N, K):
                                               d.ctypes.data_as(C.c_void_p), 3, None, 0))
     ref = a.astype(np.float64) @ b.astype(np.float64).T
     assert np.max(np.abs(d - ref)) < 1e-4 * K
+
+
+@pytest.mark.parametrize("rule", [0, 1])
+def test_device_reset_randomize_attributes(mcn, rule):
+    """[env] randomize_attributes on the device generator: v_pref in [0.5, 1.5], radius in [0.3, 0.5], heterogeneous,
+    and the reference's separation rule holds with the per-human radii (crowd_sim.py:167-186, agent.py:39-45)."""
+    E, H = 512, 5
+    env = mcn.BatchedCrowdSim(E, H, seed=3, sim_rule=rule, randomize_attributes=1)
+    env.reset_device()
+    a, t = env.get_state()
+    r, vp = a[:, 1:, 6], a[:, 1:, 7]
+    assert np.all((r >= 0.3) & (r <= 0.5)) and np.all((vp >= 0.5) & (vp <= 1.5))
+    assert r.std() > 0.03 and vp.std() > 0.15
+    assert np.all(a[:, 0, 6] == 0.3) and np.all(a[:, 0, 7] == 1.0)          # the robot keeps its configured attributes
+    for i in range(1, H + 1):
+        for j in range(i):
+            dmin = a[:, i, 6] + a[:, j, 6] + 0.2
+            assert np.all(np.hypot(a[:, i, 0] - a[:, j, 0], a[:, i, 1] - a[:, j, 1]) >= dmin)
+            if rule == 1 or j > 0:
+                assert np.all(np.hypot(a[:, i, 4] - a[:, j, 4], a[:, i, 5] - a[:, j, 5]) >= dmin)
+    env.close()

@@ -96,3 +96,21 @@ def test_scene_known_answers(oracle_mod):
     sq = oracle_mod.generate_scene("test", 0, human_num=10, rule="square_crossing")
     assert tuple(sq[1, :2]) == (-0.57503471562202868, 4.5028286434902451)
     assert tuple(sq[1, 4:6]) == (2.4109570071399911, 3.7247453518203533)
+
+
+@pytest.mark.parametrize("name", ["circle5_random", "square10_random"])
+def test_randomized_scenes_match_reference(oracle_mod, name):
+    """[env] randomize_attributes: the reference's own reset() states (first record of every fixture case) against
+    both scene generators -- the oracle's and the product's host generator (same MT19937 stream, bit-exact)."""
+    from modelcrowdnav_b200 import scenes
+    tr = load_traj(name)
+    assert tr["randomize"] == 1
+    for case, rec in tr["cases"].items():
+        phase, idx = case.rsplit("_", 1)
+        ref = rec["agents"][0]
+        got = oracle_mod.generate_scene(phase, int(idx), human_num=tr["H"], rule=tr["sim"], randomize=True)
+        assert np.array_equal(got, ref), case
+        prod = scenes.generate_scene(phase, int(idx), human_num=tr["H"], rule=tr["sim"], randomize_attributes=True)
+        assert np.array_equal(prod, ref), case
+        assert np.all((ref[1:, 6] >= 0.3) & (ref[1:, 6] <= 0.5)) and np.all((ref[1:, 7] >= 0.5) & (ref[1:, 7] <= 1.5))
+        assert len(set(ref[1:, 6])) > 1
