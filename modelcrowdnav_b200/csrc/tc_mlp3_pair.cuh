@@ -3,24 +3,26 @@
 // quarters), warp 16 of the rank-0 CTA issues the UMMAs of the pair, warps 17 / 18 stream the joint-state tiles of
 // context 0 / 1 from HBM with TMA bulk copies.  Rows = (env, action); each CTA keeps HALF of the mlp3 weights (42 KB).
 //
-//   stage  UMMA (M=256 over the pair)     A operand          D           epilogue
-//   0      mlp3.0   K=80   N=160          J    (RA, by TMA)  [0,160)     ReLU -> U0 (RA, over the dead J tile)
-//   1      mlp3.2   K=160  N=112          U0   (RA)          [0,112)     ReLU -> U1 (RB)
-//   2      mlp3.4   K=112  N=112          U1   (RB)          [0,112)     mlp3.6 as an fp32 dot on ReLU(acc),
-//                                                                         value = reward + gamma_bar * V -> values[E][A]
+//   stage  UMMA (M=256 over the pair)     A operand            D           epilogue
+//   0      mlp3.0   K=80   N=160          J  (smem, by TMA)    [0,160)     ReLU -> U0, fp16 packed IN PLACE in TMEM
+//   1      mlp3.2   K=160  N=112          U0 (TMEM, TS mode)   [120,232)   ReLU -> U1, fp16 packed in place
+//   2      mlp3.4   K=112  N=112          U1 (TMEM, TS mode)   [0,112)     mlp3.6 as an fp32 dot on ReLU(acc),
+//                                                                           value = reward + gamma_bar * V -> values[E][A]
+// The activations never touch shared memory: each column-half warp packs its half of an accumulator in place
+// (U0: K 0..79 at [0,40), K 80..159 at [80,120); U1: K 0..63 at [120,152), K 64..111 at [184,208)).
 // Reference: crowd_nav/policy/sarl.py:62-64 (mlp3 on the joint state), multi_human_rl.py:52 (scoring).
 
 constexpr int kThreadsM3 = 608;
-constexpr int M3_CTX_COLS = 160;
+constexpr int M3_CTX_COLS = 256;
+constexpr int M3_D1 = 120;                // mlp3.2 accumulator [120,232)
 
 constexpr uint32_t HM_M1 = 0;                                        //  80 x 80
 constexpr uint32_t HM_M2 = HM_M1 + bytes_of(N_H1 / 2, K_J);          //  56 x 160
 constexpr uint32_t HM_M3 = HM_M2 + bytes_of(N_M1 / 2, N_H1);         //  56 x 112
 constexpr uint32_t IMG_HM_BYTES = HM_M3 + bytes_of(N_M1 / 2, N_M1);
 
-constexpr uint32_t M_RA_BYTES = bytes_of(ROWS, N_H1);                // 40 KB: J tile (20 KB) | U0
-constexpr uint32_t M_RB_BYTES = bytes_of(ROWS, N_M1);                // 28 KB: U1
-constexpr uint32_t M_CTX_BYTES = M_RA_BYTES + M_RB_BYTES;
+constexpr uint32_t M_RA_BYTES = J_TILE_BYTES;                        // 20 KB: J tile
+constexpr uint32_t M_CTX_BYTES = M_RA_BYTES;
 constexpr uint32_t M_CTX0 = (IMG_HM_BYTES + 127) & ~127u;
 constexpr uint32_t M_MISC = M_CTX0 + 2 * M_CTX_BYTES;                // S[2][128] f32 | 10 mbarriers | tmem slot
 constexpr uint32_t M_SMEM = M_MISC + 1024 + 96 + 16;
@@ -37,7 +39,6 @@ tc_mlp3_pair_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *_
     const uint32_t rank = cluster_ctarank();
     const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
     const int row = q * 32 + lane;
-    uint8_t *RA = smem + M_CTX0 + (uint32_t)ctx * M_CTX_BYTES, *RB = RA + M_RA_BYTES;
     float *S1 = reinterpret_cast<float *>(smem + M_MISC) + ctx * 128;       // partial dot of the upper column half
     const uint32_t bar0 = smem_u32(smem + M_MISC + 1024);
     const uint32_t req0 = bar0, req1 = bar0 + 8, done0 = bar0 + 16, done1 = bar0 + 24;
@@ -86,10 +87,15 @@ tc_mlp3_pair_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *_
                     ph ^= 1;
                     fence_after_sync();
                     const uint32_t tm = tmem + (uint32_t)c * M3_CTX_COLS;
-                    const uint32_t sRA = smem_u32(smem + M_CTX0 + (uint32_t)c * M_CTX_BYTES), sRB = sRA + M_RA_BYTES;
+                    const uint32_t sRA = smem_u32(smem + M_CTX0 + (uint32_t)c * M_CTX_BYTES);
                     if (s == 0) mma_layer_2(tm, sRA, ROWS, sM1, K_J, N_H1, false);
-                    else if (s == 1) mma_layer_2(tm, sRA, ROWS, sM2, N_H1, N_M1, false);
-                    else mma_layer_2(tm, sRB, ROWS, sM3, N_M1, N_M1, false);
+                    else if (s == 1) {
+                        mma_steps_2_ts(tm + M3_D1, tm, sM2, 0, 5, N_M1, false);                 // U0, K 0..79
+                        mma_steps_2_ts(tm + M3_D1, tm + 80, sM2, 5, 10, N_M1, true);            // U0, K 80..159
+                    } else {
+                        mma_steps_2_ts(tm, tm + M3_D1, sM3, 0, 4, N_M1, false);                 // U1, K 0..63
+                        mma_steps_2_ts(tm, tm + M3_D1 + 64, sM3, 4, 7, N_M1, true);             // U1, K 64..111
+                    }
                     commit_2(c ? done1 : done0, 3);
                     ++stage;
                     t_last = clock64();
@@ -107,7 +113,7 @@ tc_mlp3_pair_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *_
             int tile = (cluster_id * 2 + (int)rank) * 2 + c;
             uint32_t phf = 0, phl = 0;
             for (int rnd = 0; rnd < rounds; ++rnd, tile += tile_stride) {
-                if (rnd > 0) { mbar_wait_guarded(xfree, phf); phf ^= 1; }              // stage 1 of the previous tile is complete: U0 is dead
+                if (rnd > 0) { mbar_wait_guarded(xfree, phf); phf ^= 1; }              // stage 0 of the previous tile is complete: its J tile is dead
                 bulk_load(dst, J + (size_t)tile * J_TILE_BYTES, J_TILE_BYTES, xl);
                 mbar_wait_guarded(xl, phl); phl ^= 1;
                 mbar_arrive_cluster(xfull_leader);
@@ -125,12 +131,12 @@ tc_mlp3_pair_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *_
         M3_SIGNAL();                                                               // stage 0 of the first tile
         for (int rnd = 0; rnd < rounds; ++rnd, tile += tile_stride) {
             M3_WAIT();
-            epilogue_to_smem<true>(tl, hf * 80, 80, RA, row, hf * 10);             // U0 over the dead J tile
+            if (warp == 4 * ctx && lane == 0) mbar_arrive(ctx ? xfree1 : xfree0);  // J is dead: the next J tile may land
+            compact_to_tmem<true>(tl, hf * 80, 80, hf * 80, 1.0f);                 // U0, packed in place
             M3_SIGNAL();
             M3_WAIT();
-            if (warp == 4 * ctx && lane == 0) mbar_arrive(ctx ? xfree1 : xfree0);  // U0 is dead: the next J tile may land
-            if (hf == 0) epilogue_to_smem<true>(tl, 0, 64, RB, row, 0);
-            else epilogue_to_smem<true>(tl, 64, 48, RB, row, 8);
+            if (hf == 0) compact_to_tmem<true>(tl, M3_D1, 64, M3_D1, 1.0f);        // U1, packed in place
+            else compact_to_tmem<true>(tl, M3_D1 + 64, 48, M3_D1 + 64, 1.0f);
             M3_SIGNAL();
             M3_WAIT();
             // mlp3.6 as an fp32 dot over ReLU(mlp3.4), split over the column halves
