@@ -393,3 +393,29 @@ def test_device_reset_randomize_attributes(mcn, rule):
             if rule == 1 or j > 0:
                 assert np.all(np.hypot(a[:, i, 4] - a[:, j, 4], a[:, i, 5] - a[:, j, 5]) >= dmin)
     env.close()
+
+
+@pytest.mark.parametrize("E,H,speeds,rots", [(1000, 4, 3, 8), (777, 6, 5, 16), (130, 13, 2, 5)])
+def test_tc_matches_f32_odd_shapes(mcn, weights0, E, H, speeds, rots):
+    """Tile bookkeeping of the CTA-pair kernels on sizes that divide nothing (env count, humans per group, action
+    count): the tensor-core values against the FP32 CUDA-core path (itself checked against the oracle) on evolving
+    device-generated states."""
+    env = mcn.BatchedCrowdSim(E, H, auto_reset=1, seed=5, sim_rule=1)
+    p32 = mcn.BatchedSARL(precision="f32", speed_samples=speeds, rotation_samples=rots)
+    p16 = mcn.BatchedSARL(precision="f16_tc", speed_samples=speeds, rotation_samples=rots)
+    p32.load_weights(weights0); p16.load_weights(weights0)
+    assert p16.A == speeds * rots + 1
+    env.reset_device()
+    agree = total = 0
+    for step in range(4):
+        env.orca()
+        p32.lookahead(env, 0); b32, v32 = p32.read(env)
+        p16.lookahead(env, 0); b16, v16 = p16.read(env)
+        assert v16.shape == (E, p16.A)
+        assert np.max(np.abs(v32 - v16)) <= 1e-3 * max(1.0, np.max(np.abs(v32)))
+        srt = np.sort(v32, axis=1)
+        clear = (srt[:, -1] - srt[:, -2]) > 2e-4
+        total += int(clear.sum()); agree += int((b32[clear] == b16[clear]).sum())
+        env.step(update=True, read=False)
+    assert total == 0 or agree / total >= 0.999, (agree, total)
+    env.close(); p32.close(); p16.close()
