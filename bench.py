@@ -240,17 +240,18 @@ def main():
     barrier()
 
     # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region ----
-    buf = mcn.HostStepBuffers(env, pinned=True)
+    # (packed blocks: one H2D of the state, one D2H of new state + reward + done + info + action per step)
+    buf = mcn.PackedHostStepBuffers(env)
     a0, t0 = env.get_state()
     buf.agents_in[...] = a0; buf.times_in[...] = t0
     for _ in range(2):
-        mcn.rollout_step_host(pol, env, buf, a.query_env)
+        mcn.rollout_step_host_packed(pol, env, buf, a.query_env)
         buf.swap()
     barrier()
     ne = max(5, min(a.steps, 30))
     te0 = time.perf_counter()
     for _ in range(ne):
-        mcn.rollout_step_host(pol, env, buf, a.query_env)
+        mcn.rollout_step_host_packed(pol, env, buf, a.query_env)
         buf.swap()                                   # next step's input = the host state just downloaded (no host copy)
     barrier()
     e2e_s = time.perf_counter() - te0

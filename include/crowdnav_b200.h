@@ -200,6 +200,14 @@ int cn_rollout_step_host(cn_policy *p, cn_env *env, int query_env, double epsilo
                          const double *times_in, double *agents_out, double *times_out, double *reward,
                          uint8_t *done, uint8_t *info, int32_t *action_idx, void *stream);
 
+/* Same with ONE host->device and ONE device->host copy per step through packed blocks (pinned memory recommended):
+ *   host_in : [agents E x (H+1) x 8 f64 | times E f64]                                      cn_host_step_bytes(env, 0)
+ *   host_out: [agents | times | reward E f64 | action_idx E i32 | done E u8 | info E u8]      cn_host_step_bytes(env, 1)
+ * The prefix of an output block is a valid input block, so a host loop can ping-pong two blocks without copying. */
+int cn_rollout_step_host_packed(cn_policy *p, cn_env *env, int query_env, double epsilon, const void *host_in,
+                                void *host_out, void *stream);
+int64_t cn_host_step_bytes(const cn_env *env, int out);
+
 /* Number of kernels this library launched so far in this process. */
 int64_t cn_launch_count(void);
 

@@ -219,6 +219,47 @@ class HostStepBuffers(object):
         self.times_in, self.times_out = self.times_out, self.times_in
 
 
+class PackedHostStepBuffers(object):
+    """Two pinned packed exchange blocks for ``rollout_step_host_packed`` (one H2D + one D2H copy per step).
+    ``agents_in / times_in`` view the input block; ``agents_out, times_out, reward, action_idx, done, info`` view the
+    output block; ``swap()`` makes the state just downloaded the next input without copying it."""
+
+    def __init__(self, env):
+        import torch
+        self.E, self.A1 = env.E, env.H + 1
+        self.in_bytes = int(env.lib.cn_host_step_bytes(env.handle, 0))
+        self.out_bytes = int(env.lib.cn_host_step_bytes(env.handle, 1))
+        nb = (self.out_bytes + 15) // 16 * 16
+        self._blocks = [torch.empty(nb, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+        self._views(0, 1)
+        self.h2d_bytes, self.d2h_bytes = self.in_bytes, self.out_bytes
+
+    def _views(self, i, o):
+        E, A1 = self.E, self.A1
+        self._in, self._out = i, o
+        bi, bo = self._blocks[i].numpy(), self._blocks[o].numpy()
+        n = E * A1 * 8
+        self.agents_in = bi[:8 * n].view(np.float64).reshape(E, A1, 8)
+        self.times_in = bi[8 * n:8 * (n + E)].view(np.float64)
+        self.agents_out = bo[:8 * n].view(np.float64).reshape(E, A1, 8)
+        self.times_out = bo[8 * n:8 * (n + E)].view(np.float64)
+        off = 8 * (n + E)
+        self.reward = bo[off:off + 8 * E].view(np.float64); off += 8 * E
+        self.action_idx = bo[off:off + 4 * E].view(np.int32); off += 4 * E
+        self.done = bo[off:off + E]; off += E
+        self.info = bo[off:off + E]
+        self.in_ptr, self.out_ptr = self._blocks[i].data_ptr(), self._blocks[o].data_ptr()
+
+    def swap(self):
+        self._views(self._out, self._in)
+
+
+def rollout_step_host_packed(policy, env, buf, query_env=False, epsilon=0.0, stream=None):
+    """One lookahead + env step through the packed host blocks: ONE H2D copy, kernels, ONE D2H copy (blocking)."""
+    check(policy.lib.cn_rollout_step_host_packed(policy.handle, env.handle, int(bool(query_env)), float(epsilon),
+                                                 C.c_void_p(buf.in_ptr), C.c_void_p(buf.out_ptr), _stream(stream)))
+
+
 def rollout_step_host(policy, env, buf, query_env=False, epsilon=0.0, stream=None):
     """One lookahead + env step through host buffers: H2D state, kernels, D2H results (blocking)."""
     check(policy.lib.cn_rollout_step_host(policy.handle, env.handle, int(bool(query_env)), float(epsilon),

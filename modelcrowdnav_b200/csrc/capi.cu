@@ -176,6 +176,7 @@ int cn_env_destroy(cn_env *env)
     void *ptrs[] = {env->state, env->time, env->human_v, env->action_xy, env->action_idx, env->reward, env->done,
                     env->info, env->dmin, env->next_obs, env->frozen, env->stage, env->step_ctr, env->accum_block};
     for (void *q : ptrs) if (q) cudaFree(q);
+    if (env->io_block) cudaFree(env->io_block);
     if (env->side_stream) cudaStreamDestroy(env->side_stream);
     if (env->ev_fork) cudaEventDestroy(env->ev_fork);
     if (env->ev_join) cudaEventDestroy(env->ev_join);
@@ -609,6 +610,32 @@ int cn_rollout_step_host(cn_policy *p, cn_env *env, int query_env, double epsilo
     if (done) CN_CUDA_CHECK(cudaMemcpyAsync(done, env->done, E, cudaMemcpyDeviceToHost, s));
     if (info) CN_CUDA_CHECK(cudaMemcpyAsync(info, env->info, E, cudaMemcpyDeviceToHost, s));
     if (action_idx) CN_CUDA_CHECK(cudaMemcpyAsync(action_idx, env->action_idx, sizeof(int32_t) * E, cudaMemcpyDeviceToHost, s));
+    CN_CUDA_CHECK(cudaStreamSynchronize(s));
+    return CN_OK;
+}
+
+int64_t cn_host_step_bytes(const cn_env *env, int out)
+{
+    if (!env) return 0;
+    const int64_t E = env->p.d.E, A1 = env->p.d.A1;
+    const int64_t in = 8 * (E * A1 * F_COUNT + E);
+    return out ? in + 8 * E + 4 * E + E + E : in;
+}
+
+int cn_rollout_step_host_packed(cn_policy *p, cn_env *env, int query_env, double epsilon, const void *host_in, void *host_out,
+                                void *stream)
+{
+    int rc = check_pair(p, env);
+    if (rc) return rc;
+    if (!host_in || !host_out) { cn_set_error("host_in / host_out must not be null"); return CN_EINVAL; }
+    CN_CUDA_CHECK(cudaSetDevice(p->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!env->io_block) CN_CUDA_CHECK(cudaMalloc((void **)&env->io_block, (size_t)cn_host_step_bytes(env, 1) + 16));
+    CN_CUDA_CHECK(cudaMemcpyAsync(env->io_block, host_in, (size_t)cn_host_step_bytes(env, 0), cudaMemcpyHostToDevice, s));
+    if ((rc = cn_launch_io(env, env->io_block, 1, s))) return rc;          // keeps the per-episode accumulators
+    if ((rc = cn_rollout_step(p, env, query_env, epsilon, s))) return rc;
+    if ((rc = cn_launch_io(env, env->io_block, 0, s))) return rc;
+    CN_CUDA_CHECK(cudaMemcpyAsync(host_out, env->io_block, (size_t)cn_host_step_bytes(env, 1), cudaMemcpyDeviceToHost, s));
     CN_CUDA_CHECK(cudaStreamSynchronize(s));
     return CN_OK;
 }

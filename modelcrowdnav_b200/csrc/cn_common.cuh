@@ -69,6 +69,7 @@ struct cn_env {
     // fork/join resources of cn_rollout_step: ORCA runs beside the lookahead when the lookahead does not read it
     cudaStream_t side_stream;
     cudaEvent_t ev_fork, ev_join;
+    double *io_block;     // device image of the packed host exchange block (cn_rollout_step_host_packed), lazily allocated
 };
 
 struct SarlDims {
@@ -189,6 +190,7 @@ int cn_launch_robot_orca(cn_env *env, double safety_space, cudaStream_t s);
 int cn_launch_step(cn_env *env, const double *action_xy_dev, int update, cudaStream_t s);
 int cn_launch_reset(cn_env *env, int only_done, cudaStream_t s);
 int cn_launch_pack(cn_env *env, int to_soa, cudaStream_t s);  // stage (AoS) <-> state (SoA)
+int cn_launch_io(cn_env *env, double *blk, int unpack, cudaStream_t s);   // packed host exchange block <-> device state
 int cn_launch_stats_reduce(cn_env *env, cn_stats *out_dev_as_host, int reset, cudaStream_t s);
 
 int cn_lookahead_f32(cn_policy *p, cn_env *env, int query_env, double epsilon, cudaStream_t s);

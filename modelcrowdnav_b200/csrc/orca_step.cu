@@ -415,6 +415,42 @@ __global__ void pack_kernel(EnvDims d, double *__restrict__ st, double *__restri
     }
 }
 
+// Packed host exchange block (cn_rollout_step_host_packed):  [agents E x A1 x 8 f64 | times E f64 | reward E f64 |
+// action_idx E i32 | done E u8 | info E u8]; the input block is its first two segments.
+__global__ void io_unpack_kernel(EnvDims d, double *__restrict__ st, double *__restrict__ time, const double *__restrict__ blk)
+{
+    const size_t n = (size_t)d.E * d.A1 * F_COUNT;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n + d.E; i += (size_t)gridDim.x * blockDim.x) {
+        if (i >= n) { time[i - n] = blk[i]; continue; }
+        const int e = (int)(i % d.E);
+        const size_t r = i / d.E;
+        const int a = (int)(r % d.A1), f = (int)(r / d.A1);
+        st[i] = blk[((size_t)e * d.A1 + a) * F_COUNT + f];
+    }
+}
+
+__global__ void io_pack_kernel(EnvDims d, const double *__restrict__ st, const double *__restrict__ time,
+                               const double *__restrict__ reward, const int32_t *__restrict__ action_idx,
+                               const uint8_t *__restrict__ done, const uint8_t *__restrict__ info, double *__restrict__ blk)
+{
+    const size_t n = (size_t)d.E * d.A1 * F_COUNT;
+    int32_t *b_idx = reinterpret_cast<int32_t *>(blk + n + 2 * (size_t)d.E);
+    uint8_t *b_done = reinterpret_cast<uint8_t *>(b_idx + d.E), *b_info = b_done + d.E;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n + d.E; i += (size_t)gridDim.x * blockDim.x) {
+        if (i >= n) {
+            const size_t e = i - n;
+            blk[n + e] = time[e];
+            blk[n + d.E + e] = reward[e];
+            b_idx[e] = action_idx[e]; b_done[e] = done[e]; b_info[e] = info[e];
+            continue;
+        }
+        const int e = (int)(i % d.E);
+        const size_t r = i / d.E;
+        const int a = (int)(r % d.A1), f = (int)(r / d.A1);
+        blk[((size_t)e * d.A1 + a) * F_COUNT + f] = st[i];
+    }
+}
+
 __global__ void clear_episode_kernel(int E, uint8_t *frozen, EnvAccum acc, uint8_t *done)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -511,6 +547,21 @@ int cn_launch_pack_keep(cn_env *env, cudaStream_t s)
     pack_kernel<<<grid, 256, 0, s>>>(env->p.d, env->state, env->stage, 1);
     CN_LAUNCH_CHECK();
     env->orca_valid = 0;
+    return CN_OK;
+}
+
+int cn_launch_io(cn_env *env, double *blk, int unpack, cudaStream_t s)
+{
+    const size_t n = (size_t)env->p.d.E * env->p.d.A1 * F_COUNT + env->p.d.E;
+    int grid = (int)((n + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (unpack) {
+        io_unpack_kernel<<<grid, 256, 0, s>>>(env->p.d, env->state, env->time, blk);
+        env->orca_valid = 0;
+    } else {
+        io_pack_kernel<<<grid, 256, 0, s>>>(env->p.d, env->state, env->time, env->reward, env->action_idx, env->done, env->info, blk);
+    }
+    CN_LAUNCH_CHECK();
     return CN_OK;
 }
 

@@ -419,3 +419,28 @@ def test_tc_matches_f32_odd_shapes(mcn, weights0, E, H, speeds, rots):
         env.step(update=True, read=False)
     assert total == 0 or agree / total >= 0.999, (agree, total)
     env.close(); p32.close(); p16.close()
+
+
+def test_packed_host_step_matches_device_step(mcn, oracle_mod, weights0):
+    """cn_rollout_step_host_packed (one H2D + one D2H per step, ping-ponged pinned blocks) == the device-resident step."""
+    E, H = 40, 5
+    agents = _scenes(oracle_mod, E, H, "circle_crossing", phase="val")
+    env_a = mcn.BatchedCrowdSim(E, H); env_b = mcn.BatchedCrowdSim(E, H)
+    pol = mcn.BatchedSARL(precision="f32"); pol.load_weights(weights0)
+    env_a.set_state(agents)
+    env_b.set_state(agents)            # initialises env_b's episode bookkeeping like a reset would
+    buf = mcn.PackedHostStepBuffers(env_b)
+    assert buf.in_bytes == 8 * (E * (H + 1) * 8 + E) and buf.out_bytes == buf.in_bytes + 14 * E
+    buf.agents_in[...] = agents; buf.times_in[...] = 0
+    for step in range(5):
+        mcn.rollout_step(pol, env_a)
+        ra, da, ia, _ = env_a.read_outputs()
+        ba = env_a.read_actions()[0] if hasattr(env_a, "read_actions") else None
+        mcn.rollout_step_host_packed(pol, env_b, buf)
+        sa, ta = env_a.get_state()
+        assert np.array_equal(sa, buf.agents_out) and np.array_equal(ta, buf.times_out)
+        assert np.array_equal(ra, buf.reward) and np.array_equal(da, buf.done) and np.array_equal(ia, buf.info)
+        if ba is not None:
+            assert np.array_equal(np.asarray(ba).reshape(-1), buf.action_idx)
+        buf.swap()
+    env_a.close(); env_b.close(); pol.close()
