@@ -146,7 +146,9 @@ struct Philox {
     {
         uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
         uint32_t k0 = key[0], k1 = key[1];
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
         for (int r = 0; r < 10; ++r) {
             uint32_t hi0, lo0, hi1, lo1;
             mulhilo(0xD2511F53u, c0, hi0, lo0);

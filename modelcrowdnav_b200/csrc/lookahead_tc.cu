@@ -170,95 +170,12 @@ __device__ __forceinline__ void row_features(const RowIn &in, double dt, uint4 &
     c3 = make_uint4(h2(lo[8], lo[9]), h2(lo[10], lo[11]), h2(lo[12], 0.0f), 0u);
 }
 
-// Per (env, action) group: lookahead reward -> rew[g]; self-state part of the joint state -> J chunks 7..9.
-// Runs on the upper 128 threads (warps 4..7): thread (gl, h) evaluates human h's clearance, a named barrier
-// joins the 128 threads, then thread gl < G folds the H clearances through the reward ladder.  "Break on the first
-// collision" (crowd_sim.py:360-363, multi_human_rl.py:71-73) only matters for dmin, which is unused once any
-// clearance is negative, so min/any over all humans is the same result.
-__device__ __forceinline__ void group_work(const EnvParams &p, const double *__restrict__ st,
-                                           const double *__restrict__ time, const double *__restrict__ human_v,
-                                           const double *__restrict__ actions, int A, int query_env, int NG, int G,
-                                           int tile, int t2, int gl, int h, double *__restrict__ D,
-                                           uint8_t *__restrict__ J, double *__restrict__ rew)
-{
-    const EnvDims ed = p.d;
-    const int H = ed.H;
-    const double dt = p.time_step;
-    {
-        const int g = tile * G + gl;
-        double clear = INFINITY;
-        if (gl < G && g < NG) {
-            const int e = g / A, a = g - e * A;
-            auto ag = [&](int f, int agent) { return st[st_idx(ed, f, agent, e)]; };
-            const double ax = actions[2 * a], ay = actions[2 * a + 1];
-            const double rpx = ag(F_PX, 0), rpy = ag(F_PY, 0), rr = ag(F_R, 0);
-            if (query_env) {
-                // crowd_sim.py:347-359: relative segment over the step, human's CURRENT velocity
-                const double px = ag(F_PX, h + 1) - rpx, py = ag(F_PY, h + 1) - rpy;
-                const double vx = ag(F_VX, h + 1) - ax, vy = ag(F_VY, h + 1) - ay;
-                const double ex = px + vx * dt, ey = py + vy * dt;
-                clear = cn_point_to_segment_dist0(px, py, ex, ey) - ag(F_R, h + 1) - rr;
-            } else {
-                // multi_human_rl.py:69-70: end-point distance with constant-velocity humans
-                const double npx = rpx + ax * dt, npy = rpy + ay * dt;
-                const double nhx = ag(F_PX, h + 1) + ag(F_VX, h + 1) * dt, nhy = ag(F_PY, h + 1) + ag(F_VY, h + 1) * dt;
-                clear = norm2d(npx - nhx, npy - nhy) - rr - ag(F_R, h + 1);
-            }
-        }
-        D[t2] = clear;
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    const int g = tile * G + t2;
-    if (t2 < G && g < NG) {
-        const int e = g / A, a = g - e * A;
-        auto ag = [&](int f, int agent) { return st[st_idx(ed, f, agent, e)]; };
-        const double ax = actions[2 * a], ay = actions[2 * a + 1];
-        const double rpx = ag(F_PX, 0), rpy = ag(F_PY, 0), rr = ag(F_R, 0), rgx = ag(F_GX, 0), rgy = ag(F_GY, 0);
-        double dmin = INFINITY;
-        bool collision = false;
-        for (int k = 0; k < H; ++k) {
-            const double c = D[t2 * H + k];
-            if (c < 0) collision = true;
-            else if (c < dmin) dmin = c;
-        }
-        const double npx = rpx + ax * dt, npy = rpy + ay * dt;
-        const bool reaching_goal = norm2d(npx - rgx, npy - rgy) < rr;
-        double reward;
-        if (query_env) {                                                                 // crowd_sim.py:382-403
-            if (time[e] >= p.time_limit - 1) reward = 0;
-            else if (collision) reward = p.collision_penalty;
-            else if (reaching_goal) reward = p.success_reward;
-            else if (dmin < p.discomfort_dist) reward = (dmin - p.discomfort_dist) * p.discomfort_penalty_factor * dt;
-            else reward = 0;
-        } else {                                                                         // multi_human_rl.py:77-86
-            if (collision) reward = -0.25;
-            else if (reaching_goal) reward = 1;
-            else if (dmin < 0.2) reward = (dmin - 0.2) * 0.5 * dt;
-            else reward = 0;
-        }
-        rew[g] = reward;
-        // self state = rotated row columns 0..5 (sarl.py:36): dg, v_pref, theta(0), radius, vx', vy'
-        float s[14], o[13];
-        s[0] = (float)npx; s[1] = (float)npy; s[2] = (float)ax; s[3] = (float)ay;
-        s[4] = (float)rr; s[5] = (float)rgx; s[6] = (float)rgy; s[7] = (float)ag(F_VPREF, 0); s[8] = 0.0f;
-        s[9] = s[10] = s[11] = s[12] = s[13] = 0.0f;
-        cn_rotate(s, o);
-        float hi[6], lo[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) split_hl(o[k], hi[k], lo[k]);
-        uint8_t *jt = J + (size_t)(g >> 7) * J_TILE_BYTES;
-        const int rb = g & 127;
-        *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 7)) =
-            make_uint4(h2(hi[0], hi[1]), h2(hi[2], hi[3]), h2(hi[4], hi[5]), h2(1.0f, 1.0f));
-        *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 8)) =
-            make_uint4(h2(lo[0], lo[1]), h2(lo[2], lo[3]), h2(lo[4], lo[5]), 0u);
-        *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 9)) = make_uint4(0, 0, 0, 0);
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");   // D is reused (it aliases the score scratch)
-}
-
-// Split form of group_work used by tc_rows_kernel: the SoA loads are issued one MMA wait earlier than the
-// arithmetic, and the self-state chunks are written by the h == 0 ROW thread (it already holds them).
+// Lookahead reward per (env, action) group, on the upper 128 threads (warps 4..7) of tc_rows_kernel: thread (gl, h)
+// evaluates human h's clearance, a named barrier joins the 128 threads, then thread gl < G folds the H clearances
+// through the reward ladder.  "Break on the first collision" (crowd_sim.py:360-363, multi_human_rl.py:71-73) only
+// matters for dmin, which is unused once any clearance is negative, so min/any over all humans is the same result.
+// The SoA loads (group_load) are issued one MMA wait earlier than the arithmetic (group_compute); the self-state
+// chunks are written by the h == 0 ROW thread (row_features_j).
 struct GrpIn {
     double rpx, rpy, rr, hpx, hpy, cvx, cvy, hr, ax, ay;   // role (gl, h): clearance of human h
     double gax, gay, gpx, gpy, grr, ggx, ggy, gt;          // role group t2 < G: reward ladder

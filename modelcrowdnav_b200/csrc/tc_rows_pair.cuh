@@ -85,7 +85,7 @@ __device__ __forceinline__ void pp_load_inputs(RowInPP &in, const EnvDims &ed, c
     in.ax = actions[2 * a]; in.ay = actions[2 * a + 1];
 }
 
-// clearance of this row's human for the lookahead reward (see group_work for the equivalence with the
+// clearance of this row's human for the lookahead reward (see group_compute in lookahead_tc.cu for the equivalence with the
 // reference's break-on-first-collision loops)
 __device__ __forceinline__ double pp_clearance(const RowInPP &in, double dt, int query_env)
 {
@@ -147,7 +147,7 @@ __device__ __forceinline__ void pair_features(const RowInPP &in, double dt, uint
     c3 = make_uint4(h2(lo[8], lo[9]), h2(lo[10], lo[11]), h2(lo[12], 0.0f), 0u);
 }
 
-// lookahead reward of one (env, action) group from the H clearances in D (see group_work for the equivalence
+// lookahead reward of one (env, action) group from the H clearances in D (see group_compute in lookahead_tc.cu for the equivalence
 // with the reference's break-on-first-collision loops)
 __device__ __forceinline__ double pair_reward(const EnvParams &p, const RowInPP &in, const double *__restrict__ D, int H,
                                               int query_env)
