@@ -93,6 +93,16 @@ def lib():
                                     C.c_int, dp, C.c_int, dp, C.c_double, dp, ip]
         L.orc_lookahead.restype = C.c_int
         L.orc_transform.argtypes = [C.c_int, dp, fp]
+        L.orc_action_space_k.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, dp]
+        L.orc_action_space_k.restype = C.c_int
+        L.orc_rotate_k.argtypes = [fp, C.c_int, fp]
+        L.orc_step_outcome_k.argtypes = [C.POINTER(EnvCfg), C.c_int, dp, C.c_double, C.c_int, C.c_double, C.c_double,
+                                         C.c_double, dp, ip, ip, dp]
+        L.orc_apply_step_k.argtypes = [C.POINTER(EnvCfg), C.c_int, dp, dp, C.c_int, dp, C.c_double, C.c_double, dp]
+        L.orc_lookahead_k.argtypes = [C.POINTER(EnvCfg), C.POINTER(SarlCfg), fp, C.c_int, dp, C.c_double, C.c_int,
+                                      C.c_double, C.c_int, dp, C.c_int, dp, C.c_double, dp, ip]
+        L.orc_lookahead_k.restype = C.c_int
+        L.orc_transform_k.argtypes = [C.c_int, dp, C.c_int, C.c_double, fp]
         L.orc_batch_lookahead_step.argtypes = [C.POINTER(EnvCfg), C.POINTER(SarlCfg), fp, C.c_int, C.c_int,
                                                dp, dp, C.c_int, dp, C.c_int, C.c_double,
                                                C.POINTER(C.c_int32), dp, C.POINTER(C.c_uint8),
@@ -157,38 +167,45 @@ def robot_orca_action(cfg, agents, safety_space):
     return out
 
 
-def step_outcome(cfg, agents, global_time, action):
+# robot kinematics (crowdnav_oracle.h): HOLONOMIC = ActionXY; UNICYCLE = ActionRot + heading feature; NONE = the fork's
+# literal behaviour (cadrl.py:66 commented out): ActionRot dynamics, heading feature left at zero
+KIN_HOLONOMIC, KIN_UNICYCLE, KIN_NONE = 0, 1, 2
+
+
+def step_outcome(cfg, agents, global_time, action, kinematics=KIN_HOLONOMIC, theta=0.0):
+    """action = (vx, vy) holonomic, (v, r) otherwise; theta = robot heading before the step."""
     agents = _f64(agents)
     r, dmin = C.c_double(), C.c_double()
     done, info = C.c_int(), C.c_int()
-    lib().orc_step_outcome(C.byref(cfg), agents.shape[0] - 1, _dp(agents), float(global_time),
-                           float(action[0]), float(action[1]), C.byref(r), C.byref(done), C.byref(info),
-                           C.byref(dmin))
+    lib().orc_step_outcome_k(C.byref(cfg), agents.shape[0] - 1, _dp(agents), float(global_time), int(kinematics),
+                             float(theta), float(action[0]), float(action[1]), C.byref(r), C.byref(done),
+                             C.byref(info), C.byref(dmin))
     return r.value, bool(done.value), info.value, dmin.value
 
 
-def apply_step(cfg, agents, global_time, action, human_vxy):
-    """In-place update of ``agents``; returns the new global time."""
+def apply_step(cfg, agents, global_time, action, human_vxy, kinematics=KIN_HOLONOMIC, theta=None):
+    """In-place update of ``agents``; returns the new global time (and the new heading when ``theta`` is given)."""
     assert agents.dtype == np.float64 and agents.flags.c_contiguous
     t = C.c_double(float(global_time))
+    th = C.c_double(float(theta if theta is not None else 0.0))
     hv = _f64(human_vxy)
-    lib().orc_apply_step(C.byref(cfg), agents.shape[0] - 1, _dp(agents), C.byref(t), float(action[0]),
-                         float(action[1]), _dp(hv))
-    return t.value
+    lib().orc_apply_step_k(C.byref(cfg), agents.shape[0] - 1, _dp(agents), C.byref(t), int(kinematics), C.byref(th),
+                           float(action[0]), float(action[1]), _dp(hv))
+    return t.value if theta is None else (t.value, th.value)
 
 
-def action_space(v_pref=1.0, speed_samples=5, rotation_samples=16):
+def action_space(v_pref=1.0, speed_samples=5, rotation_samples=16, kinematics=KIN_HOLONOMIC):
     out = np.empty((speed_samples * rotation_samples + 1, 2), np.float64)
-    n = lib().orc_action_space(float(v_pref), speed_samples, rotation_samples, _dp(out))
+    n = lib().orc_action_space_k(float(v_pref), speed_samples, rotation_samples, int(kinematics), _dp(out))
     assert n == out.shape[0]
     return out
 
 
-def rotate(rows14):
+def rotate(rows14, kinematics=KIN_HOLONOMIC):
     rows14 = _f32(rows14).reshape(-1, 14)
     out = np.empty((rows14.shape[0], 13), np.float32)
     for i in range(rows14.shape[0]):
-        lib().orc_rotate(_fp(rows14[i]), _fp(out[i]))
+        lib().orc_rotate_k(_fp(rows14[i]), int(kinematics), _fp(out[i]))
     return out
 
 
@@ -213,22 +230,23 @@ def sarl_forward(scfg, weights, x, return_attention=False):
     return (float(v), attn) if return_attention else float(v)
 
 
-def lookahead(ecfg, scfg, weights, agents, global_time, actions, query_env, human_vxy, gamma=0.9):
+def lookahead(ecfg, scfg, weights, agents, global_time, actions, query_env, human_vxy, gamma=0.9,
+              kinematics=KIN_HOLONOMIC, theta=0.0):
     agents = _f64(agents); actions = _f64(actions); weights = _f32(weights)
     hv = _f64(human_vxy if human_vxy is not None else np.zeros((agents.shape[0] - 1, 2)))
     values = np.full(actions.shape[0], np.nan)
     reached = C.c_int()
-    best = lib().orc_lookahead(C.byref(ecfg), C.byref(scfg), _fp(weights), agents.shape[0] - 1, _dp(agents),
-                               float(global_time), actions.shape[0], _dp(actions), int(query_env), _dp(hv),
-                               float(gamma), _dp(values), C.byref(reached))
+    best = lib().orc_lookahead_k(C.byref(ecfg), C.byref(scfg), _fp(weights), agents.shape[0] - 1, _dp(agents),
+                                 float(global_time), int(kinematics), float(theta), actions.shape[0], _dp(actions),
+                                 int(query_env), _dp(hv), float(gamma), _dp(values), C.byref(reached))
     return best, values, bool(reached.value)
 
 
-def transform(agents):
+def transform(agents, kinematics=KIN_HOLONOMIC, theta=0.0):
     agents = _f64(agents)
     H = agents.shape[0] - 1
     out = np.empty((H, 13), np.float32)
-    lib().orc_transform(H, _dp(agents), _fp(out))
+    lib().orc_transform_k(H, _dp(agents), int(kinematics), float(theta), _fp(out))
     return out
 
 

@@ -302,6 +302,40 @@ void orc_robot_orca_action(const orc_env_cfg *cfg, int H, const double *agents, 
 }
 
 /* crowd_sim.py:344-403 */
+/* Robot action -> the velocity the reference's non-holonomic branches use for collision checking and for
+ * compute_position: v * cos(theta + r), v * sin(theta + r) (crowd_sim.py:353-354, agent.py:115-117).  Holonomic
+ * actions are already velocities. */
+static void effective_velocity(int kinematics, double theta, double a0, double a1, double *ax, double *ay)
+{
+    if (kinematics == ORC_KIN_HOLONOMIC) { *ax = a0; *ay = a1; }
+    else { *ax = a0 * cos(a1 + theta); *ay = a0 * sin(a1 + theta); }
+}
+
+void orc_step_outcome_k(const orc_env_cfg *cfg, int H, const double *agents, double global_time, int kinematics,
+                        double theta, double a0, double a1, double *reward, int *done, int *info, double *dmin_out)
+{
+    double ax, ay;
+    effective_velocity(kinematics, theta, a0, a1, &ax, &ay);
+    orc_step_outcome(cfg, H, agents, global_time, ax, ay, reward, done, info, dmin_out);
+}
+
+/* agent.py:122-135 for the robot + crowd_sim.py:414-417 for the humans.  Non-holonomic: the position moves with the
+ * velocity of the UNWRAPPED heading theta + r, the stored velocity uses the heading wrapped to [0, 2 pi). */
+void orc_apply_step_k(const orc_env_cfg *cfg, int H, double *agents, double *global_time, int kinematics,
+                      double *theta, double a0, double a1, const double *human_vxy)
+{
+    double ax, ay;
+    effective_velocity(kinematics, *theta, a0, a1, &ax, &ay);
+    orc_apply_step(cfg, H, agents, global_time, ax, ay, human_vxy);
+    if (kinematics != ORC_KIN_HOLONOMIC) {
+        double t = fmod(*theta + a1, 2 * 3.141592653589793);      /* Python float %: result takes the divisor's sign */
+        if (t < 0) t += 2 * 3.141592653589793;
+        *theta = t;
+        AG(0, F_VX) = a0 * cos(t);
+        AG(0, F_VY) = a0 * sin(t);
+    }
+}
+
 void orc_step_outcome(const orc_env_cfg *cfg, int H, const double *agents, double global_time,
                       double ax, double ay, double *reward, int *done, int *info, double *dmin_out)
 {
@@ -371,6 +405,39 @@ int orc_action_space(double v_pref, int speed_samples, int rotation_samples, dou
         }
     }
     return n;
+}
+
+/* cadrl.py:82-102 for any kinematics: holonomic -> (vx, vy) as above; otherwise ActionRot (v, r) with
+ * r in np.linspace(-pi/4, pi/4, R) (endpoint included: step = (stop - start) / (R - 1), last sample = stop). */
+int orc_action_space_k(double v_pref, int speed_samples, int rotation_samples, int kinematics, double *out)
+{
+    if (kinematics == ORC_KIN_HOLONOMIC) return orc_action_space(v_pref, speed_samples, rotation_samples, out);
+    const double E_ = 2.718281828459045, PI = 3.141592653589793;
+    int n = 1;
+    out[0] = 0; out[1] = 0;
+    const double start = -PI / 4, stop = PI / 4;
+    const int div = rotation_samples - 1;
+    const double step = div > 0 ? (stop - start) / div : 0.0;
+    for (int r = 0; r < rotation_samples; ++r) {
+        double rotation = start + r * step;                  /* numpy: arange(0, num) * step + start */
+        if (div > 0 && r == rotation_samples - 1) rotation = stop;   /* numpy sets y[-1] = stop */
+        for (int sidx = 0; sidx < speed_samples; ++sidx) {
+            out[2 * n] = (exp((double)(sidx + 1) / speed_samples) - 1) / (E_ - 1) * v_pref;
+            out[2 * n + 1] = rotation;
+            ++n;
+        }
+    }
+    return n;
+}
+
+/* cadrl.py:217-252 with the theta slot of the 'unicycle' branch (cadrl.py:236-237): theta - rot in float32 */
+void orc_rotate_k(const float *s, int kinematics, float *o)
+{
+    orc_rotate(s, o);
+    if (kinematics == ORC_KIN_UNICYCLE) {
+        const float dx = s[5] - s[0], dy = s[6] - s[1];
+        o[2] = s[8] - atan2f(dy, dx);
+    }
 }
 
 /* cadrl.py:217-252, torch float32 ops; theta slot is zero (cadrl.py:238-240) */
@@ -533,6 +600,22 @@ float orc_sarl_forward(const orc_sarl_cfg *c, const float *weights, int H, const
     return v;
 }
 
+void orc_transform_k(int H, const double *agents, int kinematics, double theta, float *out)
+{
+    for (int h = 1; h <= H; ++h) {
+        float row[14];
+        row[0] = (float)AG(0, F_PX); row[1] = (float)AG(0, F_PY);
+        row[2] = (float)AG(0, F_VX); row[3] = (float)AG(0, F_VY);
+        row[4] = (float)AG(0, F_R);  row[5] = (float)AG(0, F_GX);
+        row[6] = (float)AG(0, F_GY); row[7] = (float)AG(0, F_VPREF);
+        row[8] = (float)theta;
+        row[9] = (float)AG(h, F_PX); row[10] = (float)AG(h, F_PY);
+        row[11] = (float)AG(h, F_VX); row[12] = (float)AG(h, F_VY);
+        row[13] = (float)AG(h, F_R);
+        orc_rotate_k(row, kinematics, out + (size_t)(h - 1) * 13);
+    }
+}
+
 /* multi_human_rl.py:90-104 */
 void orc_transform(int H, const double *agents, float *out)
 {
@@ -552,8 +635,8 @@ void orc_transform(int H, const double *agents, float *out)
 
 /* multi_human_rl.py:11-63 (greedy branch) */
 static int lookahead_prepared(const orc_env_cfg *ecfg, const orc_sarl_cfg *scfg, const sarl_prep *P, int H,
-                  const double *agents, double global_time, int A, const double *actions, int query_env,
-                  const double *human_vxy, double gamma, double *values_out, int *reached)
+                  const double *agents, double global_time, int kinematics, double theta, int A, const double *actions,
+                  int query_env, const double *human_vxy, double gamma, double *values_out, int *reached)
 {
     if (reached) *reached = 0;
     /* policy.py:43-49 reach_destination: norm((py-gy, px-gx)) < radius */
@@ -568,8 +651,10 @@ static int lookahead_prepared(const orc_env_cfg *ecfg, const orc_sarl_cfg *scfg,
     double nhx[ORC_MAXH], nhy[ORC_MAXH], nhvx[ORC_MAXH], nhvy[ORC_MAXH], hr[ORC_MAXH];
     float x[ORC_MAXH * 13];
     for (int a = 0; a < A; ++a) {
-        const double ax = actions[2 * a], ay = actions[2 * a + 1];
-        /* propagate robot (cadrl.py:113-117) */
+        /* propagate robot (cadrl.py:113-125): non-holonomic actions are (v, r), next_theta = theta + r */
+        double ax, ay;
+        effective_velocity(kinematics, theta, actions[2 * a], actions[2 * a + 1], &ax, &ay);
+        const double next_theta = kinematics == ORC_KIN_HOLONOMIC ? theta : theta + actions[2 * a + 1];
         const double npx = AG(0, F_PX) + ax * dt, npy = AG(0, F_PY) + ay * dt;
         double reward;
         for (int h = 1; h <= H; ++h) {
@@ -590,10 +675,10 @@ static int lookahead_prepared(const orc_env_cfg *ecfg, const orc_sarl_cfg *scfg,
             float row[14];
             row[0] = (float)npx; row[1] = (float)npy; row[2] = (float)ax; row[3] = (float)ay;
             row[4] = (float)AG(0, F_R); row[5] = (float)AG(0, F_GX); row[6] = (float)AG(0, F_GY);
-            row[7] = (float)AG(0, F_VPREF); row[8] = (float)1.5707963267948966;
+            row[7] = (float)AG(0, F_VPREF); row[8] = (float)next_theta;
             row[9] = (float)nhx[h]; row[10] = (float)nhy[h]; row[11] = (float)nhvx[h];
             row[12] = (float)nhvy[h]; row[13] = (float)hr[h];
-            orc_rotate(row, x + (size_t)h * 13);
+            orc_rotate_k(row, kinematics, x + (size_t)h * 13);
         }
         const double v = (double)sarl_forward_prepared(scfg, P, H, x, NULL);
         const double value = reward + gamma_bar * v;
@@ -609,7 +694,20 @@ int orc_lookahead(const orc_env_cfg *ecfg, const orc_sarl_cfg *scfg, const float
 {
     sarl_prep P;
     sarl_prepare(scfg, weights, &P);
-    const int r = lookahead_prepared(ecfg, scfg, &P, H, agents, global_time, A, actions, query_env,
+    const int r = lookahead_prepared(ecfg, scfg, &P, H, agents, global_time, ORC_KIN_HOLONOMIC, 0.0, A, actions,
+                                     query_env, human_vxy, gamma, values_out, reached);
+    free(P.store);
+    return r;
+}
+
+int orc_lookahead_k(const orc_env_cfg *ecfg, const orc_sarl_cfg *scfg, const float *weights, int H,
+                    const double *agents, double global_time, int kinematics, double theta, int A,
+                    const double *actions, int query_env, const double *human_vxy, double gamma, double *values_out,
+                    int *reached)
+{
+    sarl_prep P;
+    sarl_prepare(scfg, weights, &P);
+    const int r = lookahead_prepared(ecfg, scfg, &P, H, agents, global_time, kinematics, theta, A, actions, query_env,
                                      human_vxy, gamma, values_out, reached);
     free(P.store);
     return r;
@@ -630,7 +728,7 @@ void orc_batch_lookahead_step(const orc_env_cfg *ecfg, const orc_sarl_cfg *scfg,
         double hv[ORC_MAXH * 2], values[ORC_NUM_ACTIONS_MAX];
         orc_human_actions(ecfg, H, agents, hv);
         int reached;
-        int best = lookahead_prepared(ecfg, scfg, &P, H, agents, global_time[e], A, actions, query_env,
+        int best = lookahead_prepared(ecfg, scfg, &P, H, agents, global_time[e], ORC_KIN_HOLONOMIC, 0.0, A, actions, query_env,
                                       hv, gamma, values, &reached);
         if (best < 0) best = 0;
         action_idx[e] = best;

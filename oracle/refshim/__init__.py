@@ -72,7 +72,7 @@ def load_flat_weights(model, flat):
 
 
 def make_env_and_sarl(human_num=5, sim="circle_crossing", query_env=False, seed=0, robot_visible=False, weights=None,
-                      randomize=False):
+                      randomize=False, kinematics="holonomic"):
     """Reference CrowdSim + Robot + SARL wired as crowd_nav/test.py:52-87 does (holonomic honoured)."""
     install()
     import torch
@@ -83,7 +83,9 @@ def make_env_and_sarl(human_num=5, sim="circle_crossing", query_env=False, seed=
     policy = policy_factory["sarl"]()
     torch.manual_seed(seed)
     policy.configure(policy_config(query_env))
-    policy.kinematics = "holonomic"                        # policy.config:14 honoured (cadrl.py:66 quirk)
+    # kinematics="holonomic": policy.config:14 honoured.  kinematics=None: the fork as shipped -- cadrl.py:66 comments the
+    # config read out, so policy.kinematics stays None (ActionRot dynamics, theta feature zero).  "unicycle": explicit.
+    policy.kinematics = kinematics
     if weights is not None:
         load_flat_weights(policy.get_model(), weights)
     env = gym.make("CrowdSim-v0")

@@ -25,6 +25,14 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 INFO_CODE = {"Nothing": 0, "Danger": 1, "ReachGoal": 2, "Collision": 3, "Timeout": 4}
 
 
+KIN_CODE = {"holonomic": 0, "unicycle": 1, None: 2}
+
+
+def action_pair(a):
+    """(vx, vy) of an ActionXY, (v, r) of an ActionRot."""
+    return [a.vx, a.vy] if hasattr(a, "vx") else [a.v, a.r]
+
+
 def agents_of(env):
     rows = []
     for a in [env.robot] + env.humans:
@@ -36,21 +44,23 @@ def run_trajectory(env, robot, policy, phase, case, max_steps=None):
     """Teacher-forced record of one episode driven exactly like explorer.py:53-69."""
     ob = env.reset(phase, case)
     rec = dict(agents=[], time=[], human_v=[], values=[], best=[], reward=[], done=[], info=[], dmin=[],
-               action=[])
+               action=[], theta=[])
     done = False
     steps = 0
     table = None
     while not done and (max_steps is None or steps < max_steps):
         rec["agents"].append(agents_of(env))
         rec["time"].append(env.global_time)
+        rec["theta"].append(float(env.robot.theta))
         action = robot.act(ob)
         if table is None:
-            table = np.array([[a.vx, a.vy] for a in policy.action_space])
+            table = np.array([action_pair(a) for a in policy.action_space])
         vals = np.array(policy.action_values, dtype=np.float64)
         rec["values"].append(vals)
-        best = int(np.argmin(np.abs(table[:, 0] - action.vx) + np.abs(table[:, 1] - action.vy)))
+        ap = action_pair(action)
+        best = int(np.argmin(np.abs(table[:, 0] - ap[0]) + np.abs(table[:, 1] - ap[1])))
         rec["best"].append(best)
-        rec["action"].append([action.vx, action.vy])
+        rec["action"].append(ap)
         before = agents_of(env)
         ob, reward, done, info = env.step(action)
         after = agents_of(env)
@@ -136,6 +146,15 @@ TRAJ_SPECS_RANDOM = [
 ]
 
 
+# robot kinematics other than the honoured holonomic: None = the fork exactly as shipped (cadrl.py:66), "unicycle" explicit
+TRAJ_SPECS_KIN = [
+    ("circle5_kin_none", 5, "circle_crossing", False, False, [("test", 30, 40), ("test", 31, 40), ("train", 5, 40)], False, None),
+    ("circle5_kin_none_qtrue", 5, "circle_crossing", True, False, [("test", 32, 30)], False, None),
+    ("circle5_unicycle", 5, "circle_crossing", False, False, [("test", 33, 40), ("test", 34, 40)], False, "unicycle"),
+    ("square10_unicycle_qtrue", 10, "square_crossing", True, False, [("test", 35, 20)], False, "unicycle"),
+]
+
+
 TRAJ_SPECS_TRAINED = [
     ("circle5_qfalse_trained", 5, "circle_crossing", False, False, [("test", 10, 60), ("test", 11, 60), ("test", 12, 60)]),
     ("circle5_qtrue_trained", 5, "circle_crossing", True, False, [("test", 13, 60)]),
@@ -146,10 +165,12 @@ def gen_trajectories(specs=None, weights=None):
     for spec in (specs or TRAJ_SPECS):
         name, H, sim, qenv, vis, cases = spec[:6]
         randomize = bool(spec[6]) if len(spec) > 6 else False
+        kinematics = spec[7] if len(spec) > 7 else "holonomic"
         env, robot, policy = refshim.make_env_and_sarl(human_num=H, sim=sim, query_env=qenv, seed=0,
-                                                        robot_visible=vis, weights=weights, randomize=randomize)
+                                                        robot_visible=vis, weights=weights, randomize=randomize,
+                                                        kinematics=kinematics)
         out = {"H": np.array(H), "query_env": np.array(int(qenv)), "robot_visible": np.array(int(vis)),
-               "sim": np.array(sim), "randomize": np.array(int(randomize))}
+               "sim": np.array(sim), "randomize": np.array(int(randomize)), "kinematics": np.array(KIN_CODE[kinematics])}
         t0 = time.time()
         for (phase, case, max_steps) in cases:
             rec = run_trajectory(env, robot, policy, phase, case, max_steps)
@@ -208,6 +229,7 @@ if __name__ == "__main__":
     ap.add_argument("--procs", type=int, default=6)
     ap.add_argument("--skip-units", action="store_true")
     ap.add_argument("--random", action="store_true", help="only the randomize_attributes trajectories")
+    ap.add_argument("--kinematics", action="store_true", help="only the kinematics = None / unicycle trajectories")
     ap.add_argument("--trained", action="store_true", help="use tests/golden/sarl_weights_trained.npy (GPU-trained SARL)")
     a = ap.parse_args()
     wtrained = os.path.join(GOLD, "sarl_weights_trained.npy")
@@ -218,6 +240,8 @@ if __name__ == "__main__":
         gen_episodes(a.procs, wtrained if a.trained else None, "trained" if a.trained else "seed0")
     elif a.random:
         gen_trajectories(TRAJ_SPECS_RANDOM)
+    elif a.kinematics:
+        gen_trajectories(TRAJ_SPECS_KIN)
     elif a.trained:
         gen_trajectories(TRAJ_SPECS_TRAINED, np.load(wtrained))
     else:
@@ -225,3 +249,4 @@ if __name__ == "__main__":
             gen_units()
         gen_trajectories()
         gen_trajectories(TRAJ_SPECS_RANDOM)
+        gen_trajectories(TRAJ_SPECS_KIN)

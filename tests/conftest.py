@@ -35,7 +35,8 @@ def weights0():
 def load_traj(name):
     z = np.load(os.path.join(GOLDEN, "traj_%s.npz" % name), allow_pickle=False)
     out = {"H": int(z["H"]), "query_env": int(z["query_env"]), "robot_visible": int(z["robot_visible"]),
-           "sim": str(z["sim"]), "randomize": int(z["randomize"]) if "randomize" in z.files else 0, "cases": {}}
+           "sim": str(z["sim"]), "randomize": int(z["randomize"]) if "randomize" in z.files else 0,
+           "kinematics": int(z["kinematics"]) if "kinematics" in z.files else 0, "cases": {}}
     for case in z["cases"]:
         case = str(case)
         out["cases"][case] = {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith(case + "/")}
@@ -45,6 +46,8 @@ def load_traj(name):
 TRAJ_NAMES = ["circle5_qfalse", "circle5_qtrue", "circle5_visible", "square10_qfalse", "square10_qtrue",
               "circle5_qfalse_trained", "circle5_qtrue_trained",
               "circle5_random", "square10_random"]      # [env] randomize_attributes = true (heterogeneous humans)
+# robot kinematics: None = the fork exactly as shipped (ActionRot dynamics, theta feature zero), unicycle explicit
+TRAJ_NAMES_KIN = ["circle5_kin_none", "circle5_kin_none_qtrue", "circle5_unicycle", "square10_unicycle_qtrue"]
 
 
 def weights_for(name):

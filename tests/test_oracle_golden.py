@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import TRAJ_NAMES, load_traj, weights_for
+from conftest import TRAJ_NAMES, TRAJ_NAMES_KIN, load_traj, weights_for
 
 
 def test_action_space_matches_reference(oracle_mod, units):
@@ -46,7 +46,7 @@ def test_value_network(oracle_mod, units, weights0, H):
     assert np.max(np.abs(got - ref)) <= 1e-5 * max(1.0, np.max(np.abs(ref)))
 
 
-@pytest.mark.parametrize("name", TRAJ_NAMES)
+@pytest.mark.parametrize("name", TRAJ_NAMES + TRAJ_NAMES_KIN)
 def test_trajectories(oracle_mod, weights0, name):
     """Teacher-forced, step by step: ORCA velocities, outcome ladder, state update, 81 values, argmax."""
     o = oracle_mod
@@ -56,14 +56,18 @@ def test_trajectories(oracle_mod, weights0, name):
     ecfg = o.EnvCfg.default(robot_visible=tr["robot_visible"])
     scfg = o.SarlCfg.default()
     n_steps = 0
+    kin = tr["kinematics"]
     for case, rec in tr["cases"].items():
         table = rec["table"]
+        assert np.array_equal(table, o.action_space(1.0, 5, 16, kinematics=kin))       # bit-exact, any kinematics
         for t in range(len(rec["time"])):
             agents = np.ascontiguousarray(rec["agents"][t])
             gt = float(rec["time"][t])
+            theta = float(rec["theta"][t]) if "theta" in rec else 0.0
             hv = o.human_actions(ecfg, agents)
             assert np.array_equal(hv, rec["human_v"][t]), (case, t)
-            best, values, reached = o.lookahead(ecfg, scfg, weights0, agents, gt, table, tr["query_env"], hv)
+            best, values, reached = o.lookahead(ecfg, scfg, weights0, agents, gt, table, tr["query_env"], hv,
+                                                kinematics=kin, theta=theta)
             assert not reached
             ref_v = rec["values"][t]
             assert np.max(np.abs(values - ref_v)) <= 1e-5 * max(1.0, np.max(np.abs(ref_v))), (case, t)
@@ -71,14 +75,16 @@ def test_trajectories(oracle_mod, weights0, name):
             if top2[1] - top2[0] > 1e-5:
                 assert best == int(rec["best"][t]), (case, t)
             a = table[int(rec["best"][t])]
-            r, done, info, dmin = o.step_outcome(ecfg, agents, gt, a)
+            r, done, info, dmin = o.step_outcome(ecfg, agents, gt, a, kinematics=kin, theta=theta)
             assert r == rec["reward"][t] and done == bool(rec["done"][t]) and info == int(rec["info"][t])
             if info == o.DANGER:
                 assert dmin == rec["dmin"][t]
             if t + 1 < len(rec["time"]):
-                nt = o.apply_step(ecfg, agents, gt, a, hv)
+                nt, nth = o.apply_step(ecfg, agents, gt, a, hv, kinematics=kin, theta=theta)
                 assert nt == rec["time"][t + 1]
                 assert np.array_equal(agents, rec["agents"][t + 1]), (case, t)
+                if "theta" in rec:
+                    assert nth == rec["theta"][t + 1], (case, t)
             n_steps += 1
     assert n_steps >= 20
 
