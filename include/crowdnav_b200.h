@@ -33,6 +33,13 @@ extern "C" {
 #define CN_AGENT_STRIDE 8     /* px py vx vy gx gy radius v_pref */
 #define CN_MAX_NEIGHBORS 16   /* ORCA max_neighbors supported by the kernel (reference: 10) */
 #define CN_MAX_HUMANS 64
+/* Robot kinematics.  HOLONOMIC: ActionXY (vx, vy) -- [action_space] kinematics = holonomic.  UNICYCLE: ActionRot (v, r),
+ * r in [-pi/4, pi/4], robot heading theta in the state and in rotate().  NONE: the fork exactly as shipped -- cadrl.py:66
+ * comments the config read out, so policy.kinematics stays None: ActionRot dynamics (every `== 'holonomic'` test fails)
+ * while rotate() leaves the heading feature at zero (its test is `== 'unicycle'`). */
+#define CN_KIN_HOLONOMIC 0
+#define CN_KIN_UNICYCLE 1
+#define CN_KIN_NONE 2
 #define CN_MAX_ACTIONS 128
 
 /* info codes = crowd_sim/envs/utils/info.py:1-38 */
@@ -72,6 +79,7 @@ typedef struct {
     double gamma;                /* [rl] gamma, for the per-episode discounted return (explorer.py:124-125) */
     int32_t randomize_attributes; /* [env] randomize_attributes: device resets draw v_pref ~ U(0.5,1.5) and radius ~
                                    * U(0.3,0.5) per human before placing it (crowd_sim.py:167-168, agent.py:39-45) */
+    int32_t robot_kinematics;    /* CN_KIN_*: how CrowdSim.step reads the robot action (crowd_sim.py:350-354, agent.py:110-135) */
 } cn_env_cfg;
 
 /* SARL.configure (sarl.py:73-86) + CADRL.set_common_parameters (cadrl.py:64-73) */
@@ -87,6 +95,8 @@ typedef struct {
     double gamma;                /* 0.9 */
     double v_pref;               /* robot v_pref used to build the action table (cadrl.py:147) */
     int32_t precision;           /* CN_PREC_* */
+    int32_t kinematics;          /* CN_KIN_*: action space of CADRL.build_action_space (cadrl.py:82-102) and the theta
+                                  * feature of rotate() (cadrl.py:236-240); must equal the env's robot_kinematics */
 } cn_sarl_cfg;
 
 /* Episode statistics accumulated on the device by cn_env_step(update=1); the counters
@@ -116,6 +126,10 @@ int cn_env_destroy(cn_env *env);
 int cn_env_set_state(cn_env *env, const double *agents_host, const double *times_host, void *stream);
 /* Blocking read-back in the same layout. */
 int cn_env_get_state(cn_env *env, double *agents_host, double *times_host, void *stream);
+/* Robot heading (FullState.theta), E doubles.  Resets and cn_env_set_state put it at pi/2 (crowd_sim.py:284); the
+ * non-holonomic step wraps it to [0, 2 pi) (agent.py:131).  Only read when robot_kinematics != CN_KIN_HOLONOMIC. */
+int cn_env_set_theta(cn_env *env, const double *theta_host, void *stream);
+int cn_env_get_theta(cn_env *env, double *theta_host, void *stream);
 /* CrowdSim.reset on the device (crowd_sim.py:165-217 distributions and rejection rule, Philox stream
  * keyed by (seed, global env id, episode counter)).  env_mask_dev: E bytes on the device, NULL = all. */
 int cn_env_reset(cn_env *env, void *stream);

@@ -13,11 +13,12 @@ CN_OK, CN_EINVAL, CN_ECUDA, CN_ENOMEM, CN_EUNSUPPORTED, CN_EVALUE = 0, -1, -2, -
 NOTHING, DANGER, REACHGOAL, COLLISION, TIMEOUT = 0, 1, 2, 3, 4
 CIRCLE_CROSSING, SQUARE_CROSSING = 0, 1
 PREC_F32, PREC_F16_TC = 0, 1
+KIN_HOLONOMIC, KIN_UNICYCLE, KIN_NONE = 0, 1, 2      # robot kinematics (CN_KIN_*); NONE = the fork as shipped (cadrl.py:66)
 AGENT_STRIDE = 8
 
 EXPORTS = [
     "cn_last_error", "cn_version", "cn_device_count", "cn_env_cfg_default", "cn_sarl_cfg_default",
-    "cn_env_create", "cn_env_destroy", "cn_env_set_state", "cn_env_get_state", "cn_env_reset", "cn_env_orca",
+    "cn_env_create", "cn_env_destroy", "cn_env_set_state", "cn_env_get_state", "cn_env_set_theta", "cn_env_get_theta", "cn_env_reset", "cn_env_orca",
     "cn_env_robot_orca", "cn_env_step", "cn_env_get_views", "cn_env_read_outputs", "cn_env_read_human_actions",
     "cn_env_read_next_obs", "cn_env_read_actions", "cn_env_set_actions", "cn_env_read_stats", "cn_policy_create", "cn_policy_destroy",
     "cn_policy_param_count", "cn_policy_load_weights", "cn_policy_action_table", "cn_policy_lookahead",
@@ -41,14 +42,14 @@ class EnvCfg(C.Structure):
                 ("circle_radius", C.c_double), ("square_width", C.c_double), ("human_radius", C.c_double),
                 ("human_v_pref", C.c_double), ("robot_radius", C.c_double), ("robot_v_pref", C.c_double),
                 ("seed", C.c_uint64), ("env_id_offset", C.c_int64), ("auto_reset", C.c_int32),
-                ("gamma", C.c_double), ("randomize_attributes", C.c_int32)]
+                ("gamma", C.c_double), ("randomize_attributes", C.c_int32), ("robot_kinematics", C.c_int32)]
 
 
 class SarlCfg(C.Structure):
     _fields_ = [("input_dim", C.c_int32), ("self_state_dim", C.c_int32), ("mlp1_dims", C.c_int32 * 2),
                 ("mlp2_dims", C.c_int32 * 2), ("attn_dims", C.c_int32 * 3), ("mlp3_dims", C.c_int32 * 4),
                 ("speed_samples", C.c_int32), ("rotation_samples", C.c_int32), ("gamma", C.c_double),
-                ("v_pref", C.c_double), ("precision", C.c_int32)]
+                ("v_pref", C.c_double), ("precision", C.c_int32), ("kinematics", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -90,6 +91,8 @@ def load():
     L.cn_env_destroy.argtypes = [vp]
     L.cn_env_set_state.argtypes = [vp, vp, vp, vp]
     L.cn_env_get_state.argtypes = [vp, vp, vp, vp]
+    L.cn_env_set_theta.argtypes = [vp, vp, vp]
+    L.cn_env_get_theta.argtypes = [vp, vp, vp]
     L.cn_env_reset.argtypes = [vp, vp]
     L.cn_env_orca.argtypes = [vp, vp]
     L.cn_env_robot_orca.argtypes = [vp, dbl, vp]

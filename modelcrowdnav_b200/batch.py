@@ -44,6 +44,17 @@ class BatchedCrowdSim(object):
             pass
 
     # -- state ------------------------------------------------------------------------------------
+    def set_theta(self, theta, stream=None):
+        """Robot headings (E,), only meaningful for robot_kinematics != holonomic; resets put pi / 2."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        assert theta.shape == (self.E,)
+        check(self.lib.cn_env_set_theta(self.handle, _ptr(theta), _stream(stream)))
+
+    def get_theta(self, stream=None):
+        theta = np.empty(self.E, np.float64)
+        check(self.lib.cn_env_get_theta(self.handle, _ptr(theta), _stream(stream)))
+        return theta
+
     def set_state(self, agents, times=None, stream=None):
         agents = np.ascontiguousarray(agents, dtype=np.float64)
         assert agents.shape == (self.E, self.H + 1, _capi.AGENT_STRIDE), agents.shape

@@ -48,6 +48,7 @@ void cn_env_cfg_default(cn_env_cfg *c)
     c->human_radius = 0.3; c->human_v_pref = 1; c->robot_radius = 0.3; c->robot_v_pref = 1;
     c->seed = 0; c->env_id_offset = 0; c->auto_reset = 0; c->gamma = 0.9;
     c->randomize_attributes = 0;
+    c->robot_kinematics = CN_KIN_HOLONOMIC;
 }
 
 void cn_sarl_cfg_default(cn_sarl_cfg *c)
@@ -60,6 +61,7 @@ void cn_sarl_cfg_default(cn_sarl_cfg *c)
     c->mlp3_dims[0] = 150; c->mlp3_dims[1] = 100; c->mlp3_dims[2] = 100; c->mlp3_dims[3] = 1;
     c->speed_samples = 5; c->rotation_samples = 16;
     c->gamma = 0.9; c->v_pref = 1.0; c->precision = CN_PREC_F32;
+    c->kinematics = CN_KIN_HOLONOMIC;
 }
 
 static int use_device(int device)
@@ -120,6 +122,7 @@ int cn_env_create(const cn_env_cfg *cfg, int device, cn_env **out)
     p.seed = cfg->seed; p.env_id_offset = cfg->env_id_offset; p.auto_reset = cfg->auto_reset;
     p.gamma = cfg->gamma;
     p.randomize_attributes = cfg->randomize_attributes;
+    p.kinematics = cfg->robot_kinematics;
 
     const size_t E = p.d.E, H = p.d.H, A1 = p.d.A1;
 #define CN_ALLOC(ptr, bytes)                                                     \
@@ -145,6 +148,7 @@ int cn_env_create(const cn_env_cfg *cfg, int device, cn_env **out)
     CN_ALLOC(env->frozen, E);
     CN_ALLOC(env->stage, sizeof(double) * F_COUNT * A1 * E);
     CN_ALLOC(env->step_ctr, sizeof(uint32_t) * E);
+    CN_ALLOC(env->theta, sizeof(double) * E);
     // accumulators: 6 int64 + 6 double + 1 double + int32 + uint32 per env
     const size_t acc_bytes = E * (6 * 8 + 6 * 8 + 4 + 4);
     CN_ALLOC(env->accum_block, acc_bytes);
@@ -174,7 +178,7 @@ int cn_env_destroy(cn_env *env)
     if (!env) return CN_OK;
     cudaSetDevice(env->device);
     void *ptrs[] = {env->state, env->time, env->human_v, env->action_xy, env->action_idx, env->reward, env->done,
-                    env->info, env->dmin, env->next_obs, env->frozen, env->stage, env->step_ctr, env->accum_block};
+                    env->info, env->dmin, env->next_obs, env->frozen, env->stage, env->step_ctr, env->accum_block, env->theta};
     for (void *q : ptrs) if (q) cudaFree(q);
     if (env->io_block) cudaFree(env->io_block);
     if (env->side_stream) cudaStreamDestroy(env->side_stream);
@@ -188,6 +192,24 @@ int cn_env_destroy(cn_env *env)
     if (!(env)) { cn_set_error("null env handle"); return CN_EINVAL; } \
     CN_CUDA_CHECK(cudaSetDevice((env)->device));                       \
     cudaStream_t s = (cudaStream_t)stream
+
+int cn_env_set_theta(cn_env *env, const double *theta_host, void *stream)
+{
+    CN_ENV_ENTER(env);
+    if (!theta_host) { cn_set_error("theta_host is null"); return CN_EINVAL; }
+    CN_CUDA_CHECK(cudaMemcpyAsync(env->theta, theta_host, sizeof(double) * env->p.d.E, cudaMemcpyHostToDevice, s));
+    CN_CUDA_CHECK(cudaStreamSynchronize(s));
+    return CN_OK;
+}
+
+int cn_env_get_theta(cn_env *env, double *theta_host, void *stream)
+{
+    CN_ENV_ENTER(env);
+    if (!theta_host) { cn_set_error("theta_host is null"); return CN_EINVAL; }
+    CN_CUDA_CHECK(cudaMemcpyAsync(theta_host, env->theta, sizeof(double) * env->p.d.E, cudaMemcpyDeviceToHost, s));
+    CN_CUDA_CHECK(cudaStreamSynchronize(s));
+    return CN_OK;
+}
 
 int cn_env_set_state(cn_env *env, const double *agents_host, const double *times_host, void *stream)
 {
@@ -360,12 +382,28 @@ int64_t cn_policy_param_count(const cn_sarl_cfg *c)
     return n;
 }
 
-// CADRL.build_action_space, holonomic (cadrl.py:82-102); glibc exp/cos/sin like numpy on the host
+// CADRL.build_action_space (cadrl.py:82-102); glibc exp/cos/sin like numpy on the host.  Holonomic: (vx, vy) over 16
+// headings; otherwise ActionRot (v, r) with r in np.linspace(-pi/4, pi/4, R) (endpoint included, last sample = stop).
 static int build_action_table(const cn_sarl_cfg *c, double *out)
 {
     const double E_ = 2.718281828459045;
     int n = 0;
     out[0] = 0; out[1] = 0; n = 1;
+    if (c->kinematics != CN_KIN_HOLONOMIC) {
+        const double PI = 3.141592653589793, start = -PI / 4, stop = PI / 4;
+        const int div = c->rotation_samples - 1;
+        const double step = div > 0 ? (stop - start) / div : 0.0;
+        for (int r = 0; r < c->rotation_samples; ++r) {
+            double rotation = start + r * step;
+            if (div > 0 && r == c->rotation_samples - 1) rotation = stop;
+            for (int s = 0; s < c->speed_samples; ++s) {
+                out[2 * n] = (exp((double)(s + 1) / c->speed_samples) - 1) / (E_ - 1) * c->v_pref;
+                out[2 * n + 1] = rotation;
+                ++n;
+            }
+        }
+        return n;
+    }
     const double step = (2 * 3.141592653589793 - 0) / c->rotation_samples;
     for (int r = 0; r < c->rotation_samples; ++r) {
         const double rotation = r * step;
@@ -500,6 +538,10 @@ static int check_pair(cn_policy *p, cn_env *env)
     if (!p || !env) { cn_set_error("null handle"); return CN_EINVAL; }
     if (p->device != env->device) { cn_set_error("policy and env live on different devices"); return CN_EINVAL; }
     if (!p->weights_loaded) { cn_set_error("cn_policy_load_weights has not been called"); return CN_EINVAL; }
+    if (p->cfg.kinematics != env->p.kinematics) {
+        cn_set_error("policy kinematics (%d) and env robot_kinematics (%d) differ", p->cfg.kinematics, env->p.kinematics);
+        return CN_EINVAL;
+    }
     return CN_OK;
 }
 

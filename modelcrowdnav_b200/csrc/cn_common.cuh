@@ -36,6 +36,7 @@ struct EnvParams {
     int auto_reset;
     double gamma;
     int randomize_attributes;
+    int kinematics;       // CN_KIN_*: robot kinematics
 };
 
 // per-env episode accumulators (explorer.py:41-51,92-108,124-141)
@@ -65,6 +66,7 @@ struct cn_env {
     void *accum_block;    // single allocation backing acc.*
     double *stage;        // device staging, E x A1 x 8 (AoS exchange layout)
     uint32_t *step_ctr;   // E: lookahead draws (epsilon-greedy Philox subsequence)
+    double *theta;        // E: robot heading (only read when p.kinematics != CN_KIN_HOLONOMIC)
     int orca_valid;
     // fork/join resources of cn_rollout_step: ORCA runs beside the lookahead when the lookahead does not read it
     cudaStream_t side_stream;
@@ -182,6 +184,16 @@ struct PhiloxStream {
         return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
     }
 };
+
+// Robot action -> the velocity the reference's non-holonomic branches use for collision checking, compute_position and
+// propagate: v * cos(theta + r), v * sin(theta + r) (crowd_sim.py:353-354, agent.py:115-117, cadrl.py:119-121).
+// Holonomic actions are already velocities.  (CUDA's double cos/sin are within 1-2 ulp of glibc's: positions of the
+// non-holonomic modes agree with the reference to ~1e-15 relative, not bit for bit.)
+__device__ __forceinline__ void cn_effective_velocity(int kinematics, double theta, double a0, double a1, double &ax, double &ay)
+{
+    if (kinematics == CN_KIN_HOLONOMIC) { ax = a0; ay = a1; }
+    else { ax = a0 * cos(a1 + theta); ay = a0 * sin(a1 + theta); }
+}
 
 // np.linalg.norm of a 2-vector as numpy evaluates it: sqrt(fma(b, b, a*a))
 __host__ __device__ __forceinline__ double norm2d(double a, double b) { return sqrt(fma(b, b, a * a)); }

@@ -54,9 +54,10 @@ __device__ __forceinline__ StepOutcome cn_step_outcome(const EnvParams &p, Acc a
     return o;
 }
 
-// CADRL.rotate on one joint-state row (cadrl.py:217-252), float32; theta slot = 0 (holonomic).
+// CADRL.rotate on one joint-state row (cadrl.py:217-252), float32; theta slot = theta - rot only for
+// kinematics == 'unicycle' (cadrl.py:236-240), else 0.
 // s: px py vx vy radius gx gy v_pref theta px1 py1 vx1 vy1 radius1
-__device__ __forceinline__ void cn_rotate(const float *s, float *o)
+__device__ __forceinline__ void cn_rotate(const float *s, float *o, int kinematics = CN_KIN_HOLONOMIC)
 {
     const float dx = s[5] - s[0], dy = s[6] - s[1];
     const float rot = atan2f(dy, dx);
@@ -64,7 +65,7 @@ __device__ __forceinline__ void cn_rotate(const float *s, float *o)
     sincosf(rot, &sn, &c);
     o[0] = sqrtf(dx * dx + dy * dy);
     o[1] = s[7];
-    o[2] = 0.0f;
+    o[2] = kinematics == CN_KIN_UNICYCLE ? s[8] - rot : 0.0f;
     o[3] = s[4];
     o[4] = s[2] * c + s[3] * sn;
     o[5] = s[3] * c - s[2] * sn;

@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(kThreads, 2)
 lookahead_values_kernel(EnvParams p, SarlWeightsDev W, SarlDims d, F32Plan pl, const double *__restrict__ st,
                         const double *__restrict__ time, const double *__restrict__ human_v,
                         const uint8_t *__restrict__ frozen, const double *__restrict__ actions, int query_env,
-                        double gamma, double gamma_bar_host, double v_pref_host, double *__restrict__ values)
+                        double gamma, double gamma_bar_host, double v_pref_host, double *__restrict__ values,
+                        const double *__restrict__ theta)
 {
     extern __shared__ __align__(16) float sm[];
     const int e = blockIdx.x;
@@ -193,6 +194,8 @@ lookahead_values_kernel(EnvParams p, SarlWeightsDev W, SarlDims d, F32Plan pl, c
     __syncthreads();
     auto ag = [&](int f, int a) { return env[a * F_COUNT + f]; };
     const double dt = p.time_step;
+    const int kin = p.kinematics;
+    const double th = kin != CN_KIN_HOLONOMIC ? theta[e] : 0.0;      // robot heading (cadrl.py:119: next_theta = theta + r)
     // next human states: query_env -> ORCA action (agent.py:63-74), else constant velocity (cadrl.py:107-109)
     for (int h = threadIdx.x; h < H; h += blockDim.x) {
         double hvx, hvy;
@@ -206,7 +209,8 @@ lookahead_values_kernel(EnvParams p, SarlWeightsDev W, SarlDims d, F32Plan pl, c
     __syncthreads();
     // reward per action
     for (int i = threadIdx.x; i < na; i += blockDim.x) {
-        const double ax = actions[2 * (a0 + i)], ay = actions[2 * (a0 + i) + 1];
+        double ax, ay;
+        cn_effective_velocity(kin, th, actions[2 * (a0 + i)], actions[2 * (a0 + i) + 1], ax, ay);
         double reward;
         if (query_env) {
             reward = cn_step_outcome(p, ag, H, time[e], ax, ay).reward;   // crowd_sim.py:325-329
@@ -231,14 +235,16 @@ lookahead_values_kernel(EnvParams p, SarlWeightsDev W, SarlDims d, F32Plan pl, c
     // rotated joint-state rows (multi_human_rl.py:43-45): torch.Tensor([...]) rounds the doubles to fp32
     for (int r = threadIdx.x; r < rows; r += blockDim.x) {
         const int i = r / H, h = r - i * H;
-        const double ax = actions[2 * (a0 + i)], ay = actions[2 * (a0 + i) + 1];
+        double ax, ay;
+        cn_effective_velocity(kin, th, actions[2 * (a0 + i)], actions[2 * (a0 + i) + 1], ax, ay);
         float s[14], o[13];
         s[0] = (float)(ag(F_PX, 0) + ax * dt); s[1] = (float)(ag(F_PY, 0) + ay * dt);
         s[2] = (float)ax; s[3] = (float)ay; s[4] = (float)ag(F_R, 0);
-        s[5] = (float)ag(F_GX, 0); s[6] = (float)ag(F_GY, 0); s[7] = (float)ag(F_VPREF, 0); s[8] = 0.0f;
+        s[5] = (float)ag(F_GX, 0); s[6] = (float)ag(F_GY, 0); s[7] = (float)ag(F_VPREF, 0);
+        s[8] = kin != CN_KIN_HOLONOMIC ? (float)(th + actions[2 * (a0 + i) + 1]) : 0.0f;
         s[9] = (float)hnext[h * 4 + 0]; s[10] = (float)hnext[h * 4 + 1];
         s[11] = (float)hnext[h * 4 + 2]; s[12] = (float)hnext[h * 4 + 3]; s[13] = (float)ag(F_R, h + 1);
-        cn_rotate(s, o);
+        cn_rotate(s, o, kin);
 #pragma unroll
         for (int k = 0; k < 13; ++k) X[(size_t)r * pl.wX + k] = o[k];
     }
@@ -298,7 +304,8 @@ argmax_kernel(EnvParams p, int A, const double *__restrict__ st, const uint8_t *
 }
 
 // MultiHumanRL.transform (multi_human_rl.py:90-104): current joint state -> E x H x 13 fp32
-__global__ void transform_kernel(EnvParams p, const double *__restrict__ st, float *__restrict__ out)
+__global__ void transform_kernel(EnvParams p, const double *__restrict__ st, const double *__restrict__ theta,
+                                 float *__restrict__ out)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const EnvDims d = p.d;
@@ -307,10 +314,11 @@ __global__ void transform_kernel(EnvParams p, const double *__restrict__ st, flo
     auto ag = [&](int f, int a) { return (float)st[st_idx(d, f, a, e)]; };
     float s[14], o[13];
     s[0] = ag(F_PX, 0); s[1] = ag(F_PY, 0); s[2] = ag(F_VX, 0); s[3] = ag(F_VY, 0); s[4] = ag(F_R, 0);
-    s[5] = ag(F_GX, 0); s[6] = ag(F_GY, 0); s[7] = ag(F_VPREF, 0); s[8] = 0.0f;
+    s[5] = ag(F_GX, 0); s[6] = ag(F_GY, 0); s[7] = ag(F_VPREF, 0);
+    s[8] = p.kinematics != CN_KIN_HOLONOMIC ? (float)theta[e] : 0.0f;
     s[9] = ag(F_PX, h + 1); s[10] = ag(F_PY, h + 1); s[11] = ag(F_VX, h + 1); s[12] = ag(F_VY, h + 1);
     s[13] = ag(F_R, h + 1);
-    cn_rotate(s, o);
+    cn_rotate(s, o, p.kinematics);
     for (int k = 0; k < 13; ++k) out[((size_t)e * d.H + h) * 13 + k] = o[k];
 }
 
@@ -410,7 +418,7 @@ int cn_lookahead_f32(cn_policy *p, cn_env *env, int query_env, double epsilon, c
     dim3 grid(ed.E, (p->d.A + pl.CA - 1) / pl.CA);
     lookahead_values_kernel<<<grid, kThreads, smem, s>>>(env->p, p->w, p->d, pl, env->state, env->time, env->human_v,
                                                          env->frozen, p->action_dev, query_env, p->cfg.gamma, gamma_bar,
-                                                         p->cfg.v_pref, p->values);
+                                                         p->cfg.v_pref, p->values, env->theta);
     CN_LAUNCH_CHECK();
     return cn_lookahead_argmax(p, env, epsilon, s);
 }
@@ -419,7 +427,7 @@ int cn_transform_f32(cn_policy *p, cn_env *env, float *out_dev, cudaStream_t s)
 {
     (void)p;
     const int n = env->p.d.E * env->p.d.H;
-    transform_kernel<<<(n + 127) / 128, 128, 0, s>>>(env->p, env->state, out_dev);
+    transform_kernel<<<(n + 127) / 128, 128, 0, s>>>(env->p, env->state, env->theta, out_dev);
     CN_LAUNCH_CHECK();
     return CN_OK;
 }

@@ -256,15 +256,19 @@ __global__ void __launch_bounds__(128) step_kernel(EnvParams p, double *__restri
                                                    double *__restrict__ reward_o, uint8_t *__restrict__ done_o,
                                                    uint8_t *__restrict__ info_o, double *__restrict__ dmin_o,
                                                    double *__restrict__ next_obs, uint8_t *__restrict__ frozen,
-                                                   EnvAccum acc)
+                                                   EnvAccum acc, double *__restrict__ theta)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const EnvDims d = p.d;
     if (e >= d.E) return;
     if (frozen[e]) { reward_o[e] = 0.0; done_o[e] = 1; return; }
     const int E = d.E, H = d.H;
-    const double ax = act_aos ? act[2 * (size_t)e] : act[e];
-    const double ay = act_aos ? act[2 * (size_t)e + 1] : act[E + e];
+    // the action: (vx, vy) holonomic, (v, r) otherwise; (ax, ay) = the velocity the step moves and collision-checks with
+    const double a0 = act_aos ? act[2 * (size_t)e] : act[e];
+    const double a1 = act_aos ? act[2 * (size_t)e + 1] : act[E + e];
+    const double th = p.kinematics != CN_KIN_HOLONOMIC ? theta[e] : 0.0;
+    double ax, ay;
+    cn_effective_velocity(p.kinematics, th, a0, a1, ax, ay);
     const double dt = p.time_step;
     const double t = time[e];
     auto ag = [&](int f, int a) { return st[st_idx(d, f, a, e)]; };
@@ -275,11 +279,21 @@ __global__ void __launch_bounds__(128) step_kernel(EnvParams p, double *__restri
     reward_o[e] = reward; done_o[e] = (uint8_t)done; info_o[e] = (uint8_t)info; dmin_o[e] = dmin;
 
     if (update) {
-        // crowd_sim.py:414-417, agent.py:122-135 (holonomic)
+        // crowd_sim.py:414-417, agent.py:122-135
         st[st_idx(d, F_PX, 0, e)] = endx;
         st[st_idx(d, F_PY, 0, e)] = endy;
-        st[st_idx(d, F_VX, 0, e)] = ax;
-        st[st_idx(d, F_VY, 0, e)] = ay;
+        if (p.kinematics == CN_KIN_HOLONOMIC) {
+            st[st_idx(d, F_VX, 0, e)] = ax;
+            st[st_idx(d, F_VY, 0, e)] = ay;
+        } else {
+            // agent.py:131-133: the heading wraps to [0, 2 pi) (Python float %), the stored velocity uses the wrapped heading
+            const double TWO_PI = 2 * 3.141592653589793;
+            double t2 = fmod(th + a1, TWO_PI);
+            if (t2 < 0) t2 += TWO_PI;
+            theta[e] = t2;
+            st[st_idx(d, F_VX, 0, e)] = a0 * cos(t2);
+            st[st_idx(d, F_VY, 0, e)] = a0 * sin(t2);
+        }
         for (int h = 1; h <= H; ++h) {
             const double hvx = human_v[(size_t)(0 * H + h - 1) * E + e];
             const double hvy = human_v[(size_t)(1 * H + h - 1) * E + e];
@@ -325,7 +339,7 @@ __global__ void __launch_bounds__(128) step_kernel(EnvParams p, double *__restri
 // keyed by (seed, global env id, episode counter).  One thread per env.
 __global__ void __launch_bounds__(128) reset_kernel(EnvParams p, double *__restrict__ st, double *__restrict__ time,
                                                     const uint8_t *__restrict__ done, int only_done,
-                                                    uint8_t *__restrict__ frozen, EnvAccum acc)
+                                                    uint8_t *__restrict__ frozen, EnvAccum acc, double *__restrict__ theta)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const EnvDims d = p.d;
@@ -396,6 +410,7 @@ __global__ void __launch_bounds__(128) reset_kernel(EnvParams p, double *__restr
         st[st_idx(d, F_R, i, e)] = h_radius; st[st_idx(d, F_VPREF, i, e)] = h_v_pref;
     }
     time[e] = 0.0;
+    theta[e] = 1.5707963267948966;                       // crowd_sim.py:284: robot.set(..., np.pi / 2)
     frozen[e] = 0;
     acc.ep_steps[e] = 0; acc.ep_return[e] = 0.0;
 }
@@ -451,11 +466,12 @@ __global__ void io_pack_kernel(EnvDims d, const double *__restrict__ st, const d
     }
 }
 
-__global__ void clear_episode_kernel(int E, uint8_t *frozen, EnvAccum acc, uint8_t *done)
+__global__ void clear_episode_kernel(int E, uint8_t *frozen, EnvAccum acc, uint8_t *done, double *theta)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
     frozen[e] = 0; done[e] = 0;
+    theta[e] = 1.5707963267948966;                       // a host-generated scene is a reset: robot heading pi / 2
     acc.ep_steps[e] = 0; acc.ep_return[e] = 0.0;
 }
 
@@ -508,7 +524,7 @@ int cn_launch_step(cn_env *env, const double *action_xy_dev, int update, cudaStr
     step_kernel<<<grid_for(env->p.d.E, 128), 128, 0, s>>>(env->p, env->state, env->time, env->human_v, act,
                                                             action_xy_dev ? 1 : 0, update, env->reward, env->done,
                                                             env->info, env->dmin, env->next_obs, env->frozen,
-                                                            env->acc);
+                                                            env->acc, env->theta);
     CN_LAUNCH_CHECK();
     if (update) env->orca_valid = 0;
     return CN_OK;
@@ -517,7 +533,7 @@ int cn_launch_step(cn_env *env, const double *action_xy_dev, int update, cudaStr
 int cn_launch_reset(cn_env *env, int only_done, cudaStream_t s)
 {
     reset_kernel<<<grid_for(env->p.d.E, 128), 128, 0, s>>>(env->p, env->state, env->time, env->done, only_done,
-                                                             env->frozen, env->acc);
+                                                             env->frozen, env->acc, env->theta);
     CN_LAUNCH_CHECK();
     env->orca_valid = 0;
     return CN_OK;
@@ -531,7 +547,7 @@ int cn_launch_pack(cn_env *env, int to_soa, cudaStream_t s)
     pack_kernel<<<grid, 256, 0, s>>>(env->p.d, env->state, env->stage, to_soa);
     CN_LAUNCH_CHECK();
     if (to_soa) {
-        clear_episode_kernel<<<grid_for(env->p.d.E, 128), 128, 0, s>>>(env->p.d.E, env->frozen, env->acc, env->done);
+        clear_episode_kernel<<<grid_for(env->p.d.E, 128), 128, 0, s>>>(env->p.d.E, env->frozen, env->acc, env->done, env->theta);
         CN_LAUNCH_CHECK();
         env->orca_valid = 0;
     }

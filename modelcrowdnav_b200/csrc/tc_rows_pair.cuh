@@ -57,13 +57,14 @@ static_assert(Q_SMEM <= 232448, "tc_rows_pair_kernel exceeds 227 KB of shared me
 
 struct RowInPP {
     double rpx, rpy, rgx, rgy, rr, rvp, hpx, hpy, hvx, hvy, cvx, cvy, hr, ax, ay, t;
+    float ntheta;          // robot heading after the action (cadrl.py:119), fp32 like the reference's state tensor
     int valid;
 };
 
 __device__ __forceinline__ void pp_load_inputs(RowInPP &in, const EnvDims &ed, const double *__restrict__ st,
                                                const double *__restrict__ time, const double *__restrict__ human_v,
                                                const double *__restrict__ actions, int A, int query_env, int NG, int G,
-                                               int tile, int gl, int h)
+                                               int tile, int gl, int h, int kinematics, const double *__restrict__ theta)
 {
     const int H = ed.H;
     const int g = tile * G + gl;          // the host keeps (total tiles + 1) * G below 2^31
@@ -82,7 +83,11 @@ __device__ __forceinline__ void pp_load_inputs(RowInPP &in, const EnvDims &ed, c
     } else {                                                                            // cadrl.py:107-109
         in.hvx = in.cvx; in.hvy = in.cvy; in.t = 0.0;
     }
-    in.ax = actions[2 * a]; in.ay = actions[2 * a + 1];
+    // (ax, ay) = the velocity the robot moves with: the action itself (holonomic) or v (cos, sin)(theta + r)
+    const double a0 = actions[2 * a], a1 = actions[2 * a + 1];
+    const double th = kinematics != CN_KIN_HOLONOMIC ? theta[e] : 0.0;
+    cn_effective_velocity(kinematics, th, a0, a1, in.ax, in.ay);
+    in.ntheta = kinematics != CN_KIN_HOLONOMIC ? (float)(th + a1) : 0.0f;
 }
 
 // clearance of this row's human for the lookahead reward (see group_compute in lookahead_tc.cu for the equivalence with the
@@ -105,7 +110,7 @@ __device__ __forceinline__ double pp_clearance(const RowInPP &in, double dt, int
 // CADRL.rotate with the rotation taken from the normalised goal direction instead of atan2 -> sincos
 // (cos(atan2(dy, dx)) = dx / |d|): same quantity to ~1e-7, a fraction of the instructions.  The FP32 twin keeps
 // torch's atan2/cos/sin order (env_math.cuh); this path is fp16 downstream anyway.
-__device__ __forceinline__ void rotate_dir(const float *s, float *o)
+__device__ __forceinline__ void rotate_dir(const float *s, float *o, int kinematics)
 {
     const float dx = s[5] - s[0], dy = s[6] - s[1];
     const float d = sqrtf(dx * dx + dy * dy);
@@ -113,7 +118,7 @@ __device__ __forceinline__ void rotate_dir(const float *s, float *o)
     if (d > 0.0f) { const float inv = 1.0f / d; c = dx * inv; sn = dy * inv; }
     o[0] = d;
     o[1] = s[7];
-    o[2] = 0.0f;
+    o[2] = kinematics == CN_KIN_UNICYCLE ? s[8] - atan2f(dy, dx) : 0.0f;      // cadrl.py:236-240
     o[3] = s[4];
     o[4] = s[2] * c + s[3] * sn;
     o[5] = s[3] * c - s[2] * sn;
@@ -127,17 +132,18 @@ __device__ __forceinline__ void rotate_dir(const float *s, float *o)
     o[12] = s[4] + s[13];
 }
 
-__device__ __forceinline__ void pair_features(const RowInPP &in, double dt, uint4 &c0, uint4 &c1, uint4 &c2, uint4 &c3)
+__device__ __forceinline__ void pair_features(const RowInPP &in, double dt, int kinematics, uint4 &c0, uint4 &c1, uint4 &c2,
+                                              uint4 &c3)
 {
     c0 = make_uint4(0, 0, 0, 0); c1 = c0; c2 = c0; c3 = c0;
     if (!in.valid) return;
     float s[14], o[13];
     s[0] = (float)(in.rpx + in.ax * dt); s[1] = (float)(in.rpy + in.ay * dt);
     s[2] = (float)in.ax; s[3] = (float)in.ay; s[4] = (float)in.rr;
-    s[5] = (float)in.rgx; s[6] = (float)in.rgy; s[7] = (float)in.rvp; s[8] = 0.0f;
+    s[5] = (float)in.rgx; s[6] = (float)in.rgy; s[7] = (float)in.rvp; s[8] = in.ntheta;
     s[9] = (float)(in.hpx + in.hvx * dt); s[10] = (float)(in.hpy + in.hvy * dt);
     s[11] = (float)in.hvx; s[12] = (float)in.hvy; s[13] = (float)in.hr;
-    rotate_dir(s, o);
+    rotate_dir(s, o, kinematics);
     float hi[13], lo[13];
 #pragma unroll
     for (int k = 0; k < 13; ++k) split_hl(o[k], hi[k], lo[k]);
@@ -190,7 +196,8 @@ template <int HT>
 __global__ void __launch_bounds__(ROWS)
 tc_features_kernel(EnvParams p, const double *__restrict__ st, const double *__restrict__ time,
                    const double *__restrict__ human_v, const double *__restrict__ actions, int A, int query_env, int NG,
-                   int G_rt, uint8_t *__restrict__ X, uint8_t *__restrict__ J, double *__restrict__ rew)
+                   int G_rt, const double *__restrict__ theta, uint8_t *__restrict__ X, uint8_t *__restrict__ J,
+                   double *__restrict__ rew)
 {
     __shared__ double D[ROWS];
     const EnvDims ed = p.d;
@@ -200,10 +207,10 @@ tc_features_kernel(EnvParams p, const double *__restrict__ st, const double *__r
     const int gl = r / H, h = r - gl * H;
     const double dt = p.time_step;
     RowInPP in;
-    pp_load_inputs(in, ed, st, time, human_v, actions, A, query_env, NG, G, tile, gl, h);
+    pp_load_inputs(in, ed, st, time, human_v, actions, A, query_env, NG, G, tile, gl, h, p.kinematics, theta);
     D[r] = pp_clearance(in, dt, query_env);
     uint4 c0, c1, c2, c3;
-    pair_features(in, dt, c0, c1, c2, c3);
+    pair_features(in, dt, p.kinematics, c0, c1, c2, c3);
     uint8_t *xt = X + (size_t)tile * X_TILE_BYTES;
     *reinterpret_cast<uint4 *>(xt + chunk_off(ROWS, r, 0)) = c0;
     *reinterpret_cast<uint4 *>(xt + chunk_off(ROWS, r, 1)) = c1;

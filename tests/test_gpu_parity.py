@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import TRAJ_NAMES, load_traj, weights_for
+from conftest import TRAJ_NAMES, TRAJ_NAMES_KIN, load_traj, weights_for
 
 pytestmark = pytest.mark.gpu
 
@@ -444,3 +444,52 @@ def test_packed_host_step_matches_device_step(mcn, oracle_mod, weights0):
             assert np.array_equal(np.asarray(ba).reshape(-1), buf.action_idx)
         buf.swap()
     env_a.close(); env_b.close(); pol.close()
+
+
+@pytest.mark.parametrize("precision", ["f32", "f16_tc"])
+@pytest.mark.parametrize("name", TRAJ_NAMES_KIN)
+def test_golden_trajectories_kinematics(mcn, weights0, name, precision):
+    """Robot kinematics None (the fork exactly as shipped: ActionRot dynamics, heading feature zero) and unicycle:
+    teacher-forced replay of the reference's own episodes.  Action table bit-exact; values / argmax to the same bars as
+    the holonomic fixtures; integer outputs exact; positions, velocities and heading to 1e-12 (the non-holonomic step
+    goes through double cos / sin, where CUDA and glibc agree to 1-2 ulp, not bit for bit)."""
+    tr = load_traj(name)
+    H, kin = tr["H"], tr["kinematics"]
+    states, times, thetas, recs = [], [], [], []
+    for case, rec in tr["cases"].items():
+        for t in range(len(rec["time"])):
+            states.append(rec["agents"][t]); times.append(rec["time"][t]); thetas.append(rec["theta"][t])
+            recs.append((rec, t))
+    E = len(states)
+    env = mcn.BatchedCrowdSim(E, H, robot_visible=tr["robot_visible"], robot_kinematics=kin)
+    pol = mcn.BatchedSARL(precision=precision, kinematics=kin)
+    pol.load_weights(weights0)
+    assert np.array_equal(pol.action_table, recs[0][0]["table"])            # bit-exact (v, r) table
+    env.set_state(np.stack(states), np.array(times))
+    assert np.all(env.get_theta() == np.pi / 2)                             # a host scene is a reset
+    env.set_theta(np.array(thetas))
+    env.orca()
+    hv = env.human_actions()
+    pol.lookahead(env, query_env=tr["query_env"])
+    best, values = pol.read(env)
+    acts = np.stack([rec["action"][t] for rec, t in recs])                  # the REFERENCE's (v, r) actions
+    reward, done, info, dmin = env.step(acts, update=True)
+    got, gt = env.get_state()
+    th = env.get_theta()
+    tol = VALUE_TOL[precision]
+    agree = total = 0
+    for e, (rec, t) in enumerate(recs):
+        assert np.array_equal(hv[e], rec["human_v"][t]), (name, e)
+        ref_v = rec["values"][t]
+        assert np.max(np.abs(values[e] - ref_v)) <= tol * max(1.0, np.max(np.abs(ref_v))), (name, e)
+        top2 = np.sort(ref_v)[-2:]
+        if top2[1] - top2[0] > TIE_GAP[precision]:
+            total += 1
+            agree += int(best[e] == rec["best"][t])
+        assert (reward[e], bool(done[e]), int(info[e])) == (rec["reward"][t], bool(rec["done"][t]), int(rec["info"][t]))
+        if t + 1 < len(rec["time"]):
+            assert np.allclose(got[e], rec["agents"][t + 1], rtol=0, atol=1e-12) and gt[e] == rec["time"][t + 1]
+            assert np.array_equal(got[e][1:], rec["agents"][t + 1][1:])    # humans never touch cos / sin: bit-exact
+            assert abs(th[e] - rec["theta"][t + 1]) <= 1e-12
+    assert total == 0 or agree / total >= 0.999, (agree, total)
+    env.close(); pol.close()
