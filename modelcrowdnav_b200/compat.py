@@ -27,8 +27,11 @@ def _module(name, **attrs):
     return m
 
 
-def install_as_reference(provide_gym=True):
+def install_as_reference(provide_gym=True, literal_kinematics=False):
+    """literal_kinematics=True reproduces the fork exactly: SARL never reads [action_space] kinematics (cadrl.py:66 is
+    commented out), so it plans with ActionRot actions and non-holonomic robot dynamics whatever policy.config says."""
     from . import envs, explorer, policy, trainer
+    policy.LITERAL_FORK_KINEMATICS = bool(literal_kinematics)
     _module("crowd_sim")
     _module("crowd_sim.envs", CrowdSim=envs.CrowdSim)
     _module("crowd_sim.envs.crowd_sim", CrowdSim=envs.CrowdSim)

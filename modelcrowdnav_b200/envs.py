@@ -20,6 +20,8 @@ from .batch import BatchedCrowdSim
 
 ActionXY = namedtuple("ActionXY", ["vx", "vy"])
 ActionRot = namedtuple("ActionRot", ["v", "r"])
+# agent.kinematics -> CN_KIN_*; None = the fork exactly as shipped (every `== 'holonomic'` test fails, agent.py:104-133)
+KIN_CODE = {"holonomic": _capi.KIN_HOLONOMIC, "unicycle": _capi.KIN_UNICYCLE, None: _capi.KIN_NONE}
 
 
 class FullState(object):
@@ -199,7 +201,8 @@ def batch_env_kwargs(env):
                 circle_radius=env.circle_radius, square_width=env.square_width,
                 human_radius=cfg.getfloat("humans", "radius"), human_v_pref=cfg.getfloat("humans", "v_pref"),
                 robot_radius=cfg.getfloat("robot", "radius"), robot_v_pref=cfg.getfloat("robot", "v_pref"),
-                randomize_attributes=int(bool(env.randomize_attributes)))
+                randomize_attributes=int(bool(env.randomize_attributes)),
+                robot_kinematics=KIN_CODE[env.robot.kinematics] if env.robot is not None else _capi.KIN_HOLONOMIC)
 
 
 class CrowdSim(object):
@@ -268,7 +271,8 @@ class CrowdSim(object):
         return cases
 
     def _ensure_batch(self):
-        if self._batch is None or self._batch.H != self.human_num:
+        kin = KIN_CODE[self.robot.kinematics]        # changes when train.py swaps the robot's policy (ORCA -> SARL)
+        if self._batch is None or self._batch.H != self.human_num or self._batch.cfg.robot_kinematics != kin:
             if self._batch is not None:
                 self._batch.close()
             self._batch = BatchedCrowdSim(1, self.human_num, device=self.device, **batch_env_kwargs(self))
@@ -314,14 +318,20 @@ class CrowdSim(object):
         return self.step(action, update=False)
 
     def step(self, action, update=True):
-        if self.robot.kinematics != "holonomic":
-            raise NotImplementedError("unicycle kinematics is outside the B200 hot path (SURVEY §8(f) rank 2)")
+        if self.robot.kinematics not in KIN_CODE:
+            raise NotImplementedError("robot kinematics must be holonomic, unicycle or None")
         self.robot.check_validity(action)
+        fresh = self._batch is None or self._batch.cfg.robot_kinematics != KIN_CODE[self.robot.kinematics]
         b = self._ensure_batch()
+        if fresh:                          # the robot's policy (hence kinematics) changed since reset(): re-upload
+            b.set_state(np.array([[a._row() for a in [self.robot] + self.humans]]), np.array([self.global_time]))
+        holonomic = self.robot.kinematics == "holonomic"
+        if not holonomic:
+            b.set_theta(np.array([float(self.robot.theta)]))
         if self._human_v is None:          # one ORCA solve per env step, shared by the 81 lookahead queries
             b.orca()
             self._human_v = True
-        act = np.array([[action.vx, action.vy]], dtype=np.float64)
+        act = np.array([[action.vx, action.vy] if holonomic else [action.v, action.r]], dtype=np.float64)
         reward, done, info, dmin = b.step(act, update=update)
         info_obj = info_from_code(info[0], dmin[0])
         if update:
@@ -332,6 +342,8 @@ class CrowdSim(object):
                 self.attention_weights.append(self.robot.policy.get_attention_weights())
             agents, times = b.get_state()
             self._sync_agents(agents[0])
+            if not holonomic:
+                self.robot.theta = float(b.get_theta()[0])        # agent.py:131
             self.global_time = float(times[0])
             self._human_v = None
             for i, human in enumerate(self.humans):

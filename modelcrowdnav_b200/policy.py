@@ -57,6 +57,15 @@ def _cuda_index(device):
     return 0 if idx is None else int(idx)
 
 
+# The unmodified fork never reads [action_space] kinematics (cadrl.py:66 is commented out), so its SARL runs with
+# policy.kinematics = None: ActionRot actions with rotations in [-pi/4, pi/4], non-holonomic robot dynamics, heading
+# feature zero.  False (default): honour the config key (holonomic in the shipped policy.config, the north-star scope).
+# True: reproduce the fork literally.  compat.install_as_reference(literal_kinematics=True) sets it.
+LITERAL_FORK_KINEMATICS = False
+
+KIN_CODE = {"holonomic": _capi.KIN_HOLONOMIC, "unicycle": _capi.KIN_UNICYCLE, None: _capi.KIN_NONE}
+
+
 def joint_state_to_agents(state):
     """JointState -> (H+1, 8) exchange rows [px py vx vy gx gy radius v_pref]; unknown human goals = position."""
     s = state.self_state
@@ -188,9 +197,9 @@ class SARL(Policy):
     # -- configuration (cadrl.py:64-73, sarl.py:73-86) ---------------------------------------------
     def set_common_parameters(self, config):
         self.gamma = config.getfloat("rl", "gamma")
-        # policy.config:14 -- the reference fork comments this read out (cadrl.py:66); the north star
-        # specifies the holonomic 81-action space, so it is honoured here.
-        self.kinematics = config.get("action_space", "kinematics")
+        # policy.config:14 -- the reference fork comments this read out (cadrl.py:66); the north star specifies the
+        # holonomic 81-action space, so the key is honoured unless LITERAL_FORK_KINEMATICS asks for the fork's behaviour
+        self.kinematics = None if LITERAL_FORK_KINEMATICS else config.get("action_space", "kinematics")
         self.sampling = config.get("action_space", "sampling")
         self.speed_samples = config.getint("action_space", "speed_samples")
         self.rotation_samples = config.getint("action_space", "rotation_samples")
@@ -201,8 +210,8 @@ class SARL(Policy):
 
     def configure(self, config):
         self.set_common_parameters(config)
-        if self.kinematics != "holonomic":
-            raise NotImplementedError("only holonomic kinematics is on the B200 hot path (SURVEY §8(f) rank 2)")
+        if self.kinematics not in KIN_CODE:
+            raise NotImplementedError("kinematics must be holonomic, unicycle or None (the fork's literal behaviour)")
         mlp1_dims = [int(x) for x in config.get("sarl", "mlp1_dims").split(", ")]
         mlp2_dims = [int(x) for x in config.get("sarl", "mlp2_dims").split(", ")]
         mlp3_dims = [int(x) for x in config.get("sarl", "mlp3_dims").split(", ")]
@@ -230,22 +239,29 @@ class SARL(Policy):
         return self.model.attention_weights
 
     def build_action_space(self, v_pref):
-        """cadrl.py:82-102 (holonomic); the table itself comes from the C ABI (cn_policy_action_table)."""
-        from .envs import ActionXY
+        """cadrl.py:82-102; the table itself comes from the C ABI (cn_policy_action_table): (vx, vy) pairs for
+        holonomic kinematics, (v, r) pairs otherwise."""
+        from .envs import ActionRot, ActionXY
         h = self.handle(v_pref)
+        holonomic = self.kinematics == "holonomic"
         self.speeds = [(np.exp((i + 1) / self.speed_samples) - 1) / (np.e - 1) * v_pref
                        for i in range(self.speed_samples)]
-        self.rotations = np.linspace(0, 2 * np.pi, self.rotation_samples, endpoint=False)
-        self.action_space = [ActionXY(float(x), float(y)) for x, y in h.action_table]
+        if holonomic:
+            self.rotations = np.linspace(0, 2 * np.pi, self.rotation_samples, endpoint=False)
+        else:
+            self.rotations = np.linspace(-np.pi / 4, np.pi / 4, self.rotation_samples)
+        cls = ActionXY if holonomic else ActionRot
+        self.action_space = [cls(float(x), float(y)) for x, y in h.action_table]
 
     # -- GPU handles -------------------------------------------------------------------------------
     def handle(self, v_pref=1.0, precision=None):
         """BatchedSARL for (precision, v_pref) with the torch model's current weights."""
         precision = precision or self.precision
-        key = (precision, float(v_pref))
+        key = (precision, float(v_pref), self.kinematics)
         if key not in self._handles:
             d = self._dims
             self._handles[key] = [BatchedSARL(device=_cuda_index(self.device), precision=precision,
+                                              kinematics=KIN_CODE[self.kinematics],
                                               mlp1_dims=d["mlp1_dims"], mlp2_dims=d["mlp2_dims"],
                                               attn_dims=d["attn_dims"], mlp3_dims=d["mlp3_dims"],
                                               speed_samples=self.speed_samples, rotation_samples=self.rotation_samples,
@@ -270,14 +286,27 @@ class SARL(Policy):
             entry[1] = None
 
     # -- the reference call (multi_human_rl.py:11-63) ---------------------------------------------
+    def _single_env(self, state):
+        """One-env batch holding `state` (robot heading included) for predict() / transform()."""
+        agents = joint_state_to_agents(state)
+        H = agents.shape[0] - 1
+        kin = KIN_CODE[self.kinematics]
+        if self._single is None or self._single.H != H or self._single.cfg.robot_kinematics != kin:
+            self._single = BatchedCrowdSim(1, H, device=_cuda_index(self.device), time_step=self.time_step or 0.25,
+                                           robot_kinematics=kin)
+        self._single.set_state(agents[None])
+        if kin != _capi.KIN_HOLONOMIC:
+            self._single.set_theta(np.array([float(state.self_state.theta)]))
+        return self._single
+
     def predict(self, state):
-        from .envs import ActionXY
+        from .envs import ActionRot, ActionXY
         if self.phase is None or self.device is None:
             raise AttributeError("Phase, device attributes have to be set!")
         if self.phase == "train" and self.epsilon is None:
             raise AttributeError("Epsilon attribute has to be set in training phase")
         if self.reach_destination(state):
-            return ActionXY(0, 0)
+            return ActionXY(0, 0) if self.kinematics == "holonomic" else ActionRot(0, 0)
         v_pref = state.self_state.v_pref
         if self.action_space is None:
             self.build_action_space(v_pref)
@@ -289,13 +318,7 @@ class SARL(Policy):
                 b.orca()
                 self.env._human_v = True
         else:
-            agents = joint_state_to_agents(state)
-            H = agents.shape[0] - 1
-            if self._single is None or self._single.H != H:
-                self._single = BatchedCrowdSim(1, H, device=_cuda_index(self.device),
-                                               time_step=self.time_step or 0.25)
-            b = self._single
-            b.set_state(agents[None])
+            b = self._single_env(state)
         eps = float(self.epsilon) if self.phase == "train" else 0.0
         h.lookahead(b, query_env=self.query_env, epsilon=eps)
         try:
@@ -311,13 +334,7 @@ class SARL(Policy):
 
     def transform(self, state):
         """multi_human_rl.py:90-104 -> tensor (H, 13) on self.device."""
-        import torch
-        agents = joint_state_to_agents(state)
-        H = agents.shape[0] - 1
-        if self._single is None or self._single.H != H:
-            self._single = BatchedCrowdSim(1, H, device=_cuda_index(self.device), time_step=self.time_step or 0.25)
-        self._single.set_state(agents[None])
-        t = self.handle(state.self_state.v_pref).transform(self._single)[0]
+        t = self.handle(state.self_state.v_pref).transform(self._single_env(state))[0]
         return t.to(self.device) if self.device is not None else t
 
     def input_dim(self):

@@ -186,11 +186,11 @@ def gen_trajectories(specs=None, weights=None):
 
 
 def run_episode_chunk(args):
-    lo, hi, H, sim, qenv, wpath = args
+    lo, hi, H, sim, qenv, wpath, kinematics = args
     import torch
     torch.set_num_threads(1)
     env, robot, policy = refshim.make_env_and_sarl(human_num=H, sim=sim, query_env=qenv, seed=0,
-                                                    weights=np.load(wpath) if wpath else None)
+                                                    weights=np.load(wpath) if wpath else None, kinematics=kinematics)
     res = []
     for case in range(lo, hi):
         ob = env.reset("test", case)
@@ -205,10 +205,10 @@ def run_episode_chunk(args):
     return res
 
 
-def gen_episodes(n_proc, wpath=None, tag="seed0"):
-    """crowd_nav/test.py equivalent: 500 test cases, SARL, circle_crossing, H=5."""
+def gen_episodes(n_proc, wpath=None, tag="seed0", kinematics="holonomic"):
+    """crowd_nav/test.py equivalent: 500 test cases, SARL, circle_crossing, H=5.  kinematics=None: the fork as shipped."""
     import multiprocessing as mp
-    chunks = [(lo, min(lo + 10, 500), 5, "circle_crossing", False, wpath) for lo in range(0, 500, 10)]
+    chunks = [(lo, min(lo + 10, 500), 5, "circle_crossing", False, wpath, kinematics) for lo in range(0, 500, 10)]
     t0 = time.time()
     with mp.get_context("fork").Pool(n_proc) as pool:
         res = sum(pool.map(run_episode_chunk, chunks), [])
@@ -228,6 +228,7 @@ if __name__ == "__main__":
     ap.add_argument("--episodes", action="store_true")
     ap.add_argument("--procs", type=int, default=6)
     ap.add_argument("--skip-units", action="store_true")
+    ap.add_argument("--kin-none", action="store_true", help="with --episodes: the fork's literal kinematics (None)")
     ap.add_argument("--random", action="store_true", help="only the randomize_attributes trajectories")
     ap.add_argument("--kinematics", action="store_true", help="only the kinematics = None / unicycle trajectories")
     ap.add_argument("--trained", action="store_true", help="use tests/golden/sarl_weights_trained.npy (GPU-trained SARL)")
@@ -236,7 +237,9 @@ if __name__ == "__main__":
     assert refshim.available(), "/root/reference is required"
     os.makedirs(GOLD, exist_ok=True)
     oracle.build()
-    if a.episodes:
+    if a.episodes and a.kin_none:
+        gen_episodes(a.procs, wtrained if a.trained else None, "kin_none_" + ("trained" if a.trained else "seed0"), None)
+    elif a.episodes:
         gen_episodes(a.procs, wtrained if a.trained else None, "trained" if a.trained else "seed0")
     elif a.random:
         gen_trajectories(TRAJ_SPECS_RANDOM)

@@ -74,15 +74,26 @@ def _cfg(text, **over):
     return cp
 
 
-def _setup(weights0, precision="f32", query_env=False, human_num=5, sim="circle_crossing", randomize=False):
+KIN_NAME = {0: "holonomic", 1: "unicycle", 2: None}
+
+
+def _setup(weights0, precision="f32", query_env=False, human_num=5, sim="circle_crossing", randomize=False,
+           kinematics="holonomic"):
     """Wire env, robot, policy, explorer exactly as crowd_nav/test.py:52-87 does."""
     import torch
     import modelcrowdnav_b200 as mcn
     ecfg = _cfg(ENV_INI, sim__human_num=human_num, sim__train_val_sim=sim, sim__test_sim=sim,
                 env__randomize_attributes="true" if randomize else "false")
-    pcfg = _cfg(POLICY_INI, action_space__query_env="true" if query_env else "false")
+    pcfg = _cfg(POLICY_INI, action_space__query_env="true" if query_env else "false",
+                action_space__kinematics=kinematics or "holonomic")
     policy = mcn.policy_factory["sarl"]()
-    policy.configure(pcfg)
+    import modelcrowdnav_b200.policy as policy_mod
+    policy_mod.LITERAL_FORK_KINEMATICS = kinematics is None      # None: the fork never reads the key (cadrl.py:66)
+    try:
+        policy.configure(pcfg)
+    finally:
+        policy_mod.LITERAL_FORK_KINEMATICS = False
+    assert policy.kinematics == kinematics
     policy.precision = precision
     sd = policy.get_model().state_dict()
     off = 0
@@ -112,7 +123,8 @@ def test_state_dict_keys_match_reference(weights0, units):
 
 
 @pytest.mark.parametrize("name", ["circle5_qfalse", "circle5_qtrue", "circle5_qfalse_trained", "circle5_qtrue_trained",
-                                  "circle5_random", "square10_random"])
+                                  "circle5_random", "square10_random",
+                                  "circle5_kin_none", "circle5_kin_none_qtrue", "circle5_unicycle", "square10_unicycle_qtrue"])
 def test_facade_replays_reference_episode(name):
     """gym-style loop (explorer.py:53-69) through the single-env façade: ob/reward/done/info, action values and
     chosen actions equal the reference's, step by step, while the façade follows its own actions."""
@@ -120,7 +132,8 @@ def test_facade_replays_reference_episode(name):
     tr = load_traj(name)
     weights0 = weights_for(name)
     env, robot, policy, _ = _setup(weights0, "f32", query_env=bool(tr["query_env"]), human_num=tr["H"], sim=tr["sim"],
-                                   randomize=bool(tr["randomize"]))
+                                   randomize=bool(tr["randomize"]), kinematics=KIN_NAME[tr["kinematics"]])
+    holonomic = tr["kinematics"] == 0
     case = [c for c in tr["cases"] if c.startswith("test_")][0]
     rec = tr["cases"][case]
     ob = env.reset("test", int(case.split("_")[1]))
@@ -133,10 +146,14 @@ def test_facade_replays_reference_episode(name):
         ref_v = rec["values"][t]
         assert np.max(np.abs(np.array(policy.action_values) - ref_v)) <= 1e-5
         top2 = np.sort(ref_v)[-2:]
+        cls = mcn.ActionXY if holonomic else mcn.ActionRot
+        assert isinstance(action, cls)
         if top2[1] - top2[0] <= 2e-5:
-            action = mcn.ActionXY(*rec["action"][t])          # tie in the reference: follow its choice
+            action = cls(*rec["action"][t])                   # tie in the reference: follow its choice
         else:
-            assert (action.vx, action.vy) == tuple(rec["action"][t])
+            assert tuple(action) == tuple(rec["action"][t])
+        if not holonomic:
+            assert abs(env.robot.theta - rec["theta"][t]) <= 1e-12
         ob, reward, done, info = env.step(action)
         assert reward == rec["reward"][t] and done == bool(rec["done"][t])
         assert isinstance(info, info_types[int(rec["info"][t])])
@@ -164,7 +181,7 @@ def test_facade_errors_match_reference(weights0):
         env2.step(mcn.ActionRot(1.0, 0.0))                         # agent.py:104-108
 
 
-@pytest.mark.parametrize("wset", ["seed0", "trained"])
+@pytest.mark.parametrize("wset", ["seed0", "trained", "kin_none_trained"])
 @pytest.mark.parametrize("precision", ["f32", "f16_tc"])
 def test_explorer_500_test_episodes_match_reference(precision, wset):
     """crowd_nav/test.py equivalent: 500 test cases, SARL (random-init or GPU-trained weights), circle_crossing,
@@ -172,7 +189,8 @@ def test_explorer_500_test_episodes_match_reference(precision, wset):
     (scripts/gen_golden.py --episodes [--trained])."""
     g = np.load(os.path.join(GOLDEN, "episodes_circle5_%s.npz" % wset))
     weights0 = weights_for("x_" + wset)
-    env, robot, policy, explorer = _setup(weights0, precision)
+    # "kin_none_*": the fork exactly as shipped (policy.kinematics stays None: ActionRot actions, non-holonomic robot)
+    env, robot, policy, explorer = _setup(weights0, precision, kinematics=None if wset.startswith("kin_none") else "holonomic")
     ret, sr, cr, tr_, nav = explorer.run_k_episodes(env.case_size["test"], "test", print_failure=True, returnNav=True)
     run = explorer.last_run
     assert list(run["cases"]) == list(g["case"])
