@@ -99,7 +99,7 @@ class Explorer(object):
 
     # -- GPU plumbing ------------------------------------------------------------------------------
     def _batch(self, k):
-        key = (k, self.env.human_num)
+        key = (k, self.env.human_num, self.robot.kinematics)      # kinematics follows the robot's policy (ORCA -> SARL)
         if key not in self._batches:
             dev = getattr(self.device, "index", None) or 0     # torch.device('cuda') has index None -> GPU 0
             self._batches[key] = BatchedCrowdSim(k, self.env.human_num, device=dev, gamma=self.gamma or 0.9,
@@ -116,7 +116,8 @@ class Explorer(object):
             d = policy._dims
             self._target_handle = BatchedSARL(device=h.device, precision="f32", mlp1_dims=d["mlp1_dims"],
                                               mlp2_dims=d["mlp2_dims"], attn_dims=d["attn_dims"],
-                                              mlp3_dims=d["mlp3_dims"], gamma=policy.gamma, v_pref=self.robot.v_pref)
+                                              mlp3_dims=d["mlp3_dims"], gamma=policy.gamma, v_pref=self.robot.v_pref,
+                                              kinematics=h.cfg.kinematics)
             self._target_handle.load_weights(self.target_model.state_dict())
         return self._target_handle.forward(states.contiguous())
 
@@ -129,8 +130,8 @@ class Explorer(object):
         policy.set_phase(phase)
         if update_raw_ob or cacheFile is not None:
             raise NotImplementedError("raw-observation / SGAN caches belong to the model-based branch (out of scope)")
-        if robot.kinematics != "holonomic":
-            raise NotImplementedError("unicycle kinematics is outside the B200 hot path")
+        if robot.kinematics not in ("holonomic", "unicycle", None):
+            raise NotImplementedError("robot kinematics must be holonomic, unicycle or None (the fork's literal behaviour)")
         cases = env.next_cases(phase, k, test_case)
         agents = scenes.generate_batch(phase, cases, **env.scene_kwargs(phase))
         b = self._batch(k)
