@@ -221,6 +221,13 @@ int cn_rollout_step_host(cn_policy *p, cn_env *env, int query_env, double epsilo
 int cn_rollout_step_host_packed(cn_policy *p, cn_env *env, int query_env, double epsilon, const void *host_in,
                                 void *host_out, void *stream);
 int64_t cn_host_step_bytes(const cn_env *env, int out);
+/* Non-blocking form: enqueues copy-in, step and copy-out on `stream` and returns; host_out is valid after
+ * cn_stream_sync(device, stream).  A host loop that owns several env shards (one stream, one policy handle and one
+ * pair of pinned blocks per shard) overlaps the PCIe copies of one shard with the kernels of another: this is how a
+ * host-resident driver of explorer.py:62-69 keeps the GPU busy.  Pinned host memory is REQUIRED for the overlap. */
+int cn_rollout_step_host_packed_async(cn_policy *p, cn_env *env, int query_env, double epsilon, const void *host_in,
+                                      void *host_out, void *stream);
+int cn_stream_sync(int device, void *stream);
 
 /* Number of kernels this library launched so far in this process. */
 int64_t cn_launch_count(void);

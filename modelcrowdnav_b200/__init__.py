@@ -6,8 +6,8 @@ one-step lookahead, batched over thousands of environments per GPU behind a C AB
 """
 from . import _capi  # noqa: F401
 from ._capi import CrowdNavError  # noqa: F401
-from .batch import (BatchedCrowdSim, BatchedSARL, HostStepBuffers, PackedHostStepBuffers, rollout_step,  # noqa: F401
-                    rollout_step_host, rollout_step_host_packed)
+from .batch import (BatchedCrowdSim, BatchedSARL, HostStepBuffers, PackedHostStepBuffers, PipelinedHostRollout,  # noqa: F401
+                    rollout_step, rollout_step_host, rollout_step_host_packed)
 
 from .envs import (ActionRot, ActionXY, Collision, CrowdSim, Danger, FullState, Human, JointState, Nothing,  # noqa: F401
                    ObservableState, ReachGoal, Robot, Timeout)
@@ -18,5 +18,5 @@ __all__ = ["CrowdSim", "Robot", "Human", "SARL", "ORCA", "policy_factory", "Expl
            "ActionXY", "ActionRot", "FullState", "ObservableState", "JointState",
            "Timeout", "ReachGoal", "Danger", "Collision", "Nothing",
            "BatchedCrowdSim", "BatchedSARL", "HostStepBuffers", "PackedHostStepBuffers", "rollout_step", "rollout_step_host",
-           "rollout_step_host_packed",
+           "rollout_step_host_packed", "PipelinedHostRollout",
            "CrowdNavError"]

@@ -277,3 +277,84 @@ def rollout_step_host(policy, env, buf, query_env=False, epsilon=0.0, stream=Non
                                           _ptr(buf.agents_in), _ptr(buf.times_in), _ptr(buf.agents_out),
                                           _ptr(buf.times_out), _ptr(buf.reward), _ptr(buf.done), _ptr(buf.info),
                                           _ptr(buf.action_idx), _stream(stream)))
+
+
+class PipelinedHostRollout(object):
+    """Host-resident rollout of E envs split into `shards` env handles, each with its own stream, policy handle
+    and pair of pinned packed blocks.  ``step()`` advances every env once: while one shard's kernels run, the other
+    shards' host->device / device->host copies are in flight (cn_rollout_step_host_packed_async).  Per step every
+    env's state is uploaded from and downloaded to host memory, exactly like ``rollout_step_host_packed``; only the
+    order in which the shards are served overlaps.  Results do not depend on the shard count (envs are independent
+    and keyed by their global id)."""
+
+    def __init__(self, num_envs, human_num, weights, device=0, shards=2, precision="f16_tc", env_id_offset=0,
+                 policy_cfg=None, **env_cfg):
+        import torch
+        assert num_envs % shards == 0
+        self.E, self.shards, self.device = num_envs, shards, device
+        self.Es = num_envs // shards
+        self.envs, self.pols, self.bufs, self.streams = [], [], [], []
+        for k in range(shards):
+            env = BatchedCrowdSim(self.Es, human_num, device=device, env_id_offset=env_id_offset + k * self.Es, **env_cfg)
+            pol = BatchedSARL(device=device, precision=precision, **(policy_cfg or {}))
+            pol.load_weights(weights)
+            self.envs.append(env); self.pols.append(pol)
+            self.bufs.append(PackedHostStepBuffers(env))
+            self.streams.append(torch.cuda.Stream(device=device))
+        self.lib = self.envs[0].lib
+        self._busy = [False] * shards
+        self.h2d_bytes = sum(b.h2d_bytes for b in self.bufs)
+        self.d2h_bytes = sum(b.d2h_bytes for b in self.bufs)
+
+    def reset_device(self):
+        """CrowdSim.reset of every env on the GPU (scenes keyed by the global env id) -> host input blocks."""
+        for env, b in zip(self.envs, self.bufs):
+            env.reset_device()
+            a, t = env.get_state()
+            b.agents_in[...] = a; b.times_in[...] = t
+
+    def load_state(self, agents, times):
+        """Host state of all E envs -> the shards' input blocks."""
+        for k, b in enumerate(self.bufs):
+            sl = slice(k * self.Es, (k + 1) * self.Es)
+            b.agents_in[...] = agents[sl]; b.times_in[...] = times[sl]
+
+    def _wait(self, k):
+        if self._busy[k]:
+            check(self.lib.cn_stream_sync(self.device, C.c_void_p(self.streams[k].cuda_stream)))
+            self._busy[k] = False
+            self.bufs[k].swap()              # the state just downloaded is the next input (no host copy)
+
+    def step(self, query_env=False, epsilon=0.0):
+        """Enqueue one step of every shard; a shard is re-launched as soon as its previous step has landed."""
+        for k in range(self.shards):
+            self._wait(k)
+            b = self.bufs[k]
+            check(self.lib.cn_rollout_step_host_packed_async(
+                self.pols[k].handle, self.envs[k].handle, int(bool(query_env)), float(epsilon),
+                C.c_void_p(b.in_ptr), C.c_void_p(b.out_ptr), C.c_void_p(self.streams[k].cuda_stream)))
+            self._busy[k] = True
+
+    def sync(self):
+        """Wait for every shard; afterwards ``results()`` is valid."""
+        for k in range(self.shards):
+            self._wait(k)
+
+    def results(self):
+        """(agents, times, reward, action_idx, done, info) of the last completed step, concatenated over shards.
+        After ``sync()`` the downloaded blocks are the *input* side of the ping-pong."""
+        outs = []
+        for b in self.bufs:
+            E, A1 = b.E, b.A1
+            blk = b._blocks[b._in].numpy()
+            n = E * A1 * 8
+            off = 8 * (n + E)
+            outs.append((blk[:8 * n].view(np.float64).reshape(E, A1, 8), blk[8 * n:off].view(np.float64),
+                         blk[off:off + 8 * E].view(np.float64), blk[off + 8 * E:off + 12 * E].view(np.int32),
+                         blk[off + 12 * E:off + 13 * E], blk[off + 13 * E:off + 14 * E]))
+        return tuple(np.concatenate(x) for x in zip(*outs))
+
+    def close(self):
+        self.sync()
+        for e, p in zip(self.envs, self.pols):
+            e.close(); p.close()

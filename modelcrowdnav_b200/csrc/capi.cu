@@ -664,8 +664,8 @@ int64_t cn_host_step_bytes(const cn_env *env, int out)
     return out ? in + 8 * E + 4 * E + E + E : in;
 }
 
-int cn_rollout_step_host_packed(cn_policy *p, cn_env *env, int query_env, double epsilon, const void *host_in, void *host_out,
-                                void *stream)
+static int rollout_step_host_packed(cn_policy *p, cn_env *env, int query_env, double epsilon, const void *host_in,
+                                    void *host_out, void *stream, bool sync)
 {
     int rc = check_pair(p, env);
     if (rc) return rc;
@@ -678,7 +678,26 @@ int cn_rollout_step_host_packed(cn_policy *p, cn_env *env, int query_env, double
     if ((rc = cn_rollout_step(p, env, query_env, epsilon, s))) return rc;
     if ((rc = cn_launch_io(env, env->io_block, 0, s))) return rc;
     CN_CUDA_CHECK(cudaMemcpyAsync(host_out, env->io_block, (size_t)cn_host_step_bytes(env, 1), cudaMemcpyDeviceToHost, s));
-    CN_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (sync) CN_CUDA_CHECK(cudaStreamSynchronize(s));
+    return CN_OK;
+}
+
+int cn_rollout_step_host_packed(cn_policy *p, cn_env *env, int query_env, double epsilon, const void *host_in, void *host_out,
+                                void *stream)
+{
+    return rollout_step_host_packed(p, env, query_env, epsilon, host_in, host_out, stream, true);
+}
+
+int cn_rollout_step_host_packed_async(cn_policy *p, cn_env *env, int query_env, double epsilon, const void *host_in,
+                                      void *host_out, void *stream)
+{
+    return rollout_step_host_packed(p, env, query_env, epsilon, host_in, host_out, stream, false);
+}
+
+int cn_stream_sync(int device, void *stream)
+{
+    CN_CUDA_CHECK(cudaSetDevice(device));
+    CN_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
     return CN_OK;
 }
 

@@ -521,7 +521,7 @@ int cn_launch_robot_orca(cn_env *env, double safety_space, cudaStream_t s)
 int cn_launch_step(cn_env *env, const double *action_xy_dev, int update, cudaStream_t s)
 {
     const double *act = action_xy_dev ? action_xy_dev : env->action_xy;
-    step_kernel<<<grid_for(env->p.d.E, 128), 128, 0, s>>>(env->p, env->state, env->time, env->human_v, act,
+    step_kernel<<<grid_for(env->p.d.E, 64), 64, 0, s>>>(env->p, env->state, env->time, env->human_v, act,
                                                             action_xy_dev ? 1 : 0, update, env->reward, env->done,
                                                             env->info, env->dmin, env->next_obs, env->frozen,
                                                             env->acc, env->theta);
@@ -571,11 +571,14 @@ int cn_launch_io(cn_env *env, double *blk, int unpack, cudaStream_t s)
     const size_t n = (size_t)env->p.d.E * env->p.d.A1 * F_COUNT + env->p.d.E;
     int grid = (int)((n + 255) / 256);
     if (grid > 148 * 8) grid = 148 * 8;
+    // 128-thread blocks of <= 56 registers fit beside a resident tc_rows_pair CTA (7168 free registers per SM), so the
+    // small kernels of one env shard run under the row kernel of another (PipelinedHostRollout); step_kernel: 64 threads
+    grid *= 2;
     if (unpack) {
-        io_unpack_kernel<<<grid, 256, 0, s>>>(env->p.d, env->state, env->time, blk);
+        io_unpack_kernel<<<grid, 128, 0, s>>>(env->p.d, env->state, env->time, blk);
         env->orca_valid = 0;
     } else {
-        io_pack_kernel<<<grid, 256, 0, s>>>(env->p.d, env->state, env->time, env->reward, env->action_idx, env->done, env->info, blk);
+        io_pack_kernel<<<grid, 128, 0, s>>>(env->p.d, env->state, env->time, env->reward, env->action_idx, env->done, env->info, blk);
     }
     CN_LAUNCH_CHECK();
     return CN_OK;

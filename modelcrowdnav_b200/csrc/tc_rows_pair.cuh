@@ -193,7 +193,7 @@ constexpr uint32_t X_TILE_BYTES = bytes_of(ROWS, K_X);   // 8 KB: one tile of th
 // per tile against a 6-8 k cycle tile budget; three dedicated producer warps per CTA, re-measured with the final
 // kernel: 8.8e6 vs 1.07e7 env-steps/s).  Costs one 64 B / row round trip through L2 / HBM.
 template <int HT>
-__global__ void __launch_bounds__(ROWS)
+__global__ void __launch_bounds__(ROWS, 9)
 tc_features_kernel(EnvParams p, const double *__restrict__ st, const double *__restrict__ time,
                    const double *__restrict__ human_v, const double *__restrict__ actions, int A, int query_env, int NG,
                    int G_rt, const double *__restrict__ theta, uint8_t *__restrict__ X, uint8_t *__restrict__ J,

@@ -446,6 +446,35 @@ def test_packed_host_step_matches_device_step(mcn, oracle_mod, weights0):
     env_a.close(); env_b.close(); pol.close()
 
 
+@pytest.mark.parametrize("shards", [2, 4])
+def test_pipelined_host_rollout_matches_device_step(mcn, oracle_mod, weights0, shards):
+    """PipelinedHostRollout (env shards on their own streams, cn_rollout_step_host_packed_async: the copies of one
+    shard overlap the kernels of another) returns bit for bit what the single device-resident handle computes,
+    including the episodes that finish and are re-seeded on the device (global env ids key the Philox streams)."""
+    E, H = 256, 5
+    env = mcn.BatchedCrowdSim(E, H, auto_reset=1, seed=3)
+    pol = mcn.BatchedSARL(precision="f16_tc"); pol.load_weights(weights0)
+    env.reset_device()
+    a0, t0 = env.get_state()
+    pipe = mcn.PipelinedHostRollout(E, H, weights0, shards=shards, precision="f16_tc", auto_reset=1, seed=3)
+    pipe.reset_device()
+    b = [x for x in pipe.bufs]
+    assert np.array_equal(np.concatenate([x.agents_in for x in b]), a0)   # same scenes whatever the sharding
+    for step in range(110):                                          # past the 100-step time limit: episodes end
+        mcn.rollout_step(pol, env)
+        pipe.step()
+    pipe.sync()
+    sa, ta = env.get_state()
+    r, d, i, _ = env.read_outputs()
+    agents, times, reward, action_idx, done, info = pipe.results()
+    assert np.array_equal(sa, agents) and np.array_equal(ta, times)
+    assert np.array_equal(r, reward) and np.array_equal(d, done) and np.array_equal(i, info)
+    st = env.stats()
+    assert st["episodes"] > 0                                       # some episodes ended and were re-seeded
+    assert sum(e.stats()["episodes"] for e in pipe.envs) == st["episodes"]
+    pipe.close(); env.close(); pol.close()
+
+
 @pytest.mark.parametrize("precision", ["f32", "f16_tc"])
 @pytest.mark.parametrize("name", TRAJ_NAMES_KIN)
 def test_golden_trajectories_kinematics(mcn, weights0, name, precision):
