@@ -929,7 +929,8 @@ int cn_tc_load_weights(cn_policy *p, const float *flat, cudaStream_t s)
         split_rows(h + H_W1, a.data() + OFF_W1, N_H1, K_X, rank);
         split_rows(h + H_W2, a.data() + OFF_W2, N_M1, N_H1, rank);
         // stage 2, N = 224: rank 0 = mlp2.0 (all 112 rows), rank 1 = attention.0 rows on the mlp1_out half of K
-        memcpy(h + H_W3A, rank == 0 ? a.data() + OFF_W3 : a.data() + OFF_WA1, bytes_of(N_M1, N_M1));
+        // stage 2 is ONE N = 224 UMMA: rank 0's half = attention.0 (mlp1_out half of K) -> D [0,112), rank 1's = mlp2.0 -> [112,224)
+        memcpy(h + H_W3A, rank == 0 ? a.data() + OFF_WA1 : a.data() + OFF_W3, bytes_of(N_M1, N_M1));
         split_rows(h + H_WB, a.data() + OFF_WA1 + bytes_of(N_M1, N_M1), N_M1, N_M1, rank);   // group-mean half of K
         split_rows(h + H_W4, a.data() + OFF_W4, N_F, N_M1, rank);
         split_rows(h + H_WA2, a.data() + OFF_WA2, N_M1, N_M1, rank);

@@ -18,9 +18,9 @@
 //   stage  UMMA (M=256 over the pair)                         A operand        D          epilogue (CUDA cores)
 //   0      mlp1.0                K=32   N=160                 X    (R1 tail)   [0,160)    ReLU -> H1, fp16 packed IN PLACE in TMEM
 //   1      mlp1.2                K=160  N=112                 H1   (TMEM, TS)  [120,232)  ReLU -> mlp1_out (R2)
-//   2      [mlp2.0 | attn.0a]    K=112  N=224                 mlp1_out (R2)    [0,224)    group mean of mlp1_out in smem
-//   3      attn.0b (mean half)   K=112  N=112, accumulate     mean (R1)        [112,224)  ReLU -> H3 (R1), Ha1 (R2)
-//   4      mlp2.2 ; attn.2       K=112  N=64 ; N=112          H3 ; Ha1         [0,64) ; [64,176)
+//   2      [attn.0a | mlp2.0]    K=112  N=224                 mlp1_out (R2)    [0,224)    group mean of mlp1_out in smem
+//   3      attn.0b (mean half)   K=112  N=112, accumulate     mean (R1)        [0,112)    ReLU -> Ha1 fp16 IN PLACE in TMEM [0,56), H3 (R1)
+//   4      attn.2 ; mlp2.2       K=112  N=112 ; N=64          Ha1 (TMEM, TS) ; H3 (R1)   [56,168) ; [168,232)
 //          attention.4 as an fp32 dot -> masked softmax over the group -> w * F (fp32, smem) -> sum over the
 //          humans of the group in shared memory -> joint state J (fp16) -> HBM
 // The next tile's propagate / rotate features, clearances and rewards are computed under stages 2-3.
@@ -33,11 +33,13 @@ constexpr int N_S2 = 2 * N_M1;             // stage 2: [mlp2.0 (rank-0 half) | a
 constexpr int PAIR_CTX_COLS = 256;         // TMEM columns per tile context
 constexpr int T_H1B = 80;                  // H1 as packed fp16 (TS-mode A operand): K 0..79 at [0,40), K 80..159 at [80,120)
 constexpr int T_D1 = 120;                  // mlp1.2 accumulator [120,232)
+constexpr int T_A2 = N_M1 / 2;             // attention.2 accumulator [56,168): right behind Ha1 packed in place at [0,56)
+constexpr int T_F = T_A2 + N_M1;           // mlp2.2 accumulator (the pairwise features F) [168,232)
 
 // per-CTA HALF weight image: rows [rank * N/2, (rank+1) * N/2) of every layer, chunked K-major with R = N/2
 constexpr uint32_t H_W1 = 0;                                        //  80 x 32
 constexpr uint32_t H_W2 = H_W1 + bytes_of(N_H1 / 2, K_X);           //  56 x 160
-constexpr uint32_t H_W3A = H_W2 + bytes_of(N_M1 / 2, N_H1);         // 112 x 112  (rank 0: mlp2.0, rank 1: attention.0 first half)
+constexpr uint32_t H_W3A = H_W2 + bytes_of(N_M1 / 2, N_H1);         // 112 x 112  (rank 0: attention.0 first half, rank 1: mlp2.0)
 constexpr uint32_t H_WB = H_W3A + bytes_of(N_M1, N_M1);             //  56 x 112  attention.0, group-mean half
 constexpr uint32_t H_W4 = H_WB + bytes_of(N_M1 / 2, N_M1);          //  32 x 112
 constexpr uint32_t H_WA2 = H_W4 + bytes_of(N_F / 2, N_M1);          //  56 x 112
@@ -326,11 +328,12 @@ tc_rows_pair_kernel(EnvParams p,
                     } else if (s == 2) {
                         mma_layer_2(tm, sR2, ROWS, sW3A, N_M1, N_S2, false);          // completion rides on stage 3's commit
                     } else if (s == 3) {
-                        mma_layer_2(tm + N_M1, sR1, ROWS, sWB, N_M1, N_M1, true);
+                        mma_layer_2(tm, sR1, ROWS, sWB, N_M1, N_M1, true);             // attention.0 accumulator = [0,112)
                         commit_2(done, 3);
                     } else {
-                        mma_layer_2(tm, sR1, ROWS, sW4, N_M1, N_F, false);
-                        mma_layer_2(tm + N_F, sR2, ROWS, sWA2, N_M1, N_M1, false);
+                        // A of attention.2 = Ha1 straight from TMEM (packed in place by the hf-0 warps)
+                        mma_steps_2_ts(tm + T_A2, tm, sWA2, 0, N_M1 / 16, N_M1, false);
+                        mma_layer_2(tm + T_F, sR1, ROWS, sW4, N_M1, N_F, false);
                         commit_2(done, 3);
                     }
                     QPROBE(2 + c, 2 * s + 1);
@@ -452,8 +455,8 @@ tc_rows_pair_kernel(EnvParams p,
             QPROBE(ctx, 6);
             // ---- E3: H3 = relu(acc[0,112)) -> R1 (hf 0) ; Ha1 = relu(acc[112,224)) -> R2 (hf 1) ----
             PAIR_WAIT(); QPROBE(ctx, 7);
-            if (hf == 0) epilogue_to_smem<true>(tl, 0, N_M1, R1, row, 0);
-            else epilogue_to_smem<true>(tl, N_M1, N_M1, R2, row, 0);
+            if (hf == 0) compact_to_tmem<true>(tl, 0, N_M1, 0, 1.0f);               // Ha1: fp16 pairs in place, [0,56)
+            else epilogue_to_smem<true>(tl, N_M1, N_M1, R1, row, 0);
             PAIR_SIGNAL(); QPROBE(ctx, 8);
             // ---- E4: attention.4 dot (split over the column halves), masked softmax (sarl.py:48-53), w * F ----
             PAIR_WAIT(); QPROBE(ctx, 9);
@@ -461,8 +464,8 @@ tc_rows_pair_kernel(EnvParams p,
                 float part = 0.0f;
                 if (hf == 0) {
                     uint32_t v[32], u[32];
-                    ld32(tl + N_F, v);
-                    ld32(tl + N_F + 32, u);
+                    ld32(tl + T_A2, v);
+                    ld32(tl + T_A2 + 32, u);
                     wait_ld();
 #pragma unroll
                     for (int k = 0; k < 32; ++k) part = fmaf(fmaxf(__uint_as_float(v[k]), 0.0f), tw.w[k], part);
@@ -471,8 +474,8 @@ tc_rows_pair_kernel(EnvParams p,
                     S0[row] = part;
                 } else {
                     uint32_t x[32], y[16];
-                    ld32(tl + N_F + 64, x);
-                    ld16(tl + N_F + 96, y);
+                    ld32(tl + T_A2 + 64, x);
+                    ld16(tl + T_A2 + 96, y);
                     wait_ld();
 #pragma unroll
                     for (int k = 0; k < 32; ++k) part = fmaf(fmaxf(__uint_as_float(x[k]), 0.0f), tw.w[64 + k], part);
@@ -510,7 +513,7 @@ tc_rows_pair_kernel(EnvParams p,
                 // w * F as fp16 (fp32 product rounded once), chunked like an operand over the (dead) Ha1 tile in R2 -- not R1:
                 // the next tile's H1 epilogue may start while slower warps still sum: hf 0 -> features 0..31, hf 1 -> 32..55
                 uint32_t v[32];
-                ld32(tl + hf * 32, v);
+                ld32(tl + T_F + hf * 32, v);
                 wait_ld();
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
