@@ -60,6 +60,24 @@ class SarlCfg(C.Structure):
                    (C.c_int * 3)(100, 100, 1), (C.c_int * 4)(150, 100, 100, 1))
 
 
+NET_SARL, NET_CADRL, NET_LSTM_RL = 0, 1, 2
+
+
+class NetCfg(C.Structure):
+    """crowd_nav/configs/policy.config [cadrl] / [lstm_rl] (orc_net_cfg)."""
+    _fields_ = [("network", C.c_int), ("input_dim", C.c_int), ("self_state_dim", C.c_int), ("mlp_dims", C.c_int * 4),
+                ("lstm_hidden", C.c_int), ("mlp1_dims", C.c_int * 4)]
+
+    @classmethod
+    def cadrl(cls):
+        return cls(NET_CADRL, 13, 6, (C.c_int * 4)(150, 100, 100, 1), 0, (C.c_int * 4)(0, 0, 0, 0))
+
+    @classmethod
+    def lstm_rl(cls, with_interaction_module=False):
+        m1 = (150, 100, 100, 50) if with_interaction_module else (0, 0, 0, 0)
+        return cls(NET_LSTM_RL, 13, 6, (C.c_int * 4)(150, 100, 100, 1), 50, (C.c_int * 4)(*m1))
+
+
 _lib = None
 
 
@@ -107,6 +125,13 @@ def lib():
                                                dp, dp, C.c_int, dp, C.c_int, C.c_double,
                                                C.POINTER(C.c_int32), dp, C.POINTER(C.c_uint8),
                                                C.POINTER(C.c_uint8), C.c_int]
+        L.orc_net_param_count.argtypes = [C.POINTER(NetCfg)]
+        L.orc_net_param_count.restype = C.c_int64
+        L.orc_net_forward.argtypes = [C.POINTER(NetCfg), fp, C.c_int, fp, fp]
+        L.orc_lookahead_net.argtypes = [C.POINTER(EnvCfg), C.POINTER(NetCfg), fp, C.c_int, dp, C.c_double, C.c_int,
+                                        C.c_double, C.c_int, dp, C.c_int, dp, C.c_double, dp, ip]
+        L.orc_lookahead_net.restype = C.c_int
+        L.orc_lstm_human_order.argtypes = [C.c_int, dp, ip]
         _lib = L
     return _lib
 
@@ -240,6 +265,64 @@ def lookahead(ecfg, scfg, weights, agents, global_time, actions, query_env, huma
                                  float(global_time), int(kinematics), float(theta), actions.shape[0], _dp(actions),
                                  int(query_env), _dp(hv), float(gamma), _dp(values), C.byref(reached))
     return best, values, bool(reached.value)
+
+
+def net_param_count(ncfg):
+    return int(lib().orc_net_param_count(C.byref(ncfg)))
+
+
+def net_forward(ncfg, weights, x):
+    """model(x) for x (H, 13): CADRL -> (H,) values, LSTM-RL -> scalar."""
+    x = _f32(x); weights = _f32(weights)
+    assert weights.size == net_param_count(ncfg)
+    out = np.zeros(max(1, x.shape[0]), np.float32)
+    lib().orc_net_forward(C.byref(ncfg), _fp(weights), x.shape[0], _fp(x), _fp(out))
+    return out if ncfg.network == NET_CADRL else float(out[0])
+
+
+def lookahead_net(ecfg, ncfg, weights, agents, global_time, actions, query_env, human_vxy, gamma=0.9,
+                  kinematics=KIN_HOLONOMIC, theta=0.0):
+    """CADRL.predict / LstmRL.predict greedy branch (same return convention as lookahead)."""
+    agents = _f64(agents); actions = _f64(actions); weights = _f32(weights)
+    hv = _f64(human_vxy if human_vxy is not None else np.zeros((agents.shape[0] - 1, 2)))
+    values = np.full(actions.shape[0], np.nan)
+    reached = C.c_int()
+    best = lib().orc_lookahead_net(C.byref(ecfg), C.byref(ncfg), _fp(weights), agents.shape[0] - 1, _dp(agents),
+                                   float(global_time), int(kinematics), float(theta), actions.shape[0], _dp(actions),
+                                   int(query_env), _dp(hv), float(gamma), _dp(values), C.byref(reached))
+    return best, values, bool(reached.value)
+
+
+def lstm_human_order(agents):
+    agents = _f64(agents)
+    order = np.zeros(agents.shape[0] - 1, np.int32)
+    lib().orc_lstm_human_order(agents.shape[0] - 1, _dp(agents), order.ctypes.data_as(C.POINTER(C.c_int)))
+    return order
+
+
+def default_net_weights(ncfg, seed=0):
+    """Flat f32 parameters (state-dict order) of the reference's CADRL / LSTM-RL ValueNetwork under torch.manual_seed(seed):
+    the construction order (and hence the RNG stream) of cadrl.py:22-26 / lstm_rl.py:9-16,37-45."""
+    import torch
+    import torch.nn as nn
+    torch.manual_seed(seed)
+
+    def mlp(i, dims):
+        d = [i] + list(dims)
+        return [nn.Linear(d[k], d[k + 1]) for k in range(len(d) - 1)]
+    flat = []
+    if ncfg.network == NET_CADRL:
+        mods = mlp(ncfg.input_dim, ncfg.mlp_dims)
+    else:
+        m1 = mlp(ncfg.input_dim, ncfg.mlp1_dims) if ncfg.mlp1_dims[0] > 0 else []
+        m = mlp(ncfg.self_state_dim + ncfg.lstm_hidden, ncfg.mlp_dims)
+        lstm = nn.LSTM(ncfg.mlp1_dims[3] if m1 else ncfg.input_dim, ncfg.lstm_hidden, batch_first=True)
+        mods = m1 + m
+    for l in mods:
+        flat += [l.weight.detach().numpy().ravel(), l.bias.detach().numpy().ravel()]
+    if ncfg.network == NET_LSTM_RL:
+        flat += [t.detach().numpy().ravel() for t in (lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0)]
+    return np.concatenate(flat).astype(np.float32)
 
 
 def transform(agents, kinematics=KIN_HOLONOMIC, theta=0.0):

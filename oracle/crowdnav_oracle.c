@@ -634,7 +634,29 @@ void orc_transform(int H, const double *agents, float *out)
 }
 
 /* multi_human_rl.py:11-63 (greedy branch) */
+typedef double (*value_fn)(const void *ctx, int H, const float *x);
+static int lookahead_generic(const orc_env_cfg *ecfg, value_fn vf, const void *vctx, const int *order, int H,
+                  const double *agents, double global_time, int kinematics, double theta, int A, const double *actions,
+                  int query_env, const double *human_vxy, double gamma, double *values_out, int *reached);
+
+typedef struct { const orc_sarl_cfg *c; const sarl_prep *P; } sarl_ctx;
+static double sarl_value(const void *ctx, int H, const float *x)
+{
+    const sarl_ctx *s = (const sarl_ctx *)ctx;
+    return (double)sarl_forward_prepared(s->c, s->P, H, x, NULL);
+}
+
 static int lookahead_prepared(const orc_env_cfg *ecfg, const orc_sarl_cfg *scfg, const sarl_prep *P, int H,
+                  const double *agents, double global_time, int kinematics, double theta, int A, const double *actions,
+                  int query_env, const double *human_vxy, double gamma, double *values_out, int *reached)
+{
+    const sarl_ctx ctx = {scfg, P};
+    return lookahead_generic(ecfg, sarl_value, &ctx, NULL, H, agents, global_time, kinematics, theta, A, actions, query_env,
+                             human_vxy, gamma, values_out, reached);
+}
+
+/* order (may be NULL = env order): position j of the network input is human order[j] (0-based) */
+static int lookahead_generic(const orc_env_cfg *ecfg, value_fn vf, const void *vctx, const int *order, int H,
                   const double *agents, double global_time, int kinematics, double theta, int A, const double *actions,
                   int query_env, const double *human_vxy, double gamma, double *values_out, int *reached)
 {
@@ -657,13 +679,14 @@ static int lookahead_prepared(const orc_env_cfg *ecfg, const orc_sarl_cfg *scfg,
         const double next_theta = kinematics == ORC_KIN_HOLONOMIC ? theta : theta + actions[2 * a + 1];
         const double npx = AG(0, F_PX) + ax * dt, npy = AG(0, F_PY) + ay * dt;
         double reward;
-        for (int h = 1; h <= H; ++h) {
+        for (int j = 1; j <= H; ++j) {
+            const int h = order ? order[j - 1] + 1 : j;
             double hvx, hvy;
             if (query_env) { hvx = human_vxy[2 * (h - 1)]; hvy = human_vxy[2 * (h - 1) + 1]; } /* agent.py:63-74 */
             else { hvx = AG(h, F_VX); hvy = AG(h, F_VY); }                                    /* cadrl.py:107-109 */
-            nhx[h - 1] = AG(h, F_PX) + hvx * dt;
-            nhy[h - 1] = AG(h, F_PY) + hvy * dt;
-            nhvx[h - 1] = hvx; nhvy[h - 1] = hvy; hr[h - 1] = AG(h, F_R);
+            nhx[j - 1] = AG(h, F_PX) + hvx * dt;
+            nhy[j - 1] = AG(h, F_PY) + hvy * dt;
+            nhvx[j - 1] = hvx; nhvy[j - 1] = hvy; hr[j - 1] = AG(h, F_R);
         }
         if (query_env) {
             int done, info;
@@ -680,7 +703,7 @@ static int lookahead_prepared(const orc_env_cfg *ecfg, const orc_sarl_cfg *scfg,
             row[12] = (float)nhvy[h]; row[13] = (float)hr[h];
             orc_rotate_k(row, kinematics, x + (size_t)h * 13);
         }
-        const double v = (double)sarl_forward_prepared(scfg, P, H, x, NULL);
+        const double v = vf(vctx, H, x);
         const double value = reward + gamma_bar * v;
         values_out[a] = value;
         if (value > max_value) { max_value = value; max_action = a; }
@@ -709,6 +732,158 @@ int orc_lookahead_k(const orc_env_cfg *ecfg, const orc_sarl_cfg *scfg, const flo
     sarl_prepare(scfg, weights, &P);
     const int r = lookahead_prepared(ecfg, scfg, &P, H, agents, global_time, kinematics, theta, A, actions, query_env,
                                      human_vxy, gamma, values_out, reached);
+    free(P.store);
+    return r;
+}
+
+/* ---- CADRL / LSTM-RL value networks --------------------------------------------------------- */
+typedef struct { lin_t m1[4], m[4], ih, hh; int n1; float *store; } net_prep;
+
+int64_t orc_net_param_count(const orc_net_cfg *c)
+{
+    int64_t n = 0;
+    int in = c->input_dim;
+    if (c->network == ORC_NET_CADRL) {
+        for (int i = 0; i < 4; ++i) { n += (int64_t)in * c->mlp_dims[i] + c->mlp_dims[i]; in = c->mlp_dims[i]; }
+        return n;
+    }
+    int lstm_in = c->input_dim;
+    if (c->mlp1_dims[0] > 0) {
+        for (int i = 0; i < 4; ++i) { n += (int64_t)in * c->mlp1_dims[i] + c->mlp1_dims[i]; in = c->mlp1_dims[i]; }
+        lstm_in = c->mlp1_dims[3];
+    }
+    in = c->self_state_dim + c->lstm_hidden;
+    for (int i = 0; i < 4; ++i) { n += (int64_t)in * c->mlp_dims[i] + c->mlp_dims[i]; in = c->mlp_dims[i]; }
+    const int G = 4 * c->lstm_hidden;
+    n += (int64_t)G * lstm_in + (int64_t)G * c->lstm_hidden + 2 * G;
+    return n;
+}
+
+static void net_prepare(const orc_net_cfg *c, const float *weights, net_prep *P)
+{
+    P->store = (float *)malloc(sizeof(float) * (size_t)orc_net_param_count(c));
+    float *st = P->store;
+    const float *p = weights;
+    int in = c->input_dim;
+    P->n1 = 0;
+    if (c->network == ORC_NET_CADRL) {
+        for (int i = 0; i < 4; ++i) { p = take_linear(p, in, c->mlp_dims[i], &P->m[i], &st); in = c->mlp_dims[i]; }
+        return;
+    }
+    int lstm_in = c->input_dim;
+    if (c->mlp1_dims[0] > 0) {
+        P->n1 = 4;
+        for (int i = 0; i < 4; ++i) { p = take_linear(p, in, c->mlp1_dims[i], &P->m1[i], &st); in = c->mlp1_dims[i]; }
+        lstm_in = c->mlp1_dims[3];
+    }
+    in = c->self_state_dim + c->lstm_hidden;
+    for (int i = 0; i < 4; ++i) { p = take_linear(p, in, c->mlp_dims[i], &P->m[i], &st); in = c->mlp_dims[i]; }
+    /* nn.LSTM parameters: weight_ih_l0 [4h][in], weight_hh_l0 [4h][h], bias_ih_l0 [4h], bias_hh_l0 [4h] */
+    const int G = 4 * c->lstm_hidden, Hh = c->lstm_hidden;
+    const float *w_ih = p, *w_hh = p + (size_t)G * lstm_in, *b_ih = w_hh + (size_t)G * Hh, *b_hh = b_ih + G;
+    P->ih.wt = st; st += (size_t)G * lstm_in;
+    for (int o = 0; o < G; ++o) for (int k = 0; k < lstm_in; ++k) P->ih.wt[(size_t)k * G + o] = w_ih[(size_t)o * lstm_in + k];
+    P->ih.b = b_ih; P->ih.in = lstm_in; P->ih.out = G;
+    P->hh.wt = st; st += (size_t)G * Hh;
+    for (int o = 0; o < G; ++o) for (int k = 0; k < Hh; ++k) P->hh.wt[(size_t)k * G + o] = w_hh[(size_t)o * Hh + k];
+    P->hh.b = b_hh; P->hh.in = Hh; P->hh.out = G;
+}
+
+static inline float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+static void net_forward_prepared(const orc_net_cfg *c, const net_prep *P, int H, const float *x, float *out)
+{
+    float t0[ORC_MAXDIM], t1[ORC_MAXDIM];
+    if (c->network == ORC_NET_CADRL) {                                  /* cadrl.py:22-30 */
+        for (int h = 0; h < H; ++h) {
+            linear_fwd(&P->m[0], x + (size_t)h * c->input_dim, t0, 1);
+            linear_fwd(&P->m[1], t0, t1, 1);
+            linear_fwd(&P->m[2], t1, t0, 1);
+            linear_fwd(&P->m[3], t0, &out[h], 0);
+        }
+        return;
+    }
+    const int Hh = c->lstm_hidden;
+    float hs[ORC_MAXDIM], cs[ORC_MAXDIM], gi[ORC_MAXDIM], gh[ORC_MAXDIM];
+    for (int k = 0; k < Hh; ++k) hs[k] = cs[k] = 0.0f;                  /* lstm_rl.py:27-28 */
+    for (int t = 0; t < H; ++t) {
+        const float *xt = x + (size_t)t * c->input_dim;
+        if (P->n1) {                                                    /* ValueNetwork2: mlp1, no last ReLU (lstm_rl.py:56) */
+            linear_fwd(&P->m1[0], xt, t0, 1);
+            linear_fwd(&P->m1[1], t0, t1, 1);
+            linear_fwd(&P->m1[2], t1, t0, 1);
+            linear_fwd(&P->m1[3], t0, t1, 0);
+            xt = t1;
+        }
+        linear_fwd(&P->ih, xt, gi, 0);
+        linear_fwd(&P->hh, hs, gh, 0);
+        for (int k = 0; k < Hh; ++k) {                                  /* gate order i, f, g, o */
+            const float ig = sigmoidf_(gi[k] + gh[k]), fg = sigmoidf_(gi[Hh + k] + gh[Hh + k]);
+            const float gg = tanhf(gi[2 * Hh + k] + gh[2 * Hh + k]), og = sigmoidf_(gi[3 * Hh + k] + gh[3 * Hh + k]);
+            cs[k] = fg * cs[k] + ig * gg;
+            hs[k] = og * tanhf(cs[k]);
+        }
+    }
+    float joint[ORC_MAXDIM];
+    for (int k = 0; k < c->self_state_dim; ++k) joint[k] = x[k];        /* lstm_rl.py:25,31 */
+    for (int k = 0; k < Hh; ++k) joint[c->self_state_dim + k] = hs[k];
+    linear_fwd(&P->m[0], joint, t0, 1);
+    linear_fwd(&P->m[1], t0, t1, 1);
+    linear_fwd(&P->m[2], t1, t0, 1);
+    linear_fwd(&P->m[3], t0, &out[0], 0);
+}
+
+void orc_net_forward(const orc_net_cfg *c, const float *weights, int H, const float *x, float *out)
+{
+    net_prep P;
+    net_prepare(c, weights, &P);
+    net_forward_prepared(c, &P, H, x, out);
+    free(P.store);
+}
+
+typedef struct { const orc_net_cfg *c; const net_prep *P; } net_ctx;
+static double net_value(const void *ctx, int H, const float *x)
+{
+    const net_ctx *n = (const net_ctx *)ctx;
+    float out[ORC_MAXH];
+    net_forward_prepared(n->c, n->P, H, x, out);
+    if (n->c->network == ORC_NET_CADRL) {                               /* cadrl.py:165: torch.min(outputs, 0) */
+        float m = out[0];
+        for (int h = 1; h < H; ++h) if (out[h] < m) m = out[h];
+        return (double)m;
+    }
+    return (double)out[0];
+}
+
+/* lstm_rl.py:99-104: sorted(human_states, key=dist, reverse=True) -- stable, ties keep the env order */
+void orc_lstm_human_order(int H, const double *agents, int *order)
+{
+    double d[ORC_MAXH];
+    for (int h = 0; h < H; ++h) {
+        d[h] = norm2(AG(h + 1, F_PX) - AG(0, F_PX), AG(h + 1, F_PY) - AG(0, F_PY));
+        order[h] = h;
+    }
+    for (int i = 1; i < H; ++i) {                                       /* stable insertion sort, descending */
+        const int oi = order[i];
+        int j = i - 1;
+        while (j >= 0 && d[order[j]] < d[oi]) { order[j + 1] = order[j]; --j; }
+        order[j + 1] = oi;
+    }
+}
+
+int orc_lookahead_net(const orc_env_cfg *ecfg, const orc_net_cfg *ncfg, const float *weights, int H,
+                      const double *agents, double global_time, int kinematics, double theta, int A,
+                      const double *actions, int query_env, const double *human_vxy, double gamma, double *values_out,
+                      int *reached)
+{
+    net_prep P;
+    net_prepare(ncfg, weights, &P);
+    const net_ctx ctx = {ncfg, &P};
+    int order[ORC_MAXH];
+    const int sorted = ncfg->network == ORC_NET_LSTM_RL && !query_env;
+    if (sorted) orc_lstm_human_order(H, agents, order);
+    const int r = lookahead_generic(ecfg, net_value, &ctx, sorted ? order : NULL, H, agents, global_time, kinematics, theta,
+                                    A, actions, query_env, human_vxy, gamma, values_out, reached);
     free(P.store);
     return r;
 }

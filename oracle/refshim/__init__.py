@@ -72,7 +72,7 @@ def load_flat_weights(model, flat):
 
 
 def make_env_and_sarl(human_num=5, sim="circle_crossing", query_env=False, seed=0, robot_visible=False, weights=None,
-                      randomize=False, kinematics="holonomic"):
+                      randomize=False, kinematics="holonomic", policy_name="sarl", policy_over=None):
     """Reference CrowdSim + Robot + SARL wired as crowd_nav/test.py:52-87 does (holonomic honoured)."""
     install()
     import torch
@@ -80,9 +80,13 @@ def make_env_and_sarl(human_num=5, sim="circle_crossing", query_env=False, seed=
     from crowd_sim.envs.utils.robot import Robot
     from crowd_nav.policy.policy_factory import policy_factory
     ecfg = env_config(human_num, sim, robot_visible, env__randomize_attributes="true" if randomize else "false")
-    policy = policy_factory["sarl"]()
+    policy = policy_factory[policy_name]()
     torch.manual_seed(seed)
-    policy.configure(policy_config(query_env))
+    pcfg = policy_config(query_env)
+    for k, v in (policy_over or {}).items():
+        sec, key = k.split("__")
+        pcfg.set(sec, key, str(v))
+    policy.configure(pcfg)
     # kinematics="holonomic": policy.config:14 honoured.  kinematics=None: the fork as shipped -- cadrl.py:66 comments the
     # config read out, so policy.kinematics stays None (ActionRot dynamics, theta feature zero).  "unicycle": explicit.
     policy.kinematics = kinematics

@@ -161,16 +161,60 @@ TRAJ_SPECS_TRAINED = [
 ]
 
 
+# the other value networks behind the same lookahead (policy_factory: cadrl, lstm_rl): name, ..., randomize, kinematics,
+# policy name, policy.config overrides
+TRAJ_SPECS_NETS = [
+    ("cadrl_circle5", 5, "circle_crossing", False, False, [("test", 40, 30), ("test", 41, 30)], False, "holonomic", "cadrl", None),
+    ("cadrl_circle5_qtrue", 5, "circle_crossing", True, False, [("test", 42, 20)], False, "holonomic", "cadrl", None),
+    ("cadrl_circle1", 1, "circle_crossing", False, False, [("test", 43, 30)], False, "holonomic", "cadrl", None),
+    ("lstm_circle5", 5, "circle_crossing", False, False, [("test", 44, 30), ("test", 45, 30)], False, "holonomic", "lstm_rl", None),
+    ("lstm_circle5_qtrue", 5, "circle_crossing", True, False, [("test", 46, 20)], False, "holonomic", "lstm_rl", None),
+    ("lstm2_square10", 10, "square_crossing", False, False, [("test", 47, 20)], False, "holonomic", "lstm_rl",
+     {"lstm_rl__with_interaction_module": "true"}),
+]
+
+
+def gen_net_units():
+    """model(x) of the reference's CADRL / LSTM-RL value networks on rotated random joint states + their seed-0 weights."""
+    import torch
+    out = {}
+    rs = np.random.RandomState(4321)
+    for tag, pname, over, ncfg in (("cadrl", "cadrl", None, oracle.NetCfg.cadrl()),
+                                   ("lstm", "lstm_rl", None, oracle.NetCfg.lstm_rl()),
+                                   ("lstm2", "lstm_rl", {"lstm_rl__with_interaction_module": "true"}, oracle.NetCfg.lstm_rl(True))):
+        env, robot, policy = refshim.make_env_and_sarl(seed=0, policy_name=pname, policy_over=over)
+        sd = policy.get_model().state_dict()
+        flat = np.concatenate([v.numpy().ravel() for v in sd.values()]).astype(np.float32)
+        assert np.array_equal(flat, oracle.default_net_weights(ncfg, 0)), "oracle weight init differs from reference: " + tag
+        out[tag + "_weight_keys"] = np.array(list(sd.keys()))
+        out[tag + "_weights"] = flat
+        for H in (1, 5):
+            rows = rs.uniform(-4, 4, size=(32 * H, 14)).astype(np.float32)
+            x = policy.rotate(torch.from_numpy(rows)).reshape(32, H, 13)
+            with torch.no_grad():
+                if pname == "cadrl":
+                    v = policy.get_model()(x.reshape(-1, 13)).numpy().reshape(32, H)
+                else:
+                    v = policy.get_model()(x).numpy().ravel()
+            out["%s_in_h%d" % (tag, H)] = x.numpy()
+            out["%s_out_h%d" % (tag, H)] = v
+    np.savez_compressed(os.path.join(GOLD, "units_nets.npz"), **out)
+    print("units_nets.npz written;", len(out), "arrays")
+
+
 def gen_trajectories(specs=None, weights=None):
     for spec in (specs or TRAJ_SPECS):
         name, H, sim, qenv, vis, cases = spec[:6]
         randomize = bool(spec[6]) if len(spec) > 6 else False
         kinematics = spec[7] if len(spec) > 7 else "holonomic"
+        pname = spec[8] if len(spec) > 8 else "sarl"
+        pover = spec[9] if len(spec) > 9 else None
         env, robot, policy = refshim.make_env_and_sarl(human_num=H, sim=sim, query_env=qenv, seed=0,
                                                         robot_visible=vis, weights=weights, randomize=randomize,
-                                                        kinematics=kinematics)
+                                                        kinematics=kinematics, policy_name=pname, policy_over=pover)
         out = {"H": np.array(H), "query_env": np.array(int(qenv)), "robot_visible": np.array(int(vis)),
-               "sim": np.array(sim), "randomize": np.array(int(randomize)), "kinematics": np.array(KIN_CODE[kinematics])}
+               "sim": np.array(sim), "randomize": np.array(int(randomize)), "kinematics": np.array(KIN_CODE[kinematics]),
+               "policy": np.array(pname), "interaction_module": np.array(int(bool(pover)))}
         t0 = time.time()
         for (phase, case, max_steps) in cases:
             rec = run_trajectory(env, robot, policy, phase, case, max_steps)
@@ -231,6 +275,7 @@ if __name__ == "__main__":
     ap.add_argument("--kin-none", action="store_true", help="with --episodes: the fork's literal kinematics (None)")
     ap.add_argument("--random", action="store_true", help="only the randomize_attributes trajectories")
     ap.add_argument("--kinematics", action="store_true", help="only the kinematics = None / unicycle trajectories")
+    ap.add_argument("--nets", action="store_true", help="only the CADRL / LSTM-RL unit vectors and trajectories")
     ap.add_argument("--trained", action="store_true", help="use tests/golden/sarl_weights_trained.npy (GPU-trained SARL)")
     a = ap.parse_args()
     wtrained = os.path.join(GOLD, "sarl_weights_trained.npy")
@@ -241,6 +286,9 @@ if __name__ == "__main__":
         gen_episodes(a.procs, wtrained if a.trained else None, "kin_none_" + ("trained" if a.trained else "seed0"), None)
     elif a.episodes:
         gen_episodes(a.procs, wtrained if a.trained else None, "trained" if a.trained else "seed0")
+    elif a.nets:
+        gen_net_units()
+        gen_trajectories(TRAJ_SPECS_NETS)
     elif a.random:
         gen_trajectories(TRAJ_SPECS_RANDOM)
     elif a.kinematics:

@@ -35,6 +35,8 @@ def weights0():
 def load_traj(name):
     z = np.load(os.path.join(GOLDEN, "traj_%s.npz" % name), allow_pickle=False)
     out = {"H": int(z["H"]), "query_env": int(z["query_env"]), "robot_visible": int(z["robot_visible"]),
+           "policy": str(z["policy"]) if "policy" in z.files else "sarl",
+           "interaction_module": int(z["interaction_module"]) if "interaction_module" in z.files else 0,
            "sim": str(z["sim"]), "randomize": int(z["randomize"]) if "randomize" in z.files else 0,
            "kinematics": int(z["kinematics"]) if "kinematics" in z.files else 0, "cases": {}}
     for case in z["cases"]:
@@ -48,6 +50,21 @@ TRAJ_NAMES = ["circle5_qfalse", "circle5_qtrue", "circle5_visible", "square10_qf
               "circle5_random", "square10_random"]      # [env] randomize_attributes = true (heterogeneous humans)
 # robot kinematics: None = the fork exactly as shipped (ActionRot dynamics, theta feature zero), unicycle explicit
 TRAJ_NAMES_KIN = ["circle5_kin_none", "circle5_kin_none_qtrue", "circle5_unicycle", "square10_unicycle_qtrue"]
+
+
+# the other value networks behind the same lookahead (policy_factory: cadrl, lstm_rl; ValueNetwork2 = interaction module)
+TRAJ_NAMES_NETS = ["cadrl_circle5", "cadrl_circle5_qtrue", "cadrl_circle1", "lstm_circle5", "lstm_circle5_qtrue",
+                   "lstm2_square10"]
+
+
+@pytest.fixture(scope="session")
+def units_nets():
+    return dict(np.load(os.path.join(GOLDEN, "units_nets.npz"), allow_pickle=False))
+
+
+def net_tag(tr):
+    """key prefix of a trajectory's network inside units_nets.npz"""
+    return "cadrl" if tr["policy"] == "cadrl" else ("lstm2" if tr["interaction_module"] else "lstm")
 
 
 def weights_for(name):

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import TRAJ_NAMES, TRAJ_NAMES_KIN, load_traj, weights_for
+from conftest import TRAJ_NAMES_NETS, net_tag, TRAJ_NAMES, TRAJ_NAMES_KIN, load_traj, weights_for
 
 
 def test_action_space_matches_reference(oracle_mod, units):
@@ -120,3 +120,60 @@ def test_randomized_scenes_match_reference(oracle_mod, name):
         assert np.array_equal(prod, ref), case
         assert np.all((ref[1:, 6] >= 0.3) & (ref[1:, 6] <= 0.5)) and np.all((ref[1:, 7] >= 0.5) & (ref[1:, 7] <= 1.5))
         assert len(set(ref[1:, 6])) > 1
+
+
+def _net_cfg(o, tag):
+    return {"cadrl": o.NetCfg.cadrl(), "lstm": o.NetCfg.lstm_rl(), "lstm2": o.NetCfg.lstm_rl(True)}[tag]
+
+
+@pytest.mark.parametrize("tag", ["cadrl", "lstm", "lstm2"])
+def test_other_value_networks(oracle_mod, units_nets, tag):
+    """CADRL mlp (cadrl.py:22-30), LSTM-RL ValueNetwork1 / ValueNetwork2 (lstm_rl.py:9-66) against the reference's
+    torch modules; the seed-0 weights themselves are pinned too (state-dict order and RNG stream)."""
+    o = oracle_mod
+    ncfg = _net_cfg(o, tag)
+    w = units_nets[tag + "_weights"]
+    assert w.size == o.net_param_count(ncfg)
+    assert np.array_equal(w, o.default_net_weights(ncfg, 0))
+    for H in (1, 5):
+        x, ref = units_nets["%s_in_h%d" % (tag, H)], units_nets["%s_out_h%d" % (tag, H)]
+        got = np.array([o.net_forward(ncfg, w, xi) for xi in x])
+        assert got.shape == ref.shape
+        assert np.max(np.abs(got - ref)) <= 1e-5 * max(1.0, np.max(np.abs(ref)))
+
+
+def test_lstm_human_order_is_stable_descending(oracle_mod):
+    """lstm_rl.py:99-104: sorted(key=dist, reverse=True) keeps the env order of equidistant humans."""
+    o = oracle_mod
+    a = o.generate_scene("test", 0)
+    a[1, :2] = a[0, :2] + [3, 0]; a[2, :2] = a[0, :2] + [0, 1]; a[3, :2] = a[0, :2] + [0, -3]
+    a[4, :2] = a[0, :2] + [5, 0]; a[5, :2] = a[0, :2] + [-1, 0]
+    assert list(o.lstm_human_order(a)) == [3, 0, 2, 1, 4]
+
+
+@pytest.mark.parametrize("name", TRAJ_NAMES_NETS)
+def test_trajectories_other_networks(oracle_mod, units_nets, name):
+    """CADRL.predict (min over humans) and LstmRL.predict (humans sorted by decreasing distance unless query_env) replayed
+    step by step against the reference's own episodes: values, argmax, and the env transition under that action."""
+    o = oracle_mod
+    tr = load_traj(name)
+    tag = net_tag(tr)
+    ncfg, w = _net_cfg(o, tag), units_nets[tag + "_weights"]
+    ecfg = o.EnvCfg.default()
+    n = 0
+    for case, rec in tr["cases"].items():
+        table = rec["table"]
+        for t in range(len(rec["time"])):
+            agents = np.ascontiguousarray(rec["agents"][t])
+            gt = float(rec["time"][t])
+            hv = o.human_actions(ecfg, agents)
+            assert np.array_equal(hv, rec["human_v"][t]), (case, t)
+            best, values, reached = o.lookahead_net(ecfg, ncfg, w, agents, gt, table, tr["query_env"], hv)
+            assert not reached
+            ref_v = rec["values"][t]
+            assert np.max(np.abs(values - ref_v)) <= 1e-5 * max(1.0, np.max(np.abs(ref_v))), (case, t)
+            top2 = np.sort(ref_v)[-2:]
+            if top2[1] - top2[0] > 1e-5:
+                assert best == int(rec["best"][t]), (case, t)
+            n += 1
+    assert n >= 20
