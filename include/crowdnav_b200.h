@@ -48,6 +48,7 @@ enum { CN_NOTHING = 0, CN_DANGER = 1, CN_REACHGOAL = 2, CN_COLLISION = 3, CN_TIM
 enum { CN_CIRCLE_CROSSING = 0, CN_SQUARE_CROSSING = 1 };
 /* value-network arithmetic */
 enum { CN_PREC_F32 = 0 /* FP32 CUDA cores */, CN_PREC_F16_TC = 1 /* fp16 operands, fp32 accumulate, tcgen05 */ };
+enum { CN_NET_SARL = 0, CN_NET_CADRL = 1, CN_NET_LSTM_RL = 2 };   /* value network behind the lookahead */
 
 typedef struct cn_env cn_env;
 typedef struct cn_policy cn_policy;
@@ -97,6 +98,15 @@ typedef struct {
     int32_t precision;           /* CN_PREC_* */
     int32_t kinematics;          /* CN_KIN_*: action space of CADRL.build_action_space (cadrl.py:82-102) and the theta
                                   * feature of rotate() (cadrl.py:236-240); must equal the env's robot_kinematics */
+    /* Which value network sits behind the lookahead (policy_factory: sarl, cadrl, lstm_rl).  CN_NET_CADRL
+     * (cadrl.py:22-30,131-178): mlp3_dims = [cadrl] mlp_dims applied to every (robot, human) row, value = reward +
+     * gamma_bar * MIN over humans.  CN_NET_LSTM_RL (lstm_rl.py:9-105): humans sorted by decreasing distance (query_env =
+     * false only, see multi_human_rl.py:37-42), nn.LSTM(13 or lstm_mlp1_dims[3] -> lstm_hidden) over the rows, mlp3_dims =
+     * [lstm_rl] mlp2_dims on cat(self_state, h_n); lstm_mlp1_dims[0] > 0 selects ValueNetwork2 (with_interaction_module).
+     * Both run on the FP32 path only (CN_PREC_F32). */
+    int32_t network;             /* CN_NET_* */
+    int32_t lstm_hidden;         /* [lstm_rl] global_state_dim = 50 */
+    int32_t lstm_mlp1_dims[4];   /* [lstm_rl] mlp1_dims = 150,100,100,50; {0} = ValueNetwork1 */
 } cn_sarl_cfg;
 
 /* Episode statistics accumulated on the device by cn_env_step(update=1); the counters
@@ -199,6 +209,10 @@ int cn_policy_lookahead(cn_policy *p, cn_env *env, int query_env, double epsilon
 int cn_policy_read(cn_policy *p, cn_env *env, int32_t *best_idx, double *values, void *stream);
 /* MultiHumanRL.transform (multi_human_rl.py:90-104) for every env: E x H x 13 fp32 into a DEVICE buffer. */
 int cn_policy_transform(cn_policy *p, cn_env *env, float *out_dev, void *stream);
+/* What predict() leaves in policy.last_state in the train phase (multi_human_rl.py:60-61): transform() of the state
+ * predict() saw.  Identical to cn_policy_transform except for CN_NET_LSTM_RL, whose predict() first sorts the humans by
+ * decreasing distance to the robot (lstm_rl.py:99-104), so the rows come out in that order. */
+int cn_policy_last_state(cn_policy *p, cn_env *env, float *out_dev, void *stream);
 /* ValueNetwork.forward (sarl.py:28-65) on a DEVICE batch x: B x H x 13 fp32 -> B fp32 (FP32 path;
  * used for TD targets, explorer.py:168-174). */
 int cn_policy_forward(cn_policy *p, const float *x_dev, int32_t batch, int32_t human_num, float *out_dev,

@@ -13,6 +13,7 @@ CN_OK, CN_EINVAL, CN_ECUDA, CN_ENOMEM, CN_EUNSUPPORTED, CN_EVALUE = 0, -1, -2, -
 NOTHING, DANGER, REACHGOAL, COLLISION, TIMEOUT = 0, 1, 2, 3, 4
 CIRCLE_CROSSING, SQUARE_CROSSING = 0, 1
 PREC_F32, PREC_F16_TC = 0, 1
+NET_SARL, NET_CADRL, NET_LSTM_RL = 0, 1, 2           # value network behind the lookahead (CN_NET_*)
 KIN_HOLONOMIC, KIN_UNICYCLE, KIN_NONE = 0, 1, 2      # robot kinematics (CN_KIN_*); NONE = the fork as shipped (cadrl.py:66)
 AGENT_STRIDE = 8
 
@@ -22,7 +23,7 @@ EXPORTS = [
     "cn_env_robot_orca", "cn_env_step", "cn_env_get_views", "cn_env_read_outputs", "cn_env_read_human_actions",
     "cn_env_read_next_obs", "cn_env_read_actions", "cn_env_set_actions", "cn_env_read_stats", "cn_policy_create", "cn_policy_destroy",
     "cn_policy_param_count", "cn_policy_load_weights", "cn_policy_action_table", "cn_policy_lookahead",
-    "cn_policy_read", "cn_policy_transform", "cn_policy_forward", "cn_rollout_step", "cn_rollout_step_host", "cn_rollout_step_host_packed", "cn_rollout_step_host_packed_async", "cn_stream_sync", "cn_host_step_bytes",
+    "cn_policy_read", "cn_policy_transform", "cn_policy_last_state", "cn_policy_forward", "cn_rollout_step", "cn_rollout_step_host", "cn_rollout_step_host_packed", "cn_rollout_step_host_packed_async", "cn_stream_sync", "cn_host_step_bytes",
     "cn_launch_count", "cn_selftest_umma", "cn_selftest_umma_bmn", "cn_selftest_umma_pair", "cn_debug_tc_timing", "cn_debug_umma_bench", "cn_debug_tmem_bench",
 ]
 
@@ -49,7 +50,8 @@ class SarlCfg(C.Structure):
     _fields_ = [("input_dim", C.c_int32), ("self_state_dim", C.c_int32), ("mlp1_dims", C.c_int32 * 2),
                 ("mlp2_dims", C.c_int32 * 2), ("attn_dims", C.c_int32 * 3), ("mlp3_dims", C.c_int32 * 4),
                 ("speed_samples", C.c_int32), ("rotation_samples", C.c_int32), ("gamma", C.c_double),
-                ("v_pref", C.c_double), ("precision", C.c_int32), ("kinematics", C.c_int32)]
+                ("v_pref", C.c_double), ("precision", C.c_int32), ("kinematics", C.c_int32),
+                ("network", C.c_int32), ("lstm_hidden", C.c_int32), ("lstm_mlp1_dims", C.c_int32 * 4)]
 
 
 class Stats(C.Structure):
@@ -111,6 +113,7 @@ def load():
     L.cn_policy_lookahead.argtypes = [vp, vp, C.c_int, dbl, vp]
     L.cn_policy_read.argtypes = [vp, vp, vp, vp, vp]
     L.cn_policy_transform.argtypes = [vp, vp, vp, vp]
+    L.cn_policy_last_state.argtypes = [vp, vp, vp, vp]
     L.cn_policy_forward.argtypes = [vp, vp, i32, i32, vp, vp]
     L.cn_rollout_step.argtypes = [vp, vp, C.c_int, dbl, vp]
     L.cn_rollout_step_host.argtypes = [vp, vp, C.c_int, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp]

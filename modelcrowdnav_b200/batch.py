@@ -136,6 +136,8 @@ class BatchedSARL(object):
     def __init__(self, device=0, precision="f32", **cfg):
         self.lib = _capi.load()
         prec = {"f32": _capi.PREC_F32, "f16_tc": _capi.PREC_F16_TC}[precision]
+        if isinstance(cfg.get("network"), str):      # "sarl" | "cadrl" | "lstm_rl" (policy_factory names)
+            cfg["network"] = {"sarl": _capi.NET_SARL, "cadrl": _capi.NET_CADRL, "lstm_rl": _capi.NET_LSTM_RL}[cfg["network"]]
         self.cfg = _capi.default_sarl_cfg(precision=prec, **cfg)
         self.device = device
         self.handle = C.c_void_p()
@@ -176,16 +178,20 @@ class BatchedSARL(object):
         check(self.lib.cn_policy_read(self.handle, env.handle, _ptr(best), _ptr(vals), _stream(stream)))
         return best, vals
 
-    def transform(self, env, stream=None):
-        """MultiHumanRL.transform for every env -> torch CUDA tensor (E, H, 13) fp32."""
+    def transform(self, env, stream=None, last_state=False):
+        """MultiHumanRL.transform for every env -> torch CUDA tensor (E, H, 13) fp32.  last_state=True: what predict()
+        leaves in policy.last_state (LSTM-RL: rows in its sorted human order, lstm_rl.py:99-104)."""
         import torch
         out = torch.empty((env.E, env.H, 13), dtype=torch.float32, device="cuda:%d" % self.device)
-        check(self.lib.cn_policy_transform(self.handle, env.handle, C.c_void_p(out.data_ptr()), _stream(stream)))
+        fn = self.lib.cn_policy_last_state if last_state else self.lib.cn_policy_transform
+        check(fn(self.handle, env.handle, C.c_void_p(out.data_ptr()), _stream(stream)))
         return out
 
     def forward(self, x, stream=None):
         """ValueNetwork.forward on a CUDA tensor (B, H, 13) fp32 -> (B,) fp32 (FP32 kernel)."""
         import torch
+        if x.dim() == 2:                              # CADRL trains on single (robot, human) rows (cadrl.py:202-216)
+            x = x.unsqueeze(1)
         assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.shape[2] == 13
         x = x.contiguous()
         out = torch.empty((x.shape[0],), dtype=torch.float32, device=x.device)

@@ -52,6 +52,8 @@ def install_as_reference(provide_gym=True, literal_kinematics=False):
     _module("crowd_nav.policy")
     _module("crowd_nav.policy.policy_factory", policy_factory=policy.policy_factory)
     _module("crowd_nav.policy.sarl", SARL=policy.SARL)
+    _module("crowd_nav.policy.cadrl", CADRL=policy.CADRL, mlp=policy.mlp)
+    _module("crowd_nav.policy.lstm_rl", LstmRL=policy.LstmRL)
     _module("crowd_nav.utils")
     _module("crowd_nav.utils.explorer", Explorer=explorer.Explorer, average=explorer.average)
     _module("crowd_nav.utils.memory", ReplayMemory=explorer.ReplayMemory)

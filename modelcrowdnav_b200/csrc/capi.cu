@@ -62,6 +62,7 @@ void cn_sarl_cfg_default(cn_sarl_cfg *c)
     c->speed_samples = 5; c->rotation_samples = 16;
     c->gamma = 0.9; c->v_pref = 1.0; c->precision = CN_PREC_F32;
     c->kinematics = CN_KIN_HOLONOMIC;
+    c->network = CN_NET_SARL; c->lstm_hidden = 50;      // [lstm_rl] global_state_dim; lstm_mlp1_dims = {0}: ValueNetwork1
 }
 
 static int use_device(int device)
@@ -372,6 +373,21 @@ int64_t cn_policy_param_count(const cn_sarl_cfg *c)
     if (!c) return 0;
     int64_t n = 0;
     int in = c->input_dim;
+    if (c->network == CN_NET_CADRL) {                       // value_network.{0,2,4,6} (cadrl.py:22-26)
+        for (int i = 0; i < 4; ++i) { n += (int64_t)in * c->mlp3_dims[i] + c->mlp3_dims[i]; in = c->mlp3_dims[i]; }
+        return n;
+    }
+    if (c->network == CN_NET_LSTM_RL) {                     // [mlp1.*] mlp.* lstm.* (lstm_rl.py:9-16,37-45)
+        int lstm_in = c->input_dim;
+        if (c->lstm_mlp1_dims[0] > 0) {
+            for (int i = 0; i < 4; ++i) { n += (int64_t)in * c->lstm_mlp1_dims[i] + c->lstm_mlp1_dims[i]; in = c->lstm_mlp1_dims[i]; }
+            lstm_in = c->lstm_mlp1_dims[3];
+        }
+        in = c->self_state_dim + c->lstm_hidden;
+        for (int i = 0; i < 4; ++i) { n += (int64_t)in * c->mlp3_dims[i] + c->mlp3_dims[i]; in = c->mlp3_dims[i]; }
+        const int64_t G = 4 * (int64_t)c->lstm_hidden;
+        return n + G * lstm_in + G * c->lstm_hidden + 2 * G;
+    }
     for (int i = 0; i < 2; ++i) { n += (int64_t)in * c->mlp1_dims[i] + c->mlp1_dims[i]; in = c->mlp1_dims[i]; }
     in = c->mlp1_dims[1];
     for (int i = 0; i < 2; ++i) { n += (int64_t)in * c->mlp2_dims[i] + c->mlp2_dims[i]; in = c->mlp2_dims[i]; }
@@ -426,6 +442,18 @@ int cn_policy_create(const cn_sarl_cfg *cfg, int device, cn_policy **out)
         return CN_EUNSUPPORTED;
     }
     if (cfg->attn_dims[2] != 1 || cfg->mlp3_dims[3] != 1) { cn_set_error("attention and mlp3 must end in 1 unit"); return CN_EINVAL; }
+    if (cfg->network != CN_NET_SARL && cfg->network != CN_NET_CADRL && cfg->network != CN_NET_LSTM_RL) {
+        cn_set_error("unknown value network %d", cfg->network); return CN_EINVAL;
+    }
+    if (cfg->network != CN_NET_SARL && cfg->precision != CN_PREC_F32) {
+        cn_set_error("CADRL / LSTM-RL lookaheads run on the FP32 path only (precision = CN_PREC_F32)"); return CN_EUNSUPPORTED;
+    }
+    if (cfg->network == CN_NET_LSTM_RL) {
+        if (cfg->lstm_hidden < 1 || cfg->lstm_hidden > 64) { cn_set_error("1 <= lstm_hidden <= 64 required"); return CN_EINVAL; }
+        if (cfg->lstm_mlp1_dims[0] > 0)
+            for (int i = 0; i < 4; ++i)
+                if (cfg->lstm_mlp1_dims[i] < 1 || cfg->lstm_mlp1_dims[i] > 256) { cn_set_error("layer widths must be in [1, 256]"); return CN_EINVAL; }
+    }
     if (A < 1 || A > CN_MAX_ACTIONS) { cn_set_error("1 <= speed_samples*rotation_samples+1 <= %d required", CN_MAX_ACTIONS); return CN_EINVAL; }
     const int dims[] = {cfg->mlp1_dims[0], cfg->mlp1_dims[1], cfg->mlp2_dims[0], cfg->mlp2_dims[1], cfg->attn_dims[0],
                         cfg->attn_dims[1], cfg->mlp3_dims[0], cfg->mlp3_dims[1], cfg->mlp3_dims[2]};
@@ -442,6 +470,9 @@ int cn_policy_create(const cn_sarl_cfg *cfg, int device, cn_policy **out)
     for (int i = 0; i < 2; ++i) { d.m1[i] = cfg->mlp1_dims[i]; d.m2[i] = cfg->mlp2_dims[i]; }
     for (int i = 0; i < 3; ++i) d.at[i] = cfg->attn_dims[i];
     for (int i = 0; i < 4; ++i) d.m3[i] = cfg->mlp3_dims[i];
+    d.net = cfg->network; d.lstm_h = cfg->network == CN_NET_LSTM_RL ? cfg->lstm_hidden : 0;
+    for (int i = 0; i < 4; ++i) d.lm1[i] = cfg->network == CN_NET_LSTM_RL ? cfg->lstm_mlp1_dims[i] : 0;
+    d.lstm_in = d.lm1[0] > 0 ? d.lm1[3] : d.in;
     d.A = build_action_table(cfg, p->action_host);
     p->n_params = cn_policy_param_count(cfg);
 
@@ -453,6 +484,10 @@ int cn_policy_create(const cn_sarl_cfg *cfg, int device, cn_policy **out)
         add(d.m1[1], d.m2[0]); add(d.m2[0], d.m2[1]);
         add(2 * d.m1[1], d.at[0]); add(d.at[0], d.at[1]); add(d.at[1], d.at[2]);
         add(d.m2[1] + d.self_dim, d.m3[0]); add(d.m3[0], d.m3[1]); add(d.m3[1], d.m3[2]); add(d.m3[2], d.m3[3]);
+        // CADRL / LSTM-RL layouts are subsets of this plus the LSTM block and ValueNetwork2's mlp1
+        add(d.in, d.m3[0]); add(d.self_dim + d.lstm_h, d.m3[0]);
+        add(d.lstm_in, 4 * d.lstm_h); add(d.lstm_h, 4 * d.lstm_h);
+        if (d.lm1[0] > 0) { add(d.in, d.lm1[0]); add(d.lm1[0], d.lm1[1]); add(d.lm1[1], d.lm1[2]); add(d.lm1[2], d.lm1[3]); }
     }
     cudaError_t e1 = cudaMalloc((void **)&p->action_dev, sizeof(double) * 2 * d.A);
     cudaError_t e2 = cudaMalloc((void **)&p->w_raw, sizeof(float) * p->n_params);
@@ -494,6 +529,43 @@ int cn_policy_load_weights(cn_policy *p, const float *flat, int64_t n, void *str
     // host-side transpose to [in][pad4(out)] + bias, one contiguous block
     std::vector<float> t;
     struct Spec { int in, out; LinearDev *dst; };
+    if (d.net != CN_NET_SARL) {
+        // CADRL: value_network.{0,2,4,6}.  LSTM-RL: [mlp1.{0,2,4,6}] mlp.{0,2,4,6} lstm.weight_ih_l0 [4h][in], weight_hh_l0
+        // [4h][h], bias_ih_l0, bias_hh_l0 (state-dict order of cadrl.py:22-26 / lstm_rl.py:9-16,37-45)
+        std::vector<Spec> sp;
+        if (d.net == CN_NET_CADRL) {
+            int in = d.in;
+            for (int i = 0; i < 4; ++i) { sp.push_back({in, d.m3[i], &p->w.m3[i]}); in = d.m3[i]; }
+        } else {
+            int in = d.in;
+            if (d.lm1[0] > 0) for (int i = 0; i < 4; ++i) { sp.push_back({in, d.lm1[i], &p->w.lm1[i]}); in = d.lm1[i]; }
+            in = d.self_dim + d.lstm_h;
+            for (int i = 0; i < 4; ++i) { sp.push_back({in, d.m3[i], &p->w.m3[i]}); in = d.m3[i]; }
+        }
+        const float *src = flat;
+        auto put = [&](int in, int out, const float *w, const float *b, LinearDev *dst) {
+            const int ld = pad4i(out);
+            const size_t off = t.size();
+            t.resize(off + (size_t)in * ld + ld, 0.0f);
+            for (int o = 0; o < out; ++o)
+                for (int k = 0; k < in; ++k) t[off + (size_t)k * ld + o] = w[(size_t)o * in + k];
+            for (int o = 0; o < out; ++o) t[off + (size_t)in * ld + o] = b[o];
+            dst->wt = p->w_t + off; dst->b = p->w_t + off + (size_t)in * ld;
+            dst->in = in; dst->out = out; dst->ld = ld;
+        };
+        for (auto &x : sp) { put(x.in, x.out, src, src + (size_t)x.in * x.out, x.dst); src += (size_t)x.in * x.out + x.out; }
+        if (d.net == CN_NET_LSTM_RL) {
+            const int G = 4 * d.lstm_h;
+            const float *w_ih = src, *w_hh = w_ih + (size_t)G * d.lstm_in, *b_ih = w_hh + (size_t)G * d.lstm_h, *b_hh = b_ih + G;
+            put(d.lstm_in, G, w_ih, b_ih, &p->w.lih);
+            put(d.lstm_h, G, w_hh, b_hh, &p->w.lhh);
+        }
+        CN_CUDA_CHECK(cudaMemcpyAsync(p->w_t, t.data(), sizeof(float) * t.size(), cudaMemcpyHostToDevice, s));
+        CN_CUDA_CHECK(cudaMemcpyAsync(p->w_raw, flat, sizeof(float) * n, cudaMemcpyHostToDevice, s));
+        CN_CUDA_CHECK(cudaStreamSynchronize(s));
+        p->weights_loaded = 1;
+        return CN_OK;
+    }
     Spec specs[11] = {
         {d.in, d.m1[0], &p->w.m1[0]}, {d.m1[0], d.m1[1], &p->w.m1[1]},
         {d.m1[1], d.m2[0], &p->w.m2[0]}, {d.m2[0], d.m2[1], &p->w.m2[1]},
@@ -582,7 +654,14 @@ int cn_policy_transform(cn_policy *p, cn_env *env, float *out_dev, void *stream)
 {
     if (!p || !env || !out_dev) { cn_set_error("null argument"); return CN_EINVAL; }
     CN_CUDA_CHECK(cudaSetDevice(p->device));
-    return cn_transform_f32(p, env, out_dev, (cudaStream_t)stream);
+    return cn_transform_f32(p, env, out_dev, 0, (cudaStream_t)stream);
+}
+
+int cn_policy_last_state(cn_policy *p, cn_env *env, float *out_dev, void *stream)
+{
+    if (!p || !env || !out_dev) { cn_set_error("null argument"); return CN_EINVAL; }
+    CN_CUDA_CHECK(cudaSetDevice(p->device));
+    return cn_transform_f32(p, env, out_dev, p->cfg.network == CN_NET_LSTM_RL ? 1 : 0, (cudaStream_t)stream);
 }
 
 int cn_policy_forward(cn_policy *p, const float *x_dev, int32_t batch, int32_t human_num, float *out_dev, void *stream)

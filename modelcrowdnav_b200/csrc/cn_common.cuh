@@ -78,6 +78,10 @@ struct SarlDims {
     int in, self_dim;
     int m1[2], m2[2], at[3], m3[4];
     int A;  // actions
+    int net;        // CN_NET_*: SARL, CADRL (m3 = its mlp on every row), LSTM-RL (m3 = the mlp on cat(self, h_n))
+    int lstm_h;     // LSTM hidden size
+    int lm1[4];     // LSTM-RL ValueNetwork2's mlp1 widths, lm1[0] = 0 -> ValueNetwork1
+    int lstm_in;    // LSTM input width (13 or lm1[3])
 };
 
 // fp32 weights on the device, transposed to [in][out_padded] (out padded to a multiple of 4)
@@ -89,6 +93,7 @@ struct LinearDev {
 
 struct SarlWeightsDev {
     LinearDev m1[2], m2[2], at[3], m3[4];
+    LinearDev lm1[4], lih, lhh;      // LSTM-RL: mlp1 (ValueNetwork2), weight_ih / bias_ih, weight_hh / bias_hh as [in][4h]
 };
 
 struct cn_policy {
@@ -208,7 +213,7 @@ int cn_launch_io(cn_env *env, double *blk, int unpack, cudaStream_t s);   // pac
 int cn_launch_stats_reduce(cn_env *env, cn_stats *out_dev_as_host, int reset, cudaStream_t s);
 
 int cn_lookahead_f32(cn_policy *p, cn_env *env, int query_env, double epsilon, cudaStream_t s);
-int cn_transform_f32(cn_policy *p, cn_env *env, float *out_dev, cudaStream_t s);
+int cn_transform_f32(cn_policy *p, cn_env *env, float *out_dev, int sort_humans, cudaStream_t s);
 int cn_forward_f32(cn_policy *p, const float *x_dev, int batch, int H, float *out_dev, cudaStream_t s);
 
 int cn_tc_init(cn_policy *p);

@@ -30,7 +30,7 @@ __host__ __device__ inline int pad4(int x) { return (x + 3) & ~3; }
 struct F32Plan {
     int H, A, CA;             // humans, actions, actions per chunk
     int wX, wT0, wM1, wF, wJ; // padded smem row widths (floats)
-    int oX, oT0, oM1, oF, oG, oJ, oS, oW, oV, oEnv, total_floats;  // smem offsets (floats)
+    int oX, oT0, oM1, oF, oG, oJ, oS, oW, oV, oEnv, oOrd, total_floats;  // smem offsets (floats)
 };
 
 // out[r][n] = act( (accum ? out[r][n] : 0) + sum_k in[r / in_div][k] * Wt[k_off + k][n] (+ b[n]) )
@@ -166,6 +166,98 @@ __device__ void sarl_forward_smem(const SarlWeightsDev &W, const SarlDims &d, co
     __syncthreads();
 }
 
+// CADRL (cadrl.py:22-30,160-166): value_network = mlp(13 -> m3) on every (robot, human) row; V[g] = min over the humans.
+__device__ void cadrl_forward_smem(const SarlWeightsDev &W, const SarlDims &d, const F32Plan &pl, float *sm, int ng)
+{
+    const int H = pl.H, rows = ng * H;
+    float *X = sm + pl.oX, *T0 = sm + pl.oT0, *M1 = sm + pl.oM1, *S = sm + pl.oS, *Vv = sm + pl.oV;
+    layer(W.m3[0], 0, d.in, X, pl.wX, 1, T0, pl.wT0, rows, false, true, true);
+    __syncthreads();
+    layer(W.m3[1], 0, d.m3[0], T0, pl.wT0, 1, M1, pl.wM1, rows, false, true, true);
+    __syncthreads();
+    layer(W.m3[2], 0, d.m3[1], M1, pl.wM1, 1, T0, pl.wT0, rows, false, true, true);
+    __syncthreads();
+    head(W.m3[3], T0, pl.wT0, S, rows);
+    __syncthreads();
+    for (int g = threadIdx.x; g < ng; g += blockDim.x) {
+        float m = S[g * H];
+        for (int h = 1; h < H; ++h) m = fminf(m, S[g * H + h]);
+        Vv[g] = m;
+    }
+    __syncthreads();
+}
+
+// LSTM-RL (lstm_rl.py:9-66): nn.LSTM over the H rows of a group (gate order i, f, g, o; h0 = c0 = 0), fed by the rows
+// themselves (ValueNetwork1) or by mlp1(rows) (ValueNetwork2), then mlp(cat(self_state, h_n)).  Rows are already in
+// network order (the lookahead sorts the humans, lstm_rl.py:99-104).
+__device__ void lstm_forward_smem(const SarlWeightsDev &W, const SarlDims &d, const F32Plan &pl, float *sm, int ng)
+{
+    const int H = pl.H, rows = ng * H, Hh = d.lstm_h;
+    float *X = sm + pl.oX, *T0 = sm + pl.oT0, *M1 = sm + pl.oM1, *Cc = sm + pl.oF, *Hs = sm + pl.oG;
+    float *J = sm + pl.oJ, *Vv = sm + pl.oV;
+    const float *in = X;
+    int ldin = pl.wX;
+    if (d.lm1[0] > 0) {                                                              // lstm_rl.py:56-58, no last ReLU
+        layer(W.lm1[0], 0, d.in, X, pl.wX, 1, T0, pl.wT0, rows, false, true, true);
+        __syncthreads();
+        layer(W.lm1[1], 0, d.lm1[0], T0, pl.wT0, 1, M1, pl.wM1, rows, false, true, true);
+        __syncthreads();
+        layer(W.lm1[2], 0, d.lm1[1], M1, pl.wM1, 1, T0, pl.wT0, rows, false, true, true);
+        __syncthreads();
+        layer(W.lm1[3], 0, d.lm1[2], T0, pl.wT0, 1, M1, pl.wM1, rows, false, true, false);
+        __syncthreads();
+        in = M1; ldin = pl.wM1;
+    }
+    for (int i = threadIdx.x; i < ng * Hh; i += blockDim.x) {
+        const int g = i / Hh, k = i - g * Hh;
+        Hs[(size_t)g * pl.wM1 + k] = 0.0f;
+        Cc[(size_t)g * pl.wF + k] = 0.0f;
+    }
+    for (int i = threadIdx.x; i < ng * d.self_dim; i += blockDim.x) {               // self_state = state[:, 0, :6]
+        const int g = i / d.self_dim, k = i - g * d.self_dim;
+        J[(size_t)g * pl.wJ + k] = X[(size_t)(g * H) * pl.wX + k];
+    }
+    __syncthreads();
+    for (int t = 0; t < H; ++t) {
+        // gates = W_ih x_t + b_ih + W_hh h + b_hh, one row per group (row stride H * ldin picks step t of every group)
+        layer(W.lih, 0, d.lstm_in, in + (size_t)t * ldin, H * ldin, 1, T0, pl.wT0, ng, false, true, false);
+        __syncthreads();
+        layer(W.lhh, 0, Hh, Hs, pl.wM1, 1, T0, pl.wT0, ng, true, true, false);
+        __syncthreads();
+        for (int i = threadIdx.x; i < ng * Hh; i += blockDim.x) {
+            const int g = i / Hh, k = i - g * Hh;
+            const float *gt = T0 + (size_t)g * pl.wT0;
+            const float ig = 1.0f / (1.0f + expf(-gt[k])), fg = 1.0f / (1.0f + expf(-gt[Hh + k]));
+            const float gg = tanhf(gt[2 * Hh + k]), og = 1.0f / (1.0f + expf(-gt[3 * Hh + k]));
+            const float c = fg * Cc[(size_t)g * pl.wF + k] + ig * gg;
+            Cc[(size_t)g * pl.wF + k] = c;
+            Hs[(size_t)g * pl.wM1 + k] = og * tanhf(c);
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < ng * Hh; i += blockDim.x) {
+        const int g = i / Hh, k = i - g * Hh;
+        J[(size_t)g * pl.wJ + d.self_dim + k] = Hs[(size_t)g * pl.wM1 + k];
+    }
+    __syncthreads();
+    float *U0 = T0, *U1 = M1;
+    layer(W.m3[0], 0, d.self_dim + Hh, J, pl.wJ, 1, U0, pl.wT0, ng, false, true, true);
+    __syncthreads();
+    layer(W.m3[1], 0, d.m3[0], U0, pl.wT0, 1, U1, pl.wM1, ng, false, true, true);
+    __syncthreads();
+    layer(W.m3[2], 0, d.m3[1], U1, pl.wM1, 1, U0, pl.wT0, ng, false, true, true);
+    __syncthreads();
+    head(W.m3[3], U0, pl.wT0, Vv, ng);
+    __syncthreads();
+}
+
+__device__ __forceinline__ void net_forward_smem(const SarlWeightsDev &W, const SarlDims &d, const F32Plan &pl, float *sm, int ng)
+{
+    if (d.net == CN_NET_CADRL) cadrl_forward_smem(W, d, pl, sm, ng);
+    else if (d.net == CN_NET_LSTM_RL) lstm_forward_smem(W, d, pl, sm, ng);
+    else sarl_forward_smem(W, d, pl, sm, ng);
+}
+
 // grid = (E, chunks)
 __global__ void __launch_bounds__(kThreads, 2)
 lookahead_values_kernel(EnvParams p, SarlWeightsDev W, SarlDims d, F32Plan pl, const double *__restrict__ st,
@@ -193,6 +285,24 @@ lookahead_values_kernel(EnvParams p, SarlWeightsDev W, SarlDims d, F32Plan pl, c
     }
     __syncthreads();
     auto ag = [&](int f, int a) { return env[a * F_COUNT + f]; };
+    // network order of the humans: LstmRL.predict sorts them by DECREASING distance to the robot (stable, lstm_rl.py:99-104);
+    // with query_env the next human states come back from the env in env order (multi_human_rl.py:37-38)
+    int *ord = reinterpret_cast<int *>(sm + pl.oOrd);
+    if (threadIdx.x == 0) {
+        for (int h = 0; h < H; ++h) ord[h] = h;
+        if (d.net == CN_NET_LSTM_RL && !query_env) {
+            for (int i = 1; i < H; ++i) {
+                const int oi = ord[i];
+                const double di = norm2d(ag(F_PX, oi + 1) - ag(F_PX, 0), ag(F_PY, oi + 1) - ag(F_PY, 0));
+                int j = i - 1;
+                while (j >= 0 && norm2d(ag(F_PX, ord[j] + 1) - ag(F_PX, 0), ag(F_PY, ord[j] + 1) - ag(F_PY, 0)) < di) {
+                    ord[j + 1] = ord[j];
+                    --j;
+                }
+                ord[j + 1] = oi;
+            }
+        }
+    }
     const double dt = p.time_step;
     const int kin = p.kinematics;
     const double th = kin != CN_KIN_HOLONOMIC ? theta[e] : 0.0;      // robot heading (cadrl.py:119: next_theta = theta + r)
@@ -234,7 +344,7 @@ lookahead_values_kernel(EnvParams p, SarlWeightsDev W, SarlDims d, F32Plan pl, c
     }
     // rotated joint-state rows (multi_human_rl.py:43-45): torch.Tensor([...]) rounds the doubles to fp32
     for (int r = threadIdx.x; r < rows; r += blockDim.x) {
-        const int i = r / H, h = r - i * H;
+        const int i = r / H, h = ord[r - i * H];
         double ax, ay;
         cn_effective_velocity(kin, th, actions[2 * (a0 + i)], actions[2 * (a0 + i) + 1], ax, ay);
         float s[14], o[13];
@@ -249,7 +359,7 @@ lookahead_values_kernel(EnvParams p, SarlWeightsDev W, SarlDims d, F32Plan pl, c
         for (int k = 0; k < 13; ++k) X[(size_t)r * pl.wX + k] = o[k];
     }
     __syncthreads();
-    sarl_forward_smem(W, d, pl, sm, na);
+    net_forward_smem(W, d, pl, sm, na);
     const float *Vv = sm + pl.oV;
     const double vp = ag(F_VPREF, 0);
     const double gamma_bar = (vp == v_pref_host) ? gamma_bar_host : pow(gamma, dt * vp);
@@ -304,8 +414,10 @@ argmax_kernel(EnvParams p, int A, const double *__restrict__ st, const uint8_t *
 }
 
 // MultiHumanRL.transform (multi_human_rl.py:90-104): current joint state -> E x H x 13 fp32
+// sort_humans: rows in LstmRL.predict's order (decreasing distance to the robot, stable: lstm_rl.py:99-104) -- what
+// predict() leaves in last_state for LSTM-RL; 0 = env order (MultiHumanRL.transform itself never sorts).
 __global__ void transform_kernel(EnvParams p, const double *__restrict__ st, const double *__restrict__ theta,
-                                 float *__restrict__ out)
+                                 float *__restrict__ out, int sort_humans)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const EnvDims d = p.d;
@@ -319,7 +431,18 @@ __global__ void transform_kernel(EnvParams p, const double *__restrict__ st, con
     s[9] = ag(F_PX, h + 1); s[10] = ag(F_PY, h + 1); s[11] = ag(F_VX, h + 1); s[12] = ag(F_VY, h + 1);
     s[13] = ag(F_R, h + 1);
     cn_rotate(s, o, p.kinematics);
-    for (int k = 0; k < 13; ++k) out[((size_t)e * d.H + h) * 13 + k] = o[k];
+    int pos = h;
+    if (sort_humans) {
+        const double rx = st[st_idx(d, F_PX, 0, e)], ry = st[st_idx(d, F_PY, 0, e)];
+        const double dh = norm2d(st[st_idx(d, F_PX, h + 1, e)] - rx, st[st_idx(d, F_PY, h + 1, e)] - ry);
+        pos = 0;
+        for (int k = 0; k < d.H; ++k) {
+            if (k == h) continue;
+            const double dk = norm2d(st[st_idx(d, F_PX, k + 1, e)] - rx, st[st_idx(d, F_PY, k + 1, e)] - ry);
+            pos += (dk > dh || (dk == dh && k < h)) ? 1 : 0;
+        }
+    }
+    for (int k = 0; k < 13; ++k) out[((size_t)e * d.H + pos) * 13 + k] = o[k];
 }
 
 // ValueNetwork.forward on a device batch (B x H x 13 -> B); grid = chunks of CA items
@@ -336,7 +459,7 @@ forward_kernel(SarlWeightsDev W, SarlDims d, F32Plan pl, const float *__restrict
         X[(size_t)r * pl.wX + k] = x[(size_t)b0 * H * 13 + i];
     }
     __syncthreads();
-    sarl_forward_smem(W, d, pl, sm, nb);
+    net_forward_smem(W, d, pl, sm, nb);
     const float *Vv = sm + pl.oV;
     for (int i = threadIdx.x; i < nb; i += blockDim.x) out[b0 + i] = Vv[i];
 }
@@ -355,6 +478,12 @@ F32Plan make_plan(const SarlDims &d, int H, int A, int A1)
     pl.wM1 = pad4(mx(mx(d.m1[1], d.at[1]), d.m3[1]));
     pl.wF = pad4(d.m2[1]);
     pl.wJ = pad4(d.self_dim + d.m2[1]);
+    if (d.net == CN_NET_LSTM_RL) {          // gates (4h) in T0, h in G (ld wM1), c in F, joint = [self | h_n] in J
+        pl.wT0 = pad4(mx(pl.wT0, mx(4 * d.lstm_h, mx(d.lm1[0], d.lm1[2]))));
+        pl.wM1 = pad4(mx(pl.wM1, mx(d.lstm_h, mx(d.lm1[1], d.lm1[3]))));
+        pl.wF = pad4(mx(pl.wF, d.lstm_h));
+        pl.wJ = pad4(d.self_dim + mx(d.m2[1], d.lstm_h));
+    }
     int o = 0;
     pl.oX = o; o += rows * pl.wX;
     pl.oT0 = o; o += rows * pl.wT0;
@@ -367,6 +496,7 @@ F32Plan make_plan(const SarlDims &d, int H, int A, int A1)
     pl.oV = o; o += pad4(pl.CA);
     o = (o + 3) & ~3;
     pl.oEnv = o; o += 2 * (A1 * F_COUNT + H * 4 + pl.CA);
+    pl.oOrd = o; o += pad4(H);                      // LSTM-RL: humans in network order
     pl.total_floats = o;
     return pl;
 }
@@ -423,11 +553,11 @@ int cn_lookahead_f32(cn_policy *p, cn_env *env, int query_env, double epsilon, c
     return cn_lookahead_argmax(p, env, epsilon, s);
 }
 
-int cn_transform_f32(cn_policy *p, cn_env *env, float *out_dev, cudaStream_t s)
+int cn_transform_f32(cn_policy *p, cn_env *env, float *out_dev, int sort_humans, cudaStream_t s)
 {
     (void)p;
     const int n = env->p.d.E * env->p.d.H;
-    transform_kernel<<<(n + 127) / 128, 128, 0, s>>>(env->p, env->state, env->theta, out_dev);
+    transform_kernel<<<(n + 127) / 128, 128, 0, s>>>(env->p, env->state, env->theta, out_dev, sort_humans);
     CN_LAUNCH_CHECK();
     return CN_OK;
 }

@@ -17,7 +17,7 @@ import numpy as np
 from . import _capi, scenes
 from .batch import BatchedCrowdSim
 from .envs import batch_env_kwargs
-from .policy import ORCA, SARL
+from .policy import CADRL, ORCA, SARL
 
 
 class ReplayMemory(object):
@@ -113,11 +113,8 @@ class Explorer(object):
             h = policy.handle(self.robot.v_pref, precision="f32")
             # a separate handle so that the behaviour policy's weights are untouched
             from .batch import BatchedSARL
-            d = policy._dims
-            self._target_handle = BatchedSARL(device=h.device, precision="f32", mlp1_dims=d["mlp1_dims"],
-                                              mlp2_dims=d["mlp2_dims"], attn_dims=d["attn_dims"],
-                                              mlp3_dims=d["mlp3_dims"], gamma=policy.gamma, v_pref=self.robot.v_pref,
-                                              kinematics=h.cfg.kinematics)
+            self._target_handle = BatchedSARL(device=h.device, precision="f32", gamma=policy.gamma,
+                                              v_pref=self.robot.v_pref, kinematics=h.cfg.kinematics, **policy._net_kwargs)
             self._target_handle.load_weights(self.target_model.state_dict())
         return self._target_handle.forward(states.contiguous())
 
@@ -166,7 +163,12 @@ class Explorer(object):
                 # policy.last_state = transform(state) (multi_human_rl.py:60-61) / target_policy.transform (explorer.py:163)
                 if not isinstance(tr_policy, SARL):
                     raise ValueError("update_memory needs a SARL policy (or target_policy) to transform states")
-                states_t.append(tr_policy.handle(v_pref).transform(b))
+                # RL: predict()'s last_state (LSTM-RL rows in its sorted human order); IL: plain transform()
+                st = tr_policy.handle(v_pref).transform(b, last_state=not imitation_learning)
+                if isinstance(tr_policy, CADRL):
+                    assert st.shape[1] == 1                        # cadrl.py:209: CADRL trains on single-human states
+                    st = st[:, 0]
+                states_t.append(st)
             b.orca()
             if stay:
                 b.set_actions(np.zeros((k, 2)))

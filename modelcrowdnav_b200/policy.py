@@ -223,6 +223,7 @@ class SARL(Policy):
         if not with_global_state:
             raise NotImplementedError("with_global_state = false is not supported by the CUDA lookahead")
         self._dims = dict(mlp1_dims=mlp1_dims, mlp2_dims=mlp2_dims, attn_dims=attention_dims, mlp3_dims=mlp3_dims)
+        self._net_kwargs = dict(self._dims)
         self.model = make_value_network(self.joint_state_dim, self.self_state_dim, mlp1_dims, mlp2_dims, mlp3_dims,
                                         attention_dims, with_global_state)
         self.multiagent_training = config.getboolean("sarl", "multiagent_training")
@@ -259,13 +260,10 @@ class SARL(Policy):
         precision = precision or self.precision
         key = (precision, float(v_pref), self.kinematics)
         if key not in self._handles:
-            d = self._dims
             self._handles[key] = [BatchedSARL(device=_cuda_index(self.device), precision=precision,
                                               kinematics=KIN_CODE[self.kinematics],
-                                              mlp1_dims=d["mlp1_dims"], mlp2_dims=d["mlp2_dims"],
-                                              attn_dims=d["attn_dims"], mlp3_dims=d["mlp3_dims"],
                                               speed_samples=self.speed_samples, rotation_samples=self.rotation_samples,
-                                              gamma=self.gamma, v_pref=float(v_pref)), None]
+                                              gamma=self.gamma, v_pref=float(v_pref), **self._net_kwargs), None]
         entry = self._handles[key]
         version = self._model_version()
         if entry[1] != version:
@@ -329,7 +327,7 @@ class SARL(Policy):
             raise
         self.action_values = list(values[0])
         if self.phase == "train":
-            self.last_state = self.transform(state)
+            self.last_state = self._last_state(state)
         return self.action_space[int(best[0])]
 
     def transform(self, state):
@@ -337,8 +335,136 @@ class SARL(Policy):
         t = self.handle(state.self_state.v_pref).transform(self._single_env(state))[0]
         return t.to(self.device) if self.device is not None else t
 
+    def _last_state(self, state):
+        """What predict() stores in last_state (multi_human_rl.py:60-61)."""
+        return self.transform(state)
+
     def input_dim(self):
         return self.joint_state_dim
+
+
+def make_cadrl_network(input_dim, mlp_dims):
+    """torch ValueNetwork of CADRL with the reference's parameter names (cadrl.py:22-30)."""
+    import torch.nn as nn
+
+    class ValueNetwork(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.value_network = mlp(input_dim, mlp_dims)
+
+        def forward(self, state):
+            return self.value_network(state)
+
+    return ValueNetwork()
+
+
+def make_lstm_network(input_dim, self_state_dim, mlp1_dims, mlp_dims, lstm_hidden_dim):
+    """torch ValueNetwork1 (mlp1_dims None) / ValueNetwork2 of LSTM-RL with the reference's parameter names and
+    registration order (lstm_rl.py:9-66); the initial LSTM state follows the input's device."""
+    import torch
+    import torch.nn as nn
+
+    class ValueNetwork(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.self_state_dim = self_state_dim
+            self.lstm_hidden_dim = lstm_hidden_dim
+            if mlp1_dims:
+                self.mlp1 = mlp(input_dim, mlp1_dims)
+            self.mlp = mlp(self_state_dim + lstm_hidden_dim, mlp_dims)
+            self.lstm = nn.LSTM(mlp1_dims[-1] if mlp1_dims else input_dim, lstm_hidden_dim, batch_first=True)
+
+        def forward(self, state):
+            size = state.shape
+            self_state = state[:, 0, :self.self_state_dim]
+            seq = state
+            if mlp1_dims:
+                seq = self.mlp1(state.reshape((-1, size[2]))).reshape((size[0], size[1], -1))
+            h0 = torch.zeros(1, size[0], self.lstm_hidden_dim, device=state.device)
+            c0 = torch.zeros(1, size[0], self.lstm_hidden_dim, device=state.device)
+            _, (hn, _) = self.lstm(seq, (h0, c0))
+            return self.mlp(torch.cat([self_state, hn.squeeze(0)], dim=1))
+
+    return ValueNetwork()
+
+
+def _no_attention_weights(self):
+    raise AttributeError("this policy has no attention weights")
+
+
+class CADRL(SARL):
+    """CADRL behind the same GPU lookahead (cadrl.py:32-216): the value network scores every (robot, human) pair and an
+    action is worth reward + gamma_bar * MIN over the humans.  FP32 CUDA-core path (CN_NET_CADRL)."""
+
+    def __init__(self):
+        super().__init__()
+        self.name = "CADRL"
+        self.precision = "f32"
+
+    def configure(self, config):
+        self.set_common_parameters(config)
+        if self.kinematics not in KIN_CODE:
+            raise NotImplementedError("kinematics must be holonomic, unicycle or None (the fork's literal behaviour)")
+        mlp_dims = [int(x) for x in config.get("cadrl", "mlp_dims").split(", ")]
+        if len(mlp_dims) != 4 or mlp_dims[-1] != 1:
+            raise NotImplementedError("the CUDA CADRL network is mlp(13 -> a, b, c, 1)")
+        self.model = make_cadrl_network(self.joint_state_dim, mlp_dims)
+        self.multiagent_training = config.getboolean("cadrl", "multiagent_training")
+        self.with_om = False
+        self._dims = dict(mlp3_dims=mlp_dims)
+        self._net_kwargs = dict(network="cadrl", mlp3_dims=mlp_dims)
+        logging.info("Policy: CADRL without occupancy map")
+
+    # the reference's CADRL has no get_attention_weights; CrowdSim.step probes it with hasattr (crowd_sim.py:408-411)
+    get_attention_weights = property(_no_attention_weights)
+
+    def transform(self, state):
+        """cadrl.py:202-216: single-human joint state -> tensor (13,)."""
+        assert len(state.human_states) == 1
+        return super().transform(state)[0]
+
+
+class LstmRL(SARL):
+    """LSTM-RL behind the same GPU lookahead (lstm_rl.py:69-105): predict() sorts the humans by decreasing distance to the
+    robot, the value network runs an LSTM over them.  FP32 CUDA-core path (CN_NET_LSTM_RL)."""
+
+    def __init__(self):
+        super().__init__()
+        self.name = "LSTM-RL"
+        self.precision = "f32"
+        self.with_interaction_module = None
+        self.interaction_module_dims = None
+
+    def configure(self, config):
+        self.set_common_parameters(config)
+        if self.kinematics not in KIN_CODE:
+            raise NotImplementedError("kinematics must be holonomic, unicycle or None (the fork's literal behaviour)")
+        mlp_dims = [int(x) for x in config.get("lstm_rl", "mlp2_dims").split(", ")]
+        global_state_dim = config.getint("lstm_rl", "global_state_dim")
+        self.with_om = config.getboolean("lstm_rl", "with_om")
+        if self.with_om:
+            raise NotImplementedError("occupancy maps are outside the B200 hot path (SURVEY §8(f) rank 3)")
+        with_interaction_module = config.getboolean("lstm_rl", "with_interaction_module")
+        mlp1_dims = [int(x) for x in config.get("lstm_rl", "mlp1_dims").split(", ")] if with_interaction_module else None
+        if len(mlp_dims) != 4 or mlp_dims[-1] != 1 or (mlp1_dims and len(mlp1_dims) != 4):
+            raise NotImplementedError("the CUDA LSTM-RL network uses 4-layer mlps ending in 1 unit")
+        self.with_interaction_module = with_interaction_module
+        self.model = make_lstm_network(self.input_dim(), self.self_state_dim, mlp1_dims, mlp_dims, global_state_dim)
+        self.multiagent_training = config.getboolean("lstm_rl", "multiagent_training")
+        self._dims = dict(mlp3_dims=mlp_dims)
+        self._net_kwargs = dict(network="lstm_rl", mlp3_dims=mlp_dims, lstm_hidden=global_state_dim,
+                                lstm_mlp1_dims=mlp1_dims or [0, 0, 0, 0])
+        logging.info("Policy: {}LSTM-RL {} pairwise interaction module".format(
+            "OM-" if self.with_om else "", "w/" if with_interaction_module else "w/o"))
+
+    get_attention_weights = property(_no_attention_weights)      # as for CADRL
+
+    def _last_state(self, state):
+        # predict() re-orders state.human_states in place before calling MultiHumanRL.predict (lstm_rl.py:99-105)
+        def dist(human):
+            return np.linalg.norm(np.array(human.position) - np.array(state.self_state.position))
+        state.human_states = sorted(state.human_states, key=dist, reverse=True)
+        return self.transform(state)
 
 
 def _none():
@@ -346,4 +472,4 @@ def _none():
 
 
 # crowd_nav/policy/policy_factory.py + crowd_sim/envs/policy/policy_factory.py (hot-path policies only)
-policy_factory = {"orca": ORCA, "none": _none, "sarl": SARL}
+policy_factory = {"orca": ORCA, "none": _none, "sarl": SARL, "cadrl": CADRL, "lstm_rl": LstmRL}

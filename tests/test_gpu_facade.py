@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, load_traj, weights_for
+from conftest import GOLDEN, load_traj, net_tag, weights_for
 
 pytestmark = pytest.mark.gpu
 
@@ -62,6 +62,16 @@ mlp3_dims = 150, 100, 100, 1
 multiagent_training = true
 with_om = false
 with_global_state = true
+[cadrl]
+mlp_dims = 150, 100, 100, 1
+multiagent_training = false
+[lstm_rl]
+global_state_dim = 50
+mlp1_dims = 150, 100, 100, 50
+mlp2_dims = 150, 100, 100, 1
+multiagent_training = true
+with_om = false
+with_interaction_module = false
 """
 
 
@@ -78,15 +88,16 @@ KIN_NAME = {0: "holonomic", 1: "unicycle", 2: None}
 
 
 def _setup(weights0, precision="f32", query_env=False, human_num=5, sim="circle_crossing", randomize=False,
-           kinematics="holonomic"):
+           kinematics="holonomic", policy_name="sarl", interaction_module=False):
     """Wire env, robot, policy, explorer exactly as crowd_nav/test.py:52-87 does."""
     import torch
     import modelcrowdnav_b200 as mcn
     ecfg = _cfg(ENV_INI, sim__human_num=human_num, sim__train_val_sim=sim, sim__test_sim=sim,
                 env__randomize_attributes="true" if randomize else "false")
     pcfg = _cfg(POLICY_INI, action_space__query_env="true" if query_env else "false",
-                action_space__kinematics=kinematics or "holonomic")
-    policy = mcn.policy_factory["sarl"]()
+                action_space__kinematics=kinematics or "holonomic",
+                lstm_rl__with_interaction_module="true" if interaction_module else "false")
+    policy = mcn.policy_factory[policy_name]()
     import modelcrowdnav_b200.policy as policy_mod
     policy_mod.LITERAL_FORK_KINEMATICS = kinematics is None      # None: the fork never reads the key (cadrl.py:66)
     try:
@@ -94,7 +105,8 @@ def _setup(weights0, precision="f32", query_env=False, human_num=5, sim="circle_
     finally:
         policy_mod.LITERAL_FORK_KINEMATICS = False
     assert policy.kinematics == kinematics
-    policy.precision = precision
+    if policy_name == "sarl":
+        policy.precision = precision
     sd = policy.get_model().state_dict()
     off = 0
     new = {}
@@ -124,15 +136,20 @@ def test_state_dict_keys_match_reference(weights0, units):
 
 @pytest.mark.parametrize("name", ["circle5_qfalse", "circle5_qtrue", "circle5_qfalse_trained", "circle5_qtrue_trained",
                                   "circle5_random", "square10_random",
-                                  "circle5_kin_none", "circle5_kin_none_qtrue", "circle5_unicycle", "square10_unicycle_qtrue"])
+                                  "circle5_kin_none", "circle5_kin_none_qtrue", "circle5_unicycle", "square10_unicycle_qtrue",
+                                  "cadrl_circle5", "cadrl_circle5_qtrue", "cadrl_circle1", "lstm_circle5",
+                                  "lstm_circle5_qtrue", "lstm2_square10"])
 def test_facade_replays_reference_episode(name):
     """gym-style loop (explorer.py:53-69) through the single-env façade: ob/reward/done/info, action values and
     chosen actions equal the reference's, step by step, while the façade follows its own actions."""
     import modelcrowdnav_b200 as mcn
     tr = load_traj(name)
     weights0 = weights_for(name)
+    if tr["policy"] != "sarl":                                   # CADRL / LSTM-RL: policy_factory['cadrl' | 'lstm_rl']
+        weights0 = np.load(os.path.join(GOLDEN, "units_nets.npz"))[net_tag(tr) + "_weights"]
     env, robot, policy, _ = _setup(weights0, "f32", query_env=bool(tr["query_env"]), human_num=tr["H"], sim=tr["sim"],
-                                   randomize=bool(tr["randomize"]), kinematics=KIN_NAME[tr["kinematics"]])
+                                   randomize=bool(tr["randomize"]), kinematics=KIN_NAME[tr["kinematics"]],
+                                   policy_name=tr["policy"], interaction_module=bool(tr["interaction_module"]))
     holonomic = tr["kinematics"] == 0
     case = [c for c in tr["cases"] if c.startswith("test_")][0]
     rec = tr["cases"][case]
@@ -263,3 +280,34 @@ def test_explorer_rl_td_targets(weights0):
         gb = 0.9 ** 0.25
         resid = (values[:-1].reshape(-1) - gb * vt).abs()
         assert (resid < 1e-4).float().mean() > 0.5
+
+
+@pytest.mark.parametrize("tag,pname,im", [("cadrl", "cadrl", False), ("lstm", "lstm_rl", False), ("lstm2", "lstm_rl", True)])
+def test_other_policies_state_dict_and_training_surface(tag, pname, im):
+    """policy_factory['cadrl' | 'lstm_rl']: state-dict keys and flat weights equal the reference's (a reference checkpoint
+    loads unchanged); the torch module used for training computes what the CUDA network computes; last_state of LSTM-RL
+    comes out in predict()'s sorted human order; CADRL.transform insists on one human (cadrl.py:209)."""
+    import torch
+    import modelcrowdnav_b200 as mcn
+    z = np.load(os.path.join(GOLDEN, "units_nets.npz"))
+    w = z[tag + "_weights"]
+    env, robot, policy, _ = _setup(w, policy_name=pname, interaction_module=im)
+    assert list(policy.get_model().state_dict().keys()) == [str(k) for k in z[tag + "_weight_keys"]]
+    assert np.array_equal(policy.flat_weights(), w)
+    x = torch.from_numpy(z[tag + "_in_h5"]).cuda()
+    with torch.no_grad():
+        ref = policy.get_model()(x.reshape(-1, 13) if tag == "cadrl" else x).reshape(x.shape[0], -1)
+    got = policy.handle(1.0).forward(x)
+    want = ref.min(dim=1).values if tag == "cadrl" else ref[:, 0]
+    assert float((got - want).abs().max()) <= 1e-5
+    ob = env.reset("test", 3)
+    policy.set_phase("train"); policy.set_epsilon(0.0)
+    if tag == "cadrl":
+        with pytest.raises(AssertionError):
+            robot.act(ob)                                          # 5 humans: transform asserts a single human
+    else:
+        robot.act(ob)
+        d = [np.hypot(h.px - env.robot.px, h.py - env.robot.py) for h in env.humans]
+        order = sorted(range(len(d)), key=lambda i: d[i], reverse=True)
+        plain = policy.transform(mcn.JointState(env.robot.get_full_state(), [h.get_observable_state() for h in env.humans]))
+        assert torch.equal(policy.last_state, plain[order])

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import TRAJ_NAMES, TRAJ_NAMES_KIN, load_traj, weights_for
+from conftest import TRAJ_NAMES, TRAJ_NAMES_KIN, TRAJ_NAMES_NETS, load_traj, net_tag, weights_for
 
 pytestmark = pytest.mark.gpu
 
@@ -521,4 +521,89 @@ def test_golden_trajectories_kinematics(mcn, weights0, name, precision):
             assert np.array_equal(got[e][1:], rec["agents"][t + 1][1:])    # humans never touch cos / sin: bit-exact
             assert abs(th[e] - rec["theta"][t + 1]) <= 1e-12
     assert total == 0 or agree / total >= 0.999, (agree, total)
+    env.close(); pol.close()
+
+
+def _net_policy(mcn, tag, **kw):
+    """BatchedSARL configured as the reference's CADRL / LSTM-RL ([cadrl], [lstm_rl] of policy.config)."""
+    if tag == "cadrl":
+        return mcn.BatchedSARL(precision="f32", network="cadrl", mlp3_dims=[150, 100, 100, 1], **kw)
+    m1 = [150, 100, 100, 50] if tag == "lstm2" else [0, 0, 0, 0]
+    return mcn.BatchedSARL(precision="f32", network="lstm_rl", mlp3_dims=[150, 100, 100, 1], lstm_hidden=50,
+                           lstm_mlp1_dims=m1, **kw)
+
+
+@pytest.mark.parametrize("tag", ["cadrl", "lstm", "lstm2"])
+def test_other_value_networks_forward(mcn, units_nets, tag):
+    """cn_policy_forward for the CADRL mlp (min over the rows of an item) and both LSTM-RL networks against the outputs of
+    the reference's torch modules (tests/golden/units_nets.npz)."""
+    import torch
+    pol = _net_policy(mcn, tag)
+    w = units_nets[tag + "_weights"]
+    assert pol.n_params == w.size
+    pol.load_weights(w)
+    for H in (1, 5):
+        x, ref = units_nets["%s_in_h%d" % (tag, H)], units_nets["%s_out_h%d" % (tag, H)]
+        got = pol.forward(torch.from_numpy(x).cuda()).cpu().numpy()
+        want = ref.min(axis=1) if tag == "cadrl" else ref
+        assert np.max(np.abs(got - want)) <= 1e-5 * max(1.0, np.max(np.abs(want)))
+    with pytest.raises(mcn.CrowdNavError):
+        mcn.BatchedSARL(precision="f16_tc", network="cadrl")           # FP32 path only, no silent fallback
+    pol.close()
+
+
+@pytest.mark.parametrize("name", TRAJ_NAMES_NETS)
+def test_golden_trajectories_other_networks(mcn, oracle_mod, units_nets, name):
+    """CADRL.predict (value = reward + gamma_bar * min over humans) and LstmRL.predict (humans sorted by decreasing
+    distance unless query_env) on the GPU: teacher-forced replay of the reference's own episodes, same bars as SARL FP32."""
+    tr = load_traj(name)
+    tag = net_tag(tr)
+    H = tr["H"]
+    states, times, recs = [], [], []
+    for case, rec in tr["cases"].items():
+        for t in range(len(rec["time"])):
+            states.append(rec["agents"][t]); times.append(rec["time"][t]); recs.append((rec, t))
+    E = len(states)
+    env = mcn.BatchedCrowdSim(E, H)
+    pol = _net_policy(mcn, tag)
+    pol.load_weights(units_nets[tag + "_weights"])
+    env.set_state(np.stack(states), np.array(times))
+    env.orca()
+    pol.lookahead(env, query_env=tr["query_env"])
+    best, values = pol.read(env)
+    acts = np.stack([rec["action"][t] for rec, t in recs])
+    reward, done, info, dmin = env.step(acts, update=True)
+    got, gt = env.get_state()
+    agree = total = 0
+    for e, (rec, t) in enumerate(recs):
+        ref_v = rec["values"][t]
+        assert np.max(np.abs(values[e] - ref_v)) <= 1e-5 * max(1.0, np.max(np.abs(ref_v))), (name, e)
+        top2 = np.sort(ref_v)[-2:]
+        if top2[1] - top2[0] > 2e-5:
+            total += 1
+            agree += int(best[e] == rec["best"][t])
+        assert (reward[e], bool(done[e]), int(info[e])) == (rec["reward"][t], bool(rec["done"][t]), int(rec["info"][t]))
+        if t + 1 < len(rec["time"]):
+            assert np.array_equal(got[e], rec["agents"][t + 1]) and gt[e] == rec["time"][t + 1]
+    assert total > 0 and agree / total >= 0.999, (agree, total)
+    env.close(); pol.close()
+
+
+def test_lstm_last_state_is_sorted(mcn, oracle_mod, units_nets):
+    """cn_policy_last_state: LSTM-RL's last_state rows follow predict()'s human order (decreasing distance, stable);
+    cn_policy_transform keeps the env order (MultiHumanRL.transform never sorts)."""
+    o = oracle_mod
+    E, H = 32, 5
+    agents = _scenes(o, E, H, "square_crossing", phase="val")
+    agents[3, 2, :2] = agents[3, 0, :2] + [1.0, 2.0]; agents[3, 4, :2] = agents[3, 0, :2] + [-2.0, 1.0]   # a tie
+    env = mcn.BatchedCrowdSim(E, H)
+    pol = _net_policy(mcn, "lstm")
+    pol.load_weights(units_nets["lstm_weights"])
+    env.set_state(agents)
+    plain = pol.transform(env).cpu().numpy()
+    last = pol.transform(env, last_state=True).cpu().numpy()
+    for e in range(E):
+        want = o.transform(agents[e])
+        assert np.max(np.abs(plain[e] - want)) <= 1e-6
+        assert np.array_equal(last[e], plain[e][o.lstm_human_order(agents[e])])
     env.close(); pol.close()
