@@ -167,7 +167,7 @@ def main():
     ap.add_argument("--humans", type=int, default=5)
     ap.add_argument("--query-env", type=int, default=0)
     ap.add_argument("--sim", default="circle", choices=["circle", "square"])
-    ap.add_argument("--e2e-shards", type=int, default=2)
+    ap.add_argument("--e2e-shards", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
@@ -302,8 +302,8 @@ def main():
             "clocks": clocks,
             "e2e": {"value": world * E * ne / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "steps": ne, "shards_per_gpu": a.e2e_shards,
-                    "how": "PipelinedHostRollout: pinned host state in and out every step, copies of one env shard "
-                           "overlap the kernels of the other",
+                    "how": "PipelinedHostRollout: pinned host state in and out every step, the copies, host round trip and "
+                           "small kernels of one env shard overlap the row kernels of the others",
                     "blocking_single_handle_value": world * E * ne / e2e_blocking_s},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,

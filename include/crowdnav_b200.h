@@ -243,6 +243,11 @@ int cn_rollout_step_host_packed_async(cn_policy *p, cn_env *env, int query_env, 
                                       void *host_out, void *stream);
 int cn_stream_sync(int device, void *stream);
 
+/* Developer diagnostic: timeline of the library's stream operations (named CUDA events).  cn_debug_trace(1) starts a
+ * fresh recording, cn_debug_trace(0) stops; cn_debug_trace_dump synchronises and writes "ms stream name" lines. */
+int cn_debug_trace(int on);
+int cn_debug_trace_dump(char *buf, int64_t cap);
+
 /* Number of kernels this library launched so far in this process. */
 int64_t cn_launch_count(void);
 

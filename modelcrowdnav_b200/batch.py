@@ -291,9 +291,11 @@ class PipelinedHostRollout(object):
     shards' host->device / device->host copies are in flight (cn_rollout_step_host_packed_async).  Per step every
     env's state is uploaded from and downloaded to host memory, exactly like ``rollout_step_host_packed``; only the
     order in which the shards are served overlaps.  Results do not depend on the shard count (envs are independent
-    and keyed by their global id)."""
+    and keyed by their global id).  Measured on B200 (8192 envs x 5 humans): 1 handle blocking 8.8e6, 2 shards 9.3e6,
+    4 shards 1.05e7 env-steps/s -- with 4 shards there is always a queued row kernel, so each shard's copies, host
+    round trip, feature kernel and small kernels (which fit beside the persistent row kernel) are fully hidden."""
 
-    def __init__(self, num_envs, human_num, weights, device=0, shards=2, precision="f16_tc", env_id_offset=0,
+    def __init__(self, num_envs, human_num, weights, device=0, shards=4, precision="f16_tc", env_id_offset=0,
                  policy_cfg=None, **env_cfg):
         import torch
         assert num_envs % shards == 0

@@ -23,7 +23,47 @@ int cn_launch_transpose_out(int E, int H, int C, const double *src, double *dst,
 int cn_launch_set_actions(cn_env *env, const double *aos_dev, cudaStream_t s);
 int cn_launch_pack_keep(cn_env *env, cudaStream_t s);
 
+// ---- developer timeline: named CUDA events on whatever streams the work runs on -----------------
+struct TraceRec { const char *name; cudaStream_t stream; cudaEvent_t ev; };
+static std::vector<TraceRec> g_trace;
+static bool g_trace_on = false;
+
+void cn_trace_mark(const char *name, cudaStream_t s)
+{
+    if (!g_trace_on || g_trace.size() >= 4096) return;
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, s);
+    g_trace.push_back({name, s, ev});
+}
+
 extern "C" {
+
+/* Developer diagnostic: on = 1 starts recording a timeline of the library's stream operations (one CUDA event per mark),
+ * on = 0 stops.  cn_debug_trace_dump synchronises the device and writes "ms_since_first_mark stream name" lines. */
+int cn_debug_trace(int on)
+{
+    for (auto &r : g_trace) cudaEventDestroy(r.ev);
+    g_trace.clear();
+    g_trace_on = on != 0;
+    return CN_OK;
+}
+
+int cn_debug_trace_dump(char *buf, int64_t cap)
+{
+    if (!buf || cap < 1) { cn_set_error("null buffer"); return CN_EINVAL; }
+    CN_CUDA_CHECK(cudaDeviceSynchronize());
+    int64_t off = 0;
+    buf[0] = 0;
+    for (size_t i = 0; i < g_trace.size(); ++i) {
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, g_trace[0].ev, g_trace[i].ev);
+        const int n = snprintf(buf + off, (size_t)(cap - off), "%.4f %p %s\n", ms, (void *)g_trace[i].stream, g_trace[i].name);
+        if (n < 0 || off + n >= cap) break;
+        off += n;
+    }
+    return CN_OK;
+}
 
 const char *cn_last_error(void) { return g_err; }
 int cn_version(void) { return 100; }
@@ -185,6 +225,9 @@ int cn_env_destroy(cn_env *env)
     if (env->side_stream) cudaStreamDestroy(env->side_stream);
     if (env->ev_fork) cudaEventDestroy(env->ev_fork);
     if (env->ev_join) cudaEventDestroy(env->ev_join);
+    if (env->tail_stream) cudaStreamDestroy(env->tail_stream);
+    if (env->ev_rows) cudaEventDestroy(env->ev_rows);
+    if (env->ev_tail) cudaEventDestroy(env->ev_tail);
     delete env;
     return CN_OK;
 }
@@ -676,16 +719,29 @@ int cn_policy_forward(cn_policy *p, const float *x_dev, int32_t batch, int32_t h
 // fused hot path
 // ---------------------------------------------------------------------------------------------
 
+// tail: stream that takes over after the row kernel (nullptr = stay on s); on return *cur is the stream the step ended on
+static int rollout_step_impl(cn_policy *p, cn_env *env, int query_env, double epsilon, cudaStream_t s, cudaStream_t tail,
+                             cudaStream_t *cur);
+
 int cn_rollout_step(cn_policy *p, cn_env *env, int query_env, double epsilon, void *stream)
 {
     int rc = check_pair(p, env);
     if (rc) return rc;
     CN_CUDA_CHECK(cudaSetDevice(p->device));
-    cudaStream_t s = (cudaStream_t)stream;
+    cudaStream_t cur;
+    return rollout_step_impl(p, env, query_env, epsilon, (cudaStream_t)stream, nullptr, &cur);
+}
+
+static int rollout_step_impl(cn_policy *p, cn_env *env, int query_env, double epsilon, cudaStream_t s, cudaStream_t tail,
+                             cudaStream_t *cur)
+{
+    int rc = CN_OK;
+    if (p->cfg.precision != CN_PREC_F16_TC) tail = nullptr;
     // query_env = 0: the lookahead propagates humans with their current velocity (cadrl.py:107-109) and never reads
     // the ORCA result, so ORCA (a latency-bound 16 us kernel) runs on a forked stream beside the lookahead and joins
     // before the env step.  Event fork/join keeps the whole step capturable in a CUDA graph.
     const bool fork = !query_env;
+    cn_trace_mark("orca", fork ? s : s);
     if (fork) {
         if (!env->side_stream) {
             CN_CUDA_CHECK(cudaStreamCreateWithFlags(&env->side_stream, cudaStreamNonBlocking));
@@ -697,12 +753,16 @@ int cn_rollout_step(cn_policy *p, cn_env *env, int query_env, double epsilon, vo
         if ((rc = cn_launch_orca(env, env->side_stream))) return rc;
         CN_CUDA_CHECK(cudaEventRecord(env->ev_join, env->side_stream));
     } else if ((rc = cn_launch_orca(env, s))) return rc;
-    if (p->cfg.precision == CN_PREC_F16_TC) rc = cn_lookahead_tc(p, env, query_env, epsilon, s);
+    if (p->cfg.precision == CN_PREC_F16_TC) rc = cn_lookahead_tc(p, env, query_env, epsilon, s, tail);
     else rc = cn_lookahead_f32(p, env, query_env, epsilon, s);
     if (rc) return rc;
+    if (tail) s = tail;
+    *cur = s;
     if (fork) CN_CUDA_CHECK(cudaStreamWaitEvent(s, env->ev_join, 0));
+    cn_trace_mark("step", s);
     if ((rc = cn_launch_step(env, nullptr, 1, s))) return rc;
     if (env->p.auto_reset) rc = cn_launch_reset(env, 1, s);
+    cn_trace_mark("step_done", s);
     return rc;
 }
 
@@ -752,11 +812,33 @@ static int rollout_step_host_packed(cn_policy *p, cn_env *env, int query_env, do
     CN_CUDA_CHECK(cudaSetDevice(p->device));
     cudaStream_t s = (cudaStream_t)stream;
     if (!env->io_block) CN_CUDA_CHECK(cudaMalloc((void **)&env->io_block, (size_t)cn_host_step_bytes(env, 1) + 16));
+    cn_trace_mark("h2d", s);
     CN_CUDA_CHECK(cudaMemcpyAsync(env->io_block, host_in, (size_t)cn_host_step_bytes(env, 0), cudaMemcpyHostToDevice, s));
+    cn_trace_mark("unpack", s);
     if ((rc = cn_launch_io(env, env->io_block, 1, s))) return rc;          // keeps the per-episode accumulators
-    if ((rc = cn_rollout_step(p, env, query_env, epsilon, s))) return rc;
+    cudaStream_t tail = nullptr;
+    if (!sync) {
+        // non-blocking form = one shard of a pipelined host loop: everything after the row kernel runs at high priority
+        if (!env->tail_stream) {
+            int lo = 0, hi = 0;
+            CN_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CN_CUDA_CHECK(cudaStreamCreateWithPriority(&env->tail_stream, cudaStreamNonBlocking, hi));
+            CN_CUDA_CHECK(cudaEventCreateWithFlags(&env->ev_rows, cudaEventDisableTiming));
+            CN_CUDA_CHECK(cudaEventCreateWithFlags(&env->ev_tail, cudaEventDisableTiming));
+        }
+        tail = env->tail_stream;
+    }
+    cudaStream_t s0 = s;
+    if ((rc = rollout_step_impl(p, env, query_env, epsilon, s, tail, &s))) return rc;
     if ((rc = cn_launch_io(env, env->io_block, 0, s))) return rc;
+    cn_trace_mark("d2h", s);
     CN_CUDA_CHECK(cudaMemcpyAsync(host_out, env->io_block, (size_t)cn_host_step_bytes(env, 1), cudaMemcpyDeviceToHost, s));
+    cn_trace_mark("d2h_done", s);
+    if (s != s0) {                       // the caller's stream stays the one handle on the whole step
+        CN_CUDA_CHECK(cudaEventRecord(env->ev_tail, s));
+        CN_CUDA_CHECK(cudaStreamWaitEvent(s0, env->ev_tail, 0));
+        s = s0;
+    }
     if (sync) CN_CUDA_CHECK(cudaStreamSynchronize(s));
     return CN_OK;
 }

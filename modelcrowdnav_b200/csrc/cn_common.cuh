@@ -1,5 +1,6 @@
 // cn_common.cuh -- internal definitions shared by the kernels and the C ABI (sm_100a only).
 #pragma once
+#include <stdlib.h>
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -71,6 +72,8 @@ struct cn_env {
     // fork/join resources of cn_rollout_step: ORCA runs beside the lookahead when the lookahead does not read it
     cudaStream_t side_stream;
     cudaEvent_t ev_fork, ev_join;
+    cudaStream_t tail_stream;          // highest-priority stream for everything after the row kernel (pipelined host steps)
+    cudaEvent_t ev_rows, ev_tail;
     double *io_block;     // device image of the packed host exchange block (cn_rollout_step_host_packed), lazily allocated
 };
 
@@ -128,6 +131,23 @@ extern int64_t g_cn_launches;
             return CN_ECUDA;                                                                    \
         }                                                                                       \
     } while (0)
+
+// Block size of the small per-env kernels (ORCA, step, reset).  Co-residency with another env shard's persistent kernel
+// (PipelinedHostRollout) is decided per SM SUB-PARTITION: tc_rows_pair / tc_mlp3_pair run 19 warps (5,5,5,4 per
+// sub-partition) and are capped at 88 registers (__maxnreg__), which leaves 16384 - 5*88*32 = 2304 registers = one warp of
+// <= 72 registers in every sub-partition.  So one warp per sub-partition of step (70), reset (52), ORCA (46) or the feature
+// kernel (56, one 128-thread block per SM) runs UNDER the persistent kernel; at 96 registers only <= 32-register warps did
+// (measured with cn_debug_trace: step + reset of a shard took 258 us, i.e. waited for the other shard's row kernel to exit,
+// against 25 us now).  A preferred-carveout hint was tried first and changes nothing.  CN_SMALL_BLOCK overrides (A/B runs).
+static inline int cn_small_block()
+{
+    static const int b = [] { const char *e = getenv("CN_SMALL_BLOCK"); const int v = e ? atoi(e) : 32;
+                              return (v == 32 || v == 64 || v == 128) ? v : 32; }();
+    return b;
+}
+
+// developer timeline (cn_debug_trace): when enabled, records a CUDA event named `name` on stream `s`; a no-op otherwise
+void cn_trace_mark(const char *name, cudaStream_t s);
 
 #define CN_LAUNCH_CHECK()                                                                       \
     do {                                                                                        \
@@ -219,4 +239,5 @@ int cn_forward_f32(cn_policy *p, const float *x_dev, int batch, int H, float *ou
 int cn_tc_init(cn_policy *p);
 void cn_tc_destroy(cn_policy *p);
 int cn_tc_load_weights(cn_policy *p, const float *flat_host, cudaStream_t s);
-int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cudaStream_t s);
+// tail != nullptr: the kernels after the row kernel (mlp3, argmax) go to `tail`, ordered after `s` by env->ev_rows
+int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cudaStream_t s, cudaStream_t tail = nullptr);

@@ -943,7 +943,7 @@ int cn_tc_load_weights(cn_policy *p, const float *flat, cudaStream_t s)
     return CN_OK;
 }
 
-int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cudaStream_t s)
+int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cudaStream_t s, cudaStream_t tail)
 {
     TcState *t = (TcState *)p->tc;
     const EnvDims ed = env->p.d;
@@ -988,9 +988,11 @@ int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cu
         const int ht = (ed.H == 5 && G == ROWS / 5) ? 5 : ((ed.H == 10 && G == ROWS / 10) ? 10 : 0);
         auto feat = ht == 5 ? tc_features_kernel<5> : (ht == 10 ? tc_features_kernel<10> : tc_features_kernel<0>);
         auto kern = ht == 5 ? tc_rows_pair_kernel<5> : (ht == 10 ? tc_rows_pair_kernel<10> : tc_rows_pair_kernel<0>);
+        cn_trace_mark("features", s);
         feat<<<(unsigned)xtiles, ROWS, 0, s>>>(env->p, env->state, env->time, env->human_v, p->action_dev, A, query_env, (int)NG, G,
                                               env->theta, t->X, t->J, t->rew);
         CN_LAUNCH_CHECK();
+        cn_trace_mark("rows", s);
         kern<<<2 * nclusters, kThreadsPair, Q_SMEM, s>>>(env->p, t->img_pair, t->X, t->J, (int)NG, G, rounds, tw, t->dbg);
     } else {
         if (env->p.kinematics != CN_KIN_HOLONOMIC) {
@@ -1001,6 +1003,13 @@ int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cu
                                                             query_env, t->img_a, t->J, t->rew, (int)NG, G, ntiles_a, t->dbg);
     }
     CN_LAUNCH_CHECK();
+    if (tail && tail != s) {
+        // pipelined host steps: the rest of this shard's step runs on a HIGH-priority stream, so that when this row kernel
+        // exits its mlp3 is placed before the other shard's (already queued, lower-priority) row kernel takes every SM
+        CN_CUDA_CHECK(cudaEventRecord(env->ev_rows, s));
+        CN_CUDA_CHECK(cudaStreamWaitEvent(tail, env->ev_rows, 0));
+        s = tail;
+    }
     if (t->variant == 2) {
         int nclusters = t->num_sms / 2;
         const int slots_needed = (ntiles_b + 3) / 4;
@@ -1008,6 +1017,7 @@ int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cu
         const int rounds = (ntiles_b + 4 * nclusters - 1) / (4 * nclusters);
         TailW tw;
         memcpy(tw.w, t->tail_b, sizeof(tw.w));
+        cn_trace_mark("mlp3", s);
         tc_mlp3_pair_kernel<<<2 * nclusters, kThreadsM3, M_SMEM, s>>>(env->p, env->state, t->img_pair_b, t->J, t->rew, A, (int)NG,
                                                                      p->cfg.gamma, gamma_bar, p->cfg.v_pref, p->values, rounds, tw);
     } else {
@@ -1015,6 +1025,7 @@ int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cu
                                                    gamma_bar, p->cfg.v_pref, p->values, ntiles_b);
     }
     CN_LAUNCH_CHECK();
+    cn_trace_mark("argmax", s);
     return cn_lookahead_argmax(p, env, epsilon, s);
 }
 

@@ -504,7 +504,8 @@ static inline int grid_for(int n, int block) { return (n + block - 1) / block; }
 int cn_launch_orca(cn_env *env, cudaStream_t s)
 {
     const int n = env->p.d.E * env->p.d.H;
-    orca_humans_kernel<<<grid_for(n, 128), 128, 0, s>>>(env->p, env->state, env->frozen, env->human_v);
+    const int bs = cn_small_block();
+    orca_humans_kernel<<<grid_for(n, bs), bs, 0, s>>>(env->p, env->state, env->frozen, env->human_v);
     CN_LAUNCH_CHECK();
     env->orca_valid = 1;
     return CN_OK;
@@ -521,7 +522,8 @@ int cn_launch_robot_orca(cn_env *env, double safety_space, cudaStream_t s)
 int cn_launch_step(cn_env *env, const double *action_xy_dev, int update, cudaStream_t s)
 {
     const double *act = action_xy_dev ? action_xy_dev : env->action_xy;
-    step_kernel<<<grid_for(env->p.d.E, 64), 64, 0, s>>>(env->p, env->state, env->time, env->human_v, act,
+    const int bs = cn_small_block();
+    step_kernel<<<grid_for(env->p.d.E, bs), bs, 0, s>>>(env->p, env->state, env->time, env->human_v, act,
                                                             action_xy_dev ? 1 : 0, update, env->reward, env->done,
                                                             env->info, env->dmin, env->next_obs, env->frozen,
                                                             env->acc, env->theta);
@@ -532,7 +534,8 @@ int cn_launch_step(cn_env *env, const double *action_xy_dev, int update, cudaStr
 
 int cn_launch_reset(cn_env *env, int only_done, cudaStream_t s)
 {
-    reset_kernel<<<grid_for(env->p.d.E, 128), 128, 0, s>>>(env->p, env->state, env->time, env->done, only_done,
+    const int bs = cn_small_block();
+    reset_kernel<<<grid_for(env->p.d.E, bs), bs, 0, s>>>(env->p, env->state, env->time, env->done, only_done,
                                                              env->frozen, env->acc, env->theta);
     CN_LAUNCH_CHECK();
     env->orca_valid = 0;
@@ -571,8 +574,7 @@ int cn_launch_io(cn_env *env, double *blk, int unpack, cudaStream_t s)
     const size_t n = (size_t)env->p.d.E * env->p.d.A1 * F_COUNT + env->p.d.E;
     int grid = (int)((n + 255) / 256);
     if (grid > 148 * 8) grid = 148 * 8;
-    // 128-thread blocks of <= 56 registers fit beside a resident tc_rows_pair CTA (7168 free registers per SM), so the
-    // small kernels of one env shard run under the row kernel of another (PipelinedHostRollout); step_kernel: 64 threads
+    // <= 32 registers / thread: these blocks fit beside a resident tc_rows_pair CTA (see cn_small_block)
     grid *= 2;
     if (unpack) {
         io_unpack_kernel<<<grid, 128, 0, s>>>(env->p.d, env->state, env->time, blk);

@@ -28,7 +28,7 @@ constexpr uint32_t M_MISC = M_CTX0 + 2 * M_CTX_BYTES;                // S[2][128
 constexpr uint32_t M_SMEM = M_MISC + 1024 + 96 + 16;
 static_assert(M_SMEM <= 232448, "tc_mlp3_pair_kernel exceeds 227 KB of shared memory");
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsM3, 1)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(88)
 tc_mlp3_pair_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *__restrict__ wimg,
                     const uint8_t *__restrict__ J, const double *__restrict__ rew, int A, int NG, double gamma,
                     double gamma_bar_host, double v_pref_host, double *__restrict__ values, int rounds, const TailW tw)

@@ -240,7 +240,9 @@ __device__ __forceinline__ void ctx_barrier(int ctx)
 
 // HT = compile-time human count (5, 10: the benchmark configurations) or 0 = run-time H
 template <int HT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsPair, 1)
+// __maxnreg__(88), not __launch_bounds__ (the two exclude each other): see cn_small_block() in cn_common.cuh -- 88 registers
+// leave room for one <= 72-register warp of another shard's small kernels in every SM sub-partition; no measurable cost here.
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(88)
 tc_rows_pair_kernel(EnvParams p,
                     const uint8_t *__restrict__ wimg, const uint8_t *__restrict__ X, uint8_t *__restrict__ J, int NG, int G_rt,
                     int rounds, const TailW tw, long long *__restrict__ dbg)
