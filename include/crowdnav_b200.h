@@ -222,6 +222,11 @@ int cn_policy_forward(cn_policy *p, const float *x_dev, int32_t batch, int32_t h
 /* orca -> lookahead -> step(update=1) [-> auto reset], all on `stream`, no host round trip.
  * This is what Explorer.run_k_episodes' inner loop (explorer.py:62-69) does per env. */
 int cn_rollout_step(cn_policy *p, cn_env *env, int query_env, double epsilon, void *stream);
+/* Same step for ONE SHARD of a batch that the caller has split into several env handles, each stepped on its own
+ * stream (device-resident state, nothing synchronises): the kernels after the row kernel run on an internal
+ * high-priority stream and `stream` is made to wait for them, so that one shard's feature / small kernels run beside
+ * another shard's persistent row kernel instead of between two of them. */
+int cn_rollout_step_sharded(cn_policy *p, cn_env *env, int query_env, double epsilon, void *stream);
 /* Same through HOST buffers (blocking): uploads agents/times (E x (H+1) x 8, E), runs the step and
  * downloads the new state, reward, done, info and the chosen action index.  Pinned memory recommended. */
 int cn_rollout_step_host(cn_policy *p, cn_env *env, int query_env, double epsilon, const double *agents_in,

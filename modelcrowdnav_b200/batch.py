@@ -343,6 +343,17 @@ class PipelinedHostRollout(object):
                 C.c_void_p(b.in_ptr), C.c_void_p(b.out_ptr), C.c_void_p(self.streams[k].cuda_stream)))
             self._busy[k] = True
 
+    def step_device(self, query_env=False, epsilon=0.0):
+        """One step of every shard with the state left in HBM (cn_rollout_step_sharded, no copies, no host sync): the
+        device-resident counterpart of ``step()``; read the state back with ``envs[k].get_state()`` after ``sync()``."""
+        for k in range(self.shards):
+            check(self.lib.cn_rollout_step_sharded(self.pols[k].handle, self.envs[k].handle, int(bool(query_env)),
+                                                   float(epsilon), C.c_void_p(self.streams[k].cuda_stream)))
+
+    def sync_device(self):
+        for k in range(self.shards):
+            check(self.lib.cn_stream_sync(self.device, C.c_void_p(self.streams[k].cuda_stream)))
+
     def sync(self):
         """Wait for every shard; afterwards ``results()`` is valid."""
         for k in range(self.shards):

@@ -732,6 +732,32 @@ int cn_rollout_step(cn_policy *p, cn_env *env, int query_env, double epsilon, vo
     return rollout_step_impl(p, env, query_env, epsilon, (cudaStream_t)stream, nullptr, &cur);
 }
 
+static int ensure_tail_stream(cn_env *env)
+{
+    if (env->tail_stream) return CN_OK;
+    int lo = 0, hi = 0;
+    CN_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CN_CUDA_CHECK(cudaStreamCreateWithPriority(&env->tail_stream, cudaStreamNonBlocking, hi));
+    CN_CUDA_CHECK(cudaEventCreateWithFlags(&env->ev_rows, cudaEventDisableTiming));
+    CN_CUDA_CHECK(cudaEventCreateWithFlags(&env->ev_tail, cudaEventDisableTiming));
+    return CN_OK;
+}
+
+int cn_rollout_step_sharded(cn_policy *p, cn_env *env, int query_env, double epsilon, void *stream)
+{
+    int rc = check_pair(p, env);
+    if (rc) return rc;
+    CN_CUDA_CHECK(cudaSetDevice(p->device));
+    if ((rc = ensure_tail_stream(env))) return rc;
+    cudaStream_t s0 = (cudaStream_t)stream, cur = s0;
+    if ((rc = rollout_step_impl(p, env, query_env, epsilon, s0, env->tail_stream, &cur))) return rc;
+    if (cur != s0) {
+        CN_CUDA_CHECK(cudaEventRecord(env->ev_tail, cur));
+        CN_CUDA_CHECK(cudaStreamWaitEvent(s0, env->ev_tail, 0));
+    }
+    return CN_OK;
+}
+
 static int rollout_step_impl(cn_policy *p, cn_env *env, int query_env, double epsilon, cudaStream_t s, cudaStream_t tail,
                              cudaStream_t *cur)
 {
@@ -819,13 +845,7 @@ static int rollout_step_host_packed(cn_policy *p, cn_env *env, int query_env, do
     cudaStream_t tail = nullptr;
     if (!sync) {
         // non-blocking form = one shard of a pipelined host loop: everything after the row kernel runs at high priority
-        if (!env->tail_stream) {
-            int lo = 0, hi = 0;
-            CN_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-            CN_CUDA_CHECK(cudaStreamCreateWithPriority(&env->tail_stream, cudaStreamNonBlocking, hi));
-            CN_CUDA_CHECK(cudaEventCreateWithFlags(&env->ev_rows, cudaEventDisableTiming));
-            CN_CUDA_CHECK(cudaEventCreateWithFlags(&env->ev_tail, cudaEventDisableTiming));
-        }
+        if ((rc = ensure_tail_stream(env))) return rc;
         tail = env->tail_stream;
     }
     cudaStream_t s0 = s;

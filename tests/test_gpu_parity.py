@@ -472,7 +472,16 @@ def test_pipelined_host_rollout_matches_device_step(mcn, oracle_mod, weights0, s
     st = env.stats()
     assert st["episodes"] > 0                                       # some episodes ended and were re-seeded
     assert sum(e.stats()["episodes"] for e in pipe.envs) == st["episodes"]
-    pipe.close(); env.close(); pol.close()
+    pipe.close()
+    # the device-resident form of the same sharding (cn_rollout_step_sharded: no copies, no host sync between steps)
+    dev = mcn.PipelinedHostRollout(E, H, weights0, shards=shards, precision="f16_tc", auto_reset=1, seed=3)
+    dev.reset_device()
+    for step in range(110):
+        dev.step_device()
+    dev.sync_device()
+    got = [e.get_state() for e in dev.envs]
+    assert np.array_equal(np.concatenate([g[0] for g in got]), sa) and np.array_equal(np.concatenate([g[1] for g in got]), ta)
+    dev.close(); env.close(); pol.close()
 
 
 @pytest.mark.parametrize("precision", ["f32", "f16_tc"])
