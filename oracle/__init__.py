@@ -78,6 +78,19 @@ class NetCfg(C.Structure):
         return cls(NET_LSTM_RL, 13, 6, (C.c_int * 4)(150, 100, 100, 1), 50, (C.c_int * 4)(*m1))
 
 
+class OmCfg(C.Structure):
+    """crowd_nav/configs/policy.config [om]."""
+    _fields_ = [("cell_num", C.c_int), ("cell_size", C.c_double), ("om_channel_size", C.c_int)]
+
+    @classmethod
+    def default(cls):
+        return cls(4, 1.0, 3)
+
+    @property
+    def dim(self):
+        return self.cell_num ** 2 * self.om_channel_size
+
+
 _lib = None
 
 
@@ -132,6 +145,12 @@ def lib():
                                         C.c_double, C.c_int, dp, C.c_int, dp, C.c_double, dp, ip]
         L.orc_lookahead_net.restype = C.c_int
         L.orc_lstm_human_order.argtypes = [C.c_int, dp, ip]
+        L.orc_occupancy_maps.argtypes = [C.POINTER(OmCfg), C.c_int, dp, fp]
+        L.orc_lookahead_om.argtypes = [C.POINTER(EnvCfg), C.c_int, C.POINTER(SarlCfg), C.POINTER(NetCfg), C.POINTER(OmCfg),
+                                       fp, C.c_int, dp, C.c_double, C.c_int, C.c_double, C.c_int, dp, C.c_int, dp,
+                                       C.c_double, dp, ip]
+        L.orc_lookahead_om.restype = C.c_int
+        L.orc_transform_om.argtypes = [C.POINTER(OmCfg), C.c_int, dp, ip, C.c_int, C.c_double, fp]
         _lib = L
     return _lib
 
@@ -298,6 +317,42 @@ def lstm_human_order(agents):
     order = np.zeros(agents.shape[0] - 1, np.int32)
     lib().orc_lstm_human_order(agents.shape[0] - 1, _dp(agents), order.ctypes.data_as(C.POINTER(C.c_int)))
     return order
+
+
+def occupancy_maps(om, humans):
+    """build_occupancy_maps (multi_human_rl.py:109-163); humans (H, 4) = px py vx vy in network order -> (H, om.dim) f32."""
+    humans = _f64(humans)
+    out = np.zeros((humans.shape[0], om.dim), np.float32)
+    lib().orc_occupancy_maps(C.byref(om), humans.shape[0], _dp(humans), _fp(out))
+    return out
+
+
+def lookahead_om(ecfg, cfg, om, weights, agents, global_time, actions, query_env, human_vxy, gamma=0.9,
+                 kinematics=KIN_HOLONOMIC, theta=0.0):
+    """Lookahead with occupancy maps; cfg is a SarlCfg (SARL) or a NetCfg (LSTM-RL) whose input_dim = 13 + om.dim."""
+    agents = _f64(agents); actions = _f64(actions); weights = _f32(weights)
+    hv = _f64(human_vxy if human_vxy is not None else np.zeros((agents.shape[0] - 1, 2)))
+    values = np.full(actions.shape[0], np.nan)
+    reached = C.c_int()
+    is_sarl = isinstance(cfg, SarlCfg)
+    assert cfg.input_dim == 13 + om.dim
+    best = lib().orc_lookahead_om(C.byref(ecfg), NET_SARL if is_sarl else cfg.network, C.byref(cfg) if is_sarl else None,
+                                  None if is_sarl else C.byref(cfg), C.byref(om), _fp(weights), agents.shape[0] - 1,
+                                  _dp(agents), float(global_time), int(kinematics), float(theta), actions.shape[0],
+                                  _dp(actions), int(query_env), _dp(hv), float(gamma), _dp(values), C.byref(reached))
+    return best, values, bool(reached.value)
+
+
+def transform_om(om, agents, order=None, kinematics=KIN_HOLONOMIC, theta=0.0):
+    agents = _f64(agents)
+    H = agents.shape[0] - 1
+    out = np.empty((H, 13 + om.dim), np.float32)
+    op = None
+    if order is not None:
+        order = np.ascontiguousarray(order, dtype=np.int32)
+        op = order.ctypes.data_as(C.POINTER(C.c_int))
+    lib().orc_transform_om(C.byref(om), H, _dp(agents), op, int(kinematics), float(theta), _fp(out))
+    return out
 
 
 def default_net_weights(ncfg, seed=0):

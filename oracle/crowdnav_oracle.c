@@ -635,9 +635,17 @@ void orc_transform(int H, const double *agents, float *out)
 
 /* multi_human_rl.py:11-63 (greedy branch) */
 typedef double (*value_fn)(const void *ctx, int H, const float *x);
-static int lookahead_generic(const orc_env_cfg *ecfg, value_fn vf, const void *vctx, const int *order, int H,
+static int lookahead_generic_om(const orc_env_cfg *ecfg, value_fn vf, const void *vctx, const int *order,
+                  const orc_om_cfg *om, int H,
                   const double *agents, double global_time, int kinematics, double theta, int A, const double *actions,
                   int query_env, const double *human_vxy, double gamma, double *values_out, int *reached);
+static int lookahead_generic(const orc_env_cfg *ecfg, value_fn vf, const void *vctx, const int *order, int H,
+                  const double *agents, double global_time, int kinematics, double theta, int A, const double *actions,
+                  int query_env, const double *human_vxy, double gamma, double *values_out, int *reached)
+{
+    return lookahead_generic_om(ecfg, vf, vctx, order, NULL, H, agents, global_time, kinematics, theta, A, actions, query_env,
+                                human_vxy, gamma, values_out, reached);
+}
 
 typedef struct { const orc_sarl_cfg *c; const sarl_prep *P; } sarl_ctx;
 static double sarl_value(const void *ctx, int H, const float *x)
@@ -655,11 +663,53 @@ static int lookahead_prepared(const orc_env_cfg *ecfg, const orc_sarl_cfg *scfg,
                              human_vxy, gamma, values_out, reached);
 }
 
+/* multi_human_rl.py:109-163 */
+void orc_occupancy_maps(const orc_om_cfg *om, int H, const double *humans, float *out)
+{
+    const int cn = om->cell_num, cells = cn * cn, ch = om->om_channel_size;
+    for (int i = 0; i < H; ++i) {
+        const double *hi = humans + 4 * i;
+        double cnt[64], sx[64], sy[64];
+        for (int c = 0; c < cells; ++c) cnt[c] = sx[c] = sy[c] = 0.0;
+        const double angle = atan2(hi[3], hi[2]);                       /* human_velocity_angle */
+        for (int j = 0; j < H; ++j) {
+            if (j == i) continue;
+            const double *hj = humans + 4 * j;
+            const double opx = hj[0] - hi[0], opy = hj[1] - hi[1];
+            const double rotation = atan2(opy, opx) - angle;
+            const double distance = sqrt(opx * opx + opy * opy);       /* np.linalg.norm([px, py], axis=0) */
+            const double rx = cos(rotation) * distance, ry = sin(rotation) * distance;
+            const double xi = floor(rx / om->cell_size + cn / 2.0), yi = floor(ry / om->cell_size + cn / 2.0);
+            if (xi < 0 || xi >= cn || yi < 0 || yi >= cn) continue;    /* -inf index: in no cell */
+            const int idx = (int)(cn * yi + xi);
+            const double vrot = atan2(hj[3], hj[2]) - angle;
+            const double speed = sqrt(hj[2] * hj[2] + hj[3] * hj[3]);  /* np.linalg.norm(v, axis=1) */
+            cnt[idx] += 1.0;
+            sx[idx] += cos(vrot) * speed;                               /* python sum(): left to right, start 0 */
+            sy[idx] += sin(vrot) * speed;
+        }
+        float *o = out + (size_t)i * cells * ch;
+        for (int c = 0; c < cells; ++c) {
+            if (ch == 1) o[c] = cnt[c] > 0 ? 1.0f : 0.0f;
+            else if (ch == 2) { o[2 * c] = cnt[c] > 0 ? (float)(sx[c] / cnt[c]) : 0.0f; o[2 * c + 1] = cnt[c] > 0 ? (float)(sy[c] / cnt[c]) : 0.0f; }
+            else {
+                o[3 * c] = cnt[c] > 0 ? 1.0f : 0.0f;                    /* sum([1, 1, ..]) / len */
+                o[3 * c + 1] = cnt[c] > 0 ? (float)(sx[c] / cnt[c]) : 0.0f;
+                o[3 * c + 2] = cnt[c] > 0 ? (float)(sy[c] / cnt[c]) : 0.0f;
+            }
+        }
+    }
+}
+
 /* order (may be NULL = env order): position j of the network input is human order[j] (0-based) */
-static int lookahead_generic(const orc_env_cfg *ecfg, value_fn vf, const void *vctx, const int *order, int H,
+static int lookahead_generic_om(const orc_env_cfg *ecfg, value_fn vf, const void *vctx, const int *order,
+                  const orc_om_cfg *om, int H,
                   const double *agents, double global_time, int kinematics, double theta, int A, const double *actions,
                   int query_env, const double *human_vxy, double gamma, double *values_out, int *reached)
 {
+    const int om_dim = om ? om->cell_num * om->cell_num * om->om_channel_size : 0, in_dim = 13 + om_dim;
+    static __thread float omap[ORC_MAXH * 64 * 3];
+    int om_ready = 0;
     if (reached) *reached = 0;
     /* policy.py:43-49 reach_destination: norm((py-gy, px-gx)) < radius */
     if (norm2(AG(0, F_PY) - AG(0, F_GY), AG(0, F_PX) - AG(0, F_GX)) < AG(0, F_R)) {
@@ -671,7 +721,7 @@ static int lookahead_generic(const orc_env_cfg *ecfg, value_fn vf, const void *v
     double max_value = -INFINITY;
     int max_action = -1;
     double nhx[ORC_MAXH], nhy[ORC_MAXH], nhvx[ORC_MAXH], nhvy[ORC_MAXH], hr[ORC_MAXH];
-    float x[ORC_MAXH * 13];
+    static __thread float x[ORC_MAXH * (13 + 64 * 3)];
     for (int a = 0; a < A; ++a) {
         /* propagate robot (cadrl.py:113-125): non-holonomic actions are (v, r), next_theta = theta + r */
         double ax, ay;
@@ -701,7 +751,16 @@ static int lookahead_generic(const orc_env_cfg *ecfg, value_fn vf, const void *v
             row[7] = (float)AG(0, F_VPREF); row[8] = (float)next_theta;
             row[9] = (float)nhx[h]; row[10] = (float)nhy[h]; row[11] = (float)nhvx[h];
             row[12] = (float)nhvy[h]; row[13] = (float)hr[h];
-            orc_rotate_k(row, kinematics, x + (size_t)h * 13);
+            orc_rotate_k(row, kinematics, x + (size_t)h * in_dim);
+        }
+        if (om) {
+            if (!om_ready) {        /* built once, from the first action's next human states (multi_human_rl.py:47-49) */
+                double hs[ORC_MAXH * 4];
+                for (int h = 0; h < H; ++h) { hs[4 * h] = nhx[h]; hs[4 * h + 1] = nhy[h]; hs[4 * h + 2] = nhvx[h]; hs[4 * h + 3] = nhvy[h]; }
+                orc_occupancy_maps(om, H, hs, omap);
+                om_ready = 1;
+            }
+            for (int h = 0; h < H; ++h) memcpy(x + (size_t)h * in_dim + 13, omap + (size_t)h * om_dim, sizeof(float) * om_dim);
         }
         const double v = vf(vctx, H, x);
         const double value = reward + gamma_bar * v;
@@ -886,6 +945,53 @@ int orc_lookahead_net(const orc_env_cfg *ecfg, const orc_net_cfg *ncfg, const fl
                                     A, actions, query_env, human_vxy, gamma, values_out, reached);
     free(P.store);
     return r;
+}
+
+int orc_lookahead_om(const orc_env_cfg *ecfg, int net, const orc_sarl_cfg *scfg, const orc_net_cfg *ncfg,
+                     const orc_om_cfg *om, const float *weights, int H, const double *agents, double global_time,
+                     int kinematics, double theta, int A, const double *actions, int query_env, const double *human_vxy,
+                     double gamma, double *values_out, int *reached)
+{
+    int r;
+    if (net == ORC_NET_SARL) {
+        sarl_prep P;
+        sarl_prepare(scfg, weights, &P);
+        const sarl_ctx ctx = {scfg, &P};
+        r = lookahead_generic_om(ecfg, sarl_value, &ctx, NULL, om, H, agents, global_time, kinematics, theta, A, actions,
+                                 query_env, human_vxy, gamma, values_out, reached);
+        free(P.store);
+    } else {
+        net_prep P;
+        net_prepare(ncfg, weights, &P);
+        const net_ctx ctx = {ncfg, &P};
+        int order[ORC_MAXH];
+        const int sorted = net == ORC_NET_LSTM_RL && !query_env;
+        if (sorted) orc_lstm_human_order(H, agents, order);
+        r = lookahead_generic_om(ecfg, net_value, &ctx, sorted ? order : NULL, om, H, agents, global_time, kinematics, theta,
+                                 A, actions, query_env, human_vxy, gamma, values_out, reached);
+        free(P.store);
+    }
+    return r;
+}
+
+void orc_transform_om(const orc_om_cfg *om, int H, const double *agents, const int *order, int kinematics, double theta,
+                      float *out)
+{
+    const int om_dim = om->cell_num * om->cell_num * om->om_channel_size, in_dim = 13 + om_dim;
+    float rows[ORC_MAXH * 13];
+    static __thread float omap[ORC_MAXH * 64 * 3];
+    double hs[ORC_MAXH * 4];
+    orc_transform_k(H, agents, kinematics, theta, rows);
+    for (int j = 0; j < H; ++j) {
+        const int h = (order ? order[j] : j) + 1;
+        hs[4 * j] = AG(h, F_PX); hs[4 * j + 1] = AG(h, F_PY); hs[4 * j + 2] = AG(h, F_VX); hs[4 * j + 3] = AG(h, F_VY);
+    }
+    orc_occupancy_maps(om, H, hs, omap);
+    for (int j = 0; j < H; ++j) {
+        const int h = order ? order[j] : j;
+        memcpy(out + (size_t)j * in_dim, rows + (size_t)h * 13, sizeof(float) * 13);
+        memcpy(out + (size_t)j * in_dim + 13, omap + (size_t)j * om_dim, sizeof(float) * om_dim);
+    }
 }
 
 void orc_batch_lookahead_step(const orc_env_cfg *ecfg, const orc_sarl_cfg *scfg, const float *weights,

@@ -202,6 +202,50 @@ def gen_net_units():
     print("units_nets.npz written;", len(out), "arrays")
 
 
+# occupancy maps (with_om = true): input_dim 13 + 4 * 4 * 3 = 61
+TRAJ_SPECS_OM = [
+    ("om_sarl_circle5", 5, "circle_crossing", False, False, [("test", 50, 25), ("test", 51, 25)], False, "holonomic", "sarl",
+     {"sarl__with_om": "true"}),
+    ("om_sarl_square10_qtrue", 10, "square_crossing", True, False, [("test", 52, 15)], False, "holonomic", "sarl",
+     {"sarl__with_om": "true"}),
+    ("om_lstm_circle5", 5, "circle_crossing", False, False, [("test", 53, 25)], False, "holonomic", "lstm_rl",
+     {"lstm_rl__with_om": "true"}),
+]
+
+
+def gen_om_units():
+    """build_occupancy_maps on random human states, transform() with maps, and the seed-0 weights of the OM networks."""
+    refshim.install()
+    from crowd_sim.envs.utils.state import ObservableState, FullState, JointState
+    out = {}
+    rs = np.random.RandomState(777)
+    for tag, pname, over in (("om_sarl", "sarl", {"sarl__with_om": "true"}), ("om_lstm", "lstm_rl", {"lstm_rl__with_om": "true"})):
+        env, robot, policy = refshim.make_env_and_sarl(seed=0, policy_name=pname, policy_over=over)
+        sd = policy.get_model().state_dict()
+        out[tag + "_weights"] = np.concatenate([v.numpy().ravel() for v in sd.values()]).astype(np.float32)
+        out[tag + "_weight_keys"] = np.array(list(sd.keys()))
+    for H in (2, 5, 10):
+        ins, maps, trs = [], [], []
+        for _ in range(48):
+            hs = rs.uniform(-2.5, 2.5, size=(H, 4))
+            hs[:, 2:] = rs.uniform(-1, 1, size=(H, 2))
+            if rs.rand() < 0.2:
+                hs[0, 2:] = 0.0                                   # a standing human: arctan2(0, 0)
+            humans = [ObservableState(*row, 0.3) for row in hs]
+            maps.append(policy.build_occupancy_maps(humans).numpy())
+            robot_state = FullState(*rs.uniform(-3, 3, 2), *rs.uniform(-1, 1, 2), 0.3, *rs.uniform(-3, 3, 2), 1.0, 0.0)
+            policy.kinematics = "holonomic"
+            trs.append(policy.transform(JointState(robot_state, humans)).numpy())
+            ins.append(np.concatenate([[[robot_state.px, robot_state.py, robot_state.vx, robot_state.vy, robot_state.gx,
+                                         robot_state.gy, 0.3, 1.0]],
+                                       np.concatenate([hs, np.zeros((H, 2)), np.full((H, 1), 0.3), np.ones((H, 1))], axis=1)]))
+        out["om_agents_h%d" % H] = np.array(ins)
+        out["om_maps_h%d" % H] = np.array(maps)
+        out["om_transform_h%d" % H] = np.array(trs)
+    np.savez_compressed(os.path.join(GOLD, "units_om.npz"), **out)
+    print("units_om.npz written;", len(out), "arrays")
+
+
 def gen_trajectories(specs=None, weights=None):
     for spec in (specs or TRAJ_SPECS):
         name, H, sim, qenv, vis, cases = spec[:6]
@@ -214,7 +258,9 @@ def gen_trajectories(specs=None, weights=None):
                                                         kinematics=kinematics, policy_name=pname, policy_over=pover)
         out = {"H": np.array(H), "query_env": np.array(int(qenv)), "robot_visible": np.array(int(vis)),
                "sim": np.array(sim), "randomize": np.array(int(randomize)), "kinematics": np.array(KIN_CODE[kinematics]),
-               "policy": np.array(pname), "interaction_module": np.array(int(bool(pover)))}
+               "policy": np.array(pname),
+               "interaction_module": np.array(int(bool(pover) and pover.get("lstm_rl__with_interaction_module") == "true")),
+               "with_om": np.array(int(bool(pover) and "true" in (pover.get("sarl__with_om"), pover.get("lstm_rl__with_om"))))}
         t0 = time.time()
         for (phase, case, max_steps) in cases:
             rec = run_trajectory(env, robot, policy, phase, case, max_steps)
@@ -275,6 +321,7 @@ if __name__ == "__main__":
     ap.add_argument("--kin-none", action="store_true", help="with --episodes: the fork's literal kinematics (None)")
     ap.add_argument("--random", action="store_true", help="only the randomize_attributes trajectories")
     ap.add_argument("--kinematics", action="store_true", help="only the kinematics = None / unicycle trajectories")
+    ap.add_argument("--om", action="store_true", help="only the occupancy-map (with_om) unit vectors and trajectories")
     ap.add_argument("--nets", action="store_true", help="only the CADRL / LSTM-RL unit vectors and trajectories")
     ap.add_argument("--trained", action="store_true", help="use tests/golden/sarl_weights_trained.npy (GPU-trained SARL)")
     a = ap.parse_args()
@@ -286,6 +333,9 @@ if __name__ == "__main__":
         gen_episodes(a.procs, wtrained if a.trained else None, "kin_none_" + ("trained" if a.trained else "seed0"), None)
     elif a.episodes:
         gen_episodes(a.procs, wtrained if a.trained else None, "trained" if a.trained else "seed0")
+    elif a.om:
+        gen_om_units()
+        gen_trajectories(TRAJ_SPECS_OM)
     elif a.nets:
         gen_net_units()
         gen_trajectories(TRAJ_SPECS_NETS)

@@ -37,6 +37,7 @@ def load_traj(name):
     out = {"H": int(z["H"]), "query_env": int(z["query_env"]), "robot_visible": int(z["robot_visible"]),
            "policy": str(z["policy"]) if "policy" in z.files else "sarl",
            "interaction_module": int(z["interaction_module"]) if "interaction_module" in z.files else 0,
+           "with_om": int(z["with_om"]) if "with_om" in z.files else 0,
            "sim": str(z["sim"]), "randomize": int(z["randomize"]) if "randomize" in z.files else 0,
            "kinematics": int(z["kinematics"]) if "kinematics" in z.files else 0, "cases": {}}
     for case in z["cases"]:
@@ -55,6 +56,15 @@ TRAJ_NAMES_KIN = ["circle5_kin_none", "circle5_kin_none_qtrue", "circle5_unicycl
 # the other value networks behind the same lookahead (policy_factory: cadrl, lstm_rl; ValueNetwork2 = interaction module)
 TRAJ_NAMES_NETS = ["cadrl_circle5", "cadrl_circle5_qtrue", "cadrl_circle1", "lstm_circle5", "lstm_circle5_qtrue",
                    "lstm2_square10"]
+
+
+# occupancy maps (with_om = true, input_dim 61): OM-SARL and OM-LSTM-RL
+TRAJ_NAMES_OM = ["om_sarl_circle5", "om_sarl_square10_qtrue", "om_lstm_circle5"]
+
+
+@pytest.fixture(scope="session")
+def units_om():
+    return dict(np.load(os.path.join(GOLDEN, "units_om.npz"), allow_pickle=False))
 
 
 @pytest.fixture(scope="session")

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import TRAJ_NAMES_NETS, net_tag, TRAJ_NAMES, TRAJ_NAMES_KIN, load_traj, weights_for
+from conftest import TRAJ_NAMES_NETS, TRAJ_NAMES_OM, net_tag, TRAJ_NAMES, TRAJ_NAMES_KIN, load_traj, weights_for
 
 
 def test_action_space_matches_reference(oracle_mod, units):
@@ -177,3 +177,60 @@ def test_trajectories_other_networks(oracle_mod, units_nets, name):
                 assert best == int(rec["best"][t]), (case, t)
             n += 1
     assert n >= 20
+
+
+def _om_cfgs(o, policy):
+    """(network cfg with input_dim 61, OmCfg) of the reference's OM-SARL / OM-LSTM-RL."""
+    om = o.OmCfg.default()
+    if policy == "sarl":
+        cfg = o.SarlCfg.default()
+    else:
+        cfg = o.NetCfg.lstm_rl()
+    cfg.input_dim = 13 + om.dim
+    return cfg, om
+
+
+@pytest.mark.parametrize("H", [2, 5, 10])
+def test_occupancy_maps(oracle_mod, units_om, H):
+    """build_occupancy_maps (multi_human_rl.py:109-163) and transform() with maps against the reference, including humans
+    at rest (arctan2(0, 0)) and humans outside every cell."""
+    o = oracle_mod
+    om = o.OmCfg.default()
+    agents, maps, trs = units_om["om_agents_h%d" % H], units_om["om_maps_h%d" % H], units_om["om_transform_h%d" % H]
+    occupied = 0
+    for a, m, t in zip(agents, maps, trs):
+        got = o.occupancy_maps(om, a[1:, :4])
+        assert got.shape == m.shape and np.max(np.abs(got - m)) <= 1e-6
+        assert np.array_equal(got[:, 0::3], m[:, 0::3])                 # occupancy channel exact
+        occupied += int(m[:, 0::3].sum())
+        gt = o.transform_om(om, a)
+        assert np.max(np.abs(gt - t)) <= 1e-5
+    assert occupied > 0
+
+
+@pytest.mark.parametrize("name", TRAJ_NAMES_OM)
+def test_trajectories_with_occupancy_maps(oracle_mod, units_om, name):
+    """OM-SARL / OM-LSTM-RL predict() replayed against the reference's own episodes: the maps are built once per predict
+    from the first action's next human states (multi_human_rl.py:47-49), in the network's human order."""
+    o = oracle_mod
+    tr = load_traj(name)
+    assert tr["with_om"] == 1
+    cfg, om = _om_cfgs(o, tr["policy"])
+    w = units_om[("om_sarl" if tr["policy"] == "sarl" else "om_lstm") + "_weights"]
+    ecfg = o.EnvCfg.default()
+    n = 0
+    for case, rec in tr["cases"].items():
+        table = rec["table"]
+        for t in range(len(rec["time"])):
+            agents = np.ascontiguousarray(rec["agents"][t])
+            hv = o.human_actions(ecfg, agents)
+            assert np.array_equal(hv, rec["human_v"][t]), (case, t)
+            best, values, reached = o.lookahead_om(ecfg, cfg, om, w, agents, float(rec["time"][t]), table, tr["query_env"], hv)
+            assert not reached
+            ref_v = rec["values"][t]
+            assert np.max(np.abs(values - ref_v)) <= 1e-5 * max(1.0, np.max(np.abs(ref_v))), (case, t)
+            top2 = np.sort(ref_v)[-2:]
+            if top2[1] - top2[0] > 1e-5:
+                assert best == int(rec["best"][t]), (case, t)
+            n += 1
+    assert n >= 15
