@@ -107,6 +107,13 @@ typedef struct {
     int32_t network;             /* CN_NET_* */
     int32_t lstm_hidden;         /* [lstm_rl] global_state_dim = 50 */
     int32_t lstm_mlp1_dims[4];   /* [lstm_rl] mlp1_dims = 150,100,100,50; {0} = ValueNetwork1 */
+    /* Occupancy maps ([sarl] / [lstm_rl] with_om = true, multi_human_rl.py:43-50,98-163): every rotated row is followed by
+     * the cell_num x cell_num x om_channel_size map of the OTHER humans around that human, built once per lookahead from
+     * the next human states; input_dim must be 13 + cell_num^2 * om_channel_size.  FP32 path only. */
+    int32_t with_om;
+    int32_t cell_num;            /* [om] cell_num = 4 (<= 8) */
+    double cell_size;            /* [om] cell_size = 1 */
+    int32_t om_channel_size;     /* [om] om_channel_size = 3 (1, 2 or 3) */
 } cn_sarl_cfg;
 
 /* Episode statistics accumulated on the device by cn_env_step(update=1); the counters

@@ -182,7 +182,7 @@ class BatchedSARL(object):
         """MultiHumanRL.transform for every env -> torch CUDA tensor (E, H, 13) fp32.  last_state=True: what predict()
         leaves in policy.last_state (LSTM-RL: rows in its sorted human order, lstm_rl.py:99-104)."""
         import torch
-        out = torch.empty((env.E, env.H, 13), dtype=torch.float32, device="cuda:%d" % self.device)
+        out = torch.empty((env.E, env.H, self.cfg.input_dim), dtype=torch.float32, device="cuda:%d" % self.device)
         fn = self.lib.cn_policy_last_state if last_state else self.lib.cn_policy_transform
         check(fn(self.handle, env.handle, C.c_void_p(out.data_ptr()), _stream(stream)))
         return out
@@ -192,7 +192,7 @@ class BatchedSARL(object):
         import torch
         if x.dim() == 2:                              # CADRL trains on single (robot, human) rows (cadrl.py:202-216)
             x = x.unsqueeze(1)
-        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.shape[2] == 13
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.shape[2] == self.cfg.input_dim
         x = x.contiguous()
         out = torch.empty((x.shape[0],), dtype=torch.float32, device=x.device)
         check(self.lib.cn_policy_forward(self.handle, C.c_void_p(x.data_ptr()), x.shape[0], x.shape[1],

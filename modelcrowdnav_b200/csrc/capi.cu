@@ -103,6 +103,7 @@ void cn_sarl_cfg_default(cn_sarl_cfg *c)
     c->gamma = 0.9; c->v_pref = 1.0; c->precision = CN_PREC_F32;
     c->kinematics = CN_KIN_HOLONOMIC;
     c->network = CN_NET_SARL; c->lstm_hidden = 50;      // [lstm_rl] global_state_dim; lstm_mlp1_dims = {0}: ValueNetwork1
+    c->with_om = 0; c->cell_num = 4; c->cell_size = 1.0; c->om_channel_size = 3;   // [om]
 }
 
 static int use_device(int device)
@@ -480,8 +481,20 @@ int cn_policy_create(const cn_sarl_cfg *cfg, int device, cn_policy **out)
 {
     if (!cfg || !out) { cn_set_error("null argument"); return CN_EINVAL; }
     const int A = cfg->speed_samples * cfg->rotation_samples + 1;
-    if (cfg->input_dim != 13 || cfg->self_state_dim < 1 || cfg->self_state_dim > 13) {
-        cn_set_error("input_dim must be 13 (with_om = false) and 1 <= self_state_dim <= 13");
+    int om_dim = 0;
+    if (cfg->with_om) {
+        if (cfg->cell_num < 1 || cfg->cell_num > 8 || cfg->om_channel_size < 1 || cfg->om_channel_size > 3 || !(cfg->cell_size > 0)) {
+            cn_set_error("with_om needs 1 <= cell_num <= 8, om_channel_size in {1, 2, 3} and cell_size > 0");
+            return CN_EINVAL;
+        }
+        if (cfg->network == CN_NET_CADRL) { cn_set_error("CADRL has no occupancy maps (cadrl.py:60-62)"); return CN_EINVAL; }
+        if (cfg->precision != CN_PREC_F32) {
+            cn_set_error("occupancy maps run on the FP32 path only (precision = CN_PREC_F32)"); return CN_EUNSUPPORTED;
+        }
+        om_dim = cfg->cell_num * cfg->cell_num * cfg->om_channel_size;
+    }
+    if (cfg->input_dim != 13 + om_dim || cfg->self_state_dim < 1 || cfg->self_state_dim > 13) {
+        cn_set_error("input_dim must be 13 + cell_num^2 * om_channel_size (13 without maps) and 1 <= self_state_dim <= 13");
         return CN_EUNSUPPORTED;
     }
     if (cfg->attn_dims[2] != 1 || cfg->mlp3_dims[3] != 1) { cn_set_error("attention and mlp3 must end in 1 unit"); return CN_EINVAL; }
@@ -516,6 +529,7 @@ int cn_policy_create(const cn_sarl_cfg *cfg, int device, cn_policy **out)
     d.net = cfg->network; d.lstm_h = cfg->network == CN_NET_LSTM_RL ? cfg->lstm_hidden : 0;
     for (int i = 0; i < 4; ++i) d.lm1[i] = cfg->network == CN_NET_LSTM_RL ? cfg->lstm_mlp1_dims[i] : 0;
     d.lstm_in = d.lm1[0] > 0 ? d.lm1[3] : d.in;
+    d.om_dim = om_dim; d.cell_num = cfg->cell_num; d.om_ch = cfg->om_channel_size; d.cell_size = cfg->cell_size;
     d.A = build_action_table(cfg, p->action_host);
     p->n_params = cn_policy_param_count(cfg);
 

@@ -84,7 +84,10 @@ struct SarlDims {
     int net;        // CN_NET_*: SARL, CADRL (m3 = its mlp on every row), LSTM-RL (m3 = the mlp on cat(self, h_n))
     int lstm_h;     // LSTM hidden size
     int lm1[4];     // LSTM-RL ValueNetwork2's mlp1 widths, lm1[0] = 0 -> ValueNetwork1
-    int lstm_in;    // LSTM input width (13 or lm1[3])
+    int lstm_in;    // LSTM input width (input_dim or lm1[3])
+    int om_dim;     // occupancy-map floats per row (0 = with_om off), cell_num^2 * om_ch
+    int cell_num, om_ch;
+    double cell_size;
 };
 
 // fp32 weights on the device, transposed to [in][out_padded] (out padded to a multiple of 4)

@@ -30,7 +30,7 @@ __host__ __device__ inline int pad4(int x) { return (x + 3) & ~3; }
 struct F32Plan {
     int H, A, CA;             // humans, actions, actions per chunk
     int wX, wT0, wM1, wF, wJ; // padded smem row widths (floats)
-    int oX, oT0, oM1, oF, oG, oJ, oS, oW, oV, oEnv, oOrd, total_floats;  // smem offsets (floats)
+    int oX, oT0, oM1, oF, oG, oJ, oS, oW, oV, oEnv, oOrd, oOm, total_floats;  // smem offsets (floats)
 };
 
 // out[r][n] = act( (accum ? out[r][n] : 0) + sum_k in[r / in_div][k] * Wt[k_off + k][n] (+ b[n]) )
@@ -258,6 +258,41 @@ __device__ __forceinline__ void net_forward_smem(const SarlWeightsDev &W, const 
     else sarl_forward_smem(W, d, pl, sm, ng);
 }
 
+// build_occupancy_maps for ONE human (multi_human_rl.py:109-163): grid of cell_num x cell_num cells of cell_size metres
+// centred on the human, x axis along its velocity; per cell [occupied, mean vx, mean vy] (om_ch = 3) of the OTHER humans,
+// velocities in the same frame.  get(j, f): f = 0..3 -> px, py, vx, vy of the j-th human in network order.  float64 like
+// numpy, one float32 rounding at the end (torch .float()).
+template <typename Get>
+__device__ void occupancy_map_row(const SarlDims &d, int H, int i, Get get, float *__restrict__ out)
+{
+    const int cn = d.cell_num, cells = cn * cn, ch = d.om_ch;
+    for (int c = 0; c < cells * ch; ++c) out[c] = 0.0f;
+    const double pxi = get(i, 0), pyi = get(i, 1);
+    const double angle = atan2(get(i, 3), get(i, 2));
+    // two passes keep the accumulators in registers: per cell, sum in the reference's order (others in list order)
+    for (int c = 0; c < cells; ++c) {
+        double cnt = 0.0, sx = 0.0, sy = 0.0;
+        for (int j = 0; j < H; ++j) {
+            if (j == i) continue;
+            const double opx = get(j, 0) - pxi, opy = get(j, 1) - pyi;
+            const double rotation = atan2(opy, opx) - angle;
+            const double distance = sqrt(opx * opx + opy * opy);
+            const double xi = floor(cos(rotation) * distance / d.cell_size + cn / 2.0);
+            const double yi = floor(sin(rotation) * distance / d.cell_size + cn / 2.0);
+            if (xi < 0 || xi >= cn || yi < 0 || yi >= cn) continue;
+            if ((int)(cn * yi + xi) != c) continue;
+            const double vx = get(j, 2), vy = get(j, 3);
+            const double vrot = atan2(vy, vx) - angle, speed = sqrt(vx * vx + vy * vy);
+            cnt += 1.0; sx += cos(vrot) * speed; sy += sin(vrot) * speed;
+        }
+        if (cnt > 0.0) {
+            if (ch == 1) out[c] = 1.0f;
+            else if (ch == 2) { out[2 * c] = (float)(sx / cnt); out[2 * c + 1] = (float)(sy / cnt); }
+            else { out[3 * c] = 1.0f; out[3 * c + 1] = (float)(sx / cnt); out[3 * c + 2] = (float)(sy / cnt); }
+        }
+    }
+}
+
 // grid = (E, chunks)
 __global__ void __launch_bounds__(kThreads, 2)
 lookahead_values_kernel(EnvParams p, SarlWeightsDev W, SarlDims d, F32Plan pl, const double *__restrict__ st,
@@ -342,6 +377,13 @@ lookahead_values_kernel(EnvParams p, SarlWeightsDev W, SarlDims d, F32Plan pl, c
         }
         rew[i] = reward;
     }
+    // occupancy maps: built once per predict() from the next human states, in network order (multi_human_rl.py:47-49)
+    float *OM = sm + pl.oOm;
+    if (d.om_dim > 0) {
+        for (int i = threadIdx.x; i < H; i += blockDim.x)
+            occupancy_map_row(d, H, i, [&](int j, int f) { return hnext[ord[j] * 4 + f]; }, OM + (size_t)i * d.om_dim);
+        __syncthreads();
+    }
     // rotated joint-state rows (multi_human_rl.py:43-45): torch.Tensor([...]) rounds the doubles to fp32
     for (int r = threadIdx.x; r < rows; r += blockDim.x) {
         const int i = r / H, h = ord[r - i * H];
@@ -357,6 +399,7 @@ lookahead_values_kernel(EnvParams p, SarlWeightsDev W, SarlDims d, F32Plan pl, c
         cn_rotate(s, o, kin);
 #pragma unroll
         for (int k = 0; k < 13; ++k) X[(size_t)r * pl.wX + k] = o[k];
+        for (int k = 0; k < d.om_dim; ++k) X[(size_t)r * pl.wX + 13 + k] = OM[(size_t)(r - i * H) * d.om_dim + k];
     }
     __syncthreads();
     net_forward_smem(W, d, pl, sm, na);
@@ -416,7 +459,7 @@ argmax_kernel(EnvParams p, int A, const double *__restrict__ st, const uint8_t *
 // MultiHumanRL.transform (multi_human_rl.py:90-104): current joint state -> E x H x 13 fp32
 // sort_humans: rows in LstmRL.predict's order (decreasing distance to the robot, stable: lstm_rl.py:99-104) -- what
 // predict() leaves in last_state for LSTM-RL; 0 = env order (MultiHumanRL.transform itself never sorts).
-__global__ void transform_kernel(EnvParams p, const double *__restrict__ st, const double *__restrict__ theta,
+__global__ void transform_kernel(EnvParams p, SarlDims nd, const double *__restrict__ st, const double *__restrict__ theta,
                                  float *__restrict__ out, int sort_humans)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -442,7 +485,14 @@ __global__ void transform_kernel(EnvParams p, const double *__restrict__ st, con
             pos += (dk > dh || (dk == dh && k < h)) ? 1 : 0;
         }
     }
-    for (int k = 0; k < 13; ++k) out[((size_t)e * d.H + pos) * 13 + k] = o[k];
+    const int D = 13 + nd.om_dim;
+    float *row = out + ((size_t)e * d.H + pos) * D;
+    for (int k = 0; k < 13; ++k) row[k] = o[k];
+    // with_om (multi_human_rl.py:98-101): map of the CURRENT human states around this human.  The others are visited in env
+    // order; for a sorted last_state the reference visits them in sorted order, which only permutes a float64 sum.
+    if (nd.om_dim > 0)
+        occupancy_map_row(nd, d.H, h, [&](int j, int f) { return st[st_idx(d, f == 0 ? F_PX : f == 1 ? F_PY : f == 2 ? F_VX : F_VY, j + 1, e)]; },
+                          row + 13);
 }
 
 // ValueNetwork.forward on a device batch (B x H x 13 -> B); grid = chunks of CA items
@@ -454,9 +504,10 @@ forward_kernel(SarlWeightsDev W, SarlDims d, F32Plan pl, const float *__restrict
     const int nb = min(pl.CA, B - b0);
     const int H = pl.H;
     float *X = sm + pl.oX;
-    for (int i = threadIdx.x; i < nb * H * 13; i += blockDim.x) {
-        const int r = i / 13, k = i - r * 13;
-        X[(size_t)r * pl.wX + k] = x[(size_t)b0 * H * 13 + i];
+    const int D = d.in;                                   // 13, or 13 + occupancy map
+    for (int i = threadIdx.x; i < nb * H * D; i += blockDim.x) {
+        const int r = i / D, k = i - r * D;
+        X[(size_t)r * pl.wX + k] = x[(size_t)b0 * H * D + i];
     }
     __syncthreads();
     net_forward_smem(W, d, pl, sm, nb);
@@ -473,7 +524,7 @@ F32Plan make_plan(const SarlDims &d, int H, int A, int A1)
     if (pl.CA > A) pl.CA = A;
     const int rows = pl.CA * H;
     auto mx = [](int a, int b) { return a > b ? a : b; };
-    pl.wX = 16;
+    pl.wX = d.in <= 16 ? 16 : pad4(d.in);          // 13 rotated features (+ occupancy map)
     pl.wT0 = pad4(mx(mx(d.m1[0], d.m2[0]), mx(mx(d.at[0], d.m3[0]), d.m3[2])));
     pl.wM1 = pad4(mx(mx(d.m1[1], d.at[1]), d.m3[1]));
     pl.wF = pad4(d.m2[1]);
@@ -497,6 +548,7 @@ F32Plan make_plan(const SarlDims &d, int H, int A, int A1)
     o = (o + 3) & ~3;
     pl.oEnv = o; o += 2 * (A1 * F_COUNT + H * 4 + pl.CA);
     pl.oOrd = o; o += pad4(H);                      // LSTM-RL: humans in network order
+    pl.oOm = o; o += pad4(H * d.om_dim);            // with_om: one map per human
     pl.total_floats = o;
     return pl;
 }
@@ -555,9 +607,8 @@ int cn_lookahead_f32(cn_policy *p, cn_env *env, int query_env, double epsilon, c
 
 int cn_transform_f32(cn_policy *p, cn_env *env, float *out_dev, int sort_humans, cudaStream_t s)
 {
-    (void)p;
     const int n = env->p.d.E * env->p.d.H;
-    transform_kernel<<<(n + 127) / 128, 128, 0, s>>>(env->p, env->state, env->theta, out_dev, sort_humans);
+    transform_kernel<<<(n + 127) / 128, 128, 0, s>>>(env->p, p->d, env->state, env->theta, out_dev, sort_humans);
     CN_LAUNCH_CHECK();
     return CN_OK;
 }

@@ -217,14 +217,12 @@ class SARL(Policy):
         mlp3_dims = [int(x) for x in config.get("sarl", "mlp3_dims").split(", ")]
         attention_dims = [int(x) for x in config.get("sarl", "attention_dims").split(", ")]
         self.with_om = config.getboolean("sarl", "with_om")
-        if self.with_om:
-            raise NotImplementedError("OM-SARL occupancy maps are outside the B200 hot path (SURVEY §8(f) rank 3)")
         with_global_state = config.getboolean("sarl", "with_global_state")
         if not with_global_state:
             raise NotImplementedError("with_global_state = false is not supported by the CUDA lookahead")
         self._dims = dict(mlp1_dims=mlp1_dims, mlp2_dims=mlp2_dims, attn_dims=attention_dims, mlp3_dims=mlp3_dims)
-        self._net_kwargs = dict(self._dims)
-        self.model = make_value_network(self.joint_state_dim, self.self_state_dim, mlp1_dims, mlp2_dims, mlp3_dims,
+        self._net_kwargs = dict(self._dims, **self._om_kwargs())
+        self.model = make_value_network(self.input_dim(), self.self_state_dim, mlp1_dims, mlp2_dims, mlp3_dims,
                                         attention_dims, with_global_state)
         self.multiagent_training = config.getboolean("sarl", "multiagent_training")
         logging.info("Policy: {} {} global state".format(self.name, "w/" if with_global_state else "w/o"))
@@ -308,6 +306,8 @@ class SARL(Policy):
         v_pref = state.self_state.v_pref
         if self.action_space is None:
             self.build_action_space(v_pref)
+        if self.with_om and len(state.human_states) < 2:
+            raise ValueError("need at least one array to concatenate")     # build_occupancy_maps with a single human
         h = self.handle(v_pref)
         if self.query_env:
             # the env façade owns the one-env batch; its ORCA result is shared with the following step()
@@ -340,7 +340,19 @@ class SARL(Policy):
         return self.transform(state)
 
     def input_dim(self):
-        return self.joint_state_dim
+        """multi_human_rl.py:106-107"""
+        return self.joint_state_dim + (self.cell_num ** 2 * self.om_channel_size if self.with_om else 0)
+
+    def _om_kwargs(self):
+        """cn_sarl_cfg fields of the occupancy maps; with_om moves the lookahead to the FP32 path (the tcgen05 kernels take
+        13-feature rows only)."""
+        if not self.with_om:
+            return {}
+        if not (1 <= self.cell_num <= 8 and self.om_channel_size in (1, 2, 3)):
+            raise NotImplementedError("occupancy maps: 1 <= cell_num <= 8 and om_channel_size in {1, 2, 3}")
+        self.precision = "f32"
+        return dict(input_dim=self.input_dim(), with_om=1, cell_num=self.cell_num, cell_size=self.cell_size,
+                    om_channel_size=self.om_channel_size)
 
 
 def make_cadrl_network(input_dim, mlp_dims):
@@ -442,8 +454,6 @@ class LstmRL(SARL):
         mlp_dims = [int(x) for x in config.get("lstm_rl", "mlp2_dims").split(", ")]
         global_state_dim = config.getint("lstm_rl", "global_state_dim")
         self.with_om = config.getboolean("lstm_rl", "with_om")
-        if self.with_om:
-            raise NotImplementedError("occupancy maps are outside the B200 hot path (SURVEY §8(f) rank 3)")
         with_interaction_module = config.getboolean("lstm_rl", "with_interaction_module")
         mlp1_dims = [int(x) for x in config.get("lstm_rl", "mlp1_dims").split(", ")] if with_interaction_module else None
         if len(mlp_dims) != 4 or mlp_dims[-1] != 1 or (mlp1_dims and len(mlp1_dims) != 4):
@@ -453,7 +463,7 @@ class LstmRL(SARL):
         self.multiagent_training = config.getboolean("lstm_rl", "multiagent_training")
         self._dims = dict(mlp3_dims=mlp_dims)
         self._net_kwargs = dict(network="lstm_rl", mlp3_dims=mlp_dims, lstm_hidden=global_state_dim,
-                                lstm_mlp1_dims=mlp1_dims or [0, 0, 0, 0])
+                                lstm_mlp1_dims=mlp1_dims or [0, 0, 0, 0], **self._om_kwargs())
         logging.info("Policy: {}LSTM-RL {} pairwise interaction module".format(
             "OM-" if self.with_om else "", "w/" if with_interaction_module else "w/o"))
 

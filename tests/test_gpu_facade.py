@@ -88,7 +88,7 @@ KIN_NAME = {0: "holonomic", 1: "unicycle", 2: None}
 
 
 def _setup(weights0, precision="f32", query_env=False, human_num=5, sim="circle_crossing", randomize=False,
-           kinematics="holonomic", policy_name="sarl", interaction_module=False):
+           kinematics="holonomic", policy_name="sarl", interaction_module=False, with_om=False):
     """Wire env, robot, policy, explorer exactly as crowd_nav/test.py:52-87 does."""
     import torch
     import modelcrowdnav_b200 as mcn
@@ -96,7 +96,8 @@ def _setup(weights0, precision="f32", query_env=False, human_num=5, sim="circle_
                 env__randomize_attributes="true" if randomize else "false")
     pcfg = _cfg(POLICY_INI, action_space__query_env="true" if query_env else "false",
                 action_space__kinematics=kinematics or "holonomic",
-                lstm_rl__with_interaction_module="true" if interaction_module else "false")
+                lstm_rl__with_interaction_module="true" if interaction_module else "false",
+                sarl__with_om="true" if with_om else "false", lstm_rl__with_om="true" if with_om else "false")
     policy = mcn.policy_factory[policy_name]()
     import modelcrowdnav_b200.policy as policy_mod
     policy_mod.LITERAL_FORK_KINEMATICS = kinematics is None      # None: the fork never reads the key (cadrl.py:66)
@@ -138,18 +139,22 @@ def test_state_dict_keys_match_reference(weights0, units):
                                   "circle5_random", "square10_random",
                                   "circle5_kin_none", "circle5_kin_none_qtrue", "circle5_unicycle", "square10_unicycle_qtrue",
                                   "cadrl_circle5", "cadrl_circle5_qtrue", "cadrl_circle1", "lstm_circle5",
-                                  "lstm_circle5_qtrue", "lstm2_square10"])
+                                  "lstm_circle5_qtrue", "lstm2_square10",
+                                  "om_sarl_circle5", "om_sarl_square10_qtrue", "om_lstm_circle5"])
 def test_facade_replays_reference_episode(name):
     """gym-style loop (explorer.py:53-69) through the single-env façade: ob/reward/done/info, action values and
     chosen actions equal the reference's, step by step, while the façade follows its own actions."""
     import modelcrowdnav_b200 as mcn
     tr = load_traj(name)
     weights0 = weights_for(name)
-    if tr["policy"] != "sarl":                                   # CADRL / LSTM-RL: policy_factory['cadrl' | 'lstm_rl']
+    if tr["with_om"]:                                            # occupancy maps: [sarl] / [lstm_rl] with_om = true
+        weights0 = np.load(os.path.join(GOLDEN, "units_om.npz"))[("om_sarl" if tr["policy"] == "sarl" else "om_lstm") + "_weights"]
+    elif tr["policy"] != "sarl":                                 # CADRL / LSTM-RL: policy_factory['cadrl' | 'lstm_rl']
         weights0 = np.load(os.path.join(GOLDEN, "units_nets.npz"))[net_tag(tr) + "_weights"]
     env, robot, policy, _ = _setup(weights0, "f32", query_env=bool(tr["query_env"]), human_num=tr["H"], sim=tr["sim"],
                                    randomize=bool(tr["randomize"]), kinematics=KIN_NAME[tr["kinematics"]],
-                                   policy_name=tr["policy"], interaction_module=bool(tr["interaction_module"]))
+                                   policy_name=tr["policy"], interaction_module=bool(tr["interaction_module"]),
+                                   with_om=bool(tr["with_om"]))
     holonomic = tr["kinematics"] == 0
     case = [c for c in tr["cases"] if c.startswith("test_")][0]
     rec = tr["cases"][case]

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import TRAJ_NAMES, TRAJ_NAMES_KIN, TRAJ_NAMES_NETS, load_traj, net_tag, weights_for
+from conftest import TRAJ_NAMES, TRAJ_NAMES_KIN, TRAJ_NAMES_NETS, TRAJ_NAMES_OM, load_traj, net_tag, weights_for
 
 pytestmark = pytest.mark.gpu
 
@@ -615,4 +615,62 @@ def test_lstm_last_state_is_sorted(mcn, oracle_mod, units_nets):
         want = o.transform(agents[e])
         assert np.max(np.abs(plain[e] - want)) <= 1e-6
         assert np.array_equal(last[e], plain[e][o.lstm_human_order(agents[e])])
+    env.close(); pol.close()
+
+
+def _om_policy(mcn, policy):
+    kw = dict(precision="f32", input_dim=61, with_om=1, cell_num=4, cell_size=1.0, om_channel_size=3)
+    if policy == "sarl":
+        return mcn.BatchedSARL(**kw)
+    return mcn.BatchedSARL(network="lstm_rl", mlp3_dims=[150, 100, 100, 1], lstm_hidden=50, **kw)
+
+
+@pytest.mark.parametrize("H", [2, 5, 10])
+def test_transform_with_occupancy_maps(mcn, units_om, H):
+    """cn_policy_transform with_om: rotated rows + occupancy maps of the current human states against the reference's
+    MultiHumanRL.transform (multi_human_rl.py:90-163); the occupancy channel must be exact."""
+    agents, trs = units_om["om_agents_h%d" % H], units_om["om_transform_h%d" % H]
+    E = agents.shape[0]
+    env = mcn.BatchedCrowdSim(E, H)
+    pol = _om_policy(mcn, "sarl")
+    pol.load_weights(units_om["om_sarl_weights"])
+    env.set_state(np.ascontiguousarray(agents))
+    got = pol.transform(env).cpu().numpy()
+    assert got.shape == trs.shape == (E, H, 61)
+    assert np.max(np.abs(got - trs)) <= 1e-5
+    assert np.array_equal(got[:, :, 13::3], trs[:, :, 13::3])
+    with pytest.raises(mcn.CrowdNavError):
+        mcn.BatchedSARL(precision="f16_tc", input_dim=61, with_om=1)     # FP32 path only, no silent fallback
+    env.close(); pol.close()
+
+
+@pytest.mark.parametrize("name", TRAJ_NAMES_OM)
+def test_golden_trajectories_with_occupancy_maps(mcn, units_om, name):
+    """OM-SARL / OM-LSTM-RL lookahead on the GPU against the reference's own episodes (values 1e-5, argmax, transition)."""
+    tr = load_traj(name)
+    H = tr["H"]
+    states, times, recs = [], [], []
+    for case, rec in tr["cases"].items():
+        for t in range(len(rec["time"])):
+            states.append(rec["agents"][t]); times.append(rec["time"][t]); recs.append((rec, t))
+    E = len(states)
+    env = mcn.BatchedCrowdSim(E, H)
+    pol = _om_policy(mcn, tr["policy"])
+    pol.load_weights(units_om[("om_sarl" if tr["policy"] == "sarl" else "om_lstm") + "_weights"])
+    env.set_state(np.stack(states), np.array(times))
+    env.orca()
+    pol.lookahead(env, query_env=tr["query_env"])
+    best, values = pol.read(env)
+    acts = np.stack([rec["action"][t] for rec, t in recs])
+    reward, done, info, dmin = env.step(acts, update=True)
+    agree = total = 0
+    for e, (rec, t) in enumerate(recs):
+        ref_v = rec["values"][t]
+        assert np.max(np.abs(values[e] - ref_v)) <= 1e-5 * max(1.0, np.max(np.abs(ref_v))), (name, e)
+        top2 = np.sort(ref_v)[-2:]
+        if top2[1] - top2[0] > 2e-5:
+            total += 1
+            agree += int(best[e] == rec["best"][t])
+        assert (reward[e], bool(done[e]), int(info[e])) == (rec["reward"][t], bool(rec["done"][t]), int(rec["info"][t]))
+    assert total > 0 and agree / total >= 0.999, (agree, total)
     env.close(); pol.close()
