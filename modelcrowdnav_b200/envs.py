@@ -252,9 +252,18 @@ class CrowdSim(object):
         self.robot = robot
 
     # -- helpers -----------------------------------------------------------------------------------
+    def phase_human_num(self, phase):
+        """crowd_sim.py:272-275,288-292: a policy trained on single humans (CADRL, multiagent_training = false) sees ONE
+        circle-crossing human in the train / val phases."""
+        if phase != "test" and not self.robot.policy.multiagent_training:
+            self.train_val_sim = "circle_crossing"                     # crowd_sim.py:276-277 (mutates, like the reference)
+            return 1
+        return self.human_num
+
     def scene_kwargs(self, phase):
+        human_num = self.phase_human_num(phase)
         rule = self.test_sim if phase == "test" else self.train_val_sim
-        return dict(human_num=self.human_num, rule=rule, circle_radius=self.circle_radius,
+        return dict(human_num=human_num, rule=rule, circle_radius=self.circle_radius,
                     square_width=self.square_width, human_radius=self.config.getfloat("humans", "radius"),
                     human_v_pref=self.config.getfloat("humans", "v_pref"), discomfort_dist=self.discomfort_dist,
                     robot_radius=self.robot.radius, robot_v_pref=self.robot.v_pref,
@@ -272,10 +281,11 @@ class CrowdSim(object):
 
     def _ensure_batch(self):
         kin = KIN_CODE[self.robot.kinematics]        # changes when train.py swaps the robot's policy (ORCA -> SARL)
-        if self._batch is None or self._batch.H != self.human_num or self._batch.cfg.robot_kinematics != kin:
+        H = len(self.humans) if self.humans is not None else self.human_num
+        if self._batch is None or self._batch.H != H or self._batch.cfg.robot_kinematics != kin:
             if self._batch is not None:
                 self._batch.close()
-            self._batch = BatchedCrowdSim(1, self.human_num, device=self.device, **batch_env_kwargs(self))
+            self._batch = BatchedCrowdSim(1, H, device=self.device, **batch_env_kwargs(self))
         return self._batch
 
     def _sync_agents(self, agents):
@@ -293,10 +303,15 @@ class CrowdSim(object):
         if case < 0:
             raise NotImplementedError("debug test cases (crowd_sim.py:297-303) are not part of the hot path")
         self.global_time = 0
-        self.human_times = [0] * self.human_num
-        agents = scenes.generate_scene(phase, case, **self.scene_kwargs(phase))
+        kw = self.scene_kwargs(phase)
+        agents = scenes.generate_scene(phase, case, **kw)
+        H = agents.shape[0] - 1
+        if kw["rule"] == "mixed":                                      # crowd_sim.py:124: the drawn count sticks to the env
+            dummy = H == 1 and tuple(agents[1, [0, 1, 4, 5]]) == (0.0, -10.0, 0.0, -10.0)
+            self.human_num = 0 if dummy else H
+        self.human_times = [0] * H
         self.robot.set(*[float(agents[0, i]) for i in (0, 1, 4, 5, 2, 3)], np.pi / 2)
-        self.humans = [Human(self.config, "humans") for _ in range(self.human_num)]
+        self.humans = [Human(self.config, "humans") for _ in range(H)]
         for h, row in zip(self.humans, agents[1:]):
             h.set(*[float(row[i]) for i in (0, 1, 4, 5, 2, 3)], 0, radius=float(row[6]), v_pref=float(row[7]))
         for agent in [self.robot] + self.humans:

@@ -98,11 +98,11 @@ class Explorer(object):
         self._target_handle = None
 
     # -- GPU plumbing ------------------------------------------------------------------------------
-    def _batch(self, k):
-        key = (k, self.env.human_num, self.robot.kinematics)      # kinematics follows the robot's policy (ORCA -> SARL)
+    def _batch(self, k, H):
+        key = (k, H, self.robot.kinematics)                       # kinematics follows the robot's policy (ORCA -> SARL)
         if key not in self._batches:
             dev = getattr(self.device, "index", None) or 0     # torch.device('cuda') has index None -> GPU 0
-            self._batches[key] = BatchedCrowdSim(k, self.env.human_num, device=dev, gamma=self.gamma or 0.9,
+            self._batches[key] = BatchedCrowdSim(k, H, device=dev, gamma=self.gamma or 0.9,
                                                  **batch_env_kwargs(self.env))
         return self._batches[key]
 
@@ -130,8 +130,40 @@ class Explorer(object):
         if robot.kinematics not in ("holonomic", "unicycle", None):
             raise NotImplementedError("robot kinematics must be holonomic, unicycle or None (the fork's literal behaviour)")
         cases = env.next_cases(phase, k, test_case)
-        agents = scenes.generate_batch(phase, cases, **env.scene_kwargs(phase))
-        b = self._batch(k)
+        kw = env.scene_kwargs(phase)
+        scene_list = [scenes.generate_scene(phase, int(c), **kw) for c in cases]
+        sizes = sorted(set(a.shape[0] for a in scene_list))
+        if len(sizes) > 1:
+            # 'mixed' scenes (crowd_sim.py:111-161) draw their own human count: one batch per count, merged in case order
+            if update_memory:
+                raise NotImplementedError("replay filling over scenes with different human counts (the reference's "
+                                          "DataLoader cannot collate them either)")
+            parts = []
+            for n in sizes:
+                idx = [i for i, a in enumerate(scene_list) if a.shape[0] == n]
+                parts.append((idx, self._rollout(np.stack([scene_list[i] for i in idx]), phase, False, imitation_learning,
+                                                 stay)))
+            T = max(p[1]["R"].shape[0] for p in parts)
+            R = np.zeros((T, k)); M = np.zeros((T, k), bool)
+            final_info = np.zeros(k, np.int64); end_time = np.zeros(k)
+            too_close, min_dist = 0, []
+            for idx, r in parts:
+                R[:r["R"].shape[0], idx] = r["R"]; M[:r["M"].shape[0], idx] = r["M"]
+                final_info[idx] = r["final_info"]; end_time[idx] = r["end_time"]
+                too_close += r["too_close"]; min_dist += r["min_dist"]
+            states_t = None
+        else:
+            r = self._rollout(np.stack(scene_list), phase, update_memory, imitation_learning, stay)
+            R, M, final_info, end_time = r["R"], r["M"], r["final_info"], r["end_time"]
+            too_close, min_dist, states_t = r["too_close"], r["min_dist"], r["states_t"]
+        return self._summarise(k, phase, cases, R, M, final_info, end_time, too_close, min_dist, states_t, update_memory,
+                               imitation_learning, episode, print_failure, stay, returnRate, returnNav)
+
+    def _rollout(self, agents, phase, update_memory, imitation_learning, stay):
+        """k episodes with the same human count side by side (explorer.py:53-69 for every env of the batch)."""
+        env, robot, policy = self.env, self.robot, self.robot.policy
+        k = agents.shape[0]
+        b = self._batch(k, agents.shape[1] - 1)
         b.set_state(agents, np.zeros(k))
         dt, v_pref = env.time_step, robot.v_pref
         robot.time_step = dt                      # CrowdSim.reset does this for every agent (crowd_sim.py:307-309)
@@ -196,9 +228,14 @@ class Explorer(object):
             active &= ~finished
         if active.any():
             raise ValueError("Invalid end signal from environment")
+        return dict(R=np.stack(rewards_t), M=np.stack(active_t), final_info=final_info, end_time=end_time,
+                    too_close=too_close, min_dist=min_dist, states_t=states_t)
 
-        R = np.stack(rewards_t)                      # (T, k)
-        M = np.stack(active_t)
+    def _summarise(self, k, phase, cases, R, M, final_info, end_time, too_close, min_dist, states_t, update_memory,
+                   imitation_learning, episode, print_failure, stay, returnRate, returnNav):
+        """Counters, log lines, replay filling and return values of explorer.py:70-151."""
+        import torch
+        env, robot = self.env, self.robot
         success = final_info == _capi.REACHGOAL
         collision = final_info == _capi.COLLISION
         timeout = final_info == _capi.TIMEOUT

@@ -12,19 +12,53 @@ def _norm(a, b):
     return float(np.linalg.norm((a, b)))
 
 
+# crowd_sim.py:113-115: number of humans of a 'mixed' scene, by cumulative probability over the sorted keys
+MIXED_STATIC_NUM = {0: 0.05, 1: 0.2, 2: 0.2, 3: 0.3, 4: 0.1, 5: 0.15}
+MIXED_DYNAMIC_NUM = {1: 0.3, 2: 0.3, 3: 0.2, 4: 0.1, 5: 0.1}
+
+
 def generate_scene(phase, case, human_num=5, rule="circle_crossing", circle_radius=4.0, square_width=10.0,
                    human_radius=0.3, human_v_pref=1.0, discomfort_dist=0.2, robot_radius=0.3, robot_v_pref=1.0,
                    randomize_attributes=False):
     """Agents (H+1, 8) float64 [px py vx vy gx gy radius v_pref]; agent 0 = robot (crowd_sim.py:284).
     randomize_attributes ([env] randomize_attributes): each human first draws v_pref ~ U(0.5, 1.5) and
-    radius ~ U(0.3, 0.5) from the same stream (crowd_sim.py:167-168,190-191; agent.py:39-45)."""
+    radius ~ U(0.3, 0.5) from the same stream (crowd_sim.py:167-168,190-191; agent.py:39-45).
+    rule = 'mixed' (crowd_sim.py:111-161): the scene draws its own number of humans (the human_num argument is ignored, as
+    in the reference) -- 20 % static scenes of 0-5 standing humans (goal = position; 0 humans = one dummy human parked at
+    (0, -10)), else 1-5 moving humans, the first two circle-crossing, the rest square-crossing."""
     rs = np.random.RandomState(COUNTER_OFFSET[phase] + case)
-    agents = np.zeros((human_num + 1, 8))
-    agents[0] = [0, -circle_radius, 0, 0, 0, circle_radius, robot_radius, robot_v_pref]
+    robot = [0, -circle_radius, 0, 0, 0, circle_radius, robot_radius, robot_v_pref]
     base_radius, base_v_pref = human_radius, human_v_pref
+    rules = None
+    if rule == "mixed":
+        static = bool(rs.random_sample() < 0.2)
+        prob = rs.random_sample()
+        for key, value in sorted((MIXED_STATIC_NUM if static else MIXED_DYNAMIC_NUM).items()):
+            if prob - value <= 0:
+                human_num = key
+                break
+            prob -= value
+        if static:
+            rows = [robot]
+            if human_num == 0:
+                rows.append([0, -10, 0, 0, 0, -10, base_radius, base_v_pref])
+            for _ in range(human_num):
+                sign = -1 if rs.random_sample() > 0.5 else 1
+                while True:
+                    px = rs.random_sample() * 4 * 0.5 * sign                  # width = 4
+                    py = (rs.random_sample() - 0.5) * 8                       # height = 8
+                    if not any(_norm(px - a[0], py - a[1]) < base_radius + a[6] + discomfort_dist for a in rows):
+                        break
+                rows.append([px, py, 0, 0, px, py, base_radius, base_v_pref])
+            return np.array(rows, dtype=np.float64)
+        rules = ["circle_crossing" if i < 2 else "square_crossing" for i in range(human_num)]
+    agents = np.zeros((human_num + 1, 8))
+    agents[0] = robot
     for i in range(1, human_num + 1):
         prev = agents[:i]
         human_radius, human_v_pref = base_radius, base_v_pref
+        if rules is not None:
+            rule = rules[i - 1]
         if randomize_attributes:
             human_v_pref = rs.uniform(0.5, 1.5)
             human_radius = rs.uniform(0.3, 0.5)

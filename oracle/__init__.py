@@ -421,11 +421,40 @@ def generate_scene(phase, case, human_num=5, rule="circle_crossing", circle_radi
     randomize = [env] randomize_attributes: every human first draws v_pref ~ U(0.5, 1.5) and radius ~ U(0.3, 0.5)
     (crowd_sim.py:167-168,190-191; agent.py:39-45), one legacy-uniform draw each."""
     rs = np.random.RandomState(COUNTER_OFFSET[phase] + case)      # crowd_sim.py:286
-    agents = np.zeros((human_num + 1, AGENT_STRIDE))
-    agents[0] = [0, -circle_radius, 0, 0, 0, circle_radius, robot_radius, robot_v_pref]  # crowd_sim.py:284
     base_radius, base_v_pref = radius, v_pref
+    robot_row = [0, -circle_radius, 0, 0, 0, circle_radius, robot_radius, robot_v_pref]  # crowd_sim.py:284
+    per_human_rule = None
+    if rule == "mixed":                                            # crowd_sim.py:111-161
+        static_num = {0: 0.05, 1: 0.2, 2: 0.2, 3: 0.3, 4: 0.1, 5: 0.15}
+        dynamic_num = {1: 0.3, 2: 0.3, 3: 0.2, 4: 0.1, 5: 0.1}
+        static = rs.random_sample() < 0.2
+        prob = rs.random_sample()
+        for key, value in sorted(static_num.items() if static else dynamic_num.items()):
+            if prob - value <= 0:
+                human_num = key
+                break
+            else:
+                prob -= value
+        if static:                                                 # standing humans in a 4 x 8 box, goal = position
+            rows = [robot_row]
+            if human_num == 0:
+                rows.append([0, -10, 0, 0, 0, -10, base_radius, base_v_pref])
+            for _ in range(human_num):
+                sign = -1 if rs.random_sample() > 0.5 else 1
+                while True:
+                    px = rs.random_sample() * 4 * 0.5 * sign
+                    py = (rs.random_sample() - 0.5) * 8
+                    if not any(_norm2(px - a[0], py - a[1]) < base_radius + a[6] + discomfort_dist for a in rows):
+                        break
+                rows.append([px, py, 0, 0, px, py, base_radius, base_v_pref])
+            return np.array(rows, dtype=np.float64)
+        per_human_rule = ["circle_crossing" if i < 2 else "square_crossing" for i in range(human_num)]
+    agents = np.zeros((human_num + 1, AGENT_STRIDE))
+    agents[0] = robot_row
     for i in range(1, human_num + 1):
         radius, v_pref = base_radius, base_v_pref
+        if per_human_rule is not None:
+            rule = per_human_rule[i - 1]
         if randomize:
             v_pref = rs.uniform(0.5, 1.5)
             radius = rs.uniform(0.3, 0.5)

@@ -246,6 +246,32 @@ def gen_om_units():
     print("units_om.npz written;", len(out), "arrays")
 
 
+# [sim] train_val_sim / test_sim = mixed: every scene draws its own human count (0-5 standing or 1-5 moving humans)
+# (one case per fixture: the reference sizes human_times by the PREVIOUS scene's count, crowd_sim.py:272, and raises
+# IndexError in step() as soon as a scene draws more humans than the one before)
+TRAJ_SPECS_MIXED = [
+    ("mixed_sarl_a", 5, "mixed", False, False, [("test", 0, 30)], False, "holonomic", "sarl", None),
+    ("mixed_sarl_b", 5, "mixed", False, False, [("test", 3, 30)], False, "holonomic", "sarl", None),
+    ("mixed_sarl_c", 5, "mixed", True, False, [("test", 12, 30)], False, "holonomic", "sarl", None),
+]
+
+
+def gen_mixed_scenes(n=64):
+    """Reference reset() under sim = mixed for test cases 0..n-1 and val cases 0..15: agents per case (ragged)."""
+    env, robot, policy = refshim.make_env_and_sarl(human_num=5, sim="mixed", seed=0)
+    out = {}
+    for phase, cases in (("test", range(n)), ("val", range(16))):
+        for c in cases:
+            env.reset(phase, c)
+            a = agents_of(env)
+            out["%s_%d" % (phase, c)] = a
+            out["%s_%d_human_num" % (phase, c)] = np.array(env.human_num)
+            assert np.array_equal(a, oracle.generate_scene(phase, c, human_num=5, rule="mixed")), (phase, c)
+    np.savez_compressed(os.path.join(GOLD, "scenes_mixed.npz"), **out)
+    print("scenes_mixed.npz written;", len(out) // 2, "scenes, human counts",
+          sorted(set(int(out[k]) for k in out if k.endswith("human_num"))))
+
+
 def gen_trajectories(specs=None, weights=None):
     for spec in (specs or TRAJ_SPECS):
         name, H, sim, qenv, vis, cases = spec[:6]
@@ -268,7 +294,8 @@ def gen_trajectories(specs=None, weights=None):
             for k, v in rec.items():
                 out[key + "/" + k] = v
             # scene pin: oracle generator == reference reset
-            scene = oracle.generate_scene(phase, case, human_num=H, rule=sim, randomize=randomize)
+            scene = oracle.generate_scene(phase, case, human_num=H if pname != "cadrl" or phase == "test" else 1, rule=sim,
+                                          randomize=randomize)
             assert np.array_equal(scene, rec["agents"][0]), (name, key)
         out["cases"] = np.array(["%s_%d" % (p, c) for p, c, _ in cases])
         np.savez_compressed(os.path.join(GOLD, "traj_%s.npz" % name), **out)
@@ -321,6 +348,7 @@ if __name__ == "__main__":
     ap.add_argument("--kin-none", action="store_true", help="with --episodes: the fork's literal kinematics (None)")
     ap.add_argument("--random", action="store_true", help="only the randomize_attributes trajectories")
     ap.add_argument("--kinematics", action="store_true", help="only the kinematics = None / unicycle trajectories")
+    ap.add_argument("--mixed", action="store_true", help="only the 'mixed' scene fixtures and trajectories")
     ap.add_argument("--om", action="store_true", help="only the occupancy-map (with_om) unit vectors and trajectories")
     ap.add_argument("--nets", action="store_true", help="only the CADRL / LSTM-RL unit vectors and trajectories")
     ap.add_argument("--trained", action="store_true", help="use tests/golden/sarl_weights_trained.npy (GPU-trained SARL)")
@@ -333,6 +361,9 @@ if __name__ == "__main__":
         gen_episodes(a.procs, wtrained if a.trained else None, "kin_none_" + ("trained" if a.trained else "seed0"), None)
     elif a.episodes:
         gen_episodes(a.procs, wtrained if a.trained else None, "trained" if a.trained else "seed0")
+    elif a.mixed:
+        gen_mixed_scenes()
+        gen_trajectories(TRAJ_SPECS_MIXED)
     elif a.om:
         gen_om_units()
         gen_trajectories(TRAJ_SPECS_OM)

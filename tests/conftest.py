@@ -43,6 +43,8 @@ def load_traj(name):
     for case in z["cases"]:
         case = str(case)
         out["cases"][case] = {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith(case + "/")}
+    if out["sim"] == "mixed":            # the scene draws its own human count (crowd_sim.py:111-161); one case per fixture
+        out["H"] = int(next(iter(out["cases"].values()))["agents"].shape[1]) - 1
     return out
 
 
@@ -57,6 +59,9 @@ TRAJ_NAMES_KIN = ["circle5_kin_none", "circle5_kin_none_qtrue", "circle5_unicycl
 TRAJ_NAMES_NETS = ["cadrl_circle5", "cadrl_circle5_qtrue", "cadrl_circle1", "lstm_circle5", "lstm_circle5_qtrue",
                    "lstm2_square10"]
 
+
+# [sim] test_sim = mixed: 1, 2 and 4 humans drawn by the scene itself (the last one with query_env)
+TRAJ_NAMES_MIXED = ["mixed_sarl_a", "mixed_sarl_b", "mixed_sarl_c"]
 
 # occupancy maps (with_om = true, input_dim 61): OM-SARL and OM-LSTM-RL
 TRAJ_NAMES_OM = ["om_sarl_circle5", "om_sarl_square10_qtrue", "om_lstm_circle5"]

@@ -140,7 +140,8 @@ def test_state_dict_keys_match_reference(weights0, units):
                                   "circle5_kin_none", "circle5_kin_none_qtrue", "circle5_unicycle", "square10_unicycle_qtrue",
                                   "cadrl_circle5", "cadrl_circle5_qtrue", "cadrl_circle1", "lstm_circle5",
                                   "lstm_circle5_qtrue", "lstm2_square10",
-                                  "om_sarl_circle5", "om_sarl_square10_qtrue", "om_lstm_circle5"])
+                                  "om_sarl_circle5", "om_sarl_square10_qtrue", "om_lstm_circle5",
+                                  "mixed_sarl_a", "mixed_sarl_b", "mixed_sarl_c"])
 def test_facade_replays_reference_episode(name):
     """gym-style loop (explorer.py:53-69) through the single-env façade: ob/reward/done/info, action values and
     chosen actions equal the reference's, step by step, while the façade follows its own actions."""
@@ -151,7 +152,8 @@ def test_facade_replays_reference_episode(name):
         weights0 = np.load(os.path.join(GOLDEN, "units_om.npz"))[("om_sarl" if tr["policy"] == "sarl" else "om_lstm") + "_weights"]
     elif tr["policy"] != "sarl":                                 # CADRL / LSTM-RL: policy_factory['cadrl' | 'lstm_rl']
         weights0 = np.load(os.path.join(GOLDEN, "units_nets.npz"))[net_tag(tr) + "_weights"]
-    env, robot, policy, _ = _setup(weights0, "f32", query_env=bool(tr["query_env"]), human_num=tr["H"], sim=tr["sim"],
+    env, robot, policy, _ = _setup(weights0, "f32", query_env=bool(tr["query_env"]),
+                                   human_num=5 if tr["sim"] == "mixed" else tr["H"], sim=tr["sim"],
                                    randomize=bool(tr["randomize"]), kinematics=KIN_NAME[tr["kinematics"]],
                                    policy_name=tr["policy"], interaction_module=bool(tr["interaction_module"]),
                                    with_om=bool(tr["with_om"]))
@@ -316,3 +318,32 @@ def test_other_policies_state_dict_and_training_surface(tag, pname, im):
         order = sorted(range(len(d)), key=lambda i: d[i], reverse=True)
         plain = policy.transform(mcn.JointState(env.robot.get_full_state(), [h.get_observable_state() for h in env.humans]))
         assert torch.equal(policy.last_state, plain[order])
+
+
+def test_explorer_groups_mixed_scenes_by_human_count(weights0):
+    """[sim] mixed: run_k_episodes rolls the cases out as one batch per human count; every episode must end exactly as
+    the same case driven alone through the gym-style façade loop (explorer.py:53-69)."""
+    import modelcrowdnav_b200 as mcn
+    env, robot, policy, explorer = _setup(weights0, "f32", sim="mixed")
+    k = 12
+    explorer.run_k_episodes(k, "test")
+    run = explorer.last_run
+    assert list(run["cases"]) == list(range(k))
+    sizes = set()
+    for c in range(k):
+        ob = env.reset("test", c)
+        sizes.add(len(ob))
+        done, steps = False, 0
+        while not done:
+            ob, reward, done, info = env.step(robot.act(ob))
+            steps += 1
+        code = {mcn.ReachGoal: 2, mcn.Collision: 3, mcn.Timeout: 4}[type(info)]
+        assert (code, steps) == (int(run["info"][c]), int(run["steps"][c])), c
+    assert len(sizes) >= 3
+
+    # multiagent_training = false (CADRL): train / val scenes hold ONE circle-crossing human (crowd_sim.py:272-292)
+    z = np.load(os.path.join(GOLDEN, "units_nets.npz"))
+    env2, robot2, policy2, _ = _setup(z["cadrl_weights"], policy_name="cadrl", sim="square_crossing")
+    assert policy2.multiagent_training is False
+    assert len(env2.reset("val", 0)) == 1 and env2.train_val_sim == "circle_crossing"
+    assert len(env2.reset("test", 0)) == 5

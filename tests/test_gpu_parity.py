@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import TRAJ_NAMES, TRAJ_NAMES_KIN, TRAJ_NAMES_NETS, TRAJ_NAMES_OM, load_traj, net_tag, weights_for
+from conftest import TRAJ_NAMES, TRAJ_NAMES_KIN, TRAJ_NAMES_MIXED, TRAJ_NAMES_NETS, TRAJ_NAMES_OM, load_traj, net_tag, weights_for
 
 pytestmark = pytest.mark.gpu
 
@@ -92,7 +92,7 @@ def test_step_ladder_edge_cases(mcn, oracle_mod):
 
 
 @pytest.mark.parametrize("precision", ["f32", "f16_tc"])
-@pytest.mark.parametrize("name", TRAJ_NAMES)
+@pytest.mark.parametrize("name", TRAJ_NAMES + TRAJ_NAMES_MIXED)
 def test_golden_trajectories(mcn, oracle_mod, weights0, name, precision):
     """Teacher-forced replay of the reference's own episodes (tests/golden, scripts/gen_golden.py)."""
     tr = load_traj(name)

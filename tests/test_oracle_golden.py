@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import TRAJ_NAMES_NETS, TRAJ_NAMES_OM, net_tag, TRAJ_NAMES, TRAJ_NAMES_KIN, load_traj, weights_for
+from conftest import GOLDEN, TRAJ_NAMES_MIXED, TRAJ_NAMES_NETS, TRAJ_NAMES_OM, net_tag, TRAJ_NAMES, TRAJ_NAMES_KIN, load_traj, weights_for
 
 
 def test_action_space_matches_reference(oracle_mod, units):
@@ -46,7 +46,7 @@ def test_value_network(oracle_mod, units, weights0, H):
     assert np.max(np.abs(got - ref)) <= 1e-5 * max(1.0, np.max(np.abs(ref)))
 
 
-@pytest.mark.parametrize("name", TRAJ_NAMES + TRAJ_NAMES_KIN)
+@pytest.mark.parametrize("name", TRAJ_NAMES + TRAJ_NAMES_KIN + TRAJ_NAMES_MIXED)
 def test_trajectories(oracle_mod, weights0, name):
     """Teacher-forced, step by step: ORCA velocities, outcome ladder, state update, 81 values, argmax."""
     o = oracle_mod
@@ -234,3 +234,21 @@ def test_trajectories_with_occupancy_maps(oracle_mod, units_om, name):
                 assert best == int(rec["best"][t]), (case, t)
             n += 1
     assert n >= 15
+
+
+def test_mixed_scenes_match_reference(oracle_mod):
+    """[sim] mixed (crowd_sim.py:111-161): 80 scenes generated by the reference's reset() -- human counts 0..5, standing and
+    moving humans, the dummy human of an empty static scene -- against the oracle's and the product's host generators."""
+    import os
+    from modelcrowdnav_b200 import scenes
+    z = np.load(os.path.join(GOLDEN, "scenes_mixed.npz"))
+    counts = set()
+    for key in [k for k in z.files if not k.endswith("human_num")]:
+        phase, case = key.split("_")
+        ref = z[key]
+        assert np.array_equal(oracle_mod.generate_scene(phase, int(case), human_num=5, rule="mixed"), ref), key
+        assert np.array_equal(scenes.generate_scene(phase, int(case), human_num=5, rule="mixed"), ref), key
+        n = int(z[key + "_human_num"])
+        assert ref.shape[0] - 1 == max(n, 1)              # 0 humans -> one dummy human parked at (0, -10)
+        counts.add(n)
+    assert counts == {0, 1, 2, 3, 4, 5}
