@@ -189,6 +189,10 @@ int cn_env_read_next_obs(cn_env *env, double *obs_host, void *stream);
 /* Blocking host read of the pending action: xy as E x 2 doubles and/or the action index (E int32, -1 when the
  * action did not come from the lookahead table); either pointer may be NULL. */
 int cn_env_read_actions(cn_env *env, double *action_xy_host, int32_t *action_idx_host, void *stream);
+/* Human velocities for the next cn_env_step from the HOST (E x H x 2 doubles) instead of an ORCA solve: the hook a learned
+ * world model uses (ModelCrowdSim.step, model_crowd_sim.py:397-407,424-425: humans move with the velocities predicted by
+ * sim_world).  Valid for one step, like the cached ORCA result it replaces. */
+int cn_env_set_human_actions(cn_env *env, const double *human_vxy_host, void *stream);
 /* Set the pending action from the host: E x 2 doubles. */
 int cn_env_set_actions(cn_env *env, const double *action_xy_host, void *stream);
 /* Blocking: reduce the device accumulators (explorer.py counters).  reset != 0 clears them. */

@@ -21,7 +21,7 @@ EXPORTS = [
     "cn_last_error", "cn_version", "cn_device_count", "cn_env_cfg_default", "cn_sarl_cfg_default",
     "cn_env_create", "cn_env_destroy", "cn_env_set_state", "cn_env_get_state", "cn_env_set_theta", "cn_env_get_theta", "cn_env_reset", "cn_env_orca",
     "cn_env_robot_orca", "cn_env_step", "cn_env_get_views", "cn_env_read_outputs", "cn_env_read_human_actions",
-    "cn_env_read_next_obs", "cn_env_read_actions", "cn_env_set_actions", "cn_env_read_stats", "cn_policy_create", "cn_policy_destroy",
+    "cn_env_read_next_obs", "cn_env_read_actions", "cn_env_set_actions", "cn_env_set_human_actions", "cn_env_read_stats", "cn_policy_create", "cn_policy_destroy",
     "cn_policy_param_count", "cn_policy_load_weights", "cn_policy_action_table", "cn_policy_lookahead",
     "cn_policy_read", "cn_policy_transform", "cn_policy_last_state", "cn_policy_forward", "cn_rollout_step", "cn_rollout_step_sharded", "cn_rollout_step_host", "cn_rollout_step_host_packed", "cn_rollout_step_host_packed_async", "cn_stream_sync", "cn_host_step_bytes",
     "cn_launch_count", "cn_debug_trace", "cn_debug_trace_dump", "cn_selftest_umma", "cn_selftest_umma_bmn", "cn_selftest_umma_pair", "cn_debug_tc_timing", "cn_debug_umma_bench", "cn_debug_tmem_bench",
@@ -105,6 +105,7 @@ def load():
     L.cn_env_read_human_actions.argtypes = [vp, vp, vp]
     L.cn_env_read_next_obs.argtypes = [vp, vp, vp]
     L.cn_env_set_actions.argtypes = [vp, vp, vp]
+    L.cn_env_set_human_actions.argtypes = [vp, vp, vp]
     L.cn_env_read_actions.argtypes = [vp, vp, vp, vp]
     L.cn_env_read_stats.argtypes = [vp, C.POINTER(Stats), C.c_int, vp]
     L.cn_policy_create.argtypes = [C.POINTER(SarlCfg), C.c_int, C.POINTER(vp)]

@@ -82,6 +82,13 @@ class BatchedCrowdSim(object):
         check(self.lib.cn_env_read_human_actions(self.handle, _ptr(out), _stream(stream)))
         return out
 
+    def set_human_actions(self, human_vxy, stream=None):
+        """(E, H, 2) human velocities for the next step instead of an ORCA solve (a world model's prediction,
+        model_crowd_sim.py:397-425)."""
+        human_vxy = np.ascontiguousarray(human_vxy, dtype=np.float64)
+        assert human_vxy.shape == (self.E, self.H, 2)
+        check(self.lib.cn_env_set_human_actions(self.handle, _ptr(human_vxy), _stream(stream)))
+
     def robot_orca(self, safety_space=0.0, stream=None):
         check(self.lib.cn_env_robot_orca(self.handle, float(safety_space), _stream(stream)))
 

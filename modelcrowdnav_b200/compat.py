@@ -14,9 +14,11 @@ import types
 
 
 def make(env_id):
-    from .envs import CrowdSim
+    from .envs import CrowdSim, ModelCrowdSim
+    if env_id == "ModelCrowdSim-v0":
+        return ModelCrowdSim()
     if env_id != "CrowdSim-v0":
-        raise ValueError("only CrowdSim-v0 is provided by the B200 backend")
+        raise ValueError("only CrowdSim-v0 / ModelCrowdSim-v0 are provided by the B200 backend")
     return CrowdSim()
 
 
@@ -33,7 +35,11 @@ def install_as_reference(provide_gym=True, literal_kinematics=False):
     from . import envs, explorer, policy, trainer
     policy.LITERAL_FORK_KINEMATICS = bool(literal_kinematics)
     _module("crowd_sim")
-    _module("crowd_sim.envs", CrowdSim=envs.CrowdSim)
+    from . import world_model
+    _module("crowd_sim.envs", CrowdSim=envs.CrowdSim, ModelCrowdSim=envs.ModelCrowdSim)
+    _module("crowd_sim.envs.model_crowd_sim", ModelCrowdSim=envs.ModelCrowdSim)
+    _module("crowd_nav.policy.world_model", MlpWorld=world_model.MlpWorld, AttentionWorld=world_model.AttentionWorld,
+            SGANWorld=world_model.SGANWorld, init_weight=world_model.init_weight)
     _module("crowd_sim.envs.crowd_sim", CrowdSim=envs.CrowdSim)
     _module("crowd_sim.envs.utils")
     _module("crowd_sim.envs.utils.action", ActionXY=envs.ActionXY, ActionRot=envs.ActionRot)
@@ -68,7 +74,7 @@ def install_as_reference(provide_gym=True, literal_kinematics=False):
         orig = getattr(g, "make", None)
 
         def _make(env_id, *a, **kw):
-            if env_id == "CrowdSim-v0":
+            if env_id in ("CrowdSim-v0", "ModelCrowdSim-v0"):
                 return make(env_id)
             return orig(env_id, *a, **kw)
         g.make = _make

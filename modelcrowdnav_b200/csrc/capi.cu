@@ -21,6 +21,7 @@ void cn_set_error(const char *fmt, ...)
 
 int cn_launch_transpose_out(int E, int H, int C, const double *src, double *dst, cudaStream_t s);
 int cn_launch_set_actions(cn_env *env, const double *aos_dev, cudaStream_t s);
+int cn_launch_set_human_v(cn_env *env, const double *aos_dev, cudaStream_t s);
 int cn_launch_pack_keep(cn_env *env, cudaStream_t s);
 
 // ---- developer timeline: named CUDA events on whatever streams the work runs on -----------------
@@ -381,6 +382,15 @@ int cn_env_set_actions(cn_env *env, const double *action_xy_host, void *stream)
     const size_t E = env->p.d.E;
     CN_CUDA_CHECK(cudaMemcpyAsync(env->stage, action_xy_host, sizeof(double) * 2 * E, cudaMemcpyHostToDevice, s));
     return cn_launch_set_actions(env, env->stage, s);
+}
+
+int cn_env_set_human_actions(cn_env *env, const double *human_vxy_host, void *stream)
+{
+    CN_ENV_ENTER(env);
+    if (!human_vxy_host) { cn_set_error("human_vxy_host is null"); return CN_EINVAL; }
+    const size_t n = (size_t)env->p.d.E * env->p.d.H * 2;
+    CN_CUDA_CHECK(cudaMemcpyAsync(env->stage, human_vxy_host, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+    return cn_launch_set_human_v(env, env->stage, s);
 }
 
 int cn_env_read_stats(cn_env *env, cn_stats *out, int reset, void *stream)

@@ -497,9 +497,28 @@ __global__ void set_actions_kernel(int E, const double *__restrict__ aos, double
     action_idx[e] = -1;
 }
 
+// E x H x 2 (env-major, what a host world model produces) -> human_v[2][H][E] (the layout ORCA writes)
+__global__ void set_human_v_kernel(int E, int H, const double *__restrict__ aos, double *__restrict__ human_v)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= E * H) return;
+    const int h = i / E, e = i - h * E;
+    human_v[(size_t)(0 * H + h) * E + e] = aos[((size_t)e * H + h) * 2];
+    human_v[(size_t)(1 * H + h) * E + e] = aos[((size_t)e * H + h) * 2 + 1];
+}
+
 }  // namespace
 
 static inline int grid_for(int n, int block) { return (n + block - 1) / block; }
+
+int cn_launch_set_human_v(cn_env *env, const double *aos_dev, cudaStream_t s)
+{
+    const int n = env->p.d.E * env->p.d.H;
+    set_human_v_kernel<<<grid_for(n, 128), 128, 0, s>>>(env->p.d.E, env->p.d.H, aos_dev, env->human_v);
+    CN_LAUNCH_CHECK();
+    env->orca_valid = 1;          // the step (and a query_env lookahead) use these velocities instead of an ORCA solve
+    return CN_OK;
+}
 
 int cn_launch_orca(cn_env *env, cudaStream_t s)
 {

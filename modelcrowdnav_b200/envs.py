@@ -288,6 +288,13 @@ class CrowdSim(object):
             self._batch = BatchedCrowdSim(1, H, device=self.device, **batch_env_kwargs(self))
         return self._batch
 
+    def _ensure_human_actions(self, b):
+        """The humans' next velocities for the current state, computed once per env step: an ORCA solve here, a world-model
+        prediction in ModelCrowdSim.  Shared by step() and by a query_env lookahead (crowd_sim.py:337-342)."""
+        if self._human_v is None:
+            b.orca()
+            self._human_v = True
+
     def _sync_agents(self, agents):
         for agent, row in zip([self.robot] + self.humans, agents):
             agent._load_row(row)
@@ -343,9 +350,7 @@ class CrowdSim(object):
         holonomic = self.robot.kinematics == "holonomic"
         if not holonomic:
             b.set_theta(np.array([float(self.robot.theta)]))
-        if self._human_v is None:          # one ORCA solve per env step, shared by the 81 lookahead queries
-            b.orca()
-            self._human_v = True
+        self._ensure_human_actions(b)      # one ORCA solve per env step, shared by the 81 lookahead queries
         act = np.array([[action.vx, action.vy] if holonomic else [action.v, action.r]], dtype=np.float64)
         reward, done, info, dmin = b.step(act, update=update)
         info_obj = info_from_code(info[0], dmin[0])
@@ -372,3 +377,93 @@ class CrowdSim(object):
 
     def render(self, mode="human", output_file=None, **kw):
         raise NotImplementedError("rendering is outside the B200 hot path (SURVEY §2 #1)")
+
+
+class ModelCrowdSim(CrowdSim):
+    """Drop-in for gym.make('ModelCrowdSim-v0') (crowd_sim/envs/model_crowd_sim.py:15-441): CrowdSim whose humans move with
+    the velocities a learned world model predicts (``sim_world``: MlpWorld / AttentionWorld, any callable on a
+    (1, H * 4) tensor of px, py, vx, vy) instead of ORCA.  The world model is a torch module (it is what the fork trains);
+    collision / reward / done ladder and the state update run in the same CUDA step kernel, fed through
+    cn_env_set_human_actions.  Scenes come from the GLOBAL numpy stream (the fork never seeds, :293) and humans start
+    moving towards their goal (gen_init_v, :186-192)."""
+
+    def __init__(self):
+        super().__init__()
+        self.sim_world = None
+        self.device = None           # torch device of the world model (model_crowd_sim.py:55)
+        self._cuda_device = 0
+
+    def _ensure_batch(self):
+        dev = self.device                                  # CrowdSim uses .device as the CUDA ordinal
+        self.device = getattr(dev, "index", None) or self._cuda_device
+        try:
+            return super()._ensure_batch()
+        finally:
+            self.device = dev
+
+    def _ensure_human_actions(self, b):
+        if self._human_v is None:
+            b.set_human_actions(np.asarray(self.world_velocities(), dtype=np.float64).reshape(1, len(self.humans), 2))
+            self._human_v = True
+
+    def scene_kwargs(self, phase):
+        kw = super().scene_kwargs(phase)
+        kw.update(rs=np.random, init_velocity=True)
+        return kw
+
+    def reset(self, phase="test", test_case=None, no_random_gen=False):
+        if not no_random_gen:
+            ob = super().reset(phase, test_case)
+            if not hasattr(self.robot.policy, "get_attention_weights"):
+                self.attention_weights = None                         # model_crowd_sim.py:319-320
+            return ob
+        # model_crowd_sim.py:283-285: blank humans, to be filled by set_current_state
+        if self.robot is None:
+            raise AttributeError("robot has to be set!")
+        assert phase in ["train", "val", "test"]
+        if test_case is not None:
+            self.case_counter[phase] = test_case
+        self.global_time = 0
+        self.human_times = [0] * self.human_num
+        self.humans = [Human(self.config, "humans") for _ in range(self.human_num)]
+        self.robot.set(0, -self.circle_radius, 0, self.circle_radius, 0, 0, np.pi / 2)
+        for agent in [self.robot] + self.humans:
+            agent.time_step = self.time_step
+            agent.policy.time_step = self.time_step
+        self.states = list()
+        self.action_values = list() if hasattr(self.robot.policy, "action_values") else self.action_values
+        self.attention_weights = list() if hasattr(self.robot.policy, "get_attention_weights") else None
+        self._upload()
+        return [human.get_observable_state() for human in self.humans]
+
+    def _upload(self):
+        b = self._ensure_batch()
+        b.set_state(np.array([[a._row() for a in [self.robot] + self.humans]]), np.array([float(self.global_time)]))
+        self._human_v = None
+
+    def set_current_state(self, obs, robot_info=None, phase="train"):
+        """model_crowd_sim.py:339-345: load observed humans (position + velocity, goal at the origin) into the simulator."""
+        self.human_num = len(obs)
+        self.reset(phase, no_random_gen=True)
+        if robot_info is not None:
+            self.robot.set(robot_info.px, robot_info.py, robot_info.gx, robot_info.gy, 0, 0, np.pi / 2)
+        for i, ob in enumerate(obs):
+            self.humans[i].set(ob.px, ob.py, 0, 0, ob.vx, ob.vy, 0)
+        self._upload()
+
+    def world_velocities(self):
+        """model_crowd_sim.py:397-407: (H, 2) velocities the world model predicts for the current human states."""
+        import torch
+        current_s = [[h.px, h.py, h.vx, h.vy] for h in self.humans]
+        x = torch.Tensor([current_s]).to(self.device)
+        x = x.reshape(x.size(0), -1)
+        with torch.no_grad():
+            new_v = self.sim_world(x)[0]
+        return torch.reshape(new_v, (len(self.humans), 2)).tolist()
+
+    def step(self, action, update=True, new_v=None):
+        if new_v is not None:                      # caller-supplied velocities (model_crowd_sim.py:347,397)
+            b = self._ensure_batch()
+            b.set_human_actions(np.asarray(new_v, dtype=np.float64).reshape(1, len(self.humans), 2))
+            self._human_v = True
+        return super().step(action, update=update)

@@ -312,9 +312,7 @@ class SARL(Policy):
         if self.query_env:
             # the env façade owns the one-env batch; its ORCA result is shared with the following step()
             b = self.env._ensure_batch()
-            if self.env._human_v is None:
-                b.orca()
-                self.env._human_v = True
+            self.env._ensure_human_actions(b)
         else:
             b = self._single_env(state)
         eps = float(self.epsilon) if self.phase == "train" else 0.0

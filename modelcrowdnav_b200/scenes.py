@@ -12,6 +12,13 @@ def _norm(a, b):
     return float(np.linalg.norm((a, b)))
 
 
+def _init_v(px, py, gx, gy, v_pref):
+    """model_crowd_sim.py:186-192: goal direction scaled so that its larger component is v_pref."""
+    vx, vy = gx - px, gy - py
+    vmax = max(abs(vx), abs(vy))
+    return v_pref * vx / vmax, v_pref * vy / vmax
+
+
 # crowd_sim.py:113-115: number of humans of a 'mixed' scene, by cumulative probability over the sorted keys
 MIXED_STATIC_NUM = {0: 0.05, 1: 0.2, 2: 0.2, 3: 0.3, 4: 0.1, 5: 0.15}
 MIXED_DYNAMIC_NUM = {1: 0.3, 2: 0.3, 3: 0.2, 4: 0.1, 5: 0.1}
@@ -19,14 +26,17 @@ MIXED_DYNAMIC_NUM = {1: 0.3, 2: 0.3, 3: 0.2, 4: 0.1, 5: 0.1}
 
 def generate_scene(phase, case, human_num=5, rule="circle_crossing", circle_radius=4.0, square_width=10.0,
                    human_radius=0.3, human_v_pref=1.0, discomfort_dist=0.2, robot_radius=0.3, robot_v_pref=1.0,
-                   randomize_attributes=False):
+                   randomize_attributes=False, rs=None, init_velocity=False):
     """Agents (H+1, 8) float64 [px py vx vy gx gy radius v_pref]; agent 0 = robot (crowd_sim.py:284).
     randomize_attributes ([env] randomize_attributes): each human first draws v_pref ~ U(0.5, 1.5) and
     radius ~ U(0.3, 0.5) from the same stream (crowd_sim.py:167-168,190-191; agent.py:39-45).
     rule = 'mixed' (crowd_sim.py:111-161): the scene draws its own number of humans (the human_num argument is ignored, as
     in the reference) -- 20 % static scenes of 0-5 standing humans (goal = position; 0 humans = one dummy human parked at
     (0, -10)), else 1-5 moving humans, the first two circle-crossing, the rest square-crossing."""
-    rs = np.random.RandomState(COUNTER_OFFSET[phase] + case)
+    if rs is None:
+        rs = np.random.RandomState(COUNTER_OFFSET[phase] + case)
+    # rs given (ModelCrowdSim.reset never seeds, model_crowd_sim.py:293: pass the np.random module to draw from the global
+    # stream like the reference); init_velocity: humans start moving towards their goal (gen_init_v, model_crowd_sim.py:186-192)
     robot = [0, -circle_radius, 0, 0, 0, circle_radius, robot_radius, robot_v_pref]
     base_radius, base_v_pref = human_radius, human_v_pref
     rules = None
@@ -78,6 +88,8 @@ def generate_scene(phase, case, human_num=5, rule="circle_crossing", circle_radi
                 if not collide:
                     break
             agents[i] = [px, py, 0, 0, -px, -py, human_radius, human_v_pref]
+            if init_velocity:
+                agents[i, 2:4] = _init_v(px, py, -px, -py, human_v_pref)
         elif rule == "square_crossing":
             sign = -1 if rs.random_sample() > 0.5 else 1
             while True:
@@ -91,6 +103,8 @@ def generate_scene(phase, case, human_num=5, rule="circle_crossing", circle_radi
                 if not any(_norm(gx - a[4], gy - a[5]) < human_radius + a[6] + discomfort_dist for a in prev):
                     break
             agents[i] = [px, py, 0, 0, gx, gy, human_radius, human_v_pref]
+            if init_velocity:                  # model_crowd_sim.py:222: towards (-px, -py), not towards the square goal
+                agents[i, 2:4] = _init_v(px, py, -px, -py, human_v_pref)
         else:
             raise ValueError("Rule doesn't exist")
     return agents

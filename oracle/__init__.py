@@ -416,12 +416,23 @@ def _norm2(a, b):
 
 
 def generate_scene(phase, case, human_num=5, rule="circle_crossing", circle_radius=4.0, square_width=10.0,
-                   radius=0.3, v_pref=1.0, discomfort_dist=0.2, robot_radius=0.3, robot_v_pref=1.0, randomize=False):
+                   radius=0.3, v_pref=1.0, discomfort_dist=0.2, robot_radius=0.3, robot_v_pref=1.0, randomize=False,
+                   rs=None, init_velocity=False):
     """Agents (H+1, 8) f64 for (phase, case); agent 0 = robot at (0,-R) -> (0,R).
     randomize = [env] randomize_attributes: every human first draws v_pref ~ U(0.5, 1.5) and radius ~ U(0.3, 0.5)
     (crowd_sim.py:167-168,190-191; agent.py:39-45), one legacy-uniform draw each."""
-    rs = np.random.RandomState(COUNTER_OFFSET[phase] + case)      # crowd_sim.py:286
+    # rs / init_velocity: ModelCrowdSim.reset draws from the unseeded global stream (model_crowd_sim.py:293) and starts the
+    # humans towards (-px, -py) with the larger velocity component equal to v_pref (gen_init_v, :186-192,222)
+    if rs is None:
+        rs = np.random.RandomState(COUNTER_OFFSET[phase] + case)  # crowd_sim.py:286
     base_radius, base_v_pref = radius, v_pref
+
+    def init_v(px, py):
+        vx, vy = -px - px, -py - py
+        vmax = abs(vx)
+        if vmax < abs(vy):
+            vmax = abs(vy)
+        return v_pref * vx / vmax, v_pref * vy / vmax
     robot_row = [0, -circle_radius, 0, 0, 0, circle_radius, robot_radius, robot_v_pref]  # crowd_sim.py:284
     per_human_rule = None
     if rule == "mixed":                                            # crowd_sim.py:111-161
@@ -474,6 +485,8 @@ def generate_scene(phase, case, human_num=5, rule="circle_crossing", circle_radi
                 if not collide:
                     break
             agents[i] = [px, py, 0, 0, -px, -py, radius, v_pref]
+            if init_velocity:
+                agents[i, 2:4] = init_v(px, py)
         elif rule == "square_crossing":                            # crowd_sim.py:188-217
             sign = -1 if rs.random_sample() > 0.5 else 1
             while True:
@@ -487,6 +500,8 @@ def generate_scene(phase, case, human_num=5, rule="circle_crossing", circle_radi
                 if not any(_norm2(gx - a[4], gy - a[5]) < radius + a[6] + discomfort_dist for a in agents[:i]):
                     break
             agents[i] = [px, py, 0, 0, gx, gy, radius, v_pref]
+            if init_velocity:
+                agents[i, 2:4] = init_v(px, py)
         else:
             raise ValueError("Rule doesn't exist")
     return agents

@@ -272,6 +272,57 @@ def gen_mixed_scenes(n=64):
           sorted(set(int(out[k]) for k in out if k.endswith("human_num"))))
 
 
+def gen_model_world():
+    """ModelCrowdSim (model_crowd_sim.py) with a seed-1 AttentionWorld / MlpWorld driving the humans and the seed-0 SARL
+    driving the robot: scenes from the seeded GLOBAL numpy stream, per step the world model's velocities (passed to step()
+    through its own new_v argument so that they are on record), SARL's values, the env outcome and the next state."""
+    refshim.install()
+    import torch
+    from crowd_sim.envs.model_crowd_sim import ModelCrowdSim
+    from crowd_nav.policy.world_model import AttentionWorld, MlpWorld
+    for tag, make_world, H, sim, qenv, np_seed in (("attn_circle5", AttentionWorld, 5, "circle_crossing", False, 11),
+                                                    ("attn_square5_qtrue", AttentionWorld, 5, "square_crossing", True, 12),
+                                                    ("mlp_circle3", lambda: MlpWorld(3), 3, "circle_crossing", False, 13)):
+        _, robot, policy = refshim.make_env_and_sarl(human_num=H, sim=sim, query_env=qenv, seed=0)
+        env = ModelCrowdSim()
+        env.configure(refshim.env_config(H, sim))
+        env.set_robot(robot)
+        policy.set_env(env)
+        torch.manual_seed(1)
+        world = make_world()
+        world.eval()                                   # MlpWorld carries Dropout layers
+        env.sim_world, env.device = world, torch.device("cpu")
+        np.random.seed(np_seed)
+        ob = env.reset("test", 0)
+        rec = dict(agents=[], time=[], new_v=[], values=[], best=[], action=[], reward=[], done=[], info=[], dmin=[])
+        table, done, steps = None, False, 0
+        while not done and steps < 25:
+            rec["agents"].append(agents_of(env)); rec["time"].append(env.global_time)
+            cur = torch.Tensor([[h.get_observable_state().getvalue() for h in env.humans]])
+            with torch.no_grad():
+                new_v = torch.reshape(world(cur.reshape(1, -1))[0], (H, 2)).tolist()
+            action = robot.act(ob)
+            if table is None:
+                table = np.array([action_pair(a) for a in policy.action_space])
+            rec["values"].append(np.array(policy.action_values, dtype=np.float64))
+            ap = action_pair(action)
+            rec["best"].append(int(np.argmin(np.abs(table[:, 0] - ap[0]) + np.abs(table[:, 1] - ap[1]))))
+            rec["action"].append(ap); rec["new_v"].append(new_v)
+            ob, reward, done, info = env.step(action, new_v=new_v)
+            rec["reward"].append(reward); rec["done"].append(done); rec["info"].append(INFO_CODE[type(info).__name__])
+            rec["dmin"].append(getattr(info, "min_dist", np.inf))
+            steps += 1
+        rec["agents"].append(agents_of(env)); rec["time"].append(env.global_time)     # state after the last step
+        out = {k: np.array(v) for k, v in rec.items()}
+        sd = world.state_dict()
+        out.update(table=table, H=np.array(H), sim=np.array(sim), query_env=np.array(int(qenv)), np_seed=np.array(np_seed),
+                   world=np.array("mlp" if tag.startswith("mlp") else "attention"),
+                   world_keys=np.array(list(sd.keys())),
+                   world_weights=np.concatenate([v.numpy().ravel() for v in sd.values()]).astype(np.float32))
+        np.savez_compressed(os.path.join(GOLD, "model_world_%s.npz" % tag), **out)
+        print("model_world_%s.npz: %d steps" % (tag, steps))
+
+
 def gen_trajectories(specs=None, weights=None):
     for spec in (specs or TRAJ_SPECS):
         name, H, sim, qenv, vis, cases = spec[:6]
@@ -348,6 +399,7 @@ if __name__ == "__main__":
     ap.add_argument("--kin-none", action="store_true", help="with --episodes: the fork's literal kinematics (None)")
     ap.add_argument("--random", action="store_true", help="only the randomize_attributes trajectories")
     ap.add_argument("--kinematics", action="store_true", help="only the kinematics = None / unicycle trajectories")
+    ap.add_argument("--model-world", action="store_true", help="only the ModelCrowdSim (world-model humans) fixtures")
     ap.add_argument("--mixed", action="store_true", help="only the 'mixed' scene fixtures and trajectories")
     ap.add_argument("--om", action="store_true", help="only the occupancy-map (with_om) unit vectors and trajectories")
     ap.add_argument("--nets", action="store_true", help="only the CADRL / LSTM-RL unit vectors and trajectories")
@@ -361,6 +413,8 @@ if __name__ == "__main__":
         gen_episodes(a.procs, wtrained if a.trained else None, "kin_none_" + ("trained" if a.trained else "seed0"), None)
     elif a.episodes:
         gen_episodes(a.procs, wtrained if a.trained else None, "trained" if a.trained else "seed0")
+    elif a.model_world:
+        gen_model_world()
     elif a.mixed:
         gen_mixed_scenes()
         gen_trajectories(TRAJ_SPECS_MIXED)

@@ -63,6 +63,15 @@ TRAJ_NAMES_NETS = ["cadrl_circle5", "cadrl_circle5_qtrue", "cadrl_circle1", "lst
 # [sim] test_sim = mixed: 1, 2 and 4 humans drawn by the scene itself (the last one with query_env)
 TRAJ_NAMES_MIXED = ["mixed_sarl_a", "mixed_sarl_b", "mixed_sarl_c"]
 
+# ModelCrowdSim: humans driven by a seed-1 AttentionWorld / MlpWorld (tests/golden/model_world_*.npz)
+MODEL_WORLD_NAMES = ["attn_circle5", "attn_square5_qtrue", "mlp_circle3"]
+
+
+def load_model_world(name):
+    z = np.load(os.path.join(GOLDEN, "model_world_%s.npz" % name), allow_pickle=False)
+    return {k: (z[k] if z[k].shape else z[k].item()) for k in z.files}
+
+
 # occupancy maps (with_om = true, input_dim 61): OM-SARL and OM-LSTM-RL
 TRAJ_NAMES_OM = ["om_sarl_circle5", "om_sarl_square10_qtrue", "om_lstm_circle5"]
 

@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, load_traj, net_tag, weights_for
+from conftest import GOLDEN, MODEL_WORLD_NAMES, load_model_world, load_traj, net_tag, weights_for
 
 pytestmark = pytest.mark.gpu
 
@@ -347,3 +347,56 @@ def test_explorer_groups_mixed_scenes_by_human_count(weights0):
     assert policy2.multiagent_training is False
     assert len(env2.reset("val", 0)) == 1 and env2.train_val_sim == "circle_crossing"
     assert len(env2.reset("test", 0)) == 5
+
+
+@pytest.mark.parametrize("name", MODEL_WORLD_NAMES)
+def test_model_crowd_sim_facade_replays_reference(weights0, name):
+    """gym.make('ModelCrowdSim-v0') mirror: humans move with a world model's velocities (cn_env_set_human_actions), the robot
+    with SARL.  The reference's checkpoint layout loads unchanged; the scene comes from the seeded global numpy stream; the
+    façade's own world-model call agrees with the reference's to 1e-5, and under the recorded velocities values, outcomes
+    and states replay exactly."""
+    import torch
+    import modelcrowdnav_b200 as mcn
+    from modelcrowdnav_b200.world_model import AttentionWorld, MlpWorld
+    g = load_model_world(name)
+    H = int(g["H"])
+    _, robot, policy, _ = _setup(weights0, "f32", query_env=bool(g["query_env"]), human_num=H, sim=str(g["sim"]))
+    import modelcrowdnav_b200.compat as compat
+    env = compat.make("ModelCrowdSim-v0")
+    env.configure(_cfg(ENV_INI, sim__human_num=H, sim__train_val_sim=str(g["sim"]), sim__test_sim=str(g["sim"])))
+    env.set_robot(robot)
+    policy.set_env(env)
+    world = MlpWorld(H) if str(g["world"]) == "mlp" else AttentionWorld()
+    sd = world.state_dict()
+    assert list(sd.keys()) == [str(k) for k in g["world_keys"]]
+    off, new = 0, {}
+    for k, v in sd.items():
+        new[k] = torch.from_numpy(g["world_weights"][off:off + v.numel()].reshape(tuple(v.shape)).copy())
+        off += v.numel()
+    world.load_state_dict(new)
+    world.eval()
+    env.sim_world, env.device = world.cuda(), torch.device("cuda:0")
+    state = np.random.get_state()
+    try:
+        np.random.seed(int(g["np_seed"]))
+        ob = env.reset("test", 0)
+    finally:
+        np.random.set_state(state)
+    info_types = {0: mcn.Nothing, 1: mcn.Danger, 2: mcn.ReachGoal, 3: mcn.Collision, 4: mcn.Timeout}
+    for t in range(len(g["reward"])):
+        got = np.array([[o.px, o.py, o.vx, o.vy] for o in ob])
+        assert np.array_equal(got, g["agents"][t][1:, :4]), t
+        assert np.max(np.abs(np.array(env.world_velocities()) - g["new_v"][t])) <= 1e-5
+        if g["query_env"]:
+            env._human_v = None
+            env._ensure_batch().set_human_actions(g["new_v"][t][None])        # the lookahead sees the recorded velocities
+            env._human_v = True
+        action = robot.act(ob)
+        ref_v = g["values"][t]
+        assert np.max(np.abs(np.array(policy.action_values) - ref_v)) <= 1e-5
+        top2 = np.sort(ref_v)[-2:]
+        if top2[1] - top2[0] > 2e-5:
+            assert tuple(action) == tuple(g["action"][t])
+        ob, reward, done, info = env.step(mcn.ActionXY(*g["action"][t]), new_v=g["new_v"][t])
+        assert reward == g["reward"][t] and done == bool(g["done"][t]) and isinstance(info, info_types[int(g["info"][t])])
+        assert env.global_time == g["time"][t + 1]

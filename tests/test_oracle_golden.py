@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, TRAJ_NAMES_MIXED, TRAJ_NAMES_NETS, TRAJ_NAMES_OM, net_tag, TRAJ_NAMES, TRAJ_NAMES_KIN, load_traj, weights_for
+from conftest import GOLDEN, MODEL_WORLD_NAMES, load_model_world, TRAJ_NAMES_MIXED, TRAJ_NAMES_NETS, TRAJ_NAMES_OM, net_tag, TRAJ_NAMES, TRAJ_NAMES_KIN, load_traj, weights_for
 
 
 def test_action_space_matches_reference(oracle_mod, units):
@@ -252,3 +252,37 @@ def test_mixed_scenes_match_reference(oracle_mod):
         assert ref.shape[0] - 1 == max(n, 1)              # 0 humans -> one dummy human parked at (0, -10)
         counts.add(n)
     assert counts == {0, 1, 2, 3, 4, 5}
+
+
+@pytest.mark.parametrize("name", MODEL_WORLD_NAMES)
+def test_model_crowd_sim_fixtures(oracle_mod, weights0, name):
+    """ModelCrowdSim (model_crowd_sim.py:268-441) run by the reference with world-model humans: the scene from the seeded
+    GLOBAL numpy stream with initial velocities, then per step SARL's values, the outcome ladder and the state update under
+    the recorded world-model velocities -- oracle (and the product's host scene generator) against the fixture."""
+    from modelcrowdnav_b200 import scenes
+    o = oracle_mod
+    g = load_model_world(name)
+    H, rule = int(g["H"]), str(g["sim"])
+    state = np.random.get_state()
+    try:
+        np.random.seed(int(g["np_seed"]))
+        a0 = o.generate_scene("test", 0, human_num=H, rule=rule, rs=np.random, init_velocity=True)
+        np.random.seed(int(g["np_seed"]))
+        a1 = scenes.generate_scene("test", 0, human_num=H, rule=rule, rs=np.random, init_velocity=True)
+    finally:
+        np.random.set_state(state)
+    assert np.array_equal(a0, g["agents"][0]) and np.array_equal(a1, g["agents"][0])
+    assert np.all(np.max(np.abs(a0[1:, 2:4]), axis=1) == 1.0)          # gen_init_v: larger component = v_pref
+    ecfg, scfg = o.EnvCfg.default(), o.SarlCfg.default()
+    table = g["table"]
+    for t in range(len(g["reward"])):
+        agents = np.ascontiguousarray(g["agents"][t])
+        gt, hv = float(g["time"][t]), np.ascontiguousarray(g["new_v"][t])
+        best, values, reached = o.lookahead(ecfg, scfg, weights0, agents, gt, table, int(g["query_env"]), hv)
+        ref_v = g["values"][t]
+        assert np.max(np.abs(values - ref_v)) <= 1e-5 * max(1.0, np.max(np.abs(ref_v))), t
+        a = g["action"][t]
+        r, done, info, dmin = o.step_outcome(ecfg, agents, gt, a)
+        assert (r, done, info) == (g["reward"][t], bool(g["done"][t]), int(g["info"][t])), t
+        nt = o.apply_step(ecfg, agents, gt, a, hv)
+        assert nt == g["time"][t + 1] and np.array_equal(agents, g["agents"][t + 1]), t
