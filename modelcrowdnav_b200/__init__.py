@@ -11,10 +11,10 @@ from .batch import (BatchedCrowdSim, BatchedSARL, HostStepBuffers, PackedHostSte
 
 from .envs import (ActionRot, ActionXY, Collision, CrowdSim, Danger, FullState, Human, JointState, ModelCrowdSim,  # noqa: F401
                    Nothing, ObservableState, ReachGoal, Robot, Timeout)
-from .policy import CADRL, ORCA, SARL, LstmRL, policy_factory  # noqa: F401
+from .policy import CADRL, ORCA, SARL, Linear, LstmRL, policy_factory  # noqa: F401
 from .explorer import Explorer, ReplayMemory  # noqa: F401
 
-__all__ = ["CrowdSim", "ModelCrowdSim", "Robot", "Human", "SARL", "CADRL", "LstmRL", "ORCA", "policy_factory", "Explorer", "ReplayMemory",
+__all__ = ["CrowdSim", "ModelCrowdSim", "Robot", "Human", "SARL", "CADRL", "LstmRL", "Linear", "ORCA", "policy_factory", "Explorer", "ReplayMemory",
            "ActionXY", "ActionRot", "FullState", "ObservableState", "JointState",
            "Timeout", "ReachGoal", "Danger", "Collision", "Nothing",
            "BatchedCrowdSim", "BatchedSARL", "HostStepBuffers", "PackedHostStepBuffers", "rollout_step", "rollout_step_host",

@@ -53,6 +53,7 @@ def install_as_reference(provide_gym=True, literal_kinematics=False):
     _module("crowd_sim.envs.policy")
     _module("crowd_sim.envs.policy.policy", Policy=policy.Policy)
     _module("crowd_sim.envs.policy.orca", ORCA=policy.ORCA)
+    _module("crowd_sim.envs.policy.linear", Linear=policy.Linear)
     _module("crowd_sim.envs.policy.policy_factory", policy_factory=policy.policy_factory)
     _module("crowd_nav")
     _module("crowd_nav.policy")

@@ -487,6 +487,11 @@ tc_rows_pair_kernel(EnvParams p,
                 }
             }
             QPROBE(ctx, 15);
+            // Every TMEM read of [0,168) of this tile is done (Ha1 was consumed by the stage-4 UMMA, the attention.2 accumulator
+            // by the loads above); F at [168,232) is still live but stage 0 only writes [0,160): request the next tile's stage 0
+            // NOW, so that its UMMA runs under the softmax / w * F / group sums below.  (Stage 1 writes [120,232) and is only
+            // requested after the next E0, i.e. after every warp has finished this tile.)
+            if (has_next) PAIR_SIGNAL();
             ctx_barrier(ctx);
             QPROBE(ctx, 16);
             float w = 0.0f;
@@ -529,9 +534,7 @@ tc_rows_pair_kernel(EnvParams p,
             fence_before_sync();
             ctx_barrier(ctx);
             QPROBE(ctx, 10);
-            // every TMEM read of this tile is done: request stage 0 of the next tile now, the group sums below overlap it.
             // (R2 is next written by the next tile's E1, which needs every warp's stage-1 request, issued after its sums.)
-            if (has_next) PAIR_SIGNAL();
             // ---- weighted feature of the group (sarl.py:57-60): sum over its humans -> J chunks 0..6 ----
 #pragma unroll
             for (int si = 0; si < kSumIters; ++si) {

@@ -17,7 +17,7 @@ import numpy as np
 from . import _capi, scenes
 from .batch import BatchedCrowdSim
 from .envs import batch_env_kwargs
-from .policy import CADRL, ORCA, SARL
+from .policy import CADRL, ORCA, SARL, Linear
 
 
 class ReplayMemory(object):
@@ -178,7 +178,7 @@ class Explorer(object):
                 raise AttributeError("Epsilon attribute has to be set in training phase")
             handle = policy.handle(v_pref)
             eps = float(policy.epsilon) if phase == "train" else 0.0
-        elif not isinstance(policy, ORCA) and not stay:
+        elif not isinstance(policy, (ORCA, Linear)) and not stay:
             raise NotImplementedError("robot policy %r is not on the B200 hot path" % type(policy).__name__)
         tr_policy = self.target_policy if (imitation_learning and self.target_policy is not None) else policy
 
@@ -212,6 +212,8 @@ class Explorer(object):
                     if e.code == _capi.CN_EVALUE:
                         raise ValueError("Value network is not well trained. ")
                     raise
+            elif isinstance(policy, Linear):
+                b.set_actions(Linear.batch_actions(b.get_state()[0]))
             else:
                 b.robot_orca(policy.safety_space)
             reward, done, info, dmin = b.step(update=True)

@@ -109,6 +109,33 @@ class ORCA(Policy):
         return ActionXY(float(xy[0, 0]), float(xy[0, 1]))
 
 
+class Linear(Policy):
+    """Straight-to-goal policy (crowd_sim/envs/policy/linear.py:6-24): host arithmetic, numpy like the reference."""
+
+    def __init__(self):
+        super().__init__()
+        self.name = "Linear"
+        self.trainable = False
+        self.kinematics = "holonomic"
+        self.multiagent_training = True
+
+    def configure(self, config):
+        assert True
+
+    def predict(self, state):
+        from .envs import ActionXY
+        self_state = state.self_state
+        theta = np.arctan2(self_state.gy - self_state.py, self_state.gx - self_state.px)
+        return ActionXY(np.cos(theta) * self_state.v_pref, np.sin(theta) * self_state.v_pref)
+
+    @staticmethod
+    def batch_actions(agents):
+        """predict() for the robots of a batch: agents (E, H+1, 8) -> (E, 2)."""
+        r = agents[:, 0]
+        theta = np.arctan2(r[:, 5] - r[:, 1], r[:, 4] - r[:, 0])
+        return np.stack([np.cos(theta) * r[:, 7], np.sin(theta) * r[:, 7]], axis=1)
+
+
 def mlp(input_dim, mlp_dims, last_relu=False):
     """cadrl.py:11-19"""
     import torch.nn as nn
@@ -480,4 +507,4 @@ def _none():
 
 
 # crowd_nav/policy/policy_factory.py + crowd_sim/envs/policy/policy_factory.py (hot-path policies only)
-policy_factory = {"orca": ORCA, "none": _none, "sarl": SARL, "cadrl": CADRL, "lstm_rl": LstmRL}
+policy_factory = {"linear": Linear, "orca": ORCA, "none": _none, "sarl": SARL, "cadrl": CADRL, "lstm_rl": LstmRL}

@@ -400,3 +400,27 @@ def test_model_crowd_sim_facade_replays_reference(weights0, name):
         ob, reward, done, info = env.step(mcn.ActionXY(*g["action"][t]), new_v=g["new_v"][t])
         assert reward == g["reward"][t] and done == bool(g["done"][t]) and isinstance(info, info_types[int(g["info"][t])])
         assert env.global_time == g["time"][t + 1]
+
+
+def test_linear_robot_policy(weights0):
+    """policy_factory['linear'] (crowd_sim/envs/policy/linear.py): a robot heading straight for its goal at v_pref, both
+    through the gym-style loop and through the batched Explorer; the two must end every episode identically."""
+    import modelcrowdnav_b200 as mcn
+    env, robot, policy, _ = _setup(weights0)
+    lin = mcn.policy_factory["linear"]()
+    lin.configure(None)
+    robot.set_policy(lin)
+    import torch
+    explorer = mcn.Explorer(env, robot, torch.device("cuda:0"), gamma=0.9)
+    explorer.run_k_episodes(8, "test")
+    run = explorer.last_run
+    for c in range(8):
+        ob = env.reset("test", c)
+        done, steps = False, 0
+        while not done:
+            action = robot.act(ob)
+            assert abs(np.hypot(action.vx, action.vy) - 1.0) < 1e-12
+            ob, reward, done, info = env.step(action)
+            steps += 1
+        code = {mcn.ReachGoal: 2, mcn.Collision: 3, mcn.Timeout: 4}[type(info)]
+        assert (code, steps) == (int(run["info"][c]), int(run["steps"][c])), c

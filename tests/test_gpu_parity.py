@@ -674,3 +674,37 @@ def test_golden_trajectories_with_occupancy_maps(mcn, units_om, name):
         assert (reward[e], bool(done[e]), int(info[e])) == (rec["reward"][t], bool(rec["done"][t]), int(rec["info"][t]))
     assert total > 0 and agree / total >= 0.999, (agree, total)
     env.close(); pol.close()
+
+
+def test_rollout_step_is_cuda_graph_capturable(mcn, weights0):
+    """include/crowdnav_b200.h promises a capturable step: cn_rollout_step (ORCA forked on a side stream, lookahead, step,
+    auto-reset) captured once into a CUDA graph and replayed must walk the same trajectory as eager launches."""
+    import torch
+    E, H = 512, 5
+    envs = [mcn.BatchedCrowdSim(E, H, auto_reset=1, seed=9) for _ in range(2)]
+    pols = [mcn.BatchedSARL(precision="f16_tc") for _ in range(2)]
+    for p in pols:
+        p.load_weights(weights0)
+    for e in envs:
+        e.reset_device()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(3):                                    # warm-up: allocates the workspaces outside the capture
+            mcn.rollout_step(pols[1], envs[1], stream=side.cuda_stream)
+    side.synchronize()
+    for _ in range(3):
+        mcn.rollout_step(pols[0], envs[0])
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        mcn.rollout_step(pols[1], envs[1], stream=torch.cuda.current_stream().cuda_stream)
+    mcn.rollout_step(pols[0], envs[0])                        # the captured launch did not execute: replay it once below
+    for _ in range(40):
+        graph.replay()
+    torch.cuda.synchronize()
+    for _ in range(39):
+        mcn.rollout_step(pols[0], envs[0])
+    a0, t0 = envs[0].get_state()
+    a1, t1 = envs[1].get_state()
+    assert np.array_equal(a0, a1) and np.array_equal(t0, t1)
+    for x in envs + pols:
+        x.close()
