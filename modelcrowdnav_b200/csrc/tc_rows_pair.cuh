@@ -382,6 +382,14 @@ tc_rows_pair_kernel(EnvParams p,
             mean_off[i] = (it < G * (N_M1 / 8)) ? (int)chunk_off(ROWS, gl * H, c) : -1;
         }
         constexpr int kSumIters = HT ? 1 : 2;       // at most 448 sum items / 256 threads
+        // Run-time H with FEW, LARGE groups (H = 50: 2 groups of 50 rows): one thread per (group, chunk) item would leave 28
+        // threads walking 50 rows each (measured: 5.5 k cycles for the mean, 3.3 k for the sums, of a 20 k cycle tile).  The
+        // rows of a group are then split into P segments so that all 256 threads of the context work: partial sums into a
+        // scratch area, a context barrier, and one finishing thread per item (plus, for the mean, a parallel broadcast).
+        const int mean_split = HT ? 1 : 256 / (G * (N_M1 / 8));     // P >= 2 <=> G <= 9  <=> H >= 13
+        const int sum_split = HT ? 1 : 256 / (G * 7);               // P >= 2 <=> G <= 18 <=> H >= 8
+        uint8_t *mean_scratch = R1 + Q_X_OFF + X_TILE_BYTES;        // the 4 KB of R1 behind the X slot: 256 x 16 B
+        static_assert(Q_X_OFF + X_TILE_BYTES + 256 * 16 <= Q_R1_BYTES, "mean scratch must fit behind the X slot");
         // operand hand-over: generic-proxy writes -> async proxy, TMEM reads ordered, one arrival per warp
 #define PAIR_SIGNAL_TO(bar) do { fence_async_smem(); fence_before_sync(); __syncwarp(); if (lane == 0) mbar_arrive_cluster(bar); } while (0)
 #define PAIR_SIGNAL() PAIR_SIGNAL_TO(req_leader)
@@ -408,6 +416,46 @@ tc_rows_pair_kernel(EnvParams p,
             // ---- group mean of mlp1_out over the humans of a group (sarl.py:42), replicated on the group's rows -> R1 ----
             ctx_barrier(ctx);
             QPROBE(ctx, 13);
+            if (!HT && mean_split >= 2) {
+                const int P = mean_split, nitems = G * (N_M1 / 8);
+                const int it = t256 / P, seg = t256 - it * P;
+                const int seglen = (H + P - 1) / P;
+                if (it < nitems) {                                   // (a) partial sum of rows [h0, h1) of item (group gl, chunk c)
+                    const int c = it / G, gl = it - c * G;
+                    const int h0 = seg * seglen, h1 = min(H, h0 + seglen);
+                    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    for (int h = h0; h < h1; ++h) {
+                        const uint4 u = *reinterpret_cast<const uint4 *>(R2 + chunk_off(ROWS, gl * H + h, c));
+                        const __half2 *hv = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(hv[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+                    }
+                    *reinterpret_cast<uint4 *>(mean_scratch + (size_t)t256 * 16) =
+                        make_uint4(h2(acc[0], acc[1]), h2(acc[2], acc[3]), h2(acc[4], acc[5]), h2(acc[6], acc[7]));
+                }
+                ctx_barrier(ctx);
+                if (it < nitems && seg == 0) {                       // (b) one thread per item: P partials -> mean
+                    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    for (int sgi = 0; sgi < P; ++sgi) {
+                        if (sgi * seglen >= H) break;
+                        const uint4 u = *reinterpret_cast<const uint4 *>(mean_scratch + (size_t)(t256 + sgi) * 16);
+                        const __half2 *hv = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(hv[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+                    }
+                    *reinterpret_cast<uint4 *>(mean_scratch + (size_t)t256 * 16) =
+                        make_uint4(h2(acc[0] * invH, acc[1] * invH), h2(acc[2] * invH, acc[3] * invH),
+                                   h2(acc[4] * invH, acc[5] * invH), h2(acc[6] * invH, acc[7] * invH));
+                }
+                ctx_barrier(ctx);
+                for (int idx = t256; idx < ROWS * (N_M1 / 8); idx += 256) {   // (c) replicate on the group's rows, all threads
+                    const int c = idx / ROWS, r = idx - c * ROWS;
+                    if (r >= rows) continue;
+                    const int gl = r / H;
+                    *reinterpret_cast<uint4 *>(R1 + chunk_off(ROWS, r, c)) =
+                        *reinterpret_cast<const uint4 *>(mean_scratch + (size_t)((c * G + gl) * P) * 16);
+                }
+            } else
 #pragma unroll
             for (int i = 0; i < kMeanIters; ++i) {
                 if (mean_off[i] < 0) continue;
@@ -495,7 +543,24 @@ tc_rows_pair_kernel(EnvParams p,
             ctx_barrier(ctx);
             QPROBE(ctx, 16);
             float w = 0.0f;
-            if (row_valid) {
+            if (!HT && H >= 8) {
+                // large groups: one exp per row instead of H per row -- every thread exponentiates its own row's score into SE
+                // (both column-half threads of a row write the same value), then sums its group's H entries
+                float *SE = reinterpret_cast<float *>(mean_scratch);              // 128 floats of the (idle) mean scratch
+                float mine = 0.0f;
+                if (row_valid) {
+                    const float sc = S0[row] + S1[row] + tw.w[100];
+                    mine = __expf(sc) * (sc != 0.0f ? 1.0f : 0.0f);
+                    SE[row] = mine;
+                }
+                ctx_barrier(ctx);
+                if (row_valid) {
+                    float ssum = 0.0f;
+                    const int r0 = my_gl * H;
+                    for (int h = 0; h < H; ++h) ssum += SE[r0 + h];
+                    w = mine / ssum;
+                }
+            } else if (row_valid) {
                 float ssum = 0.0f, mine = 0.0f;
                 const int r0 = my_gl * H;
                 if (HT) {
@@ -536,6 +601,41 @@ tc_rows_pair_kernel(EnvParams p,
             QPROBE(ctx, 10);
             // (R2 is next written by the next tile's E1, which needs every warp's stage-1 request, issued after its sums.)
             // ---- weighted feature of the group (sarl.py:57-60): sum over its humans -> J chunks 0..6 ----
+            if (!HT && sum_split >= 2) {
+                const int P = sum_split, nitems = G * 7;
+                const int it = t256 / P, seg = t256 - it * P;
+                const int seglen = (H + P - 1) / P;
+                float *part = reinterpret_cast<float *>(R1);          // R1[0, 8 KB): H3 is dead once stage 4 has completed
+                const int sum_c = it / G, sum_gl = it - sum_c * G;
+                if (it < nitems) {
+                    const int h0 = seg * seglen, h1 = min(H, h0 + seglen);
+                    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    for (int h = h0; h < h1; ++h) {
+                        const uint4 u = *reinterpret_cast<const uint4 *>(R2 + chunk_off(ROWS, sum_gl * H + h, sum_c));
+                        const __half2 *hv = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(hv[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+                    }
+                    *reinterpret_cast<float4 *>(part + (size_t)t256 * 8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                    *reinterpret_cast<float4 *>(part + (size_t)t256 * 8 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                }
+                ctx_barrier(ctx);
+                const long long gg = (long long)tile * G + sum_gl;
+                if (it < nitems && seg == 0 && gg < NG) {
+                    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    for (int sgi = 0; sgi < P; ++sgi) {
+                        if (sgi * seglen >= H) break;
+                        const float4 a = *reinterpret_cast<const float4 *>(part + (size_t)(t256 + sgi) * 8);
+                        const float4 b = *reinterpret_cast<const float4 *>(part + (size_t)(t256 + sgi) * 8 + 4);
+                        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+                        acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+                    }
+                    uint8_t *jt = J + (size_t)(gg >> 7) * J_TILE_BYTES;
+                    *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, (uint32_t)(gg & 127), sum_c)) =
+                        make_uint4(h2(acc[0], acc[1]), h2(acc[2], acc[3]), h2(acc[4], acc[5]), h2(acc[6], acc[7]));
+                }
+                ctx_barrier(ctx);          // the partials are consumed before anything else reuses R1
+            } else
 #pragma unroll
             for (int si = 0; si < kSumIters; ++si) {
                 const int it = t256 + si * 256;

@@ -708,3 +708,30 @@ def test_rollout_step_is_cuda_graph_capturable(mcn, weights0):
     assert np.array_equal(a0, a1) and np.array_equal(t0, t1)
     for x in envs + pols:
         x.close()
+
+
+@pytest.mark.parametrize("H", [13, 50])
+def test_tc_large_groups_vs_oracle(mcn, oracle_mod, weights0, H):
+    """Run-time-H path of the CTA-pair kernel with few, large groups (H = 50: BASELINE's dense-crowd configuration, 2 groups
+    of 50 rows per tile; H = 13: 9 groups): split group mean, single-exp softmax and split weighted-feature sums against
+    the oracle and the FP32 path."""
+    o = oracle_mod
+    E = 6
+    ecfg, scfg = o.EnvCfg.default(), o.SarlCfg.default()
+    env = mcn.BatchedCrowdSim(E, H, square_width=14.0)
+    p16 = mcn.BatchedSARL(precision="f16_tc"); p16.load_weights(weights0)
+    p32 = mcn.BatchedSARL(precision="f32"); p32.load_weights(weights0)
+    agents = np.stack([o.generate_scene("val", c, human_num=H, rule="square_crossing", square_width=14.0) for c in range(E)])
+    env.set_state(agents)
+    for step in range(2):
+        env.orca()
+        hv = env.human_actions()
+        p32.lookahead(env, 0); b32, v32 = p32.read(env)
+        p16.lookahead(env, 0); b16, v16 = p16.read(env)
+        cur, times = env.get_state()
+        for e in range(E):
+            obest, ovals, _ = o.lookahead(ecfg, scfg, weights0, cur[e], times[e], p16.action_table, False, hv[e])
+            assert np.max(np.abs(v32[e] - ovals)) <= 1e-5 * max(1.0, np.max(np.abs(ovals)))
+            assert np.max(np.abs(v16[e] - ovals)) <= 1e-3 * max(1.0, np.max(np.abs(ovals)))
+        env.step(update=True, read=False)
+    env.close(); p16.close(); p32.close()
