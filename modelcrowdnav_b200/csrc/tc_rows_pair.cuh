@@ -232,6 +232,24 @@ tc_features_kernel(EnvParams p, const double *__restrict__ st, const double *__r
     if (lead) rew[g] = pair_reward(p, in, D + r, H, query_env);
 }
 
+// acc[8] += sum over n 16-byte chunks of 8 fp16 at base + i * stride.  Loads go out four at a time before anything is added:
+// under a streaming UMMA one ld.shared round trip costs ~150-250 cycles (measured), so dependent one-at-a-time loops crawl.
+__device__ __forceinline__ void sum_f16x8_rows(const uint8_t *base, int n, uint32_t stride, float (&acc)[8])
+{
+    for (int i0 = 0; i0 < n; i0 += 4) {
+        uint4 u[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            u[j] = (i0 + j < n) ? *reinterpret_cast<const uint4 *>(base + (size_t)(i0 + j) * stride) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __half2 *hv = reinterpret_cast<const __half2 *>(&u[j]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(hv[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+        }
+    }
+}
+
 __device__ __forceinline__ void ctx_barrier(int ctx)
 {
     if (ctx == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -384,12 +402,14 @@ tc_rows_pair_kernel(EnvParams p,
         constexpr int kSumIters = HT ? 1 : 2;       // at most 448 sum items / 256 threads
         // Run-time H with FEW, LARGE groups (H = 50: 2 groups of 50 rows): one thread per (group, chunk) item would leave 28
         // threads walking 50 rows each (measured: 5.5 k cycles for the mean, 3.3 k for the sums, of a 20 k cycle tile).  The
-        // rows of a group are then split into P segments so that all 256 threads of the context work: partial sums into a
-        // scratch area, a context barrier, and one finishing thread per item (plus, for the mean, a parallel broadcast).
-        const int mean_split = HT ? 1 : 256 / (G * (N_M1 / 8));     // P >= 2 <=> G <= 9  <=> H >= 13
-        const int sum_split = HT ? 1 : 256 / (G * 7);               // P >= 2 <=> G <= 18 <=> H >= 8
-        uint8_t *mean_scratch = R1 + Q_X_OFF + X_TILE_BYTES;        // the 4 KB of R1 behind the X slot: 256 x 16 B
-        static_assert(Q_X_OFF + X_TILE_BYTES + 256 * 16 <= Q_R1_BYTES, "mean scratch must fit behind the X slot");
+        // rows of a group are then split over P threads per item so that (nearly) all 256 threads of the context work.
+        // P = a power of two, so that the P threads of an item are adjacent lanes of one warp: they take the rows h = seg,
+        // seg + P, ... (adjacent lanes -> adjacent 16-byte rows: conflict-free) and combine their partial sums by shuffles.
+        auto pow2_floor = [](int x) { int p = 1; while (2 * p <= x && p < 16) p *= 2; return p; };
+        const int mean_split = HT ? 1 : pow2_floor(256 / (G * (N_M1 / 8)));   // 8 for G = 2 (H = 50), >= 2 <=> G <= 9 <=> H >= 13
+        const int sum_split = HT ? 1 : pow2_floor(256 / (G * 7));             // 16 for G = 2, >= 2 <=> G <= 18 <=> H >= 8
+        uint8_t *mean_scratch = R1 + Q_X_OFF + X_TILE_BYTES;        // the 4 KB of R1 behind the X slot (softmax scratch)
+        static_assert(Q_X_OFF + X_TILE_BYTES + 2 * ROWS * 4 <= Q_R1_BYTES, "softmax scratch must fit behind the X slot");
         // operand hand-over: generic-proxy writes -> async proxy, TMEM reads ordered, one arrival per warp
 #define PAIR_SIGNAL_TO(bar) do { fence_async_smem(); fence_before_sync(); __syncwarp(); if (lane == 0) mbar_arrive_cluster(bar); } while (0)
 #define PAIR_SIGNAL() PAIR_SIGNAL_TO(req_leader)
@@ -418,43 +438,19 @@ tc_rows_pair_kernel(EnvParams p,
             QPROBE(ctx, 13);
             if (!HT && mean_split >= 2) {
                 const int P = mean_split, nitems = G * (N_M1 / 8);
-                const int it = t256 / P, seg = t256 - it * P;
-                const int seglen = (H + P - 1) / P;
-                if (it < nitems) {                                   // (a) partial sum of rows [h0, h1) of item (group gl, chunk c)
-                    const int c = it / G, gl = it - c * G;
-                    const int h0 = seg * seglen, h1 = min(H, h0 + seglen);
-                    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                    for (int h = h0; h < h1; ++h) {
-                        const uint4 u = *reinterpret_cast<const uint4 *>(R2 + chunk_off(ROWS, gl * H + h, c));
-                        const __half2 *hv = reinterpret_cast<const __half2 *>(&u);
+                const int it = t256 / P, seg = t256 & (P - 1);
+                const bool on = it < nitems;
+                const int c = on ? it / G : 0, gl = on ? it - c * G : 0;
+                const int n = on ? (H - seg + P - 1) / P : 0;                    // rows seg, seg + P, ... of the group
+                float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                sum_f16x8_rows(R2 + chunk_off(ROWS, gl * H + seg, c), n, 16u * P, acc);
+                for (int off = 1; off < P; off <<= 1)                                // whole warps take part (it may be off)
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(hv[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
-                    }
-                    *reinterpret_cast<uint4 *>(mean_scratch + (size_t)t256 * 16) =
-                        make_uint4(h2(acc[0], acc[1]), h2(acc[2], acc[3]), h2(acc[4], acc[5]), h2(acc[6], acc[7]));
-                }
-                ctx_barrier(ctx);
-                if (it < nitems && seg == 0) {                       // (b) one thread per item: P partials -> mean
-                    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                    for (int sgi = 0; sgi < P; ++sgi) {
-                        if (sgi * seglen >= H) break;
-                        const uint4 u = *reinterpret_cast<const uint4 *>(mean_scratch + (size_t)(t256 + sgi) * 16);
-                        const __half2 *hv = reinterpret_cast<const __half2 *>(&u);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(hv[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
-                    }
-                    *reinterpret_cast<uint4 *>(mean_scratch + (size_t)t256 * 16) =
-                        make_uint4(h2(acc[0] * invH, acc[1] * invH), h2(acc[2] * invH, acc[3] * invH),
-                                   h2(acc[4] * invH, acc[5] * invH), h2(acc[6] * invH, acc[7] * invH));
-                }
-                ctx_barrier(ctx);
-                for (int idx = t256; idx < ROWS * (N_M1 / 8); idx += 256) {   // (c) replicate on the group's rows, all threads
-                    const int c = idx / ROWS, r = idx - c * ROWS;
-                    if (r >= rows) continue;
-                    const int gl = r / H;
-                    *reinterpret_cast<uint4 *>(R1 + chunk_off(ROWS, r, c)) =
-                        *reinterpret_cast<const uint4 *>(mean_scratch + (size_t)((c * G + gl) * P) * 16);
-                }
+                    for (int k = 0; k < 8; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+                const uint4 o = make_uint4(h2(acc[0] * invH, acc[1] * invH), h2(acc[2] * invH, acc[3] * invH),
+                                           h2(acc[4] * invH, acc[5] * invH), h2(acc[6] * invH, acc[7] * invH));
+                for (int h = seg; h < H && on; h += P)                               // replicate on the same rows
+                    *reinterpret_cast<uint4 *>(R1 + chunk_off(ROWS, gl * H + h, c)) = o;
             } else
 #pragma unroll
             for (int i = 0; i < kMeanIters; ++i) {
@@ -554,10 +550,18 @@ tc_rows_pair_kernel(EnvParams p,
                     SE[row] = mine;
                 }
                 ctx_barrier(ctx);
+                float *SP = SE + ROWS;                                            // partial sums of 8 consecutive rows of a group
+                if (row_valid && (my_h & 7) == 0) {
+                    float p8 = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) p8 += (my_h + k < H) ? SE[row + k] : 0.0f;
+                    SP[row] = p8;
+                }
+                ctx_barrier(ctx);
                 if (row_valid) {
                     float ssum = 0.0f;
                     const int r0 = my_gl * H;
-                    for (int h = 0; h < H; ++h) ssum += SE[r0 + h];
+                    for (int h = 0; h < H; h += 8) ssum += SP[r0 + h];
                     w = mine / ssum;
                 }
             } else if (row_valid) {
@@ -603,38 +607,21 @@ tc_rows_pair_kernel(EnvParams p,
             // ---- weighted feature of the group (sarl.py:57-60): sum over its humans -> J chunks 0..6 ----
             if (!HT && sum_split >= 2) {
                 const int P = sum_split, nitems = G * 7;
-                const int it = t256 / P, seg = t256 - it * P;
-                const int seglen = (H + P - 1) / P;
-                float *part = reinterpret_cast<float *>(R1);          // R1[0, 8 KB): H3 is dead once stage 4 has completed
-                const int sum_c = it / G, sum_gl = it - sum_c * G;
-                if (it < nitems) {
-                    const int h0 = seg * seglen, h1 = min(H, h0 + seglen);
-                    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                    for (int h = h0; h < h1; ++h) {
-                        const uint4 u = *reinterpret_cast<const uint4 *>(R2 + chunk_off(ROWS, sum_gl * H + h, sum_c));
-                        const __half2 *hv = reinterpret_cast<const __half2 *>(&u);
+                const int it = t256 / P, seg = t256 & (P - 1);
+                const bool on = it < nitems;
+                const int sum_c = on ? it / G : 0, sum_gl = on ? it - sum_c * G : 0;
+                const int n = on ? (H - seg + P - 1) / P : 0;
+                float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                sum_f16x8_rows(R2 + chunk_off(ROWS, sum_gl * H + seg, sum_c), n, 16u * P, acc);
+                for (int off = 1; off < P; off <<= 1)
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(hv[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
-                    }
-                    *reinterpret_cast<float4 *>(part + (size_t)t256 * 8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                    *reinterpret_cast<float4 *>(part + (size_t)t256 * 8 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-                }
-                ctx_barrier(ctx);
+                    for (int k = 0; k < 8; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
                 const long long gg = (long long)tile * G + sum_gl;
-                if (it < nitems && seg == 0 && gg < NG) {
-                    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                    for (int sgi = 0; sgi < P; ++sgi) {
-                        if (sgi * seglen >= H) break;
-                        const float4 a = *reinterpret_cast<const float4 *>(part + (size_t)(t256 + sgi) * 8);
-                        const float4 b = *reinterpret_cast<const float4 *>(part + (size_t)(t256 + sgi) * 8 + 4);
-                        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-                        acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
-                    }
+                if (on && seg == 0 && gg < NG) {
                     uint8_t *jt = J + (size_t)(gg >> 7) * J_TILE_BYTES;
                     *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, (uint32_t)(gg & 127), sum_c)) =
                         make_uint4(h2(acc[0], acc[1]), h2(acc[2], acc[3]), h2(acc[4], acc[5]), h2(acc[6], acc[7]));
                 }
-                ctx_barrier(ctx);          // the partials are consumed before anything else reuses R1
             } else
 #pragma unroll
             for (int si = 0; si < kSumIters; ++si) {

@@ -31,6 +31,10 @@ for name, r in (("CTA0 ctx0", v[0]), ("CTA0 ctx1", v[1]), ("CTA1 ctx0", v[4]), (
 for name, r in (("CTA0 ctx0", v[0]), ("CTA0 ctx1", v[1])):
     print(name, "M1 stored@%d loads issued@%d barrier passed@%d mean done@%d signalled@%d | done S4@%d score@%d barrier@%d wF@%d barrier@%d" % (
         r[4] - t0, r[12] - t0, r[13] - t0, r[14] - t0, r[5] - t0, r[9] - t0, r[15] - t0, r[16] - t0, r[17] - t0, r[10] - t0))
+for name, r in (("CTA0 ctx0", v[0]), ("CTA0 ctx1", v[1])):
+    if r[18]:
+        print(name, "split mean: barrier passed@%d partials@%d barrier@%d finished@%d barrier@%d replicated@%d" % (
+            r[13] - t0, r[18] - t0, r[19] - t0, r[20] - t0, r[21] - t0, r[14] - t0))
 print("ctx0 reqm arrival per warp (CTA0 hf0 q0-3, hf1 q0-3 | CTA1 ...):", " ".join(str(int(x - t0)) for x in v[6][:16]))
 for c in (0, 1):
     r = v[2 + c]
