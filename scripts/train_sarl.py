@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""SARL value-network training on the B200 backend: mirror of crowd_nav/train.py:21-259 (config 4).
+"""Value-network training (SARL by default; --policy cadrl | lstm_rl) on the B200 backend: mirror of crowd_nav/train.py:21-259
+(config 4).
 
   imitation learning : ORCA robot (safety_space 0.15) -> replay (return-to-go targets) -> il_epochs of SGD
   reinforcement      : epsilon-greedy rollouts -> TD targets from the target network -> train_batches of SGD,
@@ -39,7 +40,10 @@ POLICY_DEFAULT = dict(rl=dict(gamma=0.9), om=dict(cell_num=4, cell_size=1, om_ch
                                         sampling="exponential", query_env="false"),
                       sarl=dict(mlp1_dims="150, 100", mlp2_dims="100, 50", attention_dims="100, 100, 1",
                                 mlp3_dims="150, 100, 100, 1", multiagent_training="true", with_om="false",
-                                with_global_state="true"))
+                                with_global_state="true"),
+                      cadrl=dict(mlp_dims="150, 100, 100, 1", multiagent_training="false"),
+                      lstm_rl=dict(global_state_dim=50, mlp1_dims="150, 100, 100, 50", mlp2_dims="150, 100, 100, 1",
+                                   multiagent_training="true", with_om="false", with_interaction_module="false"))
 
 
 def make_config(default, path=None):
@@ -70,6 +74,7 @@ def main():
     ap.add_argument("--epsilon_end", type=float, default=0.1)
     ap.add_argument("--epsilon_decay", type=float, default=4000)
     ap.add_argument("--batch_size", type=int, default=100)
+    ap.add_argument("--policy", default="sarl", choices=["sarl", "cadrl", "lstm_rl"])    # train.py --policy
     ap.add_argument("--precision", default="f16_tc")
     ap.add_argument("--seed", type=int, default=0)
     a = ap.parse_args()
@@ -91,9 +96,10 @@ def main():
 
     env_config, policy_config = make_config(ENV_DEFAULT, a.env_config), make_config(POLICY_DEFAULT, a.policy_config)
     torch.manual_seed(a.seed)
-    policy = mcn.policy_factory["sarl"]()
+    policy = mcn.policy_factory[a.policy]()
     policy.configure(policy_config)
-    policy.precision = a.precision
+    if a.policy == "sarl" and not policy.with_om:
+        policy.precision = a.precision            # CADRL, LSTM-RL and occupancy maps run on the FP32 path
     policy.set_device(device)
     env = mcn.CrowdSim()
     env.configure(env_config)
