@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libcrowdnav_b200.so")
+# CN_LIB_PATH: developer hook for A/B runs of differently compiled builds of the same library (never a fallback)
+LIB_PATH = os.environ.get("CN_LIB_PATH") or os.path.join(_HERE, "csrc", "libcrowdnav_b200.so")
 
 CN_OK, CN_EINVAL, CN_ECUDA, CN_ENOMEM, CN_EUNSUPPORTED, CN_EVALUE = 0, -1, -2, -3, -4, -5
 NOTHING, DANGER, REACHGOAL, COLLISION, TIMEOUT = 0, 1, 2, 3, 4

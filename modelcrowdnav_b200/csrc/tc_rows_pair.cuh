@@ -316,7 +316,7 @@ tc_rows_pair_kernel(EnvParams p,
             const int total = 5 * rounds;
             int stage0 = 0, stage1 = 0;
             uint32_t ph0 = 0, ph1 = 0, phm0 = 0, phm1 = 0, phx0 = 0, phx1 = 0;
-            long long t_last = clock64();
+            uint32_t idle_polls = 0;
             while (stage0 < total || stage1 < total) {
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
@@ -358,9 +358,11 @@ tc_rows_pair_kernel(EnvParams p,
                     }
                     QPROBE(2 + c, 2 * s + 1);
                     ++stage;
-                    t_last = clock64();
+                    idle_polls = 0;
                 }
-                if (clock64() - t_last > 4000000000LL) __trap();    // protocol bug guard: never hang the GPU
+                // protocol bug guard: never hang the GPU.  (Counted in polls, not clock64() reads: the poll loop IS the hand-over
+                // latency of every stage.  A __nanosleep here was measured and costs 1.5 % at 20 ns, 2.5 % at 100 ns.)
+                if (++idle_polls > (1u << 28)) __trap();
             }
         }
     } else if (is_producer_warp) {
