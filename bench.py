@@ -263,7 +263,7 @@ def main():
                                     env_id_offset=rank * E, auto_reset=1, seed=0,
                                     sim_rule=0 if a.sim == "circle" else 1)
     pipe.reset_device()
-    for _ in range(3):
+    for _ in range(6):                               # 2 eager steps per shard, then one graph capture per block orientation
         pipe.step(a.query_env)
     pipe.sync()
     barrier()
@@ -303,7 +303,8 @@ def main():
             "e2e": {"value": world * E * ne / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "steps": ne, "shards_per_gpu": a.e2e_shards,
                     "how": "PipelinedHostRollout: pinned host state in and out every step, the copies, host round trip and "
-                           "small kernels of one env shard overlap the row kernels of the others",
+                           "small kernels of one env shard overlap the row kernels of the others; one CUDA-graph launch "
+                           "per shard and step",
                     "blocking_single_handle_value": world * E * ne / e2e_blocking_s},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,

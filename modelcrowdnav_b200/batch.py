@@ -303,7 +303,7 @@ class PipelinedHostRollout(object):
     round trip, feature kernel and small kernels (which fit beside the persistent row kernel) are fully hidden."""
 
     def __init__(self, num_envs, human_num, weights, device=0, shards=4, precision="f16_tc", env_id_offset=0,
-                 policy_cfg=None, **env_cfg):
+                 policy_cfg=None, use_graphs=True, **env_cfg):
         import torch
         assert num_envs % shards == 0
         self.E, self.shards, self.device = num_envs, shards, device
@@ -317,6 +317,9 @@ class PipelinedHostRollout(object):
             self.bufs.append(PackedHostStepBuffers(env))
             self.streams.append(torch.cuda.Stream(device=device))
         self.lib = self.envs[0].lib
+        self.use_graphs = bool(use_graphs)
+        self._graphs = {}                    # (shard, input block index, query_env, epsilon) -> torch.cuda.CUDAGraph
+        self._eager_steps = [0] * shards
         self._busy = [False] * shards
         self.h2d_bytes = sum(b.h2d_bytes for b in self.bufs)
         self.d2h_bytes = sum(b.d2h_bytes for b in self.bufs)
@@ -340,14 +343,35 @@ class PipelinedHostRollout(object):
             self._busy[k] = False
             self.bufs[k].swap()              # the state just downloaded is the next input (no host copy)
 
+    def _enqueue(self, k, query_env, epsilon, stream_ptr):
+        b = self.bufs[k]
+        check(self.lib.cn_rollout_step_host_packed_async(
+            self.pols[k].handle, self.envs[k].handle, int(bool(query_env)), float(epsilon),
+            C.c_void_p(b.in_ptr), C.c_void_p(b.out_ptr), C.c_void_p(stream_ptr)))
+
     def step(self, query_env=False, epsilon=0.0):
-        """Enqueue one step of every shard; a shard is re-launched as soon as its previous step has landed."""
+        """Enqueue one step of every shard; a shard is re-launched as soon as its previous step has landed.
+        With use_graphs, a shard's whole step (H2D copy, ~10 kernels on three streams, D2H copy) is captured once per
+        block orientation into a CUDA graph and replayed: one launch per shard and step instead of ~25 driver calls,
+        which keeps the host loop off the critical path on slow or busy hosts."""
+        import torch
         for k in range(self.shards):
             self._wait(k)
-            b = self.bufs[k]
-            check(self.lib.cn_rollout_step_host_packed_async(
-                self.pols[k].handle, self.envs[k].handle, int(bool(query_env)), float(epsilon),
-                C.c_void_p(b.in_ptr), C.c_void_p(b.out_ptr), C.c_void_p(self.streams[k].cuda_stream)))
+            st = self.streams[k]
+            if not self.use_graphs or self._eager_steps[k] < 2:          # the first steps allocate workspaces: run eagerly
+                self._enqueue(k, query_env, epsilon, st.cuda_stream)
+                self._eager_steps[k] += 1
+            else:
+                key = (k, self.bufs[k]._in, bool(query_env), float(epsilon))
+                g = self._graphs.get(key)
+                if g is None:
+                    g = torch.cuda.CUDAGraph()
+                    st.synchronize()
+                    with torch.cuda.graph(g, stream=st):
+                        self._enqueue(k, query_env, epsilon, torch.cuda.current_stream().cuda_stream)
+                    self._graphs[key] = g
+                with torch.cuda.stream(st):
+                    g.replay()
             self._busy[k] = True
 
     def step_device(self, query_env=False, epsilon=0.0):
@@ -382,5 +406,6 @@ class PipelinedHostRollout(object):
 
     def close(self):
         self.sync()
+        self._graphs.clear()
         for e, p in zip(self.envs, self.pols):
             e.close(); p.close()

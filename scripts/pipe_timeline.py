@@ -14,7 +14,7 @@ import modelcrowdnav_b200 as mcn  # noqa: E402
 shards = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 E = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
 w = np.load(os.path.join(ROOT, "tests", "golden", "sarl_weights_seed0.npy"))
-pipe = mcn.PipelinedHostRollout(E, 5, w, shards=shards, auto_reset=1, seed=0)
+pipe = mcn.PipelinedHostRollout(E, 5, w, shards=shards, auto_reset=1, seed=0, use_graphs=False)   # marks need eager calls
 pipe.reset_device()
 for _ in range(5):
     pipe.step()

@@ -446,8 +446,8 @@ def test_packed_host_step_matches_device_step(mcn, oracle_mod, weights0):
     env_a.close(); env_b.close(); pol.close()
 
 
-@pytest.mark.parametrize("shards", [2, 4])
-def test_pipelined_host_rollout_matches_device_step(mcn, oracle_mod, weights0, shards):
+@pytest.mark.parametrize("shards,graphs", [(2, False), (4, True), (2, True)])
+def test_pipelined_host_rollout_matches_device_step(mcn, oracle_mod, weights0, shards, graphs):
     """PipelinedHostRollout (env shards on their own streams, cn_rollout_step_host_packed_async: the copies of one
     shard overlap the kernels of another) returns bit for bit what the single device-resident handle computes,
     including the episodes that finish and are re-seeded on the device (global env ids key the Philox streams)."""
@@ -456,7 +456,8 @@ def test_pipelined_host_rollout_matches_device_step(mcn, oracle_mod, weights0, s
     pol = mcn.BatchedSARL(precision="f16_tc"); pol.load_weights(weights0)
     env.reset_device()
     a0, t0 = env.get_state()
-    pipe = mcn.PipelinedHostRollout(E, H, weights0, shards=shards, precision="f16_tc", auto_reset=1, seed=3)
+    pipe = mcn.PipelinedHostRollout(E, H, weights0, shards=shards, precision="f16_tc", auto_reset=1, seed=3,
+                                    use_graphs=graphs)                    # graphs: one captured launch per shard and step
     pipe.reset_device()
     b = [x for x in pipe.bufs]
     assert np.array_equal(np.concatenate([x.agents_in for x in b]), a0)   # same scenes whatever the sharding
