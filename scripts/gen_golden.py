@@ -171,6 +171,10 @@ TRAJ_SPECS_NETS = [
     ("lstm_circle5_qtrue", 5, "circle_crossing", True, False, [("test", 46, 20)], False, "holonomic", "lstm_rl", None),
     ("lstm2_square10", 10, "square_crossing", False, False, [("test", 47, 20)], False, "holonomic", "lstm_rl",
      {"lstm_rl__with_interaction_module": "true"}),
+    # the fork as shipped never reads [action_space] kinematics for ANY policy (cadrl.py:66): ActionRot planning
+    ("cadrl_circle5_kin_none", 5, "circle_crossing", False, False, [("test", 48, 25)], False, None, "cadrl", None),
+    ("lstm_circle5_kin_none_qtrue", 5, "circle_crossing", True, False, [("test", 49, 20)], False, None, "lstm_rl", None),
+    ("lstm_circle5_unicycle", 5, "circle_crossing", False, False, [("test", 54, 25)], False, "unicycle", "lstm_rl", None),
 ]
 
 
@@ -422,8 +426,12 @@ if __name__ == "__main__":
         gen_om_units()
         gen_trajectories(TRAJ_SPECS_OM)
     elif a.nets:
-        gen_net_units()
-        gen_trajectories(TRAJ_SPECS_NETS)
+        only = os.environ.get("GOLDEN_ONLY")            # comma-separated fixture names: regenerate just those
+        if only:
+            gen_trajectories([sp for sp in TRAJ_SPECS_NETS if sp[0] in only.split(",")])
+        else:
+            gen_net_units()
+            gen_trajectories(TRAJ_SPECS_NETS)
     elif a.random:
         gen_trajectories(TRAJ_SPECS_RANDOM)
     elif a.kinematics:

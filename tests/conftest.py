@@ -57,7 +57,9 @@ TRAJ_NAMES_KIN = ["circle5_kin_none", "circle5_kin_none_qtrue", "circle5_unicycl
 
 # the other value networks behind the same lookahead (policy_factory: cadrl, lstm_rl; ValueNetwork2 = interaction module)
 TRAJ_NAMES_NETS = ["cadrl_circle5", "cadrl_circle5_qtrue", "cadrl_circle1", "lstm_circle5", "lstm_circle5_qtrue",
-                   "lstm2_square10"]
+                   "lstm2_square10",
+                   # non-holonomic robots: kinematics None (what the fork ships for EVERY policy, cadrl.py:66) and unicycle
+                   "cadrl_circle5_kin_none", "lstm_circle5_kin_none_qtrue", "lstm_circle5_unicycle"]
 
 
 # [sim] test_sim = mixed: 1, 2 and 4 humans drawn by the scene itself (the last one with query_env)

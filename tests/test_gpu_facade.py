@@ -139,7 +139,8 @@ def test_state_dict_keys_match_reference(weights0, units):
                                   "circle5_random", "square10_random",
                                   "circle5_kin_none", "circle5_kin_none_qtrue", "circle5_unicycle", "square10_unicycle_qtrue",
                                   "cadrl_circle5", "cadrl_circle5_qtrue", "cadrl_circle1", "lstm_circle5",
-                                  "lstm_circle5_qtrue", "lstm2_square10",
+                                  "lstm_circle5_qtrue", "lstm2_square10", "cadrl_circle5_kin_none",
+                                  "lstm_circle5_kin_none_qtrue", "lstm_circle5_unicycle",
                                   "om_sarl_circle5", "om_sarl_square10_qtrue", "om_lstm_circle5",
                                   "mixed_sarl_a", "mixed_sarl_b", "mixed_sarl_c"])
 def test_facade_replays_reference_episode(name):

@@ -536,6 +536,7 @@ def test_golden_trajectories_kinematics(mcn, weights0, name, precision):
 
 def _net_policy(mcn, tag, **kw):
     """BatchedSARL configured as the reference's CADRL / LSTM-RL ([cadrl], [lstm_rl] of policy.config)."""
+    kw = {k: v for k, v in kw.items() if v is not None}
     if tag == "cadrl":
         return mcn.BatchedSARL(precision="f32", network="cadrl", mlp3_dims=[150, 100, 100, 1], **kw)
     m1 = [150, 100, 100, 50] if tag == "lstm2" else [0, 0, 0, 0]
@@ -574,10 +575,14 @@ def test_golden_trajectories_other_networks(mcn, oracle_mod, units_nets, name):
         for t in range(len(rec["time"])):
             states.append(rec["agents"][t]); times.append(rec["time"][t]); recs.append((rec, t))
     E = len(states)
-    env = mcn.BatchedCrowdSim(E, H)
-    pol = _net_policy(mcn, tag)
+    kin = tr["kinematics"]
+    env = mcn.BatchedCrowdSim(E, H, robot_kinematics=kin)
+    pol = _net_policy(mcn, tag, kinematics=kin)
     pol.load_weights(units_nets[tag + "_weights"])
+    assert np.array_equal(pol.action_table, recs[0][0]["table"])
     env.set_state(np.stack(states), np.array(times))
+    if kin != 0:
+        env.set_theta(np.array([rec["theta"][t] for rec, t in recs]))
     env.orca()
     pol.lookahead(env, query_env=tr["query_env"])
     best, values = pol.read(env)
@@ -594,7 +599,12 @@ def test_golden_trajectories_other_networks(mcn, oracle_mod, units_nets, name):
             agree += int(best[e] == rec["best"][t])
         assert (reward[e], bool(done[e]), int(info[e])) == (rec["reward"][t], bool(rec["done"][t]), int(rec["info"][t]))
         if t + 1 < len(rec["time"]):
-            assert np.array_equal(got[e], rec["agents"][t + 1]) and gt[e] == rec["time"][t + 1]
+            if kin == 0:
+                assert np.array_equal(got[e], rec["agents"][t + 1])
+            else:                                            # double cos / sin in the robot update: 1-2 ulp, humans exact
+                assert np.allclose(got[e], rec["agents"][t + 1], rtol=0, atol=1e-12)
+                assert np.array_equal(got[e][1:], rec["agents"][t + 1][1:])
+            assert gt[e] == rec["time"][t + 1]
     assert total > 0 and agree / total >= 0.999, (agree, total)
     env.close(); pol.close()
 

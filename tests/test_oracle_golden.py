@@ -168,7 +168,9 @@ def test_trajectories_other_networks(oracle_mod, units_nets, name):
             gt = float(rec["time"][t])
             hv = o.human_actions(ecfg, agents)
             assert np.array_equal(hv, rec["human_v"][t]), (case, t)
-            best, values, reached = o.lookahead_net(ecfg, ncfg, w, agents, gt, table, tr["query_env"], hv)
+            theta = float(rec["theta"][t]) if "theta" in rec else 0.0
+            best, values, reached = o.lookahead_net(ecfg, ncfg, w, agents, gt, table, tr["query_env"], hv,
+                                                    kinematics=tr["kinematics"], theta=theta)
             assert not reached
             ref_v = rec["values"][t]
             assert np.max(np.abs(values - ref_v)) <= 1e-5 * max(1.0, np.max(np.abs(ref_v))), (case, t)
