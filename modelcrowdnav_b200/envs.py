@@ -461,6 +461,14 @@ class ModelCrowdSim(CrowdSim):
             new_v = self.sim_world(x)[0]
         return torch.reshape(new_v, (len(self.humans), 2)).tolist()
 
+    def world_velocities_batch(self, agents):
+        """world_velocities() for a batch: agents (k, H+1, 8) -> (k, H, 2) float64, one forward of the world model."""
+        import torch
+        x = torch.as_tensor(np.ascontiguousarray(agents[:, 1:, :4]), dtype=torch.float32).to(self.device)
+        with torch.no_grad():
+            v = self.sim_world(x.reshape(x.shape[0], -1))
+        return v.reshape(x.shape[0], -1, 2).double().cpu().numpy()
+
     def step(self, action, update=True, new_v=None):
         if new_v is not None:                      # caller-supplied velocities (model_crowd_sim.py:347,397)
             b = self._ensure_batch()

@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _capi, scenes
 from .batch import BatchedCrowdSim
-from .envs import batch_env_kwargs
+from .envs import ModelCrowdSim, batch_env_kwargs
 from .policy import CADRL, ORCA, SARL, Linear
 
 
@@ -181,6 +181,7 @@ class Explorer(object):
         elif not isinstance(policy, (ORCA, Linear)) and not stay:
             raise NotImplementedError("robot policy %r is not on the B200 hot path" % type(policy).__name__)
         tr_policy = self.target_policy if (imitation_learning and self.target_policy is not None) else policy
+        world_env = isinstance(env, ModelCrowdSim)
 
         active = np.ones(k, bool)
         rewards_t, states_t, active_t = [], [], []
@@ -201,7 +202,10 @@ class Explorer(object):
                     assert st.shape[1] == 1                        # cadrl.py:209: CADRL trains on single-human states
                     st = st[:, 0]
                 states_t.append(st)
-            b.orca()
+            if world_env:                  # ModelCrowdSim: the humans' next velocities come from the world model
+                b.set_human_actions(env.world_velocities_batch(b.get_state()[0]))
+            else:
+                b.orca()
             if stay:
                 b.set_actions(np.zeros((k, 2)))
             elif is_sarl:

@@ -425,3 +425,47 @@ def test_linear_robot_policy(weights0):
             steps += 1
         code = {mcn.ReachGoal: 2, mcn.Collision: 3, mcn.Timeout: 4}[type(info)]
         assert (code, steps) == (int(run["info"][c]), int(run["steps"][c])), c
+
+
+def test_explorer_over_model_crowd_sim(weights0):
+    """Explorer.run_k_episodes on a ModelCrowdSim env: the batch asks the world model for every env's human velocities
+    (one forward per step) instead of ORCA.  Scenes come from the global numpy stream in the order sequential resets would
+    draw them; episodes must end like the same scenes driven one by one through the façade (batched and single forwards of
+    the world model may round differently, so a small fraction of episodes may drift)."""
+    import torch
+    import modelcrowdnav_b200 as mcn
+    import modelcrowdnav_b200.compat as compat
+    from modelcrowdnav_b200.world_model import AttentionWorld
+    g = load_model_world("attn_circle5")
+    _, robot, policy, _ = _setup(weights0, "f32", human_num=5)
+    env = compat.make("ModelCrowdSim-v0")
+    env.configure(_cfg(ENV_INI))
+    env.set_robot(robot)
+    policy.set_env(env)
+    world = AttentionWorld()
+    off, new = 0, {}
+    for k, v in world.state_dict().items():
+        new[k] = torch.from_numpy(g["world_weights"][off:off + v.numel()].reshape(tuple(v.shape)).copy())
+        off += v.numel()
+    world.load_state_dict(new)
+    env.sim_world, env.device = world.cuda().eval(), torch.device("cuda:0")
+    explorer = mcn.Explorer(env, robot, torch.device("cuda:0"), gamma=0.9)
+    k = 16
+    state = np.random.get_state()
+    try:
+        np.random.seed(21)
+        explorer.run_k_episodes(k, "test")
+        run = explorer.last_run
+        np.random.seed(21)
+        same = 0
+        for c in range(k):
+            ob = env.reset("test", c)
+            done, steps = False, 0
+            while not done:
+                ob, reward, done, info = env.step(robot.act(ob))
+                steps += 1
+            code = {mcn.ReachGoal: 2, mcn.Collision: 3, mcn.Timeout: 4}[type(info)]
+            same += int((code, steps) == (int(run["info"][c]), int(run["steps"][c])))
+    finally:
+        np.random.set_state(state)
+    assert same >= k - 2, same
