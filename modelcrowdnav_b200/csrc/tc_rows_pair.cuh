@@ -538,6 +538,10 @@ tc_rows_pair_kernel(EnvParams p,
             // NOW, so that its UMMA runs under the softmax / w * F / group sums below.  (Stage 1 writes [120,232) and is only
             // requested after the next E0, i.e. after every warp has finished this tile.)
             if (has_next) PAIR_SIGNAL();
+            // the pairwise features F of this thread's row: the load stays in flight across the barrier and the softmax
+            // (a tcgen05.ld + wait round trip is ~290 cycles of this, the longest, epilogue)
+            uint32_t fv[32];
+            ld32(tl + T_F + hf * 32, fv);
             ctx_barrier(ctx);
             QPROBE(ctx, 16);
             float w = 0.0f;
@@ -590,13 +594,11 @@ tc_rows_pair_kernel(EnvParams p,
             {
                 // w * F as fp16 (fp32 product rounded once), chunked like an operand over the (dead) Ha1 tile in R2 -- not R1:
                 // the next tile's H1 epilogue may start while slower warps still sum: hf 0 -> features 0..31, hf 1 -> 32..55
-                uint32_t v[32];
-                ld32(tl + T_F + hf * 32, v);
                 wait_ld();
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     if (hf == 1 && c == 3) break;
-                    const float *f = reinterpret_cast<const float *>(v) + c * 8;
+                    const float *f = reinterpret_cast<const float *>(fv) + c * 8;
                     *reinterpret_cast<uint4 *>(R2 + chunk_off(ROWS, row, hf * 4 + c)) =
                         make_uint4(h2(w * f[0], w * f[1]), h2(w * f[2], w * f[3]), h2(w * f[4], w * f[5]), h2(w * f[6], w * f[7]));
                 }
