@@ -132,10 +132,10 @@ tc_mlp3_pair_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *_
         for (int rnd = 0; rnd < rounds; ++rnd, tile += tile_stride) {
             M3_WAIT();
             if (warp == 4 * ctx && lane == 0) mbar_arrive(ctx ? xfree1 : xfree0);  // J is dead: the next J tile may land
-            compact_to_tmem<true>(tl, hf * 80, 80, hf * 80, 1.0f);                 // U0, packed in place
+            compact_to_tmem<true, true>(tl, hf * 80, 80, hf * 80, 1.0f);                 // U0, packed in place
             M3_SIGNAL();
             M3_WAIT();
-            if (hf == 0) compact_to_tmem<true>(tl, M3_D1, 64, M3_D1, 1.0f);        // U1, packed in place
+            if (hf == 0) compact_to_tmem<true, true>(tl, M3_D1, 64, M3_D1, 1.0f);        // U1, packed in place
             else compact_to_tmem<true>(tl, M3_D1 + 64, 48, M3_D1 + 64, 1.0f);
             M3_SIGNAL();
             M3_WAIT();

@@ -427,7 +427,7 @@ tc_rows_pair_kernel(EnvParams p,
             // ---- E0: H1 = relu(acc[0,160)) -> R1 ----
             PAIR_WAIT(); QPROBE(ctx, 1);
             if (warp == 4 * ctx && lane == 0) mbar_arrive(ctx ? xfree1 : xfree0);      // stage 0 is complete (H1 lives in TMEM): the X slot may be refilled
-            compact_to_tmem<true>(tl, hf * 80, 80, hf * T_H1B, 1.0f);              // in place: no shared-memory traffic for H1
+            compact_to_tmem<true, true>(tl, hf * 80, 80, hf * T_H1B, 1.0f);        // in place: no shared-memory traffic for H1
             PAIR_SIGNAL(); QPROBE(ctx, 2);
             // ---- E1: mlp1_out = relu(acc[0,112)) -> R2 ----
             PAIR_WAIT(); QPROBE(ctx, 3);
@@ -503,7 +503,7 @@ tc_rows_pair_kernel(EnvParams p,
             QPROBE(ctx, 6);
             // ---- E3: H3 = relu(acc[0,112)) -> R1 (hf 0) ; Ha1 = relu(acc[112,224)) -> R2 (hf 1) ----
             PAIR_WAIT(); QPROBE(ctx, 7);
-            if (hf == 0) compact_to_tmem<true>(tl, 0, N_M1, 0, 1.0f);               // Ha1: fp16 pairs in place, [0,56)
+            if (hf == 0) compact_to_tmem<true, true>(tl, 0, N_M1, 0, 1.0f);         // Ha1: fp16 pairs in place, [0,56)
             else epilogue_to_smem<true>(tl, N_M1, N_M1, R1, row, 0);
             PAIR_SIGNAL(); QPROBE(ctx, 8);
             // ---- E4: attention.4 dot (split over the column halves), masked softmax (sarl.py:48-53), w * F ----
@@ -511,14 +511,15 @@ tc_rows_pair_kernel(EnvParams p,
             {
                 float part = 0.0f;
                 if (hf == 0) {
-                    uint32_t v[32], u[32];
+                    uint32_t v[32];
                     ld32(tl + T_A2, v);
-                    ld32(tl + T_A2 + 32, u);
                     wait_ld();
 #pragma unroll
                     for (int k = 0; k < 32; ++k) part = fmaf(fmaxf(__uint_as_float(v[k]), 0.0f), tw.w[k], part);
+                    ld32(tl + T_A2 + 32, v);
+                    wait_ld();
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) part = fmaf(fmaxf(__uint_as_float(u[k]), 0.0f), tw.w[32 + k], part);
+                    for (int k = 0; k < 32; ++k) part = fmaf(fmaxf(__uint_as_float(v[k]), 0.0f), tw.w[32 + k], part);
                     S0[row] = part;
                 } else {
                     uint32_t x[32], y[16];

@@ -383,11 +383,11 @@ __device__ __forceinline__ void epilogue_scaled_to_smem(uint32_t taddr_lane, int
     }
 }
 
-template <bool RELU>
+template <bool RELU, bool NARROW = false>
 __device__ __forceinline__ void epilogue_to_smem(uint32_t taddr_lane, int col, int ncols, uint8_t *dst, int row, int kc0)
 {
     int done = 0;
-    while (ncols - done >= 64) {          // two TMEM loads in flight per wait
+    while (!NARROW && ncols - done >= 64) {          // two TMEM loads in flight per wait
         uint32_t v[32], u[32];
         ld32(taddr_lane + col + done, v);
         ld32(taddr_lane + col + done + 32, u);
@@ -398,7 +398,7 @@ __device__ __forceinline__ void epilogue_to_smem(uint32_t taddr_lane, int col, i
         for (int q = 0; q < 4; ++q) cvt_store8<RELU>(u + q * 8, dst + chunk_off(128, row, kc0 + done / 8 + 4 + q));
         done += 64;
     }
-    if (ncols - done >= 48) {
+    if (!NARROW && ncols - done >= 48) {
         uint32_t v[32], u[16];
         ld32(taddr_lane + col + done, v);
         ld16(taddr_lane + col + done + 32, u);
@@ -409,7 +409,7 @@ __device__ __forceinline__ void epilogue_to_smem(uint32_t taddr_lane, int col, i
         for (int q = 0; q < 2; ++q) cvt_store8<RELU>(u + q * 8, dst + chunk_off(128, row, kc0 + done / 8 + 4 + q));
         done += 48;
     }
-    if (ncols - done >= 32) {
+    while (ncols - done >= 32) {
         uint32_t v[32];
         ld32(taddr_lane + col + done, v);
         wait_ld();
@@ -430,11 +430,14 @@ __device__ __forceinline__ void epilogue_to_smem(uint32_t taddr_lane, int col, i
 // TMEM[col_src, +ncols) fp32 of this thread's lane -> fp16 pairs packed into TMEM[col_dst, +ncols/2), ascending,
 // safe in place (col_dst == col_src): every store lands behind the columns still to be read.
 // SCALE: multiply by `scale` (no ReLU); otherwise ReLU fused in the conversion.
-template <bool RELU>
+// NO64: at most one 32-column load per wait.  Measured in the CTA-pair kernels (88 registers): the "two loads per wait" form
+// costs 2.5 % of the lookahead at EACH of the three places it was used (mlp1.0, attention.0, mlp3 hidden layers) although it
+// saves a tcgen05.ld round trip; a 48-column tail in one trip was 15 % slower still.  16-column pieces: +0.6 %, within noise.
+template <bool RELU, bool NO64 = false>
 __device__ __forceinline__ void compact_to_tmem(uint32_t tlane, int col_src, int ncols, int col_dst, float scale, bool ftz = false, int synth = 0)
 {
     int done = 0;
-    while (ncols - done >= 64) {          // two TMEM loads in flight per wait (a load + wait round trip is ~290 cycles)
+    while (!NO64 && ncols - done >= 64) {          // two TMEM loads in flight per wait (a load + wait round trip is ~290 cycles)
         uint32_t v[32], u[32], w[16];
         ld32(tlane + col_src + done, v);
         ld32(tlane + col_src + done + 32, u);
@@ -468,7 +471,7 @@ __device__ __forceinline__ void compact_to_tmem(uint32_t tlane, int col_src, int
         st16(tlane + col_dst + done / 2, w);
         done += 32;
     }
-    if (ncols - done >= 16) {
+    while (ncols - done >= 16) {
         uint32_t v[16], w[8];
         ld16(tlane + col_src + done, v);
         wait_ld();
