@@ -30,7 +30,7 @@ UNIT = "env-steps/s"
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture
-NCU_DRAM_BYTES = {("f16_tc", 8192, 5): 218558976 + 56253184}   # tc_rows_pair_kernel<5>: X tiles in, J tiles out
+NCU_DRAM_BYTES = {("f16_tc", 8192, 5): 218508032 + 56814592}   # tc_rows_pair_kernel<5>: X tiles in, J tiles out
 
 
 def flops_per_env_step(H):
@@ -310,7 +310,7 @@ def main():
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                          "traffic": NCU_DRAM_BYTES.get((a.precision, E, H)),
                          "traffic_source": "ncu --set full, tc_rows_pair_kernel, dram__bytes_read+write per launch "
-                                           "(profiles/r01h_pair_kernels_ncu_summary.txt)",
+                                           "(profiles/r01k_pair_kernels_ncu_summary.txt)",
                          "kernel": "lookahead (value network)", "kernel_ms": la_ms,
                          "flops_per_env_step": F, "peak_source": peaks["source"] + ", sustained bf16"},
         }
