@@ -142,21 +142,23 @@ tc_mlp3_pair_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *_
             // mlp3.6 as an fp32 dot over ReLU(mlp3.4), split over the column halves
             float part = 0.0f;
             if (hf == 0) {
-                uint32_t v[32], u[32];
+                uint32_t v[32];                                 // one 32-column load per wait (see compact_to_tmem)
                 ld32(tl, v);
-                ld32(tl + 32, u);
                 wait_ld();
 #pragma unroll
                 for (int k = 0; k < 32; ++k) part = fmaf(fmaxf(__uint_as_float(v[k]), 0.0f), tw.w[k], part);
+                ld32(tl + 32, v);
+                wait_ld();
 #pragma unroll
-                for (int k = 0; k < 32; ++k) part = fmaf(fmaxf(__uint_as_float(u[k]), 0.0f), tw.w[32 + k], part);
+                for (int k = 0; k < 32; ++k) part = fmaf(fmaxf(__uint_as_float(v[k]), 0.0f), tw.w[32 + k], part);
             } else {
                 uint32_t x[32], y[16];
                 ld32(tl + 64, x);
-                ld16(tl + 96, y);
                 wait_ld();
 #pragma unroll
                 for (int k = 0; k < 32; ++k) part = fmaf(fmaxf(__uint_as_float(x[k]), 0.0f), tw.w[64 + k], part);
+                ld16(tl + 96, y);
+                wait_ld();
 #pragma unroll
                 for (int k = 0; k < 4; ++k) part = fmaf(fmaxf(__uint_as_float(y[k]), 0.0f), tw.w[96 + k], part);
                 S1[row] = part;

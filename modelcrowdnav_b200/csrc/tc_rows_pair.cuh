@@ -524,10 +524,11 @@ tc_rows_pair_kernel(EnvParams p,
                 } else {
                     uint32_t x[32], y[16];
                     ld32(tl + T_A2 + 64, x);
-                    ld16(tl + T_A2 + 96, y);
                     wait_ld();
 #pragma unroll
                     for (int k = 0; k < 32; ++k) part = fmaf(fmaxf(__uint_as_float(x[k]), 0.0f), tw.w[64 + k], part);
+                    ld16(tl + T_A2 + 96, y);
+                    wait_ld();
 #pragma unroll
                     for (int k = 0; k < 4; ++k) part = fmaf(fmaxf(__uint_as_float(y[k]), 0.0f), tw.w[96 + k], part);
                     S1[row] = part;
