@@ -314,6 +314,14 @@ def main():
                          "kernel": "lookahead (value network)", "kernel_ms": la_ms,
                          "flops_per_env_step": F, "peak_source": peaks["source"] + ", sustained bf16"},
         }
+        # secondary figure: the ORCA + env-step kernels against the HBM roofline.  48 (H + 1) + 22 algorithmic bytes
+        # per env step; these kernels are latency / FP32-issue bound, three orders of magnitude below the HBM ceiling.
+        step_bytes = 48 * (H + 1) + 22
+        step_ms = phases["orca"] + phases["step"]
+        line["roofline_orca_step"] = {"bound": "hbm", "achieved": E * step_bytes / (step_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"],
+                                      "unit": "GB/s", "frac": E * step_bytes / (step_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
+                                      "bytes_per_env_step": step_bytes, "kernel_ms": step_ms,
+                                      "kernel": "orca_humans_kernel + step_kernel (+ reset of finished episodes)"}
         if not a.no_cpu_baseline:
             cores = 1
             n = 16
