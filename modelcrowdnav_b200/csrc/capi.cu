@@ -810,8 +810,7 @@ static int rollout_step_impl(cn_policy *p, cn_env *env, int query_env, double ep
     *cur = s;
     if (fork) CN_CUDA_CHECK(cudaStreamWaitEvent(s, env->ev_join, 0));
     cn_trace_mark("step", s);
-    if ((rc = cn_launch_step(env, nullptr, 1, s))) return rc;
-    if (env->p.auto_reset) rc = cn_launch_reset(env, 1, s);
+    if ((rc = cn_launch_step(env, nullptr, 1, s, env->p.auto_reset ? 1 : 0))) return rc;     // auto-reset fused into the step
     cn_trace_mark("step_done", s);
     return rc;
 }

@@ -229,7 +229,7 @@ __host__ __device__ __forceinline__ double norm2d(double a, double b) { return s
 // ---- module entry points (each .cu) -----------------------------------------------------------
 int cn_launch_orca(cn_env *env, cudaStream_t s);
 int cn_launch_robot_orca(cn_env *env, double safety_space, cudaStream_t s);
-int cn_launch_step(cn_env *env, const double *action_xy_dev, int update, cudaStream_t s);
+int cn_launch_step(cn_env *env, const double *action_xy_dev, int update, cudaStream_t s, int fuse_reset = 0);
 int cn_launch_reset(cn_env *env, int only_done, cudaStream_t s);
 int cn_launch_pack(cn_env *env, int to_soa, cudaStream_t s);  // stage (AoS) <-> state (SoA)
 int cn_launch_io(cn_env *env, double *blk, int unpack, cudaStream_t s);   // packed host exchange block <-> device state

@@ -250,101 +250,12 @@ __global__ void __launch_bounds__(128) orca_robot_kernel(EnvParams p, const doub
 }
 
 // K2: CrowdSim.step for one env per thread (crowd_sim.py:344-434).
-__global__ void __launch_bounds__(128) step_kernel(EnvParams p, double *__restrict__ st, double *__restrict__ time,
-                                                   const double *__restrict__ human_v,
-                                                   const double *__restrict__ act, int act_aos, int update,
-                                                   double *__restrict__ reward_o, uint8_t *__restrict__ done_o,
-                                                   uint8_t *__restrict__ info_o, double *__restrict__ dmin_o,
-                                                   double *__restrict__ next_obs, uint8_t *__restrict__ frozen,
-                                                   EnvAccum acc, double *__restrict__ theta)
+// CrowdSim.reset on the device for ONE env: crowd_sim.py:165-217 distributions and rejection rule; Philox stream
+// keyed by (seed, global env id, episode counter).
+__device__ void reset_env(const EnvParams &p, int e, double *__restrict__ st, double *__restrict__ time,
+                          uint8_t *__restrict__ frozen, const EnvAccum &acc, double *__restrict__ theta)
 {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const EnvDims d = p.d;
-    if (e >= d.E) return;
-    if (frozen[e]) { reward_o[e] = 0.0; done_o[e] = 1; return; }
-    const int E = d.E, H = d.H;
-    // the action: (vx, vy) holonomic, (v, r) otherwise; (ax, ay) = the velocity the step moves and collision-checks with
-    const double a0 = act_aos ? act[2 * (size_t)e] : act[e];
-    const double a1 = act_aos ? act[2 * (size_t)e + 1] : act[E + e];
-    const double th = p.kinematics != CN_KIN_HOLONOMIC ? theta[e] : 0.0;
-    double ax, ay;
-    cn_effective_velocity(p.kinematics, th, a0, a1, ax, ay);
-    const double dt = p.time_step;
-    const double t = time[e];
-    auto ag = [&](int f, int a) { return st[st_idx(d, f, a, e)]; };
-    const StepOutcome oc = cn_step_outcome(p, ag, H, t, ax, ay);
-    const double reward = oc.reward, dmin = oc.dmin;
-    const int done = oc.done, info = oc.info;
-    const double endx = ag(F_PX, 0) + ax * dt, endy = ag(F_PY, 0) + ay * dt;
-    reward_o[e] = reward; done_o[e] = (uint8_t)done; info_o[e] = (uint8_t)info; dmin_o[e] = dmin;
-
-    if (update) {
-        // crowd_sim.py:414-417, agent.py:122-135
-        st[st_idx(d, F_PX, 0, e)] = endx;
-        st[st_idx(d, F_PY, 0, e)] = endy;
-        if (p.kinematics == CN_KIN_HOLONOMIC) {
-            st[st_idx(d, F_VX, 0, e)] = ax;
-            st[st_idx(d, F_VY, 0, e)] = ay;
-        } else {
-            // agent.py:131-133: the heading wraps to [0, 2 pi) (Python float %), the stored velocity uses the wrapped heading
-            const double TWO_PI = 2 * 3.141592653589793;
-            double t2 = fmod(th + a1, TWO_PI);
-            if (t2 < 0) t2 += TWO_PI;
-            theta[e] = t2;
-            st[st_idx(d, F_VX, 0, e)] = a0 * cos(t2);
-            st[st_idx(d, F_VY, 0, e)] = a0 * sin(t2);
-        }
-        for (int h = 1; h <= H; ++h) {
-            const double hvx = human_v[(size_t)(0 * H + h - 1) * E + e];
-            const double hvy = human_v[(size_t)(1 * H + h - 1) * E + e];
-            st[st_idx(d, F_PX, h, e)] = st[st_idx(d, F_PX, h, e)] + hvx * dt;
-            st[st_idx(d, F_PY, h, e)] = st[st_idx(d, F_PY, h, e)] + hvy * dt;
-            st[st_idx(d, F_VX, h, e)] = hvx;
-            st[st_idx(d, F_VY, h, e)] = hvy;
-        }
-        const double tn = t + dt;
-        time[e] = tn;
-        // explorer.py counters
-        const int k = acc.ep_steps[e];
-        const double disc = pow(p.gamma, (double)k * dt * st[st_idx(d, F_VPREF, 0, e)]);
-        const double ret = acc.ep_return[e] + disc * reward;
-        acc.steps[e] += 1;
-        if (info == CN_DANGER) { acc.too_close[e] += 1; acc.sum_min_dist[e] += dmin; }
-        if (done) {
-            acc.episodes[e] += 1;
-            if (info == CN_REACHGOAL) { acc.success[e] += 1; acc.sum_success_time[e] += tn; }
-            else if (info == CN_COLLISION) { acc.collision[e] += 1; acc.sum_collision_time[e] += tn; }
-            else { acc.timeout[e] += 1; acc.sum_timeout_time[e] += p.time_limit; }
-            acc.sum_return[e] += ret;
-            acc.ep_return[e] = 0.0; acc.ep_steps[e] = 0;
-            if (!p.auto_reset) frozen[e] = 1;
-        } else {
-            acc.ep_return[e] = ret; acc.ep_steps[e] = k + 1;
-        }
-    } else {
-        // onestep_lookahead observation (crowd_sim.py:428-430, agent.py:63-74)
-        for (int h = 1; h <= H; ++h) {
-            const double hvx = human_v[(size_t)(0 * H + h - 1) * E + e];
-            const double hvy = human_v[(size_t)(1 * H + h - 1) * E + e];
-            next_obs[(size_t)(0 * H + h - 1) * E + e] = st[st_idx(d, F_PX, h, e)] + hvx * dt;
-            next_obs[(size_t)(1 * H + h - 1) * E + e] = st[st_idx(d, F_PY, h, e)] + hvy * dt;
-            next_obs[(size_t)(2 * H + h - 1) * E + e] = hvx;
-            next_obs[(size_t)(3 * H + h - 1) * E + e] = hvy;
-            next_obs[(size_t)(4 * H + h - 1) * E + e] = st[st_idx(d, F_R, h, e)];
-        }
-    }
-}
-
-// CrowdSim.reset on the device: crowd_sim.py:165-217 distributions and rejection rule; Philox stream
-// keyed by (seed, global env id, episode counter).  One thread per env.
-__global__ void __launch_bounds__(128) reset_kernel(EnvParams p, double *__restrict__ st, double *__restrict__ time,
-                                                    const uint8_t *__restrict__ done, int only_done,
-                                                    uint8_t *__restrict__ frozen, EnvAccum acc, double *__restrict__ theta)
-{
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    const EnvDims d = p.d;
-    if (e >= d.E) return;
-    if (only_done && !done[e]) return;
     PhiloxStream rng;
     rng.init(p.seed, (uint64_t)(p.env_id_offset + e), acc.episode_ctr[e], 0u);
     acc.episode_ctr[e] += 1;
@@ -413,6 +324,105 @@ __global__ void __launch_bounds__(128) reset_kernel(EnvParams p, double *__restr
     theta[e] = 1.5707963267948966;                       // crowd_sim.py:284: robot.set(..., np.pi / 2)
     frozen[e] = 0;
     acc.ep_steps[e] = 0; acc.ep_return[e] = 0.0;
+}
+
+__global__ void __launch_bounds__(128) step_kernel(EnvParams p, double *__restrict__ st, double *__restrict__ time,
+                                                   const double *__restrict__ human_v,
+                                                   const double *__restrict__ act, int act_aos, int update,
+                                                   double *__restrict__ reward_o, uint8_t *__restrict__ done_o,
+                                                   uint8_t *__restrict__ info_o, double *__restrict__ dmin_o,
+                                                   double *__restrict__ next_obs, uint8_t *__restrict__ frozen,
+                                                   EnvAccum acc, double *__restrict__ theta, int fuse_reset)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const EnvDims d = p.d;
+    if (e >= d.E) return;
+    if (frozen[e]) { reward_o[e] = 0.0; done_o[e] = 1; return; }
+    const int E = d.E, H = d.H;
+    // the action: (vx, vy) holonomic, (v, r) otherwise; (ax, ay) = the velocity the step moves and collision-checks with
+    const double a0 = act_aos ? act[2 * (size_t)e] : act[e];
+    const double a1 = act_aos ? act[2 * (size_t)e + 1] : act[E + e];
+    const double th = p.kinematics != CN_KIN_HOLONOMIC ? theta[e] : 0.0;
+    double ax, ay;
+    cn_effective_velocity(p.kinematics, th, a0, a1, ax, ay);
+    const double dt = p.time_step;
+    const double t = time[e];
+    auto ag = [&](int f, int a) { return st[st_idx(d, f, a, e)]; };
+    const StepOutcome oc = cn_step_outcome(p, ag, H, t, ax, ay);
+    const double reward = oc.reward, dmin = oc.dmin;
+    const int done = oc.done, info = oc.info;
+    const double endx = ag(F_PX, 0) + ax * dt, endy = ag(F_PY, 0) + ay * dt;
+    reward_o[e] = reward; done_o[e] = (uint8_t)done; info_o[e] = (uint8_t)info; dmin_o[e] = dmin;
+
+    if (update) {
+        // crowd_sim.py:414-417, agent.py:122-135
+        st[st_idx(d, F_PX, 0, e)] = endx;
+        st[st_idx(d, F_PY, 0, e)] = endy;
+        if (p.kinematics == CN_KIN_HOLONOMIC) {
+            st[st_idx(d, F_VX, 0, e)] = ax;
+            st[st_idx(d, F_VY, 0, e)] = ay;
+        } else {
+            // agent.py:131-133: the heading wraps to [0, 2 pi) (Python float %), the stored velocity uses the wrapped heading
+            const double TWO_PI = 2 * 3.141592653589793;
+            double t2 = fmod(th + a1, TWO_PI);
+            if (t2 < 0) t2 += TWO_PI;
+            theta[e] = t2;
+            st[st_idx(d, F_VX, 0, e)] = a0 * cos(t2);
+            st[st_idx(d, F_VY, 0, e)] = a0 * sin(t2);
+        }
+        for (int h = 1; h <= H; ++h) {
+            const double hvx = human_v[(size_t)(0 * H + h - 1) * E + e];
+            const double hvy = human_v[(size_t)(1 * H + h - 1) * E + e];
+            st[st_idx(d, F_PX, h, e)] = st[st_idx(d, F_PX, h, e)] + hvx * dt;
+            st[st_idx(d, F_PY, h, e)] = st[st_idx(d, F_PY, h, e)] + hvy * dt;
+            st[st_idx(d, F_VX, h, e)] = hvx;
+            st[st_idx(d, F_VY, h, e)] = hvy;
+        }
+        const double tn = t + dt;
+        time[e] = tn;
+        // explorer.py counters
+        const int k = acc.ep_steps[e];
+        const double disc = pow(p.gamma, (double)k * dt * st[st_idx(d, F_VPREF, 0, e)]);
+        const double ret = acc.ep_return[e] + disc * reward;
+        acc.steps[e] += 1;
+        if (info == CN_DANGER) { acc.too_close[e] += 1; acc.sum_min_dist[e] += dmin; }
+        if (done) {
+            acc.episodes[e] += 1;
+            if (info == CN_REACHGOAL) { acc.success[e] += 1; acc.sum_success_time[e] += tn; }
+            else if (info == CN_COLLISION) { acc.collision[e] += 1; acc.sum_collision_time[e] += tn; }
+            else { acc.timeout[e] += 1; acc.sum_timeout_time[e] += p.time_limit; }
+            acc.sum_return[e] += ret;
+            acc.ep_return[e] = 0.0; acc.ep_steps[e] = 0;
+            if (!p.auto_reset) frozen[e] = 1;
+            // rollout step of an auto-reset env: the finished episode is re-generated here instead of by a reset_kernel launch
+            // behind this one (a 13 us latency-bound kernel per step for the ~2 % of envs that finish)
+            else if (fuse_reset) reset_env(p, e, st, time, frozen, acc, theta);
+        } else {
+            acc.ep_return[e] = ret; acc.ep_steps[e] = k + 1;
+        }
+    } else {
+        // onestep_lookahead observation (crowd_sim.py:428-430, agent.py:63-74)
+        for (int h = 1; h <= H; ++h) {
+            const double hvx = human_v[(size_t)(0 * H + h - 1) * E + e];
+            const double hvy = human_v[(size_t)(1 * H + h - 1) * E + e];
+            next_obs[(size_t)(0 * H + h - 1) * E + e] = st[st_idx(d, F_PX, h, e)] + hvx * dt;
+            next_obs[(size_t)(1 * H + h - 1) * E + e] = st[st_idx(d, F_PY, h, e)] + hvy * dt;
+            next_obs[(size_t)(2 * H + h - 1) * E + e] = hvx;
+            next_obs[(size_t)(3 * H + h - 1) * E + e] = hvy;
+            next_obs[(size_t)(4 * H + h - 1) * E + e] = st[st_idx(d, F_R, h, e)];
+        }
+    }
+}
+
+// One thread per env (explicit resets, and the auto-reset of finished episodes when it is not fused into step_kernel).
+__global__ void __launch_bounds__(128) reset_kernel(EnvParams p, double *__restrict__ st, double *__restrict__ time,
+                                                    const uint8_t *__restrict__ done, int only_done,
+                                                    uint8_t *__restrict__ frozen, EnvAccum acc, double *__restrict__ theta)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.d.E) return;
+    if (only_done && !done[e]) return;
+    reset_env(p, e, st, time, frozen, acc, theta);
 }
 
 // stage (AoS, E x A1 x 8) <-> state (SoA, 8 x A1 x E)
@@ -538,14 +548,14 @@ int cn_launch_robot_orca(cn_env *env, double safety_space, cudaStream_t s)
     return CN_OK;
 }
 
-int cn_launch_step(cn_env *env, const double *action_xy_dev, int update, cudaStream_t s)
+int cn_launch_step(cn_env *env, const double *action_xy_dev, int update, cudaStream_t s, int fuse_reset)
 {
     const double *act = action_xy_dev ? action_xy_dev : env->action_xy;
     const int bs = cn_small_block();
     step_kernel<<<grid_for(env->p.d.E, bs), bs, 0, s>>>(env->p, env->state, env->time, env->human_v, act,
                                                             action_xy_dev ? 1 : 0, update, env->reward, env->done,
                                                             env->info, env->dmin, env->next_obs, env->frozen,
-                                                            env->acc, env->theta);
+                                                            env->acc, env->theta, fuse_reset);
     CN_LAUNCH_CHECK();
     if (update) env->orca_valid = 0;
     return CN_OK;
