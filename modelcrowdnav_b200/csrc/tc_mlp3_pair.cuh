@@ -130,6 +130,14 @@ tc_mlp3_pair_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *_
 #define M3_WAIT() do { mbar_wait_guarded(done, ph); ph ^= 1; fence_after_sync(); } while (0)
         M3_SIGNAL();                                                               // stage 0 of the first tile
         for (int rnd = 0; rnd < rounds; ++rnd, tile += tile_stride) {
+            // reward and robot v_pref of this thread's (env, action): fetched before the first completion wait, so that the two
+            // global round trips are not left at the tail of the tile
+            const long long g_row = (long long)tile * ROWS + row;
+            double rew_g = 0.0, vp_g = v_pref_host;
+            if (hf == 0 && g_row < NG) {
+                rew_g = rew[g_row];
+                vp_g = st[st_idx(p.d, F_VPREF, 0, (int)(g_row / A))];
+            }
             M3_WAIT();
             if (warp == 4 * ctx && lane == 0) mbar_arrive(ctx ? xfree1 : xfree0);  // J is dead: the next J tile may land
             compact_to_tmem<true, true>(tl, hf * 80, 80, hf * 80, 1.0f);                 // U0, packed in place
@@ -169,12 +177,9 @@ tc_mlp3_pair_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *_
             else asm volatile("bar.sync 2, 256;" ::: "memory");
             if (hf == 0) {
                 const float v = part + S1[row] + tw.w[100];
-                const long long g = (long long)tile * ROWS + row;
-                if (g < NG) {
-                    const int e = (int)(g / A);
-                    const double vp = st[st_idx(p.d, F_VPREF, 0, e)];
-                    const double gamma_bar = (vp == v_pref_host) ? gamma_bar_host : pow(gamma, p.time_step * vp);
-                    values[g] = rew[g] + gamma_bar * (double)v;                   // multi_human_rl.py:52
+                if (g_row < NG) {
+                    const double gamma_bar = (vp_g == v_pref_host) ? gamma_bar_host : pow(gamma, p.time_step * vp_g);
+                    values[g_row] = rew_g + gamma_bar * (double)v;                // multi_human_rl.py:52
                 }
             }
             // S1 is rewritten only after the next tile's three completion waits, which every hf-0 reader precedes
