@@ -148,7 +148,7 @@ int cn_env_get_state(cn_env *env, double *agents_host, double *times_host, void 
 int cn_env_set_theta(cn_env *env, const double *theta_host, void *stream);
 int cn_env_get_theta(cn_env *env, double *theta_host, void *stream);
 /* CrowdSim.reset on the device (crowd_sim.py:165-217 distributions and rejection rule, Philox stream
- * keyed by (seed, global env id, episode counter)).  env_mask_dev: E bytes on the device, NULL = all. */
+ * keyed by (seed, global env id, episode counter)) for every env of the handle. */
 int cn_env_reset(cn_env *env, void *stream);
 
 /* Human ORCA actions for the current state: replaces the rvo2.PyRVOSimulator traffic of
@@ -218,6 +218,13 @@ int cn_policy_lookahead(cn_policy *p, cn_env *env, int query_env, double epsilon
 /* Blocking host read of the last lookahead: best_idx E int32, values E x A doubles (NULL to skip).
  * Returns CN_EVALUE when some env had no finite value (reference raises ValueError). */
 int cn_policy_read(cn_policy *p, cn_env *env, int32_t *best_idx, double *values, void *stream);
+/* Envs whose 81 action values were ALL non-finite since the handle was created (or since the last reset = 1 call): the
+ * reference raises ValueError('Value network is not well trained.') for such a state (multi_human_rl.py:57-58).  The
+ * blocking calls (cn_policy_read, cn_rollout_step_host, cn_rollout_step_host_packed) return CN_EVALUE themselves; the
+ * device-resident and async forms (cn_rollout_step, _sharded, _host_packed_async) substitute action 0 and keep going, so
+ * their callers poll this counter (blocking: one 4-byte D2H copy). */
+int cn_policy_bad_count(cn_policy *p, int64_t *count, int reset, void *stream);
+
 /* MultiHumanRL.transform (multi_human_rl.py:90-104) for every env: E x H x 13 fp32 into a DEVICE buffer. */
 int cn_policy_transform(cn_policy *p, cn_env *env, float *out_dev, void *stream);
 /* What predict() leaves in policy.last_state in the train phase (multi_human_rl.py:60-61): transform() of the state
@@ -273,6 +280,9 @@ int cn_selftest_umma(int32_t N, int32_t K, const float *a_host, const float *b_h
 /* Same product with the B operand read MN-major from an activation-style image (rows = K index, K <= 128):
  * the form the kernel uses to sum the attention-weighted features over the humans of a group. */
 int cn_selftest_umma_bmn(int32_t N, int32_t K, const float *a_host, const float *b_host, float *d_host, int device);
+/* Same product with the A operand read from TMEM (packed fp16, "TS" mode): the form in which an activation that was
+ * packed in place by an epilogue feeds the next layer without touching shared memory. */
+int cn_selftest_umma_ts(int32_t N, int32_t K, const float *a_host, const float *b_host, float *d_host, int device);
 
 /* CTA-pair building block (tcgen05 cta_group::2, M = 256 over the two SMs of a cluster, B split in N halves):
  * D[256 x N] = A[256 x K] * B[N x K]^T, repeated `reps` times; *cycles (optional) = clock64() ticks of the loop. */
@@ -282,13 +292,10 @@ int cn_selftest_umma_pair(int32_t N, int32_t K, const float *a_host, const float
 /* Developer diagnostic: clock64() at the phase boundaries of one tile of the tensor-core row kernel (CTA 0).
  * The first call arms the probes; call again after a lookahead to read 16 timestamps. */
 int cn_debug_tc_timing(cn_policy *p, long long *out16);
-/* Developer diagnostic: tcgen05.ld throughput of one SM (mode 0 = x32 pairs, 1 = x64, 2 = x16, 3 = x32 pairs + the
- * epilogue's convert / st.shared work); *cycles = clock64() ticks of the slowest of `nwarps` warps over `iters` loops. */
-int cn_debug_tmem_bench(int32_t mode, int32_t nwarps, int32_t iters, long long *cycles, int device);
-/* Developer diagnostic: the self-test product with a selectable operand mode (0 = A and B in shared memory,
- * 1 = B MN-major, 2 = A in TMEM), repeated `reps` times; *cycles = clock64() ticks of issue + commit + wait. */
-int cn_debug_umma_bench(int32_t N, int32_t K, int32_t mode, int32_t reps, const float *a_host, const float *b_host,
-                        float *d_host, long long *cycles, int device);
+/* Measurement hook (bench.py `roofline`): on = 1 makes every later tensor-core lookahead record CUDA events around its
+ * four kernels on the launching stream; out4 (optional) = durations of the LAST lookahead in ms {tc_features_kernel,
+ * tc_rows_pair_kernel, tc_mlp3_pair_kernel, argmax_kernel} (blocks on the last event). */
+int cn_debug_kernel_ms(cn_policy *p, int on, float *out4);
 
 #ifdef __cplusplus
 }

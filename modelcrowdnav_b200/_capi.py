@@ -7,8 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# CN_LIB_PATH: developer hook for A/B runs of differently compiled builds of the same library (never a fallback)
-LIB_PATH = os.environ.get("CN_LIB_PATH") or os.path.join(_HERE, "csrc", "libcrowdnav_b200.so")
+LIB_PATH = os.path.join(_HERE, "csrc", "libcrowdnav_b200.so")
 
 CN_OK, CN_EINVAL, CN_ECUDA, CN_ENOMEM, CN_EUNSUPPORTED, CN_EVALUE = 0, -1, -2, -3, -4, -5
 NOTHING, DANGER, REACHGOAL, COLLISION, TIMEOUT = 0, 1, 2, 3, 4
@@ -24,8 +23,8 @@ EXPORTS = [
     "cn_env_robot_orca", "cn_env_step", "cn_env_get_views", "cn_env_read_outputs", "cn_env_read_human_actions",
     "cn_env_read_next_obs", "cn_env_read_actions", "cn_env_set_actions", "cn_env_set_human_actions", "cn_env_read_stats", "cn_policy_create", "cn_policy_destroy",
     "cn_policy_param_count", "cn_policy_load_weights", "cn_policy_action_table", "cn_policy_lookahead",
-    "cn_policy_read", "cn_policy_transform", "cn_policy_last_state", "cn_policy_forward", "cn_rollout_step", "cn_rollout_step_sharded", "cn_rollout_step_host", "cn_rollout_step_host_packed", "cn_rollout_step_host_packed_async", "cn_stream_sync", "cn_host_step_bytes",
-    "cn_launch_count", "cn_debug_trace", "cn_debug_trace_dump", "cn_selftest_umma", "cn_selftest_umma_bmn", "cn_selftest_umma_pair", "cn_debug_tc_timing", "cn_debug_umma_bench", "cn_debug_tmem_bench",
+    "cn_policy_read", "cn_policy_bad_count", "cn_policy_transform", "cn_policy_last_state", "cn_policy_forward", "cn_rollout_step", "cn_rollout_step_sharded", "cn_rollout_step_host", "cn_rollout_step_host_packed", "cn_rollout_step_host_packed_async", "cn_stream_sync", "cn_host_step_bytes",
+    "cn_launch_count", "cn_debug_trace", "cn_debug_trace_dump", "cn_selftest_umma", "cn_selftest_umma_bmn", "cn_selftest_umma_ts", "cn_selftest_umma_pair", "cn_debug_tc_timing", "cn_debug_kernel_ms",
 ]
 
 
@@ -115,6 +114,7 @@ def load():
     L.cn_policy_action_table.argtypes = [vp, vp, C.POINTER(i32)]
     L.cn_policy_lookahead.argtypes = [vp, vp, C.c_int, dbl, vp]
     L.cn_policy_read.argtypes = [vp, vp, vp, vp, vp]
+    L.cn_policy_bad_count.argtypes = [vp, C.POINTER(i64), C.c_int, vp]
     L.cn_policy_transform.argtypes = [vp, vp, vp, vp]
     L.cn_policy_last_state.argtypes = [vp, vp, vp, vp]
     L.cn_policy_forward.argtypes = [vp, vp, i32, i32, vp, vp]
@@ -131,9 +131,9 @@ def load():
     L.cn_selftest_umma.argtypes = [i32, i32, vp, vp, vp, C.c_int]
     L.cn_selftest_umma_bmn.argtypes = [i32, i32, vp, vp, vp, C.c_int]
     L.cn_selftest_umma_pair.argtypes = [i32, i32, vp, vp, vp, i32, vp, C.c_int]
-    L.cn_debug_tmem_bench.argtypes = [i32, i32, i32, vp, C.c_int]
+    L.cn_selftest_umma_ts.argtypes = [i32, i32, vp, vp, vp, C.c_int]
     L.cn_debug_tc_timing.argtypes = [vp, vp]
-    L.cn_debug_umma_bench.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, C.c_int]
+    L.cn_debug_kernel_ms.argtypes = [vp, C.c_int, vp]
     _lib = L
     return L
 

@@ -185,6 +185,23 @@ class BatchedSARL(object):
         check(self.lib.cn_policy_read(self.handle, env.handle, _ptr(best), _ptr(vals), _stream(stream)))
         return best, vals
 
+    def bad_count(self, reset=False, stream=None):
+        """Envs whose action values were all non-finite so far (the reference's ValueError, multi_human_rl.py:57-58): the
+        device-resident / async rollout forms substitute action 0 and count here instead of raising."""
+        n = C.c_int64()
+        check(self.lib.cn_policy_bad_count(self.handle, C.byref(n), int(bool(reset)), _stream(stream)))
+        return int(n.value)
+
+    def kernel_timing(self, on=True):
+        """Measurement hook: CUDA events around the kernels of every later tensor-core lookahead (bench.py roofline)."""
+        check(self.lib.cn_debug_kernel_ms(self.handle, int(bool(on)), None))
+
+    def kernel_ms(self):
+        """ms of {features, rows, mlp3, argmax} kernels of the LAST lookahead (after kernel_timing(True)); blocks."""
+        out = (C.c_float * 4)()
+        check(self.lib.cn_debug_kernel_ms(self.handle, 1, out))
+        return dict(zip(("features", "rows", "mlp3", "argmax"), (float(x) for x in out)))
+
     def transform(self, env, stream=None, last_state=False):
         """MultiHumanRL.transform for every env -> torch CUDA tensor (E, H, 13) fp32.  last_state=True: what predict()
         leaves in policy.last_state (LSTM-RL: rows in its sorted human order, lstm_rl.py:99-104)."""

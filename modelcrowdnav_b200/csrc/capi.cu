@@ -8,7 +8,7 @@
 
 #include <vector>
 
-int64_t g_cn_launches = 0;
+std::atomic<int64_t> g_cn_launches{0};
 static thread_local char g_err[512] = "";
 
 void cn_set_error(const char *fmt, ...)
@@ -68,7 +68,7 @@ int cn_debug_trace_dump(char *buf, int64_t cap)
 
 const char *cn_last_error(void) { return g_err; }
 int cn_version(void) { return 100; }
-int64_t cn_launch_count(void) { return g_cn_launches; }
+int64_t cn_launch_count(void) { return g_cn_launches.load(); }
 
 int cn_device_count(void)
 {
@@ -527,6 +527,7 @@ int cn_policy_create(const cn_sarl_cfg *cfg, int device, cn_policy **out)
     if (cfg->precision != CN_PREC_F32 && cfg->precision != CN_PREC_F16_TC) { cn_set_error("unknown precision"); return CN_EINVAL; }
     int rc = use_device(device);
     if (rc) return rc;
+    if ((rc = cn_f32_configure_device())) return rc;
 
     cn_policy *p = new cn_policy();
     memset(p, 0, sizeof(*p));
@@ -559,13 +560,13 @@ int cn_policy_create(const cn_sarl_cfg *cfg, int device, cn_policy **out)
     cudaError_t e1 = cudaMalloc((void **)&p->action_dev, sizeof(double) * 2 * d.A);
     cudaError_t e2 = cudaMalloc((void **)&p->w_raw, sizeof(float) * p->n_params);
     cudaError_t e3 = cudaMalloc((void **)&p->w_t, sizeof(float) * tsize);
-    cudaError_t e4 = cudaMalloc((void **)&p->bad_flag, sizeof(int32_t));
+    cudaError_t e4 = cudaMalloc((void **)&p->bad_flag, 2 * sizeof(int32_t));
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
         cn_set_error("cudaMalloc failed in cn_policy_create");
         cn_policy_destroy(p);
         return CN_ENOMEM;
     }
-    cudaMemset(p->bad_flag, 0, sizeof(int32_t));
+    cudaMemset(p->bad_flag, 0, 2 * sizeof(int32_t));
     CN_CUDA_CHECK(cudaMemcpy(p->action_dev, p->action_host, sizeof(double) * 2 * d.A, cudaMemcpyHostToDevice));
     if (cfg->precision == CN_PREC_F16_TC) {
         rc = cn_tc_init(p);
@@ -717,6 +718,19 @@ int cn_policy_read(cn_policy *p, cn_env *env, int32_t *best_idx, double *values,
     return CN_OK;
 }
 
+int cn_policy_bad_count(cn_policy *p, int64_t *count, int reset, void *stream)
+{
+    if (!p || !count) { cn_set_error("null argument"); return CN_EINVAL; }
+    CN_CUDA_CHECK(cudaSetDevice(p->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int32_t n = 0;
+    CN_CUDA_CHECK(cudaMemcpyAsync(&n, p->bad_flag + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (reset) CN_CUDA_CHECK(cudaMemsetAsync(p->bad_flag + 1, 0, sizeof(int32_t), s));
+    CN_CUDA_CHECK(cudaStreamSynchronize(s));
+    *count = n;
+    return CN_OK;
+}
+
 int cn_policy_transform(cn_policy *p, cn_env *env, float *out_dev, void *stream)
 {
     if (!p || !env || !out_dev) { cn_set_error("null argument"); return CN_EINVAL; }
@@ -840,7 +854,10 @@ int cn_rollout_step_host(cn_policy *p, cn_env *env, int query_env, double epsilo
     if (done) CN_CUDA_CHECK(cudaMemcpyAsync(done, env->done, E, cudaMemcpyDeviceToHost, s));
     if (info) CN_CUDA_CHECK(cudaMemcpyAsync(info, env->info, E, cudaMemcpyDeviceToHost, s));
     if (action_idx) CN_CUDA_CHECK(cudaMemcpyAsync(action_idx, env->action_idx, sizeof(int32_t) * E, cudaMemcpyDeviceToHost, s));
+    int32_t bad = 0;
+    CN_CUDA_CHECK(cudaMemcpyAsync(&bad, p->bad_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     CN_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (bad) { cn_set_error("Value network is not well trained. "); return CN_EVALUE; }   // multi_human_rl.py:57-58
     return CN_OK;
 }
 
@@ -882,7 +899,12 @@ static int rollout_step_host_packed(cn_policy *p, cn_env *env, int query_env, do
         CN_CUDA_CHECK(cudaStreamWaitEvent(s0, env->ev_tail, 0));
         s = s0;
     }
-    if (sync) CN_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (sync) {
+        int32_t bad = 0;
+        CN_CUDA_CHECK(cudaMemcpyAsync(&bad, p->bad_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        CN_CUDA_CHECK(cudaStreamSynchronize(s));
+        if (bad) { cn_set_error("Value network is not well trained. "); return CN_EVALUE; }   // multi_human_rl.py:57-58
+    }
     return CN_OK;
 }
 

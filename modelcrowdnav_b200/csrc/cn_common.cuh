@@ -1,5 +1,6 @@
 // cn_common.cuh -- internal definitions shared by the kernels and the C ABI (sm_100a only).
 #pragma once
+#include <atomic>
 #include <stdlib.h>
 
 #include <cuda_runtime.h>
@@ -116,7 +117,8 @@ struct cn_policy {
     int weights_loaded;
     // lookahead outputs
     double *values;            // E x A
-    int32_t *bad_flag;         // 1 int: some env had no finite value
+    int32_t *bad_flag;         // [0]: some env of the LAST lookahead had no finite value (cleared per lookahead); [1]: sticky count
+                               // of such envs since the handle was created / cn_policy_bad_count(reset)
     int values_E;
     // tcgen05 path (lookahead_tc.cu)
     void *tc;                  // opaque, owned by the TC module
@@ -124,7 +126,7 @@ struct cn_policy {
 
 // ---- error plumbing --------------------------------------------------------------------------
 void cn_set_error(const char *fmt, ...);
-extern int64_t g_cn_launches;
+extern std::atomic<int64_t> g_cn_launches;
 
 #define CN_CUDA_CHECK(call)                                                                     \
     do {                                                                                        \
@@ -238,6 +240,7 @@ int cn_launch_stats_reduce(cn_env *env, cn_stats *out_dev_as_host, int reset, cu
 int cn_lookahead_f32(cn_policy *p, cn_env *env, int query_env, double epsilon, cudaStream_t s);
 int cn_transform_f32(cn_policy *p, cn_env *env, float *out_dev, int sort_humans, cudaStream_t s);
 int cn_forward_f32(cn_policy *p, const float *x_dev, int batch, int H, float *out_dev, cudaStream_t s);
+int cn_f32_configure_device(void);   // per-device kernel attributes (call after cudaSetDevice)
 
 int cn_tc_init(cn_policy *p);
 void cn_tc_destroy(cn_policy *p);

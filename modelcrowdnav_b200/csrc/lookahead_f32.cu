@@ -24,6 +24,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kRowsCap = 64;  // rows (action x human) per CTA
+constexpr size_t kMaxDynSmem = 232448;   // 227 KB: the opt-in dynamic shared memory limit of sm_100
 
 __host__ __device__ inline int pad4(int x) { return (x + 3) & ~3; }
 
@@ -449,7 +450,7 @@ argmax_kernel(EnvParams p, int A, const double *__restrict__ st, const uint8_t *
             step_ctr[e] += 1;
             if (rng.next() < epsilon) { best = min(A - 1, (int)(rng.next() * A)); random_pick = true; }
         }
-        if (!random_pick && best < 0) { atomicExch(bad_flag, 1); best = 0; }
+        if (!random_pick && best < 0) { atomicExch(bad_flag, 1); atomicAdd(bad_flag + 1, 1); best = 0; }   // [1]: sticky count
     }
     action_idx[e] = best;
     action_xy[e] = actions[2 * best];
@@ -575,6 +576,16 @@ int cn_lookahead_argmax(cn_policy *p, cn_env *env, double epsilon, cudaStream_t 
     return CN_OK;
 }
 
+// cudaFuncSetAttribute applies to the CURRENT device only: called from cn_policy_create after cudaSetDevice, so that every
+// device a policy handle lives on can launch the > 48 KB configurations (a process-wide "configured" flag would skip the
+// second device).
+int cn_f32_configure_device(void)
+{
+    CN_CUDA_CHECK(cudaFuncSetAttribute(lookahead_values_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    CN_CUDA_CHECK(cudaFuncSetAttribute(forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    return CN_OK;
+}
+
 int cn_lookahead_prepare(cn_policy *p, cn_env *env, cudaStream_t s)
 {
     int rc = ensure_values(p, env->p.d.E);
@@ -591,11 +602,7 @@ int cn_lookahead_f32(cn_policy *p, cn_env *env, int query_env, double epsilon, c
     if (rc) return rc;
     const F32Plan pl = make_plan(p->d, ed.H, p->d.A, ed.A1);
     const size_t smem = sizeof(float) * (size_t)pl.total_floats;
-    static size_t configured = 0;
-    if (smem > configured) {
-        CN_CUDA_CHECK(cudaFuncSetAttribute(lookahead_values_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (smem > kMaxDynSmem) { cn_set_error("FP32 lookahead needs %zu bytes of shared memory (layer widths too large)", smem); return CN_EUNSUPPORTED; }
     const double gamma_bar = pow(p->cfg.gamma, env->p.time_step * p->cfg.v_pref);
     dim3 grid(ed.E, (p->d.A + pl.CA - 1) / pl.CA);
     lookahead_values_kernel<<<grid, kThreads, smem, s>>>(env->p, p->w, p->d, pl, env->state, env->time, env->human_v,
@@ -608,7 +615,11 @@ int cn_lookahead_f32(cn_policy *p, cn_env *env, int query_env, double epsilon, c
 int cn_transform_f32(cn_policy *p, cn_env *env, float *out_dev, int sort_humans, cudaStream_t s)
 {
     const int n = env->p.d.E * env->p.d.H;
-    transform_kernel<<<(n + 127) / 128, 128, 0, s>>>(env->p, p->d, env->state, env->theta, out_dev, sort_humans);
+    // the heading feature follows the POLICY's kinematics (cadrl.py:236-240), not the env's robot dynamics: in imitation
+    // learning a holonomic ORCA robot drives the env while target_policy.transform() may be a unicycle SARL (explorer.py:163)
+    EnvParams ep = env->p;
+    ep.kinematics = p->cfg.kinematics;
+    transform_kernel<<<(n + 127) / 128, 128, 0, s>>>(ep, p->d, env->state, env->theta, out_dev, sort_humans);
     CN_LAUNCH_CHECK();
     return CN_OK;
 }
@@ -619,11 +630,7 @@ int cn_forward_f32(cn_policy *p, const float *x_dev, int batch, int H, float *ou
     if (batch <= 0) return CN_OK;
     const F32Plan pl = make_plan(p->d, H, batch, 1);
     const size_t smem = sizeof(float) * (size_t)pl.total_floats;
-    static size_t configured = 0;
-    if (smem > configured) {
-        CN_CUDA_CHECK(cudaFuncSetAttribute(forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (smem > kMaxDynSmem) { cn_set_error("FP32 forward needs %zu bytes of shared memory (layer widths too large)", smem); return CN_EUNSUPPORTED; }
     forward_kernel<<<(batch + pl.CA - 1) / pl.CA, kThreads, smem, s>>>(p->w, p->d, pl, x_dev, batch, out_dev);
     CN_LAUNCH_CHECK();
     return CN_OK;

@@ -434,7 +434,7 @@ __device__ __forceinline__ void epilogue_to_smem(uint32_t taddr_lane, int col, i
 // costs 2.5 % of the lookahead at EACH of the three places it was used (mlp1.0, attention.0, mlp3 hidden layers) although it
 // saves a tcgen05.ld round trip; a 48-column tail in one trip was 15 % slower still.  16-column pieces: +0.6 %, within noise.
 template <bool RELU, bool NO64 = false>
-__device__ __forceinline__ void compact_to_tmem(uint32_t tlane, int col_src, int ncols, int col_dst, float scale, bool ftz = false, int synth = 0)
+__device__ __forceinline__ void compact_to_tmem(uint32_t tlane, int col_src, int ncols, int col_dst, float scale)
 {
     int done = 0;
     while (!NO64 && ncols - done >= 64) {          // two TMEM loads in flight per wait (a load + wait round trip is ~290 cycles)
@@ -462,11 +462,8 @@ __device__ __forceinline__ void compact_to_tmem(uint32_t tlane, int col_src, int
         wait_ld();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
-            if (ftz) { a = fabsf(a) < 6.1035156e-5f ? 0.0f : a; b = fabsf(b) < 6.1035156e-5f ? 0.0f : b; }
+            const float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
             w[j] = RELU ? pack_f16x2_relu(a, b) : pack_f16x2(a * scale, b * scale);
-            if (synth == 1) w[j] = 0x3C003C00u;                                   // diagnostic: all ones
-            if (synth == 2) w[j] = pack_f16x2((float)((done + j) & 7) * 0.125f, 0.5f);   // diagnostic: smooth dense pattern
         }
         st16(tlane + col_dst + done / 2, w);
         done += 32;
@@ -477,8 +474,7 @@ __device__ __forceinline__ void compact_to_tmem(uint32_t tlane, int col_src, int
         wait_ld();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
-            if (ftz) { a = fabsf(a) < 6.1035156e-5f ? 0.0f : a; b = fabsf(b) < 6.1035156e-5f ? 0.0f : b; }
+            const float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
             w[j] = RELU ? pack_f16x2_relu(a, b) : pack_f16x2(a * scale, b * scale);
         }
         st8(tlane + col_dst + done / 2, w);

@@ -1,9 +1,20 @@
 """Value-network trainer: mirror of crowd_nav/utils/trainer.py:19-82 (MSE, SGD momentum 0.9, batch 100).
 
-PyTorch autograd does the training (the north star keeps torch "for tensor handoff and training").  Batches are
-drawn directly from the device-resident replay tensors instead of a DataLoader over Python tuples; with
-`torch.distributed` initialised the gradients are all-reduced as ONE flat bucket (96,502 fp32 = 386 kB, latency
-bound) and averaged -- the data-parallel equivalent of the reference's single-process SGD step.
+Batches are drawn directly from the device-resident replay tensors instead of a DataLoader over Python tuples.
+Three execution forms of the same optimisation step (MSE -> backward -> [gradient all-reduce] -> SGD momentum):
+
+* ``fused``  (CUDA, SARL value network): the hand-written forward / backward kernel + SGD kernel of the C ABI
+  (``cn_trainer_*``, csrc/trainer.cu) working on ONE flat fp32 parameter block that the torch model's parameters are
+  views of; the gradient all-reduce (NCCL, one 386 kB bucket) sits between the two kernels.
+* ``graph``  (CUDA, any network): torch autograd captured once per batch shape into a CUDA graph and replayed.
+* ``eager``  (CPU / gloo tests, odd batch sizes): plain torch autograd.
+
+No form synchronises with the host per batch: the loss is accumulated on the device and read once per
+``optimize_*`` call (the reference's ``loss.data.item()`` per batch, trainer.py:54,76, is a host sync per step).
+
+Data parallel: replay buffers stay rank-local, gradients are averaged over ranks, so every rank must
+run the SAME number of steps per call: the step count comes from the LARGEST ``len(memory)`` over the ranks and short
+ranks wrap around their own buffer.
 """
 import logging
 
@@ -13,7 +24,7 @@ import torch.optim as optim
 
 
 class Trainer(object):
-    def __init__(self, model, memory, device, batch_size, dist_group=None, policy=None):
+    def __init__(self, model, memory, device, batch_size, dist_group=None, policy=None, mode=None):
         self.model = model
         self.device = device
         self.criterion = nn.MSELoss().to(device)
@@ -23,14 +34,50 @@ class Trainer(object):
         self.optimizer = None
         self.dist_group = dist_group
         self.policy = policy             # SARL façade whose GPU lookahead weights are refreshed after training
-        self._flat = None
+        self.lr = None
+        self.momentum = 0.9
+        is_cuda = torch.device(device).type == "cuda"
+        self.mode = mode or ("graph" if is_cuda else "eager")
+        assert self.mode in ("eager", "graph", "fused")
+        if self.mode != "eager" and not is_cuda:
+            raise ValueError("Trainer mode %r needs a CUDA device" % self.mode)
+        self._graphs = {}                # (B, state shape) -> (CUDAGraph, x, y, loss)
+        self._fused = None
+        self._loss_sum = None
 
     def set_learning_rate(self, learning_rate):
         logging.info("Current learning rate: %f", learning_rate)
-        self.optimizer = optim.SGD(self.model.parameters(), lr=learning_rate, momentum=0.9)
+        self.lr = float(learning_rate)
+        if self.mode == "fused":
+            from .fused_trainer import FusedSarlTrainer
+            if self._fused is None:
+                self._fused = FusedSarlTrainer(self.model, self.device, momentum=self.momentum)
+            self._fused.lr = self.lr
+            self.optimizer = self._fused          # "Learning rate is not set!" check below
+            return
+        self.optimizer = optim.SGD(self.model.parameters(), lr=learning_rate, momentum=self.momentum)
+        self._graphs.clear()                      # captured graphs hold the old optimiser's buffers
 
-    # -- gradient all-reduce over NVLink (one flat bucket) ----------------------------------------------
+    # -- data-parallel plumbing ---------------------------------------------------------------------
+    def _world(self):
+        if self.dist_group is None:
+            return 1
+        import torch.distributed as dist
+        return dist.get_world_size(self.dist_group)
+
+    def _common_len(self):
+        """len(memory) every rank iterates over: the maximum over the ranks (one tiny all-reduce per optimize_* call)."""
+        n = len(self.memory)
+        if self.dist_group is None:
+            return n
+        import torch.distributed as dist
+        dev = self.device if dist.get_backend(self.dist_group) == "nccl" else "cpu"
+        t = torch.tensor([n], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.dist_group)
+        return int(t.item())
+
     def _sync_gradients(self):
+        """Average the gradients over the ranks as ONE flat bucket (96,502 fp32 = 386 kB: latency bound)."""
         if self.dist_group is None:
             return
         import torch.distributed as dist
@@ -52,33 +99,92 @@ class Trainer(object):
         for p in self.model.parameters():
             dist.broadcast(p.data, src=src, group=self.dist_group)
 
-    def _step(self, idx):
-        inputs = self.memory.states[idx].to(self.device)
-        values = self.memory.values[idx].to(self.device)
+    # -- one optimisation step ------------------------------------------------------------------------
+    def _eager_step(self, inputs, values):
         self.optimizer.zero_grad()
         outputs = self.model(inputs)
         loss = self.criterion(outputs, values)
         loss.backward()
         self._sync_gradients()
         self.optimizer.step()
-        return loss.data.item()
+        return loss.detach()
+
+    def _graph_step(self, inputs, values):
+        key = (tuple(inputs.shape), tuple(values.shape))
+        g = self._graphs.get(key)
+        if g is None:
+            x, y = inputs.clone(), values.clone()
+            # warm-up on a side stream (allocates the gradients and the momentum buffers), restoring the weights after
+            saved = [p.detach().clone() for p in self.model.parameters()]
+            s = torch.cuda.Stream(device=self.device)
+            s.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    self.optimizer.zero_grad(set_to_none=False)
+                    loss = self.criterion(self.model(x), y)
+                    loss.backward()
+                    self.optimizer.step()
+            torch.cuda.current_stream(self.device).wait_stream(s)
+            with torch.no_grad():
+                for p, q in zip(self.model.parameters(), saved):
+                    p.copy_(q)
+                for st in self.optimizer.state.values():
+                    if "momentum_buffer" in st and st["momentum_buffer"] is not None:
+                        st["momentum_buffer"].zero_()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self.optimizer.zero_grad(set_to_none=False)
+                loss = self.criterion(self.model(x), y)
+                loss.backward()
+                self._sync_gradients()
+                self.optimizer.step()
+            # SGD's first step copies the gradient into the momentum buffer (buf = grad) and later ones do
+            # buf = mu * buf + grad; with the buffers zeroed above the captured "later" form covers both.
+            g = self._graphs[key] = (graph, x, y, loss)
+        graph, x, y, loss = g
+        x.copy_(inputs); y.copy_(values)
+        graph.replay()
+        return loss
+
+    def _step_tensors(self, inputs, values):
+        if self.mode == "fused":
+            return self._fused.step(inputs, values, self.dist_group)
+        if self.mode == "graph" and inputs.shape[0] == self.batch_size:
+            return self._graph_step(inputs, values)
+        return self._eager_step(inputs, values)
+
+    def _step(self, idx):
+        """One SGD step on memory[idx]; returns the loss as a 0-d device tensor (no host sync)."""
+        inputs = self.memory.states[idx].to(self.device)
+        values = self.memory.values[idx].to(self.device)
+        return self._step_tensors(inputs, values)
 
     def _after(self):
+        if self._fused is not None:
+            self._fused.flush_to_model()
         if self.policy is not None:
             self.policy.sync_weights()
 
+    # -- the reference entry points ---------------------------------------------------------------------
     def optimize_epoch(self, num_epochs):
         """trainer.py:36-59: num_epochs passes over a shuffled memory."""
         if self.optimizer is None:
             raise ValueError("Learning rate is not set!")
-        n = len(self.memory)
+        n_local = len(self.memory)
+        n = self._common_len()
+        if n_local == 0:
+            raise ValueError("optimize_epoch on an empty replay memory")
+        mdev = self.memory.states.device
         average_epoch_loss = 0
         for _ in range(num_epochs):
-            epoch_loss = 0
-            perm = torch.randperm(n, device=self.memory.states.device)
+            epoch_loss = torch.zeros((), dtype=torch.float32, device=self.device)
+            perm = torch.randperm(n, device=mdev)
+            if n != n_local:
+                perm = perm % n_local            # short ranks wrap around: same number of steps (and collectives) everywhere
             for s in range(0, n, self.batch_size):
-                epoch_loss += self._step(perm[s:s + self.batch_size])
-            average_epoch_loss = epoch_loss / n
+                epoch_loss += self._step(perm[s:s + self.batch_size]).to(self.device)
+            average_epoch_loss = float(epoch_loss.item()) / n
+            logging.debug("Average loss in epoch : %.2E", average_epoch_loss)
         self._after()
         return average_epoch_loss
 
@@ -87,11 +193,17 @@ class Trainer(object):
         if self.optimizer is None:
             raise ValueError("Learning rate is not set!")
         n = len(self.memory)
-        losses = 0
-        for _ in range(num_batches):
-            idx = torch.randperm(n, device=self.memory.states.device)[:self.batch_size]
-            losses += self._step(idx)
-        average_loss = losses / num_batches
+        if n == 0:
+            raise ValueError("optimize_batch on an empty replay memory")
+        mdev = self.memory.states.device
+        losses = torch.zeros((), dtype=torch.float32, device=self.device)
+        b = min(self.batch_size, n)
+        # one (num_batches, b) index matrix: row i = the head of an independent uniform shuffle of the memory
+        idx = torch.rand((num_batches, n), device=mdev).topk(b, dim=1).indices if n <= 4096 else \
+            torch.stack([torch.randperm(n, device=mdev)[:b] for _ in range(num_batches)])
+        for i in range(num_batches):
+            losses += self._step(idx[i]).to(self.device)
+        average_loss = float(losses.item()) / num_batches
         logging.debug("Average loss : %.2E", average_loss)
         self._after()
         return average_loss

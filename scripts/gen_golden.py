@@ -395,6 +395,137 @@ def gen_episodes(n_proc, wpath=None, tag="seed0", kinematics="holonomic"):
     return k
 
 
+# Decisive argmax sets: ALL 500 test cases teacher-forced by the reference with the trained SARL weights
+# (|V| up to ~2, top-2 gaps far above the fp16 noise), a 1-in-`every` sample of the visited states recorded per case.
+# name, H, sim, query_env, every
+DECISIVE_SPECS = [
+    ("circle5_qfalse", 5, "circle_crossing", False, 3),
+    ("circle5_qtrue", 5, "circle_crossing", True, 6),
+    ("square10_qfalse", 10, "square_crossing", False, 6),
+]
+
+
+def run_decisive_chunk(args):
+    lo, hi, H, sim, qenv, wpath, every = args
+    import torch
+    torch.set_num_threads(1)
+    env, robot, policy = refshim.make_env_and_sarl(human_num=H, sim=sim, query_env=qenv, seed=0, weights=np.load(wpath))
+    rows = []
+    for case in range(lo, hi):
+        ob = env.reset("test", case)
+        done, t = False, 0
+        while not done:
+            agents, gtime = agents_of(env), env.global_time
+            action = robot.act(ob)
+            if t % every == case % every:
+                table = np.array([action_pair(a) for a in policy.action_space])
+                ap = action_pair(action)
+                best = int(np.argmin(np.abs(table[:, 0] - ap[0]) + np.abs(table[:, 1] - ap[1])))
+                rows.append((case, t, agents, gtime, np.array(policy.action_values, dtype=np.float64), best))
+            ob, reward, done, info = env.step(action)
+            t += 1
+    return rows
+
+
+def gen_decisive(n_proc, only=None):
+    import multiprocessing as mp
+    wpath = os.path.join(GOLD, "sarl_weights_trained.npy")
+    for name, H, sim, qenv, every in DECISIVE_SPECS:
+        if only and name not in only:
+            continue
+        chunks = [(lo, min(lo + 5, 500), H, sim, qenv, wpath, every) for lo in range(0, 500, 5)]
+        t0 = time.time()
+        with mp.get_context("fork").Pool(n_proc) as pool:
+            rows = sum(pool.map(run_decisive_chunk, chunks), [])
+        rows.sort(key=lambda r: (r[0], r[1]))
+        values = np.array([r[4] for r in rows])
+        top2 = np.sort(values, axis=1)[:, -2:]
+        np.savez_compressed(os.path.join(GOLD, "decisive_%s.npz" % name),
+                            case=np.array([r[0] for r in rows], np.int16), step=np.array([r[1] for r in rows], np.int16),
+                            agents=np.array([r[2] for r in rows]), time=np.array([r[3] for r in rows]),
+                            values=values.astype(np.float32), gap=(top2[:, 1] - top2[:, 0]),
+                            best=np.array([r[5] for r in rows], np.int16), H=np.array(H), sim=np.array(sim),
+                            query_env=np.array(int(qenv)), weights=np.array("sarl_weights_trained.npy"))
+        print("decisive_%s.npz: %d states of 500 cases, %d with top-2 gap > 2e-4 (%.0fs, %d procs)" % (
+            name, len(rows), int(((top2[:, 1] - top2[:, 0]) > 2e-4).sum()), time.time() - t0, n_proc))
+
+
+
+def gen_training():
+    """Replay filling and SGD of the reference (explorer.py:153-186, trainer.py:61-82) -> tests/golden/training.npz.
+
+    il_*: Explorer.run_k_episodes(8, 'train', update_memory=True, imitation_learning=True) with the ORCA robot
+    (safety_space 0.15) and the seed-0 SARL as target_policy (train.py:157-169): the memory it leaves behind.
+    rl_*: the same call with the trained SARL driving the robot (epsilon 0, so no random draws) and a copy of it as the
+    target model: value_i = r_i + gamma_bar * V_target(s_{i+1}).
+    sgd_*: the reference Trainer.optimize_batch(100) on the IL memory from the seed-0 network, lr 0.01, batch 100, with the
+    100 index batches its DataLoader drew on record, and the weights after the 100 steps."""
+    refshim.install()
+    import torch
+    from crowd_nav.utils.explorer import Explorer
+    from crowd_nav.utils.memory import ReplayMemory
+    from crowd_nav.utils.trainer import Trainer
+    from crowd_sim.envs.policy.policy_factory import policy_factory as sim_policy_factory
+    out = {}
+    torch.set_num_threads(1)
+
+    def dump(memory, tag):
+        out[tag + "_states"] = torch.stack([m[0] for m in memory.memory]).numpy()
+        out[tag + "_values"] = torch.stack([m[1] for m in memory.memory]).numpy().reshape(-1)
+
+    # ---- imitation learning ----
+    env, robot, policy = refshim.make_env_and_sarl(seed=0)
+    memory = ReplayMemory(100000)
+    explorer = Explorer(env, robot, torch.device("cpu"), memory, policy.gamma, target_policy=policy)
+    il_policy = sim_policy_factory["orca"]()
+    il_policy.multiagent_training = policy.multiagent_training
+    il_policy.safety_space = 0.15
+    robot.set_policy(il_policy)
+    res = explorer.run_k_episodes(8, "train", update_memory=True, imitation_learning=True)
+    dump(memory, "il")
+    out["il_result"] = np.array(res, dtype=np.float64)
+    print("IL memory: %d states, result %s" % (len(memory), res))
+
+    # ---- SGD on the IL memory (reference Trainer, batches on record) ----
+    class RecordingMemory(ReplayMemory):
+        def __init__(self, src):
+            super().__init__(src.capacity)
+            self.memory, self.position, self.log = list(src.memory), src.position, []
+
+        def __getitem__(self, item):
+            self.log.append(int(item))
+            return self.memory[item]
+
+    rec = RecordingMemory(memory)
+    torch.manual_seed(0)
+    _, _, fresh = refshim.make_env_and_sarl(seed=0)
+    model = fresh.get_model()
+    w0 = np.concatenate([v.numpy().ravel() for v in model.state_dict().values()]).astype(np.float32)
+    assert np.array_equal(w0, np.load(os.path.join(GOLD, "sarl_weights_seed0.npy")))
+    trainer = Trainer(model, rec, torch.device("cpu"), 100)
+    trainer.set_learning_rate(0.01)
+    torch.manual_seed(123)
+    loss = trainer.optimize_batch(100)
+    idx = np.array(rec.log, dtype=np.int32).reshape(100, 100)
+    out["sgd_idx"] = idx
+    out["sgd_loss"] = np.array(loss)
+    out["sgd_weights"] = np.concatenate([v.numpy().ravel() for v in model.state_dict().values()]).astype(np.float32)
+    print("SGD: average loss %.3e, |w - w0| max %.3e" % (loss, np.abs(out["sgd_weights"] - w0).max()))
+
+    # ---- reinforcement learning targets ----
+    wtr = np.load(os.path.join(GOLD, "sarl_weights_trained.npy"))
+    env, robot, policy = refshim.make_env_and_sarl(seed=0, weights=wtr)
+    memory = ReplayMemory(100000)
+    explorer = Explorer(env, robot, torch.device("cpu"), memory, policy.gamma, target_policy=policy)
+    explorer.update_target_model(policy.get_model())
+    policy.set_epsilon(0.0)
+    res = explorer.run_k_episodes(8, "train", update_memory=True, episode=0, returnRate=False)
+    dump(memory, "rl")
+    out["rl_result"] = np.array(res, dtype=np.float64)
+    print("RL memory: %d states, result %s" % (len(memory), res))
+    np.savez_compressed(os.path.join(GOLD, "training.npz"), **out)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--episodes", action="store_true")
@@ -407,13 +538,19 @@ if __name__ == "__main__":
     ap.add_argument("--mixed", action="store_true", help="only the 'mixed' scene fixtures and trajectories")
     ap.add_argument("--om", action="store_true", help="only the occupancy-map (with_om) unit vectors and trajectories")
     ap.add_argument("--nets", action="store_true", help="only the CADRL / LSTM-RL unit vectors and trajectories")
+    ap.add_argument("--training", action="store_true", help="only the replay-filling / SGD fixtures (explorer.update_memory, Trainer)")
+    ap.add_argument("--decisive", action="store_true", help="only the 500-case trained-weight argmax sets (minutes per set)")
     ap.add_argument("--trained", action="store_true", help="use tests/golden/sarl_weights_trained.npy (GPU-trained SARL)")
     a = ap.parse_args()
     wtrained = os.path.join(GOLD, "sarl_weights_trained.npy")
     assert refshim.available(), "/root/reference is required"
     os.makedirs(GOLD, exist_ok=True)
     oracle.build()
-    if a.episodes and a.kin_none:
+    if a.training:
+        gen_training()
+    elif a.decisive:
+        gen_decisive(a.procs, os.environ.get("GOLDEN_ONLY"))
+    elif a.episodes and a.kin_none:
         gen_episodes(a.procs, wtrained if a.trained else None, "kin_none_" + ("trained" if a.trained else "seed0"), None)
     elif a.episodes:
         gen_episodes(a.procs, wtrained if a.trained else None, "trained" if a.trained else "seed0")

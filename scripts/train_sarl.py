@@ -14,7 +14,6 @@ NCCL -- never anything inside the env step / lookahead.
   python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 scripts/train_sarl.py ...
 """
 import argparse
-import configparser
 import logging
 import os
 import sys
@@ -26,32 +25,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import modelcrowdnav_b200 as mcn  # noqa: E402
-from modelcrowdnav_b200.trainer import Trainer  # noqa: E402
 
-ENV_DEFAULT = dict(env=dict(time_limit=25, time_step=0.25, val_size=100, test_size=500, randomize_attributes="false"),
-                   reward=dict(success_reward=1, collision_penalty=-0.25, discomfort_dist=0.2,
-                               discomfort_penalty_factor=0.5),
-                   sim=dict(train_val_sim="circle_crossing", test_sim="circle_crossing", square_width=10,
-                            circle_radius=4, human_num=5),
-                   humans=dict(visible="true", policy="orca", radius=0.3, v_pref=1, sensor="coordinates"),
-                   robot=dict(visible="false", policy="none", radius=0.3, v_pref=1, sensor="coordinates"))
-POLICY_DEFAULT = dict(rl=dict(gamma=0.9), om=dict(cell_num=4, cell_size=1, om_channel_size=3),
-                      action_space=dict(kinematics="holonomic", speed_samples=5, rotation_samples=16,
-                                        sampling="exponential", query_env="false"),
-                      sarl=dict(mlp1_dims="150, 100", mlp2_dims="100, 50", attention_dims="100, 100, 1",
-                                mlp3_dims="150, 100, 100, 1", multiagent_training="true", with_om="false",
-                                with_global_state="true"),
-                      cadrl=dict(mlp_dims="150, 100, 100, 1", multiagent_training="false"),
-                      lstm_rl=dict(global_state_dim=50, mlp1_dims="150, 100, 100, 50", mlp2_dims="150, 100, 100, 1",
-                                   multiagent_training="true", with_om="false", with_interaction_module="false"))
-
-
-def make_config(default, path=None):
-    cp = configparser.RawConfigParser()
-    cp.read_dict({k: {kk: str(vv) for kk, vv in v.items()} for k, v in default.items()})
-    if path:
-        cp.read(path)
-    return cp
+from modelcrowdnav_b200.train_loop import TrainingLoop  # noqa: E402
 
 
 def main():
@@ -77,6 +52,7 @@ def main():
     ap.add_argument("--policy", default="sarl", choices=["sarl", "cadrl", "lstm_rl"])    # train.py --policy
     ap.add_argument("--precision", default="f16_tc")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--trainer", default="graph", choices=["eager", "graph", "fused"])
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -94,77 +70,42 @@ def main():
     logging.basicConfig(level=logging.INFO if rank == 0 else logging.WARNING,
                         format="%(asctime)s, %(levelname)s: %(message)s", datefmt="%Y-%m-%d %H:%M:%S")
 
-    env_config, policy_config = make_config(ENV_DEFAULT, a.env_config), make_config(POLICY_DEFAULT, a.policy_config)
-    torch.manual_seed(a.seed)
-    policy = mcn.policy_factory[a.policy]()
-    policy.configure(policy_config)
-    if a.policy == "sarl" and not policy.with_om:
-        policy.precision = a.precision            # CADRL, LSTM-RL and occupancy maps run on the FP32 path
-    policy.set_device(device)
-    env = mcn.CrowdSim()
-    env.configure(env_config)
-    env.device = local
-    robot = mcn.Robot(env_config, "robot")
-    env.set_robot(robot)
-    # shard the case ids: rank r starts r * sample_episodes into the case list and strides by world
-    env.case_counter["train"] = rank * a.sample_episodes
-    memory = mcn.ReplayMemory(a.capacity)
-    model = policy.get_model()
-    trainer = Trainer(model, memory, device, a.batch_size, dist_group=group, policy=policy)
-    trainer.broadcast_weights()
-    explorer = mcn.Explorer(env, robot, device, memory, policy.gamma, target_policy=policy, dist_group=group)
-    env.case_size["train"] = np.iinfo(np.uint32).max - 2000       # upstream CrowdNav value (the fork shrank it to 100)
+    loop = TrainingLoop(device, rank, world, group, policy_name=a.policy, precision=a.precision, seed=a.seed,
+                        env_config=a.env_config, policy_config=a.policy_config, capacity=a.capacity,
+                        batch_size=a.batch_size, trainer_mode=a.trainer, sample_episodes=a.sample_episodes)
+    env, policy, model, explorer, memory = loop.env, loop.policy, loop.model, loop.explorer, loop.memory
 
-    # ---- imitation learning (train.py:144-178) ----
+    # ---- imitation learning (train.py:144-178): rank r demonstrates cases [r * per_rank, (r + 1) * per_rank) ----
     t0 = time.time()
-    il_policy = mcn.policy_factory["orca"]()
-    il_policy.multiagent_training = policy.multiagent_training
-    il_policy.safety_space = a.safety_space
-    il_policy.set_device(device)
-    robot.set_policy(il_policy)
-    per_rank = (a.il_episodes + world - 1) // world
-    explorer.run_k_episodes(per_rank, "train", update_memory=True, imitation_learning=True)
-    trainer.set_learning_rate(a.il_learning_rate)
-    loss = trainer.optimize_epoch(a.il_epochs)
+    loss = loop.imitation_learning(a.il_episodes, a.il_epochs, a.il_learning_rate, a.safety_space)
     logging.info("Imitation learning: %d experiences (rank 0), final epoch loss %.3e, %.1f s", len(memory), loss,
                  time.time() - t0)
     if rank == 0:
         torch.save(model.state_dict(), os.path.join(a.output_dir, "il_model.pth"))
-    explorer.update_target_model(model)
 
-    # ---- reinforcement learning (train.py:180-246) ----
-    robot.set_policy(policy)
-    policy.set_env(env)
-    trainer.set_learning_rate(a.rl_learning_rate)
-    episode = 0
-    steps_done, t_roll = 0, 0.0
-    while episode < a.train_episodes:
+    # ---- reinforcement learning (train.py:180-246): iteration i, rank r rolls out its own block of sample_episodes cases ----
+    loop.start_rl(a.rl_learning_rate)
+    timers = {}
+    while loop.iteration < a.train_episodes:
+        episode = loop.iteration
         eps = (a.epsilon_start + (a.epsilon_end - a.epsilon_start) / a.epsilon_decay * episode
                if episode < a.epsilon_decay else a.epsilon_end)
-        policy.set_epsilon(eps)
         if episode % a.evaluation_interval == 0:
             env.case_counter["val"] = rank * (env.case_size["val"] // world)
             explorer.run_k_episodes(env.case_size["val"] // world, "val", episode=episode)
-        t1 = time.time()
-        env.case_counter["train"] += (world - 1) * a.sample_episodes       # skip the other ranks' cases
-        explorer.run_k_episodes(a.sample_episodes, "train", update_memory=True, episode=episode)
-        t_roll += time.time() - t1
-        steps_done += int(explorer.last_run["steps"].sum())
-        trainer.optimize_batch(a.train_batches)
-        episode += 1
-        if episode % a.target_update_interval == 0:
-            explorer.update_target_model(model)
-        if rank == 0 and episode % 50 == 0:
+        loop.rl_iteration(eps, a.train_batches, a.target_update_interval, timers=timers)
+        if rank == 0 and loop.iteration % 50 == 0:
             torch.save(model.state_dict(), os.path.join(a.output_dir, "rl_model.pth"))
     if rank == 0:
         torch.save(model.state_dict(), os.path.join(a.output_dir, "rl_model.pth"))
         np.save(os.path.join(a.output_dir, "rl_model_flat.npy"), policy.flat_weights())
     # ---- final test (train.py:249) ----
     env.case_counter["test"] = rank * (env.case_size["test"] // world)
-    out = explorer.run_k_episodes(env.case_size["test"] // world, "test", episode=episode, returnNav=True)
+    out = explorer.run_k_episodes(env.case_size["test"] // world, "test", episode=loop.iteration, returnNav=True)
     if rank == 0:
         logging.info("rollout env-steps/s (rank 0, train phase incl. replay filling): %.0f",
-                     steps_done / max(t_roll, 1e-9))
+                     loop.env_steps / max(timers.get("rollout_and_targets", 0.0), 1e-9))
+        logging.info("seconds per phase over %d iterations: %s", loop.iteration, {k: round(v, 2) for k, v in timers.items()})
         logging.info("final test: reward %.4f success %.3f collision %.3f timeout %.3f nav %.2f", *out)
     if world > 1:
         import torch.distributed as dist

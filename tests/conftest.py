@@ -97,3 +97,49 @@ def weights_for(name):
     """seed-0 random init for the plain fixtures, the GPU-trained SARL (scripts/train_sarl.py) for *_trained."""
     f = "sarl_weights_trained.npy" if name.endswith("trained") else "sarl_weights_seed0.npy"
     return np.load(os.path.join(GOLDEN, f))
+
+
+# ---- parity bars (north star): values within 1e-3 RELATIVE for the fp16 tensor-core path (1e-5 for the FP32 twin), argmax
+# identical on >= 99.9 % of the states that are not ties ------------------------------------------------------------------
+VALUE_RTOL = {"f32": 1e-5, "f16_tc": 1e-3}
+# |delta| <= rtol * max(|v|, VALUE_FLOOR): values live in [-0.25, 1] (rewards) + gamma * V, so below 10 % of the success
+# reward the bound stops shrinking (1e-4 absolute for f16_tc, 1e-6 for f32) -- a value of exactly 0 has no relative error
+VALUE_FLOOR = 0.1
+TIE_GAP = {"f32": 2e-5, "f16_tc": 2e-4}      # reference top-2 gaps below this are ties (excluded from argmax agreement)
+
+
+def value_errors(got, ref, precision):
+    """max over the array of |got - ref| / (rtol * max(|ref|, floor)); <= 1 passes.  NaN in either side fails."""
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    bound = VALUE_RTOL[precision] * np.maximum(np.abs(ref), VALUE_FLOOR)
+    r = np.abs(got - ref) / bound
+    return float(np.max(np.where(np.isnan(r), np.inf, r))) if r.size else 0.0
+
+
+def decidable(ref_values, precision):
+    """mask of states whose reference top-2 gap exceeds the tie threshold (ref_values: (..., A))"""
+    top2 = np.sort(np.asarray(ref_values, np.float64), axis=-1)[..., -2:]
+    return (top2[..., 1] - top2[..., 0]) > TIE_GAP[precision]
+
+
+def check_argmax(best, ref_best, ref_values, precision, min_decidable):
+    """>= 99.9 % agreement on the decidable states AND at least `min_decidable` of them (a vacuous pass is a failure)."""
+    m = decidable(ref_values, precision)
+    total = int(m.sum())
+    agree = int((np.asarray(best)[m] == np.asarray(ref_best)[m]).sum())
+    assert total >= min_decidable, "only %d decidable states (need %d): the argmax bar would be vacuous" % (total, min_decidable)
+    assert agree >= 0.999 * total, "argmax agreement %d / %d = %.4f < 0.999" % (agree, total, agree / max(total, 1))
+    return agree, total
+
+
+DECISIVE_NAMES = ["circle5_qfalse", "circle5_qtrue", "square10_qfalse"]
+
+
+def load_decisive(name):
+    z = np.load(os.path.join(GOLDEN, "decisive_%s.npz" % name), allow_pickle=False)
+    return {k: (z[k] if z[k].shape else z[k].item()) for k in z.files}
+
+
+@pytest.fixture(scope="session")
+def weights_trained():
+    return np.load(os.path.join(GOLDEN, "sarl_weights_trained.npy"))

@@ -85,6 +85,32 @@ def test_gradient_allreduce_equals_single_process(tmp_path):
     assert ref.size == 96502
 
 
+def _epoch_rank(rank, world):
+    """optimize_epoch with UNEQUAL replay sizes per rank (rank-local buffers keep only success / collision episodes)."""
+    from modelcrowdnav_b200.trainer import Trainer
+    torch.set_num_threads(1)
+    model = _make_model()
+    states, values = _data(330)
+    n = 130 if rank == 0 else 330          # ceil(130 / 100) = 2 steps vs ceil(330 / 100) = 4 steps if left unsynchronised
+    tr = Trainer(model, _Mem(states[:n], values[:n]), torch.device("cpu"), 100, dist_group=dist.group.WORLD)
+    tr.broadcast_weights()
+    tr.set_learning_rate(0.01)
+    calls = []
+    orig = tr._sync_gradients
+    tr._sync_gradients = lambda: (calls.append(1), orig())[1]
+    loss = tr.optimize_epoch(2)
+    w = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).numpy()
+    return np.concatenate([[len(calls), loss], w])
+
+
+def test_optimize_epoch_unequal_memory_sizes(tmp_path):
+    """every rank must issue the same number of gradient all-reduces per epoch, or NCCL hangs."""
+    res = _run(_epoch_rank, tmp_path)
+    assert res[0][0] == res[1][0] == 2 * 4                      # 2 epochs x ceil(max(130, 330) / 100) steps on BOTH ranks
+    assert np.array_equal(res[0][2:], res[1][2:])               # replicas stay in lock-step
+    assert np.isfinite(res[0][1]) and np.isfinite(res[1][1])
+
+
 def _stats_rank(rank, world):
     from modelcrowdnav_b200.explorer import Explorer
     ex = Explorer(None, None, torch.device("cpu"), dist_group=dist.group.WORLD)
@@ -108,6 +134,29 @@ def test_shards_are_disjoint_and_cover_all_cases():
     for r in range(world):
         shard = scenes.generate_batch("test", range(r * E, (r + 1) * E))
         assert np.array_equal(shard, full[r * E:(r + 1) * E])
+
+
+def test_training_case_shards_are_disjoint():
+    """imitation-learning demonstrations and RL roll-outs of different ranks never share a case id, for any
+    world size (rank r demonstrates [r * per_rank, (r + 1) * per_rank); RL iteration i continues from a common base)."""
+    from modelcrowdnav_b200.train_loop import shard_cases
+    for world in (1, 2, 3, 8):
+        il_episodes, k = 500, 64
+        per_rank = (il_episodes + world - 1) // world
+        seen = set()
+        for r in range(world):
+            cases = set(range(r * per_rank, (r + 1) * per_rank))
+            assert not (cases & seen)
+            seen |= cases
+        base = world * per_rank
+        assert max(seen) < base
+        for it in range(5):
+            for r in range(world):
+                first = shard_cases(base, it, world, r, k)
+                cases = set(range(first, first + k))
+                assert not (cases & seen), (world, it, r)
+                seen |= cases
+        assert seen == set(range(base + 5 * world * k))       # no holes either
 
 
 def test_product_scene_generator_matches_reference_fixture(oracle_mod):

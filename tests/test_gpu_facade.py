@@ -469,3 +469,78 @@ def test_explorer_over_model_crowd_sim(weights0):
     finally:
         np.random.set_state(state)
     assert same >= k - 2, same
+
+
+def _training_golden():
+    return dict(np.load(os.path.join(GOLDEN, "training.npz"), allow_pickle=False))
+
+
+def test_update_memory_il_matches_reference(weights0):
+    """Explorer.update_memory, imitation learning (explorer.py:153-166): the replay memory after 8 ORCA-robot episodes equals
+    the one the REFERENCE's Explorer left behind for the same cases (tests/golden/training.npz, gen_golden.py --training):
+    transformed states and discounted returns-to-go, entry by entry."""
+    import torch
+    import modelcrowdnav_b200 as mcn
+    g = _training_golden()
+    env, robot, policy, _ = _setup(weights0)
+    il_policy = mcn.policy_factory["orca"]()
+    il_policy.multiagent_training = policy.multiagent_training
+    il_policy.safety_space = 0.15
+    robot.set_policy(il_policy)
+    memory = mcn.ReplayMemory(100000)
+    explorer = mcn.Explorer(env, robot, torch.device("cuda:0"), memory, 0.9, target_policy=policy)
+    res = explorer.run_k_episodes(8, "train", update_memory=True, imitation_learning=True)
+    assert len(memory) == g["il_states"].shape[0]
+    s = memory.states[:len(memory)].cpu().numpy()
+    v = memory.values[:len(memory)].cpu().numpy().reshape(-1)
+    assert np.max(np.abs(s - g["il_states"])) < 5e-6                  # fp32 rotate: atan2 / cos / sin of two libms
+    assert np.max(np.abs(v - g["il_values"])) < 1e-6
+    assert np.allclose(np.array(res, dtype=np.float64), g["il_result"], rtol=0, atol=1e-9)
+
+
+def test_update_memory_rl_matches_reference():
+    """Explorer.update_memory, reinforcement learning (explorer.py:167-174): value_i = r_i + gamma_bar * V_target(s_{i+1}),
+    terminal = r, for the 8 'train' episodes the reference rolled out with the trained SARL (epsilon 0)."""
+    import torch
+    import modelcrowdnav_b200 as mcn
+    g = _training_golden()
+    env, robot, policy, _ = _setup(np.load(os.path.join(GOLDEN, "sarl_weights_trained.npy")))
+    memory = mcn.ReplayMemory(100000)
+    explorer = mcn.Explorer(env, robot, torch.device("cuda:0"), memory, 0.9, target_policy=policy)
+    explorer.update_target_model(policy.get_model())
+    policy.set_epsilon(0.0)
+    res = explorer.run_k_episodes(8, "train", update_memory=True, episode=0, returnRate=False)
+    assert len(memory) == g["rl_states"].shape[0]
+    s = memory.states[:len(memory)].cpu().numpy()
+    v = memory.values[:len(memory)].cpu().numpy().reshape(-1)
+    assert np.max(np.abs(s - g["rl_states"])) < 5e-6
+    assert np.max(np.abs(v - g["rl_values"]) / np.maximum(np.abs(g["rl_values"]), 0.1)) < 1e-5
+    assert np.allclose(np.array(res, dtype=np.float64), g["rl_result"], rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("mode", ["eager", "graph", "fused"])
+def test_trainer_matches_reference_sgd(weights0, mode):
+    """Trainer (trainer.py:61-82): 100 SGD-momentum steps (lr 0.01, batch 100, MSE) on the batches the REFERENCE's DataLoader
+    drew, from the same seed-0 network -> the reference's weights after the 100 steps, <= 1e-5."""
+    import torch
+    import modelcrowdnav_b200 as mcn
+    from modelcrowdnav_b200.policy import make_value_network
+    from modelcrowdnav_b200.trainer import Trainer
+    g = _training_golden()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    model = make_value_network(13, 6, [150, 100], [100, 50], [150, 100, 100, 1], [100, 100, 1]).to(dev)
+    flat0 = torch.cat([p.detach().reshape(-1) for p in model.state_dict().values()]).cpu().numpy()
+    assert np.array_equal(flat0, weights0)
+    memory = mcn.ReplayMemory(100000, device=dev)
+    memory.push_batch(torch.from_numpy(g["il_states"]).to(dev), torch.from_numpy(g["il_values"]).to(dev))
+    tr = Trainer(model, memory, dev, 100, mode=mode)
+    tr.set_learning_rate(0.01)
+    idx = torch.from_numpy(g["sgd_idx"].astype(np.int64)).to(dev)
+    loss = 0.0
+    for i in range(idx.shape[0]):
+        loss += float(tr._step(idx[i]))
+    tr._after()
+    flat = torch.cat([p.detach().reshape(-1) for p in model.state_dict().values()]).cpu().numpy()
+    assert abs(loss / idx.shape[0] - float(g["sgd_loss"])) < 1e-5
+    assert np.max(np.abs(flat - g["sgd_weights"])) <= 1e-5, np.max(np.abs(flat - g["sgd_weights"]))

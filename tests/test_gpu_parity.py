@@ -2,12 +2,22 @@
 import numpy as np
 import pytest
 
-from conftest import TRAJ_NAMES, TRAJ_NAMES_KIN, TRAJ_NAMES_MIXED, TRAJ_NAMES_NETS, TRAJ_NAMES_OM, load_traj, net_tag, weights_for
+from conftest import (TIE_GAP, TRAJ_NAMES, TRAJ_NAMES_KIN, TRAJ_NAMES_MIXED, TRAJ_NAMES_NETS, TRAJ_NAMES_OM, check_argmax,
+                      load_traj, net_tag, value_errors, weights_for)
 
 pytestmark = pytest.mark.gpu
 
-VALUE_TOL = {"f32": 1e-5, "f16_tc": 1e-3}   # relative to max(1, |v|) (north star: 1e-3 relative)
-TIE_GAP = {"f32": 2e-5, "f16_tc": 2e-4}      # top-2 gaps below this are ties (excluded from argmax agreement)
+
+def check_choice(best, ref_best, ref_values, precision, min_decidable=0):
+    """The two argmax bars of every lookahead test.  (1) On the DECIDABLE states (reference top-2 gap above the tie
+    threshold) the action index matches on >= 99.9 %, and there are at least `min_decidable` such states.  (2) On EVERY
+    state, decidable or not, the chosen action is optimal under the REFERENCE's values up to the tie threshold -- never
+    vacuous, even for random-init weights whose 81 values lie within 1e-4 of each other."""
+    ref_values = np.asarray(ref_values, np.float64)
+    best = np.asarray(best)
+    check_argmax(best, ref_best, ref_values, precision, min_decidable)
+    regret = ref_values.max(axis=1) - ref_values[np.arange(len(best)), best]
+    assert np.all(regret <= TIE_GAP[precision]), "chosen action worse than the reference optimum by %.3g" % regret.max()
 
 
 @pytest.fixture(scope="module")
@@ -116,20 +126,16 @@ def test_golden_trajectories(mcn, oracle_mod, weights0, name, precision):
     acts = np.stack([rec["action"][t] for rec, t in recs])
     reward, done, info, dmin = env.step(acts, update=True)
     got, gt = env.get_state()
-    tol = VALUE_TOL[precision]
-    agree = total = 0
     for e, (rec, t) in enumerate(recs):
         assert np.array_equal(hv[e], rec["human_v"][t]), (name, e)
-        ref_v = rec["values"][t]
-        assert np.max(np.abs(values[e] - ref_v)) <= tol * max(1.0, np.max(np.abs(ref_v))), (name, e)
-        top2 = np.sort(ref_v)[-2:]
-        if top2[1] - top2[0] > TIE_GAP[precision]:                                     # ties excluded
-            total += 1
-            agree += int(best[e] == rec["best"][t])
+        assert value_errors(values[e], rec["values"][t], precision) <= 1.0, (name, e)
         assert (reward[e], bool(done[e]), int(info[e])) == (rec["reward"][t], bool(rec["done"][t]), int(rec["info"][t]))
         if t + 1 < len(rec["time"]):
             assert np.array_equal(got[e], rec["agents"][t + 1]) and gt[e] == rec["time"][t + 1]
-    assert total == 0 or agree / total >= 0.999, (agree, total)
+    ref_values = np.stack([rec["values"][t] for rec, t in recs])
+    # the trained-weight fixtures must decide (>= 70 % of their states have a clear winner); seed-0 weights barely do
+    check_choice(best, [rec["best"][t] for rec, t in recs], ref_values, precision,
+                 min_decidable=int(0.7 * E) if name.endswith("trained") else 0)
     env.close(); pol.close()
 
 
@@ -148,24 +154,20 @@ def test_lookahead_vs_oracle(mcn, oracle_mod, weights0, H, rule, query_env, prec
     pol.load_weights(weights0)
     agents = _scenes(o, E, H, rule, phase="val")
     env.set_state(agents)
-    tol = VALUE_TOL[precision]
-    agree = total = 0
     for step in range(6):
         env.orca()
         pol.lookahead(env, query_env=query_env)
         best, values = pol.read(env)
         hv = env.human_actions()
         state, times = env.get_state()
+        obests, ovalues = [], []
         for e in range(E):
             obest, ovals, reached = o.lookahead(ecfg, scfg, weights0, state[e], times[e], pol.action_table,
                                                 query_env, hv[e])
-            assert np.max(np.abs(values[e] - ovals)) <= tol * max(1.0, np.max(np.abs(ovals))), (step, e)
-            top2 = np.sort(ovals)[-2:]
-            if top2[1] - top2[0] > TIE_GAP[precision]:
-                total += 1
-                agree += int(best[e] == obest)
+            assert value_errors(values[e], ovals, precision) <= 1.0, (step, e)
+            obests.append(obest); ovalues.append(ovals)
+        check_choice(best, obests, np.stack(ovalues), precision)
         env.step(update=True, read=False)      # advance with the GPU's own chosen actions
-    assert total == 0 or agree / total >= 0.999, (agree, total)
     env.close(); pol.close()
 
 
@@ -200,7 +202,7 @@ def test_transform_and_forward(mcn, oracle_mod, weights0, units):
         x = torch.from_numpy(units["vnet_in_h%d" % H]).cuda()
         v = pol.forward(x).cpu().numpy()
         ref = units["vnet_out_h%d" % H]
-        assert np.max(np.abs(v - ref)) <= 1e-5 * max(1.0, np.max(np.abs(ref)))
+        assert value_errors(v, ref, "f32") <= 1.0
     E, H = 32, 5
     env = mcn.BatchedCrowdSim(E, H)
     agents = _scenes(o, E, H)
@@ -342,7 +344,8 @@ def test_host_step_matches_device_step(mcn, oracle_mod, weights0):
 
 
 @pytest.mark.parametrize("N,K,bmn", [(16, 16, 0), (64, 112, 0), (112, 112, 0), (160, 32, 0), (112, 224, 0), (160, 80, 0),
-                                     (256, 64, 0), (64, 128, 1), (112, 128, 1), (16, 16, 1), (64, 48, 1)])
+                                     (256, 64, 0), (64, 128, 1), (112, 128, 1), (16, 16, 1), (64, 48, 1),
+                                     (112, 160, 2), (112, 112, 2), (64, 32, 2)])
 def test_umma_selftest(mcn, N, K, bmn):
     """tcgen05.mma building block (descriptor / chunked K-major layout / TMEM read-back) vs fp32 matmul."""
     import ctypes as C
@@ -351,7 +354,7 @@ def test_umma_selftest(mcn, N, K, bmn):
     b = rs.uniform(-1, 1, (N, K)).astype(np.float16).astype(np.float32)
     d = np.zeros((128, N), np.float32)
     lib = mcn._capi.load()
-    fn = lib.cn_selftest_umma_bmn if bmn else lib.cn_selftest_umma
+    fn = {0: lib.cn_selftest_umma, 1: lib.cn_selftest_umma_bmn, 2: lib.cn_selftest_umma_ts}[bmn]   # SS, MN-major B, A in TMEM
     mcn._capi.check(fn(N, K, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
                                          d.ctypes.data_as(C.c_void_p), 0))
     ref = a.astype(np.float64) @ b.astype(np.float64).T
@@ -406,18 +409,14 @@ def test_tc_matches_f32_odd_shapes(mcn, weights0, E, H, speeds, rots):
     p32.load_weights(weights0); p16.load_weights(weights0)
     assert p16.A == speeds * rots + 1
     env.reset_device()
-    agree = total = 0
     for step in range(4):
         env.orca()
         p32.lookahead(env, 0); b32, v32 = p32.read(env)
         p16.lookahead(env, 0); b16, v16 = p16.read(env)
         assert v16.shape == (E, p16.A)
-        assert np.max(np.abs(v32 - v16)) <= 1e-3 * max(1.0, np.max(np.abs(v32)))
-        srt = np.sort(v32, axis=1)
-        clear = (srt[:, -1] - srt[:, -2]) > 2e-4
-        total += int(clear.sum()); agree += int((b32[clear] == b16[clear]).sum())
+        assert value_errors(v16, v32, "f16_tc") <= 1.0
+        check_choice(b16, b32, v32, "f16_tc")
         env.step(update=True, read=False)
-    assert total == 0 or agree / total >= 0.999, (agree, total)
     env.close(); p32.close(); p16.close()
 
 
@@ -515,22 +514,15 @@ def test_golden_trajectories_kinematics(mcn, weights0, name, precision):
     reward, done, info, dmin = env.step(acts, update=True)
     got, gt = env.get_state()
     th = env.get_theta()
-    tol = VALUE_TOL[precision]
-    agree = total = 0
     for e, (rec, t) in enumerate(recs):
         assert np.array_equal(hv[e], rec["human_v"][t]), (name, e)
-        ref_v = rec["values"][t]
-        assert np.max(np.abs(values[e] - ref_v)) <= tol * max(1.0, np.max(np.abs(ref_v))), (name, e)
-        top2 = np.sort(ref_v)[-2:]
-        if top2[1] - top2[0] > TIE_GAP[precision]:
-            total += 1
-            agree += int(best[e] == rec["best"][t])
+        assert value_errors(values[e], rec["values"][t], precision) <= 1.0, (name, e)
         assert (reward[e], bool(done[e]), int(info[e])) == (rec["reward"][t], bool(rec["done"][t]), int(rec["info"][t]))
         if t + 1 < len(rec["time"]):
             assert np.allclose(got[e], rec["agents"][t + 1], rtol=0, atol=1e-12) and gt[e] == rec["time"][t + 1]
             assert np.array_equal(got[e][1:], rec["agents"][t + 1][1:])    # humans never touch cos / sin: bit-exact
             assert abs(th[e] - rec["theta"][t + 1]) <= 1e-12
-    assert total == 0 or agree / total >= 0.999, (agree, total)
+    check_choice(best, [rec["best"][t] for rec, t in recs], np.stack([rec["values"][t] for rec, t in recs]), precision)
     env.close(); pol.close()
 
 
@@ -557,7 +549,7 @@ def test_other_value_networks_forward(mcn, units_nets, tag):
         x, ref = units_nets["%s_in_h%d" % (tag, H)], units_nets["%s_out_h%d" % (tag, H)]
         got = pol.forward(torch.from_numpy(x).cuda()).cpu().numpy()
         want = ref.min(axis=1) if tag == "cadrl" else ref
-        assert np.max(np.abs(got - want)) <= 1e-5 * max(1.0, np.max(np.abs(want)))
+        assert value_errors(got, want, "f32") <= 1.0
     with pytest.raises(mcn.CrowdNavError):
         mcn.BatchedSARL(precision="f16_tc", network="cadrl")           # FP32 path only, no silent fallback
     pol.close()
@@ -592,7 +584,7 @@ def test_golden_trajectories_other_networks(mcn, oracle_mod, units_nets, name):
     agree = total = 0
     for e, (rec, t) in enumerate(recs):
         ref_v = rec["values"][t]
-        assert np.max(np.abs(values[e] - ref_v)) <= 1e-5 * max(1.0, np.max(np.abs(ref_v))), (name, e)
+        assert value_errors(values[e], ref_v, "f32") <= 1.0, (name, e)
         top2 = np.sort(ref_v)[-2:]
         if top2[1] - top2[0] > 2e-5:
             total += 1
@@ -677,7 +669,7 @@ def test_golden_trajectories_with_occupancy_maps(mcn, units_om, name):
     agree = total = 0
     for e, (rec, t) in enumerate(recs):
         ref_v = rec["values"][t]
-        assert np.max(np.abs(values[e] - ref_v)) <= 1e-5 * max(1.0, np.max(np.abs(ref_v))), (name, e)
+        assert value_errors(values[e], ref_v, "f32") <= 1.0, (name, e)
         top2 = np.sort(ref_v)[-2:]
         if top2[1] - top2[0] > 2e-5:
             total += 1
@@ -742,7 +734,7 @@ def test_tc_large_groups_vs_oracle(mcn, oracle_mod, weights0, H):
         cur, times = env.get_state()
         for e in range(E):
             obest, ovals, _ = o.lookahead(ecfg, scfg, weights0, cur[e], times[e], p16.action_table, False, hv[e])
-            assert np.max(np.abs(v32[e] - ovals)) <= 1e-5 * max(1.0, np.max(np.abs(ovals)))
-            assert np.max(np.abs(v16[e] - ovals)) <= 1e-3 * max(1.0, np.max(np.abs(ovals)))
+            assert value_errors(v32[e], ovals, "f32") <= 1.0
+            assert value_errors(v16[e], ovals, "f16_tc") <= 1.0
         env.step(update=True, read=False)
     env.close(); p16.close(); p32.close()
