@@ -156,37 +156,37 @@ def make_value_network(input_dim, self_state_dim, mlp1_dims, mlp2_dims, mlp3_dim
     import torch.nn as nn
 
     class ValueNetwork(nn.Module):
+        """Parameter container (state-dict keys mlp1.* mlp2.* attention.* mlp3.*) + the autograd form of the network the
+        CUDA kernels evaluate; all layers act on the last axis of (batch, humans, features) tensors."""
+
         def __init__(self):
             super().__init__()
             self.self_state_dim = self_state_dim
             self.global_state_dim = mlp1_dims[-1]
+            self.with_global_state = with_global_state
             self.mlp1 = mlp(input_dim, mlp1_dims, last_relu=True)
             self.mlp2 = mlp(mlp1_dims[-1], mlp2_dims)
-            self.with_global_state = with_global_state
-            self.attention = mlp(mlp1_dims[-1] * 2 if with_global_state else mlp1_dims[-1], attention_dims)
+            self.attention = mlp(mlp1_dims[-1] * (2 if with_global_state else 1), attention_dims)
             self.mlp3 = mlp(mlp2_dims[-1] + self_state_dim, mlp3_dims)
-            self.attention_weights = None
+            self._attn = None
+
+        @property
+        def attention_weights(self):
+            """softmax weights of the first sample of the last forward (sarl.py:54), fetched from the device on demand --
+            the reference copies them to the host inside every forward, i.e. one sync per training step."""
+            return None if self._attn is None else self._attn.cpu().numpy()
 
         def forward(self, state):
-            size = state.shape
-            self_state = state[:, 0, :self.self_state_dim]
-            mlp1_output = self.mlp1(state.reshape((-1, size[2])))
-            mlp2_output = self.mlp2(mlp1_output)
-            if self.with_global_state:
-                global_state = torch.mean(mlp1_output.view(size[0], size[1], -1), 1, keepdim=True)
-                global_state = global_state.expand((size[0], size[1], self.global_state_dim)).contiguous().view(
-                    -1, self.global_state_dim)
-                attention_input = torch.cat([mlp1_output, global_state], dim=1)
-            else:
-                attention_input = mlp1_output
-            scores = self.attention(attention_input).view(size[0], size[1], 1).squeeze(dim=2)
-            scores_exp = torch.exp(scores) * (scores != 0).float()
-            weights = (scores_exp / torch.sum(scores_exp, dim=1, keepdim=True)).unsqueeze(2)
-            self.attention_weights = weights[0, :, 0].data.cpu().numpy()
-            features = mlp2_output.view(size[0], size[1], -1)
-            weighted_feature = torch.sum(torch.mul(weights, features), dim=1)
-            joint_state = torch.cat([self_state, weighted_feature], dim=1)
-            return self.mlp3(joint_state)
+            embed = self.mlp1(state)                                   # (B, H, 100): per-human embedding e_i
+            feat = self.mlp2(embed)                                    # (B, H, 50):  pairwise feature h_i
+            if self.with_global_state:                                 # attention sees [e_i, mean_k e_k]
+                embed = torch.cat([embed, embed.mean(dim=1, keepdim=True).expand_as(embed)], dim=2)
+            score = self.attention(embed).squeeze(2)                   # (B, H)
+            w = torch.exp(score) * (score != 0)                        # un-stabilised softmax, exact zeros masked (sarl.py:52)
+            w = w / w.sum(dim=1, keepdim=True)
+            self._attn = w[0].detach()
+            crowd = (w.unsqueeze(2) * feat).sum(dim=1)                 # (B, 50)
+            return self.mlp3(torch.cat([state[:, 0, :self.self_state_dim], crowd], dim=1))
 
     return ValueNetwork()
 

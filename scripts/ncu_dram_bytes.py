@@ -3,6 +3,7 @@
 them into profiles/ncu_dram_bytes.json (read by bench.py for `roofline.traffic`).
 Usage: python scripts/ncu_dram_bytes.py gpurun_out/prof.ncu-rep f16_tc:8192:5 profiles/<summary file the numbers come from>"""
 import csv
+import re
 import io
 import json
 import os
@@ -23,7 +24,8 @@ def to_bytes(x, unit):
 
 per = {}
 for r in rows[2:]:
-    name = r[ki].split("(")[0].split("<")[0].strip()
+    m = re.search(r"(\w+_kernel)", r[ki])
+    name = m.group(1) if m else r[ki]
     per.setdefault(name, []).append(to_bytes(r[ri], U[ri]) + to_bytes(r[wi], U[wi]))
 out = {k: sum(v) / len(v) for k, v in per.items()}          # mean over the captured launches of each kernel
 out["source"] = source
