@@ -292,6 +292,27 @@ int cn_selftest_umma_pair(int32_t N, int32_t K, const float *a_host, const float
 /* Developer diagnostic: clock64() at the phase boundaries of one tile of the tensor-core row kernel (CTA 0).
  * The first call arms the probes; call again after a lookahead to read 16 timestamps. */
 int cn_debug_tc_timing(cn_policy *p, long long *out16);
+/* ---- value-network training step on the device (crowd_nav/utils/trainer.py:36-82) ------------------------------------
+ * One optimisation step of the reference Trainer -- zero_grad, model(inputs), MSELoss, backward, SGD(momentum).step -- as
+ * two kernels on ONE flat fp32 parameter block in torch state-dict order (the block cn_policy_load_weights takes; the
+ * torch model's parameters may be views of it).  SARL value network without occupancy maps.
+ * cn_trainer_step: states_dev batch x human_num x input_dim fp32, targets_dev batch fp32 (device pointers).
+ *   grad_out_dev == NULL : w_dev is updated in place (buf = momentum * buf + grad; w -= lr * buf), loss_dev (optional)
+ *                          receives the batch MSE.
+ *   grad_out_dev != NULL : only the gradient of the batch MSE is written (n_params fp32); the caller all-reduces it over
+ *                          the ranks (NCCL) and calls cn_trainer_apply(grad, 1 / world) -- the data-parallel step.
+ * cn_trainer_sync_weights: call after w_dev was changed by anyone else (load_state_dict, broadcast): refreshes the
+ *   transposed copy the forward pass reads; zero_momentum = 1 also resets the momentum buffer (a new optimiser). */
+typedef struct cn_trainer cn_trainer;
+int cn_trainer_create(const cn_sarl_cfg *cfg, int device, int32_t max_batch, int32_t max_humans, cn_trainer **out);
+int cn_trainer_destroy(cn_trainer *t);
+int64_t cn_trainer_param_count(const cn_trainer *t);
+int cn_trainer_sync_weights(cn_trainer *t, const float *w_dev, int zero_momentum, void *stream);
+int cn_trainer_step(cn_trainer *t, float *w_dev, const float *states_dev, const float *targets_dev, int32_t batch,
+                    int32_t human_num, float lr, float momentum, float *grad_out_dev, float *loss_dev, void *stream);
+int cn_trainer_apply(cn_trainer *t, float *w_dev, const float *grad_dev, float grad_scale, float lr, float momentum,
+                     void *stream);
+
 /* Measurement hook (bench.py `roofline`): on = 1 makes every later tensor-core lookahead record CUDA events around its
  * four kernels on the launching stream; out4 (optional) = durations of the LAST lookahead in ms {tc_features_kernel,
  * tc_rows_pair_kernel, tc_mlp3_pair_kernel, argmax_kernel} (blocks on the last event). */

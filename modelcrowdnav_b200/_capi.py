@@ -24,6 +24,7 @@ EXPORTS = [
     "cn_env_read_next_obs", "cn_env_read_actions", "cn_env_set_actions", "cn_env_set_human_actions", "cn_env_read_stats", "cn_policy_create", "cn_policy_destroy",
     "cn_policy_param_count", "cn_policy_load_weights", "cn_policy_action_table", "cn_policy_lookahead",
     "cn_policy_read", "cn_policy_bad_count", "cn_policy_transform", "cn_policy_last_state", "cn_policy_forward", "cn_rollout_step", "cn_rollout_step_sharded", "cn_rollout_step_host", "cn_rollout_step_host_packed", "cn_rollout_step_host_packed_async", "cn_stream_sync", "cn_host_step_bytes",
+    "cn_trainer_create", "cn_trainer_destroy", "cn_trainer_param_count", "cn_trainer_sync_weights", "cn_trainer_step", "cn_trainer_apply",
     "cn_launch_count", "cn_debug_trace", "cn_debug_trace_dump", "cn_selftest_umma", "cn_selftest_umma_bmn", "cn_selftest_umma_ts", "cn_selftest_umma_pair", "cn_debug_tc_timing", "cn_debug_kernel_ms",
 ]
 
@@ -125,6 +126,13 @@ def load():
     L.cn_rollout_step_host_packed_async.argtypes = [vp, vp, C.c_int, dbl, vp, vp, vp]
     L.cn_stream_sync.argtypes = [C.c_int, vp]
     L.cn_host_step_bytes.argtypes = [vp, C.c_int]
+    L.cn_trainer_create.argtypes = [C.POINTER(SarlCfg), C.c_int, i32, i32, C.POINTER(vp)]
+    L.cn_trainer_destroy.argtypes = [vp]
+    L.cn_trainer_param_count.argtypes = [vp]
+    L.cn_trainer_param_count.restype = i64
+    L.cn_trainer_sync_weights.argtypes = [vp, vp, C.c_int, vp]
+    L.cn_trainer_step.argtypes = [vp, vp, vp, vp, i32, i32, C.c_float, C.c_float, vp, vp, vp]
+    L.cn_trainer_apply.argtypes = [vp, vp, vp, C.c_float, C.c_float, C.c_float, vp]
     L.cn_debug_trace.argtypes = [C.c_int]
     L.cn_debug_trace_dump.argtypes = [C.c_char_p, i64]
     L.cn_host_step_bytes.restype = i64

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""GPU diagnostic: fp16 tensor-core lookahead vs the FP32 CUDA-core lookahead on the same evolving states.
-Prints max |dV|, and argmax agreement as a function of the excluded top-2 gap. Needs a B200."""
+"""Accuracy of the fp16 tensor-core lookahead against the REFERENCE's values on the decisive sets (tests/golden/decisive_*.npz,
+trained weights): percentiles of |dv| and of |dv| / max(|v|, 0.1), worst state, argmax agreement on decidable states.
+Usage: python scripts/tc_error_stats.py [lib.so]"""
 import os
 import sys
 
@@ -8,35 +9,38 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+if len(sys.argv) > 1:
+    from modelcrowdnav_b200 import _capi
+    _capi.LIB_PATH = os.path.abspath(sys.argv[1])
 import modelcrowdnav_b200 as mcn  # noqa: E402
+from conftest import DECISIVE_NAMES, load_decisive  # noqa: E402
 
-
-def main(E=2048, H=5, steps=40, weights=None, query_env=0):
-    w = np.load(weights or os.path.join(ROOT, "tests", "golden", "sarl_weights_seed0.npy"))
-    env = mcn.BatchedCrowdSim(E, H, auto_reset=1, seed=11)
-    p32 = mcn.BatchedSARL(precision="f32"); p32.load_weights(w)
-    p16 = mcn.BatchedSARL(precision="f16_tc"); p16.load_weights(w)
-    env.reset_device()
-    gaps = [0, 1e-5, 5e-5, 1e-4, 2e-4, 5e-4, 1e-3]
-    tot = np.zeros(len(gaps)); agr = np.zeros(len(gaps))
-    maxerr = 0.0; maxrel = 0.0; vmax = 0.0
-    for s in range(steps):
+w = np.load(os.path.join(ROOT, "tests", "golden", "sarl_weights_trained.npy"))
+for prec in ("f32", "f16_tc"):
+    for name in DECISIVE_NAMES:
+        d = load_decisive(name)
+        N, H = d["agents"].shape[0], int(d["H"])
+        env = mcn.BatchedCrowdSim(N, H)
+        pol = mcn.BatchedSARL(precision=prec)
+        pol.load_weights(w)
+        env.set_state(d["agents"], d["time"])
         env.orca()
-        p32.lookahead(env, query_env); b32, v32 = p32.read(env)
-        p16.lookahead(env, query_env); b16, v16 = p16.read(env)
-        err = np.abs(v32 - v16)
-        maxerr = max(maxerr, err.max()); vmax = max(vmax, np.abs(v32).max())
-        maxrel = max(maxrel, (err.max(1) / np.maximum(1.0, np.abs(v32).max(1))).max())
-        srt = np.sort(v32, axis=1)
-        gap = srt[:, -1] - srt[:, -2]
-        for i, g in enumerate(gaps):
-            m = gap > g
-            tot[i] += m.sum(); agr[i] += (b32[m] == b16[m]).sum()
-        env.step(update=True, read=False)        # continue with the fp16 path's actions
-    print("E=%d H=%d steps=%d  max|dV|=%.3g  max rel=%.3g  max|V|=%.3g" % (E, H, steps, maxerr, maxrel, vmax))
-    for g, t, a in zip(gaps, tot, agr):
-        print("  gap > %-7g states %7d  argmax agreement %.5f" % (g, t, a / max(t, 1)))
-
-
-if __name__ == "__main__":
-    main(weights=sys.argv[1] if len(sys.argv) > 1 else None)
+        pol.lookahead(env, query_env=int(d["query_env"]))
+        best, values = pol.read(env)
+        ref = d["values"].astype(np.float64)
+        dv = np.abs(values - ref)
+        rel = dv / np.maximum(np.abs(ref), 0.1)
+        relstate = dv.max(1) / np.maximum(np.abs(ref).max(1), 0.1)
+        top2 = np.sort(ref, axis=1)[:, -2:]
+        gap = top2[:, 1] - top2[:, 0]
+        line = "%-6s %-16s N=%d |dv| rms %.2e p99 %.2e p99.9 %.2e max %.2e | rel(floor .1) p99 %.2e p99.9 %.2e p99.99 %.2e max %.2e | per-state inf-norm rel max %.2e" % (
+            prec, name, N, np.sqrt((dv ** 2).mean()), np.percentile(dv, 99), np.percentile(dv, 99.9), dv.max(),
+            np.percentile(rel, 99), np.percentile(rel, 99.9), np.percentile(rel, 99.99), rel.max(), relstate.max())
+        for thr in (2e-4, 5e-4, 1e-3):
+            m = gap > thr
+            line += " | gap>%.0e: %d/%d" % (thr, int((best[m] == d["best"][m]).sum()), int(m.sum()))
+        regret = ref.max(1) - ref[np.arange(N), best]
+        line += " | regret max %.2e" % regret.max()
+        print(line, flush=True)
+        env.close(); pol.close()

@@ -544,3 +544,42 @@ def test_trainer_matches_reference_sgd(weights0, mode):
     flat = torch.cat([p.detach().reshape(-1) for p in model.state_dict().values()]).cpu().numpy()
     assert abs(loss / idx.shape[0] - float(g["sgd_loss"])) < 1e-5
     assert np.max(np.abs(flat - g["sgd_weights"])) <= 1e-5, np.max(np.abs(flat - g["sgd_weights"]))
+
+
+@pytest.mark.parametrize("B,H", [(100, 5), (37, 10), (1, 1), (64, 3)])
+def test_fused_trainer_gradient_matches_autograd(weights0, B, H):
+    """csrc/trainer.cu (forward + hand-written backward of sarl.py:28-65 with MSELoss) against torch autograd on the same
+    batch: loss and every one of the 96,502 gradient entries."""
+    import ctypes as C
+    import torch
+    from modelcrowdnav_b200.fused_trainer import FusedSarlTrainer
+    from modelcrowdnav_b200.policy import make_value_network
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    model = make_value_network(13, 6, [150, 100], [100, 50], [150, 100, 100, 1], [100, 100, 1]).to(dev)
+    g = torch.Generator(device="cpu").manual_seed(B * 100 + H)
+    x = (torch.rand((B, H, 13), generator=g) * 4 - 2).to(dev)
+    x[:, :, 2] = 0.0
+    y = torch.rand((B, 1), generator=g).to(dev)
+    loss = torch.nn.functional.mse_loss(model(x), y)
+    loss.backward()
+    ref = torch.cat([p.grad.reshape(-1) for p in model.parameters()]).cpu().numpy()
+    ft = FusedSarlTrainer(model, dev)
+    ft.lr = 0.01
+    ft.sync_from_model()
+    lossd = torch.zeros((), device=dev)
+    from modelcrowdnav_b200._capi import check
+    check(ft.lib.cn_trainer_step(ft.handle, C.c_void_p(ft.flat.data_ptr()), C.c_void_p(x.data_ptr()),
+                                 C.c_void_p(y.reshape(-1).contiguous().data_ptr()), B, H, 0.01, 0.9,
+                                 C.c_void_p(ft.grad.data_ptr()), C.c_void_p(lossd.data_ptr()), None))
+    torch.cuda.synchronize()
+    got = ft.grad.cpu().numpy()
+    assert abs(float(lossd) - float(loss)) <= 1e-6 * max(1.0, abs(float(loss)))
+    scale = np.abs(ref).max()
+    assert np.max(np.abs(got - ref)) <= 2e-5 * scale, (np.max(np.abs(got - ref)), scale)
+    # the parameters are views of the flat block: a step moves model.state_dict() itself
+    before = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).clone()
+    ft.step(x, y)
+    after = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    assert torch.allclose(after, before - 0.01 * torch.from_numpy(ref).to(dev), atol=1e-6)
+    ft.close()
