@@ -49,6 +49,7 @@ enum { CN_CIRCLE_CROSSING = 0, CN_SQUARE_CROSSING = 1 };
 /* value-network arithmetic */
 enum { CN_PREC_F32 = 0 /* FP32 CUDA cores */, CN_PREC_F16_TC = 1 /* fp16 operands, fp32 accumulate, tcgen05 */ };
 enum { CN_NET_SARL = 0, CN_NET_CADRL = 1, CN_NET_LSTM_RL = 2 };   /* value network behind the lookahead */
+enum { CN_WORLD_ATTENTION = 0, CN_WORLD_MLP = 1 };                /* learned human-motion model (world_model.py) */
 
 typedef struct cn_env cn_env;
 typedef struct cn_policy cn_policy;
@@ -197,6 +198,14 @@ int cn_env_set_human_actions(cn_env *env, const double *human_vxy_host, void *st
 int cn_env_set_actions(cn_env *env, const double *action_xy_host, void *stream);
 /* Blocking: reduce the device accumulators (explorer.py counters).  reset != 0 clears them. */
 int cn_env_read_stats(cn_env *env, cn_stats *out, int reset, void *stream);
+/* The per-ENV episode accumulators behind cn_env_read_stats, un-reduced: 11 arrays of E entries each, in this order --
+ * int64 episodes, success, collision, timeout, steps, too_close; double sum_min_dist, sum_success_time,
+ * sum_collision_time, sum_timeout_time, sum_return (table_host: cn_env_episode_table_bytes(env) bytes).  With auto_reset
+ * off every env runs ONE episode and then freezes, so after a roll-out row e IS the outcome of episode e: this is how
+ * Explorer.run_k_episodes (explorer.py:36-151) gets its per-episode results without a host sync per step.
+ * frozen_host (optional, E bytes): 1 = the env's episode has ended.  Blocking. */
+int64_t cn_env_episode_table_bytes(const cn_env *env);
+int cn_env_read_episode_table(cn_env *env, void *table_host, uint8_t *frozen_host, void *stream);
 
 /* ---- policy: replaces policy_factory['sarl']() + configure (sarl.py:68-89) ---- */
 int cn_policy_create(const cn_sarl_cfg *cfg, int device, cn_policy **out);
@@ -292,6 +301,20 @@ int cn_selftest_umma_pair(int32_t N, int32_t K, const float *a_host, const float
 /* Developer diagnostic: clock64() at the phase boundaries of one tile of the tensor-core row kernel (CTA 0).
  * The first call arms the probes; call again after a lookahead to read 16 timestamps. */
 int cn_debug_tc_timing(cn_policy *p, long long *out16);
+/* ---- learned human-motion models of ModelCrowdSim (crowd_nav/policy/world_model.py:20-106, model_crowd_sim.py:397-425) ----
+ * cn_world_create: CN_WORLD_ATTENTION (AttentionWorld, any human count <= 32) or CN_WORLD_MLP (MlpWorld(human_num)).
+ * cn_world_load_weights: flat fp32 HOST array in the torch state-dict order of the reference module (its checkpoints load
+ *   unchanged: mlp1.0 ... mlp3.6 / mlp.0, mlp.3, mlp.6, mlp.8; weight [out][in], then bias).
+ * cn_world_predict: every human's next velocity from the env's CURRENT human states (px, py, vx, vy as fp32, like the
+ *   reference's torch.Tensor([...])), written where cn_env_orca puts the ORCA velocities: the following cn_env_step /
+ *   cn_policy_lookahead(query_env) / cn_rollout_step consume it.  No host round trip. */
+typedef struct cn_world cn_world;
+int cn_world_create(int32_t kind, int32_t human_num, int device, cn_world **out);
+int cn_world_destroy(cn_world *w);
+int64_t cn_world_param_count(const cn_world *w);
+int cn_world_load_weights(cn_world *w, const float *flat_host, int64_t n, void *stream);
+int cn_world_predict(cn_world *w, cn_env *env, void *stream);
+
 /* ---- value-network training step on the device (crowd_nav/utils/trainer.py:36-82) ------------------------------------
  * One optimisation step of the reference Trainer -- zero_grad, model(inputs), MSELoss, backward, SGD(momentum).step -- as
  * two kernels on ONE flat fp32 parameter block in torch state-dict order (the block cn_policy_load_weights takes; the

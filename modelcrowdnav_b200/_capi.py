@@ -13,6 +13,7 @@ CN_OK, CN_EINVAL, CN_ECUDA, CN_ENOMEM, CN_EUNSUPPORTED, CN_EVALUE = 0, -1, -2, -
 NOTHING, DANGER, REACHGOAL, COLLISION, TIMEOUT = 0, 1, 2, 3, 4
 CIRCLE_CROSSING, SQUARE_CROSSING = 0, 1
 PREC_F32, PREC_F16_TC = 0, 1
+WORLD_ATTENTION, WORLD_MLP = 0, 1                    # learned human-motion models (CN_WORLD_*)
 NET_SARL, NET_CADRL, NET_LSTM_RL = 0, 1, 2           # value network behind the lookahead (CN_NET_*)
 KIN_HOLONOMIC, KIN_UNICYCLE, KIN_NONE = 0, 1, 2      # robot kinematics (CN_KIN_*); NONE = the fork as shipped (cadrl.py:66)
 AGENT_STRIDE = 8
@@ -21,9 +22,10 @@ EXPORTS = [
     "cn_last_error", "cn_version", "cn_device_count", "cn_env_cfg_default", "cn_sarl_cfg_default",
     "cn_env_create", "cn_env_destroy", "cn_env_set_state", "cn_env_get_state", "cn_env_set_theta", "cn_env_get_theta", "cn_env_reset", "cn_env_orca",
     "cn_env_robot_orca", "cn_env_step", "cn_env_get_views", "cn_env_read_outputs", "cn_env_read_human_actions",
-    "cn_env_read_next_obs", "cn_env_read_actions", "cn_env_set_actions", "cn_env_set_human_actions", "cn_env_read_stats", "cn_policy_create", "cn_policy_destroy",
+    "cn_env_read_next_obs", "cn_env_read_actions", "cn_env_set_actions", "cn_env_set_human_actions", "cn_env_read_stats", "cn_env_episode_table_bytes", "cn_env_read_episode_table", "cn_policy_create", "cn_policy_destroy",
     "cn_policy_param_count", "cn_policy_load_weights", "cn_policy_action_table", "cn_policy_lookahead",
     "cn_policy_read", "cn_policy_bad_count", "cn_policy_transform", "cn_policy_last_state", "cn_policy_forward", "cn_rollout_step", "cn_rollout_step_sharded", "cn_rollout_step_host", "cn_rollout_step_host_packed", "cn_rollout_step_host_packed_async", "cn_stream_sync", "cn_host_step_bytes",
+    "cn_world_create", "cn_world_destroy", "cn_world_param_count", "cn_world_load_weights", "cn_world_predict",
     "cn_trainer_create", "cn_trainer_destroy", "cn_trainer_param_count", "cn_trainer_sync_weights", "cn_trainer_step", "cn_trainer_apply",
     "cn_launch_count", "cn_debug_trace", "cn_debug_trace_dump", "cn_selftest_umma", "cn_selftest_umma_bmn", "cn_selftest_umma_ts", "cn_selftest_umma_pair", "cn_debug_tc_timing", "cn_debug_kernel_ms",
 ]
@@ -109,6 +111,9 @@ def load():
     L.cn_env_set_human_actions.argtypes = [vp, vp, vp]
     L.cn_env_read_actions.argtypes = [vp, vp, vp, vp]
     L.cn_env_read_stats.argtypes = [vp, C.POINTER(Stats), C.c_int, vp]
+    L.cn_env_episode_table_bytes.argtypes = [vp]
+    L.cn_env_episode_table_bytes.restype = i64
+    L.cn_env_read_episode_table.argtypes = [vp, vp, vp, vp]
     L.cn_policy_create.argtypes = [C.POINTER(SarlCfg), C.c_int, C.POINTER(vp)]
     L.cn_policy_destroy.argtypes = [vp]
     L.cn_policy_load_weights.argtypes = [vp, vp, i64, vp]
@@ -126,6 +131,12 @@ def load():
     L.cn_rollout_step_host_packed_async.argtypes = [vp, vp, C.c_int, dbl, vp, vp, vp]
     L.cn_stream_sync.argtypes = [C.c_int, vp]
     L.cn_host_step_bytes.argtypes = [vp, C.c_int]
+    L.cn_world_create.argtypes = [i32, i32, C.c_int, C.POINTER(vp)]
+    L.cn_world_destroy.argtypes = [vp]
+    L.cn_world_param_count.argtypes = [vp]
+    L.cn_world_param_count.restype = i64
+    L.cn_world_load_weights.argtypes = [vp, vp, i64, vp]
+    L.cn_world_predict.argtypes = [vp, vp, vp]
     L.cn_trainer_create.argtypes = [C.POINTER(SarlCfg), C.c_int, i32, i32, C.POINTER(vp)]
     L.cn_trainer_destroy.argtypes = [vp]
     L.cn_trainer_param_count.argtypes = [vp]

@@ -130,6 +130,24 @@ class BatchedCrowdSim(object):
         check(self.lib.cn_env_get_views(self.handle, C.byref(v)))
         return v
 
+    def episode_table(self, stream=None):
+        """Per-env episode accumulators (un-reduced cn_env_read_stats) + frozen flags: dict of (E,) arrays.  Blocking."""
+        E = self.E
+        raw = np.empty(E * 11, np.int64)
+        frozen = np.empty(E, np.uint8)
+        check(self.lib.cn_env_read_episode_table(self.handle, _ptr(raw), _ptr(frozen), _stream(stream)))
+        names_i = ("episodes", "success", "collision", "timeout", "steps", "too_close")
+        names_d = ("sum_min_dist", "sum_success_time", "sum_collision_time", "sum_timeout_time", "sum_return")
+        out = {k: raw[i * E:(i + 1) * E] for i, k in enumerate(names_i)}
+        out.update({k: raw[(6 + i) * E:(7 + i) * E].view(np.float64) for i, k in enumerate(names_d)})
+        out["frozen"] = frozen
+        return out
+
+    def all_done(self, stream=None):
+        frozen = np.empty(self.E, np.uint8)
+        check(self.lib.cn_env_read_episode_table(self.handle, None, _ptr(frozen), _stream(stream)))
+        return bool(frozen.all())
+
     def stats(self, reset=False, stream=None):
         s = _capi.Stats()
         check(self.lib.cn_env_read_stats(self.handle, C.byref(s), int(reset), _stream(stream)))

@@ -416,6 +416,18 @@ int cn_env_read_stats(cn_env *env, cn_stats *out, int reset, void *stream)
     return CN_OK;
 }
 
+int64_t cn_env_episode_table_bytes(const cn_env *env) { return env ? (int64_t)env->p.d.E * 8 * 11 : 0; }
+
+int cn_env_read_episode_table(cn_env *env, void *table_host, uint8_t *frozen_host, void *stream)
+{
+    CN_ENV_ENTER(env);
+    const size_t E = env->p.d.E;
+    if (table_host) CN_CUDA_CHECK(cudaMemcpyAsync(table_host, env->accum_block, E * 8 * 11, cudaMemcpyDeviceToHost, s));
+    if (frozen_host) CN_CUDA_CHECK(cudaMemcpyAsync(frozen_host, env->frozen, E, cudaMemcpyDeviceToHost, s));
+    CN_CUDA_CHECK(cudaStreamSynchronize(s));
+    return CN_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // policy
 // ---------------------------------------------------------------------------------------------

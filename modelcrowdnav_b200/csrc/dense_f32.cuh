@@ -1,0 +1,104 @@
+// dense_f32.cuh -- FP32 CUDA-core building blocks of the small dense layers that run OUTSIDE the tensor-core lookahead
+// (the fused trainer, trainer.cu, and the world models, world_model.cu): activations in shared memory, weights streamed
+// from L2 as a transposed [in][out] block, one CTA of kThreads threads.
+#pragma once
+#include <stdint.h>
+
+namespace dense_f32 {
+
+constexpr int kThreads = 256;
+
+__host__ __device__ __forceinline__ int pad4(int x) { return (x + 3) & ~3; }
+
+// Y[r][o] = act(b[o] + sum_k X[r * ldx + k] * Wt[k * O + o]),  r < R, o < O.   Wt is [K][O] in global memory (coalesced over
+// o); X lives in shared memory.  One thread = 4 rows x 1 output, K walked in steps of 4 (LDS.128 of X, broadcast in a warp).
+__device__ __forceinline__ void dense(const float *__restrict__ X, int ldx, int R, int K, const float *__restrict__ Wt,
+                                      const float *__restrict__ b, int O, float *__restrict__ Y, int ldy, bool relu, bool accumulate)
+{
+    const int groups = (R + 3) >> 2;
+    for (int idx = threadIdx.x; idx < O * groups; idx += kThreads) {
+        const int o = idx % O, r0 = (idx / O) * 4;
+        float acc[4];
+        const float bias = b ? b[o] : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = bias;
+        const float *x0 = X + (size_t)r0 * ldx;
+        const int nr = min(4, R - r0);
+        int k = 0;
+        for (; k + 4 <= K; k += 4) {
+            const float w0 = Wt[(size_t)k * O + o], w1 = Wt[(size_t)(k + 1) * O + o];
+            const float w2 = Wt[(size_t)(k + 2) * O + o], w3 = Wt[(size_t)(k + 3) * O + o];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (i < nr) {
+                    const float4 x = *reinterpret_cast<const float4 *>(x0 + (size_t)i * ldx + k);
+                    acc[i] = fmaf(x.x, w0, acc[i]); acc[i] = fmaf(x.y, w1, acc[i]);
+                    acc[i] = fmaf(x.z, w2, acc[i]); acc[i] = fmaf(x.w, w3, acc[i]);
+                }
+            }
+        }
+        for (; k < K; ++k) {
+            const float w = Wt[(size_t)k * O + o];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (i < nr) acc[i] = fmaf(x0[(size_t)i * ldx + k], w, acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (i < nr) {
+                float v = acc[i];
+                if (accumulate) v += Y[(size_t)(r0 + i) * ldy + o];
+                Y[(size_t)(r0 + i) * ldy + o] = relu ? fmaxf(v, 0.0f) : v;
+            }
+        }
+    }
+}
+
+// dW[o][k] = sum_r dY[r][o] * Xin[r][k] and db[o] = sum_r dY[r][o] -> this CTA's partial gradient block (global memory).
+// One thread = 2 outputs x 4 inputs; consecutive threads walk k (conflict-free LDS.128 of Xin, broadcast dY).
+__device__ __forceinline__ void weight_grad(const float *__restrict__ dY, int ldy, const float *__restrict__ Xin, int ldx, int R,
+                                            int O, int K, float *__restrict__ gW /*[O][K]*/, float *__restrict__ gb /*[O]*/)
+{
+    const int k4n = (K + 3) >> 2, o2n = (O + 1) >> 1;
+    for (int idx = threadIdx.x; idx < o2n * k4n; idx += kThreads) {
+        const int k = (idx % k4n) * 4, o = (idx / k4n) * 2;
+        const bool o1 = o + 1 < O;
+        float a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
+        if (k + 4 <= K) {
+            for (int r = 0; r < R; ++r) {
+                const float4 x = *reinterpret_cast<const float4 *>(Xin + (size_t)r * ldx + k);
+                const float d0 = dY[(size_t)r * ldy + o], d1 = o1 ? dY[(size_t)r * ldy + o + 1] : 0.0f;
+                a0[0] = fmaf(d0, x.x, a0[0]); a0[1] = fmaf(d0, x.y, a0[1]); a0[2] = fmaf(d0, x.z, a0[2]); a0[3] = fmaf(d0, x.w, a0[3]);
+                a1[0] = fmaf(d1, x.x, a1[0]); a1[1] = fmaf(d1, x.y, a1[1]); a1[2] = fmaf(d1, x.z, a1[2]); a1[3] = fmaf(d1, x.w, a1[3]);
+            }
+        } else {
+            for (int r = 0; r < R; ++r) {
+                const float d0 = dY[(size_t)r * ldy + o], d1 = o1 ? dY[(size_t)r * ldy + o + 1] : 0.0f;
+                for (int j = 0; k + j < K; ++j) {
+                    const float x = Xin[(size_t)r * ldx + k + j];
+                    a0[j] = fmaf(d0, x, a0[j]); a1[j] = fmaf(d1, x, a1[j]);
+                }
+            }
+        }
+        for (int j = 0; j < 4 && k + j < K; ++j) {
+            gW[(size_t)o * K + k + j] = a0[j];
+            if (o1) gW[(size_t)(o + 1) * K + k + j] = a1[j];
+        }
+    }
+    for (int o = threadIdx.x; o < O; o += kThreads) {
+        float s = 0.0f;
+        for (int r = 0; r < R; ++r) s += dY[(size_t)r * ldy + o];
+        gb[o] = s;
+    }
+}
+
+// dA[r][k] *= (act[r][k] > 0)   (ReLU backward; act holds the post-ReLU activation)
+__device__ __forceinline__ void relu_mask(float *__restrict__ dA, int ld, const float *__restrict__ act, int lda, int R, int K)
+{
+    for (int idx = threadIdx.x; idx < R * K; idx += kThreads) {
+        const int r = idx / K, k = idx - r * K;
+        if (!(act[(size_t)r * lda + k] > 0.0f)) dA[(size_t)r * ld + k] = 0.0f;
+    }
+}
+
+
+}  // namespace dense_f32

@@ -381,10 +381,10 @@ class CrowdSim(object):
 
 class ModelCrowdSim(CrowdSim):
     """Drop-in for gym.make('ModelCrowdSim-v0') (crowd_sim/envs/model_crowd_sim.py:15-441): CrowdSim whose humans move with
-    the velocities a learned world model predicts (``sim_world``: MlpWorld / AttentionWorld, any callable on a
-    (1, H * 4) tensor of px, py, vx, vy) instead of ORCA.  The world model is a torch module (it is what the fork trains);
-    collision / reward / done ladder and the state update run in the same CUDA step kernel, fed through
-    cn_env_set_human_actions.  Scenes come from the GLOBAL numpy stream (the fork never seeds, :293) and humans start
+    the velocities a learned world model predicts (``sim_world``: world_model.MlpWorld / AttentionWorld) instead of ORCA.
+    The prediction is one kernel on the env batch (cn_world_predict): it reads the humans' states on the device and leaves
+    their next velocities where the step expects the ORCA result; collision / reward / done ladder and the state update are
+    the same CUDA step kernel.  Scenes come from the GLOBAL numpy stream (the fork never seeds, :293) and humans start
     moving towards their goal (gen_init_v, :186-192)."""
 
     def __init__(self):
@@ -403,7 +403,7 @@ class ModelCrowdSim(CrowdSim):
 
     def _ensure_human_actions(self, b):
         if self._human_v is None:
-            b.set_human_actions(np.asarray(self.world_velocities(), dtype=np.float64).reshape(1, len(self.humans), 2))
+            self.world_step_batch(b)
             self._human_v = True
 
     def scene_kwargs(self, phase):
@@ -451,23 +451,19 @@ class ModelCrowdSim(CrowdSim):
             self.humans[i].set(ob.px, ob.py, 0, 0, ob.vx, ob.vy, 0)
         self._upload()
 
+    def world_step_batch(self, b):
+        """model_crowd_sim.py:397-407 for every env of a batch, ON THE DEVICE: the world model reads the humans' states from
+        the batch and leaves their next velocities where the env step expects the ORCA result (cn_world_predict)."""
+        if not hasattr(self.sim_world, "predict_into"):
+            raise NotImplementedError("sim_world must be a modelcrowdnav_b200.world_model MlpWorld / AttentionWorld")
+        self.sim_world.predict_into(b)
+
     def world_velocities(self):
         """model_crowd_sim.py:397-407: (H, 2) velocities the world model predicts for the current human states."""
-        import torch
-        current_s = [[h.px, h.py, h.vx, h.vy] for h in self.humans]
-        x = torch.Tensor([current_s]).to(self.device)
-        x = x.reshape(x.size(0), -1)
-        with torch.no_grad():
-            new_v = self.sim_world(x)[0]
-        return torch.reshape(new_v, (len(self.humans), 2)).tolist()
-
-    def world_velocities_batch(self, agents):
-        """world_velocities() for a batch: agents (k, H+1, 8) -> (k, H, 2) float64, one forward of the world model."""
-        import torch
-        x = torch.as_tensor(np.ascontiguousarray(agents[:, 1:, :4]), dtype=torch.float32).to(self.device)
-        with torch.no_grad():
-            v = self.sim_world(x.reshape(x.shape[0], -1))
-        return v.reshape(x.shape[0], -1, 2).double().cpu().numpy()
+        b = self._ensure_batch()
+        self.world_step_batch(b)
+        self._human_v = True
+        return b.human_actions()[0].tolist()
 
     def step(self, action, update=True, new_v=None):
         if new_v is not None:                      # caller-supplied velocities (model_crowd_sim.py:347,397)

@@ -3,7 +3,11 @@
 `Explorer.run_k_episodes(k, phase, ...)` keeps the reference's signature, log lines and return values, but the
 k episodes run side by side as k environments of one GPU batch (cases c, c+1, ... exactly as k successive
 `env.reset(phase)` calls would pick them).  The inner loop of the reference (explorer.py:62-69: act, step) is one
-`cn_rollout_step`-style sequence per step for all envs; only rewards / done / info codes come back to the host.
+`cn_rollout_step`-style sequence per step for all envs.  Phases that do not fill the replay memory (val / test, the bulk of
+test.py) run WITHOUT a host sync per step: the kernels are enqueued back to back, the per-env episode accumulators of the
+library (cn_env_read_episode_table) deliver every episode's outcome, end time, step count, danger count and discounted return
+at the end, and the loop only looks at the frozen flags every few steps to stop early.  Replay-filling phases read rewards /
+done / info codes back every step (the stored state sequence needs them).
 
 Replay filling (`update_memory`, explorer.py:153-186) is batched as well: states are kept as (T, k, H, 13) device
 tensors, IL targets are discounted returns-to-go, RL targets r + gamma_bar * V_target(s') with V_target evaluated
@@ -138,26 +142,18 @@ class Explorer(object):
             if update_memory:
                 raise NotImplementedError("replay filling over scenes with different human counts (the reference's "
                                           "DataLoader cannot collate them either)")
-            parts = []
+            r = dict(final_info=np.zeros(k, np.int64), end_time=np.zeros(k), steps=np.zeros(k, np.int64), returns=np.zeros(k),
+                     too_close=0, min_dist_sum=0.0, states_t=None, R=None, M=None)
             for n in sizes:
                 idx = [i for i, a in enumerate(scene_list) if a.shape[0] == n]
-                parts.append((idx, self._rollout(np.stack([scene_list[i] for i in idx]), phase, False, imitation_learning,
-                                                 stay)))
-            T = max(p[1]["R"].shape[0] for p in parts)
-            R = np.zeros((T, k)); M = np.zeros((T, k), bool)
-            final_info = np.zeros(k, np.int64); end_time = np.zeros(k)
-            too_close, min_dist = 0, []
-            for idx, r in parts:
-                R[:r["R"].shape[0], idx] = r["R"]; M[:r["M"].shape[0], idx] = r["M"]
-                final_info[idx] = r["final_info"]; end_time[idx] = r["end_time"]
-                too_close += r["too_close"]; min_dist += r["min_dist"]
-            states_t = None
+                part = self._rollout(np.stack([scene_list[i] for i in idx]), phase, False, imitation_learning, stay)
+                for key in ("final_info", "end_time", "steps", "returns"):
+                    r[key][idx] = part[key]
+                r["too_close"] += part["too_close"]; r["min_dist_sum"] += part["min_dist_sum"]
         else:
             r = self._rollout(np.stack(scene_list), phase, update_memory, imitation_learning, stay)
-            R, M, final_info, end_time = r["R"], r["M"], r["final_info"], r["end_time"]
-            too_close, min_dist, states_t = r["too_close"], r["min_dist"], r["states_t"]
-        return self._summarise(k, phase, cases, R, M, final_info, end_time, too_close, min_dist, states_t, update_memory,
-                               imitation_learning, episode, print_failure, stay, returnRate, returnNav)
+        return self._summarise(k, phase, cases, r, update_memory, imitation_learning, episode, print_failure, stay, returnRate,
+                               returnNav)
 
     def _rollout(self, agents, phase, update_memory, imitation_learning, stay):
         """k episodes with the same human count side by side (explorer.py:53-69 for every env of the batch)."""
@@ -183,12 +179,18 @@ class Explorer(object):
         tr_policy = self.target_policy if (imitation_learning and self.target_policy is not None) else policy
         world_env = isinstance(env, ModelCrowdSim)
 
+        max_steps = int(round(env.time_limit / dt)) + 2
+        gamma = self.gamma if self.gamma is not None else 1.0
+        if not update_memory and (stay or is_sarl or isinstance(policy, ORCA)):
+            humans = (lambda: env.world_step_batch(b)) if world_env else b.orca     # world model or ORCA, both on the device
+            return self._rollout_device(b, k, max_steps, stay, is_sarl, policy, handle if is_sarl else None,
+                                        eps if is_sarl else 0.0, humans)
+
         active = np.ones(k, bool)
         rewards_t, states_t, active_t = [], [], []
         final_info = np.zeros(k, np.int64)
         end_time = np.zeros(k)
-        too_close, min_dist = 0, []
-        max_steps = int(round(env.time_limit / dt)) + 2
+        too_close, min_dist_sum = 0, 0.0
         for _ in range(max_steps):
             if not active.any():
                 break
@@ -203,7 +205,7 @@ class Explorer(object):
                     st = st[:, 0]
                 states_t.append(st)
             if world_env:                  # ModelCrowdSim: the humans' next velocities come from the world model
-                b.set_human_actions(env.world_velocities_batch(b.get_state()[0]))
+                env.world_step_batch(b)
             else:
                 b.orca()
             if stay:
@@ -225,7 +227,7 @@ class Explorer(object):
             active_t.append(active.copy())
             danger = active & (info == _capi.DANGER)
             too_close += int(danger.sum())
-            min_dist.extend(dmin[danger].tolist())
+            min_dist_sum += float(dmin[danger].sum())
             finished = active & (done != 0)
             if finished.any():
                 final_info[finished] = info[finished]
@@ -234,14 +236,51 @@ class Explorer(object):
             active &= ~finished
         if active.any():
             raise ValueError("Invalid end signal from environment")
-        return dict(R=np.stack(rewards_t), M=np.stack(active_t), final_info=final_info, end_time=end_time,
-                    too_close=too_close, min_dist=min_dist, states_t=states_t)
+        R, M = np.stack(rewards_t), np.stack(active_t)
+        disc = np.array([pow(gamma, t * dt * v_pref) for t in range(R.shape[0])])
+        return dict(R=R, M=M, final_info=final_info, end_time=end_time, too_close=too_close, min_dist_sum=min_dist_sum,
+                    states_t=states_t, returns=(R * disc[:, None]).sum(0), steps=M.sum(0))
 
-    def _summarise(self, k, phase, cases, R, M, final_info, end_time, too_close, min_dist, states_t, update_memory,
-                   imitation_learning, episode, print_failure, stay, returnRate, returnNav):
+    def _rollout_device(self, b, k, max_steps, stay, is_sarl, policy, handle, eps, humans):
+        """Episodes of a batch with NO host sync per step (val / test phases): kernels back to back, outcomes from the per-env
+        episode accumulators.  Finished envs freeze (auto_reset off), so extra steps are harmless; every `check` steps the
+        frozen flags (k bytes) are read to stop as soon as the last episode has ended."""
+        b.stats(reset=True)                             # zero the accumulators (set_state cleared the per-episode parts)
+        if is_sarl:
+            bad0 = handle.bad_count()
+        if stay:
+            b.set_actions(np.zeros((k, 2)))
+        check = 8
+        for step in range(max_steps):
+            humans()
+            if stay:
+                pass                                    # pending action stays (0, 0)
+            elif is_sarl:
+                handle.lookahead(b, query_env=policy.query_env, epsilon=eps)
+            else:
+                b.robot_orca(policy.safety_space)
+            b.step(update=True, read=False)
+            if step % check == check - 1 and b.all_done():
+                break
+        t = b.episode_table()
+        if is_sarl and handle.bad_count() != bad0:
+            raise ValueError("Value network is not well trained. ")         # multi_human_rl.py:57-58
+        if not t["frozen"].all() or not (t["episodes"] == 1).all():
+            raise ValueError("Invalid end signal from environment")
+        final_info = np.where(t["success"] == 1, _capi.REACHGOAL, np.where(t["collision"] == 1, _capi.COLLISION, _capi.TIMEOUT))
+        end_time = np.where(t["success"] == 1, t["sum_success_time"],
+                            np.where(t["collision"] == 1, t["sum_collision_time"], t["sum_timeout_time"]))
+        return dict(R=None, M=None, final_info=final_info.astype(np.int64), end_time=end_time,
+                    too_close=int(t["too_close"].sum()), min_dist_sum=float(t["sum_min_dist"].sum()), states_t=None,
+                    returns=t["sum_return"].copy(), steps=t["steps"].copy())
+
+    def _summarise(self, k, phase, cases, r, update_memory, imitation_learning, episode, print_failure, stay, returnRate,
+                   returnNav):
         """Counters, log lines, replay filling and return values of explorer.py:70-151."""
         import torch
         env, robot = self.env, self.robot
+        final_info, end_time, too_close = r["final_info"], r["end_time"], r["too_close"]
+        R, M, states_t = r["R"], r["M"], r["states_t"]
         success = final_info == _capi.REACHGOAL
         collision = final_info == _capi.COLLISION
         timeout = final_info == _capi.TIMEOUT
@@ -250,9 +289,8 @@ class Explorer(object):
         timeout_times = [env.time_limit] * int(timeout.sum())
         collision_cases = np.nonzero(collision)[0].tolist()
         timeout_cases = np.nonzero(timeout)[0].tolist()
-        disc = np.array([pow(self.gamma, t * robot.time_step * robot.v_pref) for t in range(R.shape[0])]) \
-            if self.gamma is not None else np.ones(R.shape[0])
-        cumulative_rewards = (R * disc[:, None]).sum(0).tolist()
+        cumulative_rewards = r["returns"].tolist() if self.gamma is not None else \
+            (R.sum(0).tolist() if R is not None else r["returns"].tolist())
 
         if update_memory:
             if self.memory is None or self.gamma is None:
@@ -263,7 +301,7 @@ class Explorer(object):
                 self._update_memory_batched(S, R, M, keep, imitation_learning)
 
         counts = np.array([success.sum(), collision.sum(), timeout.sum(), too_close, k], dtype=np.float64)
-        sums = np.array([sum(success_times), sum(collision_times), sum(timeout_times), sum(min_dist),
+        sums = np.array([sum(success_times), sum(collision_times), sum(timeout_times), r["min_dist_sum"],
                          sum(cumulative_rewards)], dtype=np.float64)
         if self.dist_group is not None:
             counts, sums = self._all_reduce(counts, sums)
@@ -285,7 +323,7 @@ class Explorer(object):
         if print_failure:
             logging.info("Collision cases: " + " ".join([str(x) for x in collision_cases]))
             logging.info("Timeout cases: " + " ".join([str(x) for x in timeout_cases]))
-        self.last_run = dict(cases=cases, info=final_info, end_time=end_time, steps=M.sum(0), too_close=too_close,
+        self.last_run = dict(cases=cases, info=final_info, end_time=end_time, steps=np.asarray(r["steps"]), too_close=too_close,
                              returns=np.array(cumulative_rewards))
         if returnRate and returnNav:
             return avg_return, success_rate, collision_rate, timeout_rate, avg_nav_time
@@ -304,20 +342,20 @@ class Explorer(object):
         return t[:len(counts)], t[len(counts):]
 
     def _update_memory_batched(self, S, R, M, keep, imitation_learning):
-        """explorer.py:153-186 for every kept episode at once; pushes in episode-then-time order."""
+        """explorer.py:153-186 for every kept episode at once; pushes in episode-then-time order.  Everything stays on the
+        device: the IL return-to-go is a reversed cumulative sum, the RL targets one batched target-network forward, and the
+        (episode, time) pairs are gathered with ONE index and pushed with ONE ring-buffer write."""
         import torch
         T = R.shape[0]
         dev = S.device
         gamma_bar = pow(self.gamma, self.robot.time_step * self.robot.v_pref)
-        Rk = torch.as_tensor(R[:, keep], dtype=torch.float64, device=dev)          # (T, n)
+        Rk = torch.as_tensor(R[:, keep], dtype=torch.float64, device=dev)          # (T, n); zero after an episode's end
         Mk = torch.as_tensor(M[:, keep], device=dev)
         if imitation_learning:
-            # value_i = sum_{t >= i} gamma^((t - i) * dt * v_pref) * r_t  (explorer.py:161-166): reverse scan
-            V = torch.zeros_like(Rk)
-            acc = torch.zeros(Rk.shape[1], dtype=torch.float64, device=dev)
-            for t in range(T - 1, -1, -1):
-                acc = Rk[t] + gamma_bar * acc
-                V[t] = acc
+            # value_i = sum_{t >= i} gamma_bar^(t - i) r_t (explorer.py:161-166) = revcumsum(r_t gamma_bar^t)_i / gamma_bar^i
+            wgt = torch.pow(torch.tensor(gamma_bar, dtype=torch.float64, device=dev),
+                            torch.arange(T, dtype=torch.float64, device=dev)).unsqueeze(1)
+            V = torch.flip(torch.cumsum(torch.flip(Rk * wgt, [0]), 0), [0]) / wgt
         else:
             # value_i = r_i + gamma_bar * V_target(s_{i+1}); terminal: r (explorer.py:168-174)
             Sk = S[:, keep]                                                        # (T, n, H, 13)
@@ -327,6 +365,6 @@ class Explorer(object):
                 nxt[:-1] = self._target_forward(flat).reshape(T - 1, -1).double()
             last = Mk & ~torch.cat([Mk[1:], torch.zeros_like(Mk[:1])])
             V = torch.where(last, Rk, Rk + gamma_bar * nxt)
-        for j, e in enumerate(keep):                                               # episode order, then time order
-            n = int(M[:, e].sum())
-            self.memory.push_batch(S[:n, e], V[:n, j].float())
+        jj, tt = torch.nonzero(Mk.t(), as_tuple=True)                              # episode-major, time-minor
+        ee = torch.as_tensor(np.asarray(keep), device=dev)[jj]
+        self.memory.push_batch(S[tt, ee], V[tt, jj].float())

@@ -376,7 +376,7 @@ def test_model_crowd_sim_facade_replays_reference(weights0, name):
         off += v.numel()
     world.load_state_dict(new)
     world.eval()
-    env.sim_world, env.device = world.cuda(), torch.device("cuda:0")
+    env.sim_world, env.device = world, torch.device("cuda:0")
     state = np.random.get_state()
     try:
         np.random.seed(int(g["np_seed"]))
@@ -448,7 +448,7 @@ def test_explorer_over_model_crowd_sim(weights0):
         new[k] = torch.from_numpy(g["world_weights"][off:off + v.numel()].reshape(tuple(v.shape)).copy())
         off += v.numel()
     world.load_state_dict(new)
-    env.sim_world, env.device = world.cuda().eval(), torch.device("cuda:0")
+    env.sim_world, env.device = world, torch.device("cuda:0")
     explorer = mcn.Explorer(env, robot, torch.device("cuda:0"), gamma=0.9)
     k = 16
     state = np.random.get_state()
@@ -469,6 +469,42 @@ def test_explorer_over_model_crowd_sim(weights0):
     finally:
         np.random.set_state(state)
     assert same >= k - 2, same
+
+
+@pytest.mark.parametrize("name", MODEL_WORLD_NAMES)
+def test_world_model_kernel_matches_reference(name):
+    """cn_world_predict (csrc/world_model.cu) against the velocities the REFERENCE's AttentionWorld / MlpWorld predicted for
+    every recorded step (tests/golden/model_world_*.npz): all steps of the episode as one env batch, on the device."""
+    import torch
+    import modelcrowdnav_b200 as mcn
+    from modelcrowdnav_b200.world_model import AttentionWorld, MlpWorld
+    g = load_model_world(name)
+    H, T = int(g["H"]), len(g["reward"])
+    world = MlpWorld(H) if str(g["world"]) == "mlp" else AttentionWorld()
+    off, new = 0, {}
+    for k, v in world.state_dict().items():
+        new[k] = torch.from_numpy(g["world_weights"][off:off + v.numel()].reshape(tuple(v.shape)).copy())
+        off += v.numel()
+    world.load_state_dict(new)
+    env = mcn.BatchedCrowdSim(T, H)
+    env.set_state(np.stack([g["agents"][t] for t in range(T)]))
+    world.predict_into(env)
+    v = env.human_actions()
+    assert np.max(np.abs(v - g["new_v"][:T])) <= 2e-6
+    # the module call (what env.sim_world(x) did in the fork) is the same kernel
+    x = torch.tensor(np.stack([g["agents"][t][1:, :4] for t in range(T)]), dtype=torch.float32, device="cuda").reshape(T, -1)
+    out = world(x).cpu().numpy().reshape(T, H, 2)
+    assert np.max(np.abs(out - g["new_v"][:T])) <= 2e-6
+    # in-place parameter updates are picked up (version stamp)
+    with torch.no_grad():
+        list(world.parameters())[-1].add_(0.25)
+    world.predict_into(env)
+    v2 = env.human_actions()
+    if str(g["world"]) == "mlp":
+        assert np.max(np.abs(v2 - v)) > 1e-3
+    else:
+        assert np.max(np.abs(v2 - (v + 0.25))) <= 2e-6
+    env.close()
 
 
 def _training_golden():

@@ -1,6 +1,6 @@
-"""The torch mirrors of the fork's world models (crowd_nav/policy/world_model.py) against the reference's own outputs:
-tests/golden/model_world_*.npz hold the reference AttentionWorld / MlpWorld weights and, per step, the velocities the
-reference module predicted for the recorded human states.  Pure torch on the CPU: no CUDA involved."""
+"""Host side of the world models (crowd_nav/policy/world_model.py): the parameter containers carry the reference's state-dict
+keys and shapes (its checkpoints load unchanged) and refuse to compute on the CPU -- the forward is cn_world_predict
+(csrc/world_model.cu), checked against the reference's outputs in tests/test_gpu_facade.py."""
 import numpy as np
 import pytest
 
@@ -8,7 +8,7 @@ from conftest import MODEL_WORLD_NAMES, load_model_world
 
 
 @pytest.mark.parametrize("name", MODEL_WORLD_NAMES)
-def test_world_model_mirror_matches_reference(name):
+def test_world_model_containers_take_reference_checkpoints(name):
     import torch
     from modelcrowdnav_b200.world_model import AttentionWorld, MlpWorld
     g = load_model_world(name)
@@ -22,9 +22,6 @@ def test_world_model_mirror_matches_reference(name):
         off += v.numel()
     assert off == g["world_weights"].size
     world.load_state_dict(new)
-    world.eval()
-    for t in range(len(g["reward"])):
-        cur = torch.tensor(g["agents"][t][1:, :4], dtype=torch.float32).reshape(1, -1)     # px py vx vy per human
-        with torch.no_grad():
-            v = world(cur)[0].reshape(H, 2).numpy()
-        assert np.max(np.abs(v - g["new_v"][t])) <= 1e-6, t
+    assert np.array_equal(world.flat_weights(), g["world_weights"])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        world(torch.zeros((1, H * 4)))
