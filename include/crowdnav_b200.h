@@ -204,6 +204,10 @@ int cn_env_read_stats(cn_env *env, cn_stats *out, int reset, void *stream);
  * off every env runs ONE episode and then freezes, so after a roll-out row e IS the outcome of episode e: this is how
  * Explorer.run_k_episodes (explorer.py:36-151) gets its per-episode results without a host sync per step.
  * frozen_host (optional, E bytes): 1 = the env's episode has ended.  Blocking. */
+/* Outputs of the last cn_env_step copied device -> device into caller tensors (E doubles / E bytes each, any may be
+ * NULL), asynchronously on `stream`: a roll-out that fills the replay memory records its per-step rewards and done flags
+ * this way instead of reading them back (explorer.py:62-69,87-89).  A frozen env reports reward 0, done 1. */
+int cn_env_copy_outputs(cn_env *env, double *reward_dev, uint8_t *done_dev, uint8_t *info_dev, void *stream);
 int64_t cn_env_episode_table_bytes(const cn_env *env);
 int cn_env_read_episode_table(cn_env *env, void *table_host, uint8_t *frozen_host, void *stream);
 
@@ -301,6 +305,14 @@ int cn_selftest_umma_pair(int32_t N, int32_t K, const float *a_host, const float
 /* Developer diagnostic: clock64() at the phase boundaries of one tile of the tensor-core row kernel (CTA 0).
  * The first call arms the probes; call again after a lookahead to read 16 timestamps. */
 int cn_debug_tc_timing(cn_policy *p, long long *out16);
+/* CrowdSim.reset's scene generator on the host (crowd_sim.py:165-217,261-323), bit-identical to the reference: case i is
+ * drawn from numpy's legacy MT19937 stream seeded with seeds[i] (= counter_offset[phase] + case id, crowd_sim.py:282-286).
+ * rule = CN_CIRCLE_CROSSING / CN_SQUARE_CROSSING; agents_out: n x (human_num + 1) x 8 doubles in the exchange layout of
+ * cn_env_set_state.  Host-only, multi-threaded; no device work. */
+int cn_scenes_generate(int32_t n, const int64_t *seeds, int32_t human_num, int32_t rule, double circle_radius,
+                       double square_width, double human_radius, double human_v_pref, double discomfort_dist,
+                       double robot_radius, double robot_v_pref, int32_t randomize_attributes, double *agents_out);
+
 /* ---- learned human-motion models of ModelCrowdSim (crowd_nav/policy/world_model.py:20-106, model_crowd_sim.py:397-425) ----
  * cn_world_create: CN_WORLD_ATTENTION (AttentionWorld, any human count <= 32) or CN_WORLD_MLP (MlpWorld(human_num)).
  * cn_world_load_weights: flat fp32 HOST array in the torch state-dict order of the reference module (its checkpoints load

@@ -130,6 +130,12 @@ class BatchedCrowdSim(object):
         check(self.lib.cn_env_get_views(self.handle, C.byref(v)))
         return v
 
+    def copy_outputs_to(self, reward=None, done=None, info=None, stream=None):
+        """reward (E,) float64 / done, info (E,) uint8 CUDA tensors <- outputs of the last step, device to device, async."""
+        def p(t):
+            return None if t is None else C.c_void_p(t.data_ptr())
+        check(self.lib.cn_env_copy_outputs(self.handle, p(reward), p(done), p(info), _stream(stream)))
+
     def episode_table(self, stream=None):
         """Per-env episode accumulators (un-reduced cn_env_read_stats) + frozen flags: dict of (E,) arrays.  Blocking."""
         E = self.E

@@ -416,6 +416,16 @@ int cn_env_read_stats(cn_env *env, cn_stats *out, int reset, void *stream)
     return CN_OK;
 }
 
+int cn_env_copy_outputs(cn_env *env, double *reward_dev, uint8_t *done_dev, uint8_t *info_dev, void *stream)
+{
+    CN_ENV_ENTER(env);
+    const size_t E = env->p.d.E;
+    if (reward_dev) CN_CUDA_CHECK(cudaMemcpyAsync(reward_dev, env->reward, sizeof(double) * E, cudaMemcpyDeviceToDevice, s));
+    if (done_dev) CN_CUDA_CHECK(cudaMemcpyAsync(done_dev, env->done, E, cudaMemcpyDeviceToDevice, s));
+    if (info_dev) CN_CUDA_CHECK(cudaMemcpyAsync(info_dev, env->info, E, cudaMemcpyDeviceToDevice, s));
+    return CN_OK;
+}
+
 int64_t cn_env_episode_table_bytes(const cn_env *env) { return env ? (int64_t)env->p.d.E * 8 * 11 : 0; }
 
 int cn_env_read_episode_table(cn_env *env, void *table_host, uint8_t *frozen_host, void *stream)

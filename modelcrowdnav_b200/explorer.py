@@ -135,7 +135,7 @@ class Explorer(object):
             raise NotImplementedError("robot kinematics must be holonomic, unicycle or None (the fork's literal behaviour)")
         cases = env.next_cases(phase, k, test_case)
         kw = env.scene_kwargs(phase)
-        scene_list = [scenes.generate_scene(phase, int(c), **kw) for c in cases]
+        scene_list = list(scenes.generate_batch(phase, cases, **kw))       # native generator for plain seeded scenes
         sizes = sorted(set(a.shape[0] for a in scene_list))
         if len(sizes) > 1:
             # 'mixed' scenes (crowd_sim.py:111-161) draw their own human count: one batch per count, merged in case order
@@ -181,10 +181,18 @@ class Explorer(object):
 
         max_steps = int(round(env.time_limit / dt)) + 2
         gamma = self.gamma if self.gamma is not None else 1.0
-        if not update_memory and (stay or is_sarl or isinstance(policy, ORCA)):
+        if stay or is_sarl or isinstance(policy, ORCA):
             humans = (lambda: env.world_step_batch(b)) if world_env else b.orca     # world model or ORCA, both on the device
+            record = None
+            if update_memory:
+                # policy.last_state = transform(state) (multi_human_rl.py:60-61) / target_policy.transform (explorer.py:163)
+                if not isinstance(tr_policy, SARL):
+                    raise ValueError("update_memory needs a SARL policy (or target_policy) to transform states")
+                th = tr_policy.handle(v_pref)
+                # RL: predict()'s last_state (LSTM-RL rows in its sorted human order); IL: plain transform()
+                record = (lambda: th.transform(b, last_state=not imitation_learning), isinstance(tr_policy, CADRL))
             return self._rollout_device(b, k, max_steps, stay, is_sarl, policy, handle if is_sarl else None,
-                                        eps if is_sarl else 0.0, humans)
+                                        eps if is_sarl else 0.0, humans, record)
 
         active = np.ones(k, bool)
         rewards_t, states_t, active_t = [], [], []
@@ -241,17 +249,30 @@ class Explorer(object):
         return dict(R=R, M=M, final_info=final_info, end_time=end_time, too_close=too_close, min_dist_sum=min_dist_sum,
                     states_t=states_t, returns=(R * disc[:, None]).sum(0), steps=M.sum(0))
 
-    def _rollout_device(self, b, k, max_steps, stay, is_sarl, policy, handle, eps, humans):
-        """Episodes of a batch with NO host sync per step (val / test phases): kernels back to back, outcomes from the per-env
-        episode accumulators.  Finished envs freeze (auto_reset off), so extra steps are harmless; every `check` steps the
-        frozen flags (k bytes) are read to stop as soon as the last episode has ended."""
+    def _rollout_device(self, b, k, max_steps, stay, is_sarl, policy, handle, eps, humans, record=None):
+        """Episodes of a batch with NO host sync per step: kernels back to back, outcomes from the per-env episode
+        accumulators.  Finished envs freeze (auto_reset off), so extra steps are harmless; every `check` steps the frozen flags
+        (k bytes) are read to stop as soon as the last episode has ended.  record = (state_fn, squeeze): replay-filling phases
+        also keep, per step, the transformed state and the reward / done outputs as DEVICE tensors."""
+        import torch
         b.stats(reset=True)                             # zero the accumulators (set_state cleared the per-episode parts)
         if is_sarl:
             bad0 = handle.bad_count()
         if stay:
             b.set_actions(np.zeros((k, 2)))
-        check = 8
+        states_t, R, D = [], None, None
+        if record is not None:
+            dev = torch.device("cuda", b.device)
+            R = torch.zeros((max_steps, k), dtype=torch.float64, device=dev)
+            D = torch.ones((max_steps, k), dtype=torch.uint8, device=dev)
+        check, steps_run = 8, 0
         for step in range(max_steps):
+            if record is not None:
+                st = record[0]()
+                if record[1]:
+                    assert st.shape[1] == 1                        # cadrl.py:209: CADRL trains on single-human states
+                    st = st[:, 0]
+                states_t.append(st)
             humans()
             if stay:
                 pass                                    # pending action stays (0, 0)
@@ -260,6 +281,9 @@ class Explorer(object):
             else:
                 b.robot_orca(policy.safety_space)
             b.step(update=True, read=False)
+            if record is not None:
+                b.copy_outputs_to(R[step], D[step])
+            steps_run = step + 1
             if step % check == check - 1 and b.all_done():
                 break
         t = b.episode_table()
@@ -270,8 +294,14 @@ class Explorer(object):
         final_info = np.where(t["success"] == 1, _capi.REACHGOAL, np.where(t["collision"] == 1, _capi.COLLISION, _capi.TIMEOUT))
         end_time = np.where(t["success"] == 1, t["sum_success_time"],
                             np.where(t["collision"] == 1, t["sum_collision_time"], t["sum_timeout_time"]))
-        return dict(R=None, M=None, final_info=final_info.astype(np.int64), end_time=end_time,
-                    too_close=int(t["too_close"].sum()), min_dist_sum=float(t["sum_min_dist"].sum()), states_t=None,
+        M = None
+        if record is not None:
+            R, D = R[:steps_run], D[:steps_run]
+            # env e was active in step t iff it had not finished before it: done stays 1 once an env is frozen
+            M = torch.cat([torch.ones((1, k), dtype=torch.bool, device=D.device), D[:-1] == 0])
+            states_t = states_t[:steps_run]
+        return dict(R=R, M=M, final_info=final_info.astype(np.int64), end_time=end_time,
+                    too_close=int(t["too_close"].sum()), min_dist_sum=float(t["sum_min_dist"].sum()), states_t=states_t,
                     returns=t["sum_return"].copy(), steps=t["steps"].copy())
 
     def _summarise(self, k, phase, cases, r, update_memory, imitation_learning, episode, print_failure, stay, returnRate,
@@ -349,8 +379,9 @@ class Explorer(object):
         T = R.shape[0]
         dev = S.device
         gamma_bar = pow(self.gamma, self.robot.time_step * self.robot.v_pref)
-        Rk = torch.as_tensor(R[:, keep], dtype=torch.float64, device=dev)          # (T, n); zero after an episode's end
-        Mk = torch.as_tensor(M[:, keep], device=dev)
+        keep_t = torch.as_tensor(np.asarray(keep), device=dev)
+        Rk = torch.as_tensor(R, dtype=torch.float64, device=dev)[:, keep_t]        # (T, n); zero after an episode's end
+        Mk = torch.as_tensor(M, device=dev)[:, keep_t]
         if imitation_learning:
             # value_i = sum_{t >= i} gamma_bar^(t - i) r_t (explorer.py:161-166) = revcumsum(r_t gamma_bar^t)_i / gamma_bar^i
             wgt = torch.pow(torch.tensor(gamma_bar, dtype=torch.float64, device=dev),
@@ -366,5 +397,5 @@ class Explorer(object):
             last = Mk & ~torch.cat([Mk[1:], torch.zeros_like(Mk[:1])])
             V = torch.where(last, Rk, Rk + gamma_bar * nxt)
         jj, tt = torch.nonzero(Mk.t(), as_tuple=True)                              # episode-major, time-minor
-        ee = torch.as_tensor(np.asarray(keep), device=dev)[jj]
+        ee = keep_t[jj]
         self.memory.push_batch(S[tt, ee], V[tt, jj].float())

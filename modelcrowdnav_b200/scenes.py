@@ -111,4 +111,24 @@ def generate_scene(phase, case, human_num=5, rule="circle_crossing", circle_radi
 
 
 def generate_batch(phase, cases, **kw):
-    return np.stack([generate_scene(phase, int(c), **kw) for c in cases])
+    """Scenes of many cases at once.  Plain circle / square crossing scenes seeded per case go through the native generator
+    of the C ABI (cn_scenes_generate: the same MT19937 stream and arithmetic, bit-identical, ~1000x faster than the Python
+    loop); 'mixed' scenes, the global-stream / initial-velocity variants of ModelCrowdSim stay in Python."""
+    cases = [int(c) for c in cases]
+    rule = kw.get("rule", "circle_crossing")
+    if rule in ("circle_crossing", "square_crossing") and kw.get("rs") is None and not kw.get("init_velocity") and cases:
+        import ctypes as C
+        from . import _capi
+        lib = _capi.load()
+        H = int(kw.get("human_num", 5))
+        seeds = np.array([COUNTER_OFFSET[phase] + c for c in cases], dtype=np.int64)
+        out = np.empty((len(cases), H + 1, 8), np.float64)
+        _capi.check(lib.cn_scenes_generate(len(cases), seeds.ctypes.data_as(C.c_void_p), H,
+                                           _capi.CIRCLE_CROSSING if rule == "circle_crossing" else _capi.SQUARE_CROSSING,
+                                           float(kw.get("circle_radius", 4.0)), float(kw.get("square_width", 10.0)),
+                                           float(kw.get("human_radius", 0.3)), float(kw.get("human_v_pref", 1.0)),
+                                           float(kw.get("discomfort_dist", 0.2)), float(kw.get("robot_radius", 0.3)),
+                                           float(kw.get("robot_v_pref", 1.0)), int(bool(kw.get("randomize_attributes", False))),
+                                           out.ctypes.data_as(C.c_void_p)))
+        return out
+    return np.stack([generate_scene(phase, c, **kw) for c in cases])

@@ -23,6 +23,27 @@ import torch.nn as nn
 import torch.optim as optim
 
 
+def sample_batches(n, b, num_batches, device):
+    """(num_batches, b) indices into a memory of n items; every row is a uniform sample WITHOUT replacement in random order
+    -- the head of a fresh shuffle, what next(iter(DataLoader(shuffle=True))) yields (trainer.py:68).  Drawn with replacement
+    and repaired: rows of b << n items rarely collide (b^2 / 2n), so a few re-draws of the colliding entries converge; the
+    exact fallback (b largest of n uniform keys per row) only runs if collisions survive, e.g. for n close to b."""
+    if b >= n:
+        return torch.stack([torch.randperm(n, device=device)[:b] for _ in range(num_batches)])
+    idx = torch.randint(n, (num_batches, b), device=device)
+    for _ in range(6):
+        srt, order = torch.sort(idx, dim=1)
+        dup_sorted = torch.zeros_like(srt, dtype=torch.bool)
+        dup_sorted[:, 1:] = srt[:, 1:] == srt[:, :-1]
+        dup = torch.zeros_like(dup_sorted).scatter_(1, order, dup_sorted)
+        if not bool(dup.any()):                   # one small host sync per round; almost always the first or second
+            return idx
+        idx = torch.where(dup, torch.randint(n, idx.shape, device=device), idx)
+    rows = max(1, min(num_batches, (1 << 25) // n))
+    return torch.cat([torch.rand((min(rows, num_batches - i), n), device=device).topk(b, dim=1).indices
+                      for i in range(0, num_batches, rows)])
+
+
 class Trainer(object):
     def __init__(self, model, memory, device, batch_size, dist_group=None, policy=None, mode=None):
         self.model = model
@@ -116,6 +137,8 @@ class Trainer(object):
             x, y = inputs.clone(), values.clone()
             # warm-up on a side stream (allocates the gradients and the momentum buffers), restoring the weights after
             saved = [p.detach().clone() for p in self.model.parameters()]
+            saved_mom = {id(p): st["momentum_buffer"].detach().clone() for p, st in self.optimizer.state.items()
+                         if st.get("momentum_buffer") is not None}
             s = torch.cuda.Stream(device=self.device)
             s.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(s):
@@ -128,9 +151,12 @@ class Trainer(object):
             with torch.no_grad():
                 for p, q in zip(self.model.parameters(), saved):
                     p.copy_(q)
-                for st in self.optimizer.state.values():
-                    if "momentum_buffer" in st and st["momentum_buffer"] is not None:
-                        st["momentum_buffer"].zero_()
+                for p, st in self.optimizer.state.items():
+                    if st.get("momentum_buffer") is not None:       # a fresh optimiser starts from zero momentum
+                        if id(p) in saved_mom:
+                            st["momentum_buffer"].copy_(saved_mom[id(p)])
+                        else:
+                            st["momentum_buffer"].zero_()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 self.optimizer.zero_grad(set_to_none=False)
@@ -198,9 +224,7 @@ class Trainer(object):
         mdev = self.memory.states.device
         losses = torch.zeros((), dtype=torch.float32, device=self.device)
         b = min(self.batch_size, n)
-        # one (num_batches, b) index matrix: row i = the head of an independent uniform shuffle of the memory
-        idx = torch.rand((num_batches, n), device=mdev).topk(b, dim=1).indices if n <= 4096 else \
-            torch.stack([torch.randperm(n, device=mdev)[:b] for _ in range(num_batches)])
+        idx = sample_batches(n, b, num_batches, mdev)
         for i in range(num_batches):
             losses += self._step(idx[i]).to(self.device)
         average_loss = float(losses.item()) / num_batches

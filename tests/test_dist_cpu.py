@@ -172,3 +172,22 @@ def test_product_scene_generator_matches_reference_fixture(oracle_mod):
     for case, rec in tr["cases"].items():
         phase, c = case.split("_")
         assert np.array_equal(scenes.generate_scene(phase, int(c)), rec["agents"][0])
+
+
+def test_native_scene_generator_is_bit_identical():
+    """cn_scenes_generate (csrc/scenes_host.cu: MT19937 + crowd_sim.py:165-217 in C++) == the Python generator that the
+    reference fixtures pin, for every rule / attribute combination it covers; out-of-range seeds are refused like numpy's."""
+    import ctypes as C
+    from modelcrowdnav_b200 import _capi, scenes
+    for kw in (dict(), dict(rule="square_crossing", human_num=10), dict(randomize_attributes=True, human_num=7),
+               dict(rule="square_crossing", human_num=3, randomize_attributes=True), dict(human_num=1, circle_radius=5.0)):
+        for phase in ("train", "val", "test"):
+            cases = list(range(40)) + [499, 31337]
+            a = scenes.generate_batch(phase, cases, **kw)
+            b = np.stack([scenes.generate_scene(phase, c, **kw) for c in cases])
+            assert np.array_equal(a, b), (kw, phase)
+    seeds = np.array([-1], np.int64)
+    out = np.zeros((1, 6, 8))
+    rc = _capi.load().cn_scenes_generate(1, seeds.ctypes.data_as(C.c_void_p), 5, 0, 4.0, 10.0, 0.3, 1.0, 0.2, 0.3, 1.0, 0,
+                                         out.ctypes.data_as(C.c_void_p))
+    assert rc == _capi.CN_EINVAL
