@@ -11,39 +11,60 @@ constexpr int kThreads = 256;
 __host__ __device__ __forceinline__ int pad4(int x) { return (x + 3) & ~3; }
 
 // Y[r][o] = act(b[o] + sum_k X[r * ldx + k] * Wt[k * O + o]),  r < R, o < O.   Wt is [K][O] in global memory (coalesced over
-// o); X lives in shared memory.  One thread = 4 rows x 1 output, K walked in steps of 4 (LDS.128 of X, broadcast in a warp).
+// o); X lives in shared memory.  One thread = kRowsPerItem rows x 1 output: with R <= 8 every weight is fetched ONCE per CTA.
+// K is walked 16 at a time with the 16 weight loads issued before any FMA: the loop is bound by the L2 latency of those loads
+// (a CTA has 256 threads and no other work to hide it), so loads in flight per thread are what sets the speed.
+constexpr int kRowsPerItem = 8;
 __device__ __forceinline__ void dense(const float *__restrict__ X, int ldx, int R, int K, const float *__restrict__ Wt,
                                       const float *__restrict__ b, int O, float *__restrict__ Y, int ldy, bool relu, bool accumulate)
 {
-    const int groups = (R + 3) >> 2;
+    const int groups = (R + kRowsPerItem - 1) / kRowsPerItem;
     for (int idx = threadIdx.x; idx < O * groups; idx += kThreads) {
-        const int o = idx % O, r0 = (idx / O) * 4;
-        float acc[4];
+        const int o = idx % O, r0 = (idx / O) * kRowsPerItem;
+        float acc[kRowsPerItem];
         const float bias = b ? b[o] : 0.0f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[i] = bias;
+        for (int i = 0; i < kRowsPerItem; ++i) acc[i] = bias;
         const float *x0 = X + (size_t)r0 * ldx;
-        const int nr = min(4, R - r0);
+        const int nr = min(kRowsPerItem, R - r0);
+        const float *wp = Wt + o;
         int k = 0;
-        for (; k + 4 <= K; k += 4) {
-            const float w0 = Wt[(size_t)k * O + o], w1 = Wt[(size_t)(k + 1) * O + o];
-            const float w2 = Wt[(size_t)(k + 2) * O + o], w3 = Wt[(size_t)(k + 3) * O + o];
+        for (; k + 16 <= K; k += 16) {                   // 16 independent L2 loads in flight per thread
+            float w[16];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int j = 0; j < 16; ++j) w[j] = __ldg(wp + (size_t)(k + j) * O);
+#pragma unroll
+            for (int i = 0; i < kRowsPerItem; ++i) {
+                if (i < nr) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 x = *reinterpret_cast<const float4 *>(x0 + (size_t)i * ldx + k + 4 * q);
+                        acc[i] = fmaf(x.x, w[4 * q], acc[i]); acc[i] = fmaf(x.y, w[4 * q + 1], acc[i]);
+                        acc[i] = fmaf(x.z, w[4 * q + 2], acc[i]); acc[i] = fmaf(x.w, w[4 * q + 3], acc[i]);
+                    }
+                }
+            }
+        }
+        for (; k + 4 <= K; k += 4) {
+            float w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j] = __ldg(wp + (size_t)(k + j) * O);
+#pragma unroll
+            for (int i = 0; i < kRowsPerItem; ++i) {
                 if (i < nr) {
                     const float4 x = *reinterpret_cast<const float4 *>(x0 + (size_t)i * ldx + k);
-                    acc[i] = fmaf(x.x, w0, acc[i]); acc[i] = fmaf(x.y, w1, acc[i]);
-                    acc[i] = fmaf(x.z, w2, acc[i]); acc[i] = fmaf(x.w, w3, acc[i]);
+                    acc[i] = fmaf(x.x, w[0], acc[i]); acc[i] = fmaf(x.y, w[1], acc[i]);
+                    acc[i] = fmaf(x.z, w[2], acc[i]); acc[i] = fmaf(x.w, w[3], acc[i]);
                 }
             }
         }
         for (; k < K; ++k) {
-            const float w = Wt[(size_t)k * O + o];
+            const float w = __ldg(wp + (size_t)k * O);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) if (i < nr) acc[i] = fmaf(x0[(size_t)i * ldx + k], w, acc[i]);
+            for (int i = 0; i < kRowsPerItem; ++i) if (i < nr) acc[i] = fmaf(x0[(size_t)i * ldx + k], w, acc[i]);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < kRowsPerItem; ++i) {
             if (i < nr) {
                 float v = acc[i];
                 if (accumulate) v += Y[(size_t)(r0 + i) * ldy + o];

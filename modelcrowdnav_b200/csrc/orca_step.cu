@@ -249,6 +249,8 @@ __global__ void __launch_bounds__(128) orca_robot_kernel(EnvParams p, const doub
     action_idx[e] = -1;
 }
 
+constexpr int kWarpResetHumans = 16;     // from this human count on, device resets run one warp per env (reset_env_warp)
+
 // K2: CrowdSim.step for one env per thread (crowd_sim.py:344-434).
 // CrowdSim.reset on the device for ONE env: crowd_sim.py:165-217 distributions and rejection rule; Philox stream
 // keyed by (seed, global env id, episode counter).
@@ -414,6 +416,99 @@ __global__ void __launch_bounds__(128) step_kernel(EnvParams p, double *__restri
     }
 }
 
+// CrowdSim.reset of ONE env by a whole WARP, for crowds where the rejection sampling dominates (H = 50 in a 10 m square: every
+// human is re-drawn several times and checked against up to 50 earlier agents -- the thread-per-env form took 1.3 ms of a
+// 6.7 ms step, profiles/r02a_bench.json).  Every lane runs the SAME Philox stream, so the draws and the accept / reject
+// decisions are those of reset_env; only the distance checks against the earlier agents are split over the lanes
+// (agent a = lane, lane + 32, ...) and joined by a warp vote.  Bit-identical scenes (tests: shard invariance, properties).
+__device__ void reset_env_warp(const EnvParams &p, int e, int lane, double *__restrict__ st, double *__restrict__ time,
+                               uint8_t *__restrict__ frozen, const EnvAccum &acc, double *__restrict__ theta)
+{
+    const EnvDims d = p.d;
+    PhiloxStream rng;
+    rng.init(p.seed, (uint64_t)(p.env_id_offset + e), acc.episode_ctr[e], 0u);
+    __syncwarp();
+    if (lane == 0) acc.episode_ctr[e] += 1;
+    const double PI = 3.141592653589793;
+    if (lane == 0) {
+        st[st_idx(d, F_PX, 0, e)] = 0.0; st[st_idx(d, F_PY, 0, e)] = -p.circle_radius;
+        st[st_idx(d, F_VX, 0, e)] = 0.0; st[st_idx(d, F_VY, 0, e)] = 0.0;
+        st[st_idx(d, F_GX, 0, e)] = 0.0; st[st_idx(d, F_GY, 0, e)] = p.circle_radius;
+        st[st_idx(d, F_R, 0, e)] = p.robot_radius; st[st_idx(d, F_VPREF, 0, e)] = p.robot_v_pref;
+    }
+    __syncwarp();
+    const int MAX_TRIES = 4096;
+    for (int i = 1; i <= d.H; ++i) {
+        double px = 0, py = 0, gx = 0, gy = 0;
+        double h_radius = p.human_radius, h_v_pref = p.human_v_pref;
+        if (p.randomize_attributes) {
+            h_v_pref = 0.5 + (1.5 - 0.5) * rng.next();
+            h_radius = 0.3 + (0.5 - 0.3) * rng.next();
+        }
+        if (p.sim_rule == CN_CIRCLE_CROSSING) {
+            for (int tries = 0; tries < MAX_TRIES; ++tries) {
+                const double angle = rng.next() * PI * 2;
+                const double px_noise = (rng.next() - 0.5) * h_v_pref;
+                const double py_noise = (rng.next() - 0.5) * h_v_pref;
+                px = p.circle_radius * cos(angle) + px_noise;
+                py = p.circle_radius * sin(angle) + py_noise;
+                bool collide = false;
+                for (int a = lane; a < i; a += 32) {
+                    const double min_dist = h_radius + st[st_idx(d, F_R, a, e)] + p.discomfort_dist;
+                    collide = collide || norm2d(px - st[st_idx(d, F_PX, a, e)], py - st[st_idx(d, F_PY, a, e)]) < min_dist ||
+                              norm2d(px - st[st_idx(d, F_GX, a, e)], py - st[st_idx(d, F_GY, a, e)]) < min_dist;
+                }
+                if (!__any_sync(0xffffffffu, collide)) break;
+            }
+            gx = -px; gy = -py;
+        } else {
+            const double sign = (rng.next() > 0.5) ? -1.0 : 1.0;
+            for (int tries = 0; tries < MAX_TRIES; ++tries) {
+                px = rng.next() * p.square_width * 0.5 * sign;
+                py = (rng.next() - 0.5) * p.square_width;
+                bool collide = false;
+                for (int a = lane; a < i; a += 32)
+                    collide = collide || norm2d(px - st[st_idx(d, F_PX, a, e)], py - st[st_idx(d, F_PY, a, e)]) <
+                                             h_radius + st[st_idx(d, F_R, a, e)] + p.discomfort_dist;
+                if (!__any_sync(0xffffffffu, collide)) break;
+            }
+            for (int tries = 0; tries < MAX_TRIES; ++tries) {
+                gx = rng.next() * p.square_width * 0.5 * -sign;
+                gy = (rng.next() - 0.5) * p.square_width;
+                bool collide = false;
+                for (int a = lane; a < i; a += 32)
+                    collide = collide || norm2d(gx - st[st_idx(d, F_GX, a, e)], gy - st[st_idx(d, F_GY, a, e)]) <
+                                             h_radius + st[st_idx(d, F_R, a, e)] + p.discomfort_dist;
+                if (!__any_sync(0xffffffffu, collide)) break;
+            }
+        }
+        if (lane == 0) {
+            st[st_idx(d, F_PX, i, e)] = px; st[st_idx(d, F_PY, i, e)] = py;
+            st[st_idx(d, F_VX, i, e)] = 0.0; st[st_idx(d, F_VY, i, e)] = 0.0;
+            st[st_idx(d, F_GX, i, e)] = gx; st[st_idx(d, F_GY, i, e)] = gy;
+            st[st_idx(d, F_R, i, e)] = h_radius; st[st_idx(d, F_VPREF, i, e)] = h_v_pref;
+        }
+        __syncwarp();                                     // agent i is visible to every lane's checks of agent i + 1
+    }
+    if (lane == 0) {
+        time[e] = 0.0;
+        theta[e] = 1.5707963267948966;
+        frozen[e] = 0;
+        acc.ep_steps[e] = 0; acc.ep_return[e] = 0.0;
+    }
+}
+
+// One WARP per env: the form of reset_kernel for large crowds (see reset_env_warp).
+__global__ void __launch_bounds__(128) reset_warp_kernel(EnvParams p, double *__restrict__ st, double *__restrict__ time,
+                                                         const uint8_t *__restrict__ done, int only_done,
+                                                         uint8_t *__restrict__ frozen, EnvAccum acc, double *__restrict__ theta)
+{
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (e >= p.d.E) return;                      // warp-uniform
+    if (only_done && !done[e]) return;
+    reset_env_warp(p, e, lane, st, time, frozen, acc, theta);
+}
+
 // One thread per env (explicit resets, and the auto-reset of finished episodes when it is not fused into step_kernel).
 __global__ void __launch_bounds__(128) reset_kernel(EnvParams p, double *__restrict__ st, double *__restrict__ time,
                                                     const uint8_t *__restrict__ done, int only_done,
@@ -552,19 +647,28 @@ int cn_launch_step(cn_env *env, const double *action_xy_dev, int update, cudaStr
 {
     const double *act = action_xy_dev ? action_xy_dev : env->action_xy;
     const int bs = cn_small_block();
+    // large crowds: the re-generation of finished episodes is a warp-per-env kernel of its own instead of one thread of the
+    // step kernel doing the whole rejection sampling while its warp waits
+    const bool split_reset = fuse_reset && update && env->p.d.H >= kWarpResetHumans;
+    if (split_reset) fuse_reset = 0;
     step_kernel<<<grid_for(env->p.d.E, bs), bs, 0, s>>>(env->p, env->state, env->time, env->human_v, act,
                                                             action_xy_dev ? 1 : 0, update, env->reward, env->done,
                                                             env->info, env->dmin, env->next_obs, env->frozen,
                                                             env->acc, env->theta, fuse_reset);
     CN_LAUNCH_CHECK();
     if (update) env->orca_valid = 0;
+    if (split_reset) return cn_launch_reset(env, 1, s);
     return CN_OK;
 }
 
 int cn_launch_reset(cn_env *env, int only_done, cudaStream_t s)
 {
     const int bs = cn_small_block();
-    reset_kernel<<<grid_for(env->p.d.E, bs), bs, 0, s>>>(env->p, env->state, env->time, env->done, only_done,
+    if (env->p.d.H >= kWarpResetHumans)
+        reset_warp_kernel<<<grid_for(env->p.d.E * 32, 128), 128, 0, s>>>(env->p, env->state, env->time, env->done, only_done,
+                                                                          env->frozen, env->acc, env->theta);
+    else
+        reset_kernel<<<grid_for(env->p.d.E, bs), bs, 0, s>>>(env->p, env->state, env->time, env->done, only_done,
                                                              env->frozen, env->acc, env->theta);
     CN_LAUNCH_CHECK();
     env->orca_valid = 0;

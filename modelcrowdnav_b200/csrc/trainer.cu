@@ -25,7 +25,7 @@
 namespace {
 
 using namespace dense_f32;      // kThreads, pad4, dense, weight_grad, relu_mask
-constexpr int kSPC = 2;           // samples per CTA
+constexpr int kSPC = 1;           // samples per CTA: 100 CTAs for the reference batch of 100; H <= 8 rows = one weight pass per layer
 constexpr int kMaxH = 16;         // humans per sample supported by the shared-memory plan
 constexpr int kLayers = 11;
 

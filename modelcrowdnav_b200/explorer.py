@@ -95,6 +95,8 @@ class Explorer(object):
         self.dist_group = dist_group     # optional torch.distributed group: statistics are all-reduced over ranks
         self._batches = {}
         self._target_handle = None
+        self.profile = False             # True: synchronise between the phases of run_k_episodes and keep seconds in last_timing
+        self.last_timing = {}
 
     def update_target_model(self, target_model):
         """explorer.py:24-25: keep a frozen copy for TD targets; its weights also go to the FP32 CUDA network."""
@@ -133,9 +135,15 @@ class Explorer(object):
             raise NotImplementedError("raw-observation / SGAN caches belong to the model-based branch (out of scope)")
         if robot.kinematics not in ("holonomic", "unicycle", None):
             raise NotImplementedError("robot kinematics must be holonomic, unicycle or None (the fork's literal behaviour)")
+        import time
+        t_start = time.perf_counter()
         cases = env.next_cases(phase, k, test_case)
         kw = env.scene_kwargs(phase)
-        scene_list = list(scenes.generate_batch(phase, cases, **kw))       # native generator for plain seeded scenes
+        if kw.get("rule") == "mixed":                                       # ragged: every scene draws its own human count
+            scene_list = [scenes.generate_scene(phase, int(c), **kw) for c in cases]
+        else:
+            scene_list = list(scenes.generate_batch(phase, cases, **kw))   # native generator for plain seeded scenes
+        t_scenes = time.perf_counter()
         sizes = sorted(set(a.shape[0] for a in scene_list))
         if len(sizes) > 1:
             # 'mixed' scenes (crowd_sim.py:111-161) draw their own human count: one batch per count, merged in case order
@@ -152,8 +160,16 @@ class Explorer(object):
                 r["too_close"] += part["too_close"]; r["min_dist_sum"] += part["min_dist_sum"]
         else:
             r = self._rollout(np.stack(scene_list), phase, update_memory, imitation_learning, stay)
-        return self._summarise(k, phase, cases, r, update_memory, imitation_learning, episode, print_failure, stay, returnRate,
-                               returnNav)
+        if self.profile:
+            torch.cuda.synchronize()
+        t_roll = time.perf_counter()
+        out = self._summarise(k, phase, cases, r, update_memory, imitation_learning, episode, print_failure, stay, returnRate,
+                              returnNav)
+        if self.profile:
+            torch.cuda.synchronize()
+            self.last_timing = {"scenes": t_scenes - t_start, "rollout": t_roll - t_scenes,
+                                "targets_and_replay": time.perf_counter() - t_roll}
+        return out
 
     def _rollout(self, agents, phase, update_memory, imitation_learning, stay):
         """k episodes with the same human count side by side (explorer.py:53-69 for every env of the batch)."""

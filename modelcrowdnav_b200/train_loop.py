@@ -180,6 +180,7 @@ def bench_train(a):
     torch.cuda.synchronize(device)
     il_s = time.perf_counter() - t0
     loop.start_rl()
+    loop.explorer.profile = True
 
     def barrier():
         if world > 1:

@@ -276,10 +276,14 @@ def test_episode_stats_and_freeze(mcn, oracle_mod, weights0):
     env.close(); pol.close()
 
 
-def test_device_reset_properties(mcn):
-    """Device-side reset: scene invariants of crowd_sim.py:165-217 and shard invariance (global env id)."""
-    E, H = 512, 5
+@pytest.mark.parametrize("H", [5, 20])
+def test_device_reset_properties(mcn, H):
+    """Device-side reset: scene invariants of crowd_sim.py:165-217 and shard invariance (global env id).  H = 20 takes the
+    warp-per-env generator (reset_env_warp), H = 5 the thread-per-env one."""
+    E = 512
     for rule, name in ((0, "circle"), (1, "square")):
+        if H > 5 and rule == 0:
+            continue                                    # 20 humans do not fit the radius-4 circle under the separation rule
         env = mcn.BatchedCrowdSim(E, H, sim_rule=rule, seed=7)
         env.reset_device()
         a, t = env.get_state()
