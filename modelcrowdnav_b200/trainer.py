@@ -157,19 +157,43 @@ class Trainer(object):
                             st["momentum_buffer"].copy_(saved_mom[id(p)])
                         else:
                             st["momentum_buffer"].zero_()
+            params = [p for p in self.model.parameters()]
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                self.optimizer.zero_grad(set_to_none=False)
-                loss = self.criterion(self.model(x), y)
-                loss.backward()
-                self._sync_gradients()
-                self.optimizer.step()
+            graph2, flat = None, None
+            if self.dist_group is None:
+                with torch.cuda.graph(graph):
+                    self.optimizer.zero_grad(set_to_none=False)
+                    loss = self.criterion(self.model(x), y)
+                    loss.backward()
+                    self.optimizer.step()
+            else:
+                # data parallel: the NCCL all-reduce stays OUTSIDE the captured work (the process group's watchdog thread
+                # polls CUDA events, which is not allowed while a capture is open): graph 1 = forward + backward + gradient
+                # bucket, eager all-reduce of the one 386 kB bucket, graph 2 = un-bucket + SGD step
+                with torch.cuda.graph(graph):
+                    self.optimizer.zero_grad(set_to_none=False)
+                    loss = self.criterion(self.model(x), y)
+                    loss.backward()
+                    flat = torch.cat([p.grad.reshape(-1) for p in params])
+                graph2 = torch.cuda.CUDAGraph()
+                scale = 1.0 / self._world()
+                with torch.cuda.graph(graph2, pool=graph.pool()):
+                    off = 0
+                    for p in params:
+                        n = p.grad.numel()
+                        p.grad.copy_(flat[off:off + n].view_as(p.grad) * scale)
+                        off += n
+                    self.optimizer.step()
             # SGD's first step copies the gradient into the momentum buffer (buf = grad) and later ones do
             # buf = mu * buf + grad; with the buffers zeroed above the captured "later" form covers both.
-            g = self._graphs[key] = (graph, x, y, loss)
-        graph, x, y, loss = g
+            g = self._graphs[key] = (graph, x, y, loss, graph2, flat)
+        graph, x, y, loss, graph2, flat = g
         x.copy_(inputs); y.copy_(values)
         graph.replay()
+        if graph2 is not None:
+            import torch.distributed as dist
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.dist_group)
+            graph2.replay()
         return loss
 
     def _step_tensors(self, inputs, values):
