@@ -345,6 +345,13 @@ int64_t cn_trainer_param_count(const cn_trainer *t);
 int cn_trainer_sync_weights(cn_trainer *t, const float *w_dev, int zero_momentum, void *stream);
 int cn_trainer_step(cn_trainer *t, float *w_dev, const float *states_dev, const float *targets_dev, int32_t batch,
                     int32_t human_num, float lr, float momentum, float *grad_out_dev, float *loss_dev, void *stream);
+/* The same step with the batch GATHERED inside the kernel: sample i = item index_dev[i] (int64, device) of the replay
+ * tensors memory_states_dev (capacity x human_num x input_dim fp32) / memory_values_dev (capacity fp32) -- what
+ * DataLoader + collate_fn do on the host in the reference (trainer.py:9-17,68).  loss_sum_dev (optional) is ADDED to, so a
+ * whole optimize_batch call reads the loss back once. */
+int cn_trainer_step_indexed(cn_trainer *t, float *w_dev, const float *memory_states_dev, const float *memory_values_dev,
+                            const int64_t *index_dev, int32_t batch, int32_t human_num, float lr, float momentum,
+                            float *grad_out_dev, float *loss_sum_dev, void *stream);
 int cn_trainer_apply(cn_trainer *t, float *w_dev, const float *grad_dev, float grad_scale, float lr, float momentum,
                      void *stream);
 

@@ -533,8 +533,8 @@ int cn_policy_create(const cn_sarl_cfg *cfg, int device, cn_policy **out)
     if (cfg->network != CN_NET_SARL && cfg->network != CN_NET_CADRL && cfg->network != CN_NET_LSTM_RL) {
         cn_set_error("unknown value network %d", cfg->network); return CN_EINVAL;
     }
-    if (cfg->network != CN_NET_SARL && cfg->precision != CN_PREC_F32) {
-        cn_set_error("CADRL / LSTM-RL lookaheads run on the FP32 path only (precision = CN_PREC_F32)"); return CN_EUNSUPPORTED;
+    if (cfg->network == CN_NET_LSTM_RL && cfg->precision != CN_PREC_F32) {
+        cn_set_error("the LSTM-RL lookahead runs on the FP32 path only (precision = CN_PREC_F32)"); return CN_EUNSUPPORTED;
     }
     if (cfg->network == CN_NET_LSTM_RL) {
         if (cfg->lstm_hidden < 1 || cfg->lstm_hidden > 64) { cn_set_error("1 <= lstm_hidden <= 64 required"); return CN_EINVAL; }
@@ -653,6 +653,10 @@ int cn_policy_load_weights(cn_policy *p, const float *flat, int64_t n, void *str
         CN_CUDA_CHECK(cudaMemcpyAsync(p->w_t, t.data(), sizeof(float) * t.size(), cudaMemcpyHostToDevice, s));
         CN_CUDA_CHECK(cudaMemcpyAsync(p->w_raw, flat, sizeof(float) * n, cudaMemcpyHostToDevice, s));
         CN_CUDA_CHECK(cudaStreamSynchronize(s));
+        if (p->cfg.precision == CN_PREC_F16_TC) {            // CADRL on tensor cores (tc_mlp3_pair_kernel<1>)
+            int rc = cn_tc_load_weights(p, flat, s);
+            if (rc) return rc;
+        }
         p->weights_loaded = 1;
         return CN_OK;
     }

@@ -78,6 +78,8 @@ struct TcState {
     float tail_a[104];        // attention.4 weight[100] + bias (kernel parameter of tc_rows_pair_kernel)
     float tail_b[104];        // mlp3.6 weight[100] + bias (kernel parameter of tc_mlp3_pair_kernel)
     uint8_t *img_pair_b;      // two half images of mlp3 for tc_mlp3_pair_kernel
+    float *rowv;              // CADRL: one value per (env, action, human) row (tc_mlp3_pair_kernel<1> -> cadrl_min_kernel)
+    size_t cap_rowv;
     int ktime_on;             // cn_debug_kernel_ms: CUDA events around each kernel of the lookahead, on the launching stream
     cudaEvent_t kev[5];       // before features | before rows | before mlp3 | before argmax | after argmax
 };
@@ -160,6 +162,21 @@ umma_selftest_kernel(const uint8_t *__restrict__ a_img, const uint8_t *__restric
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// CADRL scoring (cadrl.py:166-168): value = reward + gamma_bar * min over the humans of the group of the per-row network outputs
+__global__ void cadrl_min_kernel(EnvParams p, const double *__restrict__ st, const float *__restrict__ rowv,
+                                 const double *__restrict__ rew, int A, int NG, int G, int H, double gamma, double gamma_bar_host,
+                                 double v_pref_host, double *__restrict__ values)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= NG) return;
+    const size_t r0 = (size_t)(g / G) * ROWS + (size_t)(g % G) * H;
+    float m = rowv[r0];
+    for (int h = 1; h < H; ++h) m = fminf(m, rowv[r0 + h]);
+    const double vp = st[st_idx(p.d, F_VPREF, 0, g / A)];
+    const double gamma_bar = (vp == v_pref_host) ? gamma_bar_host : pow(gamma, p.time_step * vp);
+    values[g] = rew[g] + gamma_bar * (double)m;
+}
+
 // ---- host-side weight images ------------------------------------------------------------------------
 struct HostLinear { const float *w, *b; int in, out; };
 
@@ -199,13 +216,22 @@ void split_rows(uint8_t *dst, const uint8_t *src, int N, int K, int rank)
 int cn_tc_init(cn_policy *p)
 {
     const SarlDims &d = p->d;
-    const bool ok = d.in == 13 && d.self_dim == 6 && d.m1[0] == 150 && d.m1[1] == 100 && d.m2[0] == 100 && d.m2[1] == 50 &&
-                    d.at[0] == 100 && d.at[1] == 100 && d.at[2] == 1 && d.m3[0] == 150 && d.m3[1] == 100 &&
-                    d.m3[2] == 100 && d.m3[3] == 1;
-    if (!ok) {
-        cn_set_error("CN_PREC_F16_TC is specialised for the default [sarl] dims (150,100 / 100,50 / 100,100,1 / "
-                     "150,100,100,1); use CN_PREC_F32 for other shapes");
-        return CN_EUNSUPPORTED;
+    if (d.net == CN_NET_CADRL) {
+        // CADRL's value network = the three tensor-core stages of the mlp3 kernel (tc_mlp3_pair_kernel<1>)
+        if (!(d.in == 13 && d.m3[0] == 150 && d.m3[1] == 100 && d.m3[2] == 100 && d.m3[3] == 1)) {
+            cn_set_error("CN_PREC_F16_TC is specialised for the default [cadrl] mlp_dims (150, 100, 100, 1); use CN_PREC_F32 "
+                         "for other shapes");
+            return CN_EUNSUPPORTED;
+        }
+    } else {
+        const bool ok = d.net == CN_NET_SARL && d.in == 13 && d.self_dim == 6 && d.m1[0] == 150 && d.m1[1] == 100 &&
+                        d.m2[0] == 100 && d.m2[1] == 50 && d.at[0] == 100 && d.at[1] == 100 && d.at[2] == 1 &&
+                        d.m3[0] == 150 && d.m3[1] == 100 && d.m3[2] == 100 && d.m3[3] == 1;
+        if (!ok) {
+            cn_set_error("CN_PREC_F16_TC is specialised for the default [sarl] dims (150,100 / 100,50 / 100,100,1 / "
+                         "150,100,100,1) and the default [cadrl] mlp_dims; use CN_PREC_F32 for other shapes / networks");
+            return CN_EUNSUPPORTED;
+        }
     }
     TcState *t = new TcState();
     memset(t, 0, sizeof(*t));
@@ -215,7 +241,8 @@ int cn_tc_init(cn_policy *p)
     CN_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
     CN_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_pair_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
     CN_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_pair_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
-    CN_CUDA_CHECK(cudaFuncSetAttribute(tc_mlp3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M_SMEM));
+    CN_CUDA_CHECK(cudaFuncSetAttribute(tc_mlp3_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M_SMEM));
+    CN_CUDA_CHECK(cudaFuncSetAttribute(tc_mlp3_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M_SMEM));
     if (cudaMalloc((void **)&t->img_pair, 2 * IMG_H_BYTES) != cudaSuccess ||
         cudaMalloc((void **)&t->img_pair_b, 2 * IMG_HM_BYTES) != cudaSuccess) {
         cn_set_error("cudaMalloc failed for the tensor-core weight images");
@@ -234,6 +261,7 @@ void cn_tc_destroy(cn_policy *p)
     if (t->J) cudaFree(t->J);
     if (t->X) cudaFree(t->X);
     if (t->rew) cudaFree(t->rew);
+    if (t->rowv) cudaFree(t->rowv);
     if (t->dbg) cudaFree(t->dbg);
     if (t->kev[0]) for (int i = 0; i < 5; ++i) cudaEventDestroy(t->kev[i]);
     delete t;
@@ -244,6 +272,37 @@ int cn_tc_load_weights(cn_policy *p, const float *flat, cudaStream_t s)
 {
     TcState *t = (TcState *)p->tc;
     const SarlDims &d = p->d;
+    if (d.net == CN_NET_CADRL) {
+        // value_network.{0,2,4,6} (cadrl.py:22-26) as the three UMMA stages + the fp32 tail of tc_mlp3_pair_kernel<1>
+        HostLinear C[4];
+        const int ins[4] = {d.in, d.m3[0], d.m3[1], d.m3[2]};
+        const float *src = flat;
+        for (int i = 0; i < 4; ++i) {
+            C[i].w = src; src += (size_t)ins[i] * d.m3[i];
+            C[i].b = src; src += d.m3[i];
+            C[i].in = ins[i]; C[i].out = d.m3[i];
+        }
+        std::vector<uint8_t> b(IMG_B_BYTES, 0);
+        // layer 0 on X = [x_hi(13) 1 1 0 | x_lo(13) 0 0 0]: bias at k = 13, 14; ones -> n = 150, 151
+        fill_layer(b, OFF_M1, N_H1, C[0], 0, 13, 0, 13, 150);
+        fill_layer(b, OFF_M1, N_H1, C[0], 0, 13, 16, -1, -1);
+        fill_layer(b, OFF_M2, N_M1, C[1], 0, 150, 0, 150, 100);
+        fill_layer(b, OFF_M3, N_M1, C[2], 0, 100, 0, 100, -1);
+        float tail[TAIL_BYTES / 4] = {0};
+        for (int k = 0; k < 100; ++k) tail[k] = C[3].w[k];
+        tail[100] = C[3].b[0];
+        memcpy(t->tail_b, tail, sizeof(t->tail_b));
+        std::vector<uint8_t> hb(2 * IMG_HM_BYTES, 0);
+        for (int rank = 0; rank < 2; ++rank) {
+            uint8_t *h = hb.data() + (size_t)rank * IMG_HM_BYTES;
+            split_rows(h + HM_M1, b.data() + OFF_M1, N_H1, K_J, rank);
+            split_rows(h + HM_M2, b.data() + OFF_M2, N_M1, N_H1, rank);
+            split_rows(h + HM_M3, b.data() + OFF_M3, N_M1, N_M1, rank);
+        }
+        CN_CUDA_CHECK(cudaMemcpyAsync(t->img_pair_b, hb.data(), 2 * IMG_HM_BYTES, cudaMemcpyHostToDevice, s));
+        CN_CUDA_CHECK(cudaStreamSynchronize(s));
+        return CN_OK;
+    }
     HostLinear L[11];
     const int ins[11] = {d.in, d.m1[0], d.m1[1], d.m2[0], 2 * d.m1[1], d.at[0], d.at[1], d.m2[1] + d.self_dim, d.m3[0], d.m3[1], d.m3[2]};
     const int outs[11] = {d.m1[0], d.m1[1], d.m2[0], d.m2[1], d.at[0], d.at[1], d.at[2], d.m3[0], d.m3[1], d.m3[2], d.m3[3]};
@@ -355,6 +414,30 @@ int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cu
         CN_LAUNCH_CHECK();
         cn_trace_mark("rows", s);
         if (t->ktime_on) CN_CUDA_CHECK(cudaEventRecord(t->kev[1], s));
+        if (p->d.net == CN_NET_CADRL) {
+            // CADRL: the whole network runs on the X tiles, one value per row, then the minimum over each group's humans
+            if (xtiles * ROWS > t->cap_rowv) {
+                if (t->rowv) cudaFree(t->rowv);
+                t->rowv = nullptr; t->cap_rowv = 0;
+                CN_CUDA_CHECK(cudaMalloc((void **)&t->rowv, sizeof(float) * xtiles * ROWS));
+                t->cap_rowv = xtiles * ROWS;
+            }
+            TailW twb;
+            memcpy(twb.w, t->tail_b, sizeof(twb.w));
+            tc_mlp3_pair_kernel<1><<<2 * nclusters, kThreadsM3, M_SMEM, s>>>(env->p, env->state, t->img_pair_b, t->X, t->rew, A, (int)NG,
+                                                                            p->cfg.gamma, gamma_bar, p->cfg.v_pref, p->values, rounds,
+                                                                            twb, t->rowv);
+            CN_LAUNCH_CHECK();
+            if (t->ktime_on) CN_CUDA_CHECK(cudaEventRecord(t->kev[2], s));
+            cadrl_min_kernel<<<(unsigned)((NG + 255) / 256), 256, 0, s>>>(env->p, env->state, t->rowv, t->rew, A, (int)NG, G, ed.H,
+                                                                          p->cfg.gamma, gamma_bar, p->cfg.v_pref, p->values);
+            CN_LAUNCH_CHECK();
+            cn_trace_mark("argmax", s);
+            if (t->ktime_on) CN_CUDA_CHECK(cudaEventRecord(t->kev[3], s));
+            rc = cn_lookahead_argmax(p, env, epsilon, s);
+            if (t->ktime_on) CN_CUDA_CHECK(cudaEventRecord(t->kev[4], s));
+            return rc;
+        }
         kern<<<2 * nclusters, kThreadsPair, Q_SMEM, s>>>(env->p, t->img_pair, t->X, t->J, (int)NG, G, rounds, tw, t->dbg);
         CN_LAUNCH_CHECK();
     }
@@ -374,8 +457,9 @@ int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cu
         memcpy(tw.w, t->tail_b, sizeof(tw.w));
         cn_trace_mark("mlp3", s);
         if (t->ktime_on) CN_CUDA_CHECK(cudaEventRecord(t->kev[2], s));
-        tc_mlp3_pair_kernel<<<2 * nclusters, kThreadsM3, M_SMEM, s>>>(env->p, env->state, t->img_pair_b, t->J, t->rew, A, (int)NG,
-                                                                     p->cfg.gamma, gamma_bar, p->cfg.v_pref, p->values, rounds, tw);
+        tc_mlp3_pair_kernel<0><<<2 * nclusters, kThreadsM3, M_SMEM, s>>>(env->p, env->state, t->img_pair_b, t->J, t->rew, A, (int)NG,
+                                                                        p->cfg.gamma, gamma_bar, p->cfg.v_pref, p->values, rounds, tw,
+                                                                        nullptr);
         CN_LAUNCH_CHECK();
     }
     cn_trace_mark("argmax", s);

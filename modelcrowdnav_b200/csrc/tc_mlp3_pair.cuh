@@ -10,7 +10,11 @@
 //                                                                           value = reward + gamma_bar * V -> values[E][A]
 // The activations never touch shared memory: each column-half warp packs its half of an accumulator in place
 // (U0: K 0..79 at [0,40), K 80..159 at [80,120); U1: K 0..63 at [120,152), K 64..111 at [184,208)).
-// Reference: crowd_nav/policy/sarl.py:62-64 (mlp3 on the joint state), multi_human_rl.py:52 (scoring).
+// MODE 1 runs CADRL's whole value network with the same three stages (cadrl.py:22-30: mlp(13 -> 150 -> 100 -> 100 -> 1) on
+// every rotated (robot, human) row): stage 0 reads the X tiles of tc_features_kernel (K = 32, inputs split hi + lo) instead of
+// the joint-state tiles, and the epilogue leaves one fp32 value per ROW; cadrl_min_kernel then takes the minimum over the
+// humans of an (env, action) group (cadrl.py:166-168).
+// Reference: crowd_nav/policy/sarl.py:62-64 (mlp3 on the joint state), multi_human_rl.py:52 (scoring); cadrl.py:131-178.
 
 constexpr int kThreadsM3 = 608;
 constexpr int M3_CTX_COLS = 256;
@@ -28,11 +32,15 @@ constexpr uint32_t M_MISC = M_CTX0 + 2 * M_CTX_BYTES;                // S[2][128
 constexpr uint32_t M_SMEM = M_MISC + 1024 + 96 + 16;
 static_assert(M_SMEM <= 232448, "tc_mlp3_pair_kernel exceeds 227 KB of shared memory");
 
+template <int MODE>       // 0: SARL mlp3 on joint-state tiles -> values[E][A];  1: CADRL network on X tiles -> rowv[tiles * 128]
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(88)
 tc_mlp3_pair_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *__restrict__ wimg,
                     const uint8_t *__restrict__ J, const double *__restrict__ rew, int A, int NG, double gamma,
-                    double gamma_bar_host, double v_pref_host, double *__restrict__ values, int rounds, const TailW tw)
+                    double gamma_bar_host, double v_pref_host, double *__restrict__ values, int rounds, const TailW tw,
+                    float *__restrict__ rowv)
 {
+    constexpr int K0 = MODE ? K_X : K_J;                                        // K of stage 0
+    constexpr uint32_t TILE_BYTES = MODE ? X_TILE_BYTES : J_TILE_BYTES;
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, ctx = (warp >> 2) & 1, hf = (warp >> 3) & 1;
@@ -88,7 +96,7 @@ tc_mlp3_pair_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *_
                     fence_after_sync();
                     const uint32_t tm = tmem + (uint32_t)c * M3_CTX_COLS;
                     const uint32_t sRA = smem_u32(smem + M_CTX0 + (uint32_t)c * M_CTX_BYTES);
-                    if (s == 0) mma_layer_2(tm, sRA, ROWS, sM1, K_J, N_H1, false);
+                    if (s == 0) mma_layer_2(tm, sRA, ROWS, sM1, K0, N_H1, false);
                     else if (s == 1) {
                         mma_steps_2_ts(tm + M3_D1, tm, sM2, 0, 5, N_M1, false);                 // U0, K 0..79
                         mma_steps_2_ts(tm + M3_D1, tm + 80, sM2, 5, 10, N_M1, true);            // U0, K 80..159
@@ -114,7 +122,7 @@ tc_mlp3_pair_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *_
             uint32_t phf = 0, phl = 0;
             for (int rnd = 0; rnd < rounds; ++rnd, tile += tile_stride) {
                 if (rnd > 0) { mbar_wait_guarded(xfree, phf); phf ^= 1; }              // stage 0 of the previous tile is complete: its J tile is dead
-                bulk_load(dst, J + (size_t)tile * J_TILE_BYTES, J_TILE_BYTES, xl);
+                bulk_load(dst, J + (size_t)tile * TILE_BYTES, TILE_BYTES, xl);
                 mbar_wait_guarded(xl, phl); phl ^= 1;
                 mbar_arrive_cluster(xfull_leader);
             }
@@ -134,7 +142,7 @@ tc_mlp3_pair_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *_
             // global round trips are not left at the tail of the tile
             const long long g_row = (long long)tile * ROWS + row;
             double rew_g = 0.0, vp_g = v_pref_host;
-            if (hf == 0 && g_row < NG) {
+            if (!MODE && hf == 0 && g_row < NG) {
                 rew_g = rew[g_row];
                 vp_g = st[st_idx(p.d, F_VPREF, 0, (int)(g_row / A))];
             }
@@ -177,7 +185,8 @@ tc_mlp3_pair_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *_
             else asm volatile("bar.sync 2, 256;" ::: "memory");
             if (hf == 0) {
                 const float v = part + S1[row] + tw.w[100];
-                if (g_row < NG) {
+                if (MODE) rowv[g_row] = v;                                          // one value per (env, action, human) row
+                else if (g_row < NG) {
                     const double gamma_bar = (vp_g == v_pref_host) ? gamma_bar_host : pow(gamma, p.time_step * vp_g);
                     values[g_row] = rew_g + gamma_bar * (double)v;                // multi_human_rl.py:52
                 }

@@ -84,7 +84,8 @@ __host__ __device__ inline Plan make_plan(const TDims &d, int H, int ns)
 
 __global__ void __launch_bounds__(kThreads, 1)
 trainer_fwd_bwd_kernel(TDims d, const float *__restrict__ W, const float *__restrict__ Wt, const float *__restrict__ X,
-                       const float *__restrict__ target, int B, int H, float *__restrict__ gpart, float *__restrict__ loss_part)
+                       const float *__restrict__ target, const int64_t *__restrict__ index, int B, int H,
+                       float *__restrict__ gpart, float *__restrict__ loss_part)
 {
     extern __shared__ __align__(16) float sm[];
     const int s0 = blockIdx.x * kSPC;
@@ -102,9 +103,11 @@ trainer_fwd_bwd_kernel(TDims d, const float *__restrict__ W, const float *__rest
 #define BS(i) (W + L[i].b_off)
 
     // ---------------- forward (sarl.py:28-65) ----------------
+    // sample s of the batch = item index[s0 + s] of the replay tensors (index == NULL: the batch is X / target itself)
     for (int idx = tid; idx < R * p.ld_x; idx += kThreads) {
         const int r = idx / p.ld_x, k = idx - r * p.ld_x;
-        xs[idx] = k < d.in ? X[((size_t)s0 * H + r) * d.in + k] : 0.0f;
+        const size_t item = index ? (size_t)index[s0 + r / H] : (size_t)(s0 + r / H);
+        xs[idx] = k < d.in ? X[(item * H + r % H) * d.in + k] : 0.0f;
     }
     __syncthreads();
     dense(xs, p.ld_x, R, L[0].in, WT(0), BS(0), L[0].out, a1, p.ld_a1, true, false);                 // mlp1.0 + ReLU
@@ -166,11 +169,11 @@ trainer_fwd_bwd_kernel(TDims d, const float *__restrict__ W, const float *__rest
     // MSELoss(mean): dL/dv_b = 2 (v_b - y_b) / B
     if (tid == 0) {
         float ls = 0.0f;
-        for (int s = 0; s < ns; ++s) { const float df = v[s] - target[s0 + s]; ls += df * df; }
+        for (int s = 0; s < ns; ++s) { const float df = v[s] - target[index ? index[s0 + s] : s0 + s]; ls += df * df; }
         loss_part[blockIdx.x] = ls;
     }
     float *dv = d0;                                                 // [ns][1]
-    if (tid < ns) dv[tid] = 2.0f * (v[tid] - target[s0 + tid]) / (float)B;
+    if (tid < ns) dv[tid] = 2.0f * (v[tid] - target[index ? index[s0 + tid] : s0 + tid]) / (float)B;
     __syncthreads();
     // mlp3.6
     weight_grad(dv, 1, g3, p.ld_g, ns, 1, L[10].in, G + L[10].w_off, G + L[10].b_off);
@@ -283,13 +286,13 @@ trainer_fwd_bwd_kernel(TDims d, const float *__restrict__ W, const float *__rest
 __global__ void trainer_reduce_kernel(int n_params, int nparts, const float *__restrict__ gpart, const float *__restrict__ loss_part,
                                       int B, float *__restrict__ grad_out, float *__restrict__ W, float *__restrict__ Wt,
                                       float *__restrict__ mom, const int32_t *__restrict__ tmap, float lr, float mu,
-                                      float *__restrict__ loss_out)
+                                      float *__restrict__ loss_out, int loss_accumulate)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && loss_out) {
         float s = 0.0f;
         for (int c = 0; c < nparts; ++c) s += loss_part[c];
-        *loss_out = s / (float)B;
+        *loss_out = (loss_accumulate ? *loss_out : 0.0f) + s / (float)B;
     }
     if (i >= n_params) return;
     float g = 0.0f;
@@ -415,8 +418,9 @@ int cn_trainer_sync_weights(cn_trainer *t, const float *w_dev, int zero_momentum
     return CN_OK;
 }
 
-int cn_trainer_step(cn_trainer *t, float *w_dev, const float *states_dev, const float *targets_dev, int32_t batch,
-                    int32_t human_num, float lr, float momentum, float *grad_out_dev, float *loss_dev, void *stream)
+static int trainer_step_impl(cn_trainer *t, float *w_dev, const float *states_dev, const float *targets_dev,
+                             const int64_t *index_dev, int32_t batch, int32_t human_num, float lr, float momentum,
+                             float *grad_out_dev, float *loss_dev, int loss_accumulate, void *stream)
 {
     if (!t || !w_dev || !states_dev || !targets_dev) { cn_set_error("null argument"); return CN_EINVAL; }
     if (batch < 1 || batch > t->max_batch || human_num < 1 || human_num > t->max_humans) {
@@ -428,14 +432,30 @@ int cn_trainer_step(cn_trainer *t, float *w_dev, const float *states_dev, const 
     const int nparts = (batch + kSPC - 1) / kSPC;
     const Plan pl = make_plan(t->d, human_num, kSPC);
     const size_t smem = sizeof(float) * (size_t)pl.total;
-    trainer_fwd_bwd_kernel<<<nparts, kThreads, smem, s>>>(t->d, w_dev, t->Wt, states_dev, targets_dev, batch, human_num, t->gpart,
-                                                         t->loss_part);
+    trainer_fwd_bwd_kernel<<<nparts, kThreads, smem, s>>>(t->d, w_dev, t->Wt, states_dev, targets_dev, index_dev, batch, human_num,
+                                                         t->gpart, t->loss_part);
     CN_LAUNCH_CHECK();
     const int n = t->d.n_params;
     trainer_reduce_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, nparts, t->gpart, t->loss_part, batch, grad_out_dev, w_dev, t->Wt, t->mom,
-                                                         t->tmap, lr, momentum, loss_dev);
+                                                         t->tmap, lr, momentum, loss_dev, loss_accumulate);
     CN_LAUNCH_CHECK();
     return CN_OK;
+}
+
+int cn_trainer_step(cn_trainer *t, float *w_dev, const float *states_dev, const float *targets_dev, int32_t batch,
+                    int32_t human_num, float lr, float momentum, float *grad_out_dev, float *loss_dev, void *stream)
+{
+    return trainer_step_impl(t, w_dev, states_dev, targets_dev, nullptr, batch, human_num, lr, momentum, grad_out_dev, loss_dev, 0,
+                             stream);
+}
+
+int cn_trainer_step_indexed(cn_trainer *t, float *w_dev, const float *memory_states_dev, const float *memory_values_dev,
+                            const int64_t *index_dev, int32_t batch, int32_t human_num, float lr, float momentum,
+                            float *grad_out_dev, float *loss_sum_dev, void *stream)
+{
+    if (!index_dev) { cn_set_error("index_dev is null"); return CN_EINVAL; }
+    return trainer_step_impl(t, w_dev, memory_states_dev, memory_values_dev, index_dev, batch, human_num, lr, momentum, grad_out_dev,
+                             loss_sum_dev, 1, stream);
 }
 
 int cn_trainer_apply(cn_trainer *t, float *w_dev, const float *grad_dev, float grad_scale, float lr, float momentum, void *stream)

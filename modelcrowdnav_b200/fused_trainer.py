@@ -91,6 +91,26 @@ class FusedSarlTrainer(object):
         return loss
 
 
+    def step_indexed(self, states, values, idx, loss_sum, dist_group=None):
+        """One SGD-momentum step on the batch memory[idx], gathered inside the kernel: states (capacity, H, D) fp32 and
+        values (capacity, 1) fp32 are the replay tensors themselves, idx an int64 device vector; the batch MSE is ADDED to
+        the 0-d device tensor loss_sum.  One C call, two kernels (+ the all-reduce and the apply kernel under dist_group)."""
+        if self.lr is None:
+            raise ValueError("Learning rate is not set!")
+        if not self._synced:
+            self.sync_from_model()
+        B, H = int(idx.shape[0]), int(states.shape[1])
+        grad = None if dist_group is None else C.c_void_p(self.grad.data_ptr())
+        check(self.lib.cn_trainer_step_indexed(self.handle, C.c_void_p(self.flat.data_ptr()), C.c_void_p(states.data_ptr()),
+                                               C.c_void_p(values.data_ptr()), C.c_void_p(idx.data_ptr()), B, H, self.lr,
+                                               self.momentum, grad, C.c_void_p(loss_sum.data_ptr()), self._stream()))
+        if dist_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=dist_group)
+            check(self.lib.cn_trainer_apply(self.handle, C.c_void_p(self.flat.data_ptr()), C.c_void_p(self.grad.data_ptr()),
+                                            1.0 / dist.get_world_size(dist_group), self.lr, self.momentum, self._stream()))
+
+
 def _layer_dims(model):
     """cn_sarl_cfg layer widths from a ValueNetwork's Linear layers (policy.make_value_network)."""
     def widths(seq):

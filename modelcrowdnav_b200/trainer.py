@@ -209,6 +209,12 @@ class Trainer(object):
         values = self.memory.values[idx].to(self.device)
         return self._step_tensors(inputs, values)
 
+    def _fused_indexed_ok(self):
+        m = self.memory
+        return (self.mode == "fused" and getattr(m, "states", None) is not None and m.states.is_cuda and m.states.dim() == 3
+                and m.states.dtype == torch.float32 and m.values.dtype == torch.float32 and m.states.is_contiguous()
+                and m.values.is_contiguous() and m.states.shape[1] <= self._fused.max_humans)
+
     def _after(self):
         if self._fused is not None:
             self._fused.flush_to_model()
@@ -231,8 +237,13 @@ class Trainer(object):
             perm = torch.randperm(n, device=mdev)
             if n != n_local:
                 perm = perm % n_local            # short ranks wrap around: same number of steps (and collectives) everywhere
-            for s in range(0, n, self.batch_size):
-                epoch_loss += self._step(perm[s:s + self.batch_size]).to(self.device)
+            if self._fused_indexed_ok():
+                for s in range(0, n, self.batch_size):
+                    self._fused.step_indexed(self.memory.states, self.memory.values, perm[s:s + self.batch_size].contiguous(),
+                                             epoch_loss, self.dist_group)
+            else:
+                for s in range(0, n, self.batch_size):
+                    epoch_loss += self._step(perm[s:s + self.batch_size]).to(self.device)
             average_epoch_loss = float(epoch_loss.item()) / n
             logging.debug("Average loss in epoch : %.2E", average_epoch_loss)
         self._after()
@@ -249,8 +260,13 @@ class Trainer(object):
         losses = torch.zeros((), dtype=torch.float32, device=self.device)
         b = min(self.batch_size, n)
         idx = sample_batches(n, b, num_batches, mdev)
-        for i in range(num_batches):
-            losses += self._step(idx[i]).to(self.device)
+        if self._fused_indexed_ok():
+            # the fused step gathers memory[idx] inside its kernel and accumulates the loss on the device: one C call per batch
+            for i in range(num_batches):
+                self._fused.step_indexed(self.memory.states, self.memory.values, idx[i], losses, self.dist_group)
+        else:
+            for i in range(num_batches):
+                losses += self._step(idx[i]).to(self.device)
         average_loss = float(losses.item()) / num_batches
         logging.debug("Average loss : %.2E", average_loss)
         self._after()
