@@ -219,6 +219,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip extra_configs / sustained (quick A/B runs)")
     ap.add_argument("--sustained-seconds", type=float, default=3.0)
     ap.add_argument("--parity-envs", type=int, default=256)
+    ap.add_argument("--preroll", type=int, default=64, help="untimed steps before the warm-up (episodes out of lock step)")
     ap.add_argument("--train-episodes", type=int, default=512, help="--workload train: episodes rolled out per iteration and rank")
     ap.add_argument("--train-batches", type=int, default=100, help="--workload train: SGD batches per iteration")
     ap.add_argument("--trainer", default="graph", choices=["eager", "graph", "fused"])
@@ -290,7 +291,9 @@ def main():
         """K timed rollout steps of one configuration (device time per step, L2 flushed between steps, max over ranks),
         then the per-phase / per-kernel breakdown of the same step."""
         env, pol = make(E, H, sim)
-        for _ in range(warmup):
+        # pre-roll: the envs start in lock step (all episodes at t = 0, humans far apart, trivially feasible ORCA problems);
+        # 64 untimed steps spread them over the episode (crossings, dangers, finished + re-generated episodes) before timing
+        for _ in range(a.preroll + warmup):
             mcn.rollout_step(pol, env, query_env)
         barrier()
         sampler = ClockSampler(local).start() if (clocks and rank == 0) else None
@@ -347,6 +350,14 @@ def main():
         import oracle
         oracle.build()
         parity = parity_sample(oracle, pol, env, a.query_env, weights, a.parity_envs)
+        # the same states through the TRAINED network (|V| up to 1, decisive top-2 gaps): the argmax comparison is not vacuous
+        wt_path = os.path.join(ROOT, "tests", "golden", "sarl_weights_trained.npy")
+        if os.path.exists(wt_path):
+            wt = np.load(wt_path)
+            pol_t = mcn.BatchedSARL(device=local, precision=a.precision)
+            pol_t.load_weights(wt)
+            parity["trained_weights"] = parity_sample(oracle, pol_t, env, a.query_env, wt, a.parity_envs)
+            pol_t.close()
     barrier()
 
     # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region ----
@@ -469,6 +480,7 @@ def main():
                        "weights": "torch.manual_seed(0) default nn.Linear init",
                        "l2": "256 MiB memset between timed steps (outside the event pair)",
                        "wall_s_timed_region": main_res["wall_s"], "phase_ms": main_res["phase_ms"],
+                       "preroll_steps": a.preroll,
                        "episodes_finished": st["episodes"], "envs_with_no_finite_value": main_res["bad_envs"]},
             "clocks": main_res["clocks"],
             "e2e": {"value": world * E * ne / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,

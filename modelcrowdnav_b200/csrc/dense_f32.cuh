@@ -15,8 +15,14 @@ __host__ __device__ __forceinline__ int pad4(int x) { return (x + 3) & ~3; }
 // K is walked 16 at a time with the 16 weight loads issued before any FMA: the loop is bound by the L2 latency of those loads
 // (a CTA has 256 threads and no other work to hide it), so loads in flight per thread are what sets the speed.
 constexpr int kRowsPerItem = 8;
-__device__ __forceinline__ void dense(const float *__restrict__ X, int ldx, int R, int K, const float *__restrict__ Wt,
-                                      const float *__restrict__ b, int O, float *__restrict__ Y, int ldy, bool relu, bool accumulate)
+template <bool W_IN_SMEM>
+__device__ __forceinline__ float ldw(const float *p) { return W_IN_SMEM ? *p : __ldg(p); }
+
+// W_IN_SMEM: the weight block (and bias) was staged into shared memory (trainer.cu prefetches the next layer's block with
+// cp.async while this one computes); otherwise it is streamed from L2.
+template <bool W_IN_SMEM>
+__device__ __forceinline__ void dense_t(const float *__restrict__ X, int ldx, int R, int K, const float *__restrict__ Wt,
+                                        const float *__restrict__ b, int O, float *__restrict__ Y, int ldy, bool relu, bool accumulate)
 {
     const int groups = (R + kRowsPerItem - 1) / kRowsPerItem;
     for (int idx = threadIdx.x; idx < O * groups; idx += kThreads) {
@@ -32,7 +38,7 @@ __device__ __forceinline__ void dense(const float *__restrict__ X, int ldx, int 
         for (; k + 16 <= K; k += 16) {                   // 16 independent L2 loads in flight per thread
             float w[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) w[j] = __ldg(wp + (size_t)(k + j) * O);
+            for (int j = 0; j < 16; ++j) w[j] = ldw<W_IN_SMEM>(wp + (size_t)(k + j) * O);
 #pragma unroll
             for (int i = 0; i < kRowsPerItem; ++i) {
                 if (i < nr) {
@@ -48,7 +54,7 @@ __device__ __forceinline__ void dense(const float *__restrict__ X, int ldx, int 
         for (; k + 4 <= K; k += 4) {
             float w[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) w[j] = __ldg(wp + (size_t)(k + j) * O);
+            for (int j = 0; j < 4; ++j) w[j] = ldw<W_IN_SMEM>(wp + (size_t)(k + j) * O);
 #pragma unroll
             for (int i = 0; i < kRowsPerItem; ++i) {
                 if (i < nr) {
@@ -59,7 +65,7 @@ __device__ __forceinline__ void dense(const float *__restrict__ X, int ldx, int 
             }
         }
         for (; k < K; ++k) {
-            const float w = __ldg(wp + (size_t)k * O);
+            const float w = ldw<W_IN_SMEM>(wp + (size_t)k * O);
 #pragma unroll
             for (int i = 0; i < kRowsPerItem; ++i) if (i < nr) acc[i] = fmaf(x0[(size_t)i * ldx + k], w, acc[i]);
         }
@@ -72,6 +78,12 @@ __device__ __forceinline__ void dense(const float *__restrict__ X, int ldx, int 
             }
         }
     }
+}
+
+__device__ __forceinline__ void dense(const float *__restrict__ X, int ldx, int R, int K, const float *__restrict__ Wt,
+                                      const float *__restrict__ b, int O, float *__restrict__ Y, int ldy, bool relu, bool accumulate)
+{
+    dense_t<false>(X, ldx, R, K, Wt, b, O, Y, ldy, relu, accumulate);
 }
 
 // dW[o][k] = sum_r dY[r][o] * Xin[r][k] and db[o] = sum_r dY[r][o] -> this CTA's partial gradient block (global memory).

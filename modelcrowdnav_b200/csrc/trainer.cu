@@ -4,7 +4,11 @@
 // (crowd_nav/utils/trainer.py:61-82: zero_grad, model(inputs), MSELoss, backward, SGD(momentum 0.9).step, loss.item())
 // with TWO kernels:
 //   trainer_fwd_bwd_kernel   one CTA per kSPC samples of the batch: the whole forward (sarl.py:28-65) and backward of those
-//                            samples with every activation in shared memory, weights streamed from L2 (386 kB, resident);
+//                            samples with every activation in shared memory.  The 21 weight blocks a step walks through
+//                            (11 forward layers, 10 backward-data products) are STAGED: while layer i computes from one
+//                            shared-memory buffer, cp.async brings layer i + 1's block (<= 80 kB, L2-resident) into the
+//                            other -- streamed straight from L2 the dependent loads of a 256-thread CTA were all latency
+//                            (226 us per step in the ncu launch list, profiles/r02l_train_launches_summary.txt);
 //                            per-CTA partial weight gradients -> gpart[cta][n_params]
 //   trainer_reduce_kernel    fixed-order sum of the partials (deterministic) -> gradient; with grad_out == NULL it also
 //                            applies SGD momentum in place and refreshes the transposed weight copy the forward reads
@@ -29,13 +33,24 @@ constexpr int kSPC = 1;           // samples per CTA: 100 CTAs for the reference
 constexpr int kMaxH = 16;         // humans per sample supported by the shared-memory plan
 constexpr int kLayers = 11;
 
-struct TLayer { int in, out; int w_off, b_off, t_off; };   // offsets into the flat master / transposed blocks
+// w_off / b_off: the flat master block (torch state-dict order).  t_off: this layer's block in the transposed copy Wt --
+// [in][out] followed by the bias, both padded to 4 floats, 16-byte aligned (one cp.async target).  a_off: its block in the
+// aligned copy Wa of the ORIGINAL [out][in] layout (what the backward-data products read).
+struct TLayer { int in, out; int w_off, b_off, t_off, a_off; };
 
 struct TDims {
     TLayer L[kLayers];
-    int n_params;
+    int n_params, t_size, a_size;
     int in, self_dim;
+    int wbuf_floats;           // size of one staging buffer = the largest block
 };
+
+__device__ __forceinline__ void cp_async16(float *dst_smem, const float *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
 // shared-memory plan (floats); every row stride is a multiple of 4 floats
 struct Plan {
@@ -83,24 +98,66 @@ __host__ __device__ inline Plan make_plan(const TDims &d, int H, int ns)
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-trainer_fwd_bwd_kernel(TDims d, const float *__restrict__ W, const float *__restrict__ Wt, const float *__restrict__ X,
-                       const float *__restrict__ target, const int64_t *__restrict__ index, int B, int H,
+trainer_fwd_bwd_kernel(TDims d, const float *__restrict__ Wt, const float *__restrict__ Wa, const float *__restrict__ X,
+                       const float *__restrict__ target, const int64_t *__restrict__ index, int B, int H, int nbuf,
                        float *__restrict__ gpart, float *__restrict__ loss_part)
 {
     extern __shared__ __align__(16) float sm[];
     const int s0 = blockIdx.x * kSPC;
     const int ns = min(kSPC, B - s0);
     const Plan p = make_plan(d, H, ns);
+    const Plan pmax = make_plan(d, H, kSPC);            // the staging buffers sit behind the largest activation plan
     const int R = p.R, tid = threadIdx.x;
     float *xs = sm + p.x, *a1 = sm + p.a1, *e = sm + p.e, *f1 = sm + p.f1, *f = sm + p.f, *u = sm + p.u, *t1 = sm + p.t1,
           *t2 = sm + p.t2, *sc = sm + p.sc, *wt = sm + p.wt, *c = sm + p.c, *j = sm + p.j, *g1 = sm + p.g1, *g2 = sm + p.g2,
           *g3 = sm + p.g3, *v = sm + p.v, *d0 = sm + p.d0, *d1 = sm + p.d1;
+    float *wbuf[2] = {sm + pad4(pmax.total), sm + pad4(pmax.total) + (nbuf == 2 ? d.wbuf_floats : 0)};
     float *G = gpart + (size_t)blockIdx.x * d.n_params;
     const TLayer *L = d.L;
     const int E1 = L[1].out, F = L[3].out;
-#define WT(i) (Wt + L[i].t_off)
-#define WM(i) (W + L[i].w_off)
-#define BS(i) (W + L[i].b_off)
+
+    // ---- the 21 weight blocks in the order the step uses them: forward layers 0..10 (transposed copy, bias behind the
+    //      weights), then the backward-data products (original [out][in] layout) ----
+    constexpr int kOps = 21;
+    const int bwd_layer[10] = {10, 9, 8, 7, 3, 6, 5, 4, 2, 1};
+    auto op_src = [&](int k) -> const float * { return k < kLayers ? Wt + L[k].t_off : Wa + L[bwd_layer[k - kLayers]].a_off; };
+    auto op_floats = [&](int k) -> int {
+        const TLayer &l = k < kLayers ? L[k] : L[bwd_layer[k - kLayers]];
+        return pad4(l.in * l.out) + (k < kLayers ? pad4(l.out) : 0);
+    };
+    auto fetch = [&](int k, float *dst) {
+        const float *src = op_src(k);
+        const int n = op_floats(k);
+        for (int i = tid * 4; i < n; i += kThreads * 4) cp_async16(dst + i, src + i);
+        cp_async_commit();
+    };
+    int op = 0;
+    // start of weighted op `op`: with two buffers the NEXT block's copy is started (its buffer was released by the barrier that
+    // ended op - 1) and this op's block, fetched one op ago, is waited for; with one buffer the block is fetched here
+    auto begin_op = [&]() -> const float * {
+        if (nbuf == 2) {
+            if (op + 1 < kOps) { fetch(op + 1, wbuf[(op + 1) & 1]); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+        } else {
+            fetch(op, wbuf[0]);
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        return wbuf[nbuf == 2 ? (op & 1) : 0];
+    };
+    auto end_op = [&]() { __syncthreads(); ++op; };
+    if (nbuf == 2) fetch(0, wbuf[0]);
+#define FWD(i, Xp, ldx_, Rr, Yp, ldy_, relu_)                                                                       \
+    do {                                                                                                            \
+        const float *wb = begin_op();                                                                               \
+        dense_t<true>(Xp, ldx_, Rr, L[i].in, wb, wb + pad4(L[i].in * L[i].out), L[i].out, Yp, ldy_, relu_, false);  \
+    } while (0)
+    // dX[r][k] = sum_o dY[r][o] W[o][k]: the same routine with X = dY, "K" = out, "O" = in, no bias
+#define BWD(i, dYp, ldy_, Rr, dXp, ldx_, acc_)                                                                      \
+    do {                                                                                                            \
+        const float *wb = begin_op();                                                                               \
+        dense_t<true>(dYp, ldy_, Rr, L[i].out, wb, nullptr, L[i].in, dXp, ldx_, false, acc_);                       \
+    } while (0)
 
     // ---------------- forward (sarl.py:28-65) ----------------
     // sample s of the batch = item index[s0 + s] of the replay tensors (index == NULL: the batch is X / target itself)
@@ -109,12 +166,9 @@ trainer_fwd_bwd_kernel(TDims d, const float *__restrict__ W, const float *__rest
         const size_t item = index ? (size_t)index[s0 + r / H] : (size_t)(s0 + r / H);
         xs[idx] = k < d.in ? X[(item * H + r % H) * d.in + k] : 0.0f;
     }
-    __syncthreads();
-    dense(xs, p.ld_x, R, L[0].in, WT(0), BS(0), L[0].out, a1, p.ld_a1, true, false);                 // mlp1.0 + ReLU
-    __syncthreads();
-    dense(a1, p.ld_a1, R, L[1].in, WT(1), BS(1), L[1].out, e, p.ld_e, true, false);                  // mlp1.2 + ReLU (last_relu)
-    __syncthreads();
-    dense(e, p.ld_e, R, L[2].in, WT(2), BS(2), L[2].out, f1, p.ld_f1, true, false);                  // mlp2.0 + ReLU
+    FWD(0, xs, p.ld_x, R, a1, p.ld_a1, true); end_op();                        // mlp1.0 + ReLU
+    FWD(1, a1, p.ld_a1, R, e, p.ld_e, true); end_op();                         // mlp1.2 + ReLU (last_relu)
+    FWD(2, e, p.ld_e, R, f1, p.ld_f1, true);                                   // mlp2.0 + ReLU
     // attention input u = [e_i | mean over the sample's humans]
     for (int idx = tid; idx < ns * E1; idx += kThreads) {
         const int s = idx / E1, k = idx - s * E1;
@@ -126,15 +180,12 @@ trainer_fwd_bwd_kernel(TDims d, const float *__restrict__ W, const float *__rest
             u[(size_t)(s * H + h) * p.ld_u + E1 + k] = m;
         }
     }
-    __syncthreads();
-    dense(f1, p.ld_f1, R, L[3].in, WT(3), BS(3), L[3].out, f, p.ld_f, false, false);                 // mlp2.2
-    dense(u, p.ld_u, R, L[4].in, WT(4), BS(4), L[4].out, t1, p.ld_t, true, false);                   // attention.0 + ReLU
-    __syncthreads();
-    dense(t1, p.ld_t, R, L[5].in, WT(5), BS(5), L[5].out, t2, p.ld_t, true, false);                  // attention.2 + ReLU
-    __syncthreads();
-    dense(t2, p.ld_t, R, L[6].in, WT(6), BS(6), 1, sc, 1, false, false);                             // attention.4 -> score
-    __syncthreads();
-    if (tid < ns) {                                                                                   // masked softmax (sarl.py:52-53)
+    end_op();
+    FWD(3, f1, p.ld_f1, R, f, p.ld_f, false); end_op();                        // mlp2.2
+    FWD(4, u, p.ld_u, R, t1, p.ld_t, true); end_op();                          // attention.0 + ReLU
+    FWD(5, t1, p.ld_t, R, t2, p.ld_t, true); end_op();                         // attention.2 + ReLU
+    FWD(6, t2, p.ld_t, R, sc, 1, false); end_op();                             // attention.4 -> score
+    if (tid < ns) {                                                            // masked softmax (sarl.py:52-53)
         float z = 0.0f;
         for (int h = 0; h < H; ++h) {
             const float s = sc[tid * H + h];
@@ -144,7 +195,7 @@ trainer_fwd_bwd_kernel(TDims d, const float *__restrict__ W, const float *__rest
         for (int h = 0; h < H; ++h) wt[tid * H + h] /= z;
     }
     __syncthreads();
-    for (int idx = tid; idx < ns * p.ld_j; idx += kThreads) {                                        // joint = [self | weighted feature]
+    for (int idx = tid; idx < ns * p.ld_j; idx += kThreads) {                  // joint = [self | weighted feature]
         const int s = idx / p.ld_j, k = idx - s * p.ld_j;
         float val = 0.0f;
         if (k < d.self_dim) val = xs[(size_t)(s * H) * p.ld_x + k];
@@ -155,15 +206,10 @@ trainer_fwd_bwd_kernel(TDims d, const float *__restrict__ W, const float *__rest
         }
         j[idx] = val;
     }
-    __syncthreads();
-    dense(j, p.ld_j, ns, L[7].in, WT(7), BS(7), L[7].out, g1, p.ld_g1, true, false);                 // mlp3.0
-    __syncthreads();
-    dense(g1, p.ld_g1, ns, L[8].in, WT(8), BS(8), L[8].out, g2, p.ld_g, true, false);                // mlp3.2
-    __syncthreads();
-    dense(g2, p.ld_g, ns, L[9].in, WT(9), BS(9), L[9].out, g3, p.ld_g, true, false);                 // mlp3.4
-    __syncthreads();
-    dense(g3, p.ld_g, ns, L[10].in, WT(10), BS(10), 1, v, 1, false, false);                          // mlp3.6 -> value
-    __syncthreads();
+    FWD(7, j, p.ld_j, ns, g1, p.ld_g1, true); end_op();                        // mlp3.0   (begin_op's barrier publishes j)
+    FWD(8, g1, p.ld_g1, ns, g2, p.ld_g, true); end_op();                       // mlp3.2
+    FWD(9, g2, p.ld_g, ns, g3, p.ld_g, true); end_op();                        // mlp3.4
+    FWD(10, g3, p.ld_g, ns, v, 1, false); end_op();                            // mlp3.6 -> value
 
     // ---------------- loss and backward ----------------
     // MSELoss(mean): dL/dv_b = 2 (v_b - y_b) / B
@@ -178,31 +224,27 @@ trainer_fwd_bwd_kernel(TDims d, const float *__restrict__ W, const float *__rest
     // mlp3.6
     weight_grad(dv, 1, g3, p.ld_g, ns, 1, L[10].in, G + L[10].w_off, G + L[10].b_off);
     float *dg3 = d1;                                                // [ns][ld_g]
-    dense(dv, 1, ns, 1, WM(10), nullptr, L[10].in, dg3, p.ld_g, false, false);       // dg3 = dv * W[0][:]  (W as [1][in])
-    __syncthreads();
+    BWD(10, dv, 1, ns, dg3, p.ld_g, false); end_op();
     relu_mask(dg3, p.ld_g, g3, p.ld_g, ns, L[9].out);
     __syncthreads();
     // mlp3.4
     weight_grad(dg3, p.ld_g, g2, p.ld_g, ns, L[9].out, L[9].in, G + L[9].w_off, G + L[9].b_off);
-    float *dg2 = d0;
-    dense(dg3, p.ld_g, ns, L[9].out, WM(9), nullptr, L[9].in, dg2, p.ld_g, false, false);
-    __syncthreads();
+    float *dg2 = d0;                                                // dv is dead
+    BWD(9, dg3, p.ld_g, ns, dg2, p.ld_g, false); end_op();
     relu_mask(dg2, p.ld_g, g2, p.ld_g, ns, L[8].out);
     __syncthreads();
     // mlp3.2
     weight_grad(dg2, p.ld_g, g1, p.ld_g1, ns, L[8].out, L[8].in, G + L[8].w_off, G + L[8].b_off);
-    float *dg1 = d1;
-    dense(dg2, p.ld_g, ns, L[8].out, WM(8), nullptr, L[8].in, dg1, p.ld_g1, false, false);
-    __syncthreads();
+    float *dg1 = d1;                                                // dg3 is dead
+    BWD(8, dg2, p.ld_g, ns, dg1, p.ld_g1, false); end_op();
     relu_mask(dg1, p.ld_g1, g1, p.ld_g1, ns, L[7].out);
     __syncthreads();
     // mlp3.0
     weight_grad(dg1, p.ld_g1, j, p.ld_j, ns, L[7].out, L[7].in, G + L[7].w_off, G + L[7].b_off);
     float *dj = d0;                                                 // [ns][ld_j]; the self-state part has no parameters upstream
-    dense(dg1, p.ld_g1, ns, L[7].out, WM(7), nullptr, L[7].in, dj, p.ld_j, false, false);
-    __syncthreads();
+    BWD(7, dg1, p.ld_g1, ns, dj, p.ld_j, false); end_op();
     // weighted feature c = sum_i w_i f_i :  df_i = w_i dc,  dw_i = dc . f_i ;  softmax: ds_i = w_i (dw_i - sum_k w_k dw_k)
-    float *df = d1;                                                 // [R][ld_f]
+    float *df = d1;                                                 // [R][ld_f]  (dg1 is dead)
     float *dsc = sm + p.sc;                                         // scores are dead after the softmax: reuse for ds
     if (tid < R) {
         const int s = tid / H;
@@ -221,39 +263,31 @@ trainer_fwd_bwd_kernel(TDims d, const float *__restrict__ W, const float *__rest
         for (int h = 0; h < H; ++h) dsc[tid * H + h] = wt[tid * H + h] * (dsc[tid * H + h] - dot);
     }
     __syncthreads();
-    // mlp2.2 (no ReLU after it)
+    // mlp2.2 (no ReLU after it) and attention.4
     weight_grad(df, p.ld_f, f1, p.ld_f1, R, L[3].out, L[3].in, G + L[3].w_off, G + L[3].b_off);
-    float *df1 = d0;                                                // [R][ld_f1]  (dj is dead)
-    dense(df, p.ld_f, R, L[3].out, WM(3), nullptr, L[3].in, df1, p.ld_f1, false, false);
-    // attention.4
     weight_grad(dsc, 1, t2, p.ld_t, R, 1, L[6].in, G + L[6].w_off, G + L[6].b_off);
-    __syncthreads();
+    float *df1 = d0;                                                // [R][ld_f1]  (dj is dead)
+    BWD(3, df, p.ld_f, R, df1, p.ld_f1, false); end_op();
     relu_mask(df1, p.ld_f1, f1, p.ld_f1, R, L[2].out);
     __syncthreads();
-    // mlp2.0: de (accumulated in u's first half? no -- a dedicated buffer: reuse f (dead after df) is too narrow, use t-space later)
+    // mlp2.0's weights now; its data path joins de below
     weight_grad(df1, p.ld_f1, e, p.ld_e, R, L[2].out, L[2].in, G + L[2].w_off, G + L[2].b_off);
-    float *dt2 = d1;                                                // [R][ld_t]  (df is dead after mlp2.2's two reads above)
-    __syncthreads();
-    dense(dsc, 1, R, 1, WM(6), nullptr, L[6].in, dt2, p.ld_t, false, false);         // dt2 = ds * W_att4[0][:]
-    __syncthreads();
+    float *dt2 = d1;                                                // [R][ld_t]  (df is dead)
+    BWD(6, dsc, 1, R, dt2, p.ld_t, false); end_op();                // dt2 = ds * W_att4[0][:]
     relu_mask(dt2, p.ld_t, t2, p.ld_t, R, L[5].out);
     __syncthreads();
     // attention.2
     weight_grad(dt2, p.ld_t, t1, p.ld_t, R, L[5].out, L[5].in, G + L[5].w_off, G + L[5].b_off);
     float *dt1 = t2;                                                // t2 is dead once its mask and attention.4's gradient are taken
-    __syncthreads();
-    dense(dt2, p.ld_t, R, L[5].out, WM(5), nullptr, L[5].in, dt1, p.ld_t, false, false);
-    __syncthreads();
+    BWD(5, dt2, p.ld_t, R, dt1, p.ld_t, false); end_op();
     relu_mask(dt1, p.ld_t, t1, p.ld_t, R, L[4].out);
     __syncthreads();
     // attention.0 on u = [e | mean]
     weight_grad(dt1, p.ld_t, u, p.ld_u, R, L[4].out, L[4].in, G + L[4].w_off, G + L[4].b_off);
     float *du = d1;                                                 // [R][ld_u]  (dt2 is dead)
-    __syncthreads();
-    dense(dt1, p.ld_t, R, L[4].out, WM(4), nullptr, L[4].in, du, p.ld_u, false, false);
-    __syncthreads();
+    BWD(4, dt1, p.ld_t, R, du, p.ld_u, false); end_op();
     // de_i = du_i[:E1] + (1/H) sum_k du_k[E1:]  + mlp2.0's path (df1 W_20)
-    float *de = t1;                                                 // t1 is dead; ld_t >= E1? e and t rows: use ld_e-compatible indexing below
+    float *de = t1;                                                 // t1 is dead; rows of ld_t floats
     for (int idx = tid; idx < ns * E1; idx += kThreads) {
         const int s = idx / E1, k = idx - s * E1;
         float m = 0.0f;
@@ -261,23 +295,19 @@ trainer_fwd_bwd_kernel(TDims d, const float *__restrict__ W, const float *__rest
         m /= (float)H;
         for (int h = 0; h < H; ++h) de[(size_t)(s * H + h) * p.ld_t + k] = du[(size_t)(s * H + h) * p.ld_u + k] + m;
     }
-    __syncthreads();
-    dense(df1, p.ld_f1, R, L[2].out, WM(2), nullptr, L[2].in, de, p.ld_t, false, true);   // += df1 * W_mlp2.0
-    __syncthreads();
+    BWD(2, df1, p.ld_f1, R, de, p.ld_t, true); end_op();            // += df1 * W_mlp2.0   (begin_op's barrier publishes de)
     relu_mask(de, p.ld_t, e, p.ld_e, R, L[1].out);
     __syncthreads();
     // mlp1.2
     weight_grad(de, p.ld_t, a1, p.ld_a1, R, L[1].out, L[1].in, G + L[1].w_off, G + L[1].b_off);
     float *da1 = d1;                                                // [R][ld_a1]  (du is dead)
-    dense(de, p.ld_t, R, L[1].out, WM(1), nullptr, L[1].in, da1, p.ld_a1, false, false);
-    __syncthreads();
+    BWD(1, de, p.ld_t, R, da1, p.ld_a1, false); end_op();
     relu_mask(da1, p.ld_a1, a1, p.ld_a1, R, L[0].out);
     __syncthreads();
     // mlp1.0 (no gradient w.r.t. the input)
     weight_grad(da1, p.ld_a1, xs, p.ld_x, R, L[0].out, L[0].in, G + L[0].w_off, G + L[0].b_off);
-#undef WT
-#undef WM
-#undef BS
+#undef FWD
+#undef BWD
 }
 
 // gradient = fixed-order sum of the per-CTA partials; loss = sum of the partial squared errors / B.
@@ -285,8 +315,9 @@ trainer_fwd_bwd_kernel(TDims d, const float *__restrict__ W, const float *__rest
 // grad_out == NULL: apply SGD with momentum in place (torch.optim.SGD: buf = mu * buf + g; w -= lr * buf) and refresh Wt.
 __global__ void trainer_reduce_kernel(int n_params, int nparts, const float *__restrict__ gpart, const float *__restrict__ loss_part,
                                       int B, float *__restrict__ grad_out, float *__restrict__ W, float *__restrict__ Wt,
-                                      float *__restrict__ mom, const int32_t *__restrict__ tmap, float lr, float mu,
-                                      float *__restrict__ loss_out, int loss_accumulate)
+                                      float *__restrict__ Wa, float *__restrict__ mom, const int32_t *__restrict__ tmap,
+                                      const int32_t *__restrict__ amap, float lr, float mu, float *__restrict__ loss_out,
+                                      int loss_accumulate)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && loss_out) {
@@ -303,10 +334,12 @@ __global__ void trainer_reduce_kernel(int n_params, int nparts, const float *__r
     const float w = W[i] - lr * b;
     W[i] = w;
     Wt[tmap[i]] = w;
+    if (amap[i] >= 0) Wa[amap[i]] = w;
 }
 
 __global__ void trainer_apply_kernel(int n_params, const float *__restrict__ grad, float scale, float *__restrict__ W,
-                                     float *__restrict__ Wt, float *__restrict__ mom, const int32_t *__restrict__ tmap, float lr, float mu)
+                                     float *__restrict__ Wt, float *__restrict__ Wa, float *__restrict__ mom,
+                                     const int32_t *__restrict__ tmap, const int32_t *__restrict__ amap, float lr, float mu)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_params) return;
@@ -315,12 +348,16 @@ __global__ void trainer_apply_kernel(int n_params, const float *__restrict__ gra
     const float w = W[i] - lr * b;
     W[i] = w;
     Wt[tmap[i]] = w;
+    if (amap[i] >= 0) Wa[amap[i]] = w;
 }
 
-__global__ void trainer_transpose_kernel(int n_params, const float *__restrict__ W, float *__restrict__ Wt, const int32_t *__restrict__ tmap)
+__global__ void trainer_transpose_kernel(int n_params, const float *__restrict__ W, float *__restrict__ Wt, float *__restrict__ Wa,
+                                         const int32_t *__restrict__ tmap, const int32_t *__restrict__ amap)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_params) Wt[tmap[i]] = W[i];
+    if (i >= n_params) return;
+    Wt[tmap[i]] = W[i];
+    if (amap[i] >= 0) Wa[amap[i]] = W[i];
 }
 
 }  // namespace
@@ -329,10 +366,9 @@ struct cn_trainer {
     int device;
     TDims d;
     int max_batch, max_humans;
-    float *Wt, *mom, *gpart, *loss_part;
-    int32_t *tmap;
+    float *Wt, *Wa, *mom, *gpart, *loss_part;     // transposed / aligned weight copies, momentum, per-CTA partials
+    int32_t *tmap, *amap;                         // flat parameter index -> index in Wt / Wa (-1: not in Wa)
     int nparts_cap;
-    size_t smem_cap;
 };
 
 extern "C" {
@@ -359,37 +395,50 @@ int cn_trainer_create(const cn_sarl_cfg *cfg, int device, int32_t max_batch, int
     const int outs[kLayers] = {cfg->mlp1_dims[0], cfg->mlp1_dims[1], cfg->mlp2_dims[0], cfg->mlp2_dims[1], cfg->attn_dims[0],
                                cfg->attn_dims[1], cfg->attn_dims[2], cfg->mlp3_dims[0], cfg->mlp3_dims[1], cfg->mlp3_dims[2],
                                cfg->mlp3_dims[3]};
-    int off = 0;
+    int off = 0, toff = 0, aoff = 0, wbuf = 0;
     for (int i = 0; i < kLayers; ++i) {
         d.L[i].in = ins[i]; d.L[i].out = outs[i];
-        d.L[i].w_off = off; d.L[i].t_off = off; off += ins[i] * outs[i];
+        d.L[i].w_off = off; off += ins[i] * outs[i];
         d.L[i].b_off = off; off += outs[i];
+        d.L[i].t_off = toff; toff += pad4(ins[i] * outs[i]) + pad4(outs[i]);      // [in][out] | bias, 16-byte aligned blocks
+        d.L[i].a_off = aoff; aoff += pad4(ins[i] * outs[i]);                      // [out][in]
+        const int blk = pad4(ins[i] * outs[i]) + pad4(outs[i]);
+        if (blk > wbuf) wbuf = blk;
     }
-    d.n_params = off; d.in = cfg->input_dim; d.self_dim = cfg->self_state_dim;
+    d.n_params = off; d.t_size = toff; d.a_size = aoff; d.wbuf_floats = wbuf;
+    d.in = cfg->input_dim; d.self_dim = cfg->self_state_dim;
     if (outs[6] != 1 || outs[10] != 1) { delete t; cn_set_error("attention and mlp3 must end in 1 unit"); return CN_EINVAL; }
-    // flat index -> index in the transposed block ([in][out] per layer; biases stay where they are)
-    std::vector<int32_t> tmap(d.n_params);
+    std::vector<int32_t> tmap(d.n_params), amap(d.n_params, -1);
     for (int i = 0; i < kLayers; ++i) {
         for (int o = 0; o < outs[i]; ++o)
-            for (int k = 0; k < ins[i]; ++k) tmap[d.L[i].w_off + o * ins[i] + k] = d.L[i].t_off + k * outs[i] + o;
-        for (int o = 0; o < outs[i]; ++o) tmap[d.L[i].b_off + o] = d.L[i].b_off + o;
+            for (int k = 0; k < ins[i]; ++k) {
+                tmap[d.L[i].w_off + o * ins[i] + k] = d.L[i].t_off + k * outs[i] + o;
+                amap[d.L[i].w_off + o * ins[i] + k] = d.L[i].a_off + o * ins[i] + k;
+            }
+        for (int o = 0; o < outs[i]; ++o) tmap[d.L[i].b_off + o] = d.L[i].t_off + pad4(ins[i] * outs[i]) + o;
     }
     t->nparts_cap = (max_batch + kSPC - 1) / kSPC;
     const Plan pl = make_plan(d, max_humans, kSPC);
-    t->smem_cap = sizeof(float) * (size_t)pl.total;
-    if (t->smem_cap > 232448) { delete t; cn_set_error("fused trainer needs %zu bytes of shared memory", t->smem_cap); return CN_EUNSUPPORTED; }
-    if (cudaMalloc((void **)&t->Wt, sizeof(float) * d.n_params) != cudaSuccess ||
+    if (sizeof(float) * ((size_t)pad4(pl.total) + wbuf) > 232448) {
+        delete t; cn_set_error("fused trainer: %d humans per sample do not fit the shared-memory plan", max_humans); return CN_EUNSUPPORTED;
+    }
+    if (cudaMalloc((void **)&t->Wt, sizeof(float) * d.t_size) != cudaSuccess ||
+        cudaMalloc((void **)&t->Wa, sizeof(float) * d.a_size) != cudaSuccess ||
         cudaMalloc((void **)&t->mom, sizeof(float) * d.n_params) != cudaSuccess ||
         cudaMalloc((void **)&t->gpart, sizeof(float) * (size_t)d.n_params * t->nparts_cap) != cudaSuccess ||
         cudaMalloc((void **)&t->loss_part, sizeof(float) * t->nparts_cap) != cudaSuccess ||
-        cudaMalloc((void **)&t->tmap, sizeof(int32_t) * d.n_params) != cudaSuccess) {
+        cudaMalloc((void **)&t->tmap, sizeof(int32_t) * d.n_params) != cudaSuccess ||
+        cudaMalloc((void **)&t->amap, sizeof(int32_t) * d.n_params) != cudaSuccess) {
         cn_set_error("cudaMalloc failed in cn_trainer_create");
         cn_trainer_destroy(t);
         return CN_ENOMEM;
     }
+    CN_CUDA_CHECK(cudaMemset(t->Wt, 0, sizeof(float) * d.t_size));          // the padding floats of the blocks are read by cp.async
+    CN_CUDA_CHECK(cudaMemset(t->Wa, 0, sizeof(float) * d.a_size));
     CN_CUDA_CHECK(cudaMemset(t->mom, 0, sizeof(float) * d.n_params));
     CN_CUDA_CHECK(cudaMemcpy(t->tmap, tmap.data(), sizeof(int32_t) * d.n_params, cudaMemcpyHostToDevice));
-    CN_CUDA_CHECK(cudaFuncSetAttribute(trainer_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->smem_cap));
+    CN_CUDA_CHECK(cudaMemcpy(t->amap, amap.data(), sizeof(int32_t) * d.n_params, cudaMemcpyHostToDevice));
+    CN_CUDA_CHECK(cudaFuncSetAttribute(trainer_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     *out = t;
     return CN_OK;
 }
@@ -398,7 +447,7 @@ int cn_trainer_destroy(cn_trainer *t)
 {
     if (!t) return CN_OK;
     cudaSetDevice(t->device);
-    void *ptrs[] = {t->Wt, t->mom, t->gpart, t->loss_part, t->tmap};
+    void *ptrs[] = {t->Wt, t->Wa, t->mom, t->gpart, t->loss_part, t->tmap, t->amap};
     for (void *q : ptrs) if (q) cudaFree(q);
     delete t;
     return CN_OK;
@@ -412,7 +461,7 @@ int cn_trainer_sync_weights(cn_trainer *t, const float *w_dev, int zero_momentum
     CN_CUDA_CHECK(cudaSetDevice(t->device));
     cudaStream_t s = (cudaStream_t)stream;
     const int n = t->d.n_params;
-    trainer_transpose_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, w_dev, t->Wt, t->tmap);
+    trainer_transpose_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, w_dev, t->Wt, t->Wa, t->tmap, t->amap);
     CN_LAUNCH_CHECK();
     if (zero_momentum) CN_CUDA_CHECK(cudaMemsetAsync(t->mom, 0, sizeof(float) * n, s));
     return CN_OK;
@@ -431,13 +480,16 @@ static int trainer_step_impl(cn_trainer *t, float *w_dev, const float *states_de
     cudaStream_t s = (cudaStream_t)stream;
     const int nparts = (batch + kSPC - 1) / kSPC;
     const Plan pl = make_plan(t->d, human_num, kSPC);
-    const size_t smem = sizeof(float) * (size_t)pl.total;
-    trainer_fwd_bwd_kernel<<<nparts, kThreads, smem, s>>>(t->d, w_dev, t->Wt, states_dev, targets_dev, index_dev, batch, human_num,
-                                                         t->gpart, t->loss_part);
+    // two staging buffers (the next weight block is copied while the current layer computes) when they fit, else one
+    const size_t act = (size_t)pad4(pl.total);
+    const int nbuf = sizeof(float) * (act + 2 * (size_t)t->d.wbuf_floats) <= 232448 ? 2 : 1;
+    const size_t smem = sizeof(float) * (act + (size_t)nbuf * t->d.wbuf_floats);
+    trainer_fwd_bwd_kernel<<<nparts, kThreads, smem, s>>>(t->d, t->Wt, t->Wa, states_dev, targets_dev, index_dev, batch, human_num,
+                                                         nbuf, t->gpart, t->loss_part);
     CN_LAUNCH_CHECK();
     const int n = t->d.n_params;
-    trainer_reduce_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, nparts, t->gpart, t->loss_part, batch, grad_out_dev, w_dev, t->Wt, t->mom,
-                                                         t->tmap, lr, momentum, loss_dev, loss_accumulate);
+    trainer_reduce_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, nparts, t->gpart, t->loss_part, batch, grad_out_dev, w_dev, t->Wt, t->Wa,
+                                                         t->mom, t->tmap, t->amap, lr, momentum, loss_dev, loss_accumulate);
     CN_LAUNCH_CHECK();
     return CN_OK;
 }
@@ -463,8 +515,8 @@ int cn_trainer_apply(cn_trainer *t, float *w_dev, const float *grad_dev, float g
     if (!t || !w_dev || !grad_dev) { cn_set_error("null argument"); return CN_EINVAL; }
     CN_CUDA_CHECK(cudaSetDevice(t->device));
     const int n = t->d.n_params;
-    trainer_apply_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, grad_dev, grad_scale, w_dev, t->Wt, t->mom, t->tmap, lr,
-                                                                          momentum);
+    trainer_apply_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, grad_dev, grad_scale, w_dev, t->Wt, t->Wa, t->mom, t->tmap,
+                                                                          t->amap, lr, momentum);
     CN_LAUNCH_CHECK();
     return CN_OK;
 }

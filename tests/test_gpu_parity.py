@@ -555,8 +555,10 @@ def test_other_value_networks_forward(mcn, units_nets, tag):
         got = pol.forward(torch.from_numpy(x).cuda()).cpu().numpy()
         want = ref.min(axis=1) if tag == "cadrl" else ref
         assert value_errors(got, want, "f32") <= 1.0
-    with pytest.raises(mcn.CrowdNavError):
-        mcn.BatchedSARL(precision="f16_tc", network="cadrl")           # FP32 path only, no silent fallback
+    with pytest.raises(mcn.CrowdNavError):                             # no tensor-core LSTM-RL, and no silent fallback
+        mcn.BatchedSARL(precision="f16_tc", network="lstm_rl", mlp3_dims=[150, 100, 100, 1], lstm_hidden=50)
+    with pytest.raises(mcn.CrowdNavError):                             # tensor-core CADRL is the default [cadrl] shape only
+        mcn.BatchedSARL(precision="f16_tc", network="cadrl", mlp3_dims=[128, 100, 100, 1])
     pol.close()
 
 
