@@ -258,6 +258,30 @@ int cn_rollout_step(cn_policy *p, cn_env *env, int query_env, double epsilon, vo
  * high-priority stream and `stream` is made to wait for them, so that one shard's feature / small kernels run beside
  * another shard's persistent row kernel instead of between two of them. */
 int cn_rollout_step_sharded(cn_policy *p, cn_env *env, int query_env, double epsilon, void *stream);
+/* ---- whole episodes: explorer.py:53-69 (`while not done: action = robot.act(ob); ob, reward, done, info = env.step(action)`)
+ * for every env of the batch, enqueued natively: per step [transform -> record] humans (ORCA, or the world model of
+ * ModelCrowdSim when `world` is given) -> robot action -> step(update=1) [-> record reward / done], no host round trip.  The env
+ * must have auto_reset = 0: finished envs freeze, and every `check_every` steps the number of running envs is read back
+ * asynchronously (looked at one interval later, so the stream never drains); the loop stops after max_steps or once that
+ * count was zero.  *steps_run = steps enqueued (>= the longest episode).  Outcomes: cn_env_read_episode_table.
+ * robot_mode: CN_ROBOT_POLICY = the lookahead of `p` (explorer.py:63 with a value-network policy), CN_ROBOT_ORCA = the
+ * robot's own ORCA with `safety_space` (imitation learning, train.py:157-166), CN_ROBOT_KEEP = the pending action is kept
+ * (run_k_episodes(stay=True) after cn_env_set_actions(0, 0)).
+ * rec (optional) fills the replay-side records of explorer.py:60-69,87-89 as DEVICE arrays: states_dev[t] = what
+ * transform_policy.transform (last_state = 0) / predict()'s last_state (1) gives for the state BEFORE step t
+ * ((max_steps, E, H, input_dim) fp32), reward_dev[t], done_dev[t] ((max_steps, E) f64 / u8). */
+enum { CN_ROBOT_POLICY = 0, CN_ROBOT_ORCA = 1, CN_ROBOT_KEEP = 2 };
+typedef struct cn_world cn_world;
+typedef struct cn_rollout_record {
+    cn_policy *transform_policy;
+    int32_t last_state;
+    float *states_dev;
+    double *reward_dev;
+    uint8_t *done_dev;
+} cn_rollout_record;
+int cn_rollout_episodes(cn_policy *p, cn_env *env, cn_world *world, int robot_mode, double safety_space, int query_env,
+                        double epsilon, int32_t max_steps, int32_t check_every, const cn_rollout_record *rec,
+                        int32_t *steps_run, void *stream);
 /* Same through HOST buffers (blocking): uploads agents/times (E x (H+1) x 8, E), runs the step and
  * downloads the new state, reward, done, info and the chosen action index.  Pinned memory recommended. */
 int cn_rollout_step_host(cn_policy *p, cn_env *env, int query_env, double epsilon, const double *agents_in,
@@ -320,7 +344,6 @@ int cn_scenes_generate(int32_t n, const int64_t *seeds, int32_t human_num, int32
  * cn_world_predict: every human's next velocity from the env's CURRENT human states (px, py, vx, vy as fp32, like the
  *   reference's torch.Tensor([...])), written where cn_env_orca puts the ORCA velocities: the following cn_env_step /
  *   cn_policy_lookahead(query_env) / cn_rollout_step consume it.  No host round trip. */
-typedef struct cn_world cn_world;
 int cn_world_create(int32_t kind, int32_t human_num, int device, cn_world **out);
 int cn_world_destroy(cn_world *w);
 int64_t cn_world_param_count(const cn_world *w);

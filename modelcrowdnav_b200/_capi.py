@@ -24,7 +24,7 @@ EXPORTS = [
     "cn_env_robot_orca", "cn_env_step", "cn_env_get_views", "cn_env_read_outputs", "cn_env_read_human_actions",
     "cn_env_read_next_obs", "cn_env_read_actions", "cn_env_set_actions", "cn_env_set_human_actions", "cn_env_read_stats", "cn_env_copy_outputs", "cn_env_episode_table_bytes", "cn_env_read_episode_table", "cn_policy_create", "cn_policy_destroy",
     "cn_policy_param_count", "cn_policy_load_weights", "cn_policy_action_table", "cn_policy_lookahead",
-    "cn_policy_read", "cn_policy_bad_count", "cn_policy_transform", "cn_policy_last_state", "cn_policy_forward", "cn_rollout_step", "cn_rollout_step_sharded", "cn_rollout_step_host", "cn_rollout_step_host_packed", "cn_rollout_step_host_packed_async", "cn_stream_sync", "cn_host_step_bytes",
+    "cn_policy_read", "cn_policy_bad_count", "cn_policy_transform", "cn_policy_last_state", "cn_policy_forward", "cn_rollout_step", "cn_rollout_step_sharded", "cn_rollout_episodes", "cn_rollout_step_host", "cn_rollout_step_host_packed", "cn_rollout_step_host_packed_async", "cn_stream_sync", "cn_host_step_bytes",
     "cn_scenes_generate", "cn_world_create", "cn_world_destroy", "cn_world_param_count", "cn_world_load_weights", "cn_world_predict",
     "cn_trainer_create", "cn_trainer_destroy", "cn_trainer_param_count", "cn_trainer_sync_weights", "cn_trainer_step", "cn_trainer_step_indexed", "cn_trainer_apply",
     "cn_launch_count", "cn_debug_trace", "cn_debug_trace_dump", "cn_selftest_umma", "cn_selftest_umma_bmn", "cn_selftest_umma_ts", "cn_selftest_umma_pair", "cn_debug_tc_timing", "cn_debug_kernel_ms",
@@ -56,6 +56,15 @@ class SarlCfg(C.Structure):
                 ("v_pref", C.c_double), ("precision", C.c_int32), ("kinematics", C.c_int32),
                 ("network", C.c_int32), ("lstm_hidden", C.c_int32), ("lstm_mlp1_dims", C.c_int32 * 4),
                 ("with_om", C.c_int32), ("cell_num", C.c_int32), ("cell_size", C.c_double), ("om_channel_size", C.c_int32)]
+
+
+class RolloutRecord(C.Structure):
+    """cn_rollout_record: replay-side records of cn_rollout_episodes (device arrays of the caller)."""
+    _fields_ = [("transform_policy", C.c_void_p), ("last_state", C.c_int32), ("states_dev", C.c_void_p),
+                ("reward_dev", C.c_void_p), ("done_dev", C.c_void_p)]
+
+
+ROBOT_POLICY, ROBOT_ORCA, ROBOT_KEEP = 0, 1, 2
 
 
 class Stats(C.Structure):
@@ -127,6 +136,8 @@ def load():
     L.cn_policy_forward.argtypes = [vp, vp, i32, i32, vp, vp]
     L.cn_rollout_step.argtypes = [vp, vp, C.c_int, dbl, vp]
     L.cn_rollout_step_sharded.argtypes = [vp, vp, C.c_int, dbl, vp]
+    L.cn_rollout_episodes.argtypes = [vp, vp, vp, C.c_int, dbl, C.c_int, dbl, C.c_int32, C.c_int32, C.POINTER(RolloutRecord),
+                                      C.POINTER(C.c_int32), vp]
     L.cn_rollout_step_host.argtypes = [vp, vp, C.c_int, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.cn_rollout_step_host_packed.argtypes = [vp, vp, C.c_int, dbl, vp, vp, vp]
     L.cn_rollout_step_host_packed_async.argtypes = [vp, vp, C.c_int, dbl, vp, vp, vp]

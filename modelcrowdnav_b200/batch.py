@@ -136,6 +136,30 @@ class BatchedCrowdSim(object):
             return None if t is None else C.c_void_p(t.data_ptr())
         check(self.lib.cn_env_copy_outputs(self.handle, p(reward), p(done), p(info), _stream(stream)))
 
+    def run_episodes(self, max_steps, policy=None, world=None, robot_mode=_capi.ROBOT_POLICY, safety_space=0.0,
+                     query_env=False, epsilon=0.0, check_every=8, record=None, stream=None):
+        """One episode per env, enqueued natively (cn_rollout_episodes; explorer.py:53-69 for the whole batch).
+        record = (transform BatchedSARL, last_state flag): also returns the device records (states (T, E, H, F) fp32,
+        reward (T, E) f64, done (T, E) u8), T = steps enqueued.  Returns (steps_run, states, reward, done)."""
+        rec_p, S, R, D = None, None, None, None
+        if record is not None:
+            import torch
+            th, last_state = record
+            dev = torch.device("cuda", self.device)
+            S = torch.empty((max_steps, self.E, self.H, th.cfg.input_dim), dtype=torch.float32, device=dev)
+            R = torch.zeros((max_steps, self.E), dtype=torch.float64, device=dev)
+            D = torch.ones((max_steps, self.E), dtype=torch.uint8, device=dev)
+            rec = _capi.RolloutRecord(th.handle, int(bool(last_state)), S.data_ptr(), R.data_ptr(), D.data_ptr())
+            rec_p = C.byref(rec)
+        n = C.c_int32(0)
+        check(self.lib.cn_rollout_episodes(policy.handle if policy is not None else None, self.handle, world, int(robot_mode),
+                                           float(safety_space), int(bool(query_env)), float(epsilon), int(max_steps),
+                                           int(check_every), rec_p, C.byref(n), _stream(stream)))
+        n = n.value
+        if record is not None:
+            S, R, D = S[:n], R[:n], D[:n]
+        return n, S, R, D
+
     def episode_table(self, stream=None):
         """Per-env episode accumulators (un-reduced cn_env_read_stats) + frozen flags: dict of (E,) arrays.  Blocking."""
         E = self.E

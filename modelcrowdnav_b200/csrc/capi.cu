@@ -230,6 +230,9 @@ int cn_env_destroy(cn_env *env)
     if (env->tail_stream) cudaStreamDestroy(env->tail_stream);
     if (env->ev_rows) cudaEventDestroy(env->ev_rows);
     if (env->ev_tail) cudaEventDestroy(env->ev_tail);
+    if (env->active_dev) cudaFree(env->active_dev);
+    if (env->active_host) cudaFreeHost(env->active_host);
+    for (cudaEvent_t ev : env->ev_active) if (ev) cudaEventDestroy(ev);
     delete env;
     return CN_OK;
 }
@@ -853,6 +856,97 @@ static int rollout_step_impl(cn_policy *p, cn_env *env, int query_env, double ep
     if ((rc = cn_launch_step(env, nullptr, 1, s, env->p.auto_reset ? 1 : 0))) return rc;     // auto-reset fused into the step
     cn_trace_mark("step_done", s);
     return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// whole episodes: the explorer's loop (explorer.py:53-69) enqueued natively
+// ---------------------------------------------------------------------------------------------
+
+static __global__ void count_active_kernel(int E, const uint8_t *__restrict__ frozen, int32_t *__restrict__ out)
+{
+    __shared__ int total;
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    int n = 0;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) n += frozen[e] ? 0 : 1;
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(&total, n);
+    __syncthreads();
+    if (threadIdx.x == 0) *out = total;
+}
+
+int cn_rollout_episodes(cn_policy *p, cn_env *env, cn_world *world, int robot_mode, double safety_space, int query_env,
+                        double epsilon, int32_t max_steps, int32_t check_every, const cn_rollout_record *rec,
+                        int32_t *steps_run, void *stream)
+{
+    if (!env || !steps_run) { cn_set_error("null argument"); return CN_EINVAL; }
+    if (robot_mode < CN_ROBOT_POLICY || robot_mode > CN_ROBOT_KEEP) { cn_set_error("robot_mode %d", robot_mode); return CN_EINVAL; }
+    if (max_steps < 0 || check_every < 1) { cn_set_error("max_steps >= 0 and check_every >= 1"); return CN_EINVAL; }
+    if (env->p.auto_reset) {
+        cn_set_error("cn_rollout_episodes runs ONE episode per env: create the env with auto_reset = 0");
+        return CN_EINVAL;
+    }
+    int rc;
+    if (robot_mode == CN_ROBOT_POLICY) {
+        if ((rc = check_pair(p, env))) return rc;
+    }
+    cn_policy *tp = rec ? rec->transform_policy : nullptr;
+    if (rec && (!tp || !rec->states_dev || !rec->reward_dev || !rec->done_dev)) {
+        cn_set_error("cn_rollout_record needs transform_policy, states_dev, reward_dev and done_dev");
+        return CN_EINVAL;
+    }
+    if (tp && tp->device != env->device) { cn_set_error("transform policy and env live on different devices"); return CN_EINVAL; }
+    CN_CUDA_CHECK(cudaSetDevice(env->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!env->active_dev) {
+        CN_CUDA_CHECK(cudaMalloc(&env->active_dev, 2 * sizeof(int32_t)));
+        CN_CUDA_CHECK(cudaMallocHost(&env->active_host, 2 * sizeof(int32_t)));
+        for (cudaEvent_t &ev : env->ev_active) CN_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
+    const size_t E = env->p.d.E;
+    const size_t state_floats = tp ? E * (size_t)env->p.d.H * (size_t)tp->cfg.input_dim : 0;
+    int slot = 0, pending = -1;
+    *steps_run = 0;
+    for (int step = 0; step < max_steps; ++step) {
+        if (tp) {
+            // policy.last_state = transform(state) (multi_human_rl.py:60-61) / target_policy.transform(state) (explorer.py:163)
+            const int sorted = rec->last_state && tp->cfg.network == CN_NET_LSTM_RL;
+            if ((rc = cn_transform_f32(tp, env, rec->states_dev + (size_t)step * state_floats, sorted, s))) return rc;
+        }
+        if (robot_mode == CN_ROBOT_POLICY && !world) {
+            cudaStream_t cur;
+            if ((rc = rollout_step_impl(p, env, query_env, epsilon, s, nullptr, &cur))) return rc;
+        } else {
+            if (world) rc = cn_world_predict(world, env, s);
+            else rc = cn_launch_orca(env, s);
+            if (rc) return rc;
+            if (robot_mode == CN_ROBOT_POLICY)
+                rc = p->cfg.precision == CN_PREC_F16_TC ? cn_lookahead_tc(p, env, query_env, epsilon, s) : cn_lookahead_f32(p, env, query_env, epsilon, s);
+            else if (robot_mode == CN_ROBOT_ORCA) rc = cn_launch_robot_orca(env, safety_space, s);
+            if (rc) return rc;
+            if ((rc = cn_launch_step(env, nullptr, 1, s, 0))) return rc;
+        }
+        if (rec) {
+            CN_CUDA_CHECK(cudaMemcpyAsync(rec->reward_dev + (size_t)step * E, env->reward, sizeof(double) * E, cudaMemcpyDeviceToDevice, s));
+            CN_CUDA_CHECK(cudaMemcpyAsync(rec->done_dev + (size_t)step * E, env->done, E, cudaMemcpyDeviceToDevice, s));
+        }
+        *steps_run = step + 1;
+        if ((step + 1) % check_every == 0) {
+            // the count enqueued one interval ago has (all but certainly) arrived: waiting for it does not drain the stream
+            if (pending >= 0) {
+                CN_CUDA_CHECK(cudaEventSynchronize(env->ev_active[pending]));
+                if (env->active_host[pending] == 0) break;
+            }
+            count_active_kernel<<<1, 256, 0, s>>>((int)E, env->frozen, env->active_dev + slot);
+            CN_CUDA_CHECK(cudaGetLastError());
+            g_cn_launches.fetch_add(1);
+            CN_CUDA_CHECK(cudaMemcpyAsync(env->active_host + slot, env->active_dev + slot, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+            CN_CUDA_CHECK(cudaEventRecord(env->ev_active[slot], s));
+            pending = slot;
+            slot ^= 1;
+        }
+    }
+    return CN_OK;
 }
 
 int cn_rollout_step_host(cn_policy *p, cn_env *env, int query_env, double epsilon, const double *agents_in,

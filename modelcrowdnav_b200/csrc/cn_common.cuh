@@ -76,6 +76,9 @@ struct cn_env {
     cudaStream_t tail_stream;          // highest-priority stream for everything after the row kernel (pipelined host steps)
     cudaEvent_t ev_rows, ev_tail;
     double *io_block;     // device image of the packed host exchange block (cn_rollout_step_host_packed), lazily allocated
+    // cn_rollout_episodes: "how many envs are still running" read back asynchronously (2 slots, checked one interval late)
+    int32_t *active_dev, *active_host;
+    cudaEvent_t ev_active[2];
 };
 
 struct SarlDims {

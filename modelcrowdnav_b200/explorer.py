@@ -198,17 +198,20 @@ class Explorer(object):
         max_steps = int(round(env.time_limit / dt)) + 2
         gamma = self.gamma if self.gamma is not None else 1.0
         if stay or is_sarl or isinstance(policy, ORCA):
-            humans = (lambda: env.world_step_batch(b)) if world_env else b.orca     # world model or ORCA, both on the device
+            world = None
+            if world_env:                              # ModelCrowdSim: the humans' next velocities come from the world model
+                if not hasattr(env.sim_world, "handle"):
+                    raise NotImplementedError("sim_world must be a modelcrowdnav_b200.world_model MlpWorld / AttentionWorld")
+                world = env.sim_world.handle(b.device)
             record = None
             if update_memory:
                 # policy.last_state = transform(state) (multi_human_rl.py:60-61) / target_policy.transform (explorer.py:163)
                 if not isinstance(tr_policy, SARL):
                     raise ValueError("update_memory needs a SARL policy (or target_policy) to transform states")
-                th = tr_policy.handle(v_pref)
                 # RL: predict()'s last_state (LSTM-RL rows in its sorted human order); IL: plain transform()
-                record = (lambda: th.transform(b, last_state=not imitation_learning), isinstance(tr_policy, CADRL))
+                record = (tr_policy.handle(v_pref), not imitation_learning, isinstance(tr_policy, CADRL))
             return self._rollout_device(b, k, max_steps, stay, is_sarl, policy, handle if is_sarl else None,
-                                        eps if is_sarl else 0.0, humans, record)
+                                        eps if is_sarl else 0.0, world, record)
 
         active = np.ones(k, bool)
         rewards_t, states_t, active_t = [], [], []
@@ -265,43 +268,29 @@ class Explorer(object):
         return dict(R=R, M=M, final_info=final_info, end_time=end_time, too_close=too_close, min_dist_sum=min_dist_sum,
                     states_t=states_t, returns=(R * disc[:, None]).sum(0), steps=M.sum(0))
 
-    def _rollout_device(self, b, k, max_steps, stay, is_sarl, policy, handle, eps, humans, record=None):
-        """Episodes of a batch with NO host sync per step: kernels back to back, outcomes from the per-env episode
-        accumulators.  Finished envs freeze (auto_reset off), so extra steps are harmless; every `check` steps the frozen flags
-        (k bytes) are read to stop as soon as the last episode has ended.  record = (state_fn, squeeze): replay-filling phases
-        also keep, per step, the transformed state and the reward / done outputs as DEVICE tensors."""
+    def _rollout_device(self, b, k, max_steps, stay, is_sarl, policy, handle, eps, world, record=None):
+        """Episodes of a batch with NO host sync per step: the whole loop of explorer.py:53-69 is enqueued natively
+        (cn_rollout_episodes), outcomes come from the per-env episode accumulators.  Finished envs freeze (auto_reset off), so
+        extra steps are harmless; the count of running envs is read back asynchronously to stop soon after the last episode
+        has ended.  record = (transform handle, last_state, squeeze): replay-filling phases also keep, per step, the transformed
+        state and the reward / done outputs as DEVICE tensors."""
         import torch
         b.stats(reset=True)                             # zero the accumulators (set_state cleared the per-episode parts)
         if is_sarl:
             bad0 = handle.bad_count()
         if stay:
             b.set_actions(np.zeros((k, 2)))
-        states_t, R, D = [], None, None
+        mode = _capi.ROBOT_KEEP if stay else (_capi.ROBOT_POLICY if is_sarl else _capi.ROBOT_ORCA)
+        steps_run, S, R, D = b.run_episodes(
+            max_steps, policy=handle if mode == _capi.ROBOT_POLICY else None, world=world, robot_mode=mode,
+            safety_space=0.0 if is_sarl or stay else policy.safety_space, query_env=bool(is_sarl and policy.query_env), epsilon=eps,
+            record=None if record is None else record[:2])
+        states_t = None
         if record is not None:
-            dev = torch.device("cuda", b.device)
-            R = torch.zeros((max_steps, k), dtype=torch.float64, device=dev)
-            D = torch.ones((max_steps, k), dtype=torch.uint8, device=dev)
-        check, steps_run = 8, 0
-        for step in range(max_steps):
-            if record is not None:
-                st = record[0]()
-                if record[1]:
-                    assert st.shape[1] == 1                        # cadrl.py:209: CADRL trains on single-human states
-                    st = st[:, 0]
-                states_t.append(st)
-            humans()
-            if stay:
-                pass                                    # pending action stays (0, 0)
-            elif is_sarl:
-                handle.lookahead(b, query_env=policy.query_env, epsilon=eps)
-            else:
-                b.robot_orca(policy.safety_space)
-            b.step(update=True, read=False)
-            if record is not None:
-                b.copy_outputs_to(R[step], D[step])
-            steps_run = step + 1
-            if step % check == check - 1 and b.all_done():
-                break
+            if record[2]:
+                assert S.shape[2] == 1                             # cadrl.py:209: CADRL trains on single-human states
+                S = S[:, :, 0]
+            states_t = S
         t = b.episode_table()
         if is_sarl and handle.bad_count() != bad0:
             raise ValueError("Value network is not well trained. ")         # multi_human_rl.py:57-58
@@ -312,10 +301,8 @@ class Explorer(object):
                             np.where(t["collision"] == 1, t["sum_collision_time"], t["sum_timeout_time"]))
         M = None
         if record is not None:
-            R, D = R[:steps_run], D[:steps_run]
             # env e was active in step t iff it had not finished before it: done stays 1 once an env is frozen
             M = torch.cat([torch.ones((1, k), dtype=torch.bool, device=D.device), D[:-1] == 0])
-            states_t = states_t[:steps_run]
         return dict(R=R, M=M, final_info=final_info.astype(np.int64), end_time=end_time,
                     too_close=int(t["too_close"].sum()), min_dist_sum=float(t["sum_min_dist"].sum()), states_t=states_t,
                     returns=t["sum_return"].copy(), steps=t["steps"].copy())
@@ -343,7 +330,7 @@ class Explorer(object):
                 raise ValueError("Memory or gamma value is not set!")
             keep = np.nonzero(success | collision)[0]              # explorer.py:110-113
             if len(keep):
-                S = torch.stack(states_t)                          # (T, k, H, 13) on the device
+                S = torch.stack(states_t) if isinstance(states_t, list) else states_t     # (T, k, H, 13) on the device
                 self._update_memory_batched(S, R, M, keep, imitation_learning)
 
         counts = np.array([success.sum(), collision.sum(), timeout.sum(), too_close, k], dtype=np.float64)

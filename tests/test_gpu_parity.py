@@ -276,6 +276,58 @@ def test_episode_stats_and_freeze(mcn, oracle_mod, weights0):
     env.close(); pol.close()
 
 
+@pytest.mark.parametrize("robot", ["policy", "orca", "keep"])
+def test_native_episode_loop_equals_stepwise(mcn, oracle_mod, weights_trained, robot):
+    """cn_rollout_episodes (explorer.py:53-69 enqueued natively, with the replay records) leaves exactly what the same steps
+    issued one call at a time leave: final state, per-env episode table, per-step transformed states / rewards / done flags."""
+    import torch
+    from modelcrowdnav_b200 import _capi
+    o = oracle_mod
+    E, H, T = 96, 5, 102
+    agents = _scenes(o, E, H)
+    agents[:8, 0, :2] = [0.0, 3.0]
+    pol = mcn.BatchedSARL(precision="f32")
+    pol.load_weights(weights_trained)
+    mode = dict(policy=_capi.ROBOT_POLICY, orca=_capi.ROBOT_ORCA, keep=_capi.ROBOT_KEEP)[robot]
+
+    ref = mcn.BatchedCrowdSim(E, H)
+    ref.set_state(agents)
+    if robot == "keep":
+        ref.set_actions(np.zeros((E, 2)))
+    S_ref, R_ref, D_ref = [], [], []
+    for t in range(T):
+        S_ref.append(pol.transform(ref))
+        ref.orca()
+        if robot == "policy":
+            pol.lookahead(ref, query_env=True, epsilon=0.0)
+        elif robot == "orca":
+            ref.robot_orca(0.0)
+        r, d, _, _ = ref.step(update=True)
+        R_ref.append(r); D_ref.append(d)
+        if ref.all_done():
+            break
+    n_ref = len(R_ref)
+
+    env = mcn.BatchedCrowdSim(E, H)
+    env.set_state(agents)
+    if robot == "keep":
+        env.set_actions(np.zeros((E, 2)))
+    n, S, R, D = env.run_episodes(T, policy=pol if robot == "policy" else None, robot_mode=mode, query_env=True,
+                                  check_every=4, record=(pol, False))
+    assert n_ref <= n <= min(T, n_ref + 8)               # stops at most two check intervals after the last episode ended
+    assert S.shape == (n, E, H, 13) and R.shape == (n, E) and D.shape == (n, E)
+    assert torch.equal(S[:n_ref], torch.stack(S_ref))
+    assert np.array_equal(R[:n_ref].cpu().numpy(), np.stack(R_ref))
+    assert np.array_equal(D[:n_ref].cpu().numpy(), np.stack(D_ref))
+    assert (D[n_ref:] == 1).all() and (R[n_ref:] == 0).all()     # steps after the last episode: everything frozen
+    a, b = env.episode_table(), ref.episode_table()
+    for key in a:
+        assert np.array_equal(a[key], b[key]), key
+    assert a["frozen"].all() and (a["episodes"] == 1).all()
+    assert np.array_equal(env.get_state()[0], ref.get_state()[0])
+    env.close(); ref.close(); pol.close()
+
+
 @pytest.mark.parametrize("H", [5, 20])
 def test_device_reset_properties(mcn, H):
     """Device-side reset: scene invariants of crowd_sim.py:165-217 and shard invariance (global env id).  H = 20 takes the
