@@ -802,3 +802,54 @@ def test_tc_large_groups_vs_oracle(mcn, oracle_mod, weights0, H):
             assert value_errors(v16[e], ovals, "f16_tc") <= 1.0
         env.step(update=True, read=False)
     env.close(); p16.close(); p32.close()
+
+
+@pytest.mark.parametrize("E,H", [(1, 1), (2, 1), (1, 5), (3, 2), (2, 64)])
+def test_smallest_and_largest_shapes_vs_oracle(mcn, oracle_mod, weights_trained, E, H):
+    """The ends of the supported range: one env, one human (the group mean and the softmax degenerate to the row itself,
+    sarl.py:47-58), a tile that is almost empty, and CN_MAX_HUMANS = 64 humans (2 groups per tile).  ORCA velocities and
+    the step bit-exact against the oracle, lookahead values to the bars of both precisions, three evolved steps."""
+    o = oracle_mod
+    ecfg, scfg = o.EnvCfg.default(), o.SarlCfg.default()
+    rule, width = ("circle_crossing", 10.0) if H <= 5 else ("square_crossing", 16.0)
+    env = mcn.BatchedCrowdSim(E, H, square_width=width)
+    p16 = mcn.BatchedSARL(precision="f16_tc"); p16.load_weights(weights_trained)
+    p32 = mcn.BatchedSARL(precision="f32"); p32.load_weights(weights_trained)
+    agents = np.stack([o.generate_scene("test", 40 + c, human_num=H, rule=rule, square_width=width) for c in range(E)])
+    env.set_state(agents)
+    times = np.zeros(E)
+    for step in range(3):
+        env.orca()
+        hv = env.human_actions()
+        p16.lookahead(env, 1); b16, v16 = p16.read(env)
+        p32.lookahead(env, 1); b32, v32 = p32.read(env)
+        ref_vals = []
+        for e in range(E):
+            ohv = o.human_actions(ecfg, agents[e])
+            assert np.array_equal(hv[e], ohv)
+            obest, ovals, _ = o.lookahead(ecfg, scfg, weights_trained, agents[e], times[e], p32.action_table, True, ohv)
+            assert value_errors(v32[e], ovals, "f32") <= 1.0
+            assert value_errors(v16[e], ovals, "f16_tc") <= 1.0
+            ref_vals.append(ovals)
+        ref_vals = np.stack(ref_vals)
+        for best, prec in ((b32, "f32"), (b16, "f16_tc")):
+            regret = ref_vals.max(axis=1) - ref_vals[np.arange(E), best]
+            assert np.all(regret <= TIE_GAP[prec])
+        reward, done, info, dmin = env.step(update=True)          # the pending action is the FP32 path's choice
+        for e in range(E):
+            act = p32.action_table[b32[e]]
+            r, d, i, dm = o.step_outcome(ecfg, agents[e], times[e], act)
+            assert (reward[e], bool(done[e]), int(info[e])) == (r, bool(d), int(i))
+            times[e] = o.apply_step(ecfg, agents[e], times[e], act, o.human_actions(ecfg, agents[e]))
+        got, gt = env.get_state()
+        assert np.array_equal(got, agents) and np.array_equal(gt, times)
+    env.close(); p16.close(); p32.close()
+
+
+def test_shape_limits_are_refused(mcn):
+    """Out-of-range shapes fail loudly at handle creation (CN_EINVAL with a message), never silently clamp."""
+    from modelcrowdnav_b200 import _capi
+    for kw in (dict(num_envs=0, human_num=5), dict(num_envs=4, human_num=0), dict(num_envs=4, human_num=65)):
+        with pytest.raises(_capi.CrowdNavError) as ei:
+            mcn.BatchedCrowdSim(kw["num_envs"], kw["human_num"])
+        assert ei.value.code == _capi.CN_EINVAL
