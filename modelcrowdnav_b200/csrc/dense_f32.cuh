@@ -18,11 +18,13 @@ constexpr int kRowsPerItem = 8;
 template <bool W_IN_SMEM>
 __device__ __forceinline__ float ldw(const float *p) { return W_IN_SMEM ? *p : __ldg(p); }
 
+// gate: optional ReLU-backward mask applied to the result (see the epilogue).
 // W_IN_SMEM: the weight block (and bias) was staged into shared memory (trainer.cu prefetches the next layer's block with
 // cp.async while this one computes); otherwise it is streamed from L2.
 template <bool W_IN_SMEM>
 __device__ __forceinline__ void dense_t(const float *__restrict__ X, int ldx, int R, int K, const float *__restrict__ Wt,
-                                        const float *__restrict__ b, int O, float *__restrict__ Y, int ldy, bool relu, bool accumulate)
+                                        const float *__restrict__ b, int O, float *__restrict__ Y, int ldy, bool relu, bool accumulate,
+                                        const float *__restrict__ gate = nullptr, int ldg = 0)
 {
     const int groups = (R + kRowsPerItem - 1) / kRowsPerItem;
     for (int idx = threadIdx.x; idx < O * groups; idx += kThreads) {
@@ -74,6 +76,8 @@ __device__ __forceinline__ void dense_t(const float *__restrict__ X, int ldx, in
             if (i < nr) {
                 float v = acc[i];
                 if (accumulate) v += Y[(size_t)(r0 + i) * ldy + o];
+                // gate = the post-ReLU activation this gradient flows back through: dA *= (act > 0), fused ReLU backward
+                if (gate && !(gate[(size_t)(r0 + i) * ldg + o] > 0.0f)) v = 0.0f;
                 Y[(size_t)(r0 + i) * ldy + o] = relu ? fmaxf(v, 0.0f) : v;
             }
         }
@@ -123,15 +127,5 @@ __device__ __forceinline__ void weight_grad(const float *__restrict__ dY, int ld
         gb[o] = s;
     }
 }
-
-// dA[r][k] *= (act[r][k] > 0)   (ReLU backward; act holds the post-ReLU activation)
-__device__ __forceinline__ void relu_mask(float *__restrict__ dA, int ld, const float *__restrict__ act, int lda, int R, int K)
-{
-    for (int idx = threadIdx.x; idx < R * K; idx += kThreads) {
-        const int r = idx / K, k = idx - r * K;
-        if (!(act[(size_t)r * lda + k] > 0.0f)) dA[(size_t)r * ld + k] = 0.0f;
-    }
-}
-
 
 }  // namespace dense_f32

@@ -28,7 +28,7 @@
 
 namespace {
 
-using namespace dense_f32;      // kThreads, pad4, dense, weight_grad, relu_mask
+using namespace dense_f32;      // kThreads, pad4, dense_t, weight_grad
 constexpr int kSPC = 1;           // samples per CTA: 100 CTAs for the reference batch of 100; H <= 8 rows = one weight pass per layer
 constexpr int kMaxH = 16;         // humans per sample supported by the shared-memory plan
 constexpr int kLayers = 11;
@@ -101,18 +101,20 @@ __host__ __device__ inline Plan make_plan(const TDims &d, int H, int ns)
 // (0.5 MB) that every CTA fetches exactly once, and the instruction fetch becomes the largest stall (ncu: stall_no_inst 31 %).
 // One out-of-line copy of each routine keeps the whole kernel inside the instruction cache.
 __device__ __noinline__ void dense_staged(const float *X, int ldx, int R, int K, const float *Wt, const float *b, int O, float *Y,
-                                          int ldy, bool relu, bool accumulate)
+                                          int ldy, bool relu, bool accumulate, const float *gate, int ldg)
 {
-    dense_t<true>(X, ldx, R, K, Wt, b, O, Y, ldy, relu, accumulate);
+    dense_t<true>(X, ldx, R, K, Wt, b, O, Y, ldy, relu, accumulate, gate, ldg);
 }
 __device__ __noinline__ void weight_grad_call(const float *dY, int ldy, const float *Xin, int ldx, int R, int O, int K, float *gW,
                                               float *gb)
 {
     weight_grad(dY, ldy, Xin, ldx, R, O, K, gW, gb);
 }
-__device__ __noinline__ void relu_mask_call(float *dA, int ld, const float *act, int lda, int R, int K)
+__device__ __noinline__ void stage_block(float *dst, const float *src, int n)
 {
-    relu_mask(dA, ld, act, lda, R, K);
+#pragma unroll 4
+    for (int i = threadIdx.x * 4; i < n; i += kThreads * 4) cp_async16(dst + i, src + i);
+    cp_async_commit();
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -146,8 +148,7 @@ trainer_fwd_bwd_kernel(TDims d, const float *__restrict__ Wt, const float *__res
     auto fetch = [&](int k, float *dst) {
         const float *src = op_src(k);
         const int n = op_floats(k);
-        for (int i = tid * 4; i < n; i += kThreads * 4) cp_async16(dst + i, src + i);
-        cp_async_commit();
+        stage_block(dst, src, n);
     };
     int op = 0;
     // start of weighted op `op`: with two buffers the NEXT block's copy is started (its buffer was released by the barrier that
@@ -168,13 +169,13 @@ trainer_fwd_bwd_kernel(TDims d, const float *__restrict__ Wt, const float *__res
 #define FWD(i, Xp, ldx_, Rr, Yp, ldy_, relu_)                                                                       \
     do {                                                                                                            \
         const float *wb = begin_op();                                                                               \
-        dense_staged(Xp, ldx_, Rr, L[i].in, wb, wb + pad4(L[i].in * L[i].out), L[i].out, Yp, ldy_, relu_, false);  \
+        dense_staged(Xp, ldx_, Rr, L[i].in, wb, wb + pad4(L[i].in * L[i].out), L[i].out, Yp, ldy_, relu_, false, nullptr, 0);  \
     } while (0)
     // dX[r][k] = sum_o dY[r][o] W[o][k]: the same routine with X = dY, "K" = out, "O" = in, no bias
-#define BWD(i, dYp, ldy_, Rr, dXp, ldx_, acc_)                                                                      \
+#define BWD(i, dYp, ldy_, Rr, dXp, ldx_, acc_, gate_, ldg_)                                                                      \
     do {                                                                                                            \
         const float *wb = begin_op();                                                                               \
-        dense_staged(dYp, ldy_, Rr, L[i].out, wb, nullptr, L[i].in, dXp, ldx_, false, acc_);                       \
+        dense_staged(dYp, ldy_, Rr, L[i].out, wb, nullptr, L[i].in, dXp, ldx_, false, acc_, gate_, ldg_);                       \
     } while (0)
 
     // ---------------- forward (sarl.py:28-65) ----------------
@@ -242,25 +243,19 @@ trainer_fwd_bwd_kernel(TDims d, const float *__restrict__ Wt, const float *__res
     // mlp3.6
     weight_grad_call(dv, 1, g3, p.ld_g, ns, 1, L[10].in, G + L[10].w_off, G + L[10].b_off);
     float *dg3 = d1;                                                // [ns][ld_g]
-    BWD(10, dv, 1, ns, dg3, p.ld_g, false); end_op();
-    relu_mask_call(dg3, p.ld_g, g3, p.ld_g, ns, L[9].out);
-    __syncthreads();
+    BWD(10, dv, 1, ns, dg3, p.ld_g, false, g3, p.ld_g); end_op();
     // mlp3.4
     weight_grad_call(dg3, p.ld_g, g2, p.ld_g, ns, L[9].out, L[9].in, G + L[9].w_off, G + L[9].b_off);
     float *dg2 = d0;                                                // dv is dead
-    BWD(9, dg3, p.ld_g, ns, dg2, p.ld_g, false); end_op();
-    relu_mask_call(dg2, p.ld_g, g2, p.ld_g, ns, L[8].out);
-    __syncthreads();
+    BWD(9, dg3, p.ld_g, ns, dg2, p.ld_g, false, g2, p.ld_g); end_op();
     // mlp3.2
     weight_grad_call(dg2, p.ld_g, g1, p.ld_g1, ns, L[8].out, L[8].in, G + L[8].w_off, G + L[8].b_off);
     float *dg1 = d1;                                                // dg3 is dead
-    BWD(8, dg2, p.ld_g, ns, dg1, p.ld_g1, false); end_op();
-    relu_mask_call(dg1, p.ld_g1, g1, p.ld_g1, ns, L[7].out);
-    __syncthreads();
+    BWD(8, dg2, p.ld_g, ns, dg1, p.ld_g1, false, g1, p.ld_g1); end_op();
     // mlp3.0
     weight_grad_call(dg1, p.ld_g1, j, p.ld_j, ns, L[7].out, L[7].in, G + L[7].w_off, G + L[7].b_off);
     float *dj = d0;                                                 // [ns][ld_j]; the self-state part has no parameters upstream
-    BWD(7, dg1, p.ld_g1, ns, dj, p.ld_j, false); end_op();
+    BWD(7, dg1, p.ld_g1, ns, dj, p.ld_j, false, nullptr, 0); end_op();
     // weighted feature c = sum_i w_i f_i :  df_i = w_i dc,  dw_i = dc . f_i ;  softmax: ds_i = w_i (dw_i - sum_k w_k dw_k)
     float *df = d1;                                                 // [R][ld_f]  (dg1 is dead)
     float *dsc = sm + p.sc;                                         // scores are dead after the softmax: reuse for ds
@@ -285,25 +280,19 @@ trainer_fwd_bwd_kernel(TDims d, const float *__restrict__ Wt, const float *__res
     weight_grad_call(df, p.ld_f, f1, p.ld_f1, R, L[3].out, L[3].in, G + L[3].w_off, G + L[3].b_off);
     weight_grad_call(dsc, 1, t2, p.ld_t, R, 1, L[6].in, G + L[6].w_off, G + L[6].b_off);
     float *df1 = d0;                                                // [R][ld_f1]  (dj is dead)
-    BWD(3, df, p.ld_f, R, df1, p.ld_f1, false); end_op();
-    relu_mask_call(df1, p.ld_f1, f1, p.ld_f1, R, L[2].out);
-    __syncthreads();
+    BWD(3, df, p.ld_f, R, df1, p.ld_f1, false, f1, p.ld_f1); end_op();
     // mlp2.0's weights now; its data path joins de below
     weight_grad_call(df1, p.ld_f1, e, p.ld_e, R, L[2].out, L[2].in, G + L[2].w_off, G + L[2].b_off);
     float *dt2 = d1;                                                // [R][ld_t]  (df is dead)
-    BWD(6, dsc, 1, R, dt2, p.ld_t, false); end_op();                // dt2 = ds * W_att4[0][:]
-    relu_mask_call(dt2, p.ld_t, t2, p.ld_t, R, L[5].out);
-    __syncthreads();
+    BWD(6, dsc, 1, R, dt2, p.ld_t, false, t2, p.ld_t); end_op();                // dt2 = ds * W_att4[0][:]
     // attention.2
     weight_grad_call(dt2, p.ld_t, t1, p.ld_t, R, L[5].out, L[5].in, G + L[5].w_off, G + L[5].b_off);
     float *dt1 = t2;                                                // t2 is dead once its mask and attention.4's gradient are taken
-    BWD(5, dt2, p.ld_t, R, dt1, p.ld_t, false); end_op();
-    relu_mask_call(dt1, p.ld_t, t1, p.ld_t, R, L[4].out);
-    __syncthreads();
+    BWD(5, dt2, p.ld_t, R, dt1, p.ld_t, false, t1, p.ld_t); end_op();
     // attention.0 on u = [e | mean]
     weight_grad_call(dt1, p.ld_t, u, p.ld_u, R, L[4].out, L[4].in, G + L[4].w_off, G + L[4].b_off);
     float *du = d1;                                                 // [R][ld_u]  (dt2 is dead)
-    BWD(4, dt1, p.ld_t, R, du, p.ld_u, false); end_op();
+    BWD(4, dt1, p.ld_t, R, du, p.ld_u, false, nullptr, 0); end_op();
     // de_i = du_i[:E1] + (1/H) sum_k du_k[E1:]  + mlp2.0's path (df1 W_20)
     float *de = t1;                                                 // t1 is dead; rows of ld_t floats
     for (int idx = tid; idx < ns * E1; idx += kThreads) {
@@ -313,15 +302,11 @@ trainer_fwd_bwd_kernel(TDims d, const float *__restrict__ Wt, const float *__res
         m /= (float)H;
         for (int h = 0; h < H; ++h) de[(size_t)(s * H + h) * p.ld_t + k] = du[(size_t)(s * H + h) * p.ld_u + k] + m;
     }
-    BWD(2, df1, p.ld_f1, R, de, p.ld_t, true); end_op();            // += df1 * W_mlp2.0   (begin_op's barrier publishes de)
-    relu_mask_call(de, p.ld_t, e, p.ld_e, R, L[1].out);
-    __syncthreads();
+    BWD(2, df1, p.ld_f1, R, de, p.ld_t, true, e, p.ld_e); end_op();            // += df1 * W_mlp2.0   (begin_op's barrier publishes de)
     // mlp1.2
     weight_grad_call(de, p.ld_t, a1, p.ld_a1, R, L[1].out, L[1].in, G + L[1].w_off, G + L[1].b_off);
     float *da1 = d1;                                                // [R][ld_a1]  (du is dead)
-    BWD(1, de, p.ld_t, R, da1, p.ld_a1, false); end_op();
-    relu_mask_call(da1, p.ld_a1, a1, p.ld_a1, R, L[0].out);
-    __syncthreads();
+    BWD(1, de, p.ld_t, R, da1, p.ld_a1, false, a1, p.ld_a1); end_op();
     // mlp1.0 (no gradient w.r.t. the input)
     weight_grad_call(da1, p.ld_a1, xs, p.ld_x, R, L[0].out, L[0].in, G + L[0].w_off, G + L[0].b_off);
 #undef FWD
@@ -451,12 +436,18 @@ int cn_trainer_create(const cn_sarl_cfg *cfg, int device, int32_t max_batch, int
         cn_trainer_destroy(t);
         return CN_ENOMEM;
     }
-    CN_CUDA_CHECK(cudaMemset(t->Wt, 0, sizeof(float) * d.t_size));          // the padding floats of the blocks are read by cp.async
-    CN_CUDA_CHECK(cudaMemset(t->Wa, 0, sizeof(float) * d.a_size));
-    CN_CUDA_CHECK(cudaMemset(t->mom, 0, sizeof(float) * d.n_params));
-    CN_CUDA_CHECK(cudaMemcpy(t->tmap, tmap.data(), sizeof(int32_t) * d.n_params, cudaMemcpyHostToDevice));
-    CN_CUDA_CHECK(cudaMemcpy(t->amap, amap.data(), sizeof(int32_t) * d.n_params, cudaMemcpyHostToDevice));
-    CN_CUDA_CHECK(cudaFuncSetAttribute(trainer_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    // (the padding floats of the blocks are read by cp.async, hence the memsets)
+    cudaError_t ce = cudaMemset(t->Wt, 0, sizeof(float) * d.t_size);
+    if (ce == cudaSuccess) ce = cudaMemset(t->Wa, 0, sizeof(float) * d.a_size);
+    if (ce == cudaSuccess) ce = cudaMemset(t->mom, 0, sizeof(float) * d.n_params);
+    if (ce == cudaSuccess) ce = cudaMemcpy(t->tmap, tmap.data(), sizeof(int32_t) * d.n_params, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(t->amap, amap.data(), sizeof(int32_t) * d.n_params, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(trainer_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (ce != cudaSuccess) {
+        cn_set_error("cn_trainer_create: %s", cudaGetErrorString(ce));
+        cn_trainer_destroy(t);
+        return CN_ECUDA;
+    }
     *out = t;
     return CN_OK;
 }

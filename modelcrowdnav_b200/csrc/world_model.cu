@@ -212,8 +212,13 @@ int cn_world_create(int32_t kind, int32_t human_num, int device, cn_world **out)
     }
     w->n_params = off;
     if (cudaMalloc((void **)&w->W, sizeof(float) * off) != cudaSuccess) { delete w; cn_set_error("cudaMalloc failed in cn_world_create"); return CN_ENOMEM; }
-    CN_CUDA_CHECK(cudaFuncSetAttribute(attention_world_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    CN_CUDA_CHECK(cudaFuncSetAttribute(mlp_world_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    cudaError_t ce = cudaFuncSetAttribute(attention_world_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(mlp_world_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (ce != cudaSuccess) {
+        cn_set_error("cn_world_create: %s", cudaGetErrorString(ce));
+        cn_world_destroy(w);
+        return CN_ECUDA;
+    }
     *out = w;
     return CN_OK;
 }
