@@ -104,13 +104,14 @@ typedef struct {
      * gamma_bar * MIN over humans.  CN_NET_LSTM_RL (lstm_rl.py:9-105): humans sorted by decreasing distance (query_env =
      * false only, see multi_human_rl.py:37-42), nn.LSTM(13 or lstm_mlp1_dims[3] -> lstm_hidden) over the rows, mlp3_dims =
      * [lstm_rl] mlp2_dims on cat(self_state, h_n); lstm_mlp1_dims[0] > 0 selects ValueNetwork2 (with_interaction_module).
-     * Both run on the FP32 path only (CN_PREC_F32). */
+     * CADRL runs on either precision (default mlp_dims on the tensor cores); LSTM-RL on the FP32 path only (CN_PREC_F32). */
     int32_t network;             /* CN_NET_* */
     int32_t lstm_hidden;         /* [lstm_rl] global_state_dim = 50 */
     int32_t lstm_mlp1_dims[4];   /* [lstm_rl] mlp1_dims = 150,100,100,50; {0} = ValueNetwork1 */
     /* Occupancy maps ([sarl] / [lstm_rl] with_om = true, multi_human_rl.py:43-50,98-163): every rotated row is followed by
      * the cell_num x cell_num x om_channel_size map of the OTHER humans around that human, built once per lookahead from
-     * the next human states; input_dim must be 13 + cell_num^2 * om_channel_size.  FP32 path only. */
+     * the next human states; input_dim must be 13 + cell_num^2 * om_channel_size.  SARL: both precisions (on the tensor-core
+     * path the map, which does not depend on the action, enters mlp1.0 as one fp32 row bias per human); LSTM-RL: FP32. */
     int32_t with_om;
     int32_t cell_num;            /* [om] cell_num = 4 (<= 8) */
     double cell_size;            /* [om] cell_size = 1 */

@@ -523,8 +523,8 @@ int cn_policy_create(const cn_sarl_cfg *cfg, int device, cn_policy **out)
             return CN_EINVAL;
         }
         if (cfg->network == CN_NET_CADRL) { cn_set_error("CADRL has no occupancy maps (cadrl.py:60-62)"); return CN_EINVAL; }
-        if (cfg->precision != CN_PREC_F32) {
-            cn_set_error("occupancy maps run on the FP32 path only (precision = CN_PREC_F32)"); return CN_EUNSUPPORTED;
+        if (cfg->precision != CN_PREC_F32 && cfg->network != CN_NET_SARL) {
+            cn_set_error("occupancy maps on the tensor-core path are built for SARL only; use CN_PREC_F32"); return CN_EUNSUPPORTED;
         }
         om_dim = cfg->cell_num * cfg->cell_num * cfg->om_channel_size;
     }

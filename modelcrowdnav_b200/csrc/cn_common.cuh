@@ -94,6 +94,53 @@ struct SarlDims {
     double cell_size;
 };
 
+// build_occupancy_maps for ONE human (multi_human_rl.py:109-163): grid of cell_num x cell_num cells of cell_size metres
+// centred on the human, x axis along its velocity; per cell [occupied, mean vx, mean vy] (om_ch = 3) of the OTHER humans,
+// velocities in the same frame.  get(j, f): f = 0..3 -> px, py, vx, vy of the j-th human in network order.  float64 like
+// numpy, one float32 rounding at the end (torch .float()).
+// occupancy_map_cell: the contribution sums of ONE cell c (the others in list order, the reference's summation order).
+template <typename Get>
+__device__ __forceinline__ void occupancy_map_cell(const SarlDims &d, int H, int i, int c, Get get, double &cnt, double &sx, double &sy)
+{
+    const int cn = d.cell_num;
+    const double pxi = get(i, 0), pyi = get(i, 1);
+    const double angle = atan2(get(i, 3), get(i, 2));
+    cnt = 0.0; sx = 0.0; sy = 0.0;
+    for (int j = 0; j < H; ++j) {
+        if (j == i) continue;
+        const double opx = get(j, 0) - pxi, opy = get(j, 1) - pyi;
+        const double rotation = atan2(opy, opx) - angle;
+        const double distance = sqrt(opx * opx + opy * opy);
+        const double xi = floor(cos(rotation) * distance / d.cell_size + cn / 2.0);
+        const double yi = floor(sin(rotation) * distance / d.cell_size + cn / 2.0);
+        if (xi < 0 || xi >= cn || yi < 0 || yi >= cn) continue;
+        if ((int)(cn * yi + xi) != c) continue;
+        const double vx = get(j, 2), vy = get(j, 3);
+        const double vrot = atan2(vy, vx) - angle, speed = sqrt(vx * vx + vy * vy);
+        cnt += 1.0; sx += cos(vrot) * speed; sy += sin(vrot) * speed;
+    }
+}
+
+// out[c * om_ch ...] of one cell from its sums
+__device__ __forceinline__ void occupancy_map_store(int ch, int c, double cnt, double sx, double sy, float *__restrict__ out)
+{
+    const bool on = cnt > 0.0;
+    if (ch == 1) out[c] = on ? 1.0f : 0.0f;
+    else if (ch == 2) { out[2 * c] = on ? (float)(sx / cnt) : 0.0f; out[2 * c + 1] = on ? (float)(sy / cnt) : 0.0f; }
+    else { out[3 * c] = on ? 1.0f : 0.0f; out[3 * c + 1] = on ? (float)(sx / cnt) : 0.0f; out[3 * c + 2] = on ? (float)(sy / cnt) : 0.0f; }
+}
+
+template <typename Get>
+__device__ void occupancy_map_row(const SarlDims &d, int H, int i, Get get, float *__restrict__ out)
+{
+    const int cells = d.cell_num * d.cell_num;
+    for (int c = 0; c < cells; ++c) {
+        double cnt, sx, sy;
+        occupancy_map_cell(d, H, i, c, get, cnt, sx, sy);
+        occupancy_map_store(d.om_ch, c, cnt, sx, sy, out);
+    }
+}
+
 // fp32 weights on the device, transposed to [in][out_padded] (out padded to a multiple of 4)
 struct LinearDev {
     const float *wt;

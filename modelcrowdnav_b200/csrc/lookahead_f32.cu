@@ -259,41 +259,6 @@ __device__ __forceinline__ void net_forward_smem(const SarlWeightsDev &W, const 
     else sarl_forward_smem(W, d, pl, sm, ng);
 }
 
-// build_occupancy_maps for ONE human (multi_human_rl.py:109-163): grid of cell_num x cell_num cells of cell_size metres
-// centred on the human, x axis along its velocity; per cell [occupied, mean vx, mean vy] (om_ch = 3) of the OTHER humans,
-// velocities in the same frame.  get(j, f): f = 0..3 -> px, py, vx, vy of the j-th human in network order.  float64 like
-// numpy, one float32 rounding at the end (torch .float()).
-template <typename Get>
-__device__ void occupancy_map_row(const SarlDims &d, int H, int i, Get get, float *__restrict__ out)
-{
-    const int cn = d.cell_num, cells = cn * cn, ch = d.om_ch;
-    for (int c = 0; c < cells * ch; ++c) out[c] = 0.0f;
-    const double pxi = get(i, 0), pyi = get(i, 1);
-    const double angle = atan2(get(i, 3), get(i, 2));
-    // two passes keep the accumulators in registers: per cell, sum in the reference's order (others in list order)
-    for (int c = 0; c < cells; ++c) {
-        double cnt = 0.0, sx = 0.0, sy = 0.0;
-        for (int j = 0; j < H; ++j) {
-            if (j == i) continue;
-            const double opx = get(j, 0) - pxi, opy = get(j, 1) - pyi;
-            const double rotation = atan2(opy, opx) - angle;
-            const double distance = sqrt(opx * opx + opy * opy);
-            const double xi = floor(cos(rotation) * distance / d.cell_size + cn / 2.0);
-            const double yi = floor(sin(rotation) * distance / d.cell_size + cn / 2.0);
-            if (xi < 0 || xi >= cn || yi < 0 || yi >= cn) continue;
-            if ((int)(cn * yi + xi) != c) continue;
-            const double vx = get(j, 2), vy = get(j, 3);
-            const double vrot = atan2(vy, vx) - angle, speed = sqrt(vx * vx + vy * vy);
-            cnt += 1.0; sx += cos(vrot) * speed; sy += sin(vrot) * speed;
-        }
-        if (cnt > 0.0) {
-            if (ch == 1) out[c] = 1.0f;
-            else if (ch == 2) { out[2 * c] = (float)(sx / cnt); out[2 * c + 1] = (float)(sy / cnt); }
-            else { out[3 * c] = 1.0f; out[3 * c + 1] = (float)(sx / cnt); out[3 * c + 2] = (float)(sy / cnt); }
-        }
-    }
-}
-
 // grid = (E, chunks)
 __global__ void __launch_bounds__(kThreads, 2)
 lookahead_values_kernel(EnvParams p, SarlWeightsDev W, SarlDims d, F32Plan pl, const double *__restrict__ st,

@@ -80,6 +80,8 @@ struct TcState {
     uint8_t *img_pair_b;      // two half images of mlp3 for tc_mlp3_pair_kernel
     float *rowv;              // CADRL: one value per (env, action, human) row (tc_mlp3_pair_kernel<1> -> cadrl_min_kernel)
     size_t cap_rowv;
+    float *omP;               // with_om: mlp1.0's occupancy-map product per (env, human), N_H1 floats each (tc_om_bias_kernel)
+    size_t cap_om;
     int ktime_on;             // cn_debug_kernel_ms: CUDA events around each kernel of the lookahead, on the launching stream
     cudaEvent_t kev[5];       // before features | before rows | before mlp3 | before argmax | after argmax
 };
@@ -213,6 +215,55 @@ void split_rows(uint8_t *dst, const uint8_t *src, int N, int K, int rank)
 
 }  // namespace
 
+// with_om: P[e][h][n] = sum_k W_mlp1.0[n][13 + k] * om[e][h][k]  (fp32), om = the occupancy map of human h built from the
+// NEXT human states of env e (multi_human_rl.py:47-49,109-163).  The map does not depend on the robot's action, so it enters
+// mlp1.0 as a per-row bias in the E0 epilogue of tc_rows_pair_kernel<.., true> instead of 48 more K columns on 81 x the rows.
+// A block serves kOmItems (env, human) pairs: one thread per (pair, cell) builds the maps (float64 like the reference, one
+// fp32 rounding), then one thread per output unit n applies the [om_dim x 150] weight block to all pairs (coalesced over n).
+constexpr int kOmItems = 8;
+__global__ void __launch_bounds__(N_H1)
+tc_om_bias_kernel(EnvParams p, SarlDims d, LinearDev m10, const double *__restrict__ st, const double *__restrict__ human_v,
+                  int query_env, float *__restrict__ P)
+{
+    __shared__ float om[kOmItems][8 * 8 * 3];
+    const EnvDims ed = p.d;
+    const int H = ed.H, cells = d.cell_num * d.cell_num;
+    const long long item0 = (long long)blockIdx.x * kOmItems, n_items = (long long)ed.E * H;
+    const double dt = p.time_step;
+    for (int idx = threadIdx.x; idx < kOmItems * cells; idx += blockDim.x) {
+        const int it = idx / cells, c = idx - it * cells;
+        const long long item = item0 + it;
+        double cnt = 0.0, sx = 0.0, sy = 0.0;
+        if (item < n_items) {
+            const int e = (int)(item / H), i = (int)(item - (long long)e * H);
+            // next human states: query_env -> the cached ORCA velocity (agent.py:63-74), else constant velocity (cadrl.py:107-109)
+            auto get = [&](int j, int f) -> double {
+                const double vx = query_env ? human_v[(size_t)(0 * H + j) * ed.E + e] : st[st_idx(ed, F_VX, j + 1, e)];
+                const double vy = query_env ? human_v[(size_t)(1 * H + j) * ed.E + e] : st[st_idx(ed, F_VY, j + 1, e)];
+                if (f == 0) return st[st_idx(ed, F_PX, j + 1, e)] + vx * dt;
+                if (f == 1) return st[st_idx(ed, F_PY, j + 1, e)] + vy * dt;
+                return f == 2 ? vx : vy;
+            };
+            occupancy_map_cell(d, H, i, c, get, cnt, sx, sy);
+        }
+        occupancy_map_store(d.om_ch, c, cnt, sx, sy, om[it]);
+    }
+    __syncthreads();
+    const int n = threadIdx.x;
+    float acc[kOmItems];
+#pragma unroll
+    for (int it = 0; it < kOmItems; ++it) acc[it] = 0.0f;
+    if (n < m10.out)
+        for (int k = 0; k < d.om_dim; ++k) {
+            const float w = m10.wt[(size_t)(13 + k) * m10.ld + n];
+#pragma unroll
+            for (int it = 0; it < kOmItems; ++it) acc[it] = fmaf(om[it][k], w, acc[it]);
+        }
+#pragma unroll
+    for (int it = 0; it < kOmItems; ++it)
+        if (item0 + it < n_items) P[(size_t)(item0 + it) * N_H1 + n] = acc[it];
+}
+
 int cn_tc_init(cn_policy *p)
 {
     const SarlDims &d = p->d;
@@ -224,7 +275,7 @@ int cn_tc_init(cn_policy *p)
             return CN_EUNSUPPORTED;
         }
     } else {
-        const bool ok = d.net == CN_NET_SARL && d.in == 13 && d.self_dim == 6 && d.m1[0] == 150 && d.m1[1] == 100 &&
+        const bool ok = d.net == CN_NET_SARL && d.in == 13 + d.om_dim && d.self_dim == 6 && d.m1[0] == 150 && d.m1[1] == 100 &&
                         d.m2[0] == 100 && d.m2[1] == 50 && d.at[0] == 100 && d.at[1] == 100 && d.at[2] == 1 &&
                         d.m3[0] == 150 && d.m3[1] == 100 && d.m3[2] == 100 && d.m3[3] == 1;
         if (!ok) {
@@ -238,9 +289,12 @@ int cn_tc_init(cn_policy *p)
     cudaDeviceProp prop;
     CN_CUDA_CHECK(cudaGetDeviceProperties(&prop, p->device));
     t->num_sms = prop.multiProcessorCount;
-    CN_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
-    CN_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_pair_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
-    CN_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_pair_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
+    CN_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_pair_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
+    CN_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_pair_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
+    CN_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_pair_kernel<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
+    CN_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_pair_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
+    CN_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_pair_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
+    CN_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_pair_kernel<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
     CN_CUDA_CHECK(cudaFuncSetAttribute(tc_mlp3_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M_SMEM));
     CN_CUDA_CHECK(cudaFuncSetAttribute(tc_mlp3_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M_SMEM));
     if (cudaMalloc((void **)&t->img_pair, 2 * IMG_H_BYTES) != cudaSuccess ||
@@ -262,6 +316,7 @@ void cn_tc_destroy(cn_policy *p)
     if (t->X) cudaFree(t->X);
     if (t->rew) cudaFree(t->rew);
     if (t->rowv) cudaFree(t->rowv);
+    if (t->omP) cudaFree(t->omP);
     if (t->dbg) cudaFree(t->dbg);
     if (t->kev[0]) for (int i = 0; i < 5; ++i) cudaEventDestroy(t->kev[i]);
     delete t;
@@ -406,7 +461,9 @@ int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cu
         memcpy(tw.w, t->tail_a, sizeof(tw.w));
         const int ht = (ed.H == 5 && G == ROWS / 5) ? 5 : ((ed.H == 10 && G == ROWS / 10) ? 10 : 0);
         auto feat = ht == 5 ? tc_features_kernel<5> : (ht == 10 ? tc_features_kernel<10> : tc_features_kernel<0>);
-        auto kern = ht == 5 ? tc_rows_pair_kernel<5> : (ht == 10 ? tc_rows_pair_kernel<10> : tc_rows_pair_kernel<0>);
+        const bool om = p->d.om_dim > 0;
+        auto kern = om ? (ht == 5 ? tc_rows_pair_kernel<5, true> : (ht == 10 ? tc_rows_pair_kernel<10, true> : tc_rows_pair_kernel<0, true>))
+                       : (ht == 5 ? tc_rows_pair_kernel<5, false> : (ht == 10 ? tc_rows_pair_kernel<10, false> : tc_rows_pair_kernel<0, false>));
         cn_trace_mark("features", s);
         if (t->ktime_on) CN_CUDA_CHECK(cudaEventRecord(t->kev[0], s));
         feat<<<(unsigned)xtiles, ROWS, 0, s>>>(env->p, env->state, env->time, env->human_v, p->action_dev, A, query_env, (int)NG, G,
@@ -438,7 +495,20 @@ int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cu
             if (t->ktime_on) CN_CUDA_CHECK(cudaEventRecord(t->kev[4], s));
             return rc;
         }
-        kern<<<2 * nclusters, kThreadsPair, Q_SMEM, s>>>(env->p, t->img_pair, t->X, t->J, (int)NG, G, rounds, tw, t->dbg);
+        if (om) {
+            // occupancy maps of the NEXT human states (multi_human_rl.py:47-49), folded into one row bias of mlp1.0 per human
+            const size_t items = (size_t)ed.E * ed.H;
+            if (items > t->cap_om) {
+                if (t->omP) cudaFree(t->omP);
+                t->omP = nullptr; t->cap_om = 0;
+                CN_CUDA_CHECK(cudaMalloc((void **)&t->omP, sizeof(float) * items * N_H1));
+                t->cap_om = items;
+            }
+            tc_om_bias_kernel<<<(unsigned)((items + kOmItems - 1) / kOmItems), N_H1, 0, s>>>(env->p, p->d, p->w.m1[0], env->state,
+                                                                                          env->human_v, query_env, t->omP);
+            CN_LAUNCH_CHECK();
+        }
+        kern<<<2 * nclusters, kThreadsPair, Q_SMEM, s>>>(env->p, t->img_pair, t->X, t->J, (int)NG, G, rounds, tw, t->dbg, t->omP, A);
         CN_LAUNCH_CHECK();
     }
     if (tail && tail != s) {

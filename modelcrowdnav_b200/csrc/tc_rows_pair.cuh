@@ -257,13 +257,15 @@ __device__ __forceinline__ void ctx_barrier(int ctx)
 }
 
 // HT = compile-time human count (5, 10: the benchmark configurations) or 0 = run-time H
-template <int HT>
+// OM = occupancy maps (multi_human_rl.py:109-163): the map of a human does not depend on the robot's action, so its product
+// with mlp1.0's map columns is one fp32 row bias per (env, human) (omP, from tc_om_bias_kernel), added in the E0 epilogue
+template <int HT, bool OM>
 // __maxnreg__(88), not __launch_bounds__ (the two exclude each other): see cn_small_block() in cn_common.cuh -- 88 registers
 // leave room for one <= 72-register warp of another shard's small kernels in every SM sub-partition; no measurable cost here.
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(88)
 tc_rows_pair_kernel(EnvParams p,
                     const uint8_t *__restrict__ wimg, const uint8_t *__restrict__ X, uint8_t *__restrict__ J, int NG, int G_rt,
-                    int rounds, const TailW tw, long long *__restrict__ dbg)
+                    int rounds, const TailW tw, long long *__restrict__ dbg, const float *__restrict__ omP, int A)
 {
 #define QPROBE(slot, i) do { if (dbg && blockIdx.x < 2 && probe_round) dbg[(blockIdx.x * 4 + (slot)) * 32 + (i)] = clock64(); } while (0)
     extern __shared__ __align__(128) uint8_t smem[];
@@ -427,6 +429,10 @@ tc_rows_pair_kernel(EnvParams p,
             // ---- E0: H1 = relu(acc[0,160)) -> R1 ----
             PAIR_WAIT(); QPROBE(ctx, 1);
             if (warp == 4 * ctx && lane == 0) mbar_arrive(ctx ? xfree1 : xfree0);      // stage 0 is complete (H1 lives in TMEM): the X slot may be refilled
+            if constexpr (OM) {
+                const float *bias = row_valid ? omP + ((size_t)(g / A) * H + my_h) * N_H1 + hf * 80 : nullptr;
+                compact_to_tmem_bias(tl, hf * 80, 80, hf * T_H1B, bias);
+            } else
             compact_to_tmem<true, true>(tl, hf * 80, 80, hf * T_H1B, 1.0f);        // in place: no shared-memory traffic for H1
             PAIR_SIGNAL(); QPROBE(ctx, 2);
             // ---- E1: mlp1_out = relu(acc[0,112)) -> R2 ----

@@ -483,5 +483,27 @@ __device__ __forceinline__ void compact_to_tmem(uint32_t tlane, int col_src, int
     wait_st();
 }
 
+// compact_to_tmem<RELU = true> with a per-ROW fp32 bias vector added to the accumulator first (bias = 16-byte aligned,
+// ncols floats for this thread's row, or nullptr for a padding row): the occupancy-map half of mlp1.0, which does not depend
+// on the action and is computed once per (env, human) by tc_om_bias_kernel.  16-column pieces keep the bias + accumulator
+// registers under the kernel's 88-register cap; the bias loads are issued before the TMEM load is waited for.
+__device__ __forceinline__ void compact_to_tmem_bias(uint32_t tlane, int col_src, int ncols, int col_dst, const float *__restrict__ bias)
+{
+    for (int done = 0; done + 16 <= ncols; done += 16) {
+        uint32_t v[16], w[8];
+        float4 b[4];
+        ld16(tlane + col_src + done, v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = bias ? __ldg(reinterpret_cast<const float4 *>(bias + done) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        wait_ld();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            w[2 * j] = pack_f16x2_relu(__uint_as_float(v[4 * j]) + b[j].x, __uint_as_float(v[4 * j + 1]) + b[j].y);
+            w[2 * j + 1] = pack_f16x2_relu(__uint_as_float(v[4 * j + 2]) + b[j].z, __uint_as_float(v[4 * j + 3]) + b[j].w);
+        }
+        st8(tlane + col_dst + done / 2, w);
+    }
+    wait_st();
+}
 
 }  // namespace umma

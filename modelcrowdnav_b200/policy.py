@@ -369,13 +369,12 @@ class SARL(Policy):
         return self.joint_state_dim + (self.cell_num ** 2 * self.om_channel_size if self.with_om else 0)
 
     def _om_kwargs(self):
-        """cn_sarl_cfg fields of the occupancy maps; with_om moves the lookahead to the FP32 path (the tcgen05 kernels take
-        13-feature rows only)."""
+        """cn_sarl_cfg fields of the occupancy maps.  OM-SARL keeps the tensor-core lookahead (the map enters mlp1.0 as a row
+        bias per human, tc_om_bias_kernel); OM-LSTM-RL is FP32 like LSTM-RL itself."""
         if not self.with_om:
             return {}
         if not (1 <= self.cell_num <= 8 and self.om_channel_size in (1, 2, 3)):
             raise NotImplementedError("occupancy maps: 1 <= cell_num <= 8 and om_channel_size in {1, 2, 3}")
-        self.precision = "f32"
         return dict(input_dim=self.input_dim(), with_om=1, cell_num=self.cell_num, cell_size=self.cell_size,
                     om_channel_size=self.om_channel_size)
 
