@@ -536,9 +536,6 @@ int cn_policy_create(const cn_sarl_cfg *cfg, int device, cn_policy **out)
     if (cfg->network != CN_NET_SARL && cfg->network != CN_NET_CADRL && cfg->network != CN_NET_LSTM_RL) {
         cn_set_error("unknown value network %d", cfg->network); return CN_EINVAL;
     }
-    if (cfg->network == CN_NET_LSTM_RL && cfg->precision != CN_PREC_F32) {
-        cn_set_error("the LSTM-RL lookahead runs on the FP32 path only (precision = CN_PREC_F32)"); return CN_EUNSUPPORTED;
-    }
     if (cfg->network == CN_NET_LSTM_RL) {
         if (cfg->lstm_hidden < 1 || cfg->lstm_hidden > 64) { cn_set_error("1 <= lstm_hidden <= 64 required"); return CN_EINVAL; }
         if (cfg->lstm_mlp1_dims[0] > 0)

@@ -80,6 +80,11 @@ struct TcState {
     uint8_t *img_pair_b;      // two half images of mlp3 for tc_mlp3_pair_kernel
     float *rowv;              // CADRL: one value per (env, action, human) row (tc_mlp3_pair_kernel<1> -> cadrl_min_kernel)
     size_t cap_rowv;
+    uint8_t *img_lstm;        // LSTM-RL: two half images [W_ih | W_hh] of tc_lstm_pair_kernel
+    uint8_t *XL;              // LSTM-RL: X_t operand tiles, (tile, step) major
+    size_t cap_xl;
+    int32_t *ord;             // LSTM-RL: predict()'s human order per env
+    size_t cap_ord;
     float *omP;               // with_om: mlp1.0's occupancy-map product per (env, human), N_H1 floats each (tc_om_bias_kernel)
     size_t cap_om;
     int ktime_on;             // cn_debug_kernel_ms: CUDA events around each kernel of the lookahead, on the launching stream
@@ -103,6 +108,7 @@ __device__ __forceinline__ void split_hl(float x, float &hi, float &lo)
 
 #include "tc_rows_pair.cuh"
 #include "tc_mlp3_pair.cuh"
+#include "tc_lstm_pair.cuh"
 
 // =====================================================================================================
 // self-test kernel: D[128 x N] = A[128 x K] * B[N x K]^T
@@ -274,6 +280,14 @@ int cn_tc_init(cn_policy *p)
                          "for other shapes");
             return CN_EUNSUPPORTED;
         }
+    } else if (d.net == CN_NET_LSTM_RL) {
+        // ValueNetwork1 (lstm_rl.py:9-34): LSTM(13 -> 50) on tc_lstm_pair_kernel, mlp(56 -> 150, 100, 100, 1) on the mlp3 kernel
+        if (!(d.in == 13 && d.self_dim == 6 && d.lstm_h == L_HIDDEN && d.lm1[0] == 0 && d.om_dim == 0 && d.m3[0] == 150 &&
+              d.m3[1] == 100 && d.m3[2] == 100 && d.m3[3] == 1)) {
+            cn_set_error("CN_PREC_F16_TC runs LSTM-RL's default shape only (no interaction module, no occupancy maps, "
+                         "global_state_dim 50, mlp2_dims 150,100,100,1); use CN_PREC_F32 for other shapes");
+            return CN_EUNSUPPORTED;
+        }
     } else {
         const bool ok = d.net == CN_NET_SARL && d.in == 13 + d.om_dim && d.self_dim == 6 && d.m1[0] == 150 && d.m1[1] == 100 &&
                         d.m2[0] == 100 && d.m2[1] == 50 && d.at[0] == 100 && d.at[1] == 100 && d.at[2] == 1 &&
@@ -297,7 +311,9 @@ int cn_tc_init(cn_policy *p)
     CN_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_pair_kernel<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
     CN_CUDA_CHECK(cudaFuncSetAttribute(tc_mlp3_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M_SMEM));
     CN_CUDA_CHECK(cudaFuncSetAttribute(tc_mlp3_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M_SMEM));
+    CN_CUDA_CHECK(cudaFuncSetAttribute(tc_lstm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L_SMEM));
     if (cudaMalloc((void **)&t->img_pair, 2 * IMG_H_BYTES) != cudaSuccess ||
+        cudaMalloc((void **)&t->img_lstm, 2 * IMG_HL_BYTES) != cudaSuccess ||
         cudaMalloc((void **)&t->img_pair_b, 2 * IMG_HM_BYTES) != cudaSuccess) {
         cn_set_error("cudaMalloc failed for the tensor-core weight images");
         return CN_ENOMEM;
@@ -317,6 +333,9 @@ void cn_tc_destroy(cn_policy *p)
     if (t->rew) cudaFree(t->rew);
     if (t->rowv) cudaFree(t->rowv);
     if (t->omP) cudaFree(t->omP);
+    if (t->img_lstm) cudaFree(t->img_lstm);
+    if (t->XL) cudaFree(t->XL);
+    if (t->ord) cudaFree(t->ord);
     if (t->dbg) cudaFree(t->dbg);
     if (t->kev[0]) for (int i = 0; i < 5; ++i) cudaEventDestroy(t->kev[i]);
     delete t;
@@ -354,6 +373,67 @@ int cn_tc_load_weights(cn_policy *p, const float *flat, cudaStream_t s)
             split_rows(h + HM_M2, b.data() + OFF_M2, N_M1, N_H1, rank);
             split_rows(h + HM_M3, b.data() + OFF_M3, N_M1, N_M1, rank);
         }
+        CN_CUDA_CHECK(cudaMemcpyAsync(t->img_pair_b, hb.data(), 2 * IMG_HM_BYTES, cudaMemcpyHostToDevice, s));
+        CN_CUDA_CHECK(cudaStreamSynchronize(s));
+        return CN_OK;
+    }
+    if (d.net == CN_NET_LSTM_RL) {
+        // state-dict order (lstm_rl.py:9-16): mlp.{0,2,4,6}, lstm.weight_ih_l0 [200][13], weight_hh_l0 [200][50], bias_ih_l0, bias_hh_l0
+        HostLinear M[4];
+        const int ins[4] = {d.self_dim + d.lstm_h, d.m3[0], d.m3[1], d.m3[2]};
+        const float *src = flat;
+        for (int i = 0; i < 4; ++i) {
+            M[i].w = src; src += (size_t)ins[i] * d.m3[i];
+            M[i].b = src; src += d.m3[i];
+            M[i].in = ins[i]; M[i].out = d.m3[i];
+        }
+        const int G4 = 4 * L_HIDDEN;
+        const float *w_ih = src, *w_hh = w_ih + (size_t)G4 * 13, *b_ih = w_hh + (size_t)G4 * L_HIDDEN, *b_hh = b_ih + G4;
+        // gate column n of the pair = half * 128 + gate * 32 + cl  <-  torch row gate * 50 + cell, cell = cl (half 0, cl < 24)
+        // or 24 + cl (half 1, cl < 26); the other columns keep zero weights and bias (their cells stay at c = h = 0)
+        std::vector<float> wi((size_t)N_LG * 13, 0.0f), wh((size_t)N_LG * L_HIDDEN, 0.0f), bb(N_LG, 0.0f);
+        for (int n = 0; n < N_LG; ++n) {
+            const int half = n / 128, gate = (n % 128) / 32, cl = n % 32;
+            const int ncell = half ? L_HIDDEN - L_CELLS0 : L_CELLS0;
+            if (cl >= ncell) continue;
+            const int r = gate * L_HIDDEN + (half ? L_CELLS0 + cl : cl);
+            memcpy(&wi[(size_t)n * 13], w_ih + (size_t)r * 13, sizeof(float) * 13);
+            memcpy(&wh[(size_t)n * L_HIDDEN], w_hh + (size_t)r * L_HIDDEN, sizeof(float) * L_HIDDEN);
+            bb[n] = b_ih[r] + b_hh[r];
+        }
+        const HostLinear Li = {wi.data(), bb.data(), 13, N_LG}, Lh = {wh.data(), bb.data(), L_HIDDEN, N_LG};
+        std::vector<uint8_t> li(bytes_of(N_LG, K_X), 0), lh(bytes_of(N_LG, K_LH), 0);
+        // X_t = [x_hi(13) 1 1 0 | x_lo(13) 0 0 0]: bias (b_ih + b_hh, hi / lo) at k = 13, 14
+        fill_layer(li, 0, N_LG, Li, 0, 13, 0, 13, -1);
+        fill_layer(li, 0, N_LG, Li, 0, 13, 16, -1, -1);
+        // h = [h_hi(50) pad6 | h_lo(50) pad6]
+        fill_layer(lh, 0, N_LG, Lh, 0, L_HIDDEN, 0, -1, -1);
+        fill_layer(lh, 0, N_LG, Lh, 0, L_HIDDEN, 56, -1, -1);
+        std::vector<uint8_t> hl(2 * IMG_HL_BYTES, 0);
+        for (int rank = 0; rank < 2; ++rank) {
+            uint8_t *h = hl.data() + (size_t)rank * IMG_HL_BYTES;
+            split_rows(h + HL_WIH, li.data(), N_LG, K_X, rank);
+            split_rows(h + HL_WHH, lh.data(), N_LG, K_LH, rank);
+        }
+        // mlp on J = [h_n(50) pad6 | self_hi(6) 1 1 | self_lo(6) 0 0 | pad8]; torch input = [self(6), h_n(50)] (lstm_rl.py:32-33)
+        std::vector<uint8_t> b(IMG_B_BYTES, 0);
+        fill_layer(b, OFF_M1, N_H1, M[0], 6, 50, 0, -1, -1);
+        fill_layer(b, OFF_M1, N_H1, M[0], 0, 6, 56, 62, 150);
+        fill_layer(b, OFF_M1, N_H1, M[0], 0, 6, 64, -1, -1);
+        fill_layer(b, OFF_M2, N_M1, M[1], 0, 150, 0, 150, 100);
+        fill_layer(b, OFF_M3, N_M1, M[2], 0, 100, 0, 100, -1);
+        float tail[TAIL_BYTES / 4] = {0};
+        for (int k = 0; k < 100; ++k) tail[k] = M[3].w[k];
+        tail[100] = M[3].b[0];
+        memcpy(t->tail_b, tail, sizeof(t->tail_b));
+        std::vector<uint8_t> hb(2 * IMG_HM_BYTES, 0);
+        for (int rank = 0; rank < 2; ++rank) {
+            uint8_t *h = hb.data() + (size_t)rank * IMG_HM_BYTES;
+            split_rows(h + HM_M1, b.data() + OFF_M1, N_H1, K_J, rank);
+            split_rows(h + HM_M2, b.data() + OFF_M2, N_M1, N_H1, rank);
+            split_rows(h + HM_M3, b.data() + OFF_M3, N_M1, N_M1, rank);
+        }
+        CN_CUDA_CHECK(cudaMemcpyAsync(t->img_lstm, hl.data(), 2 * IMG_HL_BYTES, cudaMemcpyHostToDevice, s));
         CN_CUDA_CHECK(cudaMemcpyAsync(t->img_pair_b, hb.data(), 2 * IMG_HM_BYTES, cudaMemcpyHostToDevice, s));
         CN_CUDA_CHECK(cudaStreamSynchronize(s));
         return CN_OK;
@@ -471,6 +551,47 @@ int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cu
         CN_LAUNCH_CHECK();
         cn_trace_mark("rows", s);
         if (t->ktime_on) CN_CUDA_CHECK(cudaEventRecord(t->kev[1], s));
+        if (p->d.net == CN_NET_LSTM_RL) {
+            // LSTM-RL: one sequence per (env, action) group over the humans in predict()'s order, then mlp(cat(self, h_n)) on the
+            // joint-state tiles (the feature kernel above left their self-state chunks and the rewards)
+            int ncl = t->num_sms / 2;
+            const int slots_l = (ntiles_b + 3) / 4;
+            if (ncl > slots_l) ncl = slots_l;
+            const int rnds = (ntiles_b + 4 * ncl - 1) / (4 * ncl);
+            const size_t ltiles = (size_t)rnds * 4 * ncl;
+            if (ltiles * ed.H > t->cap_xl) {
+                if (t->XL) cudaFree(t->XL);
+                t->XL = nullptr; t->cap_xl = 0;
+                CN_CUDA_CHECK(cudaMalloc((void **)&t->XL, ltiles * ed.H * X_TILE_BYTES));
+                t->cap_xl = ltiles * ed.H;
+            }
+            if ((size_t)ed.E * ed.H > t->cap_ord) {
+                if (t->ord) cudaFree(t->ord);
+                t->ord = nullptr; t->cap_ord = 0;
+                CN_CUDA_CHECK(cudaMalloc((void **)&t->ord, sizeof(int32_t) * (size_t)ed.E * ed.H));
+                t->cap_ord = (size_t)ed.E * ed.H;
+            }
+            lstm_order_kernel<<<(ed.E + 127) / 128, 128, 0, s>>>(env->p, env->state, query_env, t->ord);
+            CN_LAUNCH_CHECK();
+            tc_features_lstm_kernel<<<(unsigned)(ltiles * ed.H), ROWS, 0, s>>>(env->p, env->state, env->time, env->human_v, p->action_dev,
+                                                                            A, query_env, (int)NG, env->theta, t->ord, t->XL);
+            CN_LAUNCH_CHECK();
+            tc_lstm_pair_kernel<<<2 * ncl, kThreadsL, L_SMEM, s>>>(t->img_lstm, t->XL, t->J, ed.H, rnds);
+            CN_LAUNCH_CHECK();
+            TailW twb;
+            memcpy(twb.w, t->tail_b, sizeof(twb.w));
+            cn_trace_mark("mlp3", s);
+            if (t->ktime_on) CN_CUDA_CHECK(cudaEventRecord(t->kev[2], s));
+            tc_mlp3_pair_kernel<0><<<2 * ncl, kThreadsM3, M_SMEM, s>>>(env->p, env->state, t->img_pair_b, t->J, t->rew, A, (int)NG,
+                                                                      p->cfg.gamma, gamma_bar, p->cfg.v_pref, p->values, rnds, twb,
+                                                                      nullptr);
+            CN_LAUNCH_CHECK();
+            cn_trace_mark("argmax", s);
+            if (t->ktime_on) CN_CUDA_CHECK(cudaEventRecord(t->kev[3], s));
+            rc = cn_lookahead_argmax(p, env, epsilon, s);
+            if (t->ktime_on) CN_CUDA_CHECK(cudaEventRecord(t->kev[4], s));
+            return rc;
+        }
         if (p->d.net == CN_NET_CADRL) {
             // CADRL: the whole network runs on the X tiles, one value per row, then the minimum over each group's humans
             if (xtiles * ROWS > t->cap_rowv) {

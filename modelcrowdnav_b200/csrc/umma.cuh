@@ -316,6 +316,14 @@ __device__ __forceinline__ void ld16(uint32_t taddr, uint32_t (&r)[16])
         : "r"(taddr) : "memory");
 }
 
+__device__ __forceinline__ void ld8(uint32_t taddr, uint32_t (&r)[8])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(taddr) : "memory");
+}
+
 // pack two fp32 into f16x2 (lo = a, hi = b), optional ReLU fused in the conversion
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi)
 {

@@ -430,7 +430,8 @@ def _no_attention_weights(self):
 
 class CADRL(SARL):
     """CADRL behind the same GPU lookahead (cadrl.py:32-216): the value network scores every (robot, human) pair and an
-    action is worth reward + gamma_bar * MIN over the humans.  FP32 CUDA-core path (CN_NET_CADRL)."""
+    action is worth reward + gamma_bar * MIN over the humans (CN_NET_CADRL).  The default [cadrl] mlp_dims run on the tensor
+    cores (tc_mlp3_pair_kernel<1>), any other shape on the FP32 kernels."""
 
     def __init__(self):
         super().__init__()
@@ -449,6 +450,7 @@ class CADRL(SARL):
         self.with_om = False
         self._dims = dict(mlp3_dims=mlp_dims)
         self._net_kwargs = dict(network="cadrl", mlp3_dims=mlp_dims)
+        self.precision = "f16_tc" if mlp_dims == [150, 100, 100, 1] else "f32"
         logging.info("Policy: CADRL without occupancy map")
 
     # the reference's CADRL has no get_attention_weights; CrowdSim.step probes it with hasattr (crowd_sim.py:408-411)
@@ -462,7 +464,8 @@ class CADRL(SARL):
 
 class LstmRL(SARL):
     """LSTM-RL behind the same GPU lookahead (lstm_rl.py:69-105): predict() sorts the humans by decreasing distance to the
-    robot, the value network runs an LSTM over them.  FP32 CUDA-core path (CN_NET_LSTM_RL)."""
+    robot, the value network runs an LSTM over them (CN_NET_LSTM_RL).  The default network (no interaction module, no
+    occupancy maps, global_state_dim 50) runs on the tensor cores (tc_lstm_pair_kernel), the others on the FP32 kernels."""
 
     def __init__(self):
         super().__init__()
@@ -488,6 +491,9 @@ class LstmRL(SARL):
         self._dims = dict(mlp3_dims=mlp_dims)
         self._net_kwargs = dict(network="lstm_rl", mlp3_dims=mlp_dims, lstm_hidden=global_state_dim,
                                 lstm_mlp1_dims=mlp1_dims or [0, 0, 0, 0], **self._om_kwargs())
+        tc_shape = (not with_interaction_module and not self.with_om and global_state_dim == 50 and
+                    mlp_dims == [150, 100, 100, 1] and self.self_state_dim == 6)
+        self.precision = "f16_tc" if tc_shape else "f32"
         logging.info("Policy: {}LSTM-RL {} pairwise interaction module".format(
             "OM-" if self.with_om else "", "w/" if with_interaction_module else "w/o"))
 

@@ -106,7 +106,7 @@ def _setup(weights0, precision="f32", query_env=False, human_num=5, sim="circle_
     finally:
         policy_mod.LITERAL_FORK_KINEMATICS = False
     assert policy.kinematics == kinematics
-    if policy_name == "sarl":
+    if policy_name == "sarl" or precision == "f32":         # CADRL / LSTM-RL pick their own default (tensor cores when supported)
         policy.precision = precision
     sd = policy.get_model().state_dict()
     off = 0

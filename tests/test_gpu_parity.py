@@ -476,6 +476,31 @@ def test_tc_matches_f32_odd_shapes(mcn, weights0, E, H, speeds, rots):
     env.close(); p32.close(); p16.close()
 
 
+@pytest.mark.parametrize("net", ["cadrl", "lstm", "om_sarl"])
+@pytest.mark.parametrize("E,H,query_env", [(1000, 4, 0), (777, 6, 1), (130, 13, 0), (3000, 5, 0)])
+def test_tc_other_networks_match_f32_at_size(mcn, units_nets, units_om, net, E, H, query_env):
+    """The tensor-core forms of CADRL (tc_mlp3_pair_kernel<1>), LSTM-RL (tc_lstm_pair_kernel: several rounds per slot, every
+    step count) and OM-SARL (tc_om_bias_kernel + the row kernel's bias epilogue) against their FP32 kernels (themselves pinned
+    to the reference's episodes) on sizes that divide nothing, over evolving device-generated states."""
+    env = mcn.BatchedCrowdSim(E, H, auto_reset=1, seed=11, sim_rule=1)
+    if net == "om_sarl":
+        p32, p16 = _om_policy(mcn, "sarl", "f32"), _om_policy(mcn, "sarl", "f16_tc")
+        w = units_om["om_sarl_weights"]
+    else:
+        p32, p16 = _net_policy(mcn, net, precision="f32"), _net_policy(mcn, net, precision="f16_tc")
+        w = units_nets[net + "_weights"]
+    p32.load_weights(w); p16.load_weights(w)
+    env.reset_device()
+    for step in range(3):
+        env.orca()
+        p32.lookahead(env, query_env); b32, v32 = p32.read(env)
+        p16.lookahead(env, query_env); b16, v16 = p16.read(env)
+        assert value_errors(v16, v32, "f16_tc") <= 1.0
+        check_choice(b16, b32, v32, "f16_tc")
+        env.step(update=True, read=False)
+    env.close(); p32.close(); p16.close()
+
+
 def test_packed_host_step_matches_device_step(mcn, oracle_mod, weights0):
     """cn_rollout_step_host_packed (one H2D + one D2H per step, ping-ponged pinned blocks) == the device-resident step."""
     E, H = 40, 5
@@ -607,8 +632,11 @@ def test_other_value_networks_forward(mcn, units_nets, tag):
         got = pol.forward(torch.from_numpy(x).cuda()).cpu().numpy()
         want = ref.min(axis=1) if tag == "cadrl" else ref
         assert value_errors(got, want, "f32") <= 1.0
-    with pytest.raises(mcn.CrowdNavError):                             # no tensor-core LSTM-RL, and no silent fallback
-        mcn.BatchedSARL(precision="f16_tc", network="lstm_rl", mlp3_dims=[150, 100, 100, 1], lstm_hidden=50)
+    with pytest.raises(mcn.CrowdNavError):                             # tensor-core LSTM-RL is ValueNetwork1 only: no silent fallback
+        mcn.BatchedSARL(precision="f16_tc", network="lstm_rl", mlp3_dims=[150, 100, 100, 1], lstm_hidden=50,
+                        lstm_mlp1_dims=[150, 100, 100, 50])
+    with pytest.raises(mcn.CrowdNavError):
+        mcn.BatchedSARL(precision="f16_tc", network="lstm_rl", mlp3_dims=[150, 100, 100, 1], lstm_hidden=64)
     with pytest.raises(mcn.CrowdNavError):                             # tensor-core CADRL is the default [cadrl] shape only
         mcn.BatchedSARL(precision="f16_tc", network="cadrl", mlp3_dims=[128, 100, 100, 1])
     pol.close()
@@ -619,11 +647,12 @@ def test_other_value_networks_forward(mcn, units_nets, tag):
 def test_golden_trajectories_other_networks(mcn, oracle_mod, units_nets, name, precision):
     """CADRL.predict (value = reward + gamma_bar * min over humans) and LstmRL.predict (humans sorted by decreasing
     distance unless query_env) on the GPU: teacher-forced replay of the reference's own episodes, same bars as SARL.
-    CADRL also runs on the tensor cores (its mlp is the three UMMA stages of the mlp3 kernel); LSTM-RL is FP32 only."""
-    if precision == "f16_tc" and not name.startswith("cadrl"):
-        pytest.skip("LSTM-RL has no tensor-core path")
+    CADRL also runs on the tensor cores (its mlp is the three UMMA stages of the mlp3 kernel), and so does LSTM-RL's
+    ValueNetwork1 (tc_lstm_pair_kernel: one UMMA stage per human, then the mlp3 kernel); ValueNetwork2 is FP32 only."""
     tr = load_traj(name)
     tag = net_tag(tr)
+    if precision == "f16_tc" and tag == "lstm2":
+        pytest.skip("LSTM-RL with the interaction module has no tensor-core path (refused by cn_policy_create)")
     H = tr["H"]
     states, times, recs = [], [], []
     for case, rec in tr["cases"].items():
