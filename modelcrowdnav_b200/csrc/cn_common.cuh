@@ -98,27 +98,23 @@ struct SarlDims {
 // centred on the human, x axis along its velocity; per cell [occupied, mean vx, mean vy] (om_ch = 3) of the OTHER humans,
 // velocities in the same frame.  get(j, f): f = 0..3 -> px, py, vx, vy of the j-th human in network order.  float64 like
 // numpy, one float32 rounding at the end (torch .float()).
-// occupancy_map_cell: the contribution sums of ONE cell c (the others in list order, the reference's summation order).
+// occupancy_map_pair: the cell of human j in human i's grid (-1 = outside) and j's velocity in i's frame.
 template <typename Get>
-__device__ __forceinline__ void occupancy_map_cell(const SarlDims &d, int H, int i, int c, Get get, double &cnt, double &sx, double &sy)
+__device__ __forceinline__ int occupancy_map_pair(const SarlDims &d, int i, int j, Get get, double &vxr, double &vyr)
 {
     const int cn = d.cell_num;
     const double pxi = get(i, 0), pyi = get(i, 1);
     const double angle = atan2(get(i, 3), get(i, 2));
-    cnt = 0.0; sx = 0.0; sy = 0.0;
-    for (int j = 0; j < H; ++j) {
-        if (j == i) continue;
-        const double opx = get(j, 0) - pxi, opy = get(j, 1) - pyi;
-        const double rotation = atan2(opy, opx) - angle;
-        const double distance = sqrt(opx * opx + opy * opy);
-        const double xi = floor(cos(rotation) * distance / d.cell_size + cn / 2.0);
-        const double yi = floor(sin(rotation) * distance / d.cell_size + cn / 2.0);
-        if (xi < 0 || xi >= cn || yi < 0 || yi >= cn) continue;
-        if ((int)(cn * yi + xi) != c) continue;
-        const double vx = get(j, 2), vy = get(j, 3);
-        const double vrot = atan2(vy, vx) - angle, speed = sqrt(vx * vx + vy * vy);
-        cnt += 1.0; sx += cos(vrot) * speed; sy += sin(vrot) * speed;
-    }
+    const double opx = get(j, 0) - pxi, opy = get(j, 1) - pyi;
+    const double rotation = atan2(opy, opx) - angle;
+    const double distance = sqrt(opx * opx + opy * opy);
+    const double xi = floor(cos(rotation) * distance / d.cell_size + cn / 2.0);
+    const double yi = floor(sin(rotation) * distance / d.cell_size + cn / 2.0);
+    if (xi < 0 || xi >= cn || yi < 0 || yi >= cn) return -1;
+    const double vx = get(j, 2), vy = get(j, 3);
+    const double vrot = atan2(vy, vx) - angle, speed = sqrt(vx * vx + vy * vy);
+    vxr = cos(vrot) * speed; vyr = sin(vrot) * speed;
+    return (int)(cn * yi + xi);
 }
 
 // out[c * om_ch ...] of one cell from its sums
@@ -133,10 +129,18 @@ __device__ __forceinline__ void occupancy_map_store(int ch, int c, double cnt, d
 template <typename Get>
 __device__ void occupancy_map_row(const SarlDims &d, int H, int i, Get get, float *__restrict__ out)
 {
+    // every other human's cell and rotated velocity once, then the cells in order (same sums as occupancy_map_cell per cell)
+    int cell[CN_MAX_HUMANS];
+    double vxr[CN_MAX_HUMANS], vyr[CN_MAX_HUMANS];
+    for (int j = 0; j < H; ++j) {
+        cell[j] = -1; vxr[j] = 0.0; vyr[j] = 0.0;
+        if (j != i) cell[j] = occupancy_map_pair(d, i, j, get, vxr[j], vyr[j]);
+    }
     const int cells = d.cell_num * d.cell_num;
     for (int c = 0; c < cells; ++c) {
-        double cnt, sx, sy;
-        occupancy_map_cell(d, H, i, c, get, cnt, sx, sy);
+        double cnt = 0.0, sx = 0.0, sy = 0.0;
+        for (int j = 0; j < H; ++j)
+            if (cell[j] == c) { cnt += 1.0; sx += vxr[j]; sy += vyr[j]; }
         occupancy_map_store(d.om_ch, c, cnt, sx, sy, out);
     }
 }

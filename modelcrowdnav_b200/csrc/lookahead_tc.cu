@@ -224,34 +224,49 @@ void split_rows(uint8_t *dst, const uint8_t *src, int N, int K, int rank)
 // with_om: P[e][h][n] = sum_k W_mlp1.0[n][13 + k] * om[e][h][k]  (fp32), om = the occupancy map of human h built from the
 // NEXT human states of env e (multi_human_rl.py:47-49,109-163).  The map does not depend on the robot's action, so it enters
 // mlp1.0 as a per-row bias in the E0 epilogue of tc_rows_pair_kernel<.., true> instead of 48 more K columns on 81 x the rows.
-// A block serves kOmItems (env, human) pairs: one thread per (pair, cell) builds the maps (float64 like the reference, one
-// fp32 rounding), then one thread per output unit n applies the [om_dim x 150] weight block to all pairs (coalesced over n).
+// A block serves kOmItems (env, human) pairs: one thread per (pair, other human) finds that human's cell and rotated velocity
+// (float64 like the reference), one thread per (pair, cell) sums them in list order (one fp32 rounding), then one thread per
+// output unit n applies the [om_dim x 150] weight block to all pairs (coalesced over n).
 constexpr int kOmItems = 8;
 __global__ void __launch_bounds__(N_H1)
 tc_om_bias_kernel(EnvParams p, SarlDims d, LinearDev m10, const double *__restrict__ st, const double *__restrict__ human_v,
                   int query_env, float *__restrict__ P)
 {
     __shared__ float om[kOmItems][8 * 8 * 3];
+    __shared__ int cell_of[kOmItems][CN_MAX_HUMANS];
+    __shared__ double vrot_of[kOmItems][CN_MAX_HUMANS][2];
     const EnvDims ed = p.d;
     const int H = ed.H, cells = d.cell_num * d.cell_num;
     const long long item0 = (long long)blockIdx.x * kOmItems, n_items = (long long)ed.E * H;
     const double dt = p.time_step;
-    for (int idx = threadIdx.x; idx < kOmItems * cells; idx += blockDim.x) {
-        const int it = idx / cells, c = idx - it * cells;
+    // (pair, other human j): j's cell in the human's grid and its velocity in the human's frame
+    for (int idx = threadIdx.x; idx < kOmItems * H; idx += blockDim.x) {
+        const int it = idx / H, j = idx - it * H;
         const long long item = item0 + it;
-        double cnt = 0.0, sx = 0.0, sy = 0.0;
+        int cell = -1;
+        double vxr = 0.0, vyr = 0.0;
         if (item < n_items) {
             const int e = (int)(item / H), i = (int)(item - (long long)e * H);
             // next human states: query_env -> the cached ORCA velocity (agent.py:63-74), else constant velocity (cadrl.py:107-109)
-            auto get = [&](int j, int f) -> double {
-                const double vx = query_env ? human_v[(size_t)(0 * H + j) * ed.E + e] : st[st_idx(ed, F_VX, j + 1, e)];
-                const double vy = query_env ? human_v[(size_t)(1 * H + j) * ed.E + e] : st[st_idx(ed, F_VY, j + 1, e)];
-                if (f == 0) return st[st_idx(ed, F_PX, j + 1, e)] + vx * dt;
-                if (f == 1) return st[st_idx(ed, F_PY, j + 1, e)] + vy * dt;
+            auto get = [&](int k, int f) -> double {
+                const double vx = query_env ? human_v[(size_t)(0 * H + k) * ed.E + e] : st[st_idx(ed, F_VX, k + 1, e)];
+                const double vy = query_env ? human_v[(size_t)(1 * H + k) * ed.E + e] : st[st_idx(ed, F_VY, k + 1, e)];
+                if (f == 0) return st[st_idx(ed, F_PX, k + 1, e)] + vx * dt;
+                if (f == 1) return st[st_idx(ed, F_PY, k + 1, e)] + vy * dt;
                 return f == 2 ? vx : vy;
             };
-            occupancy_map_cell(d, H, i, c, get, cnt, sx, sy);
+            if (j != i) cell = occupancy_map_pair(d, i, j, get, vxr, vyr);
         }
+        cell_of[it][j] = cell;
+        vrot_of[it][j][0] = vxr; vrot_of[it][j][1] = vyr;
+    }
+    __syncthreads();
+    // (pair, cell): sums over the others in list order (the reference's summation order)
+    for (int idx = threadIdx.x; idx < kOmItems * cells; idx += blockDim.x) {
+        const int it = idx / cells, c = idx - it * cells;
+        double cnt = 0.0, sx = 0.0, sy = 0.0;
+        for (int j = 0; j < H; ++j)
+            if (cell_of[it][j] == c) { cnt += 1.0; sx += vrot_of[it][j][0]; sy += vrot_of[it][j][1]; }
         occupancy_map_store(d.om_ch, c, cnt, sx, sy, om[it]);
     }
     __syncthreads();

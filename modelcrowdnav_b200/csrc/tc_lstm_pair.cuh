@@ -33,7 +33,17 @@ constexpr uint32_t L_MISC = L_CTX0 + 2 * L_CTX_BYTES;                   // 10 mb
 constexpr uint32_t L_SMEM = L_MISC + 96 + 16;
 static_assert(L_SMEM <= 232448, "tc_lstm_pair_kernel exceeds 227 KB of shared memory");
 
-__device__ __forceinline__ float sigmoid_f32(float x) { return 1.0f / (1.0f + expf(-x)); }
+// sigmoid and tanh from one MUFU.EX2 + one MUFU.RCP each (absolute error ~2e-7; tanh(x) = 2 sigmoid(2x) - 1 loses only RELATIVE
+// accuracy near 0, where h = o tanh(c) is small anyway): the cell update is 5 transcendentals per cell and step, and with the libm
+// forms the epilogue, not the UMMA chain, bounds the kernel.
+__device__ __forceinline__ float sigmoid_f32(float x)
+{
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));      // exp(-x); +inf for x << 0 -> 1 / inf = 0
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));                      // (no IEEE slow path: __frcp_rn calls one)
+    return r;
+}
+__device__ __forceinline__ float tanh_f32(float x) { return fmaf(2.0f, sigmoid_f32(2.0f * x), -1.0f); }
 
 // X holds, for tile T and step t, the 8 KB operand tile at (T * H + t); J receives chunks 0..6 of tile T
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsL, 1)
@@ -151,10 +161,10 @@ tc_lstm_pair_kernel(const uint8_t *__restrict__ wimg, const uint8_t *__restrict_
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float ig = sigmoid_f32(__uint_as_float(gi[j])), fg = sigmoid_f32(__uint_as_float(gf[j]));
-                        const float g = tanhf(__uint_as_float(gg[j])), og = sigmoid_f32(__uint_as_float(go[j]));
+                        const float g = tanh_f32(__uint_as_float(gg[j])), og = sigmoid_f32(__uint_as_float(go[j]));
                         const float c = fg * cst[k8 * 8 + j] + ig * g;
                         cst[k8 * 8 + j] = c;
-                        hv[j] = og * tanhf(c);
+                        hv[j] = og * tanh_f32(c);
                     }
                     float hi[8], lo[8];
 #pragma unroll
