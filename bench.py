@@ -243,6 +243,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # host-resident legs: keep every rank's pinned buffers and launch thread on the CPUs next to its GPU (multi-GPU runs only)
+    numa_cpus = mcn.pin_to_gpu_numa(local) if world > 1 else 0
     peaks = load_peaks()
 
     def barrier():
@@ -488,7 +490,8 @@ def main():
                     "how": "PipelinedHostRollout: pinned host state in and out every step, the copies, host round trip and "
                            "small kernels of one env shard overlap the row kernels of the others; one CUDA-graph launch "
                            "per shard and step",
-                    "blocking_single_handle_value": world * E * ne / e2e_blocking_s},
+                    "blocking_single_handle_value": world * E * ne / e2e_blocking_s,
+                    "cpu_affinity": ("GPU-local CPUs (%d, NVML)" % numa_cpus) if numa_cpus else "unchanged"},
             "gpu_launches": main_res["launches"],
             "roofline": main_res["roofline"],
             "parity_sample": parity,

@@ -7,7 +7,7 @@ one-step lookahead, batched over thousands of environments per GPU behind a C AB
 from . import _capi  # noqa: F401
 from ._capi import CrowdNavError  # noqa: F401
 from .batch import (BatchedCrowdSim, BatchedSARL, HostStepBuffers, PackedHostStepBuffers, PipelinedHostRollout,  # noqa: F401
-                    rollout_step, rollout_step_host, rollout_step_host_packed)
+                    pin_to_gpu_numa, rollout_step, rollout_step_host, rollout_step_host_packed)
 
 from .envs import (ActionRot, ActionXY, Collision, CrowdSim, Danger, FullState, Human, JointState, ModelCrowdSim,  # noqa: F401
                    Nothing, ObservableState, ReachGoal, Robot, Timeout)
@@ -18,5 +18,5 @@ __all__ = ["CrowdSim", "ModelCrowdSim", "Robot", "Human", "SARL", "CADRL", "Lstm
            "ActionXY", "ActionRot", "FullState", "ObservableState", "JointState",
            "Timeout", "ReachGoal", "Danger", "Collision", "Nothing",
            "BatchedCrowdSim", "BatchedSARL", "HostStepBuffers", "PackedHostStepBuffers", "rollout_step", "rollout_step_host",
-           "rollout_step_host_packed", "PipelinedHostRollout",
+           "rollout_step_host_packed", "PipelinedHostRollout", "pin_to_gpu_numa",
            "CrowdNavError"]

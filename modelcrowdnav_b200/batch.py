@@ -474,3 +474,31 @@ class PipelinedHostRollout(object):
         self._graphs.clear()
         for e, p in zip(self.envs, self.pols):
             e.close(); p.close()
+
+
+def pin_to_gpu_numa(device_index):
+    """Restrict this process to the CPUs NVML reports as local to the GPU (its NUMA node).  A host-resident driver moves
+    6.5 MB per step and GPU through pinned memory; with every rank of a node on the same CPU set the far-socket ranks lose ~2 %
+    (8-GPU end-to-end line of round 1).  Returns the number of CPUs kept, or 0 when nothing was changed (no NVML, no overlap
+    with the allowed set, single-socket box)."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(device_index).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        local = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        keep = local & allowed
+        if not keep or keep == allowed:
+            return 0
+        os.sched_setaffinity(0, keep)
+        return len(keep)
+    except Exception:
+        return 0
