@@ -28,6 +28,10 @@
 // Reference: crowd_nav/policy/sarl.py:28-65 (value network), cadrl.py:104-129,217-252 (propagate, rotate),
 // multi_human_rl.py:65-88 / crowd_sim.py:344-403 (lookahead reward).
 
+// Timing ablations (developer builds only, never in the shipped library; see scripts/row_kernel_ablation.sh and
+// profiles/r02v_row_kernel_ablation*.txt): -DCN_ABLATE_EPI drops every epilogue's arithmetic and data movement (waits, barriers
+// and hand-over signals stay), -DCN_ABLATE_MMA drops the UMMAs (commits stay).  The values are garbage; the kernel time is the
+// point: hand-overs alone 0.164 ms, + UMMAs 0.456 ms, + epilogues instead 0.346 ms, everything 0.531 ms.
 constexpr int kThreadsPair = 608;        // 16 epilogue warps (2 contexts x 2 column halves x 4 lane quarters) + issuer warp + 2 loader warps
 constexpr int N_S2 = 2 * N_M1;             // stage 2: [mlp2.0 (rank-0 half) | attention.0 on mlp1_out (rank-1 half)]
 constexpr int PAIR_CTX_COLS = 256;         // TMEM columns per tile context
@@ -339,7 +343,13 @@ tc_rows_pair_kernel(EnvParams p,
                     const uint32_t tm = tmem + (uint32_t)c * PAIR_CTX_COLS;
                     const uint32_t sR1 = smem_u32(smem + Q_CTX0 + (uint32_t)c * Q_CTX_BYTES), sR2 = sR1 + Q_R1_BYTES;
                     const uint32_t done = c ? done1 : done0;
+#ifdef CN_ABLATE_MMA
+                    if (s != 2) commit_2(done, 3);
+                    if (1) {
+                    } else if (s == 0) {
+#else
                     if (s == 0) {
+#endif
                         mma_layer_2(tm, sR1 + Q_X_OFF, ROWS, sW1, K_X, N_H1, false);
                         commit_2(done, 3);
                     } else if (s == 1) {
@@ -445,19 +455,27 @@ tc_rows_pair_kernel(EnvParams p,
                 const float *bias = row_valid ? omP + ((size_t)(g / A) * H + my_h) * N_H1 + hf * 80 : nullptr;
                 compact_to_tmem_bias(tl, hf * 80, 80, hf * T_H1B, bias);
             } else
+#ifndef CN_ABLATE_EPI
             compact_to_tmem<true, true>(tl, hf * 80, 80, hf * T_H1B, 1.0f);        // in place: no shared-memory traffic for H1
+#endif
             PAIR_SIGNAL(); QPROBE(ctx, 2);
             if constexpr (OM) { if (has_next) om_prefetch(tile + tile_stride); }
             // ---- E1: mlp1_out = relu(acc[0,112)) -> R2 ----
             PAIR_WAIT(); QPROBE(ctx, 3);
+#ifndef CN_ABLATE_EPI
             if (hf == 0) epilogue_to_smem<true>(tl, T_D1, 64, R2, row, 0);
             else epilogue_to_smem<true>(tl, T_D1 + 64, 48, R2, row, 8);
+#endif
             PAIR_SIGNAL(); QPROBE(ctx, 4);                                         // stage 2 may start
             QPROBE(ctx, 12);
             // ---- group mean of mlp1_out over the humans of a group (sarl.py:42), replicated on the group's rows -> R1 ----
             ctx_barrier(ctx);
             QPROBE(ctx, 13);
+#ifdef CN_ABLATE_EPI
+            if (0) {
+#else
             if (!HT && mean_split >= 2) {
+#endif
                 const int P = mean_split, nitems = G * (N_M1 / 8);
                 const int it = t256 / P, seg = t256 & (P - 1);
                 const bool on = it < nitems;
@@ -475,6 +493,9 @@ tc_rows_pair_kernel(EnvParams p,
             } else
 #pragma unroll
             for (int i = 0; i < kMeanIters; ++i) {
+#ifdef CN_ABLATE_EPI
+                break;
+#endif
                 if (mean_off[i] < 0) continue;
                 const uint8_t *src = R2 + mean_off[i];
                 uint4 v[HT ? HT : 1];
@@ -522,11 +543,19 @@ tc_rows_pair_kernel(EnvParams p,
             QPROBE(ctx, 6);
             // ---- E3: H3 = relu(acc[0,112)) -> R1 (hf 0) ; Ha1 = relu(acc[112,224)) -> R2 (hf 1) ----
             PAIR_WAIT(); QPROBE(ctx, 7);
+#ifndef CN_ABLATE_EPI
             if (hf == 0) compact_to_tmem<true, true>(tl, 0, N_M1, 0, 1.0f);         // Ha1: fp16 pairs in place, [0,56)
             else epilogue_to_smem<true>(tl, N_M1, N_M1, R1, row, 0);
+#endif
             PAIR_SIGNAL(); QPROBE(ctx, 8);
             // ---- E4: attention.4 dot (split over the column halves), masked softmax (sarl.py:48-53), w * F ----
             PAIR_WAIT(); QPROBE(ctx, 9);
+#ifdef CN_ABLATE_EPI
+            if (has_next) PAIR_SIGNAL();
+            ctx_barrier(ctx);
+            QPROBE(ctx, 11);
+            continue;
+#endif
             {
                 float part = 0.0f;
                 if (hf == 0) {

@@ -35,10 +35,13 @@ def child(lib, E, H, iters, sim):
         for k, v in pol.kernel_ms().items():
             acc.setdefault(k, []).append(v)
         env.step(update=True, read=False)
-    best, values = pol.read(env)
     out = {k: float(np.median(v)) for k, v in acc.items()}
     out["lookahead"] = sum(out.values())
-    out["checksum"] = float(np.nansum(values))
+    try:                                     # ablation builds produce no finite value: the timings are what they are for
+        best, values = pol.read(env)
+        out["checksum"] = float(np.nansum(values))
+    except Exception as ex:
+        out["checksum"] = "unreadable: %s" % type(ex).__name__
     print(json.dumps(out))
 
 

@@ -12,6 +12,8 @@ sys.path.insert(0, ROOT)
 import modelcrowdnav_b200 as mcn  # noqa: E402
 
 H = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+if len(sys.argv) > 2:                      # an A/B or ablation build instead of the in-tree library
+    mcn._capi.LIB_PATH = os.path.abspath(sys.argv[2])
 w = np.load(os.path.join(ROOT, "tests", "golden", "sarl_weights_seed0.npy"))
 env = mcn.BatchedCrowdSim(8192, H, auto_reset=1)
 pol = mcn.BatchedSARL(precision="f16_tc"); pol.load_weights(w)
