@@ -222,7 +222,8 @@ def main():
     ap.add_argument("--preroll", type=int, default=64, help="untimed steps before the warm-up (episodes out of lock step)")
     ap.add_argument("--train-episodes", type=int, default=512, help="--workload train: episodes rolled out per iteration and rank")
     ap.add_argument("--train-batches", type=int, default=100, help="--workload train: SGD batches per iteration")
-    ap.add_argument("--trainer", default="graph", choices=["eager", "graph", "fused"])
+    ap.add_argument("--trainer", default="fused", choices=["eager", "graph", "fused"],
+                    help="--workload train: fused = csrc/trainer.cu (SARL, parity-tested against the reference Trainer), graph = CUDA-graph replay of torch autograd")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
     if a.impl == "reference":
