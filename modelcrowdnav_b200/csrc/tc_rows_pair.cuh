@@ -76,13 +76,16 @@ __device__ __forceinline__ void pp_load_inputs(RowInPP &in, const EnvDims &ed, c
     const int g = tile * G + gl;          // the host keeps (total tiles + 1) * G below 2^31
     in.valid = (gl < G && g < NG) ? 1 : 0;
     if (!in.valid) return;
-    const int e = g / A, a = g - e * A;
-    in.rpx = st[st_idx(ed, F_PX, 0, e)]; in.rpy = st[st_idx(ed, F_PY, 0, e)];
-    in.rgx = st[st_idx(ed, F_GX, 0, e)]; in.rgy = st[st_idx(ed, F_GY, 0, e)];
-    in.rr = st[st_idx(ed, F_R, 0, e)];   in.rvp = st[st_idx(ed, F_VPREF, 0, e)];
-    in.hpx = st[st_idx(ed, F_PX, h + 1, e)]; in.hpy = st[st_idx(ed, F_PY, h + 1, e)];
-    in.hr = st[st_idx(ed, F_R, h + 1, e)];
-    in.cvx = st[st_idx(ed, F_VX, h + 1, e)]; in.cvy = st[st_idx(ed, F_VY, h + 1, e)];
+    const int e = A == 81 ? g / 81 : g / A, a = g - e * A;        // 81 = the holonomic action space: a multiply instead of a division
+    // st[(field * A1 + agent) * E + env]: one base per agent, the field strides are uniform
+    const size_t fs = (size_t)ed.A1 * ed.E;
+    const double *__restrict__ pr = st + e, *__restrict__ ph = pr + (size_t)(h + 1) * ed.E;
+    in.rpx = pr[F_PX * fs]; in.rpy = pr[F_PY * fs];
+    in.rgx = pr[F_GX * fs]; in.rgy = pr[F_GY * fs];
+    in.rr = pr[F_R * fs];   in.rvp = pr[F_VPREF * fs];
+    in.hpx = ph[F_PX * fs]; in.hpy = ph[F_PY * fs];
+    in.hr = ph[F_R * fs];
+    in.cvx = ph[F_VX * fs]; in.cvy = ph[F_VY * fs];
     if (query_env) {                                                                    // agent.py:63-74
         in.hvx = human_v[(size_t)(0 * H + h) * ed.E + e]; in.hvy = human_v[(size_t)(1 * H + h) * ed.E + e];
         in.t = time[e];
@@ -110,7 +113,12 @@ __device__ __forceinline__ double pp_clearance(const RowInPP &in, double dt, int
     // multi_human_rl.py:69-70
     const double npx = in.rpx + in.ax * dt, npy = in.rpy + in.ay * dt;
     const double nhx = in.hpx + in.cvx * dt, nhy = in.hpy + in.cvy * dt;
-    return norm2d(npx - nhx, npy - nhy) - in.rr - in.hr;
+    const double dx = npx - nhx, dy = npy - nhy;
+    // The reward only asks "clearance < 0" and "min clearance < 0.2" (multi_human_rl.py:71-86): a row whose fp32 distance is
+    // clear of that by a wide margin needs no float64 square root -- any value >= 0.2 gives the same reward.
+    const float fx = (float)dx, fy = (float)dy, fr = (float)in.rr + (float)in.hr + 0.25f;
+    if (fx * fx + fy * fy > fr * fr) return 1.0e30;
+    return norm2d(dx, dy) - in.rr - in.hr;
 }
 
 // CADRL.rotate with the rotation taken from the normalised goal direction instead of atan2 -> sincos
@@ -233,7 +241,12 @@ tc_features_kernel(EnvParams p, const double *__restrict__ st, const double *__r
         *reinterpret_cast<uint4 *>(jt + chunk_off(ROWS, rb, 9)) = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
-    if (lead) rew[g] = pair_reward(p, in, D + r, H, query_env);
+    // the G rewards of the tile by its first G threads (whole warps instead of every H-th lane of every warp)
+    if (r < G && tile * G + r < NG) {
+        RowInPP in0;
+        pp_load_inputs(in0, ed, st, time, human_v, actions, A, query_env, NG, G, tile, r, 0, p.kinematics, theta);
+        rew[tile * G + r] = pair_reward(p, in0, D + r * H, H, query_env);
+    }
 }
 
 // acc[8] += sum over n 16-byte chunks of 8 fp16 at base + i * stride.  Loads go out four at a time before anything is added:
