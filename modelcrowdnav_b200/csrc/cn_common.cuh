@@ -197,13 +197,8 @@ extern std::atomic<int64_t> g_cn_launches;
 // <= 72 registers in every sub-partition.  So one warp per sub-partition of step (70), reset (52), ORCA (46) or the feature
 // kernel (56, one 128-thread block per SM) runs UNDER the persistent kernel; at 96 registers only <= 32-register warps did
 // (measured with cn_debug_trace: step + reset of a shard took 258 us, i.e. waited for the other shard's row kernel to exit,
-// against 25 us now).  A preferred-carveout hint was tried first and changes nothing.  CN_SMALL_BLOCK overrides (A/B runs).
-static inline int cn_small_block()
-{
-    static const int b = [] { const char *e = getenv("CN_SMALL_BLOCK"); const int v = e ? atoi(e) : 32;
-                              return (v == 32 || v == 64 || v == 128) ? v : 32; }();
-    return b;
-}
+// against 25 us now).  A preferred-carveout hint was tried first and changes nothing.
+static inline int cn_small_block() { return 32; }
 
 // developer timeline (cn_debug_trace): when enabled, records a CUDA event named `name` on stream `s`; a no-op otherwise
 void cn_trace_mark(const char *name, cudaStream_t s);
