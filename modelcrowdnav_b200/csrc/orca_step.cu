@@ -143,7 +143,35 @@ __device__ void orca_solve(const EnvParams &p, const double *__restrict__ st, in
     const int maxN = p.max_neighbors;
     float rangeSq = sqrf(p.neighbor_dist);
     const int n_cand = n_first + (extra_agent >= 0 ? 1 : 0);
-    if (maxN > 0) {
+    // positions: one base pointer, the agent stride is the env count (st[(field * A1 + agent) * E + env])
+    const double *__restrict__ pxs = st + st_idx(d, F_PX, 0, e), *__restrict__ pys = st + st_idx(d, F_PY, 0, e);
+    if (maxN == 10) {
+        // The reference's max_neighbors (orca.py:55-67): the list lives in REGISTERS, kept sorted by a branch-free insertion.
+        // Same result as the loop below: empty slots hold +inf, so "list not full or closer than its last entry" is one strict
+        // comparison with slot 9 (rangeSq only ever shrinks from neighbor_dist^2 to that entry), and the new entry lands
+        // behind every entry <= it (the strict `<` of insertAgentNeighbor: ties keep visiting order), pushing the rest down.
+        float d0 = INFINITY, d1 = INFINITY, d2 = INFINITY, d3 = INFINITY, d4 = INFINITY, d5 = INFINITY, d6 = INFINITY,
+              d7 = INFINITY, d8 = INFINITY, d9 = INFINITY;
+        int i0 = 0, i1 = 0, i2 = 0, i3 = 0, i4 = 0, i5 = 0, i6 = 0, i7 = 0, i8 = 0, i9 = 0;
+        const float nd2 = rangeSq;
+        for (int c = 0; c < n_cand; ++c) {
+            int o;
+            if (c < n_first) { o = cand_first[0] + c; if (o >= self && cand_first[1]) ++o; }
+            else o = extra_agent;
+            const size_t oo = (size_t)o * d.E;
+            const float distSq = vabssq(vsub(pos, V((float)pxs[oo], (float)pys[oo])));
+            if (distSq < nd2 && distSq < d9) {
+                if (nn < 10) ++nn;
+#define CN_INS(hi, lo) { const bool sh = distSq < d##lo; const bool here = distSq < d##hi; \
+                         i##hi = sh ? i##lo : (here ? o : i##hi); d##hi = sh ? d##lo : (here ? distSq : d##hi); }
+                CN_INS(9, 8) CN_INS(8, 7) CN_INS(7, 6) CN_INS(6, 5) CN_INS(5, 4) CN_INS(4, 3) CN_INS(3, 2) CN_INS(2, 1) CN_INS(1, 0)
+#undef CN_INS
+                if (distSq < d0) { d0 = distSq; i0 = o; }
+            }
+        }
+        nb_id[0] = i0; nb_id[1] = i1; nb_id[2] = i2; nb_id[3] = i3; nb_id[4] = i4;
+        nb_id[5] = i5; nb_id[6] = i6; nb_id[7] = i7; nb_id[8] = i8; nb_id[9] = i9;
+    } else if (maxN > 0) {
         for (int c = 0; c < n_cand; ++c) {
             int o;
             if (c < n_first) { o = cand_first[0] + c; if (o >= self && cand_first[1]) ++o; }
