@@ -465,6 +465,14 @@ __device__ void reset_env_warp(const EnvParams &p, int e, int lane, double *__re
         st[st_idx(d, F_R, 0, e)] = p.robot_radius; st[st_idx(d, F_VPREF, 0, e)] = p.robot_v_pref;
     }
     __syncwarp();
+    // The agents placed so far, cached in REGISTERS of the lane that checks them (agent a = lane + 32 k): a retry of the
+    // rejection sampling then costs no memory round trip (they were re-read from global memory on every try: ~200 us at
+    // 50 humans).  Same doubles, same arithmetic, same decisions.
+    constexpr int kSlots = (CN_MAX_HUMANS + 32) / 32;
+    double cpx[kSlots], cpy[kSlots], cgx[kSlots], cgy[kSlots], cr[kSlots];
+#pragma unroll
+    for (int k = 0; k < kSlots; ++k) { cpx[k] = cpy[k] = cgx[k] = cgy[k] = cr[k] = 0.0; }
+    if (lane == 0) { cpx[0] = 0.0; cpy[0] = -p.circle_radius; cgx[0] = 0.0; cgy[0] = p.circle_radius; cr[0] = p.robot_radius; }
     const int MAX_TRIES = 4096;
     for (int i = 1; i <= d.H; ++i) {
         double px = 0, py = 0, gx = 0, gy = 0;
@@ -481,10 +489,11 @@ __device__ void reset_env_warp(const EnvParams &p, int e, int lane, double *__re
                 px = p.circle_radius * cos(angle) + px_noise;
                 py = p.circle_radius * sin(angle) + py_noise;
                 bool collide = false;
-                for (int a = lane; a < i; a += 32) {
-                    const double min_dist = h_radius + st[st_idx(d, F_R, a, e)] + p.discomfort_dist;
-                    collide = collide || norm2d(px - st[st_idx(d, F_PX, a, e)], py - st[st_idx(d, F_PY, a, e)]) < min_dist ||
-                              norm2d(px - st[st_idx(d, F_GX, a, e)], py - st[st_idx(d, F_GY, a, e)]) < min_dist;
+#pragma unroll
+                for (int k = 0; k < kSlots; ++k) {
+                    if (lane + 32 * k >= i) continue;
+                    const double min_dist = h_radius + cr[k] + p.discomfort_dist;
+                    collide = collide || norm2d(px - cpx[k], py - cpy[k]) < min_dist || norm2d(px - cgx[k], py - cgy[k]) < min_dist;
                 }
                 if (!__any_sync(0xffffffffu, collide)) break;
             }
@@ -495,18 +504,20 @@ __device__ void reset_env_warp(const EnvParams &p, int e, int lane, double *__re
                 px = rng.next() * p.square_width * 0.5 * sign;
                 py = (rng.next() - 0.5) * p.square_width;
                 bool collide = false;
-                for (int a = lane; a < i; a += 32)
-                    collide = collide || norm2d(px - st[st_idx(d, F_PX, a, e)], py - st[st_idx(d, F_PY, a, e)]) <
-                                             h_radius + st[st_idx(d, F_R, a, e)] + p.discomfort_dist;
+#pragma unroll
+                for (int k = 0; k < kSlots; ++k)
+                    if (lane + 32 * k < i)
+                        collide = collide || norm2d(px - cpx[k], py - cpy[k]) < h_radius + cr[k] + p.discomfort_dist;
                 if (!__any_sync(0xffffffffu, collide)) break;
             }
             for (int tries = 0; tries < MAX_TRIES; ++tries) {
                 gx = rng.next() * p.square_width * 0.5 * -sign;
                 gy = (rng.next() - 0.5) * p.square_width;
                 bool collide = false;
-                for (int a = lane; a < i; a += 32)
-                    collide = collide || norm2d(gx - st[st_idx(d, F_GX, a, e)], gy - st[st_idx(d, F_GY, a, e)]) <
-                                             h_radius + st[st_idx(d, F_R, a, e)] + p.discomfort_dist;
+#pragma unroll
+                for (int k = 0; k < kSlots; ++k)
+                    if (lane + 32 * k < i)
+                        collide = collide || norm2d(gx - cgx[k], gy - cgy[k]) < h_radius + cr[k] + p.discomfort_dist;
                 if (!__any_sync(0xffffffffu, collide)) break;
             }
         }
@@ -516,7 +527,9 @@ __device__ void reset_env_warp(const EnvParams &p, int e, int lane, double *__re
             st[st_idx(d, F_GX, i, e)] = gx; st[st_idx(d, F_GY, i, e)] = gy;
             st[st_idx(d, F_R, i, e)] = h_radius; st[st_idx(d, F_VPREF, i, e)] = h_v_pref;
         }
-        __syncwarp();                                     // agent i is visible to every lane's checks of agent i + 1
+#pragma unroll
+        for (int k = 0; k < kSlots; ++k)
+            if (lane + 32 * k == i) { cpx[k] = px; cpy[k] = py; cgx[k] = gx; cgy[k] = gy; cr[k] = h_radius; }
     }
     if (lane == 0) {
         time[e] = 0.0;
