@@ -37,8 +37,12 @@ __device__ __forceinline__ StepOutcome cn_step_outcome(const EnvParams &p, Acc a
         const double ex = px + vx * dt;
         const double ey = py + vy * dt;
         const double closest = cn_point_to_segment_dist0(px, py, ex, ey) - ag(F_R, h) - rr;
-        if (closest < 0) { collision = true; break; }
-        else if (closest < dmin) dmin = closest;
+        // crowd_sim.py:353-358 breaks at the first collision; here the loop runs on (no early exit: the loads of the next
+        // humans need not wait for this human's verdict) and simply stops updating -- same collision flag, same dmin
+        if (!collision) {
+            if (closest < 0) collision = true;
+            else if (closest < dmin) dmin = closest;
+        }
     }
     const double endx = rpx + ax * dt, endy = rpy + ay * dt;
     const bool reaching_goal = norm2d(endx - ag(F_GX, 0), endy - ag(F_GY, 0)) < rr;
