@@ -295,6 +295,17 @@ __device__ void reset_env(const EnvParams &p, int e, double *__restrict__ st, do
     st[st_idx(d, F_VX, 0, e)] = 0.0; st[st_idx(d, F_VY, 0, e)] = 0.0;
     st[st_idx(d, F_GX, 0, e)] = 0.0; st[st_idx(d, F_GY, 0, e)] = p.circle_radius;
     st[st_idx(d, F_R, 0, e)] = p.robot_radius; st[st_idx(d, F_VPREF, 0, e)] = p.robot_v_pref;
+    // the agents placed so far, in thread-local arrays (L1) instead of being read back from global memory on every check of the
+    // rejection sampling (this path serves crowds below kWarpResetHumans; larger ones use reset_env_warp)
+    constexpr int kLocal = 16;
+    double cpx[kLocal], cpy[kLocal], cgx[kLocal], cgy[kLocal], cr[kLocal];
+    cpx[0] = 0.0; cpy[0] = -p.circle_radius; cgx[0] = 0.0; cgy[0] = p.circle_radius; cr[0] = p.robot_radius;
+    const bool cached = d.H < kLocal;
+    auto PX = [&](int a) { return cached ? cpx[a] : st[st_idx(d, F_PX, a, e)]; };
+    auto PY = [&](int a) { return cached ? cpy[a] : st[st_idx(d, F_PY, a, e)]; };
+    auto GX = [&](int a) { return cached ? cgx[a] : st[st_idx(d, F_GX, a, e)]; };
+    auto GY = [&](int a) { return cached ? cgy[a] : st[st_idx(d, F_GY, a, e)]; };
+    auto RR = [&](int a) { return cached ? cr[a] : st[st_idx(d, F_R, a, e)]; };
     const int MAX_TRIES = 4096;
     for (int i = 1; i <= d.H; ++i) {
         double px = 0, py = 0, gx = 0, gy = 0;
@@ -312,9 +323,8 @@ __device__ void reset_env(const EnvParams &p, int e, double *__restrict__ st, do
                 py = p.circle_radius * sin(angle) + py_noise;
                 bool collide = false;
                 for (int a = 0; a < i; ++a) {
-                    const double min_dist = h_radius + st[st_idx(d, F_R, a, e)] + p.discomfort_dist;
-                    if (norm2d(px - st[st_idx(d, F_PX, a, e)], py - st[st_idx(d, F_PY, a, e)]) < min_dist ||
-                        norm2d(px - st[st_idx(d, F_GX, a, e)], py - st[st_idx(d, F_GY, a, e)]) < min_dist) {
+                    const double min_dist = h_radius + RR(a) + p.discomfort_dist;
+                    if (norm2d(px - PX(a), py - PY(a)) < min_dist || norm2d(px - GX(a), py - GY(a)) < min_dist) {
                         collide = true;
                         break;
                     }
@@ -329,8 +339,7 @@ __device__ void reset_env(const EnvParams &p, int e, double *__restrict__ st, do
                 py = (rng.next() - 0.5) * p.square_width;
                 bool collide = false;
                 for (int a = 0; a < i; ++a) {
-                    if (norm2d(px - st[st_idx(d, F_PX, a, e)], py - st[st_idx(d, F_PY, a, e)]) <
-                        h_radius + st[st_idx(d, F_R, a, e)] + p.discomfort_dist) { collide = true; break; }
+                    if (norm2d(px - PX(a), py - PY(a)) < h_radius + RR(a) + p.discomfort_dist) { collide = true; break; }
                 }
                 if (!collide) break;
             }
@@ -339,8 +348,7 @@ __device__ void reset_env(const EnvParams &p, int e, double *__restrict__ st, do
                 gy = (rng.next() - 0.5) * p.square_width;
                 bool collide = false;
                 for (int a = 0; a < i; ++a) {
-                    if (norm2d(gx - st[st_idx(d, F_GX, a, e)], gy - st[st_idx(d, F_GY, a, e)]) <
-                        h_radius + st[st_idx(d, F_R, a, e)] + p.discomfort_dist) { collide = true; break; }
+                    if (norm2d(gx - GX(a), gy - GY(a)) < h_radius + RR(a) + p.discomfort_dist) { collide = true; break; }
                 }
                 if (!collide) break;
             }
@@ -349,6 +357,7 @@ __device__ void reset_env(const EnvParams &p, int e, double *__restrict__ st, do
         st[st_idx(d, F_VX, i, e)] = 0.0; st[st_idx(d, F_VY, i, e)] = 0.0;
         st[st_idx(d, F_GX, i, e)] = gx; st[st_idx(d, F_GY, i, e)] = gy;
         st[st_idx(d, F_R, i, e)] = h_radius; st[st_idx(d, F_VPREF, i, e)] = h_v_pref;
+        if (cached) { cpx[i] = px; cpy[i] = py; cgx[i] = gx; cgy[i] = gy; cr[i] = h_radius; }
     }
     time[e] = 0.0;
     theta[e] = 1.5707963267948966;                       // crowd_sim.py:284: robot.set(..., np.pi / 2)
