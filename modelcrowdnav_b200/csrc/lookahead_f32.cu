@@ -388,6 +388,8 @@ argmax_kernel(EnvParams p, int A, const double *__restrict__ st, const uint8_t *
 {
     const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const EnvDims d = p.d;
+    // programmatic dependent launch (cn_lookahead_argmax): the grid may be resident before the value kernel has finished
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (e >= d.E || frozen[e]) return;       // warp-uniform
     double max_value = -INFINITY;
     int best = -1;
@@ -531,12 +533,18 @@ static int ensure_values(cn_policy *p, int E)
     return CN_OK;
 }
 
-int cn_lookahead_argmax(cn_policy *p, cn_env *env, double epsilon, cudaStream_t s)
+int cn_lookahead_argmax(cn_policy *p, cn_env *env, double epsilon, cudaStream_t s, bool pdl)
 {
     const int E = env->p.d.E;
-    argmax_kernel<<<(E + 3) / 4, 128, 0, s>>>(env->p, p->d.A, env->state, env->frozen, p->values, p->action_dev,
-                                                    epsilon, env->step_ctr, env->action_xy, env->action_idx,
-                                                    p->bad_flag);
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((E + 3) / 4); lc.blockDim = dim3(128); lc.dynamicSmemBytes = 0; lc.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = pdl ? 1 : 0;           // pipelined shards (several handles sharing the SMs): plain launches
+    CN_CUDA_CHECK(cudaLaunchKernelEx(&lc, argmax_kernel, env->p, (int)p->d.A, (const double *)env->state, (const uint8_t *)env->frozen,
+                                     (const double *)p->values, (const double *)p->action_dev, epsilon, env->step_ctr, env->action_xy,
+                                     env->action_idx, p->bad_flag));
     CN_LAUNCH_CHECK();
     return CN_OK;
 }
@@ -574,7 +582,7 @@ int cn_lookahead_f32(cn_policy *p, cn_env *env, int query_env, double epsilon, c
                                                          env->frozen, p->action_dev, query_env, p->cfg.gamma, gamma_bar,
                                                          p->cfg.v_pref, p->values, env->theta);
     CN_LAUNCH_CHECK();
-    return cn_lookahead_argmax(p, env, epsilon, s);
+    return cn_lookahead_argmax(p, env, epsilon, s, true);
 }
 
 int cn_transform_f32(cn_policy *p, cn_env *env, float *out_dev, int sort_humans, cudaStream_t s)

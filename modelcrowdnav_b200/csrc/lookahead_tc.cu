@@ -29,7 +29,7 @@
 #include <vector>
 
 int cn_lookahead_prepare(cn_policy *p, cn_env *env, cudaStream_t s);
-int cn_lookahead_argmax(cn_policy *p, cn_env *env, double epsilon, cudaStream_t s);
+int cn_lookahead_argmax(cn_policy *p, cn_env *env, double epsilon, cudaStream_t s, bool pdl);
 
 namespace {
 
@@ -521,6 +521,10 @@ int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cu
     if (ed.H > CN_MAX_HUMANS) { cn_set_error("human_num too large"); return CN_EUNSUPPORTED; }
     int rc = cn_lookahead_prepare(p, env, s);
     if (rc) return rc;
+    // programmatic dependent launches only when this handle has the GPU to itself: with several env shards in flight
+    // (PipelinedHostRollout: tail stream set) a row kernel that becomes resident early and waits keeps another shard's kernels
+    // off the SMs (measured: end to end 1.18e7 -> 1.14e7 env-steps/s)
+    const bool pipelined = tail && tail != s;
     const int A = p->d.A;
     const size_t NG = (size_t)ed.E * A;
     if (NG > t->cap_groups) {
@@ -603,7 +607,7 @@ int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cu
             CN_LAUNCH_CHECK();
             cn_trace_mark("argmax", s);
             if (t->ktime_on) CN_CUDA_CHECK(cudaEventRecord(t->kev[3], s));
-            rc = cn_lookahead_argmax(p, env, epsilon, s);
+            rc = cn_lookahead_argmax(p, env, epsilon, s, !pipelined);
             if (t->ktime_on) CN_CUDA_CHECK(cudaEventRecord(t->kev[4], s));
             return rc;
         }
@@ -627,7 +631,7 @@ int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cu
             CN_LAUNCH_CHECK();
             cn_trace_mark("argmax", s);
             if (t->ktime_on) CN_CUDA_CHECK(cudaEventRecord(t->kev[3], s));
-            rc = cn_lookahead_argmax(p, env, epsilon, s);
+            rc = cn_lookahead_argmax(p, env, epsilon, s, !pipelined);
             if (t->ktime_on) CN_CUDA_CHECK(cudaEventRecord(t->kev[4], s));
             return rc;
         }
@@ -644,7 +648,19 @@ int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cu
                                                                                           env->human_v, query_env, t->omP);
             CN_LAUNCH_CHECK();
         }
-        kern<<<2 * nclusters, kThreadsPair, Q_SMEM, s>>>(env->p, t->img_pair, t->X, t->J, (int)NG, G, rounds, tw, t->dbg, t->omP, A);
+        if (om || pipelined) {          // om: the bias kernel sits between the feature kernel and this one -> plain launch
+            kern<<<2 * nclusters, kThreadsPair, Q_SMEM, s>>>(env->p, t->img_pair, t->X, t->J, (int)NG, G, rounds, tw, t->dbg, t->omP, A);
+        } else {
+            // programmatic dependent launch: the CTAs' prologue runs under the feature kernel's tail (pdl_wait() in the kernel)
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3(2 * nclusters); lc.blockDim = dim3(kThreadsPair); lc.dynamicSmemBytes = Q_SMEM; lc.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            lc.attrs = at; lc.numAttrs = 1;
+            CN_CUDA_CHECK(cudaLaunchKernelEx(&lc, kern, env->p, (const uint8_t *)t->img_pair, (const uint8_t *)t->X, t->J, (int)NG, G,
+                                             rounds, tw, t->dbg, (const float *)t->omP, A));
+        }
         CN_LAUNCH_CHECK();
     }
     if (tail && tail != s) {
@@ -663,14 +679,26 @@ int cn_lookahead_tc(cn_policy *p, cn_env *env, int query_env, double epsilon, cu
         memcpy(tw.w, t->tail_b, sizeof(tw.w));
         cn_trace_mark("mlp3", s);
         if (t->ktime_on) CN_CUDA_CHECK(cudaEventRecord(t->kev[2], s));
-        tc_mlp3_pair_kernel<0><<<2 * nclusters, kThreadsM3, M_SMEM, s>>>(env->p, env->state, t->img_pair_b, t->J, t->rew, A, (int)NG,
-                                                                        p->cfg.gamma, gamma_bar, p->cfg.v_pref, p->values, rounds, tw,
-                                                                        nullptr);
+        if (tail && tail != s) {       // (already on another stream than the row kernel: plain launch behind the event)
+            tc_mlp3_pair_kernel<0><<<2 * nclusters, kThreadsM3, M_SMEM, s>>>(env->p, env->state, t->img_pair_b, t->J, t->rew, A, (int)NG,
+                                                                            p->cfg.gamma, gamma_bar, p->cfg.v_pref, p->values, rounds, tw,
+                                                                            nullptr);
+        } else {
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3(2 * nclusters); lc.blockDim = dim3(kThreadsM3); lc.dynamicSmemBytes = M_SMEM; lc.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            lc.attrs = at; lc.numAttrs = 1;
+            CN_CUDA_CHECK(cudaLaunchKernelEx(&lc, tc_mlp3_pair_kernel<0>, env->p, (const double *)env->state, (const uint8_t *)t->img_pair_b,
+                                             (const uint8_t *)t->J, (const double *)t->rew, A, (int)NG, (double)p->cfg.gamma, gamma_bar,
+                                             (double)p->cfg.v_pref, p->values, rounds, tw, (float *)nullptr));
+        }
         CN_LAUNCH_CHECK();
     }
     cn_trace_mark("argmax", s);
     if (t->ktime_on) CN_CUDA_CHECK(cudaEventRecord(t->kev[3], s));
-    rc = cn_lookahead_argmax(p, env, epsilon, s);
+    rc = cn_lookahead_argmax(p, env, epsilon, s, !pipelined);
     if (t->ktime_on) CN_CUDA_CHECK(cudaEventRecord(t->kev[4], s));
     return rc;
 }

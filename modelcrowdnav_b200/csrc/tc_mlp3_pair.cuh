@@ -70,6 +70,8 @@ tc_mlp3_pair_kernel(EnvParams p, const double *__restrict__ st, const uint8_t *_
     fence_after_sync();
     const uint32_t tmem = *tmem_slot;
     const int tile_stride = 4 * nclusters;
+    pdl_wait();                            // (programmatic dependent launch) the prologue above overlapped the producer kernel's tail
+    pdl_launch_dependents();               // the argmax grid may be placed as this grid's CTAs exit
 
     if (warp == 16) {
         // ================= issuer (rank-0 CTA only) =================

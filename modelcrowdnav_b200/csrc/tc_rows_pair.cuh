@@ -214,6 +214,7 @@ tc_features_kernel(EnvParams p, const double *__restrict__ st, const double *__r
                    double *__restrict__ rew)
 {
     __shared__ double D[ROWS];
+    pdl_launch_dependents();               // the row kernel's CTAs may take the SMs this grid frees (they wait before reading X)
     const EnvDims ed = p.d;
     const int H = HT ? HT : ed.H;
     const int G = HT ? ROWS / HT : G_rt;
@@ -324,6 +325,8 @@ tc_rows_pair_kernel(EnvParams p,
     cluster_sync_all();
     fence_after_sync();
     const uint32_t tmem = *tmem_slot;
+    pdl_launch_dependents();               // mlp3's CTAs may be placed as this grid's CTAs exit
+    pdl_wait();                            // everything above overlapped the feature kernel's tail; X / J / rewards are complete from here
 
     if (is_issuer_warp) {
         // ================= issuer warp (rank-0 CTA only) =================

@@ -172,6 +172,13 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
 }
 
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (prologue:
+// weight image into shared memory, TMEM allocation, barrier set-up) while the kernel before it in the stream drains; pdl_wait()
+// returns once that kernel has completed and its writes are visible (a no-op under a plain launch); pdl_launch_dependents() in the
+// earlier kernel lets the next one be scheduled as soon as SM resources free up.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- CTA pair (cta_group::2): one UMMA spans the two SMs of a 2-CTA cluster -----------------------------
 // M = 256: CTA r of the pair owns rows [128 r, 128 r + 128) -- its A tile in its own shared memory, its
 // accumulator in its own TMEM -- and supplies rows [r N/2, (r + 1) N/2) of the K-major B operand (N split in
